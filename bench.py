@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of 256x256 GANsformer synthesis (BASELINE.json configs[1]) + attention roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one generator forward over one batch of synthetic latents (B = 32 per GPU; weak scaling: every rank
+runs its own slice of a globally seeded batch, no data-path collective -- SURVEY 8e).  Rank 0 prints ONE JSON line.
+
+  value        images/s with latents resident in HBM (CUDA events, max over ranks)
+  e2e          images/s through the public ``Generator.run``-shaped call: pinned host latents -> H2D -> forward ->
+               D2H of the images, every step
+  roofline     the stage-T attention kernel (dominant kernel of the hot path): ALGORITHMIC bytes (read X once +
+               write X' once per layer) / CUDA-event time of those launches, vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline the CPU oracle (oracle/generator.py, fp32, all host threads) on a bounded sample, rank 0, N = 1 only
+
+--impl reference times the reference arm: the reference's own implementation cannot be installed (no source in
+/root/reference, TensorFlow 1.14 unavailable -- DESIGN.md), so per the tier contract the arm is the CPU oracle port.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+RES, K_LATENTS, LATENT_SIZE, B_PER_GPU = 256, 16, 512, 32
+METRIC = "images/sec @256^2 synth (GANsformer generator forward, K=16 latents, 12 attention layers, batch 32/GPU)"
+UNIT = "images/s"
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (recipe in B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [t.strip() for t in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_generator(device):
+    import gansformer_b200 as gf
+    torch.manual_seed(0)                                   # weights seed 0, N(0,1), biases 0
+    G = gf.Generator(resolution=RES, components_num=K_LATENTS, latent_size=LATENT_SIZE)
+    return G.to(device).eval()
+
+
+def global_latents(world: int):
+    g = torch.Generator().manual_seed(1)                   # latents seed 1, generated on CPU
+    return torch.randn(B_PER_GPU * world, K_LATENTS + 1, LATENT_SIZE // K_LATENTS, generator=g)
+
+
+def cpu_oracle_run(G_state, steps: int, warmup: int, sample_b: int):
+    """Times the CPU oracle generator (fp32, NCHW, direct op order) on `sample_b` images per step."""
+    from oracle import generator as og
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    z = global_latents(1)[:sample_b]
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        og.generator_forward(G_state, z, resolution=RES, components_num=K_LATENTS, latent_dim=LATENT_SIZE // K_LATENTS,
+                             dtype=torch.float32)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = statistics.median(times)
+    return sample_b / t, t, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return 0
+    torch.manual_seed(0)
+    import gansformer_b200 as gf
+    G = gf.Generator(resolution=RES, components_num=K_LATENTS, latent_size=LATENT_SIZE)
+    sample_b = 2
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    ips, t, cores = cpu_oracle_run(G.state_dict(), steps, warmup, sample_b)
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: 256x256 synthesis, K=16 latents, 12 attention layers", "batch_per_step": sample_b,
+                       "note": "reference source absent from /root/reference and TF1.14 unavailable: CPU oracle port (parity unpinned)"},
+            "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample_b} images/step x {steps} steps of the config-2 generator forward (oracle/generator.py, fp32)"},
+            "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(args):
+    import gansformer_b200 as gf
+    from importlib import import_module
+    dist_mod = import_module("gansformer-reproducibility-challenge_b200.dist")
+    attn_mod = import_module("gansformer-reproducibility-challenge_b200.attention")
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl ours needs a CUDA device: the product has no CPU path")
+    rank, world, local = dist_mod.init_distributed("nccl")
+    if world != args.gpus:
+        raise RuntimeError(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    # surrounding cuDNN convolutions (plumbing, SURVEY row f1 is "next"): TF32 tensor-core math, fp32 storage
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+
+    G = build_generator(device)
+    z_host = dist_mod.shard_batch(global_latents(world), rank, world).contiguous().pin_memory()
+    z_dev = z_host.to(device)
+    B = z_host.shape[0]
+    img_host = torch.empty((B, 3, RES, RES), dtype=torch.float32).pin_memory()
+    timer = attn_mod.StageTimer()
+
+    def step_resident():
+        with torch.no_grad():
+            return G(z_dev)
+
+    def step_e2e():
+        with torch.no_grad():
+            z = z_host.to(device, non_blocking=True)
+            img = G(z)
+            img_host.copy_(img, non_blocking=True)
+        return img
+
+    for _ in range(args.warmup):
+        step_resident()
+        step_e2e()
+    torch.cuda.synchronize()
+
+    # ---- timed region 1: latents resident in HBM -------------------------------------------------------------
+    sampler = ClockSampler(local)
+    attn_mod.STAGE_TIMER = timer
+    timer.reset()
+    launches0 = gf._lib.launch_count()
+    dist_mod.barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step_resident()
+    ev1.record()
+    torch.cuda.synchronize()
+    dist_mod.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = gf._lib.launch_count() - launches0
+    attn_mod.STAGE_TIMER = None
+    t_total = dist_mod.max_over_ranks(ev0.elapsed_time(ev1) * 1e-3, device)
+    attn_s = sum(a.elapsed_time(b) for a, b, _ in timer.records) * 1e-3
+    attn_bytes = sum(nb for _, _, nb in timer.records)
+    n_attn_launches = len(timer.records)
+    path = gf._lib.last_path()
+
+    # ---- timed region 2: end to end through the public call (H2D + forward + D2H every step) -----------------
+    dist_mod.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    torch.cuda.synchronize()
+    dist_mod.barrier()
+    t_e2e = dist_mod.max_over_ranks(e0.elapsed_time(e1) * 1e-3, device)
+
+    if rank != 0:
+        return 0
+    peak, peak_src = measured_peak_gbs()
+    achieved = attn_bytes / attn_s / 1e9 if attn_s > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": world * B * args.steps / t_total, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t_total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "tf32 (fp32 storage; tcgen05 kind::tf32 attention, TF32 cuDNN convs)" if path == "tcgen05_tf32" else "f32 (CUDA-core attention; TF32 cuDNN convs)",
+        "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: 256x256 synthesis, K=16 latents, 12 attention layers, batch 32 per GPU, simplex, "
+                               "integration=mul, norm=layer, random-init weights (seed 0), latents seed 1",
+                   "global_batch": world * B, "parallelism": f"dp{world} (images sharded, no data-path collective)",
+                   "l2_policy": "activations per layer (up to 1.07 GB) exceed the 126 MB L2; no flush needed",
+                   "attention_path": path},
+        "gpu_launches": int(launches),
+        "e2e": {"value": world * B * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(z_host.numel() * 4 * world),
+                "d2h_bytes_per_step": int(img_host.numel() * 4 * world), "ms_per_step": t_e2e / args.steps * 1e3},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": f"stage-T attention ({path})",
+                     "launches_timed": n_attn_launches, "alg_bytes_per_step": attn_bytes // max(args.steps, 1),
+                     "attention_ms_per_step": attn_s / args.steps * 1e3,
+                     "attention_share_of_step": attn_s / (ev0.elapsed_time(ev1) * 1e-3)},
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        ips, t, cores = cpu_oracle_run(G.state_dict(), steps=2, warmup=1, sample_b=2)
+        line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "2 images/step x 2 steps (+1 warm-up) of the same 256x256 K=16 generator forward, "
+                                          "oracle/generator.py fp32 on all host threads; oracle = in-repo restatement, "
+                                          "reference source unavailable, parity unpinned"}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "ours":
+        args.warmup = max(args.warmup, 3)
+    rc = run_reference(args) if args.impl == "reference" else run_ours(args)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+    return rc
+
+
+if __name__ == "__main__":
+    sys.exit(main())

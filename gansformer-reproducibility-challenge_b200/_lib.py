@@ -1,0 +1,107 @@
+"""ctypes binding of the C ABI in include/gf_attn.h (libgf_attn.so).
+
+This is the binding a maintainer of the reference would add inside ``transformer_layer``:
+raw device pointers and sizes only, no torch types cross the boundary.  There is no fallback: if the library
+cannot be loaded, or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_int, c_int32, c_size_t, c_void_p, c_char_p, POINTER, byref
+from typing import Optional
+
+from ._build import LIB_PATH, build_extension
+
+GF_OK = 0
+NORM = {None: 0, "none": 0, "layer": 1, "instance": 2, "batch": 3}
+INTEGRATION = {"mul": 0, "add": 1, "both": 2}
+FLAG_FP32_EXACT = 1
+FLAG_CENTROIDS_IN = 2
+PATH_NAMES = {0: "none", 1: "simt_fp32", 2: "tcgen05_tf32"}
+
+WEIGHT_FIELDS = ("wq", "bq", "wpq", "wk", "bk", "wpk", "wv", "bv", "wo", "bo", "pos_latent",
+                 "wq2", "bq2", "wpq2", "wk2", "bk2", "wpk2", "wv2", "bv2", "wkc")
+
+# every symbol include/gf_attn.h declares (tests check the .so exports each of them)
+EXPORTS = ("gf_attn_abi_version", "gf_last_error", "gf_attn_last_path", "gf_attn_folded_floats",
+           "gf_attn_fold_weights", "gf_attn_workspace_bytes", "gf_attn_prologue", "gf_attn_simplex_fwd",
+           "gf_attn_duplex_fwd", "gf_attn_norm_stats", "gf_attn_launch_count")
+
+
+class GfAttnDesc(ctypes.Structure):
+    _fields_ = [(n, c_int32) for n in ("B", "H", "W", "C", "k", "D", "heads", "norm", "integration",
+                                       "pos_dim", "duplex", "flags")]
+
+
+class GfAttnWeights(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in WEIGHT_FIELDS]
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def load() -> ctypes.CDLL:
+    """Load (building first if missing/stale) libgf_attn.so.  Raises on failure -- never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    try:
+        build_extension()
+    except Exception as e:  # nvcc missing is fine as long as a prebuilt .so is present
+        if not LIB_PATH.exists():
+            raise RuntimeError(f"libgf_attn.so is missing and could not be built: {e}") from e
+    lib = ctypes.CDLL(str(LIB_PATH))
+    lib.gf_attn_abi_version.restype = c_int
+    lib.gf_last_error.restype = c_char_p
+    lib.gf_attn_last_path.restype = c_int
+    lib.gf_attn_folded_floats.argtypes = [POINTER(GfAttnDesc), POINTER(c_size_t)]
+    lib.gf_attn_workspace_bytes.argtypes = [POINTER(GfAttnDesc), POINTER(c_size_t)]
+    lib.gf_attn_fold_weights.argtypes = [POINTER(GfAttnDesc), POINTER(GfAttnWeights), c_void_p, c_void_p]
+    lib.gf_attn_prologue.argtypes = [POINTER(GfAttnDesc), c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.gf_attn_simplex_fwd.argtypes = [POINTER(GfAttnDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.gf_attn_duplex_fwd.argtypes = [POINTER(GfAttnDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p]
+    lib.gf_attn_norm_stats.argtypes = [POINTER(GfAttnDesc), c_void_p, c_void_p, c_void_p]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("gf_last_error", "gf_attn_launch_count"):
+            fn.restype = c_int
+    lib.gf_attn_launch_count.restype = ctypes.c_longlong
+    if lib.gf_attn_abi_version() != 1:
+        raise RuntimeError("libgf_attn.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != GF_OK:
+        msg = load().gf_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (gf_status {rc}): {msg}")
+
+
+def make_desc(B, H, W, C, k, D, *, heads=1, norm="layer", integration="mul", pos_dim=0, duplex=False, flags=0) -> GfAttnDesc:
+    if norm not in NORM:
+        raise ValueError(f"unknown norm {norm!r}")
+    if integration not in INTEGRATION:
+        raise ValueError(f"unknown integration {integration!r}")
+    return GfAttnDesc(B, H, W, C, k, D, heads, NORM[norm], INTEGRATION[integration], pos_dim, int(bool(duplex)), flags)
+
+
+def folded_floats(desc: GfAttnDesc) -> int:
+    out = c_size_t(0)
+    check(load().gf_attn_folded_floats(byref(desc), byref(out)), "gf_attn_folded_floats")
+    return out.value
+
+
+def workspace_bytes(desc: GfAttnDesc) -> int:
+    out = c_size_t(0)
+    check(load().gf_attn_workspace_bytes(byref(desc), byref(out)), "gf_attn_workspace_bytes")
+    return out.value
+
+
+def launch_count() -> int:
+    return int(load().gf_attn_launch_count())
+
+
+def last_path() -> str:
+    return PATH_NAMES.get(load().gf_attn_last_path(), "?")

@@ -1,0 +1,232 @@
+"""Host-side mirror of the reference's attention operator, backed by libgf_attn.so (sm_100a kernels).
+
+Reference interface mirrored (expected ``src/training/network.py`` upstream; the file is NOT in the reference
+checkout -- ``/root/reference/.SUBMODULES.json:2`` reports zero payload bytes -- so names/kwargs follow
+SURVEY.md section 8a/8b):
+
+    transformer_layer(dim, pos_dim, from_tensor, to_tensor, from_len, to_len, from_pos, to_pos, num_heads,
+                      att_dp, integration, norm, kmeans, kmeans_iters, att_vars, iterative, ...)
+        -> (from_tensor', att_probs, att_vars)
+
+Here: ``BipartiteAttention(nn.Module)`` owns one layer's parameters and ``transformer_layer(...)`` is the
+functional form with the reference's argument names.  Activations are channels-last ``[B, H, W, C]`` fp32 so
+the two NCHW<->[B,n,C] transposes of the reference disappear.  PyTorch is used for device memory and streams
+only; all arithmetic of the block happens inside the C-ABI calls.  No CPU path exists: a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib
+
+SIMPLEX_PARAMS = ("wq", "bq", "wpq", "wk", "bk", "wpk", "wv", "bv", "wo", "bo", "pos_latent")
+DUPLEX_PARAMS = ("wq2", "bq2", "wpq2", "wk2", "bk2", "wpk2", "wv2", "bv2", "wkc")
+
+
+def param_shapes(dim: int, latent_dim: int, components_num: int, pos_dim: int, integration: str, duplex: bool):
+    """Raw parameter shapes, [fan_in, fan_out]; equalised-LR scaling happens inside the library."""
+    C, D, k, p = dim, latent_dim, components_num, pos_dim
+    cout = 2 * C if integration == "both" else C
+    shapes = {"wq": (C, C), "bq": (C,), "wpq": (p, C), "wk": (D, C), "bk": (C,), "wpk": (p, C),
+              "wv": (D, C), "bv": (C,), "wo": (C, cout), "bo": (cout,), "pos_latent": (k, p)}
+    if duplex:
+        shapes.update({"wq2": (D, C), "bq2": (C,), "wpq2": (p, C), "wk2": (C, C), "bk2": (C,), "wpk2": (p, C),
+                       "wv2": (C, C), "bv2": (C,), "wkc": (C, C)})
+    return shapes
+
+
+class StageTimer:
+    """Optional CUDA-event timer around the stage-T launch (the dominant kernel); bench.py installs one.
+
+    Events are recorded on the stream the kernel is launched on; `records` holds (start, end, alg_bytes)."""
+
+    def __init__(self):
+        self.records = []
+
+    def reset(self):
+        self.records = []
+
+
+STAGE_TIMER: Optional[StageTimer] = None
+
+
+class _Plan:
+    """Folded weights + workspace for one (shape, config); owns the device buffers the library writes into."""
+
+    def __init__(self):
+        self.folded: Optional[torch.Tensor] = None
+        self.folded_key = None
+        self.ws: Dict[tuple, torch.Tensor] = {}
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _check_tensor(t: torch.Tensor, name: str, device) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: bipartite attention has no CPU path (tensor is on {t.device})")
+    if t.device != device:
+        raise RuntimeError(f"{name} is on {t.device}, expected {device}")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+
+
+def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[str, torch.Tensor], plan: _Plan, *,
+                                integration: str = "mul", norm: Optional[str] = "layer", duplex: bool = False,
+                                num_heads: int = 1, use_pos: bool = True, return_att: bool = False,
+                                centroids: Optional[torch.Tensor] = None, exact_fp32: bool = False,
+                                out: Optional[torch.Tensor] = None, weights_version=None):
+    """x [B,H,W,C] channels-last fp32 (CUDA), y [B,k,D].  Returns (x', att [B,k,H,W] | None, centroids | None)."""
+    lib = _lib.load()
+    if x.dim() != 4:
+        raise ValueError("x must be [B, H, W, C] (channels-last)")
+    dev = x.device
+    _check_tensor(x, "x", dev)
+    _check_tensor(y, "y", dev)
+    B, H, W, C = x.shape
+    if y.dim() != 3 or y.shape[0] != B:
+        raise ValueError(f"y must be [B, k, D] with B={B}, got {tuple(y.shape)}")
+    k, D = y.shape[1], y.shape[2]
+    pos_dim = params["pos_latent"].shape[1] if use_pos else 0
+    flags = (_lib.FLAG_FP32_EXACT if exact_fp32 else 0) | (_lib.FLAG_CENTROIDS_IN if (duplex and centroids is not None) else 0)
+    desc = _lib.make_desc(B, H, W, C, k, D, heads=num_heads, norm=norm, integration=integration, pos_dim=pos_dim,
+                          duplex=duplex, flags=flags)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    with torch.cuda.device(dev):
+        # stage W: fold weights (cached until a parameter changes)
+        names = SIMPLEX_PARAMS + (DUPLEX_PARAMS if duplex else ())
+        if weights_version is None:
+            weights_version = tuple((params[n].data_ptr(), params[n]._version) for n in names)
+        fkey = (H, W, k, D, C, pos_dim, integration, duplex, str(dev), weights_version)
+        if plan.folded is None or plan.folded_key != fkey:
+            nfl = _lib.folded_floats(desc)
+            if plan.folded is None or plan.folded.numel() != nfl or plan.folded.device != dev:
+                plan.folded = torch.empty(nfl, dtype=torch.float32, device=dev)
+            wstruct = _lib.GfAttnWeights()
+            for n in names:
+                t = params[n].detach()
+                _check_tensor(t, n, dev)
+                setattr(wstruct, n, t.data_ptr())
+            _lib.check(lib.gf_attn_fold_weights(ctypes.byref(desc), ctypes.byref(wstruct), plan.folded.data_ptr(), stream),
+                       "gf_attn_fold_weights")
+            plan.folded_key = fkey
+        # workspace
+        wkey = (B, H, W, C, k, D, pos_dim, integration, norm, duplex, str(dev))
+        ws = plan.ws.get(wkey)
+        if ws is None:
+            ws = torch.empty(_lib.workspace_bytes(desc), dtype=torch.uint8, device=dev)
+            plan.ws[wkey] = ws
+        if out is None:
+            out = torch.empty_like(x)
+        else:
+            _check_tensor(out, "out", dev)
+        att = torch.empty((B, H * W, k), dtype=torch.float32, device=dev) if return_att else None
+        timer = STAGE_TIMER
+        if timer is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if duplex:
+            if timer is not None:
+                ev0.record()
+            if centroids is None:
+                cen = torch.empty((B, k, C), dtype=torch.float32, device=dev)
+            else:
+                _check_tensor(centroids, "centroids", dev)
+                cen = centroids
+            _lib.check(lib.gf_attn_duplex_fwd(ctypes.byref(desc), x.data_ptr(), y.data_ptr(), plan.folded.data_ptr(),
+                                              out.data_ptr(), _ptr(att), cen.data_ptr(), ws.data_ptr(), stream),
+                       "gf_attn_duplex_fwd")
+        else:
+            cen = None
+            _lib.check(lib.gf_attn_prologue(ctypes.byref(desc), y.data_ptr(), plan.folded.data_ptr(), ws.data_ptr(), stream),
+                       "gf_attn_prologue")
+            if timer is not None:
+                ev0.record()
+            _lib.check(lib.gf_attn_simplex_fwd(ctypes.byref(desc), x.data_ptr(), out.data_ptr(), _ptr(att), ws.data_ptr(), stream),
+                       "gf_attn_simplex_fwd")
+        if timer is not None:
+            ev1.record()
+            timer.records.append((ev0, ev1, 2 * 4 * B * H * W * C))
+    att_map = att.view(B, H, W, k).permute(0, 3, 1, 2) if att is not None else None   # [B,k,H,W] view
+    return out, att_map, cen
+
+
+class BipartiteAttention(nn.Module):
+    """One bipartite attention layer (simplex, or duplex when ``kmeans=True``) + region-wise modulation.
+
+    kwargs follow the reference's names: ``dim`` (C), ``pos_dim``, ``num_heads``, ``integration`` ('mul' |
+    'add' | 'both'), ``norm`` ('layer' | 'instance' | 'batch' | None), ``kmeans`` (duplex), ``kmeans_iters`` (1).
+    """
+
+    def __init__(self, dim: int, latent_dim: int, components_num: int, pos_dim: Optional[int] = None,
+                 num_heads: int = 1, integration: str = "mul", norm: Optional[str] = "layer", kmeans: bool = False,
+                 kmeans_iters: int = 1, use_pos: bool = True, att_dp: float = 0.0, exact_fp32: bool = False):
+        super().__init__()
+        if kmeans_iters != 1:
+            raise NotImplementedError("kmeans_iters != 1 is not implemented (SURVEY A.4 item 3 freezes 1)")
+        if att_dp != 0.0:
+            raise NotImplementedError("attention dropout is not implemented in the fused kernel (inference path: 0)")
+        self.dim, self.latent_dim, self.components_num = dim, latent_dim, components_num
+        self.pos_dim = latent_dim if pos_dim is None else pos_dim
+        self.num_heads, self.integration, self.norm = num_heads, integration, norm
+        self.duplex, self.use_pos, self.exact_fp32 = bool(kmeans), use_pos, exact_fp32
+        for name, shape in param_shapes(dim, latent_dim, components_num, self.pos_dim, integration, self.duplex).items():
+            init = torch.zeros(shape) if name.startswith("b") else torch.randn(shape)
+            self.register_parameter(name, nn.Parameter(init))
+        self._plan = _Plan()
+
+    def param_dict(self) -> Dict[str, torch.Tensor]:
+        return {n: p for n, p in self.named_parameters(recurse=False)}
+
+    def forward(self, x: torch.Tensor, y: torch.Tensor, centroids: Optional[torch.Tensor] = None,
+                return_att: bool = False, out: Optional[torch.Tensor] = None):
+        """x [B,H,W,C] channels-last, y [B,k,D] -> (x', att [B,k,H,W] | None, centroids [B,k,C] | None)."""
+        if torch.is_grad_enabled() and (x.requires_grad or y.requires_grad or any(p.requires_grad for p in self.parameters())):
+            from .autograd import bipartite_attention_autograd
+            return bipartite_attention_autograd(self, x, y, centroids, return_att)
+        return bipartite_attention_forward(x, y, self.param_dict(), self._plan, integration=self.integration,
+                                           norm=self.norm, duplex=self.duplex, num_heads=self.num_heads,
+                                           use_pos=self.use_pos, return_att=return_att, centroids=centroids,
+                                           exact_fp32=self.exact_fp32, out=out)
+
+
+_FUNCTIONAL_PLANS: Dict[int, _Plan] = {}
+
+
+def transformer_layer(dim: int, pos_dim: int, from_tensor: torch.Tensor, to_tensor: torch.Tensor, from_len: int,
+                      to_len: int, params: Dict[str, torch.Tensor], *, grid_shape: Tuple[int, int],
+                      num_heads: int = 1, att_dp: float = 0.0, integration: str = "mul", norm: Optional[str] = "layer",
+                      kmeans: bool = False, kmeans_iters: int = 1, att_vars: Optional[dict] = None,
+                      iterative: bool = False, use_pos: bool = True, exact_fp32: bool = False):
+    """Functional form with the reference's argument names (see module docstring).
+
+    from_tensor [B, from_len, dim] (grid tokens, row-major over grid_shape=(H, W)); to_tensor [B, to_len, D].
+    Returns (from_tensor' [B, from_len, dim], att_probs [B, from_len, to_len], att_vars).
+    """
+    if att_dp != 0.0 or kmeans_iters != 1:
+        raise NotImplementedError("att_dp != 0 / kmeans_iters != 1 are not implemented")
+    H, W = grid_shape
+    B = from_tensor.shape[0]
+    if from_len != H * W or from_tensor.shape[1] != from_len or from_tensor.shape[2] != dim or to_tensor.shape[1] != to_len:
+        raise ValueError("from_len/to_len/dim do not match the tensors")
+    if use_pos and params["pos_latent"].shape[1] != pos_dim:
+        raise ValueError("pos_dim does not match params['pos_latent']")
+    plan = _FUNCTIONAL_PLANS.setdefault(id(params), _Plan())
+    att_vars = dict(att_vars or {})
+    cen_in = att_vars.get("centroids") if (kmeans and iterative) else None
+    x = from_tensor.reshape(B, H, W, dim)
+    out, att, cen = bipartite_attention_forward(x, to_tensor, params, plan, integration=integration, norm=norm,
+                                                duplex=kmeans, num_heads=num_heads, use_pos=use_pos, return_att=True,
+                                                centroids=cen_in, exact_fp32=exact_fp32)
+    if cen is not None:
+        att_vars["centroids"] = cen
+    att_probs = att.permute(0, 2, 3, 1).reshape(B, from_len, to_len)
+    return out.reshape(B, from_len, dim), att_probs, att_vars

@@ -1,0 +1,134 @@
+// gf_api.cu -- the extern "C" surface declared in include/gf_attn.h.
+#include <stdarg.h>
+#include <string.h>
+#include <atomic>
+#include "gf_common.cuh"
+
+namespace gf {
+
+static thread_local char g_err[1024] = "";
+static thread_local int g_path = GF_PATH_NONE;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void set_path(int path) { g_path = path; }
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// The library is sm_100a-only: refuse anything else loudly instead of failing at launch.
+static int check_device() {
+  static thread_local int checked_dev = -1;
+  int dev = -1;
+  GF_CUDA_OK(cudaGetDevice(&dev));
+  if (dev == checked_dev) return GF_OK;
+  int major = 0, minor = 0;
+  GF_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  GF_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (major != 10) {
+    set_error("libgf_attn is built for sm_100a (B200) only; device %d has compute capability %d.%d", dev, major, minor);
+    return GF_ERR_UNSUPPORTED;
+  }
+  checked_dev = dev;
+  return GF_OK;
+}
+
+static int token_pass(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, cudaStream_t st) {
+  int rc;
+  if ((rc = norm_stats(L, d, X, ws, st))) return rc;
+  if (!(d->flags & GF_FLAG_FP32_EXACT) && tc_supported(L, d)) return token_pass_tc(L, d, X, Xout, att, ws, st);
+  return token_pass_simt(L, d, X, Xout, att, ws, st);
+}
+
+}  // namespace gf
+
+using namespace gf;
+
+extern "C" {
+
+int gf_attn_abi_version(void) { return GF_ATTN_ABI_VERSION; }
+const char* gf_last_error(void) { return g_err; }
+int gf_attn_last_path(void) { return g_path; }
+long long gf_attn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int gf_attn_folded_floats(const gf_attn_desc* desc, size_t* out_floats) {
+  Layout L;
+  int rc = make_layout(desc, &L);
+  if (rc) return rc;
+  if (!out_floats) { set_error("null out_floats"); return GF_ERR_INVALID; }
+  *out_floats = L.f_total;
+  return GF_OK;
+}
+
+int gf_attn_workspace_bytes(const gf_attn_desc* desc, size_t* out_bytes) {
+  Layout L;
+  int rc = make_layout(desc, &L);
+  if (rc) return rc;
+  if (!out_bytes) { set_error("null out_bytes"); return GF_ERR_INVALID; }
+  *out_bytes = L.w_total * sizeof(float);
+  return GF_OK;
+}
+
+int gf_attn_fold_weights(const gf_attn_desc* desc, const gf_attn_weights* weights, float* folded, void* stream) {
+  Layout L;
+  int rc = make_layout(desc, &L);
+  if (rc) return rc;
+  if (!weights || !folded) { set_error("gf_attn_fold_weights: null pointer"); return GF_ERR_INVALID; }
+  if ((rc = check_device())) return rc;
+  return fold_weights(L, desc, weights, folded, (cudaStream_t)stream);
+}
+
+int gf_attn_prologue(const gf_attn_desc* desc, const float* Y, const float* folded, void* ws, void* stream) {
+  Layout L;
+  int rc = make_layout(desc, &L);
+  if (rc) return rc;
+  if (!Y || !folded || !ws) { set_error("gf_attn_prologue: null pointer"); return GF_ERR_INVALID; }
+  if (L.duplex) { set_error("gf_attn_prologue: duplex layers build their keys inside gf_attn_duplex_fwd"); return GF_ERR_INVALID; }
+  if ((rc = check_device())) return rc;
+  return prologue(L, desc, Y, Y, L.D, folded, (float*)ws, (cudaStream_t)stream);
+}
+
+int gf_attn_norm_stats(const gf_attn_desc* desc, const float* X, void* ws, void* stream) {
+  Layout L;
+  int rc = make_layout(desc, &L);
+  if (rc) return rc;
+  if (!X || !ws) { set_error("gf_attn_norm_stats: null pointer"); return GF_ERR_INVALID; }
+  if ((rc = check_device())) return rc;
+  return norm_stats(L, desc, X, (float*)ws, (cudaStream_t)stream);
+}
+
+int gf_attn_simplex_fwd(const gf_attn_desc* desc, const float* X, float* Xout, float* att, void* ws, void* stream) {
+  Layout L;
+  int rc = make_layout(desc, &L);
+  if (rc) return rc;
+  if (!X || !Xout || !ws) { set_error("gf_attn_simplex_fwd: null pointer"); return GF_ERR_INVALID; }
+  if ((rc = check_device())) return rc;
+  return token_pass(L, desc, X, Xout, att, (float*)ws, (cudaStream_t)stream);
+}
+
+int gf_attn_duplex_fwd(const gf_attn_desc* desc, const float* X, const float* Y, const float* folded,
+                       float* Xout, float* att, float* centroids_inout, void* ws_, void* stream) {
+  Layout L;
+  int rc = make_layout(desc, &L);
+  if (rc) return rc;
+  if (!L.duplex) { set_error("gf_attn_duplex_fwd: desc.duplex is 0"); return GF_ERR_INVALID; }
+  if (!X || !Y || !folded || !Xout || !centroids_inout || !ws_) { set_error("gf_attn_duplex_fwd: null pointer"); return GF_ERR_INVALID; }
+  if ((rc = check_device())) return rc;
+  float* ws = (float*)ws_;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!(desc->flags & GF_FLAG_CENTROIDS_IN)) {
+    if ((rc = duplex_tables(L, desc, Y, folded, ws, st))) return rc;
+    if ((rc = centroid_pass_simt(L, desc, X, ws, st))) return rc;
+    // centroids = Xbar @ Wv2_e + bv2
+    if ((rc = gemm(st, L.B * L.k, L.C, L.C, ws + L.w_XBAR, L.C, false, folded + L.f_WV2, L.C, false, centroids_inout, L.C, 1.f,
+                   nullptr, 0, 1, folded + L.f_BV2)))
+      return rc;
+  }
+  if ((rc = prologue(L, desc, Y, centroids_inout, L.C, folded, ws, st))) return rc;
+  return token_pass(L, desc, X, Xout, att, ws, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// gf_common.cuh -- shared host/device definitions for libgf_attn (sm_100a only).
+//
+// Buffer layouts are the ones restated in oracle/folded.py (stage W / I / T); keep the two in sync.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+#include "../../include/gf_attn.h"
+
+namespace gf {
+
+// ---- thread-local error reporting -----------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void set_path(int path);
+void note_launch();
+
+#define GF_CUDA_OK(expr)                                                                         \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      gf::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));       \
+      return GF_ERR_CUDA;                                                                        \
+    }                                                                                            \
+  } while (0)
+
+#define GF_LAUNCH_OK()                                                                           \
+  do {                                                                                           \
+    cudaError_t _e = cudaGetLastError();                                                         \
+    if (_e != cudaSuccess) {                                                                     \
+      gf::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e));   \
+      return GF_ERR_CUDA;                                                                        \
+    }                                                                                            \
+    gf::note_launch();                                                                           \
+  } while (0)
+
+// ---- layout of the folded-weight buffer and of the per-call workspace -----------------------------
+// All offsets in floats, each region 64-float (256 B) aligned.
+struct Layout {
+  int B, H, W, C, k, D, p, KP, Cout, LDK, n, duplex;
+  // folded buffer (stage W)
+  size_t f_AK, f_CK, f_AV, f_CV, f_ROW, f_COL;        // simplex + duplex
+  size_t f_WV2, f_BV2, f_AM, f_CM;                    // duplex only
+  size_t f_QFOLD, f_KCONST, f_MFOLD, f_QCONST;        // scratch of stage W
+  size_t f_total;
+  // workspace (stage I/T)
+  size_t w_KPALL, w_Kp, w_Vt, w_Rt, w_Ct;             // keys / values / positional logit tables
+  size_t w_NSCALE, w_NSHIFT, w_NPART;                 // instance/batch norm statistics
+  size_t w_MALL, w_M, w_Rt2, w_Ct2, w_PART, w_XBAR;   // duplex pass A
+  size_t w_total;
+  int nsplit_norm, nsplit_cen;
+};
+
+inline size_t align64(size_t x) { return (x + 63) & ~size_t(63); }
+inline int pad_k(int k) { return k <= 16 ? 16 : 32; }
+
+// Fills L; returns GF_OK or an error (message set).
+int make_layout(const gf_attn_desc* d, Layout* L);
+
+// ---- stage W / I kernels (gf_fold.cu) ---------------------------------------------------------------
+int fold_weights(const Layout& L, const gf_attn_desc* d, const gf_attn_weights* w, float* folded, cudaStream_t st);
+// key_source: Y [B*k, D] (simplex) or centroids [B*k, C] (duplex); kdim = D or C.
+int prologue(const Layout& L, const gf_attn_desc* d, const float* Y, const float* key_source, int kdim,
+             const float* folded, float* ws, cudaStream_t st);
+int duplex_tables(const Layout& L, const gf_attn_desc* d, const float* Y, const float* folded, float* ws, cudaStream_t st);
+// C[M,N] = alpha * opA(A) opB(B) + E[(m % emod), n] + v[n]
+int gemm(cudaStream_t st, int M, int N, int K, const float* A, int lda, bool ta, const float* B, int ldb, bool tb,
+         float* Cm, int ldc, float alpha, const float* E = nullptr, int lde = 0, int emod = 1, const float* v = nullptr);
+
+// ---- stage T kernels ----------------------------------------------------------------------------------
+int token_pass_simt(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, cudaStream_t st);
+int norm_stats(const Layout& L, const gf_attn_desc* d, const float* X, float* ws, cudaStream_t st);
+int centroid_pass_simt(const Layout& L, const gf_attn_desc* d, const float* X, float* ws, cudaStream_t st);
+// tcgen05 / TMA path (gf_tc.cu).  tc_supported() says whether the shape is served by it.
+bool tc_supported(const Layout& L, const gf_attn_desc* d);
+int token_pass_tc(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, cudaStream_t st);
+
+}  // namespace gf

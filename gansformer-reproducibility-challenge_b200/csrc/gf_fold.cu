@@ -1,0 +1,325 @@
+// gf_fold.cu -- stage W (weight folding) and stage I (per-image prologue) of the bipartite attention block.
+//
+// Replaces, on the reference side (expected src/training/network.py, not in the checkout): dense_layer /
+// get_weight (equalised-LR scaling), the K and V dense layers of transformer_layer, and
+// get_positional_embeddings.  Buffer layouts mirror oracle/folded.py: fold_weights(), prologue().
+#include "gf_common.cuh"
+
+namespace gf {
+
+// ------------------------------------------------------------------------------------------------------
+// layout
+// ------------------------------------------------------------------------------------------------------
+int make_layout(const gf_attn_desc* d, Layout* L) {
+  if (!d) { set_error("null descriptor"); return GF_ERR_INVALID; }
+  if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->C <= 0 || d->k <= 0 || d->D <= 0) {
+    set_error("non-positive dimension in descriptor (B=%d H=%d W=%d C=%d k=%d D=%d)", d->B, d->H, d->W, d->C, d->k, d->D);
+    return GF_ERR_INVALID;
+  }
+  if (d->C % 32 != 0 || d->C > 1024) { set_error("C=%d unsupported: need C %% 32 == 0 and C <= 1024", d->C); return GF_ERR_UNSUPPORTED; }
+  if (d->k > 32) { set_error("k=%d unsupported: at most 32 latents", d->k); return GF_ERR_UNSUPPORTED; }
+  if (d->heads != 1) { set_error("num_heads=%d unsupported: this build implements 1 head", d->heads); return GF_ERR_UNSUPPORTED; }
+  if (d->norm < GF_NORM_NONE || d->norm > GF_NORM_BATCH) { set_error("bad norm %d", d->norm); return GF_ERR_INVALID; }
+  if (d->integration < GF_INT_MUL || d->integration > GF_INT_BOTH) { set_error("bad integration %d", d->integration); return GF_ERR_INVALID; }
+  if (d->pos_dim < 0 || d->pos_dim % 4 != 0 || d->pos_dim > 256) { set_error("pos_dim=%d unsupported: need multiple of 4, <= 256", d->pos_dim); return GF_ERR_UNSUPPORTED; }
+  if ((long long)d->B * d->H * d->W > (1ll << 31) - 1) { set_error("B*H*W overflows int32"); return GF_ERR_UNSUPPORTED; }
+
+  Layout& l = *L;
+  l.B = d->B; l.H = d->H; l.W = d->W; l.C = d->C; l.k = d->k; l.D = d->D; l.p = d->pos_dim;
+  l.KP = pad_k(d->k);
+  l.Cout = d->integration == GF_INT_BOTH ? 2 * d->C : d->C;
+  l.LDK = d->C + d->pos_dim + 4;
+  l.n = d->H * d->W;
+  l.duplex = d->duplex ? 1 : 0;
+  const size_t C = l.C, k = l.k, D = l.D, p = l.p, LDK = l.LDK;
+  const size_t Din = l.duplex ? C : D;
+
+  size_t o = 0;
+  auto take = [&](size_t nfloats) { size_t r = o; o += align64(nfloats); return r; };
+  l.f_AK = take(Din * LDK);
+  l.f_CK = take(k * LDK);
+  l.f_AV = take(D * l.Cout);
+  l.f_CV = take(l.Cout);
+  l.f_ROW = take((size_t)l.H * (p / 2) + 1);
+  l.f_COL = take((size_t)l.W * (p / 2) + 1);
+  l.f_QFOLD = take(C * LDK);
+  l.f_KCONST = take(k * C);
+  if (l.duplex) {
+    l.f_WV2 = take(C * C);
+    l.f_BV2 = take(C);
+    l.f_AM = take(D * LDK);
+    l.f_CM = take(k * LDK);
+    l.f_MFOLD = take(C * LDK);
+    l.f_QCONST = take(k * C);
+  } else {
+    l.f_WV2 = l.f_BV2 = l.f_AM = l.f_CM = l.f_MFOLD = l.f_QCONST = 0;
+  }
+  l.f_total = o;
+
+  // statistics / centroid splits: about two waves of CTAs over 148 SMs
+  int want = (2 * 148 + l.B - 1) / l.B;
+  l.nsplit_norm = want; if (l.nsplit_norm > (l.n + 63) / 64) l.nsplit_norm = (l.n + 63) / 64; if (l.nsplit_norm < 1) l.nsplit_norm = 1;
+  l.nsplit_cen = want;  if (l.nsplit_cen > (l.n + 127) / 128) l.nsplit_cen = (l.n + 127) / 128; if (l.nsplit_cen < 1) l.nsplit_cen = 1;
+
+  o = 0;
+  const size_t B = l.B, KP = l.KP;
+  l.w_KPALL = take(B * k * LDK);
+  l.w_Kp = take(B * KP * C);
+  l.w_Vt = take(B * l.Cout * KP);
+  l.w_Rt = take(B * l.H * KP);
+  l.w_Ct = take(B * l.W * KP);
+  if (d->norm == GF_NORM_INSTANCE || d->norm == GF_NORM_BATCH) {
+    l.w_NSCALE = take(B * C);
+    l.w_NSHIFT = take(B * C);
+    l.w_NPART = take(B * (size_t)l.nsplit_norm * 2 * C * 2);  // doubles
+  } else {
+    l.w_NSCALE = l.w_NSHIFT = l.w_NPART = 0;
+  }
+  if (l.duplex) {
+    l.w_MALL = take(B * k * LDK);
+    l.w_M = take(B * KP * C);
+    l.w_Rt2 = take(B * l.H * KP);
+    l.w_Ct2 = take(B * l.W * KP);
+    l.w_PART = take(B * (size_t)l.nsplit_cen * KP * (C + 4));
+    l.w_XBAR = take(B * k * C);
+  } else {
+    l.w_MALL = l.w_M = l.w_Rt2 = l.w_Ct2 = l.w_PART = l.w_XBAR = 0;
+  }
+  l.w_total = o;
+  return GF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// small SGEMM used by the folding stages (weights-only / per-image [B*k] rows: tiny problems)
+// ------------------------------------------------------------------------------------------------------
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                   const float* __restrict__ Bm, int ldb, float* __restrict__ Cm, int ldc,
+                                                   float alpha, const float* __restrict__ E, int lde, int emod,
+                                                   const float* __restrict__ v) {
+  __shared__ float As[32][33];
+  __shared__ float Bs[32][33];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    for (int i = threadIdx.x; i < 1024; i += 256) {
+      const int r = i >> 5, c = i & 31;
+      const int m = m0 + r, kk = k0 + c;
+      As[r][c] = (m < M && kk < K) ? (TA ? A[(size_t)kk * lda + m] : A[(size_t)m * lda + kk]) : 0.f;
+      const int kb = k0 + r, nn = n0 + c;
+      Bs[r][c] = (kb < K && nn < N) ? (TB ? Bm[(size_t)nn * ldb + kb] : Bm[(size_t)kb * ldb + nn]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < 32; ++kk) {
+      const float a0 = As[ty * 2][kk], a1 = As[ty * 2 + 1][kk];
+      const float b0 = Bs[kk][tx * 2], b1 = Bs[kk][tx * 2 + 1];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int m = m0 + ty * 2 + i, nn = n0 + tx * 2 + j;
+      if (m < M && nn < N) {
+        float r = alpha * acc[i][j];
+        if (E) r += E[(size_t)(m % emod) * lde + nn];
+        if (v) r += v[nn];
+        Cm[(size_t)m * ldc + nn] = r;
+      }
+    }
+}
+
+int gemm(cudaStream_t st, int M, int N, int K, const float* A, int lda, bool ta, const float* B, int ldb, bool tb,
+         float* Cm, int ldc, float alpha, const float* E, int lde, int emod, const float* v) {
+  if (M <= 0 || N <= 0) return GF_OK;
+  dim3 grid((N + 31) / 32, (M + 31) / 32);
+  if (emod < 1) emod = 1;
+  if (!ta && !tb) gemm_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, Cm, ldc, alpha, E, lde, emod, v);
+  else if (ta && !tb) gemm_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, Cm, ldc, alpha, E, lde, emod, v);
+  else if (!ta && tb) gemm_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, Cm, ldc, alpha, E, lde, emod, v);
+  else gemm_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, Cm, ldc, alpha, E, lde, emod, v);
+  GF_LAUNCH_OK();
+  return GF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// stage W helper kernels
+// ------------------------------------------------------------------------------------------------------
+// out[c', col], c' < C, col < LDK:  [ Wq^T * a | Wp^T * ap | bias * s | 0 0 0 ]   (oracle/folded.py: qfold / m_fold)
+__global__ void build_fold_kernel(float* __restrict__ out, const float* __restrict__ wq, const float* __restrict__ wp,
+                                  const float* __restrict__ bias, int C, int p, int LDK, float a, float ap, float s) {
+  const size_t total = (size_t)C * LDK;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cp = (int)(i / LDK), col = (int)(i % LDK);
+    float r = 0.f;
+    if (col < C) r = wq[(size_t)col * C + cp] * a;
+    else if (col < C + p) r = wp ? wp[(size_t)(col - C) * C + cp] * ap : 0.f;
+    else if (col == C + p) r = bias ? bias[cp] * s : 0.f;
+    out[i] = r;
+  }
+}
+
+__global__ void scale_copy_kernel(float* __restrict__ out, const float* __restrict__ in, size_t nel, float a, float add, size_t add_upto) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nel; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = in[i] * a + (i < add_upto ? add : 0.f);
+}
+
+// sinusoidal_axis(length, dim): [sin(pos*f_m) m<dim/2 | cos(pos*f_m)], f_m = (pi/2) 2^m, pos = (i+.5)/length*2-1
+__global__ void pos_axis_kernel(float* __restrict__ out, int length, int dim) {
+  const int total = length * dim;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / dim, q = i % dim, hq = dim / 2;
+    const double pos = ((double)r + 0.5) / (double)length * 2.0 - 1.0;
+    const int m = q < hq ? q : q - hq;
+    const double ang = pos * (1.5707963267948966 * exp2((double)m));
+    out[i] = (float)(q < hq ? sin(ang) : cos(ang));
+  }
+}
+
+static inline int blocks_for(size_t nel) { size_t b = (nel + 255) / 256; return (int)(b > 1184 ? 1184 : (b < 1 ? 1 : b)); }
+
+int fold_weights(const Layout& L, const gf_attn_desc* d, const gf_attn_weights* w, float* f, cudaStream_t st) {
+  const int C = L.C, k = L.k, D = L.D, p = L.p, LDK = L.LDK, Cout = L.Cout;
+  const bool pos = p > 0;
+  if (!w->wq || !w->bq || !w->bk || !w->wv || !w->bv || !w->wo || !w->bo) { set_error("fold_weights: null simplex weight pointer"); return GF_ERR_INVALID; }
+  if (pos && (!w->wpq || !w->wpk || !w->pos_latent)) { set_error("fold_weights: pos_dim>0 but positional weights are null"); return GF_ERR_INVALID; }
+  if (!L.duplex && !w->wk) { set_error("fold_weights: null wk"); return GF_ERR_INVALID; }
+  if (L.duplex && (!w->wq2 || !w->bq2 || !w->wk2 || !w->wv2 || !w->bv2 || !w->wkc || (pos && (!w->wpq2 || !w->wpk2)))) {
+    set_error("fold_weights: duplex weights are null"); return GF_ERR_INVALID;
+  }
+  const float s = 1.f / sqrtf((float)C);           // 1/sqrt(C/heads), heads = 1
+  const float rC = 1.f / sqrtf((float)C), rD = 1.f / sqrtf((float)D), rp = pos ? 1.f / sqrtf((float)p) : 0.f;
+  int rc;
+  // qfold [C, LDK]
+  build_fold_kernel<<<blocks_for((size_t)C * LDK), 256, 0, st>>>(f + L.f_QFOLD, w->wq, pos ? w->wpq : nullptr, w->bq, C, p, LDK, s * rC, s * rp, s);
+  GF_LAUNCH_OK();
+  // kconst [k, C] = bk + Pl @ wpk_e
+  if ((rc = gemm(st, k, C, pos ? p : 0, w->pos_latent, p, false, w->wpk, C, false, f + L.f_KCONST, C, rp, nullptr, 0, 1, w->bk))) return rc;
+  // CK = kconst @ qfold
+  if ((rc = gemm(st, k, LDK, C, f + L.f_KCONST, C, false, f + L.f_QFOLD, LDK, false, f + L.f_CK, LDK, 1.f))) return rc;
+  if (L.duplex) {
+    // AK [C, LDK] = wkc_e @ qfold  (applied to centroids)
+    if ((rc = gemm(st, C, LDK, C, w->wkc, C, false, f + L.f_QFOLD, LDK, false, f + L.f_AK, LDK, rC))) return rc;
+    scale_copy_kernel<<<blocks_for((size_t)C * C), 256, 0, st>>>(f + L.f_WV2, w->wv2, (size_t)C * C, rC, 0.f, 0);
+    GF_LAUNCH_OK();
+    scale_copy_kernel<<<blocks_for(C), 256, 0, st>>>(f + L.f_BV2, w->bv2, C, 1.f, 0.f, 0);
+    GF_LAUNCH_OK();
+    // pass A: mfold [C, LDK] (no bias column: the bk2 term is constant over n and cancels in softmax_n)
+    build_fold_kernel<<<blocks_for((size_t)C * LDK), 256, 0, st>>>(f + L.f_MFOLD, w->wk2, pos ? w->wpk2 : nullptr, nullptr, C, p, LDK, s * rC, s * rp, 0.f);
+    GF_LAUNCH_OK();
+    if ((rc = gemm(st, k, C, pos ? p : 0, w->pos_latent, p, false, w->wpq2, C, false, f + L.f_QCONST, C, rp, nullptr, 0, 1, w->bq2))) return rc;
+    if ((rc = gemm(st, D, LDK, C, w->wq2, C, false, f + L.f_MFOLD, LDK, false, f + L.f_AM, LDK, rD))) return rc;
+    if ((rc = gemm(st, k, LDK, C, f + L.f_QCONST, C, false, f + L.f_MFOLD, LDK, false, f + L.f_CM, LDK, 1.f))) return rc;
+  } else {
+    if ((rc = gemm(st, D, LDK, C, w->wk, C, false, f + L.f_QFOLD, LDK, false, f + L.f_AK, LDK, rD))) return rc;
+  }
+  // AV [D, Cout] = wv_e @ wo_e ; CV = bv @ wo_e + bo (+1 on the gain half)
+  if ((rc = gemm(st, D, Cout, C, w->wv, C, false, w->wo, Cout, false, f + L.f_AV, Cout, rD * rC))) return rc;
+  if ((rc = gemm(st, 1, Cout, C, w->bv, C, false, w->wo, Cout, false, f + L.f_CV, Cout, rC, nullptr, 0, 1, w->bo))) return rc;
+  if (d->integration != GF_INT_ADD) {
+    scale_copy_kernel<<<blocks_for(Cout), 256, 0, st>>>(f + L.f_CV, f + L.f_CV, Cout, 1.f, 1.f, (size_t)C);
+    GF_LAUNCH_OK();
+  }
+  if (pos) {
+    pos_axis_kernel<<<blocks_for((size_t)L.H * (p / 2)), 256, 0, st>>>(f + L.f_ROW, L.H, p / 2);
+    GF_LAUNCH_OK();
+    pos_axis_kernel<<<blocks_for((size_t)L.W * (p / 2)), 256, 0, st>>>(f + L.f_COL, L.W, p / 2);
+    GF_LAUNCH_OK();
+  }
+  return GF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// stage I: per-image tables
+// ------------------------------------------------------------------------------------------------------
+// grid (nblk, B).  blockIdx.x == 0: positional logit tables Rt/Ct of image b.  blockIdx.x >= 1: Kp and (optionally) Vt.
+__global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ kpall, const float* __restrict__ Y,
+                                                       const float* __restrict__ AV, const float* __restrict__ CV,
+                                                       const float* __restrict__ ROW, const float* __restrict__ COL,
+                                                       float* __restrict__ Kp, float* __restrict__ Vt,
+                                                       float* __restrict__ Rt, float* __restrict__ Ct,
+                                                       int H, int W, int C, int k, int D, int p, int KP, int Cout, int LDK) {
+  const int b = blockIdx.y;
+  const float* kp = kpall + (size_t)b * k * LDK;
+  if (blockIdx.x == 0) {
+    const int half = p / 2;
+    for (int i = threadIdx.x; i < (H + W) * KP; i += blockDim.x) {
+      const int r = i / KP, j = i % KP;
+      const bool is_row = r < H;
+      float val;
+      if (j >= k) {
+        val = is_row ? -INFINITY : 0.f;
+      } else {
+        const float* kj = kp + (size_t)j * LDK + C;
+        float acc = 0.f;
+        if (is_row) {
+          for (int q = 0; q < half; ++q) acc = fmaf(ROW[r * half + q], kj[q], acc);
+          acc += kj[p];
+        } else {
+          for (int q = 0; q < half; ++q) acc = fmaf(COL[(r - H) * half + q], kj[half + q], acc);
+        }
+        val = acc;
+      }
+      if (is_row) Rt[((size_t)b * H + r) * KP + j] = val;
+      else Ct[((size_t)b * W + (r - H)) * KP + j] = val;
+    }
+    return;
+  }
+  const int nK = KP * C, nV = Vt ? Cout * KP : 0;
+  const int stride = (gridDim.x - 1) * blockDim.x;
+  for (int i = (blockIdx.x - 1) * blockDim.x + threadIdx.x; i < nK + nV; i += stride) {
+    if (i < nK) {
+      const int j = i / C, c = i % C;
+      Kp[(size_t)b * nK + i] = j < k ? kp[(size_t)j * LDK + c] : 0.f;
+    } else {
+      const int e = i - nK, c = e / KP, j = e % KP;
+      float acc = 0.f;
+      if (j < k) {
+        const float* yj = Y + ((size_t)b * k + j) * D;
+        for (int dd = 0; dd < D; ++dd) acc = fmaf(yj[dd], AV[(size_t)dd * Cout + c], acc);
+        acc += CV[c];
+      }
+      Vt[(size_t)b * nV + e] = acc;
+    }
+  }
+}
+
+int prologue(const Layout& L, const gf_attn_desc* d, const float* Y, const float* key_source, int kdim,
+             const float* f, float* ws, cudaStream_t st) {
+  (void)d;
+  int rc;
+  // KPALL [B*k, LDK] = key_source @ AK + CK
+  if ((rc = gemm(st, L.B * L.k, L.LDK, kdim, key_source, kdim, false, f + L.f_AK, L.LDK, false, ws + L.w_KPALL, L.LDK, 1.f,
+                 f + L.f_CK, L.LDK, L.k)))
+    return rc;
+  const int nel = L.KP * L.C + L.Cout * L.KP;
+  int nblk = 1 + (nel + 256 * 8 - 1) / (256 * 8);
+  finalize_kernel<<<dim3(nblk, L.B), 256, 0, st>>>(ws + L.w_KPALL, Y, f + L.f_AV, f + L.f_CV, f + L.f_ROW, f + L.f_COL,
+                                                   ws + L.w_Kp, ws + L.w_Vt, ws + L.w_Rt, ws + L.w_Ct,
+                                                   L.H, L.W, L.C, L.k, L.D, L.p, L.KP, L.Cout, L.LDK);
+  GF_LAUNCH_OK();
+  return GF_OK;
+}
+
+// duplex pass A tables: M [B,KP,C] and the positional logit tables of the latent queries
+int duplex_tables(const Layout& L, const gf_attn_desc* d, const float* Y, const float* f, float* ws, cudaStream_t st) {
+  (void)d;
+  int rc;
+  if ((rc = gemm(st, L.B * L.k, L.LDK, L.D, Y, L.D, false, f + L.f_AM, L.LDK, false, ws + L.w_MALL, L.LDK, 1.f,
+                 f + L.f_CM, L.LDK, L.k)))
+    return rc;
+  const int nel = L.KP * L.C;
+  int nblk = 1 + (nel + 256 * 8 - 1) / (256 * 8);
+  finalize_kernel<<<dim3(nblk, L.B), 256, 0, st>>>(ws + L.w_MALL, Y, nullptr, nullptr, f + L.f_ROW, f + L.f_COL,
+                                                   ws + L.w_M, nullptr, ws + L.w_Rt2, ws + L.w_Ct2,
+                                                   L.H, L.W, L.C, L.k, L.D, L.p, L.KP, L.Cout, L.LDK);
+  GF_LAUNCH_OK();
+  return GF_OK;
+}
+
+}  // namespace gf

@@ -1,0 +1,253 @@
+"""GANsformer generator host code around the bipartite-attention hot path.
+
+Mirrors the reference's model API (expected ``src/training/network.py`` upstream -- ``G_GANsformer`` /
+``G_mapping`` / ``G_synthesis`` -- not present in the reference checkout; kwarg names
+follow SURVEY.md section 8b): ``Generator(z[B,k+1,D], c=None, truncation_psi=1.0, noise_mode=..., return_att=False)
+-> img[B,3,R,R]`` with ``.mapping`` / ``.synthesis`` sub-modules, plus a ``Gs.run``-style ``run(...)`` wrapper.
+
+Everything here except the attention block is plain PyTorch plumbing (cuDNN convolutions, channels-last
+memory format); the attention block -- the hot path -- is the C-ABI call in ``attention.py``.  Architecture
+choices the reference source cannot arbitrate are frozen in SURVEY.md A.4 ([SPEC] items 1-9).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .attention import BipartiteAttention
+
+SQRT2 = math.sqrt(2.0)
+
+
+def nf(res: int, fmap_base: int = 16384, fmap_max: int = 512) -> int:
+    """StyleGAN2 config-f channel schedule."""
+    return int(min(fmap_base // (2 ** (int(math.log2(res)) - 1)), fmap_max))
+
+
+def fir_filter(device=None, dtype=torch.float32) -> torch.Tensor:
+    f = torch.tensor([1.0, 3.0, 3.0, 1.0], dtype=torch.float64)
+    f = torch.outer(f, f)
+    return (f / f.sum()).to(device=device, dtype=dtype)
+
+
+def upfirdn2d(x: torch.Tensor, f: torch.Tensor, up: int = 1, pad=(0, 0, 0, 0), gain: float = 1.0) -> torch.Tensor:
+    """Zero-insert upsample by `up`, pad (x0, x1, y0, y1), correlate with the (symmetric) FIR filter `f`.
+
+    Host stand-in for the reference's native op dnnlib/tflib/ops/upfirdn_2d.cu."""
+    B, C, H, W = x.shape
+    if up > 1:
+        x = x.reshape(B, C, H, 1, W, 1)
+        x = F.pad(x, [0, up - 1, 0, 0, 0, up - 1])
+        x = x.reshape(B, C, H * up, W * up)
+    x = F.pad(x, [pad[0], pad[1], pad[2], pad[3]])
+    w = (f * gain).to(x.dtype)[None, None].expand(C, 1, *f.shape)
+    return F.conv2d(x, w, groups=C)
+
+
+def bias_act(x: torch.Tensor, b: Optional[torch.Tensor], act: str = "lrelu") -> torch.Tensor:
+    """Host stand-in for the reference's native op dnnlib/tflib/ops/fused_bias_act.cu."""
+    if b is not None:
+        x = x + b.to(x.dtype).reshape(1, -1, *([1] * (x.dim() - 2)))
+    if act == "lrelu":
+        x = F.leaky_relu(x, 0.2) * SQRT2
+    return x
+
+
+def modulated_conv2d(x: torch.Tensor, weight: torch.Tensor, styles: torch.Tensor, *, demodulate: bool = True,
+                     up: int = 1, f: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """StyleGAN2 modulated convolution in its activation-scaling form: (x * s) conv w, then * demod.
+
+    Identical in exact arithmetic to modulating the weights per sample (the reference's grouped-conv form);
+    avoids B separate weight tensors.  weight [O, I, kh, kw]; styles [B, I]."""
+    O, I, kh, kw = weight.shape
+    w = weight * (1.0 / math.sqrt(I * kh * kw))
+    x = x * styles[:, :, None, None]
+    if up == 1:
+        x = F.conv2d(x, w, padding=kh // 2)
+    else:
+        x = F.conv_transpose2d(x, w.transpose(0, 1), stride=2)        # [B, O, 2H+1, 2W+1]
+        x = upfirdn2d(x, f, pad=(1, 1, 1, 1), gain=4.0)                # -> [B, O, 2H, 2W]
+    if demodulate:
+        wsq = w.square().sum(dim=[2, 3])                               # [O, I]
+        d = torch.rsqrt(styles.square() @ wsq.t() + 1e-8)             # [B, O]
+        x = x * d[:, :, None, None]
+    return x
+
+
+class FullyConnected(nn.Module):
+    def __init__(self, in_features: int, out_features: int, bias_init: float = 0.0, lr_mul: float = 1.0, act: str = "linear"):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(out_features, in_features) / lr_mul)
+        self.bias = nn.Parameter(torch.full((out_features,), float(bias_init)))
+        self.wgain = lr_mul / math.sqrt(in_features)
+        self.bgain = lr_mul
+        self.act = act
+
+    def forward(self, x):
+        x = F.linear(x, self.weight * self.wgain, self.bias * self.bgain)
+        return F.leaky_relu(x, 0.2) * SQRT2 if self.act == "lrelu" else x
+
+
+class MappingNetwork(nn.Module):
+    """G_mapping: z [B, k+1, D] -> w [B, k+1, D]; the k local components share one MLP, the global latent has its own."""
+
+    def __init__(self, latent_dim: int, components_num: int, num_layers: int = 8, lr_mul: float = 0.01):
+        super().__init__()
+        self.latent_dim, self.components_num = latent_dim, components_num
+        self.local = nn.ModuleList([FullyConnected(latent_dim, latent_dim, lr_mul=lr_mul, act="lrelu") for _ in range(num_layers)])
+        self.glob = nn.ModuleList([FullyConnected(latent_dim, latent_dim, lr_mul=lr_mul, act="lrelu") for _ in range(num_layers)])
+        self.register_buffer("w_avg", torch.zeros(2, latent_dim))
+
+    def forward(self, z: torch.Tensor, truncation_psi: float = 1.0) -> torch.Tensor:
+        k = self.components_num
+        if z.dim() != 3 or z.shape[1] != k + 1 or z.shape[2] != self.latent_dim:
+            raise ValueError(f"z must be [B, {k + 1}, {self.latent_dim}], got {tuple(z.shape)}")
+        z = z * torch.rsqrt(z.square().mean(dim=2, keepdim=True) + 1e-8)
+        loc, glo = z[:, :k], z[:, k:]
+        for fc in self.local:
+            loc = fc(loc)
+        for fc in self.glob:
+            glo = fc(glo)
+        if truncation_psi != 1.0:
+            loc = self.w_avg[0].lerp(loc, truncation_psi)
+            glo = self.w_avg[1].lerp(glo, truncation_psi)
+        return torch.cat([loc, glo], dim=1)
+
+
+class SynthesisLayer(nn.Module):
+    """mod-conv -> bipartite attention (the hot path) -> noise -> bias + lrelu."""
+
+    def __init__(self, in_ch: int, out_ch: int, w_dim: int, resolution: int, up: bool, components_num: int,
+                 use_attention: bool, attn_kwargs: dict):
+        super().__init__()
+        self.resolution, self.up = resolution, up
+        self.affine = FullyConnected(w_dim, in_ch, bias_init=1.0)
+        self.weight = nn.Parameter(torch.randn(out_ch, in_ch, 3, 3))
+        self.bias = nn.Parameter(torch.zeros(out_ch))
+        self.register_buffer("noise_const", torch.randn(resolution, resolution))
+        self.noise_strength = nn.Parameter(torch.zeros([]))
+        self.register_buffer("fir", fir_filter())
+        self.attention = BipartiteAttention(out_ch, w_dim, components_num, **attn_kwargs) if use_attention else None
+
+    def forward(self, x, w_glob, y, noise_mode="const", centroids=None, return_att=False):
+        styles = self.affine(w_glob)
+        x = modulated_conv2d(x, self.weight, styles, up=2 if self.up else 1, f=self.fir)
+        att = None
+        if self.attention is not None:
+            xl = x.permute(0, 2, 3, 1)                                  # channels-last storage -> [B,H,W,C] view
+            if not xl.is_contiguous():
+                xl = xl.contiguous()
+            xo, att, centroids = self.attention(xl, y, centroids=centroids, return_att=return_att)
+            x = xo.permute(0, 3, 1, 2)                                  # back to an NCHW view of channels-last data
+        if noise_mode == "const":
+            x = x + self.noise_const * self.noise_strength
+        elif noise_mode == "random":
+            x = x + torch.randn(x.shape[0], 1, self.resolution, self.resolution, device=x.device, dtype=x.dtype) * self.noise_strength
+        x = bias_act(x, self.bias, "lrelu")
+        return x, att, centroids
+
+
+class ToRGB(nn.Module):
+    def __init__(self, in_ch: int, w_dim: int, img_channels: int = 3):
+        super().__init__()
+        self.affine = FullyConnected(w_dim, in_ch, bias_init=1.0)
+        self.weight = nn.Parameter(torch.randn(img_channels, in_ch, 1, 1))
+        self.bias = nn.Parameter(torch.zeros(img_channels))
+
+    def forward(self, x, w_glob):
+        styles = self.affine(w_glob)
+        x = modulated_conv2d(x, self.weight, styles, demodulate=False)
+        return bias_act(x, self.bias, "linear")
+
+
+class SynthesisNetwork(nn.Module):
+    """G_synthesis, skip architecture.  Attention on both conv layers of every resolution in [start_res, end_res]."""
+
+    def __init__(self, resolution: int, latent_dim: int, components_num: int, fmap_base: int = 16384, fmap_max: int = 512,
+                 g_start_res: int = 8, g_end_res: Optional[int] = None, transformer: bool = True, attn_kwargs: Optional[dict] = None):
+        super().__init__()
+        assert resolution >= 4 and resolution & (resolution - 1) == 0
+        self.resolution, self.components_num = resolution, components_num
+        g_end_res = resolution if g_end_res is None else g_end_res
+        self.block_resolutions = [2 ** i for i in range(2, int(math.log2(resolution)) + 1)]
+        attn_kwargs = dict(attn_kwargs or {})
+        self.const = nn.Parameter(torch.randn(nf(4, fmap_base, fmap_max), 4, 4))
+        self.layers = nn.ModuleList()
+        self.torgbs = nn.ModuleList()
+        self.layer_res: List[int] = []
+        self.iterative = bool(attn_kwargs.pop("iterative", False))
+        for res in self.block_resolutions:
+            out_ch = nf(res, fmap_base, fmap_max)
+            use_att = transformer and components_num > 0 and g_start_res <= res <= g_end_res
+            if res > 4:
+                in_ch = nf(res // 2, fmap_base, fmap_max)
+                self.layers.append(SynthesisLayer(in_ch, out_ch, latent_dim, res, True, components_num, use_att, attn_kwargs))
+                self.layer_res.append(res)
+            self.layers.append(SynthesisLayer(out_ch, out_ch, latent_dim, res, False, components_num, use_att, attn_kwargs))
+            self.layer_res.append(res)
+            self.torgbs.append(ToRGB(out_ch, latent_dim))
+        self.register_buffer("fir", fir_filter())
+        self.num_attention_layers = sum(1 for l in self.layers if l.attention is not None)
+
+    def forward(self, ws: torch.Tensor, noise_mode: str = "const", return_att: bool = False):
+        k = self.components_num
+        B = ws.shape[0]
+        y = ws[:, :k].contiguous()
+        w_glob = ws[:, k]
+        x = self.const[None].expand(B, -1, -1, -1).contiguous(memory_format=torch.channels_last)
+        img = None
+        atts = []
+        li = 0
+        for bi, res in enumerate(self.block_resolutions):
+            nl = 1 if res == 4 else 2
+            for _ in range(nl):
+                layer = self.layers[li]
+                li += 1
+                x, att, _ = layer(x, w_glob, y, noise_mode=noise_mode, return_att=return_att)
+                if att is not None:
+                    atts.append(att)
+            rgb = self.torgbs[bi](x, w_glob)
+            img = rgb if img is None else upfirdn2d(img, self.fir, up=2, pad=(2, 1, 2, 1), gain=4.0) + rgb
+        return (img, atts) if return_att else img
+
+
+class Generator(nn.Module):
+    """G_GANsformer.  ``G(z, c=None, truncation_psi=1.0, noise_mode='const', return_att=False) -> img [B,3,R,R]``."""
+
+    def __init__(self, resolution: int = 256, components_num: int = 16, latent_size: int = 512, latent_dim: Optional[int] = None,
+                 transformer: bool = True, g_start_res: int = 8, g_end_res: Optional[int] = None, kmeans: bool = False,
+                 kmeans_iters: int = 1, iterative: bool = False, integration: str = "mul", norm: Optional[str] = "layer",
+                 use_pos: bool = True, pos_dim: Optional[int] = None, num_heads: int = 1, mapping_layers: int = 8,
+                 fmap_base: int = 16384, fmap_max: int = 512, exact_fp32: bool = False):
+        super().__init__()
+        # D = latent_size // components_num unless given
+        self.latent_dim = latent_dim if latent_dim is not None else max(latent_size // max(components_num, 1), 1)
+        self.components_num, self.resolution = components_num, resolution
+        attn_kwargs = dict(pos_dim=pos_dim, num_heads=num_heads, integration=integration, norm=norm, kmeans=kmeans,
+                           kmeans_iters=kmeans_iters, use_pos=use_pos, exact_fp32=exact_fp32, iterative=iterative)
+        self.mapping = MappingNetwork(self.latent_dim, components_num, num_layers=mapping_layers)
+        self.synthesis = SynthesisNetwork(resolution, self.latent_dim, components_num, fmap_base=fmap_base, fmap_max=fmap_max,
+                                          g_start_res=g_start_res, g_end_res=g_end_res, transformer=transformer,
+                                          attn_kwargs=attn_kwargs)
+
+    def forward(self, z: torch.Tensor, c=None, truncation_psi: float = 1.0, noise_mode: str = "const", return_att: bool = False):
+        ws = self.mapping(z, truncation_psi=truncation_psi)
+        return self.synthesis(ws, noise_mode=noise_mode, return_att=return_att)
+
+    @torch.no_grad()
+    def run(self, latents, labels=None, truncation_psi: float = 1.0, randomize_noise: bool = False, minibatch_size: int = 32):
+        """``Gs.run``-shaped convenience wrapper (reference: dnnlib/tflib/network.py Network.run): host numpy/tensor
+        latents in, host images out, processed in minibatches on this module's device."""
+        dev = next(self.parameters()).device
+        lat = torch.as_tensor(np.asarray(latents) if not torch.is_tensor(latents) else latents, dtype=torch.float32)
+        outs = []
+        for i in range(0, lat.shape[0], minibatch_size):
+            z = lat[i:i + minibatch_size].to(dev, non_blocking=True)
+            img = self(z, truncation_psi=truncation_psi, noise_mode="random" if randomize_noise else "const")
+            outs.append(img.contiguous().cpu())
+        return torch.cat(outs, dim=0)

@@ -1,0 +1,120 @@
+/*
+ * gf_attn.h -- C ABI of the B200-native GANsformer bipartite-attention hot path.
+ *
+ * Drop-in boundary.  The reference has no FFI for this path: its attention block
+ * is Python/TensorFlow graph code, expected at src/training/network.py (transformer_layer, integrate,
+ * att_norm, dense_layer, get_positional_embeddings) -- NOT present in the reference checkout
+ * (/root/reference/.SUBMODULES.json:2 reports "bytes": 0), so no file:line can be cited; the only
+ * reference files on disk are LICENSE and src/Dockerfile (:7 pins tensorflow 1.14).  Each entry point
+ * below names the reference function it replaces.  INTEGRATION.md shows the ctypes stub a maintainer of
+ * the reference would add inside transformer_layer().
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA-runtime types in signatures; `stream` is a cudaStream_t passed as void*.
+ *   - every pointer is a DEVICE pointer unless named host_*; the library never allocates or frees
+ *     device memory and never synchronises; all work is enqueued on `stream`.
+ *   - activations are channels-last fp32: X[B][H][W][C]  (== [B*n][C] row-major, n = H*W).
+ *   - return value: GF_OK (0) or a negative gf_status; gf_last_error() gives a thread-local message.
+ *   - unsupported shape / device => error.  There is no CPU path and no fallback of any kind.
+ */
+#ifndef GF_ATTN_H_
+#define GF_ATTN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GF_ATTN_ABI_VERSION 1
+
+typedef enum gf_status {
+  GF_OK = 0,
+  GF_ERR_INVALID = -1,      /* bad descriptor / null pointer */
+  GF_ERR_UNSUPPORTED = -2,  /* valid request this build has no kernel for */
+  GF_ERR_CUDA = -3,         /* CUDA runtime / driver error (message has the string) */
+  GF_ERR_WORKSPACE = -4     /* workspace or folded buffer too small */
+} gf_status;
+
+/* att_norm(): which statistics normalise X before modulation */
+enum { GF_NORM_NONE = 0, GF_NORM_LAYER = 1, GF_NORM_INSTANCE = 2, GF_NORM_BATCH = 3 };
+/* integrate(): how the control signal modulates X */
+enum { GF_INT_MUL = 0, GF_INT_ADD = 1, GF_INT_BOTH = 2 };
+/* desc.flags */
+enum {
+  GF_FLAG_FP32_EXACT = 1,   /* force the CUDA-core fp32-FMA kernel (tight-tolerance mode); default = tcgen05 TF32 */
+  GF_FLAG_CENTROIDS_IN = 2  /* duplex: skip pass A, take centroids_inout as input (iterative=True upstream) */
+};
+/* which kernel family served the last forward on this thread (gf_attn_last_path) */
+enum { GF_PATH_NONE = 0, GF_PATH_SIMT_FP32 = 1, GF_PATH_TCGEN05_TF32 = 2 };
+
+/* Shape/config of one attention layer call.  Mirrors the kwargs of the reference's
+ * transformer_layer(dim, pos_dim, from_tensor, to_tensor, from_len, to_len, num_heads, integration, norm, kmeans...) */
+typedef struct gf_attn_desc {
+  int32_t B, H, W, C;   /* X[B,H,W,C]; from_len = H*W, dim = C */
+  int32_t k, D;         /* Y[B,k,D]; to_len = k latents of size D */
+  int32_t heads;        /* num_heads; this build: 1 */
+  int32_t norm;         /* GF_NORM_* */
+  int32_t integration;  /* GF_INT_* */
+  int32_t pos_dim;      /* width of the positional embeddings; 0 = use_pos False */
+  int32_t duplex;       /* 0 = simplex (latents -> image), 1 = duplex (kmeans, one iteration) */
+  int32_t flags;        /* GF_FLAG_* */
+} gf_attn_desc;
+
+/* Raw (un-scaled) parameters of one layer, each [fan_in, fan_out] row-major; equalised-LR scaling
+ * (1/sqrt(fan_in), reference: get_weight/dense_layer) is applied by the library.  The *2 / wkc
+ * members are only read when desc.duplex; wpq/wpk/pos_latent (and wpq2/wpk2) only when pos_dim>0. */
+typedef struct gf_attn_weights {
+  const float *wq, *bq, *wpq;      /* [C,C] [C] [p,C]   query side (grid)            */
+  const float *wk, *bk, *wpk;      /* [D,C] [C] [p,C]   key side (latents; wk unused in duplex) */
+  const float *wv, *bv;            /* [D,C] [C]         values (latents)             */
+  const float *wo, *bo;            /* [C,Cout] [Cout]   integrate()'s dense, Cout = C or 2C ("both") */
+  const float *pos_latent;         /* [k,p]             learned latent positional embedding */
+  const float *wq2, *bq2, *wpq2;   /* [D,C] [C] [p,C]   duplex pass A: latent queries */
+  const float *wk2, *bk2, *wpk2;   /* [C,C] [C] [p,C]   duplex pass A: grid keys      */
+  const float *wv2, *bv2;          /* [C,C] [C]         duplex pass A: grid values    */
+  const float *wkc;                /* [C,C]             centroid -> key               */
+} gf_attn_weights;
+
+/* Library / device introspection. */
+int gf_attn_abi_version(void);
+const char* gf_last_error(void);
+int gf_attn_last_path(void);
+/* Number of kernels this library has launched in this process (all threads); bench.py reports the delta. */
+long long gf_attn_launch_count(void);
+
+/* Size in floats of the folded-weight buffer (stage W output + its scratch). */
+int gf_attn_folded_floats(const gf_attn_desc* desc, size_t* out_floats);
+
+/* Stage W -- replaces the weight-only part of dense_layer()/get_weight(): folds Wq,Wk,Wpq,Wpk,Wo,...
+ * into the small matrices the per-image prologue consumes.  Run once per weight update. */
+int gf_attn_fold_weights(const gf_attn_desc* desc, const gf_attn_weights* weights, float* folded, void* stream);
+
+/* Size in bytes of the per-call workspace for batch desc->B. */
+int gf_attn_workspace_bytes(const gf_attn_desc* desc, size_t* out_bytes);
+
+/* Stage I -- replaces the K/V dense layers + get_positional_embeddings() of transformer_layer():
+ * per image builds K' [B,KP,C], V^T [B,Cout,KP] and the separable positional-logit tables in `ws`.
+ * Simplex: keys from Y.  Duplex: called internally by gf_attn_duplex_fwd after pass A. */
+int gf_attn_prologue(const gf_attn_desc* desc, const float* Y, const float* folded, void* ws, void* stream);
+
+/* Stage T -- replaces the body of transformer_layer() + integrate() + att_norm() for simplex attention:
+ * one read of X, one write of Xout (may alias X).  att (nullable) receives softmax probabilities [B,n,k].
+ * Requires gf_attn_prologue() on the same ws/stream first. */
+int gf_attn_simplex_fwd(const gf_attn_desc* desc, const float* X, float* Xout, float* att, void* ws, void* stream);
+
+/* Duplex (kmeans) layer: pass A (latents attend to the grid, softmax over n, centroids [B,k,C]) then
+ * prologue with keys from the centroids, then stage T.  centroids_inout: output (and input when
+ * GF_FLAG_CENTROIDS_IN). */
+int gf_attn_duplex_fwd(const gf_attn_desc* desc, const float* X, const float* Y, const float* folded,
+                       float* Xout, float* att, float* centroids_inout, void* ws, void* stream);
+
+/* Per-(b,c) statistics for GF_NORM_INSTANCE / GF_NORM_BATCH, written into ws by a reduction pass over X
+ * (called internally by the forward entry points; exported for tests). */
+int gf_attn_norm_stats(const gf_attn_desc* desc, const float* X, void* ws, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GF_ATTN_H_ */

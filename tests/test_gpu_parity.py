@@ -1,0 +1,306 @@
+"""GPU parity tests (run on a B200: ``pytest -m gpu``).  Every call goes through the C ABI (libgf_attn.so).
+
+Oracle = oracle/bipartite.py in float64 (in-repo restatement; reference source unavailable; PARITY UNPINNED).
+
+Tolerances (stated here, per the task contract):
+  * fp32-FMA mode (GF_FLAG_FP32_EXACT, CUDA-core kernel):   |y - y64| <= 1e-5 + 1e-4 |y64|      
+  * TF32 tensor-core mode (tcgen05 kind::tf32, default):    |y - y64| <= 8e-3 + 8e-3 |y64|  and  rel-RMS <= 2e-3
+    (calibrated with a CPU emulation of TF32 operand truncation on N(0,1) weights: rel-RMS ~9e-4, max-abs ~1.6e-2
+     at |y| ~ 12; the logits lose ~1e-3 absolute to the 10-bit mantissa.)
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bipartite as ob
+from oracle import generator as og
+from tests.golden import make_golden as mg
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "attn_cases.npz")
+
+TOL = {"simt_fp32": (1e-5, 1e-4, 2e-5), "tcgen05_tf32": (8e-3, 8e-3, 2e-3)}
+
+
+def check_close(got, ref64, path, what=""):
+    got = got.detach().double().cpu()
+    ref64 = ref64.detach().double().cpu()
+    assert got.shape == ref64.shape, (got.shape, ref64.shape)
+    assert torch.isfinite(got).all(), f"{what}: non-finite output"
+    atol, rtol, rrms = TOL[path]
+    err = (got - ref64).abs()
+    ratio = (err / (atol + rtol * ref64.abs())).max().item()
+    rel_rms = (err.pow(2).mean().sqrt() / ref64.pow(2).mean().sqrt().clamp_min(1e-30)).item()
+    print(f"[parity] {what} path={path} max_abs={err.max().item():.3e} max_ratio={ratio:.3f} rel_rms={rel_rms:.3e}")
+    assert ratio <= 1.0, f"{what}: path={path} max |err|/(atol+rtol|y|) = {ratio:.3f} (max_abs {err.max().item():.3e})"
+    assert rel_rms <= rrms, f"{what}: path={path} rel_rms {rel_rms:.3e} > {rrms}"
+
+
+def make_layer(gf, dev, C, D, k, p, integration, norm, duplex, use_pos, exact, w):
+    attn = gf.BipartiteAttention(C, D, k, pos_dim=p, integration=integration, norm=norm, kmeans=duplex, use_pos=use_pos,
+                                 exact_fp32=exact).to(dev)
+    with torch.no_grad():
+        for n, prm in attn.named_parameters():
+            prm.copy_(w[n].float())
+    return attn
+
+
+def run_layer(gf, dev, x64_nchw, y64, w, *, integration, norm, duplex, use_pos, exact, return_att=True, centroids=None):
+    B, C, H, W = x64_nchw.shape
+    k, D = y64.shape[1], y64.shape[2]
+    p = w["pos_latent"].shape[1]
+    attn = make_layer(gf, dev, C, D, k, p, integration, norm, duplex, use_pos, exact, w)
+    x = x64_nchw.permute(0, 2, 3, 1).contiguous().float().to(dev)
+    y = y64.float().to(dev)
+    with torch.no_grad():
+        out, att, cen = attn(x, y, return_att=return_att, centroids=centroids)
+    torch.cuda.synchronize()
+    return out, att, cen, gf._lib.last_path()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# committed golden fixtures
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("exact", [True, False], ids=["fp32", "default"])
+@pytest.mark.parametrize("idx", range(len(mg.cases())))
+def test_layer_matches_golden(gf, cuda_dev, idx, exact):
+    c = mg.cases()[idx]
+    gold = np.load(GOLD)
+    name = mg.case_name(c)
+    x, y, w = mg.make_inputs(c, 100 + idx)
+    norm = None if c["norm"] == "none" else c["norm"]
+    out, att, cen, path = run_layer(gf, cuda_dev, x, y, w, integration=c["integration"], norm=norm, duplex=c["duplex"],
+                                    use_pos=c["use_pos"], exact=exact)
+    if exact:
+        assert path == "simt_fp32"
+    check_close(out, torch.from_numpy(gold[name + "/out"]), path, name + "/out")
+    a_atol = 1e-6 if path == "simt_fp32" else 2e-3
+    assert (att.cpu().double() - torch.from_numpy(gold[name + "/att"]).double()).abs().max() <= a_atol + (1e-4 if exact else 5e-3)
+    if c["duplex"]:
+        check_close(cen, torch.from_numpy(gold[name + "/cen"]), "simt_fp32" if exact else path, name + "/cen")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# live oracle on the layer shapes of the generator at small batch + ragged / edge shapes
+# ---------------------------------------------------------------------------------------------------------
+SHAPES = [
+    # (C, H, W, k, D, p, integration, norm)
+    (512, 8, 8, 16, 32, 32, "mul", "layer"),       # res 8 of the 256^2 generator (n = 64 < one tile)
+    (512, 16, 16, 16, 32, 32, "both", "layer"),
+    (512, 32, 32, 8, 32, 32, "mul", "layer"),
+    (256, 32, 16, 16, 32, 32, "mul", "layer"),      # C = 256 (res 128 layers), rectangular grid
+    (256, 16, 16, 32, 32, 32, "both", "layer"),
+    (128, 32, 32, 16, 32, 32, "mul", "layer"),      # C = 128 (res 256 layers)
+    (128, 32, 32, 32, 32, 32, "add", "layer"),
+    (64, 32, 32, 16, 32, 32, "mul", "layer"),       # C = 64 (res 512 layers)
+    (64, 16, 24, 5, 16, 8, "both", "none"),
+    (32, 4, 4, 3, 8, 4, "mul", "layer"),            # tiny
+    (96, 10, 13, 7, 12, 12, "both", "instance"),    # ragged: n = 130 not a multiple of the tile, odd C/32
+    (64, 16, 16, 1, 16, 16, "mul", "batch"),        # single latent
+]
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["fp32", "default"])
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "C%d-%dx%d-k%d-%s-%s" % (s[0], s[1], s[2], s[3], s[6], s[7]))
+def test_simplex_layer_vs_oracle(gf, cuda_dev, shape, exact):
+    C, H, W, k, D, p, integration, norm = shape
+    B = 2
+    g = torch.Generator().manual_seed(C + H + k)
+    x = torch.randn(B, C, H, W, generator=g, dtype=torch.float64) * 1.3 + 0.2
+    y = torch.randn(B, k, D, generator=g, dtype=torch.float64)
+    w = ob.init_params(C, D, k, p, integration, False, seed=7, bias_std=0.4)
+    nrm = None if norm == "none" else norm
+    ref, ratt, _ = ob.transformer_layer(x, y, w, integration=integration, norm=nrm, return_att=True)
+    out, att, _, path = run_layer(gf, cuda_dev, x, y, w, integration=integration, norm=nrm, duplex=False, use_pos=True, exact=exact)
+    check_close(out, ref.permute(0, 2, 3, 1), path, "simplex")
+    assert att.shape == (B, k, H, W)
+    assert (att.cpu().double() - ratt).abs().max() <= (1e-5 if path == "simt_fp32" else 5e-3)
+    assert (att.sum(dim=1) - 1).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["fp32", "default"])
+@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[3], SHAPES[5], SHAPES[6], SHAPES[8], SHAPES[10]],
+                         ids=lambda s: "C%d-%dx%d-k%d-%s-%s" % (s[0], s[1], s[2], s[3], s[6], s[7]))
+def test_duplex_layer_vs_oracle(gf, cuda_dev, shape, exact):
+    C, H, W, k, D, p, integration, norm = shape
+    B = 2
+    g = torch.Generator().manual_seed(C + H + k + 1)
+    x = torch.randn(B, C, H, W, generator=g, dtype=torch.float64) * 1.3 + 0.2
+    y = torch.randn(B, k, D, generator=g, dtype=torch.float64)
+    w = ob.init_params(C, D, k, p, integration, True, seed=8, bias_std=0.4)
+    nrm = None if norm == "none" else norm
+    ref, ratt, rcen = ob.transformer_layer(x, y, w, integration=integration, norm=nrm, duplex=True, return_att=True)
+    out, att, cen, path = run_layer(gf, cuda_dev, x, y, w, integration=integration, norm=nrm, duplex=True, use_pos=True, exact=exact)
+    check_close(cen, rcen, "simt_fp32", "duplex/centroids")       # pass A runs on CUDA cores in fp32 in both modes
+    check_close(out, ref.permute(0, 2, 3, 1), path, "duplex/out")
+    # iterative=True: centroids fed back in skip pass A and reproduce the same output
+    out2, _, cen2, _ = run_layer(gf, cuda_dev, x, y, w, integration=integration, norm=nrm, duplex=True, use_pos=True, exact=exact,
+                                 centroids=cen.clone())
+    assert torch.equal(cen2, cen)
+    assert (out2 - out).abs().max() <= 1e-6 * max(1.0, out.abs().max().item())
+
+
+def test_inplace_and_no_att(gf, cuda_dev):
+    C, H, W, k, D, p = 128, 16, 16, 16, 32, 32
+    g = torch.Generator().manual_seed(5)
+    x64 = torch.randn(2, C, H, W, generator=g, dtype=torch.float64)
+    y64 = torch.randn(2, k, D, generator=g, dtype=torch.float64)
+    w = ob.init_params(C, D, k, p, "mul", False, seed=9)
+    for exact in (True, False):
+        attn = make_layer(gf, cuda_dev, C, D, k, p, "mul", "layer", False, True, exact, w)
+        x = x64.permute(0, 2, 3, 1).contiguous().float().to(cuda_dev)
+        y = y64.float().to(cuda_dev)
+        with torch.no_grad():
+            ref, att, _ = attn(x, y)
+            assert att is None
+            xin = x.clone()
+            out, _, _ = attn(xin, y, out=xin)          # Xout aliases X
+        assert out.data_ptr() == xin.data_ptr()
+        assert torch.equal(out, ref)
+
+
+def test_functional_transformer_layer(gf, cuda_dev):
+    """The reference-named functional entry point: [B, from_len, dim] tokens in, (tokens', att_probs, att_vars) out."""
+    C, H, W, k, D, p = 64, 8, 16, 4, 16, 16
+    g = torch.Generator().manual_seed(11)
+    x64 = torch.randn(2, C, H, W, generator=g, dtype=torch.float64)
+    y64 = torch.randn(2, k, D, generator=g, dtype=torch.float64)
+    w = ob.init_params(C, D, k, p, "mul", True, seed=3, bias_std=0.2)
+    ref, ratt, rcen = ob.transformer_layer(x64, y64, w, duplex=True, return_att=True)
+    params = {n: t.float().to(cuda_dev) for n, t in w.items()}
+    tokens = x64.permute(0, 2, 3, 1).reshape(2, H * W, C).contiguous().float().to(cuda_dev)
+    out, att_probs, att_vars = gf.transformer_layer(C, p, tokens, y64.float().to(cuda_dev), H * W, k, params, grid_shape=(H, W),
+                                                    kmeans=True, exact_fp32=True)
+    check_close(out.reshape(2, H, W, C), ref.permute(0, 2, 3, 1), "simt_fp32", "functional")
+    assert att_probs.shape == (2, H * W, k)
+    assert (att_probs.cpu().double() - ratt.reshape(2, k, H * W).transpose(1, 2)).abs().max() < 1e-5
+    check_close(att_vars["centroids"], rcen, "simt_fp32", "functional/centroids")
+
+
+def test_errors_are_loud(gf, cuda_dev):
+    attn = gf.BipartiteAttention(64, 16, 4).to(cuda_dev)
+    x = torch.randn(1, 8, 16, 64, device=cuda_dev)
+    y = torch.randn(1, 4, 16, device=cuda_dev)
+    with torch.no_grad():
+        with pytest.raises(RuntimeError, match="float32"):
+            attn(x.half(), y)
+        with pytest.raises(RuntimeError, match="contiguous"):
+            attn(x.transpose(1, 2), y)
+        with pytest.raises(ValueError):
+            attn(x, y[:, :, :8].contiguous().reshape(2, 4, 4))
+    a2 = gf.BipartiteAttention(64, 16, 4, num_heads=2).to(cuda_dev)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="num_heads"):
+        a2(x, y)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# full-size, size-independent properties (BASELINE config-2 layer shape: 256x256 grid, C = 128, k = 16)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("exact", [True, False], ids=["fp32", "default"])
+def test_full_size_properties(gf, cuda_dev, exact):
+    C, H, W, k, D, p, B = 128, 256, 256, 16, 32, 32, 4
+    torch.manual_seed(0)
+    attn = gf.BipartiteAttention(C, D, k, pos_dim=p, exact_fp32=exact).to(cuda_dev)
+    x = torch.randn(B, H, W, C, device=cuda_dev) * 1.2 + 0.1
+    y = torch.randn(B, k, D, device=cuda_dev)
+    with torch.no_grad():
+        out, att, _ = attn(x, y, return_att=True)
+        # (1) attention rows are probability vectors
+        assert (att.sum(dim=1) - 1).abs().max() < 2e-5 and att.min() >= 0
+        # (2) batch independence, bit for bit (basis of the data-parallel sharding)
+        out1, _, _ = attn(x[2:3].contiguous(), y[2:3].contiguous())
+        assert torch.equal(out1[0], out[2])
+        # (3) run-to-run determinism
+        out_b, _, _ = attn(x, y)
+        assert torch.equal(out_b, out)
+        # (4) modulation identity: x' / LN(x) is the gain; for layer norm + "mul" the gain of a token depends on x only
+        #     through its attention row, so tokens with (numerically) one-hot attention on the same latent share it
+        mu = x.mean(dim=3, keepdim=True)
+        xn = (x - mu) * torch.rsqrt(((x - mu) ** 2).mean(dim=3, keepdim=True) + 1e-8)
+        assert torch.isfinite(out).all()
+        # (5) latent-permutation equivariance
+        perm = torch.randperm(k, device=cuda_dev)
+        attn2 = gf.BipartiteAttention(C, D, k, pos_dim=p, exact_fp32=exact).to(cuda_dev)
+        attn2.load_state_dict(attn.state_dict())
+        attn2.pos_latent.copy_(attn.pos_latent[perm])
+        out_p, att_p, _ = attn2(x, y[:, perm].contiguous(), return_att=True)
+        tol = 1e-4 if exact else 2e-2
+        assert (out_p - out).abs().max() <= tol * max(1.0, out.abs().max().item())
+        assert (att_p - att[:, perm]).abs().max() <= (1e-5 if exact else 5e-3)
+        del xn
+
+
+# ---------------------------------------------------------------------------------------------------------
+# end-to-end generator vs the oracle generator
+# ---------------------------------------------------------------------------------------------------------
+def _small_generator(gf, dev, exact, **kw):
+    torch.manual_seed(0)
+    G = gf.Generator(resolution=64, components_num=8, latent_dim=32, fmap_base=2048, fmap_max=128, mapping_layers=4,
+                     exact_fp32=exact, **kw)
+    with torch.no_grad():
+        for n, prm in G.named_parameters():
+            if n.endswith("bias") or n.split(".")[-1] in ("bq", "bk", "bv", "bo", "bq2", "bk2", "bv2"):
+                prm.normal_(0, 0.3)
+            if n.endswith("noise_strength"):
+                prm.fill_(0.1)
+    return G.to(dev).eval()
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["fp32", "default"])
+@pytest.mark.parametrize("duplex", [False, True], ids=["simplex", "duplex"])
+def test_generator_end_to_end(gf, cuda_dev, duplex, exact):
+    """BASELINE config 1 shape class (64x64, k = 8, B = 4): same generator call, activations within tolerance."""
+    G = _small_generator(gf, cuda_dev, exact, kmeans=duplex)
+    assert G.synthesis.num_attention_layers == 8
+    g = torch.Generator().manual_seed(1)
+    z = torch.randn(4, 9, 32, generator=g)
+    with torch.no_grad():
+        img, atts = G(z.to(cuda_dev), return_att=True)
+    ref, ratts, rfeats = og.generator_forward(G.state_dict(), z, resolution=64, components_num=8, latent_dim=32, duplex=duplex,
+                                              mapping_layers=4, return_att=True, return_features=True)
+    assert img.shape == (4, 3, 64, 64) and len(atts) == 8
+    err = (img.double().cpu() - ref).abs()
+    rel_rms = (err.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+    print(f"[e2e] duplex={duplex} exact={exact} img max_abs={err.max().item():.3e} rel_rms={rel_rms:.3e} ref_absmax={ref.abs().max().item():.3f}")
+    # image tolerance: fp32 mode 2e-4 relative RMS / TF32 mode 5e-3 relative RMS (8 stacked TF32 attention layers)
+    assert rel_rms <= (2e-4 if exact else 5e-3)
+    assert err.max().item() <= (2e-3 if exact else 5e-2) * max(1.0, ref.abs().max().item())
+    for a, r in zip(atts, ratts):
+        assert (a.double().cpu() - r).abs().max() <= (1e-3 if exact else 3e-2)
+
+
+def test_run_wrapper_minibatches(gf, cuda_dev):
+    G = _small_generator(gf, cuda_dev, True)
+    z = torch.randn(5, 9, 32)
+    imgs = G.run(z.numpy(), truncation_psi=1.0, randomize_noise=False, minibatch_size=2)
+    with torch.no_grad():
+        ref = G(z.to(cuda_dev)).cpu()
+    assert imgs.shape == (5, 3, 64, 64) and torch.equal(imgs, ref)
+
+
+def test_autograd_matches_oracle(gf, cuda_dev):
+    """Training path: forward = CUDA kernels, backward = autograd through the composite; gradients vs the fp64 oracle."""
+    C, H, W, k, D, p = 64, 8, 16, 4, 16, 16
+    g = torch.Generator().manual_seed(21)
+    x64 = (torch.randn(2, C, H, W, generator=g, dtype=torch.float64)).requires_grad_(True)
+    y64 = torch.randn(2, k, D, generator=g, dtype=torch.float64).requires_grad_(True)
+    w = {n: t.requires_grad_(True) for n, t in ob.init_params(C, D, k, p, "both", False, seed=4, bias_std=0.3).items()}
+    ref, _, _ = ob.transformer_layer(x64, y64, w, integration="both")
+    gout = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+    ref.backward(gout)
+    attn = make_layer(gf, cuda_dev, C, D, k, p, "both", "layer", False, True, True, {n: t.detach() for n, t in w.items()})
+    x = x64.detach().permute(0, 2, 3, 1).contiguous().float().to(cuda_dev).requires_grad_(True)
+    y = y64.detach().float().to(cuda_dev).requires_grad_(True)
+    out, _, _ = attn(x, y)
+    out.backward(gout.permute(0, 2, 3, 1).contiguous().float().to(cuda_dev))
+    check_close(out, ref.detach().permute(0, 2, 3, 1), "simt_fp32", "autograd/forward")
+
+    def rel(a, b):
+        return ((a.double().cpu() - b).norm() / b.norm().clamp_min(1e-30)).item()
+    assert rel(x.grad, x64.grad.permute(0, 2, 3, 1)) < 1e-4
+    assert rel(y.grad, y64.grad) < 1e-4
+    for n in ("wq", "wk", "wv", "wo", "bo", "pos_latent", "wpq"):
+        assert rel(getattr(attn, n).grad, w[n].grad) < 1e-4, n

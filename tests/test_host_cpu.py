@@ -1,0 +1,174 @@
+"""CPU tests of the host side: the C-ABI library loads and exports what include/gf_attn.h declares, descriptor
+validation, the generator plumbing against the oracle, and the world_size-2 (gloo) data-parallel helpers.
+No kernel is launched here (no GPU in this container)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle import bipartite as ob
+from oracle import generator as og
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "gf_attn.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported(gf):
+    lib = gf._lib.load()
+    declared = _declared_symbols()
+    assert declared == sorted(gf._lib.EXPORTS), (declared, gf._lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/gf_attn.h but not exported by libgf_attn.so"
+    assert lib.gf_attn_abi_version() == 1
+
+
+def test_struct_layouts_match_c(gf):
+    assert ctypes.sizeof(gf._lib.GfAttnDesc) == 12 * 4
+    assert ctypes.sizeof(gf._lib.GfAttnWeights) == 20 * ctypes.sizeof(ctypes.c_void_p)
+
+
+def test_sizes_and_validation(gf):
+    L = gf._lib
+    d = L.make_desc(4, 16, 16, 128, 16, 32, pos_dim=32)
+    f1, w1 = L.folded_floats(d), L.workspace_bytes(d)
+    assert f1 > 32 * (128 + 36) and w1 > 4 * 16 * 128 * 4
+    d2 = L.make_desc(8, 16, 16, 128, 16, 32, pos_dim=32)
+    assert L.workspace_bytes(d2) > w1 and L.folded_floats(d2) == f1          # folded weights do not depend on B
+    dd = L.make_desc(4, 16, 16, 128, 16, 32, pos_dim=32, duplex=True)
+    assert L.folded_floats(dd) > f1 and L.workspace_bytes(dd) > w1
+    for bad, msg in [(dict(C=100), "C=100"), (dict(k=33), "k=33"), (dict(heads=2), "num_heads"), (dict(pos_dim=6), "pos_dim")]:
+        kw = dict(B=1, H=8, W=8, C=64, k=4, D=16, heads=1, pos_dim=16)
+        kw.update(bad)
+        desc = L.make_desc(kw["B"], kw["H"], kw["W"], kw["C"], kw["k"], kw["D"], heads=kw["heads"], pos_dim=kw["pos_dim"])
+        with pytest.raises(RuntimeError, match=msg):
+            L.workspace_bytes(desc)
+
+
+def test_no_cpu_path(gf):
+    """The product must fail loudly on CPU tensors: there is no CPU fallback."""
+    attn = gf.BipartiteAttention(64, 16, 4)
+    x = torch.randn(1, 8, 16, 64)
+    y = torch.randn(1, 4, 16)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU path"):
+        attn(x, y)
+
+
+def _small_generator(gf, **kw):
+    torch.manual_seed(0)
+    G = gf.Generator(resolution=32, components_num=4, latent_dim=16, fmap_base=512, fmap_max=64, mapping_layers=2, **kw)
+    with torch.no_grad():  # make every term live: biases, noise strengths, w_avg
+        for n, p in G.named_parameters():
+            if n.endswith("bias") or n.endswith(".bq") or n.endswith(".bk") or n.endswith(".bv") or n.endswith(".bo"):
+                p.normal_(0, 0.3)
+            if n.endswith("noise_strength"):
+                p.fill_(0.1)
+        G.mapping.w_avg.normal_(0, 0.2)
+    return G.double()
+
+
+def test_generator_plumbing_matches_oracle_without_attention(gf):
+    G = _small_generator(gf, transformer=False)
+    z = torch.randn(2, 5, 16, dtype=torch.float64)
+    with torch.no_grad():
+        img = G(z, truncation_psi=0.7)
+    ref = og.generator_forward(G.state_dict(), z, resolution=32, components_num=4, latent_dim=16, truncation_psi=0.7, mapping_layers=2)
+    assert img.shape == (2, 3, 32, 32)
+    assert (img - ref).abs().max() < 1e-9 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("duplex", [False, True])
+def test_generator_plumbing_matches_oracle_with_patched_attention(gf, monkeypatch, duplex):
+    """Host plumbing (layout, layer order, skip connections) checked on CPU by swapping the CUDA op for the oracle."""
+    G = _small_generator(gf, kmeans=duplex, integration="both")
+
+    def fake_forward(self, x, y, centroids=None, return_att=False, out=None):
+        w = {n: p.detach() for n, p in self.named_parameters(recurse=False)}
+        o, att, cen = ob.transformer_layer(x.permute(0, 3, 1, 2), y, w, integration=self.integration, norm=self.norm,
+                                           duplex=self.duplex, use_pos=self.use_pos, return_att=return_att)
+        return o.permute(0, 2, 3, 1).contiguous(), att, cen
+
+    monkeypatch.setattr(gf.BipartiteAttention, "forward", fake_forward)
+    z = torch.randn(2, 5, 16, dtype=torch.float64)
+    with torch.no_grad():
+        img, atts = G(z, return_att=True)
+    ref, ratts = og.generator_forward(G.state_dict(), z, resolution=32, components_num=4, latent_dim=16, integration="both",
+                                      duplex=duplex, mapping_layers=2, return_att=True)
+    assert len(atts) == len(ratts) == G.synthesis.num_attention_layers == 6
+    assert (img - ref).abs().max() < 1e-9 * max(1.0, ref.abs().max().item())
+    for a, r in zip(atts, ratts):
+        assert (a - r).abs().max() < 1e-10
+
+
+def test_attention_layer_count_at_256(gf):
+    """BASELINE config 2: 256x256, attention on both conv layers of every resolution 8..256 -> 12 layers."""
+    from importlib import import_module
+    nets = import_module("gansformer-reproducibility-challenge_b200.networks")
+    assert [nets.nf(r) for r in (4, 8, 16, 32, 64, 128, 256, 512)] == [512, 512, 512, 512, 512, 256, 128, 64]
+    with torch.device("meta"):
+        G = gf.Generator(resolution=256, components_num=16, latent_size=512)
+    assert G.latent_dim == 32 and G.synthesis.num_attention_layers == 12
+    per_image = sum(l.resolution ** 2 * l.weight.shape[0] for l in G.synthesis.layers if l.attention is not None)
+    assert per_image == 30736384          # feature elements per image per pass
+
+
+def _dist_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import gansformer_b200  # noqa: F401
+    from importlib import import_module
+    d = import_module("gansformer-reproducibility-challenge_b200.dist")
+    r, w, _ = d.init_distributed("gloo")
+    g = torch.Generator().manual_seed(1)
+    glob = torch.randn(7, 3, generator=g)
+    mine = d.shard_batch(glob, r, w)
+    gathered = [None] * w
+    dist.all_gather_object(gathered, mine)
+    ok_union = torch.equal(torch.cat(gathered), glob)
+    lin = torch.nn.Linear(3, 2)
+    with torch.no_grad():
+        lin.weight.fill_(0.5)
+        lin.bias.zero_()
+    lin(mine).square().sum().backward()
+    nbytes = d.allreduce_gradients(lin.parameters(), w)
+    mx = d.max_over_ranks(float(r + 1))
+    q.put((r, ok_union, lin.weight.grad.clone(), nbytes, mx))
+    d.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_helpers_world2():
+    """world_size-2 gloo: shards tile the global batch; the all-reduced gradient equals the mean of per-rank gradients."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dist_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(1)
+    glob = torch.randn(7, 3, generator=g)
+    lin = torch.nn.Linear(3, 2)
+    with torch.no_grad():
+        lin.weight.fill_(0.5)
+        lin.bias.zero_()
+    grads = []
+    for lo, hi in ((0, 4), (4, 7)):
+        lin.zero_grad()
+        lin(glob[lo:hi]).square().sum().backward()
+        grads.append(lin.weight.grad.clone())
+    expect = (grads[0] + grads[1]) / 2
+    for r, ok_union, grad, nbytes, mx in res:
+        assert ok_union
+        assert torch.allclose(grad, expect, atol=1e-6)
+        assert nbytes == (6 + 2) * 4 and mx == 2.0
