@@ -1,6 +1,622 @@
-// placeholder, replaced below
+// gf_tc.cu -- stage T on the Blackwell tensor path: TMA-staged tiles, tcgen05 (kind::tf32) MMAs with TMEM
+// accumulators, per-token softmax and LayerNorm on CUDA cores, in-place modulation in shared memory, TMA stores.
+//
+// Replaces, on the reference side (expected src/training/network.py, not in the checkout): the body of
+// transformer_layer (Q projection folded into K', QK^T, softmax, PV), integrate and att_norm.  Same algorithm as
+// oracle/folded.py per_token(); operands of both contractions are rounded to TF32 by the tensor cores.
+//
+// One persistent CTA per SM, 10 warps:
+//   warp 0      TMA producer: X slabs (128 tokens x 32 channels, 16 KB, SWIZZLE_128B) into a ring; K'/V^T per image
+//   warp 1      MMA issuer:   GEMM1  S[128,KP]   = X[128,C] . K'^T            (A,B from smem, D in TMEM)
+//                             GEMM2  G[128,32]   = P[128,KP] . V^T[32 ch,KP]^T per slab (A = P from TMEM, B from smem)
+//   warps 2-9   two groups of 4 warps (one warp per TMEM lane quadrant, thread = token row); group g owns the slabs
+//               with (slab & 1) == g: LayerNorm partial statistics, epilogue y = LN(x)*g (+b) written in place over the
+//               slab, TMA store.  Group 0 also does the softmax (S from TMEM -> P back to TMEM).
+// HBM traffic: X read once, X' written once (the algorithmic bytes of SURVEY 8d).
+#include <cuda.h>
+#include <stdlib.h>
 #include "gf_common.cuh"
+
 namespace gf {
-bool tc_supported(const Layout&, const gf_attn_desc*) { return false; }
-int token_pass_tc(const Layout&, const gf_attn_desc*, const float*, float*, float*, float*, cudaStream_t) { set_error("tc path not built"); return GF_ERR_UNSUPPORTED; }
+
+namespace tc {
+
+constexpr int TILE = 128;                 // tokens per tile (UMMA M)
+constexpr int SLAB_CH = 32;               // channels per slab = one 128-byte swizzle span of fp32
+constexpr int SLAB_BYTES = TILE * SLAB_CH * 4;
+constexpr int MAX_STAGES = 13;
+constexpr int NACC = 4;                   // accumulator stages of GEMM2 in TMEM
+constexpr int NUM_THREADS = 320;
+constexpr int TMEM_COLS = 512;
+// TMEM column map
+constexpr int COL_S = 0;                  // S[2]  : 2 x 32
+constexpr int COL_P = 64;                 // P[2]  : 2 x 32
+constexpr int COL_ACC = 128;              // ACC[4]: 4 x 64
+
+struct Params {
+  float* att; const float* Rt; const float* Ct;
+  int n, H, W, k, Cout, B;
+  int norm_layer;            // 1 = LayerNorm over C, 0 = none
+  int nstages;
+  long long total_tiles;
+  int tiles_per_image;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if ((++spins & 1023u) == 0) {            // watchdog: a protocol bug must trap, not hang the GPU
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 r;\n\t.reg .pred p;\n\t"
+      "elect.sync r|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// UMMA shared-memory descriptor, K-major operand with 8-row swizzle atoms (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1),
+//   [32,46) stride byte offset >> 4 (between 8-row groups), [46,48) version = 1, [61,64) layout type.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW64 = 4;
+
+// Instruction descriptor, kind::tf32, fp32 accumulate, K-major A and B (cute::UMMA::InstrDescriptor).
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] . B[smem]
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------
+// shared-memory carve-up (dynamic smem, 1024-byte aligned base)
+// ---------------------------------------------------------------------------------------------------------
+struct Bars {
+  uint64_t slab_full[MAX_STAGES], slab_empty[MAX_STAGES];
+  uint64_t kv_full, kv_free;
+  uint64_t s_full[2], p_full[2], p_free[2];
+  uint64_t acc_full[NACC], acc_empty[NACC];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+template <int KP, int NS, int MODE>
+struct Cfg {
+  static constexpr int C = NS * SLAB_CH;
+  static constexpr int COUT = MODE == GF_INT_BOTH ? 2 * C : C;
+  static constexpr int KP_BYTES = KP * C * 4;            // K' : NS chunks of [KP rows x 128 B]
+  static constexpr int V_ROW_BYTES = KP * 4;             // V^T row (one channel): KP latents
+  static constexpr int V_BYTES = COUT * V_ROW_BYTES;
+  static constexpr int STATS_BYTES = 2 * 2 * TILE * 2 * 4;  // [tile parity][group][row]{mean, M2}
+  static constexpr int OFF_KP = 0;
+  static constexpr int OFF_V = OFF_KP + KP_BYTES;
+  static constexpr int OFF_STATS = OFF_V + V_BYTES;
+  static constexpr int OFF_BARS = OFF_STATS + STATS_BYTES;
+  static constexpr int OFF_RING = (OFF_BARS + (int)sizeof(Bars) + 1023) / 1024 * 1024;
+  static constexpr int FIXED_BYTES = OFF_RING;
+};
+
+template <int KP, int NS, int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmO,
+                const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const Params P) {
+  using CF = Cfg<KP, NS, MODE>;
+  constexpr int C = CF::C;
+  constexpr int ACC_W = MODE == GF_INT_BOTH ? 64 : 32;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms need 1024 B alignment
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t s_kp = s_base + CF::OFF_KP, s_v = s_base + CF::OFF_V, s_ring = s_base + CF::OFF_RING;
+  Bars* bars = reinterpret_cast<Bars*>(smem + CF::OFF_BARS);
+  float* stats = reinterpret_cast<float*>(smem + CF::OFF_STATS);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nst = P.nstages;
+
+  // contiguous tile range of this CTA
+  const long long tile_beg = (long long)blockIdx.x * P.total_tiles / gridDim.x;
+  const long long tile_end = (long long)(blockIdx.x + 1) * P.total_tiles / gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmX); prefetch_tmap(&tmO); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
+    for (int i = 0; i < nst; ++i) { mbar_init(smem_u32(&bars->slab_full[i]), 1); mbar_init(smem_u32(&bars->slab_empty[i]), 1); }
+    mbar_init(smem_u32(&bars->kv_full), 1); mbar_init(smem_u32(&bars->kv_free), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bars->s_full[i]), 1);
+      mbar_init(smem_u32(&bars->p_full[i]), 4);
+      mbar_init(smem_u32(&bars->p_free[i]), 1);
+    }
+    for (int i = 0; i < NACC; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      long long ctr = 0;       // global slab counter of this CTA
+      int img_changes = 0;
+      int prev_b = -1;
+      for (long long tile = tile_beg; tile < tile_end; ++tile) {
+        const int b = (int)(tile / P.tiles_per_image);
+        if (b != prev_b) {
+          if (prev_b >= 0) mbar_wait(smem_u32(&bars->kv_free), (uint32_t)((img_changes - 1) & 1));
+          const uint32_t bar = smem_u32(&bars->kv_full);
+          mbar_expect_tx(bar, (uint32_t)(CF::KP_BYTES + CF::V_BYTES));
+#pragma unroll
+          for (int s = 0; s < NS; ++s) tma_load_2d(s_kp + s * (KP * 128), &tmK, bar, s * SLAB_CH, b * KP);
+          constexpr int VROWS = CF::COUT < 256 ? CF::COUT : 256;
+#pragma unroll
+          for (int r0 = 0; r0 < CF::COUT; r0 += VROWS) tma_load_2d(s_v + r0 * CF::V_ROW_BYTES, &tmV, bar, 0, b * CF::COUT + r0);
+          prev_b = b;
+          ++img_changes;
+        }
+        const int row0 = (int)(tile * TILE);
+        for (int s = 0; s < NS; ++s, ++ctr) {
+          const int stage = (int)(ctr % nst);
+          const uint32_t phase = (uint32_t)((ctr / nst) & 1);
+          mbar_wait(smem_u32(&bars->slab_empty[stage]), phase ^ 1u);
+          const uint32_t bar = smem_u32(&bars->slab_full[stage]);
+          mbar_expect_tx(bar, SLAB_BYTES);
+          tma_load_2d(s_ring + stage * SLAB_BYTES, &tmX, bar, s * SLAB_CH, row0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t IDESC1 = umma_idesc_tf32(TILE, KP);
+      constexpr uint32_t IDESC2 = umma_idesc_tf32(TILE, 32);
+      constexpr uint32_t V_LAYOUT = KP == 32 ? LAYOUT_SW128 : LAYOUT_SW64;
+      constexpr uint32_t V_SBO = 8 * CF::V_ROW_BYTES;
+      long long ctr = 0, actr = 0;
+      int img_changes = 0, prev_b = -1;
+      long long it = 0;
+      for (long long tile = tile_beg; tile < tile_end; ++tile, ++it) {
+        const int b = (int)(tile / P.tiles_per_image);
+        const int buf = (int)(it & 1);
+        const uint32_t bphase = (uint32_t)((it >> 1) & 1);
+        if (b != prev_b) {
+          mbar_wait(smem_u32(&bars->kv_full), (uint32_t)(img_changes & 1));
+          tc_fence_after();
+          prev_b = b;
+          ++img_changes;
+        }
+        // ---- GEMM1: S[buf] = X . K'^T over all slabs
+        const uint32_t d_s = tmem + COL_S + buf * 32;
+        for (int s = 0; s < NS; ++s, ++ctr) {
+          const int stage = (int)(ctr % nst);
+          mbar_wait(smem_u32(&bars->slab_full[stage]), (uint32_t)((ctr / nst) & 1));
+          tc_fence_after();
+          const uint32_t a_addr = s_ring + stage * SLAB_BYTES, b_addr = s_kp + s * (KP * 128);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_ss(d_s, umma_desc(a_addr + kk * 32, 1024, LAYOUT_SW128), umma_desc(b_addr + kk * 32, 1024, LAYOUT_SW128),
+                    IDESC1, (s | kk) ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&bars->s_full[buf]));
+        // ---- GEMM2: per slab, ACC = P[buf] . V^T (gain | bias)
+        mbar_wait(smem_u32(&bars->p_full[buf]), bphase);
+        tc_fence_after();
+        const uint32_t a_p = tmem + COL_P + buf * 32;
+        for (int s = 0; s < NS; ++s, ++actr) {
+          const int a = (int)(actr % NACC);
+          mbar_wait(smem_u32(&bars->acc_empty[a]), (uint32_t)(((actr / NACC) & 1) ^ 1));
+          tc_fence_after();
+          const uint32_t d_acc = tmem + COL_ACC + a * 64;
+          const uint32_t vg = s_v + s * 32 * CF::V_ROW_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < KP / 8; ++kk)
+            umma_ts(d_acc, a_p + kk * 8, umma_desc(vg + kk * 32, V_SBO, V_LAYOUT), IDESC2, kk ? 1u : 0u);
+          if constexpr (MODE == GF_INT_BOTH) {
+            const uint32_t vb = s_v + (C + s * 32) * CF::V_ROW_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < KP / 8; ++kk)
+              umma_ts(d_acc + 32, a_p + kk * 8, umma_desc(vb + kk * 32, V_SBO, V_LAYOUT), IDESC2, kk ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&bars->acc_full[a]));
+        }
+        umma_commit(smem_u32(&bars->p_free[buf]));
+        const bool last = tile + 1 == tile_end;
+        if (!last && (int)((tile + 1) / P.tiles_per_image) != b) umma_commit(smem_u32(&bars->kv_free));
+      }
+    }
+  } else {
+    // =============================== epilogue warps ===============================
+    const int q = warp & 3;                        // TMEM lane quadrant this warp may access
+    const int g = (warp - 2) >> 2;                 // group: owns slabs with (slab & 1) == g
+    const int row = q * 32 + lane;                 // token row inside the tile
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
+    const int sw = row & 7;                        // 128B-swizzle phase of this row
+    const uint32_t row_off = (uint32_t)row * 128u;
+    int pending_stage = -1;
+    long long it = 0;
+    for (long long tile = tile_beg; tile < tile_end; ++tile, ++it) {
+      const int b = (int)(tile / P.tiles_per_image);
+      const int buf = (int)(it & 1);
+      const uint32_t bphase = (uint32_t)((it >> 1) & 1);
+      const long long ctr0 = it * NS;
+      // ---- 1. LayerNorm statistics over this group's slabs
+      float mean = 0.f, rstd = 1.f;
+      if (P.norm_layer) {
+        float sh = 0.f, sum = 0.f, sumsq = 0.f;
+#pragma unroll 1
+        for (int s = g; s < NS; s += 2) {
+          const long long ctr = ctr0 + s;
+          const int stage = (int)(ctr % nst);
+          mbar_wait(smem_u32(&bars->slab_full[stage]), (uint32_t)((ctr / nst) & 1));
+          const uint8_t* slab = smem + CF::OFF_RING + stage * SLAB_BYTES + row_off;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 x = *reinterpret_cast<const float4*>(slab + ((c ^ sw) << 4));
+            if (s == g && c == 0) sh = x.x;
+            const float d0 = x.x - sh, d1 = x.y - sh, d2 = x.z - sh, d3 = x.w - sh;
+            sum += (d0 + d1) + (d2 + d3);
+            sumsq = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, sumsq))));
+          }
+        }
+        constexpr float CNT = (float)(C / 2);
+        const float mg = sh + sum * (1.f / CNT);
+        const float m2g = fmaxf(sumsq - sum * sum * (1.f / CNT), 0.f);
+        float* st = stats + ((buf * 2 + g) * TILE + row) * 2;
+        st[0] = mg; st[1] = m2g;
+        named_bar_sync(1, 256);
+        const float* so = stats + ((buf * 2 + (g ^ 1)) * TILE + row) * 2;
+        const float mo = so[0], m2o = so[1];
+        mean = 0.5f * (mg + mo);
+        const float dg = mg - mean, dd = mo - mean;
+        const float var = (m2g + m2o + CNT * (dg * dg + dd * dd)) * (1.f / (float)C);
+        rstd = rsqrtf(var + 1e-8f);
+      }
+      // ---- 2. softmax over the latents (group 0): S (TMEM) -> P (TMEM)
+      if (g == 0) {
+        const long long tok = (tile % P.tiles_per_image) * TILE + row;      // token index inside the image
+        const int h = (int)(tok / P.W), w = (int)(tok % P.W);
+        const float4* rt = reinterpret_cast<const float4*>(P.Rt + ((size_t)b * P.H + h) * KP);
+        const float4* ct = reinterpret_cast<const float4*>(P.Ct + ((size_t)b * P.W + w) * KP);
+        float sv[KP];
+#pragma unroll
+        for (int j4 = 0; j4 < KP / 4; ++j4) {
+          const float4 r = __ldg(rt + j4), c = __ldg(ct + j4);
+          sv[j4 * 4 + 0] = r.x + c.x; sv[j4 * 4 + 1] = r.y + c.y; sv[j4 * 4 + 2] = r.z + c.z; sv[j4 * 4 + 3] = r.w + c.w;
+        }
+        mbar_wait(smem_u32(&bars->s_full[buf]), bphase);
+        tc_fence_after();
+        float acc[KP];
+        tmem_ld16(tmem + lane_addr + COL_S + buf * 32, acc);
+        if constexpr (KP == 32) tmem_ld16(tmem + lane_addr + COL_S + buf * 32 + 16, acc + 16);
+        tmem_wait_ld();
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) { sv[j] += acc[j]; mx = fmaxf(mx, sv[j]); }
+        float den = 0.f;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) { sv[j] = exp2f((sv[j] - mx) * 1.4426950408889634f); den += sv[j]; }
+        const float inv = 1.f / den;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) sv[j] *= inv;
+        if (P.att) {
+          float* a = P.att + ((size_t)b * P.n + tok) * P.k;
+#pragma unroll
+          for (int j = 0; j < KP; ++j) if (j < P.k) a[j] = sv[j];
+        }
+        mbar_wait(smem_u32(&bars->p_free[buf]), bphase ^ 1u);       // GEMM2 of the tile two iterations back is done
+        tc_fence_after();
+        tmem_st16(tmem + lane_addr + COL_P + buf * 32, sv);
+        if constexpr (KP == 32) tmem_st16(tmem + lane_addr + COL_P + buf * 32 + 16, sv + 16);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->p_full[buf]));
+      }
+      // ---- 3. epilogue of this group's slabs: y = LN(x) * gain (+ bias), in place, TMA store
+      const float mr = -mean * rstd;
+#pragma unroll 1
+      for (int s = g; s < NS; s += 2) {
+        const long long ctr = ctr0 + s;
+        const int stage = (int)(ctr % nst);
+        const int a = (int)(ctr % NACC);
+        if (!P.norm_layer) mbar_wait(smem_u32(&bars->slab_full[stage]), (uint32_t)((ctr / nst) & 1));
+        mbar_wait(smem_u32(&bars->acc_full[a]), (uint32_t)((ctr / NACC) & 1));
+        tc_fence_after();
+        float gv[32], bv[MODE == GF_INT_BOTH ? 32 : 1];
+        const uint32_t t_acc = tmem + lane_addr + COL_ACC + a * 64;
+        tmem_ld16(t_acc, gv);
+        tmem_ld16(t_acc + 16, gv + 16);
+        if constexpr (MODE == GF_INT_BOTH) { tmem_ld16(t_acc + 32, bv); tmem_ld16(t_acc + 48, bv + 16); }
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[a]));
+        uint8_t* slab = smem + CF::OFF_RING + stage * SLAB_BYTES + row_off;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4* px = reinterpret_cast<float4*>(slab + ((c ^ sw) << 4));
+          float4 x = *px;
+          float xn0 = fmaf(x.x, rstd, mr), xn1 = fmaf(x.y, rstd, mr), xn2 = fmaf(x.z, rstd, mr), xn3 = fmaf(x.w, rstd, mr);
+          if constexpr (MODE == GF_INT_MUL) {
+            x.x = xn0 * gv[c * 4 + 0]; x.y = xn1 * gv[c * 4 + 1]; x.z = xn2 * gv[c * 4 + 2]; x.w = xn3 * gv[c * 4 + 3];
+          } else if constexpr (MODE == GF_INT_ADD) {
+            x.x = xn0 + gv[c * 4 + 0]; x.y = xn1 + gv[c * 4 + 1]; x.z = xn2 + gv[c * 4 + 2]; x.w = xn3 + gv[c * 4 + 3];
+          } else {
+            x.x = fmaf(xn0, gv[c * 4 + 0], bv[c * 4 + 0]); x.y = fmaf(xn1, gv[c * 4 + 1], bv[c * 4 + 1]);
+            x.z = fmaf(xn2, gv[c * 4 + 2], bv[c * 4 + 2]); x.w = fmaf(xn3, gv[c * 4 + 3], bv[c * 4 + 3]);
+          }
+          *px = x;
+        }
+        fence_proxy_async();                       // generic-proxy writes -> visible to the TMA (async proxy)
+        named_bar_sync(2 + g, 128);
+        if (leader) {
+          tma_store_2d(&tmO, s_ring + stage * SLAB_BYTES, s * SLAB_CH, (int)(tile * TILE));
+          tma_commit();
+          if (pending_stage >= 0) {
+            tma_wait_read1();                      // the previous store has finished reading its slab
+            mbar_arrive(smem_u32(&bars->slab_empty[pending_stage]));
+          }
+          pending_stage = stage;
+        }
+      }
+      if (leader && pending_stage >= 0) {          // drain at tile end (keeps a ring of exactly one tile deadlock-free)
+        tma_wait_read0();
+        mbar_arrive(smem_u32(&bars->slab_empty[pending_stage]));
+        pending_stage = -1;
+      }
+    }
+    if (leader) tma_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major [rows, cols] tensor, box [box_rows, box_cols]
+static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return GF_ERR_CUDA; }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * sizeof(float)};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu box=%ux%u)", (int)r,
+                                     (unsigned long long)rows, (unsigned long long)cols, box_rows, box_cols); return GF_ERR_CUDA; }
+  return GF_OK;
+}
+
+static int device_smem_optin() {
+  static int v = -1;
+  if (v < 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) v = 0;
+  }
+  return v;
+}
+static int device_sms() {
+  static int v = -1;
+  if (v < 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) v = 0;
+  }
+  return v;
+}
+
+template <int KP, int NS, int MODE>
+static int stages_for(int smem_limit) {
+  int st = (smem_limit - Cfg<KP, NS, MODE>::FIXED_BYTES - 1024) / SLAB_BYTES;   // 1024: worst-case base alignment slack
+  return st > MAX_STAGES ? MAX_STAGES : st;
+}
+
+template <int KP, int NS, int MODE>
+static int launch(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, cudaStream_t st) {
+  using CF = Cfg<KP, NS, MODE>;
+  const int nst = stages_for<KP, NS, MODE>(device_smem_optin());
+  if (nst < NS) { set_error("tcgen05 path: shared memory too small for C=%d KP=%d mode=%d", L.C, KP, MODE); return GF_ERR_UNSUPPORTED; }
+  CUtensorMap tmX, tmO, tmK, tmV;
+  int rc;
+  const uint64_t rows = (uint64_t)L.B * L.n;
+  if ((rc = make_map(&tmX, X, rows, L.C, TILE, SLAB_CH, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map(&tmO, Xout, rows, L.C, TILE, SLAB_CH, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map(&tmK, ws + L.w_Kp, (uint64_t)L.B * KP, L.C, KP, SLAB_CH, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  const uint32_t vrows = CF::COUT < 256 ? CF::COUT : 256;
+  if ((rc = make_map(&tmV, ws + L.w_Vt, (uint64_t)L.B * CF::COUT, KP, vrows, KP, KP == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  Params P;
+  P.att = att; P.Rt = ws + L.w_Rt; P.Ct = ws + L.w_Ct;
+  P.n = L.n; P.H = L.H; P.W = L.W; P.k = L.k; P.Cout = L.Cout; P.B = L.B;
+  P.norm_layer = d->norm == GF_NORM_LAYER ? 1 : 0;
+  P.nstages = nst;
+  P.tiles_per_image = L.n / TILE;
+  P.total_tiles = (long long)L.B * P.tiles_per_image;
+  const int smem_bytes = CF::FIXED_BYTES + nst * SLAB_BYTES + 1024;
+  auto kern = token_tc_kernel<KP, NS, MODE>;
+  GF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  long long grid = device_sms();
+  if (grid > P.total_tiles) grid = P.total_tiles;
+  kern<<<(unsigned)grid, NUM_THREADS, smem_bytes, st>>>(tmX, tmO, tmK, tmV, P);
+  GF_LAUNCH_OK();
+  set_path(GF_PATH_TCGEN05_TF32);
+  return GF_OK;
+}
+
+template <int KP, int NS>
+static int launch_mode(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, cudaStream_t st) {
+  switch (d->integration) {
+    case GF_INT_MUL: return launch<KP, NS, GF_INT_MUL>(L, d, X, Xout, att, ws, st);
+    case GF_INT_ADD: return launch<KP, NS, GF_INT_ADD>(L, d, X, Xout, att, ws, st);
+    default: return launch<KP, NS, GF_INT_BOTH>(L, d, X, Xout, att, ws, st);
+  }
+}
+
+template <int KP, int NS>
+static bool fits(int integration, int limit) {
+  switch (integration) {
+    case GF_INT_MUL: return stages_for<KP, NS, GF_INT_MUL>(limit) >= NS;
+    case GF_INT_ADD: return stages_for<KP, NS, GF_INT_ADD>(limit) >= NS;
+    default: return stages_for<KP, NS, GF_INT_BOTH>(limit) >= NS;
+  }
+}
+
+}  // namespace tc
+
+bool tc_supported(const Layout& L, const gf_attn_desc* d) {
+  static const bool disabled = getenv("GF_DISABLE_TC") != nullptr;
+  if (disabled) return false;
+  if (L.C != 64 && L.C != 128 && L.C != 256) return false;
+  if (L.n % tc::TILE != 0) return false;
+  if (d->norm != GF_NORM_LAYER && d->norm != GF_NORM_NONE) return false;
+  if ((long long)L.B * L.n > 0x7fffffffll) return false;
+  const int limit = tc::device_smem_optin();
+  const int ns = L.C / 32;
+  if (L.KP == 16) return ns == 2 ? tc::fits<16, 2>(d->integration, limit) : ns == 4 ? tc::fits<16, 4>(d->integration, limit) : tc::fits<16, 8>(d->integration, limit);
+  return ns == 2 ? tc::fits<32, 2>(d->integration, limit) : ns == 4 ? tc::fits<32, 4>(d->integration, limit) : tc::fits<32, 8>(d->integration, limit);
+}
+
+int token_pass_tc(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, cudaStream_t st) {
+  const int ns = L.C / 32;
+  if (L.KP == 16) {
+    if (ns == 2) return tc::launch_mode<16, 2>(L, d, X, Xout, att, ws, st);
+    if (ns == 4) return tc::launch_mode<16, 4>(L, d, X, Xout, att, ws, st);
+    return tc::launch_mode<16, 8>(L, d, X, Xout, att, ws, st);
+  }
+  if (ns == 2) return tc::launch_mode<32, 2>(L, d, X, Xout, att, ws, st);
+  if (ns == 4) return tc::launch_mode<32, 4>(L, d, X, Xout, att, ws, st);
+  return tc::launch_mode<32, 8>(L, d, X, Xout, att, ws, st);
+}
+
+}  // namespace gf

@@ -278,7 +278,9 @@ def test_run_wrapper_minibatches(gf, cuda_dev):
     imgs = G.run(z.numpy(), truncation_psi=1.0, randomize_noise=False, minibatch_size=2)
     with torch.no_grad():
         ref = G(z.to(cuda_dev)).cpu()
-    assert imgs.shape == (5, 3, 64, 64) and torch.equal(imgs, ref)
+    assert imgs.shape == (5, 3, 64, 64)
+    # cuDNN may pick different algorithms for minibatch 2 vs 5: equal up to fp32 rounding, not bit for bit
+    assert (imgs - ref).abs().max() <= 1e-4 * max(1.0, ref.abs().max().item())
 
 
 def test_autograd_matches_oracle(gf, cuda_dev):
