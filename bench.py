@@ -211,11 +211,13 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()              # ncu --profile-from-start off captures exactly the timed steps
     ev0.record()
     for _ in range(args.steps):
         step_resident()
     ev1.record()
     torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
     dist_mod.barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = gf._lib.launch_count() - launches0

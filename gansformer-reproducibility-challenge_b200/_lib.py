@@ -25,7 +25,10 @@ WEIGHT_FIELDS = ("wq", "bq", "wpq", "wk", "bk", "wpk", "wv", "bv", "wo", "bo", "
 # every symbol include/gf_attn.h declares (tests check the .so exports each of them)
 EXPORTS = ("gf_attn_abi_version", "gf_last_error", "gf_attn_last_path", "gf_attn_folded_floats",
            "gf_attn_fold_weights", "gf_attn_workspace_bytes", "gf_attn_prologue", "gf_attn_simplex_fwd",
-           "gf_attn_duplex_fwd", "gf_attn_norm_stats", "gf_attn_launch_count")
+           "gf_attn_duplex_fwd", "gf_attn_norm_stats", "gf_attn_launch_count",
+           "gf_attn_simplex_fwd_ex", "gf_attn_duplex_fwd_ex")
+# include/gf_ops.h
+OPS_EXPORTS = ("gf_chan_scale_nhwc", "gf_blur_up_nhwc", "gf_upsample2x_nchw", "gf_bias_act_nhwc")
 
 
 class GfAttnDesc(ctypes.Structure):
@@ -35,6 +38,11 @@ class GfAttnDesc(ctypes.Structure):
 
 class GfAttnWeights(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in WEIGHT_FIELDS]
+
+
+class GfAttnPostop(ctypes.Structure):
+    _fields_ = [("bias", c_void_p), ("noise", c_void_p), ("strength", c_void_p), ("noise_bstride", ctypes.c_longlong),
+                ("act", c_int32), ("gain", ctypes.c_float)]
 
 
 _lib: Optional[ctypes.CDLL] = None
@@ -62,6 +70,16 @@ def load() -> ctypes.CDLL:
     lib.gf_attn_duplex_fwd.argtypes = [POINTER(GfAttnDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p]
     lib.gf_attn_norm_stats.argtypes = [POINTER(GfAttnDesc), c_void_p, c_void_p, c_void_p]
+    lib.gf_attn_simplex_fwd_ex.argtypes = [POINTER(GfAttnDesc), c_void_p, c_void_p, c_void_p, c_void_p, POINTER(GfAttnPostop), c_void_p]
+    lib.gf_attn_duplex_fwd_ex.argtypes = [POINTER(GfAttnDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, POINTER(GfAttnPostop), c_void_p]
+    lib.gf_chan_scale_nhwc.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
+    lib.gf_blur_up_nhwc.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, ctypes.c_float, c_void_p]
+    lib.gf_upsample2x_nchw.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+    lib.gf_bias_act_nhwc.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_int,
+                                     c_int, ctypes.c_float, c_void_p]
+    for name in OPS_EXPORTS:
+        getattr(lib, name).restype = c_int
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("gf_last_error", "gf_attn_launch_count"):

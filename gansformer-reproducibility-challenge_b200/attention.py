@@ -83,8 +83,11 @@ def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[s
                                 integration: str = "mul", norm: Optional[str] = "layer", duplex: bool = False,
                                 num_heads: int = 1, use_pos: bool = True, return_att: bool = False,
                                 centroids: Optional[torch.Tensor] = None, exact_fp32: bool = False,
-                                out: Optional[torch.Tensor] = None, weights_version=None):
-    """x [B,H,W,C] channels-last fp32 (CUDA), y [B,k,D].  Returns (x', att [B,k,H,W] | None, centroids | None)."""
+                                out: Optional[torch.Tensor] = None, weights_version=None, postop: Optional[dict] = None):
+    """x [B,H,W,C] channels-last fp32 (CUDA), y [B,k,D].  Returns (x', att [B,k,H,W] | None, centroids | None).
+
+    postop (optional): dict(bias [C] | None, noise [H*W] or [B,H*W] | None, strength 0-d tensor | None, act 'lrelu' |
+    'linear', gain float) -- the noise + fused_bias_act step that follows the block, fused into the kernel's store."""
     lib = _lib.load()
     if x.dim() != 4:
         raise ValueError("x must be [B, H, W, C] (channels-last)")
@@ -130,6 +133,26 @@ def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[s
         else:
             _check_tensor(out, "out", dev)
         att = torch.empty((B, H * W, k), dtype=torch.float32, device=dev) if return_att else None
+        post_ref = None
+        if postop is not None:
+            pst = _lib.GfAttnPostop()
+            keep = []
+            for fld in ("bias", "noise", "strength"):
+                t = postop.get(fld)
+                if t is not None:
+                    t = t.detach()
+                    _check_tensor(t, "postop." + fld, dev)
+                    keep.append(t)
+                    setattr(pst, fld, t.data_ptr())
+            nz = postop.get("noise")
+            if nz is not None and nz.numel() not in (H * W, B * H * W):
+                raise ValueError("postop.noise must have H*W or B*H*W elements")
+            if postop.get("bias") is not None and postop["bias"].numel() != C:
+                raise ValueError("postop.bias must have C elements")
+            pst.noise_bstride = H * W if (nz is not None and nz.numel() == B * H * W and B > 1) else 0
+            pst.act = {"linear": 0, "lrelu": 1}[postop.get("act", "lrelu")]
+            pst.gain = float(postop.get("gain", 1.0))
+            post_ref = ctypes.byref(pst)
         timer = STAGE_TIMER
         if timer is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -141,17 +164,18 @@ def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[s
             else:
                 _check_tensor(centroids, "centroids", dev)
                 cen = centroids
-            _lib.check(lib.gf_attn_duplex_fwd(ctypes.byref(desc), x.data_ptr(), y.data_ptr(), plan.folded.data_ptr(),
-                                              out.data_ptr(), _ptr(att), cen.data_ptr(), ws.data_ptr(), stream),
-                       "gf_attn_duplex_fwd")
+            _lib.check(lib.gf_attn_duplex_fwd_ex(ctypes.byref(desc), x.data_ptr(), y.data_ptr(), plan.folded.data_ptr(),
+                                                 out.data_ptr(), _ptr(att), cen.data_ptr(), ws.data_ptr(), post_ref, stream),
+                       "gf_attn_duplex_fwd_ex")
         else:
             cen = None
             _lib.check(lib.gf_attn_prologue(ctypes.byref(desc), y.data_ptr(), plan.folded.data_ptr(), ws.data_ptr(), stream),
                        "gf_attn_prologue")
             if timer is not None:
                 ev0.record()
-            _lib.check(lib.gf_attn_simplex_fwd(ctypes.byref(desc), x.data_ptr(), out.data_ptr(), _ptr(att), ws.data_ptr(), stream),
-                       "gf_attn_simplex_fwd")
+            _lib.check(lib.gf_attn_simplex_fwd_ex(ctypes.byref(desc), x.data_ptr(), out.data_ptr(), _ptr(att), ws.data_ptr(),
+                                                  post_ref, stream),
+                       "gf_attn_simplex_fwd_ex")
         if timer is not None:
             ev1.record()
             timer.records.append((ev0, ev1, 2 * 4 * B * H * W * C))
@@ -187,15 +211,17 @@ class BipartiteAttention(nn.Module):
         return {n: p for n, p in self.named_parameters(recurse=False)}
 
     def forward(self, x: torch.Tensor, y: torch.Tensor, centroids: Optional[torch.Tensor] = None,
-                return_att: bool = False, out: Optional[torch.Tensor] = None):
+                return_att: bool = False, out: Optional[torch.Tensor] = None, postop: Optional[dict] = None):
         """x [B,H,W,C] channels-last, y [B,k,D] -> (x', att [B,k,H,W] | None, centroids [B,k,C] | None)."""
         if torch.is_grad_enabled() and (x.requires_grad or y.requires_grad or any(p.requires_grad for p in self.parameters())):
+            if postop is not None:
+                raise RuntimeError("the fused post-op is inference-only; apply noise/bias/activation outside when training")
             from .autograd import bipartite_attention_autograd
             return bipartite_attention_autograd(self, x, y, centroids, return_att)
         return bipartite_attention_forward(x, y, self.param_dict(), self._plan, integration=self.integration,
                                            norm=self.norm, duplex=self.duplex, num_heads=self.num_heads,
                                            use_pos=self.use_pos, return_att=return_att, centroids=centroids,
-                                           exact_fp32=self.exact_fp32, out=out)
+                                           exact_fp32=self.exact_fp32, out=out, postop=postop)
 
 
 _FUNCTIONAL_PLANS: Dict[int, _Plan] = {}

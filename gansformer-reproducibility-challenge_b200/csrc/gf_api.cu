@@ -36,11 +36,13 @@ static int check_device() {
   return GF_OK;
 }
 
-static int token_pass(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, cudaStream_t st) {
+static int token_pass(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws,
+                      const gf_attn_postop* post, cudaStream_t st) {
   int rc;
+  if (post && (post->act < 0 || post->act > 1)) { set_error("postop: act must be 0 (linear) or 1 (lrelu), got %d", post->act); return GF_ERR_INVALID; }
   if ((rc = norm_stats(L, d, X, ws, st))) return rc;
-  if (!(d->flags & GF_FLAG_FP32_EXACT) && tc_supported(L, d)) return token_pass_tc(L, d, X, Xout, att, ws, st);
-  return token_pass_simt(L, d, X, Xout, att, ws, st);
+  if (!(d->flags & GF_FLAG_FP32_EXACT) && tc_supported(L, d)) return token_pass_tc(L, d, X, Xout, att, ws, post, st);
+  return token_pass_simt(L, d, X, Xout, att, ws, post, st);
 }
 
 }  // namespace gf
@@ -101,16 +103,26 @@ int gf_attn_norm_stats(const gf_attn_desc* desc, const float* X, void* ws, void*
 }
 
 int gf_attn_simplex_fwd(const gf_attn_desc* desc, const float* X, float* Xout, float* att, void* ws, void* stream) {
+  return gf_attn_simplex_fwd_ex(desc, X, Xout, att, ws, nullptr, stream);
+}
+
+int gf_attn_simplex_fwd_ex(const gf_attn_desc* desc, const float* X, float* Xout, float* att, void* ws,
+                           const gf_attn_postop* post, void* stream) {
   Layout L;
   int rc = make_layout(desc, &L);
   if (rc) return rc;
   if (!X || !Xout || !ws) { set_error("gf_attn_simplex_fwd: null pointer"); return GF_ERR_INVALID; }
   if ((rc = check_device())) return rc;
-  return token_pass(L, desc, X, Xout, att, (float*)ws, (cudaStream_t)stream);
+  return token_pass(L, desc, X, Xout, att, (float*)ws, post, (cudaStream_t)stream);
 }
 
 int gf_attn_duplex_fwd(const gf_attn_desc* desc, const float* X, const float* Y, const float* folded,
                        float* Xout, float* att, float* centroids_inout, void* ws_, void* stream) {
+  return gf_attn_duplex_fwd_ex(desc, X, Y, folded, Xout, att, centroids_inout, ws_, nullptr, stream);
+}
+
+int gf_attn_duplex_fwd_ex(const gf_attn_desc* desc, const float* X, const float* Y, const float* folded,
+                          float* Xout, float* att, float* centroids_inout, void* ws_, const gf_attn_postop* post, void* stream) {
   Layout L;
   int rc = make_layout(desc, &L);
   if (rc) return rc;
@@ -128,7 +140,7 @@ int gf_attn_duplex_fwd(const gf_attn_desc* desc, const float* X, const float* Y,
       return rc;
   }
   if ((rc = prologue(L, desc, Y, centroids_inout, L.C, folded, ws, st))) return rc;
-  return token_pass(L, desc, X, Xout, att, ws, st);
+  return token_pass(L, desc, X, Xout, att, ws, post, st);
 }
 
 }  // extern "C"

@@ -68,11 +68,11 @@ int gemm(cudaStream_t st, int M, int N, int K, const float* A, int lda, bool ta,
          float* Cm, int ldc, float alpha, const float* E = nullptr, int lde = 0, int emod = 1, const float* v = nullptr);
 
 // ---- stage T kernels ----------------------------------------------------------------------------------
-int token_pass_simt(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, cudaStream_t st);
+int token_pass_simt(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, const gf_attn_postop* post, cudaStream_t st);
 int norm_stats(const Layout& L, const gf_attn_desc* d, const float* X, float* ws, cudaStream_t st);
 int centroid_pass_simt(const Layout& L, const gf_attn_desc* d, const float* X, float* ws, cudaStream_t st);
 // tcgen05 / TMA path (gf_tc.cu).  tc_supported() says whether the shape is served by it.
 bool tc_supported(const Layout& L, const gf_attn_desc* d);
-int token_pass_tc(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, cudaStream_t st);
+int token_pass_tc(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, const gf_attn_postop* post, cudaStream_t st);
 
 }  // namespace gf

@@ -238,12 +238,25 @@ int fold_weights(const Layout& L, const gf_attn_desc* d, const gf_attn_weights* 
 // stage I: per-image tables
 // ------------------------------------------------------------------------------------------------------
 // grid (nblk, B).  blockIdx.x == 0: positional logit tables Rt/Ct of image b.  blockIdx.x >= 1: Kp and (optionally) Vt.
+// fp32 -> nearest-even TF32 (10 mantissa bits).  The tensor cores TRUNCATE fp32 operands to TF32; pre-rounding the
+// small operands (K', V^T, and P in the kernel) makes that truncation a no-op for them and halves their error.
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t b = __float_as_uint(v);
+  if ((b & 0x7f800000u) == 0x7f800000u) return v;      // inf / nan untouched
+  b = (b + 0xFFFu + ((b >> 13) & 1u)) & 0xFFFFE000u;
+  return __uint_as_float(b);
+}
+// Truncation of X toward zero biases every product x*K' by E[eps] = 2^-11 / ln 2 * (1/2) = 0.7213 * 2^-11 (log-uniform
+// mantissa); K' is scaled up by that factor so the logits are unbiased.
+#define GF_TF32_TRUNC_COMP 1.000352220f
+
 __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ kpall, const float* __restrict__ Y,
                                                        const float* __restrict__ AV, const float* __restrict__ CV,
                                                        const float* __restrict__ ROW, const float* __restrict__ COL,
                                                        float* __restrict__ Kp, float* __restrict__ Vt,
                                                        float* __restrict__ Rt, float* __restrict__ Ct,
-                                                       int H, int W, int C, int k, int D, int p, int KP, int Cout, int LDK) {
+                                                       int H, int W, int C, int k, int D, int p, int KP, int Cout, int LDK,
+                                                       int tf32) {
   const int b = blockIdx.y;
   const float* kp = kpall + (size_t)b * k * LDK;
   if (blockIdx.x == 0) {
@@ -275,7 +288,9 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
   for (int i = (blockIdx.x - 1) * blockDim.x + threadIdx.x; i < nK + nV; i += stride) {
     if (i < nK) {
       const int j = i / C, c = i % C;
-      Kp[(size_t)b * nK + i] = j < k ? kp[(size_t)j * LDK + c] : 0.f;
+      float v = j < k ? kp[(size_t)j * LDK + c] : 0.f;
+      if (tf32) v = round_tf32(v * GF_TF32_TRUNC_COMP);
+      Kp[(size_t)b * nK + i] = v;
     } else {
       const int e = i - nK, c = e / KP, j = e % KP;
       float acc = 0.f;
@@ -284,15 +299,16 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
         for (int dd = 0; dd < D; ++dd) acc = fmaf(yj[dd], AV[(size_t)dd * Cout + c], acc);
         acc += CV[c];
       }
-      Vt[(size_t)b * nV + e] = acc;
+      Vt[(size_t)b * nV + e] = tf32 ? round_tf32(acc) : acc;
     }
   }
 }
 
 int prologue(const Layout& L, const gf_attn_desc* d, const float* Y, const float* key_source, int kdim,
              const float* f, float* ws, cudaStream_t st) {
-  (void)d;
   int rc;
+  // operands of the tcgen05 TF32 contractions are pre-rounded here; the fp32-FMA kernel gets them untouched
+  const int tf32 = (!(d->flags & GF_FLAG_FP32_EXACT) && tc_supported(L, d)) ? 1 : 0;
   // KPALL [B*k, LDK] = key_source @ AK + CK
   if ((rc = gemm(st, L.B * L.k, L.LDK, kdim, key_source, kdim, false, f + L.f_AK, L.LDK, false, ws + L.w_KPALL, L.LDK, 1.f,
                  f + L.f_CK, L.LDK, L.k)))
@@ -301,7 +317,7 @@ int prologue(const Layout& L, const gf_attn_desc* d, const float* Y, const float
   int nblk = 1 + (nel + 256 * 8 - 1) / (256 * 8);
   finalize_kernel<<<dim3(nblk, L.B), 256, 0, st>>>(ws + L.w_KPALL, Y, f + L.f_AV, f + L.f_CV, f + L.f_ROW, f + L.f_COL,
                                                    ws + L.w_Kp, ws + L.w_Vt, ws + L.w_Rt, ws + L.w_Ct,
-                                                   L.H, L.W, L.C, L.k, L.D, L.p, L.KP, L.Cout, L.LDK);
+                                                   L.H, L.W, L.C, L.k, L.D, L.p, L.KP, L.Cout, L.LDK, tf32);
   GF_LAUNCH_OK();
   return GF_OK;
 }
@@ -317,7 +333,7 @@ int duplex_tables(const Layout& L, const gf_attn_desc* d, const float* Y, const 
   int nblk = 1 + (nel + 256 * 8 - 1) / (256 * 8);
   finalize_kernel<<<dim3(nblk, L.B), 256, 0, st>>>(ws + L.w_MALL, Y, nullptr, nullptr, f + L.f_ROW, f + L.f_COL,
                                                    ws + L.w_M, nullptr, ws + L.w_Rt2, ws + L.w_Ct2,
-                                                   L.H, L.W, L.C, L.k, L.D, L.p, L.KP, L.Cout, L.LDK);
+                                                   L.H, L.W, L.C, L.k, L.D, L.p, L.KP, L.Cout, L.LDK, 0);
   GF_LAUNCH_OK();
   return GF_OK;
 }

@@ -18,6 +18,8 @@ struct TokenParams {
   const float* nscale; const float* nshift;
   int n, H, W, C, k, Cout;
   int norm, integration;
+  // fused epilogue (gf_attn_postop)
+  const float* pbias; const float* pnoise; const float* pstrength; long long pnoise_bstride; int pact; float pgain; int has_post;
 };
 
 __device__ __forceinline__ void load_x_chunk(float (*xs)[XS], const float* __restrict__ Xb, int t0, int n, int C, int c0) {
@@ -36,7 +38,7 @@ __global__ void __launch_bounds__(TM) token_simt_kernel(const TokenParams P) {
   __shared__ __align__(16) float xs[TM][XS];
   __shared__ __align__(16) float ks[KP][CH];        // K' chunk, later reused for V^T chunks [CH][KP] (gain)
   __shared__ __align__(16) float vs2[CH][KP];       // bias half of V^T ("both")
-  __shared__ float nsc[CH], nsh[CH];
+  __shared__ float nsc[CH], nsh[CH], pbs[CH];
 
   const int b = blockIdx.y, t0 = blockIdx.x * TM, tid = threadIdx.x, t = t0 + tid;
   const int n = P.n, C = P.C;
@@ -106,6 +108,9 @@ __global__ void __launch_bounds__(TM) token_simt_kernel(const TokenParams P) {
   }
   const bool affine = P.norm == GF_NORM_INSTANCE || P.norm == GF_NORM_BATCH;
   const int integ = P.integration;
+  float pnz = 0.f;
+  if (P.has_post && P.pnoise && valid)
+    pnz = __ldg(P.pnoise + (size_t)b * P.pnoise_bstride + t) * (P.pstrength ? __ldg(P.pstrength) : 1.f);
   float (*vs)[KP] = reinterpret_cast<float (*)[KP]>(&ks[0][0]);   // [CH][KP] view of the same bytes
 
   // ---- sweep 2: control signal, normalise, modulate, store -----------------------------------------
@@ -121,6 +126,7 @@ __global__ void __launch_bounds__(TM) token_simt_kernel(const TokenParams P) {
       nsc[tid] = P.nscale[(size_t)b * C + c0 + tid];
       nsh[tid] = P.nshift[(size_t)b * C + c0 + tid];
     }
+    if (P.has_post && tid < CH) pbs[tid] = P.pbias ? P.pbias[c0 + tid] : 0.f;
     __syncthreads();
 #pragma unroll 4
     for (int cc = 0; cc < CH; ++cc) {
@@ -146,6 +152,11 @@ __global__ void __launch_bounds__(TM) token_simt_kernel(const TokenParams P) {
         }
         y = fmaf(xn, g, bb);
       }
+      if (P.has_post) {
+        y += pnz + pbs[cc];
+        if (P.pact == 1) y = fmaxf(y, 0.2f * y);
+        y *= P.pgain;
+      }
       xs[tid][cc] = y;
     }
     __syncthreads();
@@ -158,13 +169,16 @@ __global__ void __launch_bounds__(TM) token_simt_kernel(const TokenParams P) {
   }
 }
 
-int token_pass_simt(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, cudaStream_t st) {
+int token_pass_simt(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, const gf_attn_postop* post, cudaStream_t st) {
   TokenParams P;
   P.X = X; P.Xout = Xout; P.att = att;
   P.Kp = ws + L.w_Kp; P.Vt = ws + L.w_Vt; P.Rt = ws + L.w_Rt; P.Ct = ws + L.w_Ct;
   P.nscale = ws + L.w_NSCALE; P.nshift = ws + L.w_NSHIFT;
   P.n = L.n; P.H = L.H; P.W = L.W; P.C = L.C; P.k = L.k; P.Cout = L.Cout;
   P.norm = d->norm; P.integration = d->integration;
+  P.has_post = post ? 1 : 0;
+  P.pbias = post ? post->bias : nullptr; P.pnoise = post ? post->noise : nullptr; P.pstrength = post ? post->strength : nullptr;
+  P.pnoise_bstride = post ? post->noise_bstride : 0; P.pact = post ? post->act : 0; P.pgain = post ? post->gain : 1.f;
   dim3 grid((L.n + TM - 1) / TM, L.B);
   if (L.KP == 16) token_simt_kernel<16><<<grid, TM, 0, st>>>(P);
   else token_simt_kernel<32><<<grid, TM, 0, st>>>(P);

@@ -40,6 +40,8 @@ struct Params {
   int nstages;
   long long total_tiles;
   int tiles_per_image;
+  // fused epilogue (gf_attn_postop)
+  const float* pbias; const float* pnoise; const float* pstrength; long long pnoise_bstride; int pact; float pgain; int has_post;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -193,10 +195,12 @@ struct Cfg {
   static constexpr int V_ROW_BYTES = KP * 4;             // V^T row (one channel): KP latents
   static constexpr int V_BYTES = COUT * V_ROW_BYTES;
   static constexpr int STATS_BYTES = 2 * 2 * TILE * 2 * 4;  // [tile parity][group][row]{mean, M2}
+  static constexpr int PBIAS_BYTES = C * 4;                 // post-op bias vector
   static constexpr int OFF_KP = 0;
   static constexpr int OFF_V = OFF_KP + KP_BYTES;
   static constexpr int OFF_STATS = OFF_V + V_BYTES;
-  static constexpr int OFF_BARS = OFF_STATS + STATS_BYTES;
+  static constexpr int OFF_PBIAS = OFF_STATS + STATS_BYTES;
+  static constexpr int OFF_BARS = OFF_PBIAS + PBIAS_BYTES;
   static constexpr int OFF_RING = (OFF_BARS + (int)sizeof(Bars) + 1023) / 1024 * 1024;
   static constexpr int FIXED_BYTES = OFF_RING;
 };
@@ -214,6 +218,9 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const uint32_t s_kp = s_base + CF::OFF_KP, s_v = s_base + CF::OFF_V, s_ring = s_base + CF::OFF_RING;
   Bars* bars = reinterpret_cast<Bars*>(smem + CF::OFF_BARS);
   float* stats = reinterpret_cast<float*>(smem + CF::OFF_STATS);
+  float* pbias_s = reinterpret_cast<float*>(smem + CF::OFF_PBIAS);
+  if (P.has_post)
+    for (int i = threadIdx.x; i < C; i += NUM_THREADS) pbias_s[i] = P.pbias ? P.pbias[i] : 0.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nst = P.nstages;
 
@@ -348,6 +355,11 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const int buf = (int)(it & 1);
       const uint32_t bphase = (uint32_t)((it >> 1) & 1);
       const long long ctr0 = it * NS;
+      float pnz = 0.f;                               // post-op: per-token noise value
+      if (P.has_post && P.pnoise) {
+        const long long tokp = (tile % P.tiles_per_image) * TILE + row;
+        pnz = __ldg(P.pnoise + (size_t)b * P.pnoise_bstride + tokp) * (P.pstrength ? __ldg(P.pstrength) : 1.f);
+      }
       // ---- 1. LayerNorm statistics over this group's slabs
       float mean = 0.f, rstd = 1.f;
       if (P.norm_layer) {
@@ -412,6 +424,13 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < KP; ++j) if (j < P.k) a[j] = sv[j];
         }
+        // round P to the nearest TF32 so the tensor core's operand truncation is exact (see gf_fold.cu: round_tf32)
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+          uint32_t bits = __float_as_uint(sv[j]);
+          bits = (bits + 0xFFFu + ((bits >> 13) & 1u)) & 0xFFFFE000u;
+          sv[j] = __uint_as_float(bits);
+        }
         mbar_wait(smem_u32(&bars->p_free[buf]), bphase ^ 1u);       // GEMM2 of the tile two iterations back is done
         tc_fence_after();
         tmem_st16(tmem + lane_addr + COL_P + buf * 32, sv);
@@ -453,6 +472,12 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           } else {
             x.x = fmaf(xn0, gv[c * 4 + 0], bv[c * 4 + 0]); x.y = fmaf(xn1, gv[c * 4 + 1], bv[c * 4 + 1]);
             x.z = fmaf(xn2, gv[c * 4 + 2], bv[c * 4 + 2]); x.w = fmaf(xn3, gv[c * 4 + 3], bv[c * 4 + 3]);
+          }
+          if (P.has_post) {
+            const float4 pb = *reinterpret_cast<const float4*>(pbias_s + s * SLAB_CH + c * 4);   // broadcast read
+            x.x += pnz + pb.x; x.y += pnz + pb.y; x.z += pnz + pb.z; x.w += pnz + pb.w;
+            if (P.pact == 1) { x.x = fmaxf(x.x, 0.2f * x.x); x.y = fmaxf(x.y, 0.2f * x.y); x.z = fmaxf(x.z, 0.2f * x.z); x.w = fmaxf(x.w, 0.2f * x.w); }
+            x.x *= P.pgain; x.y *= P.pgain; x.z *= P.pgain; x.w *= P.pgain;
           }
           *px = x;
         }
@@ -544,7 +569,7 @@ static int stages_for(int smem_limit) {
 }
 
 template <int KP, int NS, int MODE>
-static int launch(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, cudaStream_t st) {
+static int launch(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, const gf_attn_postop* post, cudaStream_t st) {
   using CF = Cfg<KP, NS, MODE>;
   const int nst = stages_for<KP, NS, MODE>(device_smem_optin());
   if (nst < NS) { set_error("tcgen05 path: shared memory too small for C=%d KP=%d mode=%d", L.C, KP, MODE); return GF_ERR_UNSUPPORTED; }
@@ -563,6 +588,9 @@ static int launch(const Layout& L, const gf_attn_desc* d, const float* X, float*
   P.nstages = nst;
   P.tiles_per_image = L.n / TILE;
   P.total_tiles = (long long)L.B * P.tiles_per_image;
+  P.has_post = post ? 1 : 0;
+  P.pbias = post ? post->bias : nullptr; P.pnoise = post ? post->noise : nullptr; P.pstrength = post ? post->strength : nullptr;
+  P.pnoise_bstride = post ? post->noise_bstride : 0; P.pact = post ? post->act : 0; P.pgain = post ? post->gain : 1.f;
   const int smem_bytes = CF::FIXED_BYTES + nst * SLAB_BYTES + 1024;
   auto kern = token_tc_kernel<KP, NS, MODE>;
   GF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -575,11 +603,11 @@ static int launch(const Layout& L, const gf_attn_desc* d, const float* X, float*
 }
 
 template <int KP, int NS>
-static int launch_mode(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, cudaStream_t st) {
+static int launch_mode(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, const gf_attn_postop* post, cudaStream_t st) {
   switch (d->integration) {
-    case GF_INT_MUL: return launch<KP, NS, GF_INT_MUL>(L, d, X, Xout, att, ws, st);
-    case GF_INT_ADD: return launch<KP, NS, GF_INT_ADD>(L, d, X, Xout, att, ws, st);
-    default: return launch<KP, NS, GF_INT_BOTH>(L, d, X, Xout, att, ws, st);
+    case GF_INT_MUL: return launch<KP, NS, GF_INT_MUL>(L, d, X, Xout, att, ws, post, st);
+    case GF_INT_ADD: return launch<KP, NS, GF_INT_ADD>(L, d, X, Xout, att, ws, post, st);
+    default: return launch<KP, NS, GF_INT_BOTH>(L, d, X, Xout, att, ws, post, st);
   }
 }
 
@@ -607,16 +635,16 @@ bool tc_supported(const Layout& L, const gf_attn_desc* d) {
   return ns == 2 ? tc::fits<32, 2>(d->integration, limit) : ns == 4 ? tc::fits<32, 4>(d->integration, limit) : tc::fits<32, 8>(d->integration, limit);
 }
 
-int token_pass_tc(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, cudaStream_t st) {
+int token_pass_tc(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, const gf_attn_postop* post, cudaStream_t st) {
   const int ns = L.C / 32;
   if (L.KP == 16) {
-    if (ns == 2) return tc::launch_mode<16, 2>(L, d, X, Xout, att, ws, st);
-    if (ns == 4) return tc::launch_mode<16, 4>(L, d, X, Xout, att, ws, st);
-    return tc::launch_mode<16, 8>(L, d, X, Xout, att, ws, st);
+    if (ns == 2) return tc::launch_mode<16, 2>(L, d, X, Xout, att, ws, post, st);
+    if (ns == 4) return tc::launch_mode<16, 4>(L, d, X, Xout, att, ws, post, st);
+    return tc::launch_mode<16, 8>(L, d, X, Xout, att, ws, post, st);
   }
-  if (ns == 2) return tc::launch_mode<32, 2>(L, d, X, Xout, att, ws, st);
-  if (ns == 4) return tc::launch_mode<32, 4>(L, d, X, Xout, att, ws, st);
-  return tc::launch_mode<32, 8>(L, d, X, Xout, att, ws, st);
+  if (ns == 2) return tc::launch_mode<32, 2>(L, d, X, Xout, att, ws, post, st);
+  if (ns == 4) return tc::launch_mode<32, 4>(L, d, X, Xout, att, ws, post, st);
+  return tc::launch_mode<32, 8>(L, d, X, Xout, att, ws, post, st);
 }
 
 }  // namespace gf

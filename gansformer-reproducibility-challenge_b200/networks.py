@@ -20,6 +20,8 @@ import torch.nn.functional as F
 from torch import nn
 
 from .attention import BipartiteAttention
+from . import ops
+from .ops import fir_filter
 
 SQRT2 = math.sqrt(2.0)
 
@@ -29,53 +31,27 @@ def nf(res: int, fmap_base: int = 16384, fmap_max: int = 512) -> int:
     return int(min(fmap_base // (2 ** (int(math.log2(res)) - 1)), fmap_max))
 
 
-def fir_filter(device=None, dtype=torch.float32) -> torch.Tensor:
-    f = torch.tensor([1.0, 3.0, 3.0, 1.0], dtype=torch.float64)
-    f = torch.outer(f, f)
-    return (f / f.sum()).to(device=device, dtype=dtype)
-
-
-def upfirdn2d(x: torch.Tensor, f: torch.Tensor, up: int = 1, pad=(0, 0, 0, 0), gain: float = 1.0) -> torch.Tensor:
-    """Zero-insert upsample by `up`, pad (x0, x1, y0, y1), correlate with the (symmetric) FIR filter `f`.
-
-    Host stand-in for the reference's native op dnnlib/tflib/ops/upfirdn_2d.cu."""
-    B, C, H, W = x.shape
-    if up > 1:
-        x = x.reshape(B, C, H, 1, W, 1)
-        x = F.pad(x, [0, up - 1, 0, 0, 0, up - 1])
-        x = x.reshape(B, C, H * up, W * up)
-    x = F.pad(x, [pad[0], pad[1], pad[2], pad[3]])
-    w = (f * gain).to(x.dtype)[None, None].expand(C, 1, *f.shape)
-    return F.conv2d(x, w, groups=C)
-
-
-def bias_act(x: torch.Tensor, b: Optional[torch.Tensor], act: str = "lrelu") -> torch.Tensor:
-    """Host stand-in for the reference's native op dnnlib/tflib/ops/fused_bias_act.cu."""
-    if b is not None:
-        x = x + b.to(x.dtype).reshape(1, -1, *([1] * (x.dim() - 2)))
-    if act == "lrelu":
-        x = F.leaky_relu(x, 0.2) * SQRT2
-    return x
-
-
 def modulated_conv2d(x: torch.Tensor, weight: torch.Tensor, styles: torch.Tensor, *, demodulate: bool = True,
                      up: int = 1, f: Optional[torch.Tensor] = None) -> torch.Tensor:
     """StyleGAN2 modulated convolution in its activation-scaling form: (x * s) conv w, then * demod.
 
     Identical in exact arithmetic to modulating the weights per sample (the reference's grouped-conv form);
-    avoids B separate weight tensors.  weight [O, I, kh, kw]; styles [B, I]."""
+    avoids B separate weight tensors.  weight [O, I, kh, kw]; styles [B, I].  The two scalings and the FIR blur of the
+    upsampling path are the native ops of ops.py (gf_ops.h); the convolution itself is cuDNN (SURVEY row f1 is next)."""
     O, I, kh, kw = weight.shape
     w = weight * (1.0 / math.sqrt(I * kh * kw))
-    x = x * styles[:, :, None, None]
-    if up == 1:
-        x = F.conv2d(x, w, padding=kh // 2)
-    else:
-        x = F.conv_transpose2d(x, w.transpose(0, 1), stride=2)        # [B, O, 2H+1, 2W+1]
-        x = upfirdn2d(x, f, pad=(1, 1, 1, 1), gain=4.0)                # -> [B, O, 2H, 2W]
+    d = None
     if demodulate:
         wsq = w.square().sum(dim=[2, 3])                               # [O, I]
         d = torch.rsqrt(styles.square() @ wsq.t() + 1e-8)             # [B, O]
-        x = x * d[:, :, None, None]
+    x = ops.chan_scale(x, styles)
+    if up == 1:
+        x = F.conv2d(x, w, padding=kh // 2)
+        if d is not None:
+            x = ops.chan_scale(x, d)
+    else:
+        x = F.conv_transpose2d(x, w.transpose(0, 1), stride=2)        # [B, O, 2H+1, 2W+1]
+        x = ops.blur_up(x, f, scale=d, gain=4.0)                       # -> [B, O, 2H, 2W], demodulated
     return x
 
 
@@ -137,18 +113,25 @@ class SynthesisLayer(nn.Module):
     def forward(self, x, w_glob, y, noise_mode="const", centroids=None, return_att=False):
         styles = self.affine(w_glob)
         x = modulated_conv2d(x, self.weight, styles, up=2 if self.up else 1, f=self.fir)
+        if noise_mode == "const":
+            noise = self.noise_const
+        elif noise_mode == "random":
+            noise = torch.randn(x.shape[0], 1, self.resolution, self.resolution, device=x.device, dtype=x.dtype)
+        else:
+            noise = None
         att = None
         if self.attention is not None:
             xl = x.permute(0, 2, 3, 1)                                  # channels-last storage -> [B,H,W,C] view
             if not xl.is_contiguous():
                 xl = xl.contiguous()
+            fused = x.is_cuda and not (torch.is_grad_enabled() and (x.requires_grad or self.bias.requires_grad))
+            if fused:   # noise + bias + leaky-ReLU ride on the attention kernel's store
+                post = dict(bias=self.bias, noise=noise, strength=self.noise_strength, act="lrelu", gain=SQRT2)
+                xo, att, centroids = self.attention(xl, y, centroids=centroids, return_att=return_att, postop=post)
+                return xo.permute(0, 3, 1, 2), att, centroids
             xo, att, centroids = self.attention(xl, y, centroids=centroids, return_att=return_att)
             x = xo.permute(0, 3, 1, 2)                                  # back to an NCHW view of channels-last data
-        if noise_mode == "const":
-            x = x + self.noise_const * self.noise_strength
-        elif noise_mode == "random":
-            x = x + torch.randn(x.shape[0], 1, self.resolution, self.resolution, device=x.device, dtype=x.dtype) * self.noise_strength
-        x = bias_act(x, self.bias, "lrelu")
+        x = ops.bias_act(x, self.bias, "lrelu", noise=noise, strength=self.noise_strength)
         return x, att, centroids
 
 
@@ -160,9 +143,15 @@ class ToRGB(nn.Module):
         self.bias = nn.Parameter(torch.zeros(img_channels))
 
     def forward(self, x, w_glob):
-        styles = self.affine(w_glob)
-        x = modulated_conv2d(x, self.weight, styles, demodulate=False)
-        return bias_act(x, self.bias, "linear")
+        """1x1 modulated conv without demodulation: the style is folded into per-sample [3, C] weights, so the
+        activations are read once and no styled copy is written."""
+        styles = self.affine(w_glob)                                    # [B, C]
+        O, I = self.weight.shape[:2]
+        wm = self.weight.reshape(1, O, I) * styles[:, None, :] * (1.0 / math.sqrt(I))      # [B, 3, C]
+        B, C, H, W = x.shape
+        xl = x.permute(0, 2, 3, 1).reshape(B, H * W, C)
+        rgb = torch.matmul(xl, wm.transpose(1, 2)) + self.bias         # [B, HW, 3]
+        return rgb.transpose(1, 2).reshape(B, O, H, W)
 
 
 class SynthesisNetwork(nn.Module):
@@ -212,7 +201,7 @@ class SynthesisNetwork(nn.Module):
                 if att is not None:
                     atts.append(att)
             rgb = self.torgbs[bi](x, w_glob)
-            img = rgb if img is None else upfirdn2d(img, self.fir, up=2, pad=(2, 1, 2, 1), gain=4.0) + rgb
+            img = rgb if img is None else ops.upsample2x(img, self.fir, add=rgb)
         return (img, atts) if return_att else img
 
 

@@ -1,0 +1,122 @@
+"""Host wrappers of the memory-bound companion ops (include/gf_ops.h): the B200-native equivalents of the
+reference's native ops ``dnnlib/tflib/ops/upfirdn_2d.cu`` and ``fused_bias_act.cu`` (expected upstream; not in the
+checkout) in the forms the generator uses, plus channel scaling (style modulation / demodulation).
+
+Inference on CUDA fp32 tensors goes through libgf_attn.so.  The plain-torch forms below are the *definition* of each
+op (and serve autograd / float64 / CPU plumbing tests of the surrounding host code -- none of this is the attention
+hot path, which has no CPU form at all).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+SQRT2 = math.sqrt(2.0)
+
+
+def _use_cuda(*tensors) -> bool:
+    ts = [t for t in tensors if t is not None]
+    if not all(t.is_cuda and t.dtype == torch.float32 for t in ts):
+        return False
+    return not (torch.is_grad_enabled() and any(t.requires_grad for t in ts))
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def fir_filter(device=None, dtype=torch.float32) -> torch.Tensor:
+    f = torch.tensor([1.0, 3.0, 3.0, 1.0], dtype=torch.float64)
+    f = torch.outer(f, f)
+    return (f / f.sum()).to(device=device, dtype=dtype)
+
+
+def upfirdn2d_ref(x: torch.Tensor, f: torch.Tensor, up: int = 1, pad=(0, 0, 0, 0), gain: float = 1.0) -> torch.Tensor:
+    """Definition: zero-insert upsample by `up`, pad (x0, x1, y0, y1), correlate with the symmetric FIR filter `f`."""
+    B, C, H, W = x.shape
+    if up > 1:
+        x = x.reshape(B, C, H, 1, W, 1)
+        x = F.pad(x, [0, up - 1, 0, 0, 0, up - 1])
+        x = x.reshape(B, C, H * up, W * up)
+    x = F.pad(x, [pad[0], pad[1], pad[2], pad[3]])
+    w = (f * gain).to(x.dtype)[None, None].expand(C, 1, *f.shape)
+    return F.conv2d(x, w, groups=C)
+
+
+def _nhwc_view(x: torch.Tensor) -> torch.Tensor:
+    """NCHW-shaped tensor -> contiguous [B,H,W,C] view (free when x is channels_last)."""
+    v = x.permute(0, 2, 3, 1)
+    return v if v.is_contiguous() else v.contiguous()
+
+
+def chan_scale(x: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
+    """x [B,C,H,W] * s [B,C] (style modulation / demodulation as activation scaling)."""
+    if _use_cuda(x, s) and x.shape[1] % 4 == 0:
+        xv = _nhwc_view(x)
+        B, H, W, C = xv.shape
+        y = torch.empty_like(xv)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().gf_chan_scale_nhwc(xv.data_ptr(), s.contiguous().data_ptr(), y.data_ptr(), B, H * W, C,
+                                                      _stream(x.device)), "gf_chan_scale_nhwc")
+        return y.permute(0, 3, 1, 2)
+    return x * s[:, :, None, None].to(x.dtype)
+
+
+def blur_up(x: torch.Tensor, f: torch.Tensor, scale: Optional[torch.Tensor] = None, gain: float = 4.0) -> torch.Tensor:
+    """FIR blur after a stride-2 transposed conv: x [B,C,2H+1,2W+1] -> [B,C,2H,2W] (pad 1), optional * scale [B,C]."""
+    if _use_cuda(x, scale) and x.shape[1] % 4 == 0:
+        xv = _nhwc_view(x)
+        B, Hin, Win, C = xv.shape
+        y = torch.empty((B, Hin - 1, Win - 1, C), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().gf_blur_up_nhwc(xv.data_ptr(), y.data_ptr(), None if scale is None else scale.contiguous().data_ptr(),
+                                                   B, Hin - 1, Win - 1, C, float(gain), _stream(x.device)), "gf_blur_up_nhwc")
+        return y.permute(0, 3, 1, 2)
+    y = upfirdn2d_ref(x, f, pad=(1, 1, 1, 1), gain=gain)
+    return y if scale is None else y * scale[:, :, None, None].to(y.dtype)
+
+
+def upsample2x(x: torch.Tensor, f: torch.Tensor, add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """2x FIR upsampling of an NCHW image (tRGB skip connection), optionally + add."""
+    if _use_cuda(x, add):
+        xc = x.contiguous()
+        B, C, H, W = xc.shape
+        y = torch.empty((B, C, 2 * H, 2 * W), dtype=torch.float32, device=x.device)
+        ac = None if add is None else add.contiguous()
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().gf_upsample2x_nchw(xc.data_ptr(), None if ac is None else ac.data_ptr(), y.data_ptr(), B, C, H, W,
+                                                      _stream(x.device)), "gf_upsample2x_nchw")
+        return y
+    y = upfirdn2d_ref(x, f, up=2, pad=(2, 1, 2, 1), gain=4.0)
+    return y if add is None else y + add
+
+
+def bias_act(x: torch.Tensor, bias: Optional[torch.Tensor], act: str = "lrelu", noise: Optional[torch.Tensor] = None,
+             strength: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """act(x + noise * strength + bias[c]) * gain; x [B,C,H,W]; noise [H,W] (shared) or [B,1,H,W]; lrelu gain sqrt(2)."""
+    gain = SQRT2 if act == "lrelu" else 1.0
+    if _use_cuda(x, bias, noise, strength) and x.shape[1] % 4 == 0:
+        xv = _nhwc_view(x)
+        B, H, W, C = xv.shape
+        y = torch.empty_like(xv)
+        nz = None if noise is None else noise.contiguous()
+        bstride = H * W if (nz is not None and nz.numel() == B * H * W and B > 1) else 0
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().gf_bias_act_nhwc(xv.data_ptr(), y.data_ptr(), None if bias is None else bias.contiguous().data_ptr(),
+                                                    None if nz is None else nz.data_ptr(),
+                                                    None if strength is None else strength.data_ptr(), bstride, B, H * W, C,
+                                                    1 if act == "lrelu" else 0, float(gain), _stream(x.device)), "gf_bias_act_nhwc")
+        return y.permute(0, 3, 1, 2)
+    if noise is not None:
+        x = x + noise.to(x.dtype) * (1.0 if strength is None else strength.to(x.dtype))
+    if bias is not None:
+        x = x + bias.to(x.dtype).reshape(1, -1, 1, 1)
+    if act == "lrelu":
+        x = F.leaky_relu(x, 0.2) * SQRT2
+    return x

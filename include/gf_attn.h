@@ -62,6 +62,17 @@ typedef struct gf_attn_desc {
   int32_t flags;        /* GF_FLAG_* */
 } gf_attn_desc;
 
+/* Optional fused epilogue of stage T (what follows the attention block inside the reference's synthesis layer:
+ * noise input + fused_bias_act):   x'' = act(x' + noise[b*noise_bstride + t] * (*strength) + bias[c]) * gain */
+typedef struct gf_attn_postop {
+  const float* bias;         /* [C] or NULL */
+  const float* noise;        /* [H*W] (noise_bstride = 0: shared by the batch) or [B][H*W]; NULL = no noise */
+  const float* strength;     /* device scalar; NULL = 1 */
+  long long noise_bstride;
+  int32_t act;               /* 0 linear, 1 leaky-ReLU(0.2) */
+  float gain;
+} gf_attn_postop;
+
 /* Raw (un-scaled) parameters of one layer, each [fan_in, fan_out] row-major; equalised-LR scaling
  * (1/sqrt(fan_in), reference: get_weight/dense_layer) is applied by the library.  The *2 / wkc
  * members are only read when desc.duplex; wpq/wpk/pos_latent (and wpq2/wpk2) only when pos_dim>0. */
@@ -104,11 +115,18 @@ int gf_attn_prologue(const gf_attn_desc* desc, const float* Y, const float* fold
  * Requires gf_attn_prologue() on the same ws/stream first. */
 int gf_attn_simplex_fwd(const gf_attn_desc* desc, const float* X, float* Xout, float* att, void* ws, void* stream);
 
+/* Same as gf_attn_simplex_fwd with the fused noise + bias + activation epilogue (post may be NULL). */
+int gf_attn_simplex_fwd_ex(const gf_attn_desc* desc, const float* X, float* Xout, float* att, void* ws,
+                           const gf_attn_postop* post, void* stream);
+
 /* Duplex (kmeans) layer: pass A (latents attend to the grid, softmax over n, centroids [B,k,C]) then
  * prologue with keys from the centroids, then stage T.  centroids_inout: output (and input when
  * GF_FLAG_CENTROIDS_IN). */
 int gf_attn_duplex_fwd(const gf_attn_desc* desc, const float* X, const float* Y, const float* folded,
                        float* Xout, float* att, float* centroids_inout, void* ws, void* stream);
+
+int gf_attn_duplex_fwd_ex(const gf_attn_desc* desc, const float* X, const float* Y, const float* folded,
+                          float* Xout, float* att, float* centroids_inout, void* ws, const gf_attn_postop* post, void* stream);
 
 /* Per-(b,c) statistics for GF_NORM_INSTANCE / GF_NORM_BATCH, written into ws by a reduction pass over X
  * (called internally by the forward entry points; exported for tests). */

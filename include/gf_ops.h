@@ -1,0 +1,42 @@
+/*
+ * gf_ops.h -- C ABI of the memory-bound companions of the attention hot path.
+ *
+ * B200-native equivalents of the reference's two native CUDA ops -- dnnlib/tflib/ops/fused_bias_act.cu and
+ * dnnlib/tflib/ops/upfirdn_2d.cu (expected upstream locations; NOT in the reference checkout,
+ * /root/reference/.SUBMODULES.json:2) -- restricted to the uses the generator makes of them, plus the
+ * activation-scaling form of StyleGAN2's weight (de)modulation.  Channels-last fp32, raw device pointers,
+ * enqueue-only on `stream` (a cudaStream_t passed as void*), same error convention as gf_attn.h.
+ */
+#ifndef GF_OPS_H_
+#define GF_OPS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* y[b,t,c] = x[b,t,c] * s[b,c].   Style modulation of a conv input / demodulation of a conv output
+ * (modulated_conv2d_layer in the reference, activation-scaling form).  y may alias x.  C % 4 == 0. */
+int gf_chan_scale_nhwc(const float* x, const float* s, float* y, int B, int HW, int C, void* stream);
+
+/* upfirdn_2d, use (a): the FIR blur that follows a stride-2 transposed convolution.
+ * x [B, Hout+1, Wout+1, C] -> y [B, Hout, Wout, C]; separable filter [1,3,3,1]/8 per axis, total gain `gain`
+ * (4 after an upsampling conv), zero padding 1 on every side; optional per-(b,c) scale (demodulation). C % 4 == 0. */
+int gf_blur_up_nhwc(const float* x, float* y, const float* scale, int B, int Hout, int Wout, int C, float gain, void* stream);
+
+/* upfirdn_2d, use (b): 2x upsampling of an NCHW image (skip connection of the tRGB outputs):
+ * zero-insert, pad (2,1,2,1), FIR [1,3,3,1]^2/64 * 4.  y [B,C,2H,2W] = up(x [B,C,H,W]) (+ add, nullable, same shape as y). */
+int gf_upsample2x_nchw(const float* x, const float* add, float* y, int B, int C, int H, int W, void* stream);
+
+/* fused_bias_act (+ the noise input of the synthesis layer):
+ *   y = act(x + noise[b*noise_bstride + t] * (*strength) + bias[c]) * gain
+ * act: 0 linear, 1 leaky-ReLU(0.2).  noise / strength / bias nullable.  y may alias x.  C % 4 == 0. */
+int gf_bias_act_nhwc(const float* x, float* y, const float* bias, const float* noise, const float* strength,
+                     long long noise_bstride, int B, int HW, int C, int act, float gain, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GF_OPS_H_ */

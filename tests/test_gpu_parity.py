@@ -306,3 +306,63 @@ def test_autograd_matches_oracle(gf, cuda_dev):
     assert rel(y.grad, y64.grad) < 1e-4
     for n in ("wq", "wk", "wv", "wo", "bo", "pos_latent", "wpq"):
         assert rel(getattr(attn, n).grad, w[n].grad) < 1e-4, n
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fused post-op (noise + bias + leaky-ReLU on the attention store) and the native companion ops (gf_ops.h)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("exact", [True, False], ids=["fp32", "default"])
+@pytest.mark.parametrize("C,H,W,k,random_noise", [(128, 16, 16, 16, False), (256, 16, 8, 8, True), (512, 8, 8, 4, False)])
+def test_attention_postop(gf, cuda_dev, C, H, W, k, random_noise, exact):
+    D = p = 16
+    B = 3
+    g = torch.Generator().manual_seed(C + k)
+    x64 = torch.randn(B, C, H, W, generator=g, dtype=torch.float64)
+    y64 = torch.randn(B, k, D, generator=g, dtype=torch.float64)
+    bias = torch.randn(C, generator=g, dtype=torch.float64) * 0.5
+    noise = torch.randn((B, 1, H, W) if random_noise else (H, W), generator=g, dtype=torch.float64)
+    strength = torch.tensor(0.37, dtype=torch.float64)
+    w = ob.init_params(C, D, k, p, "both", False, seed=5, bias_std=0.3)
+    ref, _, _ = ob.transformer_layer(x64, y64, w, integration="both")
+    ref = ref + noise * strength + bias[None, :, None, None]
+    ref = torch.nn.functional.leaky_relu(ref, 0.2) * math.sqrt(2.0)
+    attn = make_layer(gf, cuda_dev, C, D, k, p, "both", "layer", False, True, exact, w)
+    post = dict(bias=bias.float().to(cuda_dev), noise=noise.float().to(cuda_dev), strength=strength.float().to(cuda_dev),
+                act="lrelu", gain=math.sqrt(2.0))
+    with torch.no_grad():
+        out, _, _ = attn(x64.permute(0, 2, 3, 1).contiguous().float().to(cuda_dev), y64.float().to(cuda_dev), postop=post)
+    check_close(out, ref.permute(0, 2, 3, 1), gf._lib.last_path(), "postop")
+
+
+def test_native_ops_match_definitions(gf, cuda_dev):
+    """gf_ops.h kernels vs their plain-torch definitions (ops.py *_ref / torch path), fp32, channels-last inputs."""
+    from importlib import import_module
+    ops = import_module("gansformer-reproducibility-challenge_b200.ops")
+    g = torch.Generator().manual_seed(0)
+    f = ops.fir_filter(cuda_dev)
+    for (B, C, H, W) in [(2, 64, 8, 8), (3, 128, 16, 12), (1, 32, 4, 4)]:
+        x = torch.randn(B, C, 2 * H + 1, 2 * W + 1, generator=g).to(cuda_dev).contiguous(memory_format=torch.channels_last)
+        s = torch.rand(B, C, generator=g).to(cuda_dev) + 0.5
+        with torch.no_grad():
+            got = ops.blur_up(x, f, scale=s)
+        want = ops.upfirdn2d_ref(x.double(), f.double(), pad=(1, 1, 1, 1), gain=4.0) * s.double()[:, :, None, None]
+        assert got.shape == (B, C, 2 * H, 2 * W)
+        assert (got.double() - want).abs().max() < 1e-5
+        xs = torch.randn(B, C, H, W, generator=g).to(cuda_dev).contiguous(memory_format=torch.channels_last)
+        with torch.no_grad():
+            assert torch.equal(ops.chan_scale(xs, s), xs * s[:, :, None, None])
+            bias = torch.randn(C, generator=g).to(cuda_dev)
+            nz = torch.randn(H, W, generator=g).to(cuda_dev)
+            st = torch.tensor(0.3, device=cuda_dev)
+            got = ops.bias_act(xs, bias, "lrelu", noise=nz, strength=st)
+            want = torch.nn.functional.leaky_relu(xs + nz * st + bias[None, :, None, None], 0.2) * math.sqrt(2.0)
+            assert (got - want).abs().max() < 1e-5
+            nzb = torch.randn(B, 1, H, W, generator=g).to(cuda_dev)
+            got = ops.bias_act(xs, bias, "linear", noise=nzb, strength=None)
+            assert (got - (xs + nzb + bias[None, :, None, None])).abs().max() < 1e-5
+        img = torch.randn(B, 3, H, W, generator=g).to(cuda_dev)
+        add = torch.randn(B, 3, 2 * H, 2 * W, generator=g).to(cuda_dev)
+        with torch.no_grad():
+            got = ops.upsample2x(img, f, add=add)
+        want = ops.upfirdn2d_ref(img.double(), f.double(), up=2, pad=(2, 1, 2, 1), gain=4.0) + add.double()
+        assert (got.double() - want).abs().max() < 1e-5

@@ -15,24 +15,26 @@ from oracle import generator as og
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    src = open(os.path.join(ROOT, "include", "gf_attn.h")).read()
+def _declared_symbols(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(gf_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_header_symbols_are_exported(gf):
     lib = gf._lib.load()
-    declared = _declared_symbols()
-    assert declared == sorted(gf._lib.EXPORTS), (declared, gf._lib.EXPORTS)
-    for name in declared:
-        assert hasattr(lib, name), f"{name} declared in include/gf_attn.h but not exported by libgf_attn.so"
+    for header, exports in (("gf_attn.h", gf._lib.EXPORTS), ("gf_ops.h", gf._lib.OPS_EXPORTS)):
+        declared = _declared_symbols(header)
+        assert declared == sorted(exports), (header, declared, exports)
+        for name in declared:
+            assert hasattr(lib, name), f"{name} declared in include/{header} but not exported by libgf_attn.so"
     assert lib.gf_attn_abi_version() == 1
 
 
 def test_struct_layouts_match_c(gf):
     assert ctypes.sizeof(gf._lib.GfAttnDesc) == 12 * 4
     assert ctypes.sizeof(gf._lib.GfAttnWeights) == 20 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(gf._lib.GfAttnPostop) == 3 * 8 + 8 + 4 + 4
 
 
 def test_sizes_and_validation(gf):
