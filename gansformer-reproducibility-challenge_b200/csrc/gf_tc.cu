@@ -5,14 +5,17 @@
 // transformer_layer (Q projection folded into K', QK^T, softmax, PV), integrate and att_norm.  Same algorithm as
 // oracle/folded.py per_token(); operands of both contractions are rounded to TF32 by the tensor cores.
 //
-// One persistent CTA per SM, 10 warps:
-//   warp 0      TMA producer: X slabs (128 tokens x 32 channels, 16 KB, SWIZZLE_128B) into a ring; K'/V^T per image
-//   warp 1      MMA issuer:   GEMM1  S[128,KP]   = X[128,C] . K'^T            (A,B from smem, D in TMEM)
-//                             GEMM2  G[128,32]   = P[128,KP] . V^T[32 ch,KP]^T per slab (A = P from TMEM, B from smem)
-//   warps 2-9   two groups of 4 warps (one warp per TMEM lane quadrant, thread = token row); group g owns the slabs
-//               with (slab & 1) == g: LayerNorm partial statistics, epilogue y = LN(x)*g (+b) written in place over the
-//               slab, TMA store.  Group 0 also does the softmax (S from TMEM -> P back to TMEM).
-// HBM traffic: X read once, X' written once (the algorithmic bytes of SURVEY 8d).
+// One persistent CTA per SM, 14 warps:
+//   warp 0       TMA producer: X slabs (128 tokens x 32 channels, 16 KB, SWIZZLE_128B) into a ring; K'/V^T per image
+//   warp 1       MMA issuer:   GEMM1  S[128,KP]   = X[128,C] . K'^T            (A,B from smem, D in TMEM)
+//                              GEMM2  G[128,32]   = P[128,KP] . V^T[32 ch,KP]^T per slab (A = P from TMEM, B from smem)
+//   warps 10-13  row warps (one per TMEM lane quadrant, thread = token row), run up to a tile ahead: LayerNorm statistics
+//                of the whole row from the swizzled slabs, softmax (S from TMEM -> P back to TMEM), attention-map store
+//   warps 2-9    two epilogue groups of 4 warps; group g owns the slabs with (slab & 1) == g: gain(/bias) from TMEM,
+//                y = LN(x)*g (+b) [+ noise + bias, leaky-ReLU] written in place over the slab, TMA store, slab release
+// Single-pass mode (C <= 256): the tile's slabs stay resident from load to store -> X read once, X' written once from HBM
+// (the algorithmic bytes of SURVEY 8d).  Two-pass mode (C = 512, a tile does not fit): slabs stream through the ring
+// once for GEMM1 + statistics and are fetched a second time (L2 hits) for the epilogue.
 #include <cuda.h>
 #include <stdlib.h>
 #include "gf_common.cuh"
@@ -26,7 +29,7 @@ constexpr int SLAB_CH = 32;               // channels per slab = one 128-byte sw
 constexpr int SLAB_BYTES = TILE * SLAB_CH * 4;
 constexpr int MAX_STAGES = 13;
 constexpr int NACC = 4;                   // accumulator stages of GEMM2 in TMEM
-constexpr int NUM_THREADS = 320;
+constexpr int NUM_THREADS = 448;        // warp 0 producer, 1 MMA, 2-9 epilogue (two groups), 10-13 row warps
 constexpr int TMEM_COLS = 512;
 // TMEM column map
 constexpr int COL_S = 0;                  // S[2]  : 2 x 32
@@ -38,6 +41,7 @@ struct Params {
   int n, H, W, k, Cout, B;
   int norm_layer;            // 1 = LayerNorm over C, 0 = none
   int nstages;
+  int drain_each_tile;       // 1: release every slab at tile end (ring barely larger than a tile)
   long long total_tiles;
   int tiles_per_image;
   // fused epilogue (gf_attn_postop)
@@ -182,6 +186,7 @@ struct Bars {
   uint64_t slab_full[MAX_STAGES], slab_empty[MAX_STAGES];
   uint64_t kv_full, kv_free;
   uint64_t s_full[2], p_full[2], p_free[2];
+  uint64_t st_full[2], st_free[2];
   uint64_t acc_full[NACC], acc_empty[NACC];
   uint32_t tmem_base;
   uint32_t pad;
@@ -194,8 +199,8 @@ struct Cfg {
   static constexpr int KP_BYTES = KP * C * 4;            // K' : NS chunks of [KP rows x 128 B]
   static constexpr int V_ROW_BYTES = KP * 4;             // V^T row (one channel): KP latents
   static constexpr int V_BYTES = COUT * V_ROW_BYTES;
-  static constexpr int STATS_BYTES = 2 * 2 * TILE * 2 * 4;  // [tile parity][group][row]{mean, M2}
-  static constexpr int PBIAS_BYTES = C * 4;                 // post-op bias vector
+  static constexpr int STATS_BYTES = 2 * TILE * 2 * 4;   // [tile parity][row]{mean, rstd}
+  static constexpr int PBIAS_BYTES = C * 4;              // post-op bias vector
   static constexpr int OFF_KP = 0;
   static constexpr int OFF_V = OFF_KP + KP_BYTES;
   static constexpr int OFF_STATS = OFF_V + V_BYTES;
@@ -205,13 +210,18 @@ struct Cfg {
   static constexpr int FIXED_BYTES = OFF_RING;
 };
 
-template <int KP, int NS, int MODE>
+__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+
+template <int KP, int NS, int MODE, bool TWO_PASS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmO,
                 const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const Params P) {
   using CF = Cfg<KP, NS, MODE>;
   constexpr int C = CF::C;
-  constexpr int ACC_W = MODE == GF_INT_BOTH ? 64 : 32;
+  constexpr int SPT = TWO_PASS ? 2 * NS : NS;          // ring slots a tile consumes
+  constexpr uint32_t EMPTY_COUNT = TWO_PASS ? 5u : 1u;  // pass-1 slab: MMA commit + 4 row warps; pass-2 / single: store leader
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms need 1024 B alignment
   const uint32_t s_base = smem_u32(smem);
@@ -230,12 +240,14 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmX); prefetch_tmap(&tmO); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
-    for (int i = 0; i < nst; ++i) { mbar_init(smem_u32(&bars->slab_full[i]), 1); mbar_init(smem_u32(&bars->slab_empty[i]), 1); }
+    for (int i = 0; i < nst; ++i) { mbar_init(smem_u32(&bars->slab_full[i]), 1); mbar_init(smem_u32(&bars->slab_empty[i]), EMPTY_COUNT); }
     mbar_init(smem_u32(&bars->kv_full), 1); mbar_init(smem_u32(&bars->kv_free), 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars->s_full[i]), 1);
       mbar_init(smem_u32(&bars->p_full[i]), 4);
       mbar_init(smem_u32(&bars->p_free[i]), 1);
+      mbar_init(smem_u32(&bars->st_full[i]), 4);
+      mbar_init(smem_u32(&bars->st_free[i]), 8);
     }
     for (int i = 0; i < NACC; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 4); }
     fence_barrier_init();
@@ -252,7 +264,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
-      long long ctr = 0;       // global slab counter of this CTA
+      long long ctr = 0;       // global ring-slot counter of this CTA
       int img_changes = 0;
       int prev_b = -1;
       for (long long tile = tile_beg; tile < tile_end; ++tile) {
@@ -270,7 +282,8 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           ++img_changes;
         }
         const int row0 = (int)(tile * TILE);
-        for (int s = 0; s < NS; ++s, ++ctr) {
+        for (int ss = 0; ss < SPT; ++ss, ++ctr) {
+          const int s = ss % NS;                     // two-pass: the same slabs are fetched again for the epilogue
           const int stage = (int)(ctr % nst);
           const uint32_t phase = (uint32_t)((ctr / nst) & 1);
           mbar_wait(smem_u32(&bars->slab_empty[stage]), phase ^ 1u);
@@ -287,7 +300,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       constexpr uint32_t IDESC2 = umma_idesc_tf32(TILE, 32);
       constexpr uint32_t V_LAYOUT = KP == 32 ? LAYOUT_SW128 : LAYOUT_SW64;
       constexpr uint32_t V_SBO = 8 * CF::V_ROW_BYTES;
-      long long ctr = 0, actr = 0;
+      long long actr = 0;
       int img_changes = 0, prev_b = -1;
       long long it = 0;
       for (long long tile = tile_beg; tile < tile_end; ++tile, ++it) {
@@ -300,9 +313,10 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           prev_b = b;
           ++img_changes;
         }
-        // ---- GEMM1: S[buf] = X . K'^T over all slabs
+        // ---- GEMM1: S[buf] = X . K'^T over all slabs (pass 1 of a two-pass tile)
         const uint32_t d_s = tmem + COL_S + buf * 32;
-        for (int s = 0; s < NS; ++s, ++ctr) {
+        for (int s = 0; s < NS; ++s) {
+          const long long ctr = it * SPT + s;
           const int stage = (int)(ctr % nst);
           mbar_wait(smem_u32(&bars->slab_full[stage]), (uint32_t)((ctr / nst) & 1));
           tc_fence_after();
@@ -311,6 +325,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           for (int kk = 0; kk < 4; ++kk)
             umma_ss(d_s, umma_desc(a_addr + kk * 32, 1024, LAYOUT_SW128), umma_desc(b_addr + kk * 32, 1024, LAYOUT_SW128),
                     IDESC1, (s | kk) ? 1u : 0u);
+          if (TWO_PASS) umma_commit(smem_u32(&bars->slab_empty[stage]));    // slab may be recycled once these MMAs are done
         }
         umma_commit(smem_u32(&bars->s_full[buf]));
         // ---- GEMM2: per slab, ACC = P[buf] . V^T (gain | bias)
@@ -339,6 +354,105 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         if (!last && (int)((tile + 1) / P.tiles_per_image) != b) umma_commit(smem_u32(&bars->kv_free));
       }
     }
+  } else if (warp >= 10) {
+    // =============================== row warps: statistics + softmax ===============================
+    const int q = warp & 3;                        // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;                 // token row inside the tile
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int sw = row & 7;
+    const uint32_t row_off = (uint32_t)row * 128u;
+    long long it = 0;
+    for (long long tile = tile_beg; tile < tile_end; ++tile, ++it) {
+      const int b = (int)(tile / P.tiles_per_image);
+      const int buf = (int)(it & 1);
+      const uint32_t bphase = (uint32_t)((it >> 1) & 1);
+      const long long tok = (tile % P.tiles_per_image) * TILE + row;      // token index inside the image
+      // positional logits of this token (issued first: their L2 latency hides behind the statistics)
+      float sv[KP];
+      {
+        const int h = (int)(tok / P.W), w = (int)(tok % P.W);
+        const float4* rt = reinterpret_cast<const float4*>(P.Rt + ((size_t)b * P.H + h) * KP);
+        const float4* ct = reinterpret_cast<const float4*>(P.Ct + ((size_t)b * P.W + w) * KP);
+#pragma unroll
+        for (int j4 = 0; j4 < KP / 4; ++j4) {
+          const float4 r = __ldg(rt + j4), c = __ldg(ct + j4);
+          sv[j4 * 4 + 0] = r.x + c.x; sv[j4 * 4 + 1] = r.y + c.y; sv[j4 * 4 + 2] = r.z + c.z; sv[j4 * 4 + 3] = r.w + c.w;
+        }
+      }
+      // ---- LayerNorm statistics of the whole row (shifted sums)
+      float mean = 0.f, rstd = 1.f;
+      if (P.norm_layer || TWO_PASS) {
+        float sh = 0.f, sum = 0.f, sumsq = 0.f;
+#pragma unroll 1
+        for (int s = 0; s < NS; ++s) {
+          const long long ctr = it * SPT + s;
+          const int stage = (int)(ctr % nst);
+          mbar_wait(smem_u32(&bars->slab_full[stage]), (uint32_t)((ctr / nst) & 1));
+          if (P.norm_layer) {
+            const uint8_t* slab = smem + CF::OFF_RING + stage * SLAB_BYTES + row_off;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 x = *reinterpret_cast<const float4*>(slab + ((c ^ sw) << 4));
+              if (s == 0 && c == 0) sh = x.x;
+              const float d0 = x.x - sh, d1 = x.y - sh, d2 = x.z - sh, d3 = x.w - sh;
+              sum += (d0 + d1) + (d2 + d3);
+              sumsq = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, sumsq))));
+            }
+          }
+          if (TWO_PASS) {                            // this warp is done with the pass-1 slab
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars->slab_empty[stage]));
+          }
+        }
+        if (P.norm_layer) {
+          const float md = sum * (1.f / (float)C);
+          const float var = fmaxf(sumsq * (1.f / (float)C) - md * md, 0.f);
+          mean = sh + md;
+          rstd = rsqrtf(var + 1e-8f);
+        }
+      }
+      mbar_wait(smem_u32(&bars->st_free[buf]), bphase ^ 1u);       // epilogue of the tile two iterations back has read its stats
+      stats[(buf * TILE + row) * 2 + 0] = mean;
+      stats[(buf * TILE + row) * 2 + 1] = rstd;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->st_full[buf]));
+      // ---- softmax over the latents: S (TMEM) -> P (TMEM)
+      mbar_wait(smem_u32(&bars->s_full[buf]), bphase);
+      tc_fence_after();
+      float acc[KP];
+      tmem_ld16(tmem + lane_addr + COL_S + buf * 32, acc);
+      if constexpr (KP == 32) tmem_ld16(tmem + lane_addr + COL_S + buf * 32 + 16, acc + 16);
+      tmem_wait_ld();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < KP; ++j) { sv[j] += acc[j]; mx = fmaxf(mx, sv[j]); }
+      float den = 0.f;
+#pragma unroll
+      for (int j = 0; j < KP; ++j) { sv[j] = exp2f((sv[j] - mx) * 1.4426950408889634f); den += sv[j]; }
+      const float inv = 1.f / den;
+#pragma unroll
+      for (int j = 0; j < KP; ++j) sv[j] *= inv;
+      if (P.att) {
+        float* a = P.att + ((size_t)b * P.n + tok) * P.k;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) if (j < P.k) a[j] = sv[j];
+      }
+      // round P to the nearest TF32 so the tensor core's operand truncation is exact (see gf_fold.cu: round_tf32)
+#pragma unroll
+      for (int j = 0; j < KP; ++j) {
+        uint32_t bits = __float_as_uint(sv[j]);
+        bits = (bits + 0xFFFu + ((bits >> 13) & 1u)) & 0xFFFFE000u;
+        sv[j] = __uint_as_float(bits);
+      }
+      mbar_wait(smem_u32(&bars->p_free[buf]), bphase ^ 1u);       // GEMM2 of the tile two iterations back is done
+      tc_fence_after();
+      tmem_st16(tmem + lane_addr + COL_P + buf * 32, sv);
+      if constexpr (KP == 32) tmem_st16(tmem + lane_addr + COL_P + buf * 32 + 16, sv + 16);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->p_full[buf]));
+    }
   } else {
     // =============================== epilogue warps ===============================
     const int q = warp & 3;                        // TMEM lane quadrant this warp may access
@@ -354,101 +468,26 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const int b = (int)(tile / P.tiles_per_image);
       const int buf = (int)(it & 1);
       const uint32_t bphase = (uint32_t)((it >> 1) & 1);
-      const long long ctr0 = it * NS;
       float pnz = 0.f;                               // post-op: per-token noise value
       if (P.has_post && P.pnoise) {
         const long long tokp = (tile % P.tiles_per_image) * TILE + row;
         pnz = __ldg(P.pnoise + (size_t)b * P.pnoise_bstride + tokp) * (P.pstrength ? __ldg(P.pstrength) : 1.f);
       }
-      // ---- 1. LayerNorm statistics over this group's slabs
-      float mean = 0.f, rstd = 1.f;
-      if (P.norm_layer) {
-        float sh = 0.f, sum = 0.f, sumsq = 0.f;
-#pragma unroll 1
-        for (int s = g; s < NS; s += 2) {
-          const long long ctr = ctr0 + s;
-          const int stage = (int)(ctr % nst);
-          mbar_wait(smem_u32(&bars->slab_full[stage]), (uint32_t)((ctr / nst) & 1));
-          const uint8_t* slab = smem + CF::OFF_RING + stage * SLAB_BYTES + row_off;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 x = *reinterpret_cast<const float4*>(slab + ((c ^ sw) << 4));
-            if (s == g && c == 0) sh = x.x;
-            const float d0 = x.x - sh, d1 = x.y - sh, d2 = x.z - sh, d3 = x.w - sh;
-            sum += (d0 + d1) + (d2 + d3);
-            sumsq = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, sumsq))));
-          }
-        }
-        constexpr float CNT = (float)(C / 2);
-        const float mg = sh + sum * (1.f / CNT);
-        const float m2g = fmaxf(sumsq - sum * sum * (1.f / CNT), 0.f);
-        float* st = stats + ((buf * 2 + g) * TILE + row) * 2;
-        st[0] = mg; st[1] = m2g;
-        named_bar_sync(1, 256);
-        const float* so = stats + ((buf * 2 + (g ^ 1)) * TILE + row) * 2;
-        const float mo = so[0], m2o = so[1];
-        mean = 0.5f * (mg + mo);
-        const float dg = mg - mean, dd = mo - mean;
-        const float var = (m2g + m2o + CNT * (dg * dg + dd * dd)) * (1.f / (float)C);
-        rstd = rsqrtf(var + 1e-8f);
-      }
-      // ---- 2. softmax over the latents (group 0): S (TMEM) -> P (TMEM)
-      if (g == 0) {
-        const long long tok = (tile % P.tiles_per_image) * TILE + row;      // token index inside the image
-        const int h = (int)(tok / P.W), w = (int)(tok % P.W);
-        const float4* rt = reinterpret_cast<const float4*>(P.Rt + ((size_t)b * P.H + h) * KP);
-        const float4* ct = reinterpret_cast<const float4*>(P.Ct + ((size_t)b * P.W + w) * KP);
-        float sv[KP];
-#pragma unroll
-        for (int j4 = 0; j4 < KP / 4; ++j4) {
-          const float4 r = __ldg(rt + j4), c = __ldg(ct + j4);
-          sv[j4 * 4 + 0] = r.x + c.x; sv[j4 * 4 + 1] = r.y + c.y; sv[j4 * 4 + 2] = r.z + c.z; sv[j4 * 4 + 3] = r.w + c.w;
-        }
-        mbar_wait(smem_u32(&bars->s_full[buf]), bphase);
-        tc_fence_after();
-        float acc[KP];
-        tmem_ld16(tmem + lane_addr + COL_S + buf * 32, acc);
-        if constexpr (KP == 32) tmem_ld16(tmem + lane_addr + COL_S + buf * 32 + 16, acc + 16);
-        tmem_wait_ld();
-        float mx = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < KP; ++j) { sv[j] += acc[j]; mx = fmaxf(mx, sv[j]); }
-        float den = 0.f;
-#pragma unroll
-        for (int j = 0; j < KP; ++j) { sv[j] = exp2f((sv[j] - mx) * 1.4426950408889634f); den += sv[j]; }
-        const float inv = 1.f / den;
-#pragma unroll
-        for (int j = 0; j < KP; ++j) sv[j] *= inv;
-        if (P.att) {
-          float* a = P.att + ((size_t)b * P.n + tok) * P.k;
-#pragma unroll
-          for (int j = 0; j < KP; ++j) if (j < P.k) a[j] = sv[j];
-        }
-        // round P to the nearest TF32 so the tensor core's operand truncation is exact (see gf_fold.cu: round_tf32)
-#pragma unroll
-        for (int j = 0; j < KP; ++j) {
-          uint32_t bits = __float_as_uint(sv[j]);
-          bits = (bits + 0xFFFu + ((bits >> 13) & 1u)) & 0xFFFFE000u;
-          sv[j] = __uint_as_float(bits);
-        }
-        mbar_wait(smem_u32(&bars->p_free[buf]), bphase ^ 1u);       // GEMM2 of the tile two iterations back is done
-        tc_fence_after();
-        tmem_st16(tmem + lane_addr + COL_P + buf * 32, sv);
-        if constexpr (KP == 32) tmem_st16(tmem + lane_addr + COL_P + buf * 32 + 16, sv + 16);
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bars->p_full[buf]));
-      }
-      // ---- 3. epilogue of this group's slabs: y = LN(x) * gain (+ bias), in place, TMA store
+      // ---- row statistics from the row warps
+      mbar_wait(smem_u32(&bars->st_full[buf]), bphase);
+      const float mean = stats[(buf * TILE + row) * 2 + 0], rstd = stats[(buf * TILE + row) * 2 + 1];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->st_free[buf]));
       const float mr = -mean * rstd;
+      // ---- epilogue of this group's slabs: y = LN(x) * gain (+ bias) [post-op], in place, TMA store
 #pragma unroll 1
       for (int s = g; s < NS; s += 2) {
-        const long long ctr = ctr0 + s;
+        const long long ctr = it * SPT + (TWO_PASS ? NS : 0) + s;
+        const long long actr = it * NS + s;
         const int stage = (int)(ctr % nst);
-        const int a = (int)(ctr % NACC);
-        if (!P.norm_layer) mbar_wait(smem_u32(&bars->slab_full[stage]), (uint32_t)((ctr / nst) & 1));
-        mbar_wait(smem_u32(&bars->acc_full[a]), (uint32_t)((ctr / NACC) & 1));
+        const int a = (int)(actr % NACC);
+        mbar_wait(smem_u32(&bars->slab_full[stage]), (uint32_t)((ctr / nst) & 1));
+        mbar_wait(smem_u32(&bars->acc_full[a]), (uint32_t)((actr / NACC) & 1));
         tc_fence_after();
         float gv[32], bv[MODE == GF_INT_BOTH ? 32 : 1];
         const uint32_t t_acc = tmem + lane_addr + COL_ACC + a * 64;
@@ -488,14 +527,14 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           tma_commit();
           if (pending_stage >= 0) {
             tma_wait_read1();                      // the previous store has finished reading its slab
-            mbar_arrive(smem_u32(&bars->slab_empty[pending_stage]));
+            mbar_arrive_n(smem_u32(&bars->slab_empty[pending_stage]), EMPTY_COUNT);
           }
           pending_stage = stage;
         }
       }
-      if (leader && pending_stage >= 0) {          // drain at tile end (keeps a ring of exactly one tile deadlock-free)
+      if (leader && P.drain_each_tile && pending_stage >= 0) {   // small rings: no slab may stay held across tiles
         tma_wait_read0();
-        mbar_arrive(smem_u32(&bars->slab_empty[pending_stage]));
+        mbar_arrive_n(smem_u32(&bars->slab_empty[pending_stage]), EMPTY_COUNT);
         pending_stage = -1;
       }
     }
@@ -567,12 +606,16 @@ static int stages_for(int smem_limit) {
   int st = (smem_limit - Cfg<KP, NS, MODE>::FIXED_BYTES - 1024) / SLAB_BYTES;   // 1024: worst-case base alignment slack
   return st > MAX_STAGES ? MAX_STAGES : st;
 }
+// single-pass needs the whole tile resident; two-pass only streams (a few slabs of slack keep the pipes busy)
+template <int NS> constexpr bool two_pass_shape() { return NS > 8; }
+template <int NS> constexpr int min_stages() { return two_pass_shape<NS>() ? 4 : NS; }
 
 template <int KP, int NS, int MODE>
 static int launch(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, const gf_attn_postop* post, cudaStream_t st) {
   using CF = Cfg<KP, NS, MODE>;
+  constexpr bool TWO = two_pass_shape<NS>();
   const int nst = stages_for<KP, NS, MODE>(device_smem_optin());
-  if (nst < NS) { set_error("tcgen05 path: shared memory too small for C=%d KP=%d mode=%d", L.C, KP, MODE); return GF_ERR_UNSUPPORTED; }
+  if (nst < min_stages<NS>()) { set_error("tcgen05 path: shared memory too small for C=%d KP=%d mode=%d", L.C, KP, MODE); return GF_ERR_UNSUPPORTED; }
   CUtensorMap tmX, tmO, tmK, tmV;
   int rc;
   const uint64_t rows = (uint64_t)L.B * L.n;
@@ -586,13 +629,14 @@ static int launch(const Layout& L, const gf_attn_desc* d, const float* X, float*
   P.n = L.n; P.H = L.H; P.W = L.W; P.k = L.k; P.Cout = L.Cout; P.B = L.B;
   P.norm_layer = d->norm == GF_NORM_LAYER ? 1 : 0;
   P.nstages = nst;
+  P.drain_each_tile = TWO ? (nst < 6 ? 1 : 0) : (nst < NS + 2 ? 1 : 0);
   P.tiles_per_image = L.n / TILE;
   P.total_tiles = (long long)L.B * P.tiles_per_image;
   P.has_post = post ? 1 : 0;
   P.pbias = post ? post->bias : nullptr; P.pnoise = post ? post->noise : nullptr; P.pstrength = post ? post->strength : nullptr;
   P.pnoise_bstride = post ? post->noise_bstride : 0; P.pact = post ? post->act : 0; P.pgain = post ? post->gain : 1.f;
   const int smem_bytes = CF::FIXED_BYTES + nst * SLAB_BYTES + 1024;
-  auto kern = token_tc_kernel<KP, NS, MODE>;
+  auto kern = token_tc_kernel<KP, NS, MODE, TWO>;
   GF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   long long grid = device_sms();
   if (grid > P.total_tiles) grid = P.total_tiles;
@@ -614,9 +658,29 @@ static int launch_mode(const Layout& L, const gf_attn_desc* d, const float* X, f
 template <int KP, int NS>
 static bool fits(int integration, int limit) {
   switch (integration) {
-    case GF_INT_MUL: return stages_for<KP, NS, GF_INT_MUL>(limit) >= NS;
-    case GF_INT_ADD: return stages_for<KP, NS, GF_INT_ADD>(limit) >= NS;
-    default: return stages_for<KP, NS, GF_INT_BOTH>(limit) >= NS;
+    case GF_INT_MUL: return stages_for<KP, NS, GF_INT_MUL>(limit) >= min_stages<NS>();
+    case GF_INT_ADD: return stages_for<KP, NS, GF_INT_ADD>(limit) >= min_stages<NS>();
+    default: return stages_for<KP, NS, GF_INT_BOTH>(limit) >= min_stages<NS>();
+  }
+}
+
+template <int KP>
+static bool fits_ns(int ns, int integration, int limit) {
+  switch (ns) {
+    case 2: return fits<KP, 2>(integration, limit);
+    case 4: return fits<KP, 4>(integration, limit);
+    case 8: return fits<KP, 8>(integration, limit);
+    default: return fits<KP, 16>(integration, limit);
+  }
+}
+
+template <int KP>
+static int launch_ns(int ns, const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, const gf_attn_postop* post, cudaStream_t st) {
+  switch (ns) {
+    case 2: return launch_mode<KP, 2>(L, d, X, Xout, att, ws, post, st);
+    case 4: return launch_mode<KP, 4>(L, d, X, Xout, att, ws, post, st);
+    case 8: return launch_mode<KP, 8>(L, d, X, Xout, att, ws, post, st);
+    default: return launch_mode<KP, 16>(L, d, X, Xout, att, ws, post, st);
   }
 }
 
@@ -625,26 +689,17 @@ static bool fits(int integration, int limit) {
 bool tc_supported(const Layout& L, const gf_attn_desc* d) {
   static const bool disabled = getenv("GF_DISABLE_TC") != nullptr;
   if (disabled) return false;
-  if (L.C != 64 && L.C != 128 && L.C != 256) return false;
+  if (L.C != 64 && L.C != 128 && L.C != 256 && L.C != 512) return false;
   if (L.n % tc::TILE != 0) return false;
   if (d->norm != GF_NORM_LAYER && d->norm != GF_NORM_NONE) return false;
   if ((long long)L.B * L.n > 0x7fffffffll) return false;
   const int limit = tc::device_smem_optin();
-  const int ns = L.C / 32;
-  if (L.KP == 16) return ns == 2 ? tc::fits<16, 2>(d->integration, limit) : ns == 4 ? tc::fits<16, 4>(d->integration, limit) : tc::fits<16, 8>(d->integration, limit);
-  return ns == 2 ? tc::fits<32, 2>(d->integration, limit) : ns == 4 ? tc::fits<32, 4>(d->integration, limit) : tc::fits<32, 8>(d->integration, limit);
+  return L.KP == 16 ? tc::fits_ns<16>(L.C / 32, d->integration, limit) : tc::fits_ns<32>(L.C / 32, d->integration, limit);
 }
 
 int token_pass_tc(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, const gf_attn_postop* post, cudaStream_t st) {
-  const int ns = L.C / 32;
-  if (L.KP == 16) {
-    if (ns == 2) return tc::launch_mode<16, 2>(L, d, X, Xout, att, ws, post, st);
-    if (ns == 4) return tc::launch_mode<16, 4>(L, d, X, Xout, att, ws, post, st);
-    return tc::launch_mode<16, 8>(L, d, X, Xout, att, ws, post, st);
-  }
-  if (ns == 2) return tc::launch_mode<32, 2>(L, d, X, Xout, att, ws, post, st);
-  if (ns == 4) return tc::launch_mode<32, 4>(L, d, X, Xout, att, ws, post, st);
-  return tc::launch_mode<32, 8>(L, d, X, Xout, att, ws, post, st);
+  if (L.KP == 16) return tc::launch_ns<16>(L.C / 32, L, d, X, Xout, att, ws, post, st);
+  return tc::launch_ns<32>(L.C / 32, L, d, X, Xout, att, ws, post, st);
 }
 
 }  // namespace gf
