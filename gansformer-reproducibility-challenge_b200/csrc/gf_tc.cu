@@ -629,7 +629,10 @@ static int launch(const Layout& L, const gf_attn_desc* d, const float* X, float*
   P.n = L.n; P.H = L.H; P.W = L.W; P.k = L.k; P.Cout = L.Cout; P.B = L.B;
   P.norm_layer = d->norm == GF_NORM_LAYER ? 1 : 0;
   P.nstages = nst;
-  P.drain_each_tile = TWO ? (nst < 6 ? 1 : 0) : (nst < NS + 2 ? 1 : 0);
+  // Ring slots are handed out strictly round-robin.  A store leader keeps its last slab one store longer (release lag);
+  // across a tile boundary that is only safe when the next tile never needs that slot: single-pass with nst >= NS + 2.
+  // A two-pass tile wraps the ring several times, so it always drains at tile end.
+  P.drain_each_tile = TWO ? 1 : (nst < NS + 2 ? 1 : 0);
   P.tiles_per_image = L.n / TILE;
   P.total_tiles = (long long)L.B * P.tiles_per_image;
   P.has_post = post ? 1 : 0;

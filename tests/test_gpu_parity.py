@@ -121,6 +121,25 @@ def test_simplex_layer_vs_oracle(gf, cuda_dev, shape, exact):
     assert (att.sum(dim=1) - 1).abs().max() < 1e-5
 
 
+@pytest.mark.parametrize("C,H,W,k,B,integration", [(512, 32, 32, 16, 40, "mul"),    # two-pass, 320 tiles: 2-3 tiles per CTA
+                                                    (128, 16, 16, 8, 200, "both"),   # 2 tiles per image: K'/V reloads inside a CTA
+                                                    (256, 16, 32, 32, 70, "mul"),    # ring barely larger than a tile
+                                                    (64, 32, 32, 16, 37, "add")])
+def test_persistent_schedule_many_tiles(gf, cuda_dev, C, H, W, k, B, integration):
+    """More tiles than SMs: every CTA walks several tiles, crosses image boundaries (K'/V^T reload) and wraps the
+    slab ring; checked against the fp64 oracle, with the attention map."""
+    D = p = 32
+    g = torch.Generator().manual_seed(C + B)
+    x = torch.randn(B, C, H, W, generator=g, dtype=torch.float64) * 1.2 + 0.1
+    y = torch.randn(B, k, D, generator=g, dtype=torch.float64)
+    w = ob.init_params(C, D, k, p, integration, False, seed=17, bias_std=0.3)
+    ref, ratt, _ = ob.transformer_layer(x, y, w, integration=integration, return_att=True)
+    out, att, _, path = run_layer(gf, cuda_dev, x, y, w, integration=integration, norm="layer", duplex=False, use_pos=True, exact=False)
+    assert path == "tcgen05_tf32"
+    check_close(out, ref.permute(0, 2, 3, 1), path, "many-tiles")
+    assert (att.cpu().double() - ratt).abs().max() <= 5e-3
+
+
 @pytest.mark.parametrize("exact", [True, False], ids=["fp32", "default"])
 @pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[3], SHAPES[5], SHAPES[6], SHAPES[8], SHAPES[10]],
                          ids=lambda s: "C%d-%dx%d-k%d-%s-%s" % (s[0], s[1], s[2], s[3], s[6], s[7]))

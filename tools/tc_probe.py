@@ -17,6 +17,11 @@ shapes = [  # C, H, W, k, integration, norm, B
     (256, 32, 32, 32, "mul", "layer", 5),
     (64, 64, 64, 8, "both", "layer", 40),
     (128, 128, 128, 16, "mul", "layer", 20),
+    (512, 16, 16, 16, "mul", "layer", 2),
+    (512, 32, 32, 8, "both", "layer", 3),
+    (512, 16, 16, 32, "mul", "none", 2),
+    (512, 64, 64, 16, "mul", "layer", 10),
+    (256, 64, 64, 32, "both", "layer", 6),
 ]
 if len(sys.argv) > 1:
     shapes = shapes[:int(sys.argv[1])]
