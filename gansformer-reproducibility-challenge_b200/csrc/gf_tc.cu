@@ -334,6 +334,12 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const uint32_t a_p = tmem + COL_P + buf * 32;
         for (int s = 0; s < NS; ++s, ++actr) {
           const int a = (int)(actr % NACC);
+          if (TWO_PASS) {
+            // Parity waits are only valid if a waiter never falls two phases behind a barrier: every consumer walks the
+            // fills of the ring in slot order.  Waiting the pass-2 fill here also makes acc_full(s) imply "slab s landed".
+            const long long c2 = it * SPT + NS + s;
+            mbar_wait(smem_u32(&bars->slab_full[(int)(c2 % nst)]), (uint32_t)((c2 / nst) & 1));
+          }
           mbar_wait(smem_u32(&bars->acc_empty[a]), (uint32_t)(((actr / NACC) & 1) ^ 1));
           tc_fence_after();
           const uint32_t d_acc = tmem + COL_ACC + a * 64;
@@ -452,6 +458,13 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bars->p_full[buf]));
+      if (TWO_PASS) {   // observe the pass-2 fills too (see the MMA warp): keeps this thread's parity bookkeeping in step
+#pragma unroll 1
+        for (int s = 0; s < NS; ++s) {
+          const long long c2 = it * SPT + NS + s;
+          mbar_wait(smem_u32(&bars->slab_full[(int)(c2 % nst)]), (uint32_t)((c2 / nst) & 1));
+        }
+      }
     }
   } else {
     // =============================== epilogue warps ===============================
@@ -486,8 +499,11 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const long long actr = it * NS + s;
         const int stage = (int)(ctr % nst);
         const int a = (int)(actr % NACC);
-        mbar_wait(smem_u32(&bars->slab_full[stage]), (uint32_t)((ctr / nst) & 1));
+        // acc_full first: GEMM2(s) was issued after GEMM1 of this tile completed (single-pass: every slab of the tile has
+        // landed) and, in two-pass mode, after the MMA warp saw this slab's pass-2 fill -- so the slab_full wait below can
+        // never be a phase early; it is kept for the async-proxy -> generic-proxy visibility of the TMA write.
         mbar_wait(smem_u32(&bars->acc_full[a]), (uint32_t)((actr / NACC) & 1));
+        mbar_wait(smem_u32(&bars->slab_full[stage]), (uint32_t)((ctr / nst) & 1));
         tc_fence_after();
         float gv[32], bv[MODE == GF_INT_BOTH ? 32 : 1];
         const uint32_t t_acc = tmem + lane_addr + COL_ACC + a * 64;

@@ -121,7 +121,8 @@ def test_simplex_layer_vs_oracle(gf, cuda_dev, shape, exact):
     assert (att.sum(dim=1) - 1).abs().max() < 1e-5
 
 
-@pytest.mark.parametrize("C,H,W,k,B,integration", [(512, 32, 32, 16, 40, "mul"),    # two-pass, 320 tiles: 2-3 tiles per CTA
+@pytest.mark.parametrize("C,H,W,k,B,integration", [(512, 64, 64, 16, 32, "mul"),    # the res-64 layer of config 2: two-pass, ~7 tiles/CTA
+                                                    (512, 32, 32, 16, 40, "mul"),    # two-pass, 320 tiles: 2-3 tiles per CTA
                                                     (128, 16, 16, 8, 200, "both"),   # 2 tiles per image: K'/V reloads inside a CTA
                                                     (256, 16, 32, 32, 70, "mul"),    # ring barely larger than a tile
                                                     (64, 32, 32, 16, 37, "add")])
