@@ -26,9 +26,9 @@ WEIGHT_FIELDS = ("wq", "bq", "wpq", "wk", "bk", "wpk", "wv", "bv", "wo", "bo", "
 EXPORTS = ("gf_attn_abi_version", "gf_last_error", "gf_attn_last_path", "gf_attn_folded_floats",
            "gf_attn_fold_weights", "gf_attn_workspace_bytes", "gf_attn_prologue", "gf_attn_simplex_fwd",
            "gf_attn_duplex_fwd", "gf_attn_norm_stats", "gf_attn_launch_count",
-           "gf_attn_simplex_fwd_ex", "gf_attn_duplex_fwd_ex")
+           "gf_attn_simplex_fwd_ex", "gf_attn_duplex_fwd_ex", "gf_attn_prologue_ex")
 # include/gf_ops.h
-OPS_EXPORTS = ("gf_chan_scale_nhwc", "gf_blur_up_nhwc", "gf_upsample2x_nchw", "gf_bias_act_nhwc")
+OPS_EXPORTS = ("gf_chan_scale_nhwc", "gf_blur_up_nhwc", "gf_upsample2x_nchw", "gf_bias_act_nhwc", "gf_demod_coef")
 
 
 class GfAttnDesc(ctypes.Structure):
@@ -42,7 +42,8 @@ class GfAttnWeights(ctypes.Structure):
 
 class GfAttnPostop(ctypes.Structure):
     _fields_ = [("bias", c_void_p), ("noise", c_void_p), ("strength", c_void_p), ("noise_bstride", ctypes.c_longlong),
-                ("act", c_int32), ("gain", ctypes.c_float)]
+                ("act", c_int32), ("gain", ctypes.c_float), ("in_scale", c_void_p), ("post_scale", c_void_p),
+                ("in_scale_ld", c_int32), ("post_scale_ld", c_int32)]
 
 
 _lib: Optional[ctypes.CDLL] = None
@@ -70,14 +71,16 @@ def load() -> ctypes.CDLL:
     lib.gf_attn_duplex_fwd.argtypes = [POINTER(GfAttnDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p]
     lib.gf_attn_norm_stats.argtypes = [POINTER(GfAttnDesc), c_void_p, c_void_p, c_void_p]
+    lib.gf_attn_prologue_ex.argtypes = [POINTER(GfAttnDesc), c_void_p, c_void_p, c_void_p, POINTER(GfAttnPostop), c_void_p]
     lib.gf_attn_simplex_fwd_ex.argtypes = [POINTER(GfAttnDesc), c_void_p, c_void_p, c_void_p, c_void_p, POINTER(GfAttnPostop), c_void_p]
     lib.gf_attn_duplex_fwd_ex.argtypes = [POINTER(GfAttnDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_void_p, POINTER(GfAttnPostop), c_void_p]
-    lib.gf_chan_scale_nhwc.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
+    lib.gf_chan_scale_nhwc.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]
     lib.gf_blur_up_nhwc.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, ctypes.c_float, c_void_p]
     lib.gf_upsample2x_nchw.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     lib.gf_bias_act_nhwc.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_int,
                                      c_int, ctypes.c_float, c_void_p]
+    lib.gf_demod_coef.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_float, c_void_p]
     for name in OPS_EXPORTS:
         getattr(lib, name).restype = c_int
     for name in EXPORTS:

@@ -87,7 +87,9 @@ def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[s
     """x [B,H,W,C] channels-last fp32 (CUDA), y [B,k,D].  Returns (x', att [B,k,H,W] | None, centroids | None).
 
     postop (optional): dict(bias [C] | None, noise [H*W] or [B,H*W] | None, strength 0-d tensor | None, act 'lrelu' |
-    'linear', gain float) -- the noise + fused_bias_act step that follows the block, fused into the kernel's store."""
+    'linear', gain float, in_scale [B,C] | None, post_scale [B,C] | None) -- the demodulation scale of the preceding
+    convolution (load side) and the noise + fused_bias_act step + next-layer style scale (store side), fused into the
+    kernel."""
     lib = _lib.load()
     if x.dim() != 4:
         raise ValueError("x must be [B, H, W, C] (channels-last)")
@@ -152,6 +154,18 @@ def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[s
             pst.noise_bstride = H * W if (nz is not None and nz.numel() == B * H * W and B > 1) else 0
             pst.act = {"linear": 0, "lrelu": 1}[postop.get("act", "lrelu")]
             pst.gain = float(postop.get("gain", 1.0))
+            for fld in ("in_scale", "post_scale"):
+                t = postop.get(fld)
+                if t is None:
+                    continue
+                t = t.detach()
+                if t.shape != (B, C) or t.dtype != torch.float32 or t.device != dev:
+                    raise ValueError(f"postop.{fld} must be a float32 [B, C] tensor on {dev}")
+                if not (t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.stride(0) >= C and t.data_ptr() % 16 == 0):
+                    t = t.contiguous()
+                keep.append(t)
+                setattr(pst, fld, t.data_ptr())
+                setattr(pst, fld + "_ld", t.stride(0))
             post_ref = ctypes.byref(pst)
         timer = STAGE_TIMER
         if timer is not None:
@@ -169,8 +183,8 @@ def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[s
                        "gf_attn_duplex_fwd_ex")
         else:
             cen = None
-            _lib.check(lib.gf_attn_prologue(ctypes.byref(desc), y.data_ptr(), plan.folded.data_ptr(), ws.data_ptr(), stream),
-                       "gf_attn_prologue")
+            _lib.check(lib.gf_attn_prologue_ex(ctypes.byref(desc), y.data_ptr(), plan.folded.data_ptr(), ws.data_ptr(), post_ref, stream),
+                       "gf_attn_prologue_ex")
             if timer is not None:
                 ev0.record()
             _lib.check(lib.gf_attn_simplex_fwd_ex(ctypes.byref(desc), x.data_ptr(), out.data_ptr(), _ptr(att), ws.data_ptr(),

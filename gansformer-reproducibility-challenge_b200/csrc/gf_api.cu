@@ -40,6 +40,15 @@ static int token_pass(const Layout& L, const gf_attn_desc* d, const float* X, fl
                       const gf_attn_postop* post, cudaStream_t st) {
   int rc;
   if (post && (post->act < 0 || post->act > 1)) { set_error("postop: act must be 0 (linear) or 1 (lrelu), got %d", post->act); return GF_ERR_INVALID; }
+  if (post && (post->in_scale || post->post_scale)) {
+    if (d->norm != GF_NORM_LAYER && d->norm != GF_NORM_NONE) { set_error("postop: in_scale/post_scale need norm layer or none"); return GF_ERR_UNSUPPORTED; }
+    if (d->duplex && post->in_scale) { set_error("postop: in_scale is not supported for duplex layers"); return GF_ERR_UNSUPPORTED; }
+    if ((post->in_scale && (post->in_scale_ld < L.C || (post->in_scale_ld & 3) || ((uintptr_t)post->in_scale & 15))) ||
+        (post->post_scale && (post->post_scale_ld < L.C || (post->post_scale_ld & 3) || ((uintptr_t)post->post_scale & 15)))) {
+      set_error("postop: scale rows must be 16-byte aligned with ld >= C and ld %% 4 == 0");
+      return GF_ERR_INVALID;
+    }
+  }
   if ((rc = norm_stats(L, d, X, ws, st))) return rc;
   if (!(d->flags & GF_FLAG_FP32_EXACT) && tc_supported(L, d)) return token_pass_tc(L, d, X, Xout, att, ws, post, st);
   return token_pass_simt(L, d, X, Xout, att, ws, post, st);
@@ -84,13 +93,17 @@ int gf_attn_fold_weights(const gf_attn_desc* desc, const gf_attn_weights* weight
 }
 
 int gf_attn_prologue(const gf_attn_desc* desc, const float* Y, const float* folded, void* ws, void* stream) {
+  return gf_attn_prologue_ex(desc, Y, folded, ws, nullptr, stream);
+}
+
+int gf_attn_prologue_ex(const gf_attn_desc* desc, const float* Y, const float* folded, void* ws, const gf_attn_postop* post, void* stream) {
   Layout L;
   int rc = make_layout(desc, &L);
   if (rc) return rc;
   if (!Y || !folded || !ws) { set_error("gf_attn_prologue: null pointer"); return GF_ERR_INVALID; }
   if (L.duplex) { set_error("gf_attn_prologue: duplex layers build their keys inside gf_attn_duplex_fwd"); return GF_ERR_INVALID; }
   if ((rc = check_device())) return rc;
-  return prologue(L, desc, Y, Y, L.D, folded, (float*)ws, (cudaStream_t)stream);
+  return prologue(L, desc, Y, Y, L.D, folded, (float*)ws, (cudaStream_t)stream, post ? post->in_scale : nullptr, post ? post->in_scale_ld : 0);
 }
 
 int gf_attn_norm_stats(const gf_attn_desc* desc, const float* X, void* ws, void* stream) {

@@ -61,7 +61,7 @@ int make_layout(const gf_attn_desc* d, Layout* L);
 int fold_weights(const Layout& L, const gf_attn_desc* d, const gf_attn_weights* w, float* folded, cudaStream_t st);
 // key_source: Y [B*k, D] (simplex) or centroids [B*k, C] (duplex); kdim = D or C.
 int prologue(const Layout& L, const gf_attn_desc* d, const float* Y, const float* key_source, int kdim,
-             const float* folded, float* ws, cudaStream_t st);
+             const float* folded, float* ws, cudaStream_t st, const float* in_scale = nullptr, int in_scale_ld = 0);
 int duplex_tables(const Layout& L, const gf_attn_desc* d, const float* Y, const float* folded, float* ws, cudaStream_t st);
 // C[M,N] = alpha * opA(A) opB(B) + E[(m % emod), n] + v[n]
 int gemm(cudaStream_t st, int M, int N, int K, const float* A, int lda, bool ta, const float* B, int ldb, bool tb,

@@ -237,7 +237,7 @@ int fold_weights(const Layout& L, const gf_attn_desc* d, const gf_attn_weights* 
 // ------------------------------------------------------------------------------------------------------
 // stage I: per-image tables
 // ------------------------------------------------------------------------------------------------------
-// grid (nblk, B).  blockIdx.x == 0: positional logit tables Rt/Ct of image b.  blockIdx.x >= 1: Kp and (optionally) Vt.
+// grid (npos + nblk, B).  blockIdx.x < npos: positional logit tables Rt/Ct of image b.  Others: Kp and (optionally) Vt.
 // fp32 -> nearest-even TF32 (10 mantissa bits).  The tensor cores TRUNCATE fp32 operands to TF32; pre-rounding the
 // small operands (K', V^T, and P in the kernel) makes that truncation a no-op for them and halves their error.
 __device__ __forceinline__ float round_tf32(float v) {
@@ -256,12 +256,12 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
                                                        float* __restrict__ Kp, float* __restrict__ Vt,
                                                        float* __restrict__ Rt, float* __restrict__ Ct,
                                                        int H, int W, int C, int k, int D, int p, int KP, int Cout, int LDK,
-                                                       int tf32) {
+                                                       int tf32, int npos, const float* __restrict__ in_scale, int in_ld) {
   const int b = blockIdx.y;
   const float* kp = kpall + (size_t)b * k * LDK;
-  if (blockIdx.x == 0) {
+  if ((int)blockIdx.x < npos) {
     const int half = p / 2;
-    for (int i = threadIdx.x; i < (H + W) * KP; i += blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (H + W) * KP; i += npos * blockDim.x) {
       const int r = i / KP, j = i % KP;
       const bool is_row = r < H;
       float val;
@@ -284,11 +284,12 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
     return;
   }
   const int nK = KP * C, nV = Vt ? Cout * KP : 0;
-  const int stride = (gridDim.x - 1) * blockDim.x;
-  for (int i = (blockIdx.x - 1) * blockDim.x + threadIdx.x; i < nK + nV; i += stride) {
+  const int stride = (gridDim.x - npos) * blockDim.x;
+  for (int i = (blockIdx.x - npos) * blockDim.x + threadIdx.x; i < nK + nV; i += stride) {
     if (i < nK) {
       const int j = i / C, c = i % C;
       float v = j < k ? kp[(size_t)j * LDK + c] : 0.f;
+      if (in_scale) v *= in_scale[(size_t)b * in_ld + c];      // x_in = x * in_scale: (x*d).K' == x.(K'*d)
       if (tf32) v = round_tf32(v * GF_TF32_TRUNC_COMP);
       Kp[(size_t)b * nK + i] = v;
     } else {
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
 }
 
 int prologue(const Layout& L, const gf_attn_desc* d, const float* Y, const float* key_source, int kdim,
-             const float* f, float* ws, cudaStream_t st) {
+             const float* f, float* ws, cudaStream_t st, const float* in_scale, int in_scale_ld) {
   int rc;
   // operands of the tcgen05 TF32 contractions are pre-rounded here; the fp32-FMA kernel gets them untouched
   const int tf32 = (!(d->flags & GF_FLAG_FP32_EXACT) && tc_supported(L, d)) ? 1 : 0;
@@ -314,10 +315,11 @@ int prologue(const Layout& L, const gf_attn_desc* d, const float* Y, const float
                  f + L.f_CK, L.LDK, L.k)))
     return rc;
   const int nel = L.KP * L.C + L.Cout * L.KP;
-  int nblk = 1 + (nel + 256 * 8 - 1) / (256 * 8);
+  const int npos = ((L.H + L.W) * L.KP + 1023) / 1024;
+  int nblk = npos + (nel + 256 * 4 - 1) / (256 * 4);
   finalize_kernel<<<dim3(nblk, L.B), 256, 0, st>>>(ws + L.w_KPALL, Y, f + L.f_AV, f + L.f_CV, f + L.f_ROW, f + L.f_COL,
                                                    ws + L.w_Kp, ws + L.w_Vt, ws + L.w_Rt, ws + L.w_Ct,
-                                                   L.H, L.W, L.C, L.k, L.D, L.p, L.KP, L.Cout, L.LDK, tf32);
+                                                   L.H, L.W, L.C, L.k, L.D, L.p, L.KP, L.Cout, L.LDK, tf32, npos, in_scale, in_scale_ld);
   GF_LAUNCH_OK();
   return GF_OK;
 }
@@ -330,10 +332,11 @@ int duplex_tables(const Layout& L, const gf_attn_desc* d, const float* Y, const 
                  f + L.f_CM, L.LDK, L.k)))
     return rc;
   const int nel = L.KP * L.C;
-  int nblk = 1 + (nel + 256 * 8 - 1) / (256 * 8);
+  const int npos = ((L.H + L.W) * L.KP + 1023) / 1024;
+  int nblk = npos + (nel + 256 * 4 - 1) / (256 * 4);
   finalize_kernel<<<dim3(nblk, L.B), 256, 0, st>>>(ws + L.w_MALL, Y, nullptr, nullptr, f + L.f_ROW, f + L.f_COL,
                                                    ws + L.w_M, nullptr, ws + L.w_Rt2, ws + L.w_Ct2,
-                                                   L.H, L.W, L.C, L.k, L.D, L.p, L.KP, L.Cout, L.LDK, 0);
+                                                   L.H, L.W, L.C, L.k, L.D, L.p, L.KP, L.Cout, L.LDK, 0, npos, nullptr, 0);
   GF_LAUNCH_OK();
   return GF_OK;
 }

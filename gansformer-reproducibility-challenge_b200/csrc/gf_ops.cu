@@ -16,10 +16,10 @@ static inline int grid_for(size_t work_items, int threads) {
 }
 
 __global__ void __launch_bounds__(256) chan_scale_kernel(const float4* __restrict__ x, const float4* __restrict__ s,
-                                                         float4* __restrict__ y, size_t total4, int hw_c4, int c4n) {
+                                                         float4* __restrict__ y, size_t total4, int hw_c4, int c4n, int s_ld4) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
     const int b = (int)(i / hw_c4), c4 = (int)(i % c4n);
-    const float4 v = x[i], sc = __ldg(s + (size_t)b * c4n + c4);
+    const float4 v = x[i], sc = __ldg(s + (size_t)b * s_ld4 + c4);
     y[i] = make_float4(v.x * sc.x, v.y * sc.y, v.z * sc.z, v.w * sc.w);
   }
 }
@@ -124,18 +124,36 @@ __global__ void __launch_bounds__(256) bias_act_kernel(const float4* __restrict_
   }
 }
 
+// d[b,o] = rsqrt(sum_i s[b,i]^2 * wsq[o,i] + eps): one warp per output, lanes stride over i
+__global__ void __launch_bounds__(256) demod_coef_kernel(const float* __restrict__ s, const float* __restrict__ wsq,
+                                                         float* __restrict__ d, int B, int O, int I, float eps, int s_ld) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B * O) return;
+  const int b = warp / O, o = warp % O;
+  const float* sb = s + (size_t)b * s_ld;
+  const float* wo = wsq + (size_t)o * I;
+  float acc = 0.f;
+  for (int i = lane; i < I; i += 32) { const float v = sb[i]; acc = fmaf(v * v, wo[i], acc); }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) d[warp] = rsqrtf(acc + eps);
+}
+
 }  // namespace gf
 
 using namespace gf;
 
 extern "C" {
 
-int gf_chan_scale_nhwc(const float* x, const float* s, float* y, int B, int HW, int C, void* stream) {
+int gf_chan_scale_nhwc(const float* x, const float* s, int s_ld, float* y, int B, int HW, int C, void* stream) {
   if (!x || !s || !y) { set_error("gf_chan_scale_nhwc: null pointer"); return GF_ERR_INVALID; }
-  if (B <= 0 || HW <= 0 || C <= 0 || (C & 3)) { set_error("gf_chan_scale_nhwc: need B,HW,C > 0 and C %% 4 == 0 (C=%d)", C); return GF_ERR_UNSUPPORTED; }
+  if (B <= 0 || HW <= 0 || C <= 0 || (C & 3) || s_ld < C || (s_ld & 3) || ((uintptr_t)s & 15)) {
+    set_error("gf_chan_scale_nhwc: need B,HW,C > 0, C %% 4 == 0, s_ld >= C, s_ld %% 4 == 0, s 16-byte aligned (C=%d s_ld=%d)", C, s_ld);
+    return GF_ERR_UNSUPPORTED;
+  }
   const size_t total4 = (size_t)B * HW * (C >> 2);
   chan_scale_kernel<<<grid_for(total4, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(s), reinterpret_cast<float4*>(y), total4, HW * (C >> 2), C >> 2);
+      reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(s), reinterpret_cast<float4*>(y), total4, HW * (C >> 2), C >> 2, s_ld >> 2);
   GF_LAUNCH_OK();
   return GF_OK;
 }
@@ -166,6 +184,15 @@ int gf_bias_act_nhwc(const float* x, float* y, const float* bias, const float* n
   const size_t total4 = (size_t)B * HW * (C >> 2);
   bias_act_kernel<<<grid_for(total4, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), bias, noise, strength, noise_bstride, total4, HW, C >> 2, act, gain);
+  GF_LAUNCH_OK();
+  return GF_OK;
+}
+
+int gf_demod_coef(const float* styles, int s_ld, const float* wsq, float* d, int B, int O, int I, float eps, void* stream) {
+  if (!styles || !wsq || !d) { set_error("gf_demod_coef: null pointer"); return GF_ERR_INVALID; }
+  if (B <= 0 || O <= 0 || I <= 0 || s_ld < I) { set_error("gf_demod_coef: bad shape"); return GF_ERR_INVALID; }
+  const long long warps = (long long)B * O;
+  demod_coef_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(styles, wsq, d, B, O, I, eps, s_ld);
   GF_LAUNCH_OK();
   return GF_OK;
 }

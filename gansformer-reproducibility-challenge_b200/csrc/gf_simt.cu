@@ -20,6 +20,7 @@ struct TokenParams {
   int norm, integration;
   // fused epilogue (gf_attn_postop)
   const float* pbias; const float* pnoise; const float* pstrength; long long pnoise_bstride; int pact; float pgain; int has_post;
+  const float* in_scale; const float* post_scale; int in_ld, post_ld;
 };
 
 __device__ __forceinline__ void load_x_chunk(float (*xs)[XS], const float* __restrict__ Xb, int t0, int n, int C, int c0) {
@@ -38,7 +39,7 @@ __global__ void __launch_bounds__(TM) token_simt_kernel(const TokenParams P) {
   __shared__ __align__(16) float xs[TM][XS];
   __shared__ __align__(16) float ks[KP][CH];        // K' chunk, later reused for V^T chunks [CH][KP] (gain)
   __shared__ __align__(16) float vs2[CH][KP];       // bias half of V^T ("both")
-  __shared__ float nsc[CH], nsh[CH], pbs[CH];
+  __shared__ float nsc[CH], nsh[CH], pbs[CH], isc[CH], psc[CH];
 
   const int b = blockIdx.y, t0 = blockIdx.x * TM, tid = threadIdx.x, t = t0 + tid;
   const int n = P.n, C = P.C;
@@ -66,12 +67,15 @@ __global__ void __launch_bounds__(TM) token_simt_kernel(const TokenParams P) {
       const int j = i / (CH / 4), c4 = (i % (CH / 4)) * 4;
       *reinterpret_cast<float4*>(&ks[j][c4]) = __ldg(reinterpret_cast<const float4*>(Kpb + (size_t)j * C + c0 + c4));
     }
+    if (tid < CH) isc[tid] = P.in_scale ? P.in_scale[(size_t)b * P.in_ld + c0 + tid] : 1.f;
     __syncthreads();
-    if (c0 == 0) shift = xs[tid][0];   // shifted sums: avoids cancellation in E[x^2]-E[x]^2
+    if (c0 == 0) shift = xs[tid][0] * isc[0];   // shifted sums: avoids cancellation in E[x^2]-E[x]^2
 #pragma unroll
     for (int c4 = 0; c4 < CH; c4 += 4) {
-      const float4 x = *reinterpret_cast<const float4*>(&xs[tid][c4]);
-      const float d0 = x.x - shift, d1 = x.y - shift, d2 = x.z - shift, d3 = x.w - shift;
+      const float4 xr = *reinterpret_cast<const float4*>(&xs[tid][c4]);
+      const float4 xq = make_float4(xr.x * isc[c4], xr.y * isc[c4 + 1], xr.z * isc[c4 + 2], xr.w * isc[c4 + 3]);   // statistics see x_in
+      const float4 x = xr;                                                                                        // logits: K' already carries in_scale
+      const float d0 = xq.x - shift, d1 = xq.y - shift, d2 = xq.z - shift, d3 = xq.w - shift;
       sum += (d0 + d1) + (d2 + d3);
       sumsq = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, sumsq))));
 #pragma unroll
@@ -127,6 +131,10 @@ __global__ void __launch_bounds__(TM) token_simt_kernel(const TokenParams P) {
       nsh[tid] = P.nshift[(size_t)b * C + c0 + tid];
     }
     if (P.has_post && tid < CH) pbs[tid] = P.pbias ? P.pbias[c0 + tid] : 0.f;
+    if (tid < CH) {
+      isc[tid] = P.in_scale ? P.in_scale[(size_t)b * P.in_ld + c0 + tid] : 1.f;
+      psc[tid] = P.post_scale ? P.post_scale[(size_t)b * P.post_ld + c0 + tid] : 1.f;
+    }
     __syncthreads();
 #pragma unroll 4
     for (int cc = 0; cc < CH; ++cc) {
@@ -136,7 +144,7 @@ __global__ void __launch_bounds__(TM) token_simt_kernel(const TokenParams P) {
         const float4 v = *reinterpret_cast<const float4*>(&vs[cc][j4]);
         g = fmaf(s[j4], v.x, fmaf(s[j4 + 1], v.y, fmaf(s[j4 + 2], v.z, fmaf(s[j4 + 3], v.w, g))));
       }
-      const float x = xs[tid][cc];
+      const float x = xs[tid][cc] * isc[cc];
       float xn;
       if (affine) xn = fmaf(x, nsc[cc], nsh[cc]);
       else xn = (x - mean) * rstd;
@@ -155,7 +163,7 @@ __global__ void __launch_bounds__(TM) token_simt_kernel(const TokenParams P) {
       if (P.has_post) {
         y += pnz + pbs[cc];
         if (P.pact == 1) y = fmaxf(y, 0.2f * y);
-        y *= P.pgain;
+        y *= P.pgain * psc[cc];
       }
       xs[tid][cc] = y;
     }
@@ -179,6 +187,8 @@ int token_pass_simt(const Layout& L, const gf_attn_desc* d, const float* X, floa
   P.has_post = post ? 1 : 0;
   P.pbias = post ? post->bias : nullptr; P.pnoise = post ? post->noise : nullptr; P.pstrength = post ? post->strength : nullptr;
   P.pnoise_bstride = post ? post->noise_bstride : 0; P.pact = post ? post->act : 0; P.pgain = post ? post->gain : 1.f;
+  P.in_scale = post ? post->in_scale : nullptr; P.post_scale = post ? post->post_scale : nullptr;
+  P.in_ld = post ? post->in_scale_ld : 0; P.post_ld = post ? post->post_scale_ld : 0;
   dim3 grid((L.n + TM - 1) / TM, L.B);
   if (L.KP == 16) token_simt_kernel<16><<<grid, TM, 0, st>>>(P);
   else token_simt_kernel<32><<<grid, TM, 0, st>>>(P);

@@ -46,6 +46,7 @@ struct Params {
   int tiles_per_image;
   // fused epilogue (gf_attn_postop)
   const float* pbias; const float* pnoise; const float* pstrength; long long pnoise_bstride; int pact; float pgain; int has_post;
+  const float* in_scale; const float* post_scale; int in_ld, post_ld;   // per-(b,c) load-side / store-side scales
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -396,9 +397,11 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           mbar_wait(smem_u32(&bars->slab_full[stage]), (uint32_t)((ctr / nst) & 1));
           if (P.norm_layer) {
             const uint8_t* slab = smem + CF::OFF_RING + stage * SLAB_BYTES + row_off;
+            const float4* isc = P.in_scale ? reinterpret_cast<const float4*>(P.in_scale + (size_t)b * P.in_ld + s * SLAB_CH) : nullptr;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-              const float4 x = *reinterpret_cast<const float4*>(slab + ((c ^ sw) << 4));
+              float4 x = *reinterpret_cast<const float4*>(slab + ((c ^ sw) << 4));
+              if (isc) { const float4 d = __ldg(isc + c); x.x *= d.x; x.y *= d.y; x.z *= d.z; x.w *= d.w; }   // warp-uniform address
               if (s == 0 && c == 0) sh = x.x;
               const float d0 = x.x - sh, d1 = x.y - sh, d2 = x.z - sh, d3 = x.w - sh;
               sum += (d0 + d1) + (d2 + d3);
@@ -515,10 +518,13 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[a]));
         uint8_t* slab = smem + CF::OFF_RING + stage * SLAB_BYTES + row_off;
+        const float4* isc = P.in_scale ? reinterpret_cast<const float4*>(P.in_scale + (size_t)b * P.in_ld + s * SLAB_CH) : nullptr;
+        const float4* psc = P.post_scale ? reinterpret_cast<const float4*>(P.post_scale + (size_t)b * P.post_ld + s * SLAB_CH) : nullptr;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float4* px = reinterpret_cast<float4*>(slab + ((c ^ sw) << 4));
           float4 x = *px;
+          if (isc) { const float4 d = __ldg(isc + c); x.x *= d.x; x.y *= d.y; x.z *= d.z; x.w *= d.w; }
           float xn0 = fmaf(x.x, rstd, mr), xn1 = fmaf(x.y, rstd, mr), xn2 = fmaf(x.z, rstd, mr), xn3 = fmaf(x.w, rstd, mr);
           if constexpr (MODE == GF_INT_MUL) {
             x.x = xn0 * gv[c * 4 + 0]; x.y = xn1 * gv[c * 4 + 1]; x.z = xn2 * gv[c * 4 + 2]; x.w = xn3 * gv[c * 4 + 3];
@@ -533,6 +539,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             x.x += pnz + pb.x; x.y += pnz + pb.y; x.z += pnz + pb.z; x.w += pnz + pb.w;
             if (P.pact == 1) { x.x = fmaxf(x.x, 0.2f * x.x); x.y = fmaxf(x.y, 0.2f * x.y); x.z = fmaxf(x.z, 0.2f * x.z); x.w = fmaxf(x.w, 0.2f * x.w); }
             x.x *= P.pgain; x.y *= P.pgain; x.z *= P.pgain; x.w *= P.pgain;
+            if (psc) { const float4 q4 = __ldg(psc + c); x.x *= q4.x; x.y *= q4.y; x.z *= q4.z; x.w *= q4.w; }
           }
           *px = x;
         }
@@ -654,6 +661,8 @@ static int launch(const Layout& L, const gf_attn_desc* d, const float* X, float*
   P.has_post = post ? 1 : 0;
   P.pbias = post ? post->bias : nullptr; P.pnoise = post ? post->noise : nullptr; P.pstrength = post ? post->strength : nullptr;
   P.pnoise_bstride = post ? post->noise_bstride : 0; P.pact = post ? post->act : 0; P.pgain = post ? post->gain : 1.f;
+  P.in_scale = post ? post->in_scale : nullptr; P.post_scale = post ? post->post_scale : nullptr;
+  P.in_ld = post ? post->in_scale_ld : 0; P.post_ld = post ? post->post_scale_ld : 0;
   const int smem_bytes = CF::FIXED_BYTES + nst * SLAB_BYTES + 1024;
   auto kern = token_tc_kernel<KP, NS, MODE, TWO>;
   GF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));

@@ -26,31 +26,59 @@ from .ops import fir_filter
 SQRT2 = math.sqrt(2.0)
 
 
+def _inference(*params) -> bool:
+    """True when no autograd graph is needed: derived tensors (scaled weights, ...) may then be cached."""
+    return not (torch.is_grad_enabled() and any(p.requires_grad for p in params))
+
+
+def _cached(module: nn.Module, key: str, params, fn):
+    """Cache `fn()` on `module` until one of `params` changes (version counter / storage / device)."""
+    ver = tuple((p.data_ptr(), p._version, str(p.device), p.dtype) for p in params)
+    store = module.__dict__.setdefault("_icache", {})
+    ent = store.get(key)
+    if ent is None or ent[0] != ver:
+        with torch.no_grad():
+            ent = (ver, fn())
+        store[key] = ent
+    return ent[1]
+
+
 def nf(res: int, fmap_base: int = 16384, fmap_max: int = 512) -> int:
     """StyleGAN2 config-f channel schedule."""
     return int(min(fmap_base // (2 ** (int(math.log2(res)) - 1)), fmap_max))
 
 
 def modulated_conv2d(x: torch.Tensor, weight: torch.Tensor, styles: torch.Tensor, *, demodulate: bool = True,
-                     up: int = 1, f: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     up: int = 1, f: Optional[torch.Tensor] = None, w_eff: Optional[torch.Tensor] = None,
+                     wsq: Optional[torch.Tensor] = None, prescaled: bool = False, defer_demod: bool = False):
     """StyleGAN2 modulated convolution in its activation-scaling form: (x * s) conv w, then * demod.
 
     Identical in exact arithmetic to modulating the weights per sample (the reference's grouped-conv form);
     avoids B separate weight tensors.  weight [O, I, kh, kw]; styles [B, I].  The two scalings and the FIR blur of the
-    upsampling path are the native ops of ops.py (gf_ops.h); the convolution itself is cuDNN (SURVEY row f1 is next)."""
+    upsampling path are the native ops of ops.py (gf_ops.h); the convolution itself is cuDNN (SURVEY row f1 is next).
+    w_eff / wsq: optional cached equalised-LR weight (already transposed for up=2) and its squared sum over the taps.
+    prescaled: x already carries the style scale (fused into the producer's store).  defer_demod (up == 1 only): return
+    (conv output, d) and let the consumer (the attention kernel's load side) apply the demodulation."""
     O, I, kh, kw = weight.shape
-    w = weight * (1.0 / math.sqrt(I * kh * kw))
+    if w_eff is None:
+        w_eff = weight * (1.0 / math.sqrt(I * kh * kw))
+        if up != 1:
+            w_eff = w_eff.transpose(0, 1)
     d = None
     if demodulate:
-        wsq = w.square().sum(dim=[2, 3])                               # [O, I]
-        d = torch.rsqrt(styles.square() @ wsq.t() + 1e-8)             # [B, O]
-    x = ops.chan_scale(x, styles)
+        if wsq is None:
+            wsq = (weight * (1.0 / math.sqrt(I * kh * kw))).square().sum(dim=[2, 3])    # [O, I]
+        d = ops.demod_coef(styles, wsq)                                                  # [B, O]
+    if not prescaled:
+        x = ops.chan_scale(x, styles)
     if up == 1:
-        x = F.conv2d(x, w, padding=kh // 2)
+        x = F.conv2d(x, w_eff, padding=kh // 2)
+        if defer_demod:
+            return x, d
         if d is not None:
             x = ops.chan_scale(x, d)
     else:
-        x = F.conv_transpose2d(x, w.transpose(0, 1), stride=2)        # [B, O, 2H+1, 2W+1]
+        x = F.conv_transpose2d(x, w_eff, stride=2)                    # [B, O, 2H+1, 2W+1]
         x = ops.blur_up(x, f, scale=d, gain=4.0)                       # -> [B, O, 2H, 2W], demodulated
     return x
 
@@ -64,7 +92,16 @@ class FullyConnected(nn.Module):
         self.bgain = lr_mul
         self.act = act
 
+    def effective(self):
+        """(W^T [in,out], b [out]) with the equalised-LR gains folded in (and sqrt(2) for lrelu: lrelu(z)*g == lrelu(g*z))."""
+        g = SQRT2 if self.act == "lrelu" else 1.0
+        return (self.weight * (self.wgain * g)).t().contiguous(), self.bias * (self.bgain * g)
+
     def forward(self, x):
+        if _inference(self.weight, self.bias):
+            wt, b = _cached(self, "eff", (self.weight, self.bias), self.effective)
+            y = torch.addmm(b, x.reshape(-1, x.shape[-1]), wt).reshape(*x.shape[:-1], wt.shape[1])
+            return F.leaky_relu(y, 0.2) if self.act == "lrelu" else y
         x = F.linear(x, self.weight * self.wgain, self.bias * self.bgain)
         return F.leaky_relu(x, 0.2) * SQRT2 if self.act == "lrelu" else x
 
@@ -110,9 +147,37 @@ class SynthesisLayer(nn.Module):
         self.register_buffer("fir", fir_filter())
         self.attention = BipartiteAttention(out_ch, w_dim, components_num, **attn_kwargs) if use_attention else None
 
-    def forward(self, x, w_glob, y, noise_mode="const", centroids=None, return_att=False):
-        styles = self.affine(w_glob)
-        x = modulated_conv2d(x, self.weight, styles, up=2 if self.up else 1, f=self.fir)
+    def _conv_weights(self):
+        O, I, kh, kw = self.weight.shape
+        w = self.weight * (1.0 / math.sqrt(I * kh * kw))
+        wsq = w.square().sum(dim=[2, 3])
+        if self.up:
+            w = w.transpose(0, 1)
+        return w.contiguous(memory_format=torch.channels_last), wsq.contiguous()
+
+    def fusable(self, x) -> bool:
+        """Inference on CUDA with an attention block whose norm the kernels can fuse around."""
+        a = self.attention
+        return (a is not None and x.is_cuda and a.norm in ("layer", None, "none") and not a.duplex
+                and _inference(self.weight, self.bias, self.noise_strength, *a.parameters()))
+
+    def forward(self, x, w_glob, y, noise_mode="const", centroids=None, return_att=False, styles=None,
+                prescaled=False, post_scale=None):
+        """prescaled: x already carries this layer's style scale.  post_scale [B,C]: the NEXT convolution's style scale,
+        folded into this layer's store (only honoured -- and only passed by SynthesisNetwork -- when `fusable`)."""
+        if styles is None:
+            styles = self.affine(w_glob)
+        w_eff = wsq = None
+        if _inference(self.weight) and x.is_cuda:
+            w_eff, wsq = _cached(self, "conv", (self.weight,), self._conv_weights)
+        fused = self.fusable(x)
+        in_scale = None
+        if fused and not self.up:      # demodulation rides on the attention kernel's load side (folded into K')
+            x, in_scale = modulated_conv2d(x, self.weight, styles, up=1, f=self.fir, w_eff=w_eff, wsq=wsq,
+                                           prescaled=prescaled, defer_demod=True)
+        else:
+            x = modulated_conv2d(x, self.weight, styles, up=2 if self.up else 1, f=self.fir, w_eff=w_eff, wsq=wsq,
+                                 prescaled=prescaled)
         if noise_mode == "const":
             noise = self.noise_const
         elif noise_mode == "random":
@@ -124,14 +189,16 @@ class SynthesisLayer(nn.Module):
             xl = x.permute(0, 2, 3, 1)                                  # channels-last storage -> [B,H,W,C] view
             if not xl.is_contiguous():
                 xl = xl.contiguous()
-            fused = x.is_cuda and not (torch.is_grad_enabled() and (x.requires_grad or self.bias.requires_grad))
-            if fused:   # noise + bias + leaky-ReLU ride on the attention kernel's store
-                post = dict(bias=self.bias, noise=noise, strength=self.noise_strength, act="lrelu", gain=SQRT2)
+            if fused:   # demod (load side) + noise + bias + leaky-ReLU + next style (store side) ride on the attention kernel
+                post = dict(bias=self.bias, noise=noise, strength=self.noise_strength, act="lrelu", gain=SQRT2,
+                            in_scale=in_scale, post_scale=post_scale)
                 xo, att, centroids = self.attention(xl, y, centroids=centroids, return_att=return_att, postop=post)
                 return xo.permute(0, 3, 1, 2), att, centroids
             xo, att, centroids = self.attention(xl, y, centroids=centroids, return_att=return_att)
             x = xo.permute(0, 3, 1, 2)                                  # back to an NCHW view of channels-last data
         x = ops.bias_act(x, self.bias, "lrelu", noise=noise, strength=self.noise_strength)
+        if post_scale is not None:
+            x = ops.chan_scale(x, post_scale)
         return x, att, centroids
 
 
@@ -142,10 +209,11 @@ class ToRGB(nn.Module):
         self.weight = nn.Parameter(torch.randn(img_channels, in_ch, 1, 1))
         self.bias = nn.Parameter(torch.zeros(img_channels))
 
-    def forward(self, x, w_glob):
+    def forward(self, x, w_glob, styles=None):
         """1x1 modulated conv without demodulation: the style is folded into per-sample [3, C] weights, so the
         activations are read once and no styled copy is written."""
-        styles = self.affine(w_glob)                                    # [B, C]
+        if styles is None:
+            styles = self.affine(w_glob)                                # [B, C]
         O, I = self.weight.shape[:2]
         wm = self.weight.reshape(1, O, I) * styles[:, None, :] * (1.0 / math.sqrt(I))      # [B, 3, C]
         B, C, H, W = x.shape
@@ -189,18 +257,36 @@ class SynthesisNetwork(nn.Module):
         y = ws[:, :k].contiguous()
         w_glob = ws[:, k]
         x = self.const[None].expand(B, -1, -1, -1).contiguous(memory_format=torch.channels_last)
+        # all style affines (one per conv layer and per tRGB) read the same global latent: one batched GEMM at inference
+        mods = list(self.layers) + list(self.torgbs)
+        aff = [m.affine for m in mods]
+        aff_params = [t for a in aff for t in (a.weight, a.bias)]
+        styles_all = [None] * len(mods)
+        if _inference(*aff_params):
+            def cat_affines():
+                ws_, bs_ = zip(*[a.effective() for a in aff])
+                return torch.cat(ws_, dim=1).contiguous(), torch.cat(bs_)
+            wt_cat, b_cat = _cached(self, "affines", aff_params, cat_affines)
+            styles_all = torch.addmm(b_cat, w_glob, wt_cat).split([a.weight.shape[0] for a in aff], dim=1)
         img = None
         atts = []
         li = 0
         for bi, res in enumerate(self.block_resolutions):
             nl = 1 if res == 4 else 2
-            for _ in range(nl):
+            prescaled = False
+            for j in range(nl):
                 layer = self.layers[li]
+                # conv0 -> conv1 inside a block has a single consumer: conv1's style scale is folded into conv0's store
+                post_scale = None
+                if j == 0 and nl == 2 and styles_all[li + 1] is not None and layer.fusable(x):
+                    post_scale = styles_all[li + 1]
+                x, att, _ = layer(x, w_glob, y, noise_mode=noise_mode, return_att=return_att, styles=styles_all[li],
+                                  prescaled=prescaled, post_scale=post_scale)
+                prescaled = post_scale is not None
                 li += 1
-                x, att, _ = layer(x, w_glob, y, noise_mode=noise_mode, return_att=return_att)
                 if att is not None:
                     atts.append(att)
-            rgb = self.torgbs[bi](x, w_glob)
+            rgb = self.torgbs[bi](x, w_glob, styles=styles_all[len(self.layers) + bi])
             img = rgb if img is None else ops.upsample2x(img, self.fir, add=rgb)
         return (img, atts) if return_att else img
 

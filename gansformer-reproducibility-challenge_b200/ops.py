@@ -55,14 +55,23 @@ def _nhwc_view(x: torch.Tensor) -> torch.Tensor:
     return v if v.is_contiguous() else v.contiguous()
 
 
+def _rows(s: torch.Tensor):
+    """(tensor, row stride in floats) of a [B, C] matrix that may be a column slice of a wider contiguous matrix."""
+    if s.dim() == 2 and s.stride(1) == 1 and s.stride(0) % 4 == 0 and s.data_ptr() % 16 == 0 and s.stride(0) >= s.shape[1]:
+        return s, s.stride(0)
+    s = s.contiguous()
+    return s, s.shape[1]
+
+
 def chan_scale(x: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
     """x [B,C,H,W] * s [B,C] (style modulation / demodulation as activation scaling)."""
     if _use_cuda(x, s) and x.shape[1] % 4 == 0:
         xv = _nhwc_view(x)
         B, H, W, C = xv.shape
         y = torch.empty_like(xv)
+        sr, ld = _rows(s)
         with torch.cuda.device(x.device):
-            _lib.check(_lib.load().gf_chan_scale_nhwc(xv.data_ptr(), s.contiguous().data_ptr(), y.data_ptr(), B, H * W, C,
+            _lib.check(_lib.load().gf_chan_scale_nhwc(xv.data_ptr(), sr.data_ptr(), ld, y.data_ptr(), B, H * W, C,
                                                       _stream(x.device)), "gf_chan_scale_nhwc")
         return y.permute(0, 3, 1, 2)
     return x * s[:, :, None, None].to(x.dtype)
@@ -120,3 +129,17 @@ def bias_act(x: torch.Tensor, bias: Optional[torch.Tensor], act: str = "lrelu", 
     if act == "lrelu":
         x = F.leaky_relu(x, 0.2) * SQRT2
     return x
+
+
+def demod_coef(styles: torch.Tensor, wsq: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
+    """d[b,o] = rsqrt(sum_i styles[b,i]^2 wsq[o,i] + eps) (StyleGAN2 demodulation, activation-scaling form)."""
+    if _use_cuda(styles, wsq):
+        B, I = styles.shape
+        O = wsq.shape[0]
+        d = torch.empty((B, O), dtype=torch.float32, device=styles.device)
+        sr, ld = _rows(styles)
+        with torch.cuda.device(styles.device):
+            _lib.check(_lib.load().gf_demod_coef(sr.data_ptr(), ld, wsq.contiguous().data_ptr(), d.data_ptr(), B, O, I,
+                                                 float(eps), _stream(styles.device)), "gf_demod_coef")
+        return d
+    return torch.rsqrt(styles.square() @ wsq.t() + eps)

@@ -62,8 +62,12 @@ typedef struct gf_attn_desc {
   int32_t flags;        /* GF_FLAG_* */
 } gf_attn_desc;
 
-/* Optional fused epilogue of stage T (what follows the attention block inside the reference's synthesis layer:
- * noise input + fused_bias_act):   x'' = act(x' + noise[b*noise_bstride + t] * (*strength) + bias[c]) * gain */
+/* Optional fusion of what surrounds the attention block inside the reference's synthesis layer:
+ *   load side :  x_in = X * in_scale[b,c]            (StyleGAN2 demodulation of the preceding convolution's output)
+ *   store side:  x'' = act(x' + noise[b*noise_bstride + t] * (*strength) + bias[c]) * gain * post_scale[b,c]
+ *                (noise input + fused_bias_act, then the style modulation of the NEXT convolution's input)
+ * in_scale must be given to BOTH gf_attn_prologue_ex (it is folded into K') and gf_attn_simplex_fwd_ex.
+ * Supported with norm layer/none, simplex; every member may be NULL. */
 typedef struct gf_attn_postop {
   const float* bias;         /* [C] or NULL */
   const float* noise;        /* [H*W] (noise_bstride = 0: shared by the batch) or [B][H*W]; NULL = no noise */
@@ -71,6 +75,9 @@ typedef struct gf_attn_postop {
   long long noise_bstride;
   int32_t act;               /* 0 linear, 1 leaky-ReLU(0.2) */
   float gain;
+  const float* in_scale;     /* [B][in_scale_ld] rows of C floats, 16-byte aligned rows; NULL = 1 */
+  const float* post_scale;   /* [B][post_scale_ld]; NULL = 1 */
+  int32_t in_scale_ld, post_scale_ld;
 } gf_attn_postop;
 
 /* Raw (un-scaled) parameters of one layer, each [fan_in, fan_out] row-major; equalised-LR scaling
@@ -109,6 +116,9 @@ int gf_attn_workspace_bytes(const gf_attn_desc* desc, size_t* out_bytes);
  * per image builds K' [B,KP,C], V^T [B,Cout,KP] and the separable positional-logit tables in `ws`.
  * Simplex: keys from Y.  Duplex: called internally by gf_attn_duplex_fwd after pass A. */
 int gf_attn_prologue(const gf_attn_desc* desc, const float* Y, const float* folded, void* ws, void* stream);
+
+/* gf_attn_prologue with the load-side fusion: K' is additionally scaled by post->in_scale (post may be NULL). */
+int gf_attn_prologue_ex(const gf_attn_desc* desc, const float* Y, const float* folded, void* ws, const gf_attn_postop* post, void* stream);
 
 /* Stage T -- replaces the body of transformer_layer() + integrate() + att_norm() for simplex attention:
  * one read of X, one write of Xout (may alias X).  att (nullable) receives softmax probabilities [B,n,k].

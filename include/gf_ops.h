@@ -17,9 +17,10 @@
 extern "C" {
 #endif
 
-/* y[b,t,c] = x[b,t,c] * s[b,c].   Style modulation of a conv input / demodulation of a conv output
- * (modulated_conv2d_layer in the reference, activation-scaling form).  y may alias x.  C % 4 == 0. */
-int gf_chan_scale_nhwc(const float* x, const float* s, float* y, int B, int HW, int C, void* stream);
+/* y[b,t,c] = x[b,t,c] * s[b*s_ld + c].   Style modulation of a conv input / demodulation of a conv output
+ * (modulated_conv2d_layer in the reference, activation-scaling form).  y may alias x.  C % 4 == 0; s_ld (row stride
+ * of s in floats) % 4 == 0 so that rows of a column slice of a wider [B, sum C] style matrix can be passed directly. */
+int gf_chan_scale_nhwc(const float* x, const float* s, int s_ld, float* y, int B, int HW, int C, void* stream);
 
 /* upfirdn_2d, use (a): the FIR blur that follows a stride-2 transposed convolution.
  * x [B, Hout+1, Wout+1, C] -> y [B, Hout, Wout, C]; separable filter [1,3,3,1]/8 per axis, total gain `gain`
@@ -35,6 +36,10 @@ int gf_upsample2x_nchw(const float* x, const float* add, float* y, int B, int C,
  * act: 0 linear, 1 leaky-ReLU(0.2).  noise / strength / bias nullable.  y may alias x.  C % 4 == 0. */
 int gf_bias_act_nhwc(const float* x, float* y, const float* bias, const float* noise, const float* strength,
                      long long noise_bstride, int B, int HW, int C, int act, float gain, void* stream);
+
+/* StyleGAN2 demodulation coefficients of the activation-scaling form:
+ *   d[b,o] = rsqrt( sum_i styles[b*s_ld + i]^2 * wsq[o,i] + eps ),  wsq[o,i] = sum_{kh,kw} w_eff[o,i,kh,kw]^2 */
+int gf_demod_coef(const float* styles, int s_ld, const float* wsq, float* d, int B, int O, int I, float eps, void* stream);
 
 #ifdef __cplusplus
 }

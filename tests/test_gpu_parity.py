@@ -332,12 +332,19 @@ def test_autograd_matches_oracle(gf, cuda_dev):
 # fused post-op (noise + bias + leaky-ReLU on the attention store) and the native companion ops (gf_ops.h)
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("exact", [True, False], ids=["fp32", "default"])
-@pytest.mark.parametrize("C,H,W,k,random_noise", [(128, 16, 16, 16, False), (256, 16, 8, 8, True), (512, 8, 8, 4, False)])
-def test_attention_postop(gf, cuda_dev, C, H, W, k, random_noise, exact):
+@pytest.mark.parametrize("scales", [False, True], ids=["plain", "scales"])
+@pytest.mark.parametrize("C,H,W,k,random_noise", [(128, 16, 16, 16, False), (256, 16, 8, 8, True), (512, 8, 8, 4, False), (512, 16, 16, 16, False)])
+def test_attention_postop(gf, cuda_dev, C, H, W, k, random_noise, exact, scales):
+    """Fused load side (demodulation scale) and store side (noise + bias + lrelu + next style scale) vs the oracle."""
     D = p = 16
     B = 3
     g = torch.Generator().manual_seed(C + k)
     x64 = torch.randn(B, C, H, W, generator=g, dtype=torch.float64)
+    d_in = (torch.rand(B, C, generator=g, dtype=torch.float64) + 0.5) if scales else None
+    ps = (torch.randn(B, C, generator=g, dtype=torch.float64) + 1.0) if scales else None
+    x_raw = x64
+    if scales:
+        x64 = x64 * d_in[:, :, None, None]
     y64 = torch.randn(B, k, D, generator=g, dtype=torch.float64)
     bias = torch.randn(C, generator=g, dtype=torch.float64) * 0.5
     noise = torch.randn((B, 1, H, W) if random_noise else (H, W), generator=g, dtype=torch.float64)
@@ -346,11 +353,18 @@ def test_attention_postop(gf, cuda_dev, C, H, W, k, random_noise, exact):
     ref, _, _ = ob.transformer_layer(x64, y64, w, integration="both")
     ref = ref + noise * strength + bias[None, :, None, None]
     ref = torch.nn.functional.leaky_relu(ref, 0.2) * math.sqrt(2.0)
+    if scales:
+        ref = ref * ps[:, :, None, None]
     attn = make_layer(gf, cuda_dev, C, D, k, p, "both", "layer", False, True, exact, w)
     post = dict(bias=bias.float().to(cuda_dev), noise=noise.float().to(cuda_dev), strength=strength.float().to(cuda_dev),
                 act="lrelu", gain=math.sqrt(2.0))
+    if scales:   # pass them as column slices of a wider matrix, as the generator does (row stride != C)
+        wide = torch.zeros(B, 2 * C + 8, device=cuda_dev)
+        wide[:, 8:8 + C] = d_in.float().to(cuda_dev)
+        wide[:, 8 + C:] = ps.float().to(cuda_dev)
+        post.update(in_scale=wide[:, 8:8 + C], post_scale=wide[:, 8 + C:])
     with torch.no_grad():
-        out, _, _ = attn(x64.permute(0, 2, 3, 1).contiguous().float().to(cuda_dev), y64.float().to(cuda_dev), postop=post)
+        out, _, _ = attn(x_raw.permute(0, 2, 3, 1).contiguous().float().to(cuda_dev), y64.float().to(cuda_dev), postop=post)
     check_close(out, ref.permute(0, 2, 3, 1), gf._lib.last_path(), "postop")
 
 
@@ -371,6 +385,12 @@ def test_native_ops_match_definitions(gf, cuda_dev):
         xs = torch.randn(B, C, H, W, generator=g).to(cuda_dev).contiguous(memory_format=torch.channels_last)
         with torch.no_grad():
             assert torch.equal(ops.chan_scale(xs, s), xs * s[:, :, None, None])
+            wide = torch.rand(B, C + 8, generator=g).to(cuda_dev)
+            assert torch.equal(ops.chan_scale(xs, wide[:, 4:4 + C]), xs * wide[:, 4:4 + C, None, None])     # strided rows
+            wsq = torch.rand(48, C, generator=g).to(cuda_dev)
+            dd = ops.demod_coef(wide[:, 4:4 + C], wsq)
+            want_d = torch.rsqrt(wide[:, 4:4 + C].double().square() @ wsq.double().t() + 1e-8)
+            assert (dd.double() - want_d).abs().max() <= 1e-5 * want_d.abs().max()
             bias = torch.randn(C, generator=g).to(cuda_dev)
             nz = torch.randn(H, W, generator=g).to(cuda_dev)
             st = torch.tensor(0.3, device=cuda_dev)
