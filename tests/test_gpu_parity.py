@@ -25,12 +25,12 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden", "attn_cases.npz")
 TOL = {"simt_fp32": (1e-5, 1e-4, 2e-5), "tcgen05_tf32": (8e-3, 8e-3, 2e-3)}
 
 
-def check_close(got, ref64, path, what=""):
+def check_close(got, ref64, path, what="", tol_scale=1.0):
     got = got.detach().double().cpu()
     ref64 = ref64.detach().double().cpu()
     assert got.shape == ref64.shape, (got.shape, ref64.shape)
     assert torch.isfinite(got).all(), f"{what}: non-finite output"
-    atol, rtol, rrms = TOL[path]
+    atol, rtol, rrms = (t * tol_scale for t in TOL[path])
     err = (got - ref64).abs()
     ratio = (err / (atol + rtol * ref64.abs())).max().item()
     rel_rms = (err.pow(2).mean().sqrt() / ref64.pow(2).mean().sqrt().clamp_min(1e-30)).item()
@@ -365,7 +365,8 @@ def test_attention_postop(gf, cuda_dev, C, H, W, k, random_noise, exact, scales)
         post.update(in_scale=wide[:, 8:8 + C], post_scale=wide[:, 8 + C:])
     with torch.no_grad():
         out, _, _ = attn(x_raw.permute(0, 2, 3, 1).contiguous().float().to(cuda_dev), y64.float().to(cuda_dev), postop=post)
-    check_close(out, ref.permute(0, 2, 3, 1), gf._lib.last_path(), "postop")
+    # with the per-channel scales the error of the block is multiplied by |post_scale| (up to ~4): tolerance x2
+    check_close(out, ref.permute(0, 2, 3, 1), gf._lib.last_path(), "postop", tol_scale=2.0 if scales else 1.0)
 
 
 def test_native_ops_match_definitions(gf, cuda_dev):

@@ -9,6 +9,7 @@ import gansformer_b200 as gf
 dev = torch.device("cuda:0")
 B = int(os.environ.get("AB_BATCH", 32)); k = int(os.environ.get("AB_K", 16)); D = 32
 integ = os.environ.get("AB_INT", "mul")
+duplex = bool(int(os.environ.get("AB_DUPLEX", "0")))
 layers = [(8, 512), (16, 512), (32, 512), (64, 512), (128, 256), (256, 128)]
 if os.environ.get("AB_ONLY"):
     layers = [l for l in layers if str(l[0]) in os.environ["AB_ONLY"].split(",")]
@@ -23,7 +24,7 @@ for res, C in layers:
     y = torch.randn(B, k, D, device=dev)
     o = torch.empty_like(xs[0])
     for mode in modes:
-        attn = gf.BipartiteAttention(C, D, k, integration=integ, exact_fp32=(mode == "fp32")).to(dev)
+        attn = gf.BipartiteAttention(C, D, k, integration=integ, kmeans=duplex, exact_fp32=(mode == "fp32")).to(dev)
         with torch.no_grad():
             for i in range(3):
                 attn(xs[i % nbuf], y, out=o)
@@ -43,7 +44,7 @@ for res, C in layers:
             am.STAGE_TIMER = None
         path = gf._lib.last_path()
         gbs = nbytes / (t_stage * 1e-3) / 1e9
-        rec = dict(res=res, C=C, B=B, k=k, integration=integ, mode=mode, path=path, stage_ms=t_stage, call_ms=t_call,
+        rec = dict(res=res, C=C, B=B, k=k, integration=integ, duplex=duplex, mode=mode, path=path, stage_ms=t_stage, call_ms=t_call,
                    alg_GB=nbytes / 1e9, GBps=gbs, frac=gbs / peak)
         out.append(rec)
         print(f"res={res:4d} C={C:4d} {mode:8s} path={path:13s} stage={t_stage:8.4f} ms call={t_call:8.4f} ms  {gbs:8.1f} GB/s  frac={gbs/peak:.3f}", flush=True)
