@@ -26,7 +26,7 @@ WEIGHT_FIELDS = ("wq", "bq", "wpq", "wk", "bk", "wpk", "wv", "bv", "wo", "bo", "
 EXPORTS = ("gf_attn_abi_version", "gf_last_error", "gf_attn_last_path", "gf_attn_folded_floats",
            "gf_attn_fold_weights", "gf_attn_workspace_bytes", "gf_attn_prologue", "gf_attn_simplex_fwd",
            "gf_attn_duplex_fwd", "gf_attn_norm_stats", "gf_attn_launch_count",
-           "gf_attn_simplex_fwd_ex", "gf_attn_duplex_fwd_ex", "gf_attn_prologue_ex")
+           "gf_attn_simplex_fwd_ex", "gf_attn_duplex_fwd_ex", "gf_attn_prologue_ex", "gf_attn_last_centroid_path")
 # include/gf_ops.h
 OPS_EXPORTS = ("gf_chan_scale_nhwc", "gf_blur_up_nhwc", "gf_upsample2x_nchw", "gf_bias_act_nhwc", "gf_demod_coef")
 
@@ -122,6 +122,10 @@ def workspace_bytes(desc: GfAttnDesc) -> int:
 
 def launch_count() -> int:
     return int(load().gf_attn_launch_count())
+
+
+def last_centroid_path() -> str:
+    return PATH_NAMES.get(load().gf_attn_last_centroid_path(), "?")
 
 
 def last_path() -> str:

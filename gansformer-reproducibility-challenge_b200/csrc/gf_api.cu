@@ -16,6 +16,8 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void set_path(int path) { g_path = path; }
+static thread_local int g_cen_path = GF_PATH_NONE;
+void set_centroid_path(int path) { g_cen_path = path; }
 static std::atomic<long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -63,6 +65,7 @@ extern "C" {
 int gf_attn_abi_version(void) { return GF_ATTN_ABI_VERSION; }
 const char* gf_last_error(void) { return g_err; }
 int gf_attn_last_path(void) { return g_path; }
+int gf_attn_last_centroid_path(void) { return g_cen_path; }
 long long gf_attn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int gf_attn_folded_floats(const gf_attn_desc* desc, size_t* out_floats) {
@@ -146,7 +149,14 @@ int gf_attn_duplex_fwd_ex(const gf_attn_desc* desc, const float* X, const float*
   cudaStream_t st = (cudaStream_t)stream;
   if (!(desc->flags & GF_FLAG_CENTROIDS_IN)) {
     if ((rc = duplex_tables(L, desc, Y, folded, ws, st))) return rc;
-    if ((rc = centroid_pass_simt(L, desc, X, ws, st))) return rc;
+    if (tc_centroid_supported(L, desc)) {
+      if ((rc = centroid_pass_tc(L, desc, X, ws, st))) return rc;
+      if ((rc = centroid_merge(L, ws, st))) return rc;
+      set_centroid_path(GF_PATH_TCGEN05_TF32);
+    } else {
+      if ((rc = centroid_pass_simt(L, desc, X, ws, st))) return rc;
+      set_centroid_path(GF_PATH_SIMT_FP32);
+    }
     // centroids = Xbar @ Wv2_e + bv2
     if ((rc = gemm(st, L.B * L.k, L.C, L.C, ws + L.w_XBAR, L.C, false, folded + L.f_WV2, L.C, false, centroids_inout, L.C, 1.f,
                    nullptr, 0, 1, folded + L.f_BV2)))

@@ -13,6 +13,7 @@ namespace gf {
 // ---- thread-local error reporting -----------------------------------------------------------------
 void set_error(const char* fmt, ...);
 void set_path(int path);
+void set_centroid_path(int path);
 void note_launch();
 
 #define GF_CUDA_OK(expr)                                                                         \
@@ -71,6 +72,10 @@ int gemm(cudaStream_t st, int M, int N, int K, const float* A, int lda, bool ta,
 int token_pass_simt(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, const gf_attn_postop* post, cudaStream_t st);
 int norm_stats(const Layout& L, const gf_attn_desc* d, const float* X, float* ws, cudaStream_t st);
 int centroid_pass_simt(const Layout& L, const gf_attn_desc* d, const float* X, float* ws, cudaStream_t st);
+int centroid_merge(const Layout& L, float* ws, cudaStream_t st);
+// tcgen05 duplex pass A (gf_tc_cen.cu): partials into ws (same format as the CUDA-core kernel), then centroid_merge
+bool tc_centroid_supported(const Layout& L, const gf_attn_desc* d);
+int centroid_pass_tc(const Layout& L, const gf_attn_desc* d, const float* X, float* ws, cudaStream_t st);
 // tcgen05 / TMA path (gf_tc.cu).  tc_supported() says whether the shape is served by it.
 bool tc_supported(const Layout& L, const gf_attn_desc* d);
 int token_pass_tc(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, const gf_attn_postop* post, cudaStream_t st);

@@ -415,6 +415,10 @@ int centroid_pass_simt(const Layout& L, const gf_attn_desc* d, const float* X, f
     centroid_simt_kernel<32><<<grid, TM, dyn, st>>>(P);
   }
   GF_LAUNCH_OK();
+  return centroid_merge(L, ws, st);
+}
+
+int centroid_merge(const Layout& L, float* ws, cudaStream_t st) {
   const int tot = L.B * L.k * L.C;
   centroid_merge_kernel<<<(tot + 255) / 256, 256, 0, st>>>(ws + L.w_PART, ws + L.w_XBAR, L.B, L.k, L.KP, L.C, L.nsplit_cen);
   GF_LAUNCH_OK();

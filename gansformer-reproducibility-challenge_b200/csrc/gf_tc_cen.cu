@@ -1,0 +1,382 @@
+// gf_tc_cen.cu -- duplex pass A (latents attend to the grid, softmax over the n grid cells) on the tensor path.
+//
+// Replaces, on the reference side (expected src/training/network.py, not in the checkout): the k-means / centroid branch
+// of transformer_layer (image -> latents attention).  Algorithm = oracle/folded.py centroid_pass():
+//     L[t,j] = x_t . M_j + pos(t,j);   A[j,:] = softmax_t L[:,j];   Xbar[j,:] = sum_t A[j,t] x_t
+// streamed once over X with an online softmax (lazy rescaling), split over `nsplit` CTAs per image whose partials
+// (acc[KP][C], m[KP], l[KP]) are merged by centroid_merge_kernel (gf_simt.cu).
+//
+// grid (nsplit, B), 6 warps:
+//   warp 0     TMA producer: M (latent-query matrix, once) and the X slabs (128 tokens x 32 channels, SWIZZLE_128B)
+//   warp 1     MMA issuer:   GEMM1  S[128 tok, KP]   = X . M^T                      (M=128, as in stage T)
+//                            GEMM2  D2[KP->64, 32ch] += E^T[64, 128 tok] . X_slab   (M=64; A = E^T from smem, K-major;
+//                                   B = the SAME X slab read MN-major: tokens are the contraction dimension)
+//                            GEMM3  D3[64, 8]        += E^T . 1                      (softmax denominators)
+//   warps 2-5  row warps (thread = token): positional logits, S from TMEM, per-latent tile maximum (warp shuffles +
+//              shared memory), E = exp(S - m) rounded to TF32 and written TRANSPOSED into shared memory, lazy rescale of
+//              the TMEM accumulators when a running maximum moves by more than TAU, final flush of the partials.
+// HBM traffic: X read once.
+#include <stdlib.h>
+#include "gf_common.cuh"
+#include "gf_tc_common.cuh"
+
+namespace gf {
+namespace tcc {
+
+using namespace tc;
+
+constexpr int TILE = 128;
+constexpr int SLAB_CH = 32;
+constexpr int SLAB_BYTES = TILE * SLAB_CH * 4;
+constexpr int MAX_STAGES = 12;
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int COL_S = 0;          // S[2]: 2 x 32 columns
+constexpr int COL_D3 = 64;        // softmax denominators (8 columns used)
+constexpr int COL_D2 = 128;       // Xbar accumulators: C columns (C <= 256)
+constexpr float TAU = 8.f;        // lazy rescale threshold (natural-log units): exp(8) ~ 3e3 of headroom is harmless in fp32
+
+struct Params {
+  const float* Rt; const float* Ct; float* part;
+  int n, H, W, k, nsplit, tiles_per_image, nstages, ahead;
+};
+
+struct Bars {
+  uint64_t slab_full[MAX_STAGES], slab_empty[MAX_STAGES];
+  uint64_t m_full, done;
+  uint64_t s_full[2], e_full[2], e_free[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+template <int KP, int NS>
+struct Cfg {
+  static constexpr int C = NS * SLAB_CH;
+  static constexpr int M_BYTES = KP * C * 4;                 // NS chunks of [KP rows x 128 B]
+  static constexpr int E_CHUNK = KP * 128;                   // one 32-token chunk of E^T: [KP rows x 128 B]
+  static constexpr int E_BYTES = 4 * E_CHUNK;                // 128 tokens
+  static constexpr int OFF_M = 0;
+  static constexpr int OFF_E = OFF_M + M_BYTES;              // 2 buffers
+  static constexpr int OFF_ONES = OFF_E + 2 * E_BYTES;       // 1 KB of 1.0f
+  static constexpr int OFF_SMALL = OFF_ONES + 1024;          // red[4][KP], mref[KP], resc[KP], flag
+  static constexpr int SMALL_BYTES = (4 * KP + 2 * KP + 4) * 4;
+  static constexpr int OFF_BARS = (OFF_SMALL + SMALL_BYTES + 15) / 16 * 16;
+  // the M=64 A descriptor of GEMM2 reads 64 rows from each E chunk: rows >= KP alias whatever follows (their D rows are
+  // never read); the ring behind keeps those reads inside the allocation.
+  static constexpr int OFF_RING = (OFF_BARS + (int)sizeof(Bars) + 1023) / 1024 * 1024;
+  static constexpr int FIXED_BYTES = OFF_RING;
+};
+
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// MN-major operand, SWIZZLE_128B: 32 contiguous MN elements (128 B) per K row, 8 K rows per 1024-byte atom;
+// leading byte offset = next block of 32 MN elements, stride byte offset = next 8 K rows.
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)LAYOUT_SW128 << 61;
+  return d;
+}
+
+template <int KP, int NS>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmM, const Params P) {
+  using CF = Cfg<KP, NS>;
+  constexpr int C = CF::C;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t s_m = s_base + CF::OFF_M, s_e = s_base + CF::OFF_E, s_ones = s_base + CF::OFF_ONES, s_ring = s_base + CF::OFF_RING;
+  Bars* bars = reinterpret_cast<Bars*>(smem + CF::OFF_BARS);
+  float* red = reinterpret_cast<float*>(smem + CF::OFF_SMALL);      // [4][KP]
+  float* mref = red + 4 * KP;                                       // [KP]
+  float* resc = mref + KP;                                          // [KP]
+  int* flag = reinterpret_cast<int*>(resc + KP);                    // any latent needs a rescale this tile
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nst = P.nstages;
+  const int b = blockIdx.y, sp = blockIdx.x;
+  const int per = (P.tiles_per_image + P.nsplit - 1) / P.nsplit;
+  const int tile_beg = sp * per, tile_end = min(P.tiles_per_image, tile_beg + per);
+  const int ntiles = tile_end - tile_beg;
+  float* part = P.part + ((size_t)b * P.nsplit + sp) * KP * (C + 4);
+
+  if (ntiles <= 0) {                          // empty split: neutral partial
+    for (int i = threadIdx.x; i < KP * (C + 4); i += NUM_THREADS) {
+      const int c = i % (C + 4);
+      part[i] = c == C ? -INFINITY : 0.f;
+    }
+    return;
+  }
+
+  for (int i = threadIdx.x; i < 256; i += NUM_THREADS) reinterpret_cast<float*>(smem + CF::OFF_ONES)[i] = 1.f;
+  if (threadIdx.x < KP) { mref[threadIdx.x] = -INFINITY; resc[threadIdx.x] = 1.f; }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmX); prefetch_tmap(&tmM);
+    for (int i = 0; i < nst; ++i) { mbar_init(smem_u32(&bars->slab_full[i]), 1); mbar_init(smem_u32(&bars->slab_empty[i]), 1); }
+    mbar_init(smem_u32(&bars->m_full), 1); mbar_init(smem_u32(&bars->done), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bars->s_full[i]), 1);
+      mbar_init(smem_u32(&bars->e_full[i]), 4);
+      mbar_init(smem_u32(&bars->e_free[i]), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async();                        // the generic-proxy writes of `ones` must be visible to the tensor core
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      const uint32_t mb = smem_u32(&bars->m_full);
+      mbar_expect_tx(mb, (uint32_t)CF::M_BYTES);
+#pragma unroll
+      for (int s = 0; s < NS; ++s) tma_load_2d(s_m + s * (KP * 128), &tmM, mb, s * SLAB_CH, b * KP);
+      long long ctr = 0;
+      for (int t = tile_beg; t < tile_end; ++t) {
+        const int row0 = (b * P.tiles_per_image + t) * TILE;
+        for (int s = 0; s < NS; ++s, ++ctr) {
+          const int stage = (int)(ctr % nst);
+          mbar_wait(smem_u32(&bars->slab_empty[stage]), (uint32_t)(((ctr / nst) & 1) ^ 1));
+          const uint32_t bar = smem_u32(&bars->slab_full[stage]);
+          mbar_expect_tx(bar, SLAB_BYTES);
+          tma_load_2d(s_ring + stage * SLAB_BYTES, &tmX, bar, s * SLAB_CH, row0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t IDESC1 = idesc_tf32(TILE, KP, 0);
+      constexpr uint32_t IDESC2 = idesc_tf32(64, 32, 1);
+      constexpr uint32_t IDESC3 = idesc_tf32(64, 8, 0);
+      mbar_wait(smem_u32(&bars->m_full), 0);
+      tc_fence_after();
+      auto gemm1 = [&](int it) {
+        const uint32_t d_s = tmem + COL_S + (it & 1) * 32;
+        for (int s = 0; s < NS; ++s) {
+          const long long ctr = (long long)it * NS + s;
+          const int stage = (int)(ctr % nst);
+          mbar_wait(smem_u32(&bars->slab_full[stage]), (uint32_t)((ctr / nst) & 1));
+          tc_fence_after();
+          const uint32_t a_addr = s_ring + stage * SLAB_BYTES, b_addr = s_m + s * (KP * 128);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_ss(d_s, umma_desc(a_addr + kk * 32, 1024, LAYOUT_SW128), umma_desc(b_addr + kk * 32, 1024, LAYOUT_SW128),
+                    IDESC1, (s | kk) ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&bars->s_full[it & 1]));
+      };
+      gemm1(0);
+      for (int it = 0; it < ntiles; ++it) {
+        const int buf = it & 1;
+        if (P.ahead && it + 1 < ntiles) gemm1(it + 1);            // ring holds two tiles: keep the row warps fed
+        mbar_wait(smem_u32(&bars->e_full[buf]), (uint32_t)((it >> 1) & 1));
+        tc_fence_after();
+        const uint32_t e_addr = s_e + buf * CF::E_BYTES;
+        for (int s = 0; s < NS; ++s) {
+          const long long ctr = (long long)it * NS + s;
+          const int stage = (int)(ctr % nst);
+          const uint32_t x_addr = s_ring + stage * SLAB_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < 16; ++kk)                           // 8 tokens per MMA
+            umma_ss(tmem + COL_D2 + s * 32,
+                    umma_desc(e_addr + (kk >> 2) * CF::E_CHUNK + (kk & 3) * 32, 1024, LAYOUT_SW128),
+                    umma_desc_mn(x_addr + kk * 1024, SLAB_BYTES, 1024), IDESC2, (it | kk) ? 1u : 0u);
+          umma_commit(smem_u32(&bars->slab_empty[stage]));          // slab recycled once everything issued so far is done
+        }
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk)
+          umma_ss(tmem + COL_D3, umma_desc(e_addr + (kk >> 2) * CF::E_CHUNK + (kk & 3) * 32, 1024, LAYOUT_SW128),
+                  umma_desc(s_ones, 1024, LAYOUT_SW128), IDESC3, (it | kk) ? 1u : 0u);
+        umma_commit(smem_u32(&bars->e_free[buf]));
+        if (!P.ahead && it + 1 < ntiles) gemm1(it + 1);
+      }
+      umma_commit(smem_u32(&bars->done));
+    }
+  } else {
+    // =============================== row warps ===============================
+    const int q = warp & 3;                                         // TMEM lane quadrant == 32-token chunk of the tile
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int rtid = (warp - 2) * 32 + lane;                        // 0..127 inside the row-warp group
+    for (int it = 0; it < ntiles; ++it) {
+      const int buf = it & 1;
+      const uint32_t bph = (uint32_t)((it >> 1) & 1);
+      const int tok = (tile_beg + it) * TILE + row;
+      float sv[KP];
+      {
+        const int h = tok / P.W, w = tok % P.W;
+        const float4* rt = reinterpret_cast<const float4*>(P.Rt + ((size_t)b * P.H + h) * KP);
+        const float4* ct = reinterpret_cast<const float4*>(P.Ct + ((size_t)b * P.W + w) * KP);
+#pragma unroll
+        for (int j4 = 0; j4 < KP / 4; ++j4) {
+          const float4 r = __ldg(rt + j4), c = __ldg(ct + j4);
+          sv[j4 * 4 + 0] = r.x + c.x; sv[j4 * 4 + 1] = r.y + c.y; sv[j4 * 4 + 2] = r.z + c.z; sv[j4 * 4 + 3] = r.w + c.w;
+        }
+      }
+      mbar_wait(smem_u32(&bars->s_full[buf]), bph);
+      tc_fence_after();
+      float acc[KP];
+      tmem_ld16(tmem + lane_addr + COL_S + buf * 32, acc);
+      if constexpr (KP == 32) tmem_ld16(tmem + lane_addr + COL_S + buf * 32 + 16, acc + 16);
+      tmem_wait_ld();
+      // ---- per-latent maximum over the 128 tokens of the tile
+#pragma unroll
+      for (int j = 0; j < KP; ++j) {
+        sv[j] += acc[j];
+        float v = sv[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (lane == 0) red[(warp - 2) * KP + j] = v;
+      }
+      named_bar_sync(1, 128);
+      if (rtid < KP) {
+        const float tm = fmaxf(fmaxf(red[rtid], red[KP + rtid]), fmaxf(red[2 * KP + rtid], red[3 * KP + rtid]));
+        const float mo = mref[rtid];
+        float mn = mo, f = 1.f;
+        if (tm > mo + TAU || (mo == -INFINITY && tm > -INFINITY)) {   // lazy: move the reference only on a real jump
+          mn = tm;
+          f = (mo == -INFINITY) ? 1.f : __expf(mo - mn);
+        }
+        mref[rtid] = mn;
+        resc[rtid] = f;
+      }
+      if (rtid == 0) *flag = 0;
+      named_bar_sync(1, 128);
+      if (rtid < KP && resc[rtid] != 1.f) *flag = 1;
+      // ---- E = exp(S - m): TF32-rounded, written transposed (E^T[latent][token], K-major SW128, 32-token chunks)
+      // buffer `buf` was last read by GEMM2(it-2), whose completion this thread observed during tile it-1 (below)
+      uint8_t* eb = smem + CF::OFF_E + buf * CF::E_BYTES + q * CF::E_CHUNK;
+#pragma unroll
+      for (int j = 0; j < KP; ++j) {
+        const float mn = mref[j];
+        const float e = (mn == -INFINITY) ? 0.f : exp2f((sv[j] - mn) * 1.4426950408889634f);
+        *reinterpret_cast<float*>(eb + j * 128 + (((lane >> 2) ^ (j & 7)) << 4) + (lane & 3) * 4) = round_tf32_rn(e);
+      }
+      // ---- every tile: observe the completion of GEMM2(it-1) (parity bookkeeping must not skip phases); then, if a
+      //      running maximum moved, rescale the accumulators before GEMM2(it) adds to them
+      if (it > 0) {
+        mbar_wait(smem_u32(&bars->e_free[buf ^ 1]), (uint32_t)(((it - 1) >> 1) & 1));
+        tc_fence_after();
+      }
+      named_bar_sync(1, 128);                                       // flag complete
+      if (*flag && it > 0) {
+        // M=64 accumulators: latent j lives in TMEM lane (j % 16) + 32 * (j / 16): lanes 0-15 of quadrants 0 (and 1)
+        if (q * 16 < KP) {
+          const float f = lane < 16 ? resc[q * 16 + lane] : 1.f;
+          float v[16];
+#pragma unroll 1
+          for (int c0 = 0; c0 < C; c0 += 16) {
+            tmem_ld16(tmem + lane_addr + COL_D2 + c0, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= f;
+            tmem_st16(tmem + lane_addr + COL_D2 + c0, v);
+          }
+          tmem_ld16(tmem + lane_addr + COL_D3, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= f;
+          tmem_st16(tmem + lane_addr + COL_D3, v);
+          tmem_wait_st();
+        }
+      }
+      fence_proxy_async();                                          // E^T (generic proxy) -> tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->e_full[buf]));
+    }
+    // ---- flush: partial accumulators, running maxima and denominators of this split
+    mbar_wait(smem_u32(&bars->done), 0);
+    tc_fence_after();
+    if (q * 16 < KP) {
+      const int j = q * 16 + lane;                                  // valid for lane < 16
+      float v[16];
+#pragma unroll 1
+      for (int c0 = 0; c0 < C; c0 += 16) {
+        tmem_ld16(tmem + lane_addr + COL_D2 + c0, v);
+        tmem_wait_ld();
+        if (lane < 16) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) part[(size_t)j * (C + 4) + c0 + i] = v[i] * 1.000352220f;   // X truncation bias (gf_fold.cu)
+        }
+      }
+      tmem_ld16(tmem + lane_addr + COL_D3, v);
+      tmem_wait_ld();
+      if (lane < 16) {
+        part[(size_t)j * (C + 4) + C] = mref[j];
+        part[(size_t)j * (C + 4) + C + 1] = v[0];
+        part[(size_t)j * (C + 4) + C + 2] = 0.f;
+        part[(size_t)j * (C + 4) + C + 3] = 0.f;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int KP, int NS>
+static int stages_for(int smem_limit) {
+  int st = (smem_limit - Cfg<KP, NS>::FIXED_BYTES - 1024) / SLAB_BYTES;
+  return st > MAX_STAGES ? MAX_STAGES : st;
+}
+
+template <int KP, int NS>
+static int launch(const Layout& L, const float* X, float* ws, cudaStream_t st) {
+  using CF = Cfg<KP, NS>;
+  const int nst = stages_for<KP, NS>(device_smem_optin());
+  if (nst < NS) { set_error("tcgen05 centroid pass: shared memory too small for C=%d KP=%d", L.C, KP); return GF_ERR_UNSUPPORTED; }
+  CUtensorMap tmX, tmM;
+  int rc;
+  if ((rc = make_map(&tmX, X, (uint64_t)L.B * L.n, L.C, TILE, SLAB_CH, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map(&tmM, ws + L.w_M, (uint64_t)L.B * KP, L.C, KP, SLAB_CH, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  Params P;
+  P.Rt = ws + L.w_Rt2; P.Ct = ws + L.w_Ct2; P.part = ws + L.w_PART;
+  P.n = L.n; P.H = L.H; P.W = L.W; P.k = L.k; P.nsplit = L.nsplit_cen; P.tiles_per_image = L.n / TILE;
+  P.nstages = nst;
+  P.ahead = nst >= 2 * NS ? 1 : 0;
+  const int smem_bytes = CF::FIXED_BYTES + nst * SLAB_BYTES + 1024;
+  auto kern = centroid_tc_kernel<KP, NS>;
+  GF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  kern<<<dim3(L.nsplit_cen, L.B), NUM_THREADS, smem_bytes, st>>>(tmX, tmM, P);
+  GF_LAUNCH_OK();
+  return GF_OK;
+}
+
+}  // namespace tcc
+
+bool tc_centroid_supported(const Layout& L, const gf_attn_desc* d) {
+  static const bool disabled = getenv("GF_DISABLE_TC") != nullptr || getenv("GF_DISABLE_TC_CENTROID") != nullptr;
+  if (disabled || (d->flags & GF_FLAG_FP32_EXACT)) return false;
+  if (L.C != 64 && L.C != 128 && L.C != 256) return false;       // C columns of TMEM accumulators (+ S, denominators) <= 512
+  if (L.n % tcc::TILE != 0 || L.B > 65535) return false;
+  const int limit = tc::device_smem_optin();
+  const int ns = L.C / 32;
+  if (L.KP == 16) return ns == 2 ? tcc::stages_for<16, 2>(limit) >= 2 : ns == 4 ? tcc::stages_for<16, 4>(limit) >= 4 : tcc::stages_for<16, 8>(limit) >= 8;
+  return ns == 2 ? tcc::stages_for<32, 2>(limit) >= 2 : ns == 4 ? tcc::stages_for<32, 4>(limit) >= 4 : tcc::stages_for<32, 8>(limit) >= 8;
+}
+
+int centroid_pass_tc(const Layout& L, const gf_attn_desc* d, const float* X, float* ws, cudaStream_t st) {
+  (void)d;
+  const int ns = L.C / 32;
+  if (L.KP == 16) return ns == 2 ? tcc::launch<16, 2>(L, X, ws, st) : ns == 4 ? tcc::launch<16, 4>(L, X, ws, st) : tcc::launch<16, 8>(L, X, ws, st);
+  return ns == 2 ? tcc::launch<32, 2>(L, X, ws, st) : ns == 4 ? tcc::launch<32, 4>(L, X, ws, st) : tcc::launch<32, 8>(L, X, ws, st);
+}
+
+}  // namespace gf

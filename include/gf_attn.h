@@ -99,6 +99,8 @@ typedef struct gf_attn_weights {
 int gf_attn_abi_version(void);
 const char* gf_last_error(void);
 int gf_attn_last_path(void);
+/* same for the duplex pass-A (centroid) kernel of the last gf_attn_duplex_fwd on this thread */
+int gf_attn_last_centroid_path(void);
 /* Number of kernels this library has launched in this process (all threads); bench.py reports the delta. */
 long long gf_attn_launch_count(void);
 
