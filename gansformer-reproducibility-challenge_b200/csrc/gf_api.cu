@@ -68,6 +68,15 @@ int gf_attn_last_path(void) { return g_path; }
 int gf_attn_last_centroid_path(void) { return g_cen_path; }
 long long gf_attn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+int gf_attn_debug_layout(const gf_attn_desc* desc, long long* out, int n) {
+  Layout L;
+  int rc = make_layout(desc, &L);
+  if (rc) return rc;
+  const long long v[8] = {(long long)L.w_PART, (long long)L.w_XBAR, L.nsplit_cen, L.KP, (long long)L.w_M, (long long)L.w_Rt2, (long long)L.w_Ct2, (long long)L.w_total};
+  for (int i = 0; i < n && i < 8; ++i) out[i] = v[i];
+  return GF_OK;
+}
+
 int gf_attn_folded_floats(const gf_attn_desc* desc, size_t* out_floats) {
   Layout L;
   int rc = make_layout(desc, &L);

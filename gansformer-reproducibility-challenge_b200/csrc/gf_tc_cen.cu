@@ -7,15 +7,19 @@
 // (acc[KP][C], m[KP], l[KP]) are merged by centroid_merge_kernel (gf_simt.cu).
 //
 // grid (nsplit, B), 6 warps:
-//   warp 0     TMA producer: M (latent-query matrix, once) and the X slabs (128 tokens x 32 channels, SWIZZLE_128B)
-//   warp 1     MMA issuer:   GEMM1  S[128 tok, KP]   = X . M^T                      (M=128, as in stage T)
-//                            GEMM2  D2[KP->64, 32ch] += E^T[64, 128 tok] . X_slab   (M=64; A = E^T from smem, K-major;
-//                                   B = the SAME X slab read MN-major: tokens are the contraction dimension)
+//   warp 0     TMA producer: M (latent-query matrix, once) and the X slabs (128 tokens x 32 channels).  Every slab is
+//              fetched twice: with SWIZZLE_128B for GEMM1 (X is the K-major A operand: contraction over channels) and with
+//              SWIZZLE_128B_ATOM_32B for GEMM2 (X is the MN-major B operand: contraction over tokens; for 32-bit MN-major
+//              operands that swizzle -- UMMA layout SWIZZLE_128B_BASE32B -- is the only one the tensor core accepts).
+//              The second fetch hits L2; slot order in the ring: P1(0), [P1(i+1), P2(i)] for i = 0, 1, ...
+//   warp 1     MMA issuer (the only slab consumer, same order):
+//                            GEMM1  S[128 tok, KP]   = X . M^T                      (M=128, as in stage T)
+//                            GEMM2  D2[KP->64, 32ch] += E^T[64, 128 tok] . X_slab   (M=64; A = E^T from smem, K-major)
 //                            GEMM3  D3[64, 8]        += E^T . 1                      (softmax denominators)
 //   warps 2-5  row warps (thread = token): positional logits, S from TMEM, per-latent tile maximum (warp shuffles +
 //              shared memory), E = exp(S - m) rounded to TF32 and written TRANSPOSED into shared memory, lazy rescale of
 //              the TMEM accumulators when a running maximum moves by more than TAU, final flush of the partials.
-// HBM traffic: X read once.
+// HBM traffic: X read once (+ one L2 re-read).
 #include <stdlib.h>
 #include "gf_common.cuh"
 #include "gf_tc_common.cuh"
@@ -38,7 +42,7 @@ constexpr float TAU = 8.f;        // lazy rescale threshold (natural-log units):
 
 struct Params {
   const float* Rt; const float* Ct; float* part;
-  int n, H, W, k, nsplit, tiles_per_image, nstages, ahead;
+  int n, H, W, k, nsplit, tiles_per_image, nstages;
 };
 
 struct Bars {
@@ -70,21 +74,24 @@ struct Cfg {
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-// MN-major operand, SWIZZLE_128B: 32 contiguous MN elements (128 B) per K row, 8 K rows per 1024-byte atom;
-// leading byte offset = next block of 32 MN elements, stride byte offset = next 8 K rows.
+// MN-major 32-bit operand, UMMA layout SWIZZLE_128B_BASE32B (= TMA SWIZZLE_128B_ATOM_32B, cute Swizzle<2,5,2>):
+// 32 contiguous MN elements (128 B) per K row, 4 K rows per 512-byte atom (32-byte chunks XOR row % 4);
+// leading byte offset = next block of 32 MN elements, stride byte offset = next 4 K rows.
+constexpr uint32_t LAYOUT_SW128_BASE32B = 1;
 __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)LAYOUT_SW128 << 61;
+  d |= (uint64_t)LAYOUT_SW128_BASE32B << 61;
   return d;
 }
 
 template <int KP, int NS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmM, const Params P) {
+centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmX2,
+                   const __grid_constant__ CUtensorMap tmM, const Params P) {
   using CF = Cfg<KP, NS>;
   constexpr int C = CF::C;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -115,7 +122,7 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   for (int i = threadIdx.x; i < 256; i += NUM_THREADS) reinterpret_cast<float*>(smem + CF::OFF_ONES)[i] = 1.f;
   if (threadIdx.x < KP) { mref[threadIdx.x] = -INFINITY; resc[threadIdx.x] = 1.f; }
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmX); prefetch_tmap(&tmM);
+    prefetch_tmap(&tmX); prefetch_tmap(&tmX2); prefetch_tmap(&tmM);
     for (int i = 0; i < nst; ++i) { mbar_init(smem_u32(&bars->slab_full[i]), 1); mbar_init(smem_u32(&bars->slab_empty[i]), 1); }
     mbar_init(smem_u32(&bars->m_full), 1); mbar_init(smem_u32(&bars->done), 1);
     for (int i = 0; i < 2; ++i) {
@@ -143,15 +150,20 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
       for (int s = 0; s < NS; ++s) tma_load_2d(s_m + s * (KP * 128), &tmM, mb, s * SLAB_CH, b * KP);
       long long ctr = 0;
-      for (int t = tile_beg; t < tile_end; ++t) {
-        const int row0 = (b * P.tiles_per_image + t) * TILE;
+      auto load_tile = [&](int it, const CUtensorMap* map) {
+        const int row0 = (b * P.tiles_per_image + tile_beg + it) * TILE;
         for (int s = 0; s < NS; ++s, ++ctr) {
           const int stage = (int)(ctr % nst);
           mbar_wait(smem_u32(&bars->slab_empty[stage]), (uint32_t)(((ctr / nst) & 1) ^ 1));
           const uint32_t bar = smem_u32(&bars->slab_full[stage]);
           mbar_expect_tx(bar, SLAB_BYTES);
-          tma_load_2d(s_ring + stage * SLAB_BYTES, &tmX, bar, s * SLAB_CH, row0);
+          tma_load_2d(s_ring + stage * SLAB_BYTES, map, bar, s * SLAB_CH, row0);
         }
+      };
+      load_tile(0, &tmX);
+      for (int it = 0; it < ntiles; ++it) {
+        if (it + 1 < ntiles) load_tile(it + 1, &tmX);      // GEMM1 of the next tile runs ahead of GEMM2 of this one
+        load_tile(it, &tmX2);                                 // second fetch (L2), MN-major swizzle
       }
     }
   } else if (warp == 1) {
@@ -162,10 +174,10 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       constexpr uint32_t IDESC3 = idesc_tf32(64, 8, 0);
       mbar_wait(smem_u32(&bars->m_full), 0);
       tc_fence_after();
+      long long ctr = 0;
       auto gemm1 = [&](int it) {
         const uint32_t d_s = tmem + COL_S + (it & 1) * 32;
-        for (int s = 0; s < NS; ++s) {
-          const long long ctr = (long long)it * NS + s;
+        for (int s = 0; s < NS; ++s, ++ctr) {
           const int stage = (int)(ctr % nst);
           mbar_wait(smem_u32(&bars->slab_full[stage]), (uint32_t)((ctr / nst) & 1));
           tc_fence_after();
@@ -174,25 +186,27 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           for (int kk = 0; kk < 4; ++kk)
             umma_ss(d_s, umma_desc(a_addr + kk * 32, 1024, LAYOUT_SW128), umma_desc(b_addr + kk * 32, 1024, LAYOUT_SW128),
                     IDESC1, (s | kk) ? 1u : 0u);
+          umma_commit(smem_u32(&bars->slab_empty[stage]));
         }
         umma_commit(smem_u32(&bars->s_full[it & 1]));
       };
       gemm1(0);
       for (int it = 0; it < ntiles; ++it) {
         const int buf = it & 1;
-        if (P.ahead && it + 1 < ntiles) gemm1(it + 1);            // ring holds two tiles: keep the row warps fed
+        if (it + 1 < ntiles) gemm1(it + 1);                          // keeps the row warps fed while GEMM2(it) is pending
         mbar_wait(smem_u32(&bars->e_full[buf]), (uint32_t)((it >> 1) & 1));
         tc_fence_after();
         const uint32_t e_addr = s_e + buf * CF::E_BYTES;
-        for (int s = 0; s < NS; ++s) {
-          const long long ctr = (long long)it * NS + s;
+        for (int s = 0; s < NS; ++s, ++ctr) {
           const int stage = (int)(ctr % nst);
+          mbar_wait(smem_u32(&bars->slab_full[stage]), (uint32_t)((ctr / nst) & 1));
+          tc_fence_after();
           const uint32_t x_addr = s_ring + stage * SLAB_BYTES;
 #pragma unroll
-          for (int kk = 0; kk < 16; ++kk)                           // 8 tokens per MMA
+          for (int kk = 0; kk < 16; ++kk)                           // 8 tokens (two 4-row swizzle atoms) per MMA
             umma_ss(tmem + COL_D2 + s * 32,
                     umma_desc(e_addr + (kk >> 2) * CF::E_CHUNK + (kk & 3) * 32, 1024, LAYOUT_SW128),
-                    umma_desc_mn(x_addr + kk * 1024, SLAB_BYTES, 1024), IDESC2, (it | kk) ? 1u : 0u);
+                    umma_desc_mn(x_addr + kk * 1024, SLAB_BYTES, 512), IDESC2, (it | kk) ? 1u : 0u);
           umma_commit(smem_u32(&bars->slab_empty[stage]));          // slab recycled once everything issued so far is done
         }
 #pragma unroll
@@ -200,7 +214,6 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           umma_ss(tmem + COL_D3, umma_desc(e_addr + (kk >> 2) * CF::E_CHUNK + (kk & 3) * 32, 1024, LAYOUT_SW128),
                   umma_desc(s_ones, 1024, LAYOUT_SW128), IDESC3, (it | kk) ? 1u : 0u);
         umma_commit(smem_u32(&bars->e_free[buf]));
-        if (!P.ahead && it + 1 < ntiles) gemm1(it + 1);
       }
       umma_commit(smem_u32(&bars->done));
     }
@@ -341,20 +354,20 @@ template <int KP, int NS>
 static int launch(const Layout& L, const float* X, float* ws, cudaStream_t st) {
   using CF = Cfg<KP, NS>;
   const int nst = stages_for<KP, NS>(device_smem_optin());
-  if (nst < NS) { set_error("tcgen05 centroid pass: shared memory too small for C=%d KP=%d", L.C, KP); return GF_ERR_UNSUPPORTED; }
-  CUtensorMap tmX, tmM;
+  if (nst < 4) { set_error("tcgen05 centroid pass: shared memory too small for C=%d KP=%d", L.C, KP); return GF_ERR_UNSUPPORTED; }
+  CUtensorMap tmX, tmX2, tmM;
   int rc;
   if ((rc = make_map(&tmX, X, (uint64_t)L.B * L.n, L.C, TILE, SLAB_CH, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map(&tmX2, X, (uint64_t)L.B * L.n, L.C, TILE, SLAB_CH, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
   if ((rc = make_map(&tmM, ws + L.w_M, (uint64_t)L.B * KP, L.C, KP, SLAB_CH, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   Params P;
   P.Rt = ws + L.w_Rt2; P.Ct = ws + L.w_Ct2; P.part = ws + L.w_PART;
   P.n = L.n; P.H = L.H; P.W = L.W; P.k = L.k; P.nsplit = L.nsplit_cen; P.tiles_per_image = L.n / TILE;
   P.nstages = nst;
-  P.ahead = nst >= 2 * NS ? 1 : 0;
   const int smem_bytes = CF::FIXED_BYTES + nst * SLAB_BYTES + 1024;
   auto kern = centroid_tc_kernel<KP, NS>;
   GF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  kern<<<dim3(L.nsplit_cen, L.B), NUM_THREADS, smem_bytes, st>>>(tmX, tmM, P);
+  kern<<<dim3(L.nsplit_cen, L.B), NUM_THREADS, smem_bytes, st>>>(tmX, tmX2, tmM, P);
   GF_LAUNCH_OK();
   return GF_OK;
 }
@@ -368,8 +381,8 @@ bool tc_centroid_supported(const Layout& L, const gf_attn_desc* d) {
   if (L.n % tcc::TILE != 0 || L.B > 65535) return false;
   const int limit = tc::device_smem_optin();
   const int ns = L.C / 32;
-  if (L.KP == 16) return ns == 2 ? tcc::stages_for<16, 2>(limit) >= 2 : ns == 4 ? tcc::stages_for<16, 4>(limit) >= 4 : tcc::stages_for<16, 8>(limit) >= 8;
-  return ns == 2 ? tcc::stages_for<32, 2>(limit) >= 2 : ns == 4 ? tcc::stages_for<32, 4>(limit) >= 4 : tcc::stages_for<32, 8>(limit) >= 8;
+  if (L.KP == 16) return (ns == 2 ? tcc::stages_for<16, 2>(limit) : ns == 4 ? tcc::stages_for<16, 4>(limit) : tcc::stages_for<16, 8>(limit)) >= 4;
+  return (ns == 2 ? tcc::stages_for<32, 2>(limit) : ns == 4 ? tcc::stages_for<32, 4>(limit) : tcc::stages_for<32, 8>(limit)) >= 4;
 }
 
 int centroid_pass_tc(const Layout& L, const gf_attn_desc* d, const float* X, float* ws, cudaStream_t st) {

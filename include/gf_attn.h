@@ -104,6 +104,9 @@ int gf_attn_last_centroid_path(void);
 /* Number of kernels this library has launched in this process (all threads); bench.py reports the delta. */
 long long gf_attn_launch_count(void);
 
+/* Debug aid for the bring-up probes (tools/): float offsets {w_PART, w_XBAR, nsplit_cen, KP, w_M, w_Rt2, w_Ct2, w_total} of the workspace. */
+int gf_attn_debug_layout(const gf_attn_desc* desc, long long* out, int n);
+
 /* Size in floats of the folded-weight buffer (stage W output + its scratch). */
 int gf_attn_folded_floats(const gf_attn_desc* desc, size_t* out_floats);
 
