@@ -102,7 +102,7 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   float* red = reinterpret_cast<float*>(smem + CF::OFF_SMALL);      // [4][KP]
   float* mref = red + 4 * KP;                                       // [KP]
   float* resc = mref + KP;                                          // [KP]
-  int* flag = reinterpret_cast<int*>(resc + KP);                    // any latent needs a rescale this tile
+  volatile int* trigf = reinterpret_cast<volatile int*>(resc + KP);  // [2] per-tile-parity trigger flags
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nst = P.nstages;
   const int b = blockIdx.y, sp = blockIdx.x;
@@ -121,6 +121,7 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 
   for (int i = threadIdx.x; i < 256; i += NUM_THREADS) reinterpret_cast<float*>(smem + CF::OFF_ONES)[i] = 1.f;
   if (threadIdx.x < KP) { mref[threadIdx.x] = -INFINITY; resc[threadIdx.x] = 1.f; }
+  if (threadIdx.x < 2) trigf[threadIdx.x] = 0;
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmX); prefetch_tmap(&tmX2); prefetch_tmap(&tmM);
     for (int i = 0; i < nst; ++i) { mbar_init(smem_u32(&bars->slab_full[i]), 1); mbar_init(smem_u32(&bars->slab_empty[i]), 1); }
@@ -244,38 +245,52 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       tmem_ld16(tmem + lane_addr + COL_S + buf * 32, acc);
       if constexpr (KP == 32) tmem_ld16(tmem + lane_addr + COL_S + buf * 32 + 16, acc + 16);
       tmem_wait_ld();
-      // ---- per-latent maximum over the 128 tokens of the tile
+      // ---- running reference m_j of the online softmax.  Cheap path (almost every tile): each thread checks its own
+      //      logits against m_j + TAU, one warp vote, one flag in shared memory.  Only when some logit jumps more than TAU
+      //      above the reference (always on the first tile) is the full per-latent maximum reduced (warp shuffles + smem).
+      float ex = -INFINITY;
 #pragma unroll
       for (int j = 0; j < KP; ++j) {
         sv[j] += acc[j];
-        float v = sv[j];
+        ex = fmaxf(ex, sv[j] - mref[j]);             // padded latents: (-inf) - (-inf) = NaN, ignored by fmaxf
+      }
+      const bool trig = __any_sync(0xffffffffu, ex > TAU);
+      if (lane == 0 && trig) trigf[buf] = 1;
+      if (rtid == 0) trigf[buf ^ 1] = 0;               // clean flag for the next tile
+      named_bar_sync(1, 128);
+      const bool full = trigf[buf] != 0;
+      if (full) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-        if (lane == 0) red[(warp - 2) * KP + j] = v;
-      }
-      named_bar_sync(1, 128);
-      if (rtid < KP) {
-        const float tm = fmaxf(fmaxf(red[rtid], red[KP + rtid]), fmaxf(red[2 * KP + rtid], red[3 * KP + rtid]));
-        const float mo = mref[rtid];
-        float mn = mo, f = 1.f;
-        if (tm > mo + TAU || (mo == -INFINITY && tm > -INFINITY)) {   // lazy: move the reference only on a real jump
-          mn = tm;
-          f = (mo == -INFINITY) ? 1.f : __expf(mo - mn);
+        for (int j = 0; j < KP; ++j) {
+          float v = sv[j];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+          if (lane == 0) red[(warp - 2) * KP + j] = v;
         }
-        mref[rtid] = mn;
-        resc[rtid] = f;
+        named_bar_sync(1, 128);
+        if (rtid < KP) {
+          const float tm = fmaxf(fmaxf(red[rtid], red[KP + rtid]), fmaxf(red[2 * KP + rtid], red[3 * KP + rtid]));
+          const float mo = mref[rtid];
+          float mn = mo, f = 1.f;
+          if (tm > mo + TAU || (mo == -INFINITY && tm > -INFINITY)) {
+            mn = tm;
+            f = (mo == -INFINITY) ? 1.f : __expf(mo - mn);
+          }
+          mref[rtid] = mn;
+          resc[rtid] = f;
+        }
+        named_bar_sync(1, 128);
       }
-      if (rtid == 0) *flag = 0;
-      named_bar_sync(1, 128);
-      if (rtid < KP && resc[rtid] != 1.f) *flag = 1;
-      // ---- E = exp(S - m): TF32-rounded, written transposed (E^T[latent][token], K-major SW128, 32-token chunks)
+      // ---- E = exp(S - m), written transposed (E^T[latent][token], K-major SW128, 32-token chunks).  E is NOT rounded
+      //      to TF32: the tensor core's truncation bias hits numerator (D2) and denominator (D3) alike and cancels.
       // buffer `buf` was last read by GEMM2(it-2), whose completion this thread observed during tile it-1 (below)
-      uint8_t* eb = smem + CF::OFF_E + buf * CF::E_BYTES + q * CF::E_CHUNK;
+      uint8_t* eb = smem + CF::OFF_E + buf * CF::E_BYTES + q * CF::E_CHUNK + (lane & 3) * 4;
+      const int c16 = lane >> 2;
 #pragma unroll
       for (int j = 0; j < KP; ++j) {
-        const float mn = mref[j];
-        const float e = (mn == -INFINITY) ? 0.f : exp2f((sv[j] - mn) * 1.4426950408889634f);
-        *reinterpret_cast<float*>(eb + j * 128 + (((lane >> 2) ^ (j & 7)) << 4) + (lane & 3) * 4) = round_tf32_rn(e);
+        const float ml = mref[j] * 1.4426950408889634f;
+        const float e = (ml == -INFINITY) ? 0.f : exp2f(fmaf(sv[j], 1.4426950408889634f, -ml));
+        *reinterpret_cast<float*>(eb + j * 128 + ((c16 ^ (j & 7)) << 4)) = e;
       }
       // ---- every tile: observe the completion of GEMM2(it-1) (parity bookkeeping must not skip phases); then, if a
       //      running maximum moved, rescale the accumulators before GEMM2(it) adds to them
@@ -283,8 +298,7 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         mbar_wait(smem_u32(&bars->e_free[buf ^ 1]), (uint32_t)(((it - 1) >> 1) & 1));
         tc_fence_after();
       }
-      named_bar_sync(1, 128);                                       // flag complete
-      if (*flag && it > 0) {
+      if (full && it > 0) {
         // M=64 accumulators: latent j lives in TMEM lane (j % 16) + 32 * (j / 16): lanes 0-15 of quadrants 0 (and 1)
         if (q * 16 < KP) {
           const float f = lane < 16 ? resc[q * 16 + lane] : 1.f;
