@@ -169,6 +169,10 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       long long actr = 0;
       int img_changes = 0, prev_b = -1;
       long long it = 0;
+      // base descriptors, advanced with one 64-bit add per MMA (start-address field = 16-byte units)
+      const uint64_t dRing = umma_desc(s_ring, 1024, LAYOUT_SW128);
+      const uint64_t dKp = umma_desc(s_kp, 1024, LAYOUT_SW128);
+      const uint64_t dV = umma_desc(s_v, V_SBO, V_LAYOUT);
       for (long long tile = tile_beg; tile < tile_end; ++tile, ++it) {
         const int b = (int)(tile / P.tiles_per_image);
         const int buf = (int)(it & 1);
@@ -186,11 +190,10 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           const int stage = (int)(ctr % nst);
           mbar_wait(smem_u32(&bars->slab_full[stage]), (uint32_t)((ctr / nst) & 1));
           tc_fence_after();
-          const uint32_t a_addr = s_ring + stage * SLAB_BYTES, b_addr = s_kp + s * (KP * 128);
+          const uint64_t da = dRing + (uint64_t)(stage * (SLAB_BYTES >> 4));
+          const uint64_t db = dKp + (uint64_t)(s * ((KP * 128) >> 4));
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_ss(d_s, umma_desc(a_addr + kk * 32, 1024, LAYOUT_SW128), umma_desc(b_addr + kk * 32, 1024, LAYOUT_SW128),
-                    IDESC1, (s | kk) ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk) umma_ss(d_s, da + kk * 2, db + kk * 2, IDESC1, (s | kk) ? 1u : 0u);
           if (TWO_PASS) umma_commit(smem_u32(&bars->slab_empty[stage]));    // slab may be recycled once these MMAs are done
         }
         umma_commit(smem_u32(&bars->s_full[buf]));
@@ -209,15 +212,13 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           mbar_wait(smem_u32(&bars->acc_empty[a]), (uint32_t)(((actr / NACC) & 1) ^ 1));
           tc_fence_after();
           const uint32_t d_acc = tmem + COL_ACC + a * 64;
-          const uint32_t vg = s_v + s * 32 * CF::V_ROW_BYTES;
+          const uint64_t dvg = dV + (uint64_t)((s * 32 * CF::V_ROW_BYTES) >> 4);
 #pragma unroll
-          for (int kk = 0; kk < KP / 8; ++kk)
-            umma_ts(d_acc, a_p + kk * 8, umma_desc(vg + kk * 32, V_SBO, V_LAYOUT), IDESC2, kk ? 1u : 0u);
+          for (int kk = 0; kk < KP / 8; ++kk) umma_ts(d_acc, a_p + kk * 8, dvg + kk * 2, IDESC2, kk ? 1u : 0u);
           if constexpr (MODE == GF_INT_BOTH) {
-            const uint32_t vb = s_v + (C + s * 32) * CF::V_ROW_BYTES;
+            const uint64_t dvb = dV + (uint64_t)(((C + s * 32) * CF::V_ROW_BYTES) >> 4);
 #pragma unroll
-            for (int kk = 0; kk < KP / 8; ++kk)
-              umma_ts(d_acc + 32, a_p + kk * 8, umma_desc(vb + kk * 32, V_SBO, V_LAYOUT), IDESC2, kk ? 1u : 0u);
+            for (int kk = 0; kk < KP / 8; ++kk) umma_ts(d_acc + 32, a_p + kk * 8, dvb + kk * 2, IDESC2, kk ? 1u : 0u);
           }
           umma_commit(smem_u32(&bars->acc_full[a]));
         }

@@ -175,6 +175,13 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       constexpr uint32_t IDESC3 = idesc_tf32(64, 8, 0);
       mbar_wait(smem_u32(&bars->m_full), 0);
       tc_fence_after();
+      // Descriptors are built once and advanced with one 64-bit add per MMA (the start-address field counts 16-byte units and
+      // never overflows its 14 bits inside the 227 KB window): the issuing thread is a serial bottleneck otherwise.
+      const uint64_t dM0 = umma_desc(s_m, 1024, LAYOUT_SW128);
+      const uint64_t dOnes = umma_desc(s_ones, 1024, LAYOUT_SW128);
+      const uint64_t dRingK = umma_desc(s_ring, 1024, LAYOUT_SW128);             // slab as K-major A (GEMM1)
+      const uint64_t dRingMN = umma_desc_mn(s_ring, SLAB_BYTES, 512);            // slab as MN-major B (GEMM2)
+      const uint64_t dE0 = umma_desc(s_e, 1024, LAYOUT_SW128);
       long long ctr = 0;
       auto gemm1 = [&](int it) {
         const uint32_t d_s = tmem + COL_S + (it & 1) * 32;
@@ -182,11 +189,10 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           const int stage = (int)(ctr % nst);
           mbar_wait(smem_u32(&bars->slab_full[stage]), (uint32_t)((ctr / nst) & 1));
           tc_fence_after();
-          const uint32_t a_addr = s_ring + stage * SLAB_BYTES, b_addr = s_m + s * (KP * 128);
+          const uint64_t da = dRingK + (uint64_t)(stage * (SLAB_BYTES >> 4));
+          const uint64_t db = dM0 + (uint64_t)(s * ((KP * 128) >> 4));
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_ss(d_s, umma_desc(a_addr + kk * 32, 1024, LAYOUT_SW128), umma_desc(b_addr + kk * 32, 1024, LAYOUT_SW128),
-                    IDESC1, (s | kk) ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk) umma_ss(d_s, da + kk * 2, db + kk * 2, IDESC1, (s | kk) ? 1u : 0u);
           umma_commit(smem_u32(&bars->slab_empty[stage]));
         }
         umma_commit(smem_u32(&bars->s_full[it & 1]));
@@ -197,23 +203,23 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         if (it + 1 < ntiles) gemm1(it + 1);                          // keeps the row warps fed while GEMM2(it) is pending
         mbar_wait(smem_u32(&bars->e_full[buf]), (uint32_t)((it >> 1) & 1));
         tc_fence_after();
-        const uint32_t e_addr = s_e + buf * CF::E_BYTES;
+        const uint64_t de = dE0 + (uint64_t)(buf * (CF::E_BYTES >> 4));
+        const uint32_t acc0 = it ? 1u : 0u;
         for (int s = 0; s < NS; ++s, ++ctr) {
           const int stage = (int)(ctr % nst);
           mbar_wait(smem_u32(&bars->slab_full[stage]), (uint32_t)((ctr / nst) & 1));
           tc_fence_after();
-          const uint32_t x_addr = s_ring + stage * SLAB_BYTES;
+          const uint64_t dx = dRingMN + (uint64_t)(stage * (SLAB_BYTES >> 4));
+          const uint32_t d2 = tmem + COL_D2 + s * 32;
 #pragma unroll
           for (int kk = 0; kk < 16; ++kk)                           // 8 tokens (two 4-row swizzle atoms) per MMA
-            umma_ss(tmem + COL_D2 + s * 32,
-                    umma_desc(e_addr + (kk >> 2) * CF::E_CHUNK + (kk & 3) * 32, 1024, LAYOUT_SW128),
-                    umma_desc_mn(x_addr + kk * 1024, SLAB_BYTES, 512), IDESC2, (it | kk) ? 1u : 0u);
+            umma_ss(d2, de + (uint64_t)(((kk >> 2) * CF::E_CHUNK + (kk & 3) * 32) >> 4), dx + (uint64_t)(kk * 64), IDESC2,
+                    kk ? 1u : acc0);
           umma_commit(smem_u32(&bars->slab_empty[stage]));          // slab recycled once everything issued so far is done
         }
 #pragma unroll
         for (int kk = 0; kk < 16; ++kk)
-          umma_ss(tmem + COL_D3, umma_desc(e_addr + (kk >> 2) * CF::E_CHUNK + (kk & 3) * 32, 1024, LAYOUT_SW128),
-                  umma_desc(s_ones, 1024, LAYOUT_SW128), IDESC3, (it | kk) ? 1u : 0u);
+          umma_ss(tmem + COL_D3, de + (uint64_t)(((kk >> 2) * CF::E_CHUNK + (kk & 3) * 32) >> 4), dOnes, IDESC3, kk ? 1u : acc0);
         umma_commit(smem_u32(&bars->e_free[buf]));
       }
       umma_commit(smem_u32(&bars->done));
