@@ -59,7 +59,19 @@ int make_layout(const gf_attn_desc* d, Layout* L) {
   // statistics / centroid splits: about two waves of CTAs over 148 SMs
   int want = (2 * 148 + l.B - 1) / l.B;
   l.nsplit_norm = want; if (l.nsplit_norm > (l.n + 63) / 64) l.nsplit_norm = (l.n + 63) / 64; if (l.nsplit_norm < 1) l.nsplit_norm = 1;
-  l.nsplit_cen = want;  if (l.nsplit_cen > (l.n + 127) / 128) l.nsplit_cen = (l.n + 127) / 128; if (l.nsplit_cen < 1) l.nsplit_cen = 1;
+  {
+    // centroid splits: one CTA per SM; pick the split count (<= 16) whose grid B*nsplit fills whole waves of 148 SMs best
+    const int tiles = (l.n + 127) / 128;
+    int best = 1;
+    double best_u = -1.0;
+    for (int ns = 1; ns <= 16 && ns <= tiles; ++ns) {
+      const double waves = (double)l.B * ns / 148.0;
+      double u = waves / ceil(waves);
+      if (waves < 1.0) u = waves;                       // under one wave: utilisation is just the fill
+      if (u > best_u + 1e-9) { best_u = u; best = ns; }
+    }
+    l.nsplit_cen = best;
+  }
 
   o = 0;
   const size_t B = l.B, KP = l.KP;

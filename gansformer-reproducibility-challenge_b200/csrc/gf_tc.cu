@@ -130,7 +130,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
-      long long ctr = 0;       // global ring-slot counter of this CTA
+      uint32_t ctr = 0;        // global ring-slot counter of this CTA (32-bit: 64-bit div/mod is ~100 instructions)
       int img_changes = 0;
       int prev_b = -1;
       for (long long tile = tile_beg; tile < tile_end; ++tile) {
@@ -150,8 +150,8 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const int row0 = (int)(tile * TILE);
         for (int ss = 0; ss < SPT; ++ss, ++ctr) {
           const int s = ss % NS;                     // two-pass: the same slabs are fetched again for the epilogue
-          const int stage = (int)(ctr % nst);
-          const uint32_t phase = (uint32_t)((ctr / nst) & 1);
+          const int stage = (int)(ctr % (uint32_t)nst);
+          const uint32_t phase = (ctr / (uint32_t)nst) & 1u;
           mbar_wait(smem_u32(&bars->slab_empty[stage]), phase ^ 1u);
           const uint32_t bar = smem_u32(&bars->slab_full[stage]);
           mbar_expect_tx(bar, SLAB_BYTES);
@@ -166,9 +166,9 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       constexpr uint32_t IDESC2 = umma_idesc_tf32(TILE, 32);
       constexpr uint32_t V_LAYOUT = KP == 32 ? LAYOUT_SW128 : LAYOUT_SW64;
       constexpr uint32_t V_SBO = 8 * CF::V_ROW_BYTES;
-      long long actr = 0;
+      uint32_t actr = 0;
       int img_changes = 0, prev_b = -1;
-      long long it = 0;
+      uint32_t it = 0;
       // base descriptors, advanced with one 64-bit add per MMA (start-address field = 16-byte units)
       const uint64_t dRing = umma_desc(s_ring, 1024, LAYOUT_SW128);
       const uint64_t dKp = umma_desc(s_kp, 1024, LAYOUT_SW128);
@@ -176,7 +176,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       for (long long tile = tile_beg; tile < tile_end; ++tile, ++it) {
         const int b = (int)(tile / P.tiles_per_image);
         const int buf = (int)(it & 1);
-        const uint32_t bphase = (uint32_t)((it >> 1) & 1);
+        const uint32_t bphase = (it >> 1) & 1u;
         if (b != prev_b) {
           mbar_wait(smem_u32(&bars->kv_full), (uint32_t)(img_changes & 1));
           tc_fence_after();
@@ -186,9 +186,9 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         // ---- GEMM1: S[buf] = X . K'^T over all slabs (pass 1 of a two-pass tile)
         const uint32_t d_s = tmem + COL_S + buf * 32;
         for (int s = 0; s < NS; ++s) {
-          const long long ctr = it * SPT + s;
-          const int stage = (int)(ctr % nst);
-          mbar_wait(smem_u32(&bars->slab_full[stage]), (uint32_t)((ctr / nst) & 1));
+          const uint32_t ctr = it * SPT + s;
+          const int stage = (int)(ctr % (uint32_t)nst);
+          mbar_wait(smem_u32(&bars->slab_full[stage]), (ctr / (uint32_t)nst) & 1u);
           tc_fence_after();
           const uint64_t da = dRing + (uint64_t)(stage * (SLAB_BYTES >> 4));
           const uint64_t db = dKp + (uint64_t)(s * ((KP * 128) >> 4));
@@ -206,10 +206,10 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           if (TWO_PASS) {
             // Parity waits are only valid if a waiter never falls two phases behind a barrier: every consumer walks the
             // fills of the ring in slot order.  Waiting the pass-2 fill here also makes acc_full(s) imply "slab s landed".
-            const long long c2 = it * SPT + NS + s;
-            mbar_wait(smem_u32(&bars->slab_full[(int)(c2 % nst)]), (uint32_t)((c2 / nst) & 1));
+            const uint32_t c2 = it * SPT + NS + s;
+            mbar_wait(smem_u32(&bars->slab_full[(int)(c2 % (uint32_t)nst)]), (c2 / (uint32_t)nst) & 1u);
           }
-          mbar_wait(smem_u32(&bars->acc_empty[a]), (uint32_t)(((actr / NACC) & 1) ^ 1));
+          mbar_wait(smem_u32(&bars->acc_empty[a]), ((actr / NACC) & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t d_acc = tmem + COL_ACC + a * 64;
           const uint64_t dvg = dV + (uint64_t)((s * 32 * CF::V_ROW_BYTES) >> 4);
@@ -234,11 +234,11 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int sw = row & 7;
     const uint32_t row_off = (uint32_t)row * 128u;
-    long long it = 0;
+    uint32_t it = 0;
     for (long long tile = tile_beg; tile < tile_end; ++tile, ++it) {
       const int b = (int)(tile / P.tiles_per_image);
       const int buf = (int)(it & 1);
-      const uint32_t bphase = (uint32_t)((it >> 1) & 1);
+      const uint32_t bphase = (it >> 1) & 1u;
       const long long tok = (tile % P.tiles_per_image) * TILE + row;      // token index inside the image
       // positional logits of this token (issued first: their L2 latency hides behind the statistics)
       float sv[KP];
@@ -258,9 +258,9 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         float sh = 0.f, sum = 0.f, sumsq = 0.f;
 #pragma unroll 1
         for (int s = 0; s < NS; ++s) {
-          const long long ctr = it * SPT + s;
-          const int stage = (int)(ctr % nst);
-          mbar_wait(smem_u32(&bars->slab_full[stage]), (uint32_t)((ctr / nst) & 1));
+          const uint32_t ctr = it * SPT + s;
+          const int stage = (int)(ctr % (uint32_t)nst);
+          mbar_wait(smem_u32(&bars->slab_full[stage]), (ctr / (uint32_t)nst) & 1u);
           if (P.norm_layer) {
             const uint8_t* slab = smem + CF::OFF_RING + stage * SLAB_BYTES + row_off;
             const float4* isc = P.in_scale ? reinterpret_cast<const float4*>(P.in_scale + (size_t)b * P.in_ld + s * SLAB_CH) : nullptr;
@@ -330,8 +330,8 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       if (TWO_PASS) {   // observe the pass-2 fills too (see the MMA warp): keeps this thread's parity bookkeeping in step
 #pragma unroll 1
         for (int s = 0; s < NS; ++s) {
-          const long long c2 = it * SPT + NS + s;
-          mbar_wait(smem_u32(&bars->slab_full[(int)(c2 % nst)]), (uint32_t)((c2 / nst) & 1));
+          const uint32_t c2 = it * SPT + NS + s;
+          mbar_wait(smem_u32(&bars->slab_full[(int)(c2 % (uint32_t)nst)]), (c2 / (uint32_t)nst) & 1u);
         }
       }
     }
@@ -345,11 +345,11 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const int sw = row & 7;                        // 128B-swizzle phase of this row
     const uint32_t row_off = (uint32_t)row * 128u;
     int pending_stage = -1;
-    long long it = 0;
+    uint32_t it = 0;
     for (long long tile = tile_beg; tile < tile_end; ++tile, ++it) {
       const int b = (int)(tile / P.tiles_per_image);
       const int buf = (int)(it & 1);
-      const uint32_t bphase = (uint32_t)((it >> 1) & 1);
+      const uint32_t bphase = (it >> 1) & 1u;
       float pnz = 0.f;                               // post-op: per-token noise value
       if (P.has_post && P.pnoise) {
         const long long tokp = (tile % P.tiles_per_image) * TILE + row;
@@ -364,15 +364,15 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       // ---- epilogue of this group's slabs: y = LN(x) * gain (+ bias) [post-op], in place, TMA store
 #pragma unroll 1
       for (int s = g; s < NS; s += 2) {
-        const long long ctr = it * SPT + (TWO_PASS ? NS : 0) + s;
-        const long long actr = it * NS + s;
-        const int stage = (int)(ctr % nst);
+        const uint32_t ctr = it * SPT + (TWO_PASS ? NS : 0) + s;
+        const uint32_t actr = it * NS + s;
+        const int stage = (int)(ctr % (uint32_t)nst);
         const int a = (int)(actr % NACC);
         // acc_full first: GEMM2(s) was issued after GEMM1 of this tile completed (single-pass: every slab of the tile has
         // landed) and, in two-pass mode, after the MMA warp saw this slab's pass-2 fill -- so the slab_full wait below can
         // never be a phase early; it is kept for the async-proxy -> generic-proxy visibility of the TMA write.
-        mbar_wait(smem_u32(&bars->acc_full[a]), (uint32_t)((actr / NACC) & 1));
-        mbar_wait(smem_u32(&bars->slab_full[stage]), (uint32_t)((ctr / nst) & 1));
+        mbar_wait(smem_u32(&bars->acc_full[a]), (actr / NACC) & 1u);
+        mbar_wait(smem_u32(&bars->slab_full[stage]), (ctr / (uint32_t)nst) & 1u);
         tc_fence_after();
         float gv[32], bv[MODE == GF_INT_BOTH ? 32 : 1];
         const uint32_t t_acc = tmem + lane_addr + COL_ACC + a * 64;

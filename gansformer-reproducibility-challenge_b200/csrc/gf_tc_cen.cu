@@ -150,12 +150,12 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       mbar_expect_tx(mb, (uint32_t)CF::M_BYTES);
 #pragma unroll
       for (int s = 0; s < NS; ++s) tma_load_2d(s_m + s * (KP * 128), &tmM, mb, s * SLAB_CH, b * KP);
-      long long ctr = 0;
+      uint32_t ctr = 0;
       auto load_tile = [&](int it, const CUtensorMap* map) {
         const int row0 = (b * P.tiles_per_image + tile_beg + it) * TILE;
         for (int s = 0; s < NS; ++s, ++ctr) {
-          const int stage = (int)(ctr % nst);
-          mbar_wait(smem_u32(&bars->slab_empty[stage]), (uint32_t)(((ctr / nst) & 1) ^ 1));
+          const int stage = (int)(ctr % (uint32_t)nst);
+          mbar_wait(smem_u32(&bars->slab_empty[stage]), ((ctr / (uint32_t)nst) & 1u) ^ 1u);
           const uint32_t bar = smem_u32(&bars->slab_full[stage]);
           mbar_expect_tx(bar, SLAB_BYTES);
           tma_load_2d(s_ring + stage * SLAB_BYTES, map, bar, s * SLAB_CH, row0);
@@ -182,12 +182,12 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       const uint64_t dRingK = umma_desc(s_ring, 1024, LAYOUT_SW128);             // slab as K-major A (GEMM1)
       const uint64_t dRingMN = umma_desc_mn(s_ring, SLAB_BYTES, 512);            // slab as MN-major B (GEMM2)
       const uint64_t dE0 = umma_desc(s_e, 1024, LAYOUT_SW128);
-      long long ctr = 0;
+      uint32_t ctr = 0;
       auto gemm1 = [&](int it) {
         const uint32_t d_s = tmem + COL_S + (it & 1) * 32;
         for (int s = 0; s < NS; ++s, ++ctr) {
-          const int stage = (int)(ctr % nst);
-          mbar_wait(smem_u32(&bars->slab_full[stage]), (uint32_t)((ctr / nst) & 1));
+          const int stage = (int)(ctr % (uint32_t)nst);
+          mbar_wait(smem_u32(&bars->slab_full[stage]), (ctr / (uint32_t)nst) & 1u);
           tc_fence_after();
           const uint64_t da = dRingK + (uint64_t)(stage * (SLAB_BYTES >> 4));
           const uint64_t db = dM0 + (uint64_t)(s * ((KP * 128) >> 4));
@@ -206,8 +206,8 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         const uint64_t de = dE0 + (uint64_t)(buf * (CF::E_BYTES >> 4));
         const uint32_t acc0 = it ? 1u : 0u;
         for (int s = 0; s < NS; ++s, ++ctr) {
-          const int stage = (int)(ctr % nst);
-          mbar_wait(smem_u32(&bars->slab_full[stage]), (uint32_t)((ctr / nst) & 1));
+          const int stage = (int)(ctr % (uint32_t)nst);
+          mbar_wait(smem_u32(&bars->slab_full[stage]), (ctr / (uint32_t)nst) & 1u);
           tc_fence_after();
           const uint64_t dx = dRingMN + (uint64_t)(stage * (SLAB_BYTES >> 4));
           const uint32_t d2 = tmem + COL_D2 + s * 32;
@@ -226,46 +226,56 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     }
   } else {
     // =============================== row warps ===============================
+    // One warp per scheduler and nothing to hide latency with: the loop is written for few instructions and no exposed
+    // loads -- next tile's positional logits are prefetched, references live in registers (pre-multiplied by log2 e),
+    // exp is one ex2.approx, the swizzled store offsets are precomputed.
     const int q = warp & 3;                                         // TMEM lane quadrant == 32-token chunk of the tile
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int rtid = (warp - 2) * 32 + lane;                        // 0..127 inside the row-warp group
+    constexpr float LOG2E = 1.4426950408889634f;
+    auto load_pos = [&](int it, float* dst) {
+      const int tok = (tile_beg + it) * TILE + row;
+      const int h = tok / P.W, w = tok - h * P.W;
+      const float4* rt = reinterpret_cast<const float4*>(P.Rt + ((size_t)b * P.H + h) * KP);
+      const float4* ct = reinterpret_cast<const float4*>(P.Ct + ((size_t)b * P.W + w) * KP);
+#pragma unroll
+      for (int j4 = 0; j4 < KP / 4; ++j4) {
+        const float4 r = __ldg(rt + j4), c = __ldg(ct + j4);
+        dst[j4 * 4 + 0] = r.x + c.x; dst[j4 * 4 + 1] = r.y + c.y; dst[j4 * 4 + 2] = r.z + c.z; dst[j4 * 4 + 3] = r.w + c.w;
+      }
+    };
+    float pos[KP];                                                  // positional logits of the current tile
+    float ml[KP];                                                   // running references * log2(e); padded latents: 0
+    load_pos(0, pos);
+#pragma unroll
+    for (int j = 0; j < KP; ++j) ml[j] = j < P.k ? -INFINITY : 0.f;
+    uint32_t soff[8];                                               // byte offset of this token inside row j of a chunk
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) soff[jj] = (uint32_t)((((lane >> 2) ^ jj) << 4) + (lane & 3) * 4);
     for (int it = 0; it < ntiles; ++it) {
       const int buf = it & 1;
       const uint32_t bph = (uint32_t)((it >> 1) & 1);
-      const int tok = (tile_beg + it) * TILE + row;
-      float sv[KP];
-      {
-        const int h = tok / P.W, w = tok % P.W;
-        const float4* rt = reinterpret_cast<const float4*>(P.Rt + ((size_t)b * P.H + h) * KP);
-        const float4* ct = reinterpret_cast<const float4*>(P.Ct + ((size_t)b * P.W + w) * KP);
-#pragma unroll
-        for (int j4 = 0; j4 < KP / 4; ++j4) {
-          const float4 r = __ldg(rt + j4), c = __ldg(ct + j4);
-          sv[j4 * 4 + 0] = r.x + c.x; sv[j4 * 4 + 1] = r.y + c.y; sv[j4 * 4 + 2] = r.z + c.z; sv[j4 * 4 + 3] = r.w + c.w;
-        }
-      }
       mbar_wait(smem_u32(&bars->s_full[buf]), bph);
       tc_fence_after();
-      float acc[KP];
-      tmem_ld16(tmem + lane_addr + COL_S + buf * 32, acc);
-      if constexpr (KP == 32) tmem_ld16(tmem + lane_addr + COL_S + buf * 32 + 16, acc + 16);
+      float sv[KP];
+      tmem_ld16(tmem + lane_addr + COL_S + buf * 32, sv);
+      if constexpr (KP == 32) tmem_ld16(tmem + lane_addr + COL_S + buf * 32 + 16, sv + 16);
       tmem_wait_ld();
-      // ---- running reference m_j of the online softmax.  Cheap path (almost every tile): each thread checks its own
-      //      logits against m_j + TAU, one warp vote, one flag in shared memory.  Only when some logit jumps more than TAU
-      //      above the reference (always on the first tile) is the full per-latent maximum reduced (warp shuffles + smem).
+      // t_j = (logit - reference) * log2(e); the trigger test needs only its maximum over this thread's latents
       float ex = -INFINITY;
 #pragma unroll
       for (int j = 0; j < KP; ++j) {
-        sv[j] += acc[j];
-        ex = fmaxf(ex, sv[j] - mref[j]);             // padded latents: (-inf) - (-inf) = NaN, ignored by fmaxf
+        sv[j] = (sv[j] + pos[j]) * LOG2E;                           // logits in log2 units (padded latents: -inf)
+        ex = fmaxf(ex, sv[j] - ml[j]);                              // first tile: +inf -> trigger
       }
-      const bool trig = __any_sync(0xffffffffu, ex > TAU);
+      if (it + 1 < ntiles) load_pos(it + 1, pos);                   // prefetch: consumed one tile later
+      const bool trig = __any_sync(0xffffffffu, ex > TAU * LOG2E);
       if (lane == 0 && trig) trigf[buf] = 1;
-      if (rtid == 0) trigf[buf ^ 1] = 0;               // clean flag for the next tile
+      if (rtid == 0) trigf[buf ^ 1] = 0;                            // clean flag for the next tile
       named_bar_sync(1, 128);
       const bool full = trigf[buf] != 0;
-      if (full) {
+      if (full) {   // rare: some logit jumped more than TAU above its reference (always on the first tile)
 #pragma unroll
         for (int j = 0; j < KP; ++j) {
           float v = sv[j];
@@ -276,27 +286,28 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         named_bar_sync(1, 128);
         if (rtid < KP) {
           const float tm = fmaxf(fmaxf(red[rtid], red[KP + rtid]), fmaxf(red[2 * KP + rtid], red[3 * KP + rtid]));
-          const float mo = mref[rtid];
+          const float mo = mref[rtid];                              // log2 units; -inf before the first tile
           float mn = mo, f = 1.f;
-          if (tm > mo + TAU || (mo == -INFINITY && tm > -INFINITY)) {
+          if (rtid < P.k && (tm > mo + TAU * LOG2E || mo == -INFINITY)) {
             mn = tm;
-            f = (mo == -INFINITY) ? 1.f : __expf(mo - mn);
+            f = (mo == -INFINITY) ? 1.f : exp2f(mo - mn);
           }
           mref[rtid] = mn;
           resc[rtid] = f;
         }
         named_bar_sync(1, 128);
+#pragma unroll
+        for (int j = 0; j < KP; ++j) ml[j] = j < P.k ? mref[j] : 0.f;
       }
-      // ---- E = exp(S - m), written transposed (E^T[latent][token], K-major SW128, 32-token chunks).  E is NOT rounded
-      //      to TF32: the tensor core's truncation bias hits numerator (D2) and denominator (D3) alike and cancels.
+      // ---- E = 2^(t_j), written transposed (E^T[latent][token], K-major SW128, 32-token chunks).  E is NOT rounded to
+      //      TF32: the tensor core's truncation bias hits numerator (D2) and denominator (D3) alike and cancels.
       // buffer `buf` was last read by GEMM2(it-2), whose completion this thread observed during tile it-1 (below)
-      uint8_t* eb = smem + CF::OFF_E + buf * CF::E_BYTES + q * CF::E_CHUNK + (lane & 3) * 4;
-      const int c16 = lane >> 2;
+      uint8_t* eb = smem + CF::OFF_E + buf * CF::E_BYTES + q * CF::E_CHUNK;
 #pragma unroll
       for (int j = 0; j < KP; ++j) {
-        const float ml = mref[j] * 1.4426950408889634f;
-        const float e = (ml == -INFINITY) ? 0.f : exp2f(fmaf(sv[j], 1.4426950408889634f, -ml));
-        *reinterpret_cast<float*>(eb + j * 128 + ((c16 ^ (j & 7)) << 4)) = e;
+        float e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(sv[j] - ml[j]));
+        *reinterpret_cast<float*>(eb + j * 128 + soff[j & 7]) = e;
       }
       // ---- every tile: observe the completion of GEMM2(it-1) (parity bookkeeping must not skip phases); then, if a
       //      running maximum moved, rescale the accumulators before GEMM2(it) adds to them
@@ -348,7 +359,7 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       tmem_ld16(tmem + lane_addr + COL_D3, v);
       tmem_wait_ld();
       if (lane < 16) {
-        part[(size_t)j * (C + 4) + C] = mref[j];
+        part[(size_t)j * (C + 4) + C] = j < P.k ? mref[j] * 0.6931471805599453f : -INFINITY;   // log2 -> natural units
         part[(size_t)j * (C + 4) + C + 1] = v[0];
         part[(size_t)j * (C + 4) + C + 2] = 0.f;
         part[(size_t)j * (C + 4) + C + 3] = 0.f;
