@@ -65,7 +65,7 @@ int make_layout(const gf_attn_desc* d, Layout* L) {
     int best = 1;
     double best_u = -1.0;
     for (int ns = 1; ns <= 16 && ns <= tiles; ++ns) {
-      const double waves = (double)l.B * ns / 148.0;
+      const double waves = (double)l.B * ns * (l.C == 512 ? 2 : 1) / 148.0;   // C = 512: two CTAs per split (channel halves)
       double u = waves / ceil(waves);
       if (waves < 1.0) u = waves;                       // under one wave: utilisation is just the fill
       if (u > best_u + 1e-9) { best_u = u; best = ns; }

@@ -53,7 +53,9 @@ struct Bars {
   uint32_t pad;
 };
 
-template <int KP, int NS>
+// NS = slabs of GEMM1 (all C channels); NS2 = slabs of GEMM2 handled by this CTA (C/32 or, for C = 512, half of them:
+// blockIdx.z selects the channel half, both CTAs recompute the cheap GEMM1 + softmax; TMEM holds NS2*32 accumulator columns)
+template <int KP, int NS, int NS2 = (NS > 8 ? NS / 2 : NS)>
 struct Cfg {
   static constexpr int C = NS * SLAB_CH;
   static constexpr int M_BYTES = KP * C * 4;                 // NS chunks of [KP rows x 128 B]
@@ -88,12 +90,14 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_by
   return d;
 }
 
-template <int KP, int NS>
+template <int KP, int NS, int NS2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmX2,
                    const __grid_constant__ CUtensorMap tmM, const Params P) {
-  using CF = Cfg<KP, NS>;
+  using CF = Cfg<KP, NS, NS2>;
   constexpr int C = CF::C;
+  constexpr int C2 = NS2 * SLAB_CH;                  // accumulator channels of this CTA
+  const int zoff = blockIdx.z * C2;                   // first channel of this CTA's GEMM2 share
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t s_base = smem_u32(smem);
@@ -112,9 +116,10 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   float* part = P.part + ((size_t)b * P.nsplit + sp) * KP * (C + 4);
 
   if (ntiles <= 0) {                          // empty split: neutral partial
-    for (int i = threadIdx.x; i < KP * (C + 4); i += NUM_THREADS) {
-      const int c = i % (C + 4);
-      part[i] = c == C ? -INFINITY : 0.f;
+    for (int i = threadIdx.x; i < KP * (C2 + 4); i += NUM_THREADS) {
+      const int j = i / (C2 + 4), c = i % (C2 + 4);
+      if (c < C2) part[(size_t)j * (C + 4) + zoff + c] = 0.f;
+      else if (blockIdx.z == 0) part[(size_t)j * (C + 4) + C + (c - C2)] = (c == C2) ? -INFINITY : 0.f;
     }
     return;
   }
@@ -151,20 +156,20 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
       for (int s = 0; s < NS; ++s) tma_load_2d(s_m + s * (KP * 128), &tmM, mb, s * SLAB_CH, b * KP);
       uint32_t ctr = 0;
-      auto load_tile = [&](int it, const CUtensorMap* map) {
+      auto load_tile = [&](int it, const CUtensorMap* map, int nslabs, int c_first) {
         const int row0 = (b * P.tiles_per_image + tile_beg + it) * TILE;
-        for (int s = 0; s < NS; ++s, ++ctr) {
+        for (int s = 0; s < nslabs; ++s, ++ctr) {
           const int stage = (int)(ctr % (uint32_t)nst);
           mbar_wait(smem_u32(&bars->slab_empty[stage]), ((ctr / (uint32_t)nst) & 1u) ^ 1u);
           const uint32_t bar = smem_u32(&bars->slab_full[stage]);
           mbar_expect_tx(bar, SLAB_BYTES);
-          tma_load_2d(s_ring + stage * SLAB_BYTES, map, bar, s * SLAB_CH, row0);
+          tma_load_2d(s_ring + stage * SLAB_BYTES, map, bar, c_first + s * SLAB_CH, row0);
         }
       };
-      load_tile(0, &tmX);
+      load_tile(0, &tmX, NS, 0);
       for (int it = 0; it < ntiles; ++it) {
-        if (it + 1 < ntiles) load_tile(it + 1, &tmX);      // GEMM1 of the next tile runs ahead of GEMM2 of this one
-        load_tile(it, &tmX2);                                 // second fetch (L2), MN-major swizzle
+        if (it + 1 < ntiles) load_tile(it + 1, &tmX, NS, 0);   // GEMM1 of the next tile runs ahead of GEMM2 of this one
+        load_tile(it, &tmX2, NS2, zoff);                        // second fetch (L2), MN-major swizzle, this CTA's channels
       }
     }
   } else if (warp == 1) {
@@ -205,7 +210,7 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         tc_fence_after();
         const uint64_t de = dE0 + (uint64_t)(buf * (CF::E_BYTES >> 4));
         const uint32_t acc0 = it ? 1u : 0u;
-        for (int s = 0; s < NS; ++s, ++ctr) {
+        for (int s = 0; s < NS2; ++s, ++ctr) {
           const int stage = (int)(ctr % (uint32_t)nst);
           mbar_wait(smem_u32(&bars->slab_full[stage]), (ctr / (uint32_t)nst) & 1u);
           tc_fence_after();
@@ -321,7 +326,7 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           const float f = lane < 16 ? resc[q * 16 + lane] : 1.f;
           float v[16];
 #pragma unroll 1
-          for (int c0 = 0; c0 < C; c0 += 16) {
+          for (int c0 = 0; c0 < C2; c0 += 16) {
             tmem_ld16(tmem + lane_addr + COL_D2 + c0, v);
             tmem_wait_ld();
 #pragma unroll
@@ -348,17 +353,17 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       const int j = q * 16 + lane;                                  // valid for lane < 16
       float v[16];
 #pragma unroll 1
-      for (int c0 = 0; c0 < C; c0 += 16) {
+      for (int c0 = 0; c0 < C2; c0 += 16) {
         tmem_ld16(tmem + lane_addr + COL_D2 + c0, v);
         tmem_wait_ld();
         if (lane < 16) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) part[(size_t)j * (C + 4) + c0 + i] = v[i] * 1.000352220f;   // X truncation bias (gf_fold.cu)
+          for (int i = 0; i < 16; ++i) part[(size_t)j * (C + 4) + zoff + c0 + i] = v[i] * 1.000352220f;   // X truncation bias (gf_fold.cu)
         }
       }
       tmem_ld16(tmem + lane_addr + COL_D3, v);
       tmem_wait_ld();
-      if (lane < 16) {
+      if (lane < 16 && blockIdx.z == 0) {
         part[(size_t)j * (C + 4) + C] = j < P.k ? mref[j] * 0.6931471805599453f : -INFINITY;   // log2 -> natural units
         part[(size_t)j * (C + 4) + C + 1] = v[0];
         part[(size_t)j * (C + 4) + C + 2] = 0.f;
@@ -384,6 +389,7 @@ static int stages_for(int smem_limit) {
 template <int KP, int NS>
 static int launch(const Layout& L, const float* X, float* ws, cudaStream_t st) {
   using CF = Cfg<KP, NS>;
+  constexpr int NS2 = NS > 8 ? NS / 2 : NS;
   const int nst = stages_for<KP, NS>(device_smem_optin());
   if (nst < 4) { set_error("tcgen05 centroid pass: shared memory too small for C=%d KP=%d", L.C, KP); return GF_ERR_UNSUPPORTED; }
   CUtensorMap tmX, tmX2, tmM;
@@ -396,9 +402,9 @@ static int launch(const Layout& L, const float* X, float* ws, cudaStream_t st) {
   P.n = L.n; P.H = L.H; P.W = L.W; P.k = L.k; P.nsplit = L.nsplit_cen; P.tiles_per_image = L.n / TILE;
   P.nstages = nst;
   const int smem_bytes = CF::FIXED_BYTES + nst * SLAB_BYTES + 1024;
-  auto kern = centroid_tc_kernel<KP, NS>;
+  auto kern = centroid_tc_kernel<KP, NS, NS2>;
   GF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  kern<<<dim3(L.nsplit_cen, L.B), NUM_THREADS, smem_bytes, st>>>(tmX, tmX2, tmM, P);
+  kern<<<dim3(L.nsplit_cen, L.B, NS / NS2), NUM_THREADS, smem_bytes, st>>>(tmX, tmX2, tmM, P);
   GF_LAUNCH_OK();
   return GF_OK;
 }
@@ -408,19 +414,19 @@ static int launch(const Layout& L, const float* X, float* ws, cudaStream_t st) {
 bool tc_centroid_supported(const Layout& L, const gf_attn_desc* d) {
   static const bool disabled = getenv("GF_DISABLE_TC") != nullptr || getenv("GF_DISABLE_TC_CENTROID") != nullptr;
   if (disabled || (d->flags & GF_FLAG_FP32_EXACT)) return false;
-  if (L.C != 64 && L.C != 128 && L.C != 256) return false;       // C columns of TMEM accumulators (+ S, denominators) <= 512
+  if (L.C != 64 && L.C != 128 && L.C != 256 && L.C != 512) return false;   // C = 512: two CTAs share the channels
   if (L.n % tcc::TILE != 0 || L.B > 65535) return false;
   const int limit = tc::device_smem_optin();
   const int ns = L.C / 32;
-  if (L.KP == 16) return (ns == 2 ? tcc::stages_for<16, 2>(limit) : ns == 4 ? tcc::stages_for<16, 4>(limit) : tcc::stages_for<16, 8>(limit)) >= 4;
-  return (ns == 2 ? tcc::stages_for<32, 2>(limit) : ns == 4 ? tcc::stages_for<32, 4>(limit) : tcc::stages_for<32, 8>(limit)) >= 4;
+  if (L.KP == 16) return (ns == 2 ? tcc::stages_for<16, 2>(limit) : ns == 4 ? tcc::stages_for<16, 4>(limit) : ns == 8 ? tcc::stages_for<16, 8>(limit) : tcc::stages_for<16, 16>(limit)) >= 4;
+  return (ns == 2 ? tcc::stages_for<32, 2>(limit) : ns == 4 ? tcc::stages_for<32, 4>(limit) : ns == 8 ? tcc::stages_for<32, 8>(limit) : tcc::stages_for<32, 16>(limit)) >= 4;
 }
 
 int centroid_pass_tc(const Layout& L, const gf_attn_desc* d, const float* X, float* ws, cudaStream_t st) {
   (void)d;
   const int ns = L.C / 32;
-  if (L.KP == 16) return ns == 2 ? tcc::launch<16, 2>(L, X, ws, st) : ns == 4 ? tcc::launch<16, 4>(L, X, ws, st) : tcc::launch<16, 8>(L, X, ws, st);
-  return ns == 2 ? tcc::launch<32, 2>(L, X, ws, st) : ns == 4 ? tcc::launch<32, 4>(L, X, ws, st) : tcc::launch<32, 8>(L, X, ws, st);
+  if (L.KP == 16) return ns == 2 ? tcc::launch<16, 2>(L, X, ws, st) : ns == 4 ? tcc::launch<16, 4>(L, X, ws, st) : ns == 8 ? tcc::launch<16, 8>(L, X, ws, st) : tcc::launch<16, 16>(L, X, ws, st);
+  return ns == 2 ? tcc::launch<32, 2>(L, X, ws, st) : ns == 4 ? tcc::launch<32, 4>(L, X, ws, st) : ns == 8 ? tcc::launch<32, 8>(L, X, ws, st) : tcc::launch<32, 16>(L, X, ws, st);
 }
 
 }  // namespace gf

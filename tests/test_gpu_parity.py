@@ -142,7 +142,7 @@ def test_persistent_schedule_many_tiles(gf, cuda_dev, C, H, W, k, B, integration
 
 
 @pytest.mark.parametrize("exact", [True, False], ids=["fp32", "default"])
-@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[3], SHAPES[5], SHAPES[6], SHAPES[8], SHAPES[10]],
+@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[1], SHAPES[2], SHAPES[3], SHAPES[5], SHAPES[6], SHAPES[8], SHAPES[10]],
                          ids=lambda s: "C%d-%dx%d-k%d-%s-%s" % (s[0], s[1], s[2], s[3], s[6], s[7]))
 def test_duplex_layer_vs_oracle(gf, cuda_dev, shape, exact):
     C, H, W, k, D, p, integration, norm = shape

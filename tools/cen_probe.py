@@ -5,7 +5,7 @@ import torch
 import gansformer_b200 as gf
 from oracle import bipartite as ob
 dev = torch.device("cuda:0")
-shapes = [(64, 8, 16, 4, 1), (128, 16, 16, 16, 2), (128, 32, 32, 32, 3), (256, 32, 16, 16, 2), (64, 64, 64, 8, 5), (256, 64, 64, 32, 4), (128, 128, 128, 16, 3)]
+shapes = [(64, 8, 16, 4, 1), (128, 16, 16, 16, 2), (128, 32, 32, 32, 3), (256, 32, 16, 16, 2), (64, 64, 64, 8, 5), (256, 64, 64, 32, 4), (128, 128, 128, 16, 3), (512, 16, 16, 16, 2), (512, 32, 32, 32, 3), (512, 64, 64, 8, 9)]
 for (C, H, W, k, B) in shapes:
     D = p = 32
     g = torch.Generator().manual_seed(C + k)
