@@ -18,6 +18,7 @@ int make_layout(const gf_attn_desc* d, Layout* L) {
   }
   if (d->C % 32 != 0 || d->C > 1024) { set_error("C=%d unsupported: need C %% 32 == 0 and C <= 1024", d->C); return GF_ERR_UNSUPPORTED; }
   if (d->k > 32) { set_error("k=%d unsupported: at most 32 latents", d->k); return GF_ERR_UNSUPPORTED; }
+  if (d->D > 256) { set_error("D=%d unsupported: latent size at most 256", d->D); return GF_ERR_UNSUPPORTED; }
   if (d->heads != 1) { set_error("num_heads=%d unsupported: this build implements 1 head", d->heads); return GF_ERR_UNSUPPORTED; }
   if (d->norm < GF_NORM_NONE || d->norm > GF_NORM_BATCH) { set_error("bad norm %d", d->norm); return GF_ERR_INVALID; }
   if (d->integration < GF_INT_MUL || d->integration > GF_INT_BOTH) { set_error("bad integration %d", d->integration); return GF_ERR_INVALID; }
@@ -146,9 +147,81 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const fl
     }
 }
 
+// Register-blocked NN SGEMM for the per-image [B*k, C] x [C, C(+p+4)] products of the duplex path: 64x64 block tile,
+// BK = 16, 256 threads x (4x4) outputs, float4 shared-memory reads.  Requires lda, ldb % 4 == 0 and 16-byte aligned bases.
+__global__ void __launch_bounds__(256) gemm64_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                     const float* __restrict__ Bm, int ldb, float* __restrict__ Cm, int ldc,
+                                                     float alpha, const float* __restrict__ E, int lde, int emod,
+                                                     const float* __restrict__ v) {
+  __shared__ __align__(16) float As[16][64 + 4];     // [k][m] (transposed on load)
+  __shared__ __align__(16) float Bs[16][64 + 4];     // [k][n]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int ar = tid >> 2, ac = (tid & 3) * 4;       // A tile 64 x 16: row ar, cols ac..ac+3
+  const int br = tid >> 4, bc = (tid & 15) * 4;      // B tile 16 x 64: row br, cols bc..bc+3
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m0 + ar < M) {
+      if (k0 + ac + 3 < K) a4 = *reinterpret_cast<const float4*>(A + (size_t)(m0 + ar) * lda + k0 + ac);
+      else {
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int i = 0; i < 4; ++i) if (k0 + ac + i < K) t[i] = A[(size_t)(m0 + ar) * lda + k0 + ac + i];
+        a4 = make_float4(t[0], t[1], t[2], t[3]);
+      }
+    }
+    if (k0 + br < K) {
+      if (n0 + bc + 3 < N) b4 = *reinterpret_cast<const float4*>(Bm + (size_t)(k0 + br) * ldb + n0 + bc);
+      else {
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int i = 0; i < 4; ++i) if (n0 + bc + i < N) t[i] = Bm[(size_t)(k0 + br) * ldb + n0 + bc + i];
+        b4 = make_float4(t[0], t[1], t[2], t[3]);
+      }
+    }
+    __syncthreads();
+    As[ac + 0][ar] = a4.x; As[ac + 1][ar] = a4.y; As[ac + 2][ar] = a4.z; As[ac + 3][ar] = a4.w;
+    *reinterpret_cast<float4*>(&Bs[br][bc]) = b4;
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int nn = n0 + tx * 4 + j;
+      if (nn >= N) continue;
+      float r = alpha * acc[i][j];
+      if (E) r += E[(size_t)(m % emod) * lde + nn];
+      if (v) r += v[nn];
+      Cm[(size_t)m * ldc + nn] = r;
+    }
+  }
+}
+
 int gemm(cudaStream_t st, int M, int N, int K, const float* A, int lda, bool ta, const float* B, int ldb, bool tb,
          float* Cm, int ldc, float alpha, const float* E, int lde, int emod, const float* v) {
   if (M <= 0 || N <= 0) return GF_OK;
+  if (!ta && !tb && M >= 256 && N >= 64 && K >= 64 && (lda & 3) == 0 && (ldb & 3) == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0) {
+    if (emod < 1) emod = 1;
+    gemm64_kernel<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, st>>>(M, N, K, A, lda, B, ldb, Cm, ldc, alpha, E, lde, emod, v);
+    GF_LAUNCH_OK();
+    return GF_OK;
+  }
   dim3 grid((N + 31) / 32, (M + 31) / 32);
   if (emod < 1) emod = 1;
   if (!ta && !tb) gemm_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, Cm, ldc, alpha, E, lde, emod, v);
@@ -295,25 +368,42 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
     }
     return;
   }
-  const int nK = KP * C, nV = Vt ? Cout * KP : 0;
-  const int stride = (gridDim.x - npos) * blockDim.x;
-  for (int i = (blockIdx.x - npos) * blockDim.x + threadIdx.x; i < nK + nV; i += stride) {
-    if (i < nK) {
-      const int j = i / C, c = i % C;
-      float v = j < k ? kp[(size_t)j * LDK + c] : 0.f;
-      if (in_scale) v *= in_scale[(size_t)b * in_ld + c];      // x_in = x * in_scale: (x*d).K' == x.(K'*d)
-      if (tf32) v = round_tf32(v * GF_TF32_TRUNC_COMP);
-      Kp[(size_t)b * nK + i] = v;
-    } else {
-      const int e = i - nK, c = e / KP, j = e % KP;
-      float acc = 0.f;
-      if (j < k) {
-        const float* yj = Y + ((size_t)b * k + j) * D;
-        for (int dd = 0; dd < D; ++dd) acc = fmaf(yj[dd], AV[(size_t)dd * Cout + c], acc);
-        acc += CV[c];
-      }
-      Vt[(size_t)b * nV + e] = tf32 ? round_tf32(acc) : acc;
+  const int nK = KP * C;
+  const int nvblk = Vt ? (Cout + 255) / 256 : 0;                 // V^T role: one thread per channel
+  const int role = blockIdx.x - npos;
+  if (role < nvblk) {
+    // V^T[b, c, :] = (Y[b] . AV[:, c] + CV[c]) for the k latents (zero for the padded ones); AV reads coalesced over c
+    extern __shared__ float ysm[];                                // Y[b]: k x D
+    for (int i = threadIdx.x; i < k * D; i += blockDim.x) ysm[i] = Y[(size_t)b * k * D + i];
+    __syncthreads();
+    const int c = role * 256 + threadIdx.x;
+    if (c >= Cout) return;
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    for (int dd = 0; dd < D; ++dd) {
+      const float a = AV[(size_t)dd * Cout + c];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < k) acc[j] = fmaf(ysm[j * D + dd], a, acc[j]);
     }
+    const float cv = CV[c];
+    float* out = Vt + ((size_t)b * Cout + c) * KP;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < KP) {
+        float r = j < k ? acc[j] + cv : 0.f;
+        out[j] = tf32 ? round_tf32(r) : r;
+      }
+    }
+    return;
+  }
+  const int stride = (gridDim.x - npos - nvblk) * blockDim.x;
+  for (int i = (role - nvblk) * blockDim.x + threadIdx.x; i < nK; i += stride) {
+    const int j = i / C, c = i % C;
+    float v = j < k ? kp[(size_t)j * LDK + c] : 0.f;
+    if (in_scale) v *= in_scale[(size_t)b * in_ld + c];      // x_in = x * in_scale: (x*d).K' == x.(K'*d)
+    if (tf32) v = round_tf32(v * GF_TF32_TRUNC_COMP);
+    Kp[(size_t)b * nK + i] = v;
   }
 }
 
@@ -326,10 +416,9 @@ int prologue(const Layout& L, const gf_attn_desc* d, const float* Y, const float
   if ((rc = gemm(st, L.B * L.k, L.LDK, kdim, key_source, kdim, false, f + L.f_AK, L.LDK, false, ws + L.w_KPALL, L.LDK, 1.f,
                  f + L.f_CK, L.LDK, L.k)))
     return rc;
-  const int nel = L.KP * L.C + L.Cout * L.KP;
   const int npos = ((L.H + L.W) * L.KP + 1023) / 1024;
-  int nblk = npos + (nel + 256 * 4 - 1) / (256 * 4);
-  finalize_kernel<<<dim3(nblk, L.B), 256, 0, st>>>(ws + L.w_KPALL, Y, f + L.f_AV, f + L.f_CV, f + L.f_ROW, f + L.f_COL,
+  const int nblk = npos + (L.Cout + 255) / 256 + (L.KP * L.C + 256 * 4 - 1) / (256 * 4);
+  finalize_kernel<<<dim3(nblk, L.B), 256, (size_t)L.k * L.D * sizeof(float), st>>>(ws + L.w_KPALL, Y, f + L.f_AV, f + L.f_CV, f + L.f_ROW, f + L.f_COL,
                                                    ws + L.w_Kp, ws + L.w_Vt, ws + L.w_Rt, ws + L.w_Ct,
                                                    L.H, L.W, L.C, L.k, L.D, L.p, L.KP, L.Cout, L.LDK, tf32, npos, in_scale, in_scale_ld);
   GF_LAUNCH_OK();
@@ -343,9 +432,8 @@ int duplex_tables(const Layout& L, const gf_attn_desc* d, const float* Y, const 
   if ((rc = gemm(st, L.B * L.k, L.LDK, L.D, Y, L.D, false, f + L.f_AM, L.LDK, false, ws + L.w_MALL, L.LDK, 1.f,
                  f + L.f_CM, L.LDK, L.k)))
     return rc;
-  const int nel = L.KP * L.C;
   const int npos = ((L.H + L.W) * L.KP + 1023) / 1024;
-  int nblk = npos + (nel + 256 * 4 - 1) / (256 * 4);
+  const int nblk = npos + (L.KP * L.C + 256 * 4 - 1) / (256 * 4);
   finalize_kernel<<<dim3(nblk, L.B), 256, 0, st>>>(ws + L.w_MALL, Y, nullptr, nullptr, f + L.f_ROW, f + L.f_COL,
                                                    ws + L.w_M, nullptr, ws + L.w_Rt2, ws + L.w_Ct2,
                                                    L.H, L.W, L.C, L.k, L.D, L.p, L.KP, L.Cout, L.LDK, tf32, npos, nullptr, 0);
