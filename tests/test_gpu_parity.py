@@ -158,7 +158,8 @@ def test_duplex_layer_vs_oracle(gf, cuda_dev, shape, exact):
     if exact:
         assert cpath == "simt_fp32"
     check_close(cen, rcen, cpath, "duplex/centroids")
-    check_close(out, ref.permute(0, 2, 3, 1), path, "duplex/out")
+    # two chained [B*k, C] x [C, C] fp32 products sit between pass A and the keys: fp32 mode gets 2x the layer tolerance
+    check_close(out, ref.permute(0, 2, 3, 1), path, "duplex/out", tol_scale=2.0 if path == "simt_fp32" else 1.0)
     # iterative=True: centroids fed back in skip pass A and reproduce the same output
     out2, _, cen2, _ = run_layer(gf, cuda_dev, x, y, w, integration=integration, norm=nrm, duplex=True, use_pos=True, exact=exact,
                                  centroids=cen.clone())
