@@ -54,12 +54,17 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    try:
-        build_extension()
-    except Exception as e:  # nvcc missing is fine as long as a prebuilt .so is present
-        if not LIB_PATH.exists():
-            raise RuntimeError(f"libgf_attn.so is missing and could not be built: {e}") from e
-    lib = ctypes.CDLL(str(LIB_PATH))
+    import os
+    alt = os.environ.get("GF_ATTN_LIB")          # A/B benchmarking of two builds of the same sources (tools/ab_build.sh)
+    if alt:
+        lib = ctypes.CDLL(alt)
+    else:
+        try:
+            build_extension()
+        except Exception as e:  # nvcc missing is fine as long as a prebuilt .so is present
+            if not LIB_PATH.exists():
+                raise RuntimeError(f"libgf_attn.so is missing and could not be built: {e}") from e
+        lib = ctypes.CDLL(str(LIB_PATH))
     lib.gf_attn_abi_version.restype = c_int
     lib.gf_last_error.restype = c_char_p
     lib.gf_attn_last_path.restype = c_int

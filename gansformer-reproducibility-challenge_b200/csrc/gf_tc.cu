@@ -229,33 +229,29 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
   } else if (warp >= 10) {
     // =============================== row warps: statistics + softmax ===============================
-    // One warp per scheduler, nothing to hide latency with: the next tile's positional logits are prefetched, exp is one
-    // ex2.approx on log2-scaled logits, the TF32 rounding of P is two integer ops.
     const int q = warp & 3;                        // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;                 // token row inside the tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int sw = row & 7;
     const uint32_t row_off = (uint32_t)row * 128u;
-    constexpr float LOG2E = 1.4426950408889634f;
-    auto load_pos = [&](long long tile, float* dst) {
-      const int bb = (int)(tile / P.tiles_per_image);
-      const int tok = (int)(tile % P.tiles_per_image) * TILE + row;
-      const int h = tok / P.W, w = tok - h * P.W;
-      const float4* rt = reinterpret_cast<const float4*>(P.Rt + ((size_t)bb * P.H + h) * KP);
-      const float4* ct = reinterpret_cast<const float4*>(P.Ct + ((size_t)bb * P.W + w) * KP);
-#pragma unroll
-      for (int j4 = 0; j4 < KP / 4; ++j4) {
-        const float4 r = __ldg(rt + j4), c = __ldg(ct + j4);
-        dst[j4 * 4 + 0] = r.x + c.x; dst[j4 * 4 + 1] = r.y + c.y; dst[j4 * 4 + 2] = r.z + c.z; dst[j4 * 4 + 3] = r.w + c.w;
-      }
-    };
-    float pos[KP];
-    if (tile_beg < tile_end) load_pos(tile_beg, pos);
     uint32_t it = 0;
     for (long long tile = tile_beg; tile < tile_end; ++tile, ++it) {
       const int b = (int)(tile / P.tiles_per_image);
       const int buf = (int)(it & 1);
       const uint32_t bphase = (it >> 1) & 1u;
+      const long long tok = (tile % P.tiles_per_image) * TILE + row;      // token index inside the image
+      // positional logits of this token (issued first: their L2 latency hides behind the statistics)
+      float sv[KP];
+      {
+        const int h = (int)(tok / P.W), w = (int)(tok % P.W);
+        const float4* rt = reinterpret_cast<const float4*>(P.Rt + ((size_t)b * P.H + h) * KP);
+        const float4* ct = reinterpret_cast<const float4*>(P.Ct + ((size_t)b * P.W + w) * KP);
+#pragma unroll
+        for (int j4 = 0; j4 < KP / 4; ++j4) {
+          const float4 r = __ldg(rt + j4), c = __ldg(ct + j4);
+          sv[j4 * 4 + 0] = r.x + c.x; sv[j4 * 4 + 1] = r.y + c.y; sv[j4 * 4 + 2] = r.z + c.z; sv[j4 * 4 + 3] = r.w + c.w;
+        }
+      }
       // ---- LayerNorm statistics of the whole row (shifted sums)
       float mean = 0.f, rstd = 1.f;
       if (P.norm_layer || TWO_PASS) {
@@ -298,32 +294,31 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       // ---- softmax over the latents: S (TMEM) -> P (TMEM)
       mbar_wait(smem_u32(&bars->s_full[buf]), bphase);
       tc_fence_after();
-      float sv[KP];
-      tmem_ld16(tmem + lane_addr + COL_S + buf * 32, sv);
-      if constexpr (KP == 32) tmem_ld16(tmem + lane_addr + COL_S + buf * 32 + 16, sv + 16);
+      float acc[KP];
+      tmem_ld16(tmem + lane_addr + COL_S + buf * 32, acc);
+      if constexpr (KP == 32) tmem_ld16(tmem + lane_addr + COL_S + buf * 32 + 16, acc + 16);
       tmem_wait_ld();
       float mx = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < KP; ++j) { sv[j] = (sv[j] + pos[j]) * LOG2E; mx = fmaxf(mx, sv[j]); }   // padded latents: -inf
-      if (tile + 1 < tile_end) load_pos(tile + 1, pos);             // prefetch: consumed one tile later
+      for (int j = 0; j < KP; ++j) { sv[j] += acc[j]; mx = fmaxf(mx, sv[j]); }
       float den = 0.f;
 #pragma unroll
-      for (int j = 0; j < KP; ++j) {
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(sv[j]) : "f"(sv[j] - mx));
-        den += sv[j];
-      }
-      const float inv = __fdividef(1.f, den);
+      for (int j = 0; j < KP; ++j) { sv[j] = exp2f((sv[j] - mx) * 1.4426950408889634f); den += sv[j]; }
+      const float inv = 1.f / den;
 #pragma unroll
       for (int j = 0; j < KP; ++j) sv[j] *= inv;
       if (P.att) {
-        const long long tok = (tile % P.tiles_per_image) * TILE + row;
         float* a = P.att + ((size_t)b * P.n + tok) * P.k;
 #pragma unroll
         for (int j = 0; j < KP; ++j) if (j < P.k) a[j] = sv[j];
       }
-      // round P to the nearest TF32 (half-up; ties are 2^-13 rare) so the tensor core's operand truncation is exact
+      // round P to the nearest TF32 so the tensor core's operand truncation is exact (see gf_fold.cu: round_tf32)
 #pragma unroll
-      for (int j = 0; j < KP; ++j) sv[j] = __uint_as_float((__float_as_uint(sv[j]) + 0x1000u) & 0xFFFFE000u);
+      for (int j = 0; j < KP; ++j) {
+        uint32_t bits = __float_as_uint(sv[j]);
+        bits = (bits + 0xFFFu + ((bits >> 13) & 1u)) & 0xFFFFE000u;
+        sv[j] = __uint_as_float(bits);
+      }
       mbar_wait(smem_u32(&bars->p_free[buf]), bphase ^ 1u);       // GEMM2 of the tile two iterations back is done
       tc_fence_after();
       tmem_st16(tmem + lane_addr + COL_P + buf * 32, sv);
