@@ -7,10 +7,8 @@
 //
 // One persistent CTA per SM, 14 warps:
 //   warp 0       TMA producer: X slabs (128 tokens x 32 channels, 16 KB, SWIZZLE_128B) into a ring; K'/V^T per image
-//   warp 1       GEMM1 issuer: S[128,KP]   = X[128,C] . K'^T            (A,B from smem, D in TMEM), runs a tile ahead
-//   warp 14      GEMM2 issuer: G[128,32]   = P[128,KP] . V^T[32 ch,KP]^T per slab (A = P from TMEM, B from smem)
-//                (one thread issues ~10 instructions per MMA at ~8 cycles each: two issuers keep GEMM1(i+1) off the
-//                softmax(i) -> GEMM2(i) -> epilogue(i) critical path)
+//   warp 1       MMA issuer:   GEMM1  S[128,KP]   = X[128,C] . K'^T            (A,B from smem, D in TMEM)
+//                              GEMM2  G[128,32]   = P[128,KP] . V^T[32 ch,KP]^T per slab (A = P from TMEM, B from smem)
 //   warps 10-13  row warps (one per TMEM lane quadrant, thread = token row), run up to a tile ahead: LayerNorm statistics
 //                of the whole row from the swizzled slabs, softmax (S from TMEM -> P back to TMEM), attention-map store
 //   warps 2-9    two epilogue groups of 4 warps; group g owns the slabs with (slab & 1) == g: gain(/bias) from TMEM,
@@ -31,7 +29,7 @@ constexpr int SLAB_CH = 32;               // channels per slab = one 128-byte sw
 constexpr int SLAB_BYTES = TILE * SLAB_CH * 4;
 constexpr int MAX_STAGES = 13;
 constexpr int NACC = 4;                   // accumulator stages of GEMM2 in TMEM
-constexpr int NUM_THREADS = 480;        // warp 0 producer, 1 GEMM1 issuer, 2-9 epilogue (two groups), 10-13 row warps, 14 GEMM2 issuer
+constexpr int NUM_THREADS = 448;        // warp 0 producer, 1 MMA, 2-9 epilogue (two groups), 10-13 row warps
 constexpr int TMEM_COLS = 512;
 // TMEM column map
 constexpr int COL_S = 0;                  // S[2]  : 2 x 32
@@ -162,24 +160,30 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // =============================== GEMM1 issuer ===============================
+    // =============================== MMA issuer ===============================
     if (lane == 0) {
       constexpr uint32_t IDESC1 = umma_idesc_tf32(TILE, KP);
+      constexpr uint32_t IDESC2 = umma_idesc_tf32(TILE, 32);
+      constexpr uint32_t V_LAYOUT = KP == 32 ? LAYOUT_SW128 : LAYOUT_SW64;
+      constexpr uint32_t V_SBO = 8 * CF::V_ROW_BYTES;
+      uint32_t actr = 0;
       int img_changes = 0, prev_b = -1;
       uint32_t it = 0;
+      // base descriptors, advanced with one 64-bit add per MMA (start-address field = 16-byte units)
       const uint64_t dRing = umma_desc(s_ring, 1024, LAYOUT_SW128);
       const uint64_t dKp = umma_desc(s_kp, 1024, LAYOUT_SW128);
+      const uint64_t dV = umma_desc(s_v, V_SBO, V_LAYOUT);
       for (long long tile = tile_beg; tile < tile_end; ++tile, ++it) {
         const int b = (int)(tile / P.tiles_per_image);
         const int buf = (int)(it & 1);
+        const uint32_t bphase = (it >> 1) & 1u;
         if (b != prev_b) {
           mbar_wait(smem_u32(&bars->kv_full), (uint32_t)(img_changes & 1));
           tc_fence_after();
           prev_b = b;
           ++img_changes;
         }
-        // S[buf] was last read by the softmax of tile it-2, which arrives on p_full[buf] after reading it
-        if (it >= 2) { mbar_wait(smem_u32(&bars->p_full[buf]), ((it - 2) >> 1) & 1u); tc_fence_after(); }
+        // ---- GEMM1: S[buf] = X . K'^T over all slabs (pass 1 of a two-pass tile)
         const uint32_t d_s = tmem + COL_S + buf * 32;
         for (int s = 0; s < NS; ++s) {
           const uint32_t ctr = it * SPT + s;
@@ -193,42 +197,6 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           if (TWO_PASS) umma_commit(smem_u32(&bars->slab_empty[stage]));    // slab may be recycled once these MMAs are done
         }
         umma_commit(smem_u32(&bars->s_full[buf]));
-        if (TWO_PASS) {   // walk the pass-2 fills too: a parity wait must never be two phases behind its barrier
-#pragma unroll 1
-          for (int s = 0; s < NS; ++s) {
-            const uint32_t c2 = it * SPT + NS + s;
-            mbar_wait(smem_u32(&bars->slab_full[(int)(c2 % (uint32_t)nst)]), (c2 / (uint32_t)nst) & 1u);
-          }
-        }
-      }
-    }
-  } else if (warp == 14) {
-    // =============================== GEMM2 issuer ===============================
-    if (lane == 0) {
-      constexpr uint32_t IDESC2 = umma_idesc_tf32(TILE, 32);
-      constexpr uint32_t V_LAYOUT = KP == 32 ? LAYOUT_SW128 : LAYOUT_SW64;
-      constexpr uint32_t V_SBO = 8 * CF::V_ROW_BYTES;
-      uint32_t actr = 0;
-      int img_changes = 0, prev_b = -1;
-      uint32_t it = 0;
-      const uint64_t dV = umma_desc(s_v, V_SBO, V_LAYOUT);
-      for (long long tile = tile_beg; tile < tile_end; ++tile, ++it) {
-        const int b = (int)(tile / P.tiles_per_image);
-        const int buf = (int)(it & 1);
-        const uint32_t bphase = (it >> 1) & 1u;
-        if (b != prev_b) {
-          mbar_wait(smem_u32(&bars->kv_full), (uint32_t)(img_changes & 1));
-          tc_fence_after();
-          prev_b = b;
-          ++img_changes;
-        }
-        if (TWO_PASS) {   // observe the pass-1 fills as well (parity bookkeeping), they are long complete when P is ready
-#pragma unroll 1
-          for (int s = 0; s < NS; ++s) {
-            const uint32_t c1 = it * SPT + s;
-            mbar_wait(smem_u32(&bars->slab_full[(int)(c1 % (uint32_t)nst)]), (c1 / (uint32_t)nst) & 1u);
-          }
-        }
         // ---- GEMM2: per slab, ACC = P[buf] . V^T (gain | bias)
         mbar_wait(smem_u32(&bars->p_full[buf]), bphase);
         tc_fence_after();
@@ -236,7 +204,8 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         for (int s = 0; s < NS; ++s, ++actr) {
           const int a = (int)(actr % NACC);
           if (TWO_PASS) {
-            // Waiting the pass-2 fill here also makes acc_full(s) imply "slab s landed" for the epilogue.
+            // Parity waits are only valid if a waiter never falls two phases behind a barrier: every consumer walks the
+            // fills of the ring in slot order.  Waiting the pass-2 fill here also makes acc_full(s) imply "slab s landed".
             const uint32_t c2 = it * SPT + NS + s;
             mbar_wait(smem_u32(&bars->slab_full[(int)(c2 % (uint32_t)nst)]), (c2 / (uint32_t)nst) & 1u);
           }
@@ -258,7 +227,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         if (!last && (int)((tile + 1) / P.tiles_per_image) != b) umma_commit(smem_u32(&bars->kv_free));
       }
     }
-  } else if (warp >= 10 && warp < 14) {
+  } else if (warp >= 10) {
     // =============================== row warps: statistics + softmax ===============================
     const int q = warp & 3;                        // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;                 // token row inside the tile
