@@ -210,27 +210,21 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         tc_fence_after();
         const uint64_t de = dE0 + (uint64_t)(buf * (CF::E_BYTES >> 4));
         const uint32_t acc0 = it ? 1u : 0u;
-        // Dependent MMAs into the same TMEM tile serialise at ~100 cycles each, so the k-steps of the NS2 slab accumulators
-        // and of the denominator tile are interleaved: consecutive instructions always target different accumulators.
-        uint64_t dx[NS2];
-        int stg[NS2];
-#pragma unroll
         for (int s = 0; s < NS2; ++s, ++ctr) {
-          stg[s] = (int)(ctr % (uint32_t)nst);
-          mbar_wait(smem_u32(&bars->slab_full[stg[s]]), (ctr / (uint32_t)nst) & 1u);
-          dx[s] = dRingMN + (uint64_t)(stg[s] * (SLAB_BYTES >> 4));
-        }
-        tc_fence_after();
+          const int stage = (int)(ctr % (uint32_t)nst);
+          mbar_wait(smem_u32(&bars->slab_full[stage]), (ctr / (uint32_t)nst) & 1u);
+          tc_fence_after();
+          const uint64_t dx = dRingMN + (uint64_t)(stage * (SLAB_BYTES >> 4));
+          const uint32_t d2 = tmem + COL_D2 + s * 32;
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {                           // 8 tokens (two 4-row swizzle atoms) per MMA
-          const uint64_t dek = de + (uint64_t)(((kk >> 2) * CF::E_CHUNK + (kk & 3) * 32) >> 4);
-#pragma unroll
-          for (int s = 0; s < NS2; ++s)
-            umma_ss(tmem + COL_D2 + s * 32, dek, dx[s] + (uint64_t)(kk * 64), IDESC2, kk ? 1u : acc0);
-          umma_ss(tmem + COL_D3, dek, dOnes, IDESC3, kk ? 1u : acc0);
+          for (int kk = 0; kk < 16; ++kk)                           // 8 tokens (two 4-row swizzle atoms) per MMA
+            umma_ss(d2, de + (uint64_t)(((kk >> 2) * CF::E_CHUNK + (kk & 3) * 32) >> 4), dx + (uint64_t)(kk * 64), IDESC2,
+                    kk ? 1u : acc0);
+          umma_commit(smem_u32(&bars->slab_empty[stage]));          // slab recycled once everything issued so far is done
         }
 #pragma unroll
-        for (int s = 0; s < NS2; ++s) umma_commit(smem_u32(&bars->slab_empty[stg[s]]));   // all slabs free once the batch is done
+        for (int kk = 0; kk < 16; ++kk)
+          umma_ss(tmem + COL_D3, de + (uint64_t)(((kk >> 2) * CF::E_CHUNK + (kk & 3) * 32) >> 4), dOnes, IDESC3, kk ? 1u : acc0);
         umma_commit(smem_u32(&bars->e_free[buf]));
       }
       umma_commit(smem_u32(&bars->done));
@@ -397,7 +391,7 @@ static int launch(const Layout& L, const float* X, float* ws, cudaStream_t st) {
   using CF = Cfg<KP, NS>;
   constexpr int NS2 = NS > 8 ? NS / 2 : NS;
   const int nst = stages_for<KP, NS>(device_smem_optin());
-  if (nst < NS2 + 1) { set_error("tcgen05 centroid pass: shared memory too small for C=%d KP=%d", L.C, KP); return GF_ERR_UNSUPPORTED; }
+  if (nst < 4) { set_error("tcgen05 centroid pass: shared memory too small for C=%d KP=%d", L.C, KP); return GF_ERR_UNSUPPORTED; }
   CUtensorMap tmX, tmX2, tmM;
   int rc;
   if ((rc = make_map(&tmX, X, (uint64_t)L.B * L.n, L.C, TILE, SLAB_CH, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
@@ -424,9 +418,8 @@ bool tc_centroid_supported(const Layout& L, const gf_attn_desc* d) {
   if (L.n % tcc::TILE != 0 || L.B > 65535) return false;
   const int limit = tc::device_smem_optin();
   const int ns = L.C / 32;
-  const int need = (ns > 8 ? ns / 2 : ns) + 1;                    // all pass-2 slabs of a tile resident + one in flight
-  if (L.KP == 16) return (ns == 2 ? tcc::stages_for<16, 2>(limit) : ns == 4 ? tcc::stages_for<16, 4>(limit) : ns == 8 ? tcc::stages_for<16, 8>(limit) : tcc::stages_for<16, 16>(limit)) >= need;
-  return (ns == 2 ? tcc::stages_for<32, 2>(limit) : ns == 4 ? tcc::stages_for<32, 4>(limit) : ns == 8 ? tcc::stages_for<32, 8>(limit) : tcc::stages_for<32, 16>(limit)) >= need;
+  if (L.KP == 16) return (ns == 2 ? tcc::stages_for<16, 2>(limit) : ns == 4 ? tcc::stages_for<16, 4>(limit) : ns == 8 ? tcc::stages_for<16, 8>(limit) : tcc::stages_for<16, 16>(limit)) >= 4;
+  return (ns == 2 ? tcc::stages_for<32, 2>(limit) : ns == 4 ? tcc::stages_for<32, 4>(limit) : ns == 8 ? tcc::stages_for<32, 8>(limit) : tcc::stages_for<32, 16>(limit)) >= 4;
 }
 
 int centroid_pass_tc(const Layout& L, const gf_attn_desc* d, const float* X, float* ws, cudaStream_t st) {
