@@ -12,10 +12,13 @@
 //              SWIZZLE_128B_ATOM_32B for GEMM2 (X is the MN-major B operand: contraction over tokens; for 32-bit MN-major
 //              operands that swizzle -- UMMA layout SWIZZLE_128B_BASE32B -- is the only one the tensor core accepts).
 //              The second fetch hits L2; slot order in the ring: P1(0), [P1(i+1), P2(i)] for i = 0, 1, ...
-//   warp 1     MMA issuer (the only slab consumer, same order):
-//                            GEMM1  S[128 tok, KP]   = X . M^T                      (M=128, as in stage T)
-//                            GEMM2  D2[KP->64, 32ch] += E^T[64, 128 tok] . X_slab   (M=64; A = E^T from smem, K-major)
-//                            GEMM3  D3[64, 8]        += E^T . 1                      (softmax denominators)
+//   MMA issuers: one thread retires ~10 scalar instructions (~90 cycles) per tcgen05.mma whatever its shape
+//              (tools/probes/mma_probe.cu), and a tile needs 4*C/32 + 16*C/32 + 16 of them, so the issue is spread over warps:
+//   warp 1     GEMM1  S[128 tok, KP]   = X . M^T                      (M=128, as in stage T), runs one tile ahead
+//   warps 6-9  GEMM2  D2[KP->64, 32ch] += E^T[64, 128 tok] . X_slab   (M=64; A = E^T from smem, K-major); slab s -> warp 6 + s%4
+//   warp 10    GEMM3  D3[64, 8]        += E^T . 1                      (softmax denominators)
+//              Every issuer walks ALL ring fills in slot order (waiting on the ones that are not its own): a parity wait
+//              must never fall two phases behind its barrier.
 //   warps 2-5  row warps (thread = token): positional logits, S from TMEM, per-latent tile maximum (warp shuffles +
 //              shared memory), E = exp(S - m) rounded to TF32 and written TRANSPOSED into shared memory, lazy rescale of
 //              the TMEM accumulators when a running maximum moves by more than TAU, final flush of the partials.
@@ -33,7 +36,7 @@ constexpr int TILE = 128;
 constexpr int SLAB_CH = 32;
 constexpr int SLAB_BYTES = TILE * SLAB_CH * 4;
 constexpr int MAX_STAGES = 12;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 352;     // warp 0 producer, 1 GEMM1, 2-5 row warps, 6-9 GEMM2 issuers, 10 GEMM3 (denominators)
 constexpr int TMEM_COLS = 512;
 constexpr int COL_S = 0;          // S[2]: 2 x 32 columns
 constexpr int COL_D3 = 64;        // softmax denominators (8 columns used)
@@ -97,6 +100,7 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   using CF = Cfg<KP, NS, NS2>;
   constexpr int C = CF::C;
   constexpr int C2 = NS2 * SLAB_CH;                  // accumulator channels of this CTA
+  constexpr int NG2 = NS2 < 4 ? NS2 : 4;             // GEMM2 issuer warps
   const int zoff = blockIdx.z * C2;                   // first channel of this CTA's GEMM2 share
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -130,11 +134,11 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmX); prefetch_tmap(&tmX2); prefetch_tmap(&tmM);
     for (int i = 0; i < nst; ++i) { mbar_init(smem_u32(&bars->slab_full[i]), 1); mbar_init(smem_u32(&bars->slab_empty[i]), 1); }
-    mbar_init(smem_u32(&bars->m_full), 1); mbar_init(smem_u32(&bars->done), 1);
+    mbar_init(smem_u32(&bars->m_full), 1); mbar_init(smem_u32(&bars->done), NG2 + 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars->s_full[i]), 1);
       mbar_init(smem_u32(&bars->e_full[i]), 4);
-      mbar_init(smem_u32(&bars->e_free[i]), 1);
+      mbar_init(smem_u32(&bars->e_free[i]), NG2 + 1);
     }
     fence_barrier_init();
   }
@@ -172,62 +176,76 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         load_tile(it, &tmX2, NS2, zoff);                        // second fetch (L2), MN-major swizzle, this CTA's channels
       }
     }
-  } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
+  } else if (warp == 1 || warp >= 6) {
+    // =============================== MMA issuers ===============================
+    // ring slot order: P1(0) | P1(1) P2(0) | P1(2) P2(1) | ... ; slots before block `it`: NS + it*(NS+NS2)
+    const int role = warp == 1 ? 0 : (warp == 10 ? 2 : 1);         // 0: GEMM1, 1: GEMM2 share (warp - 6), 2: GEMM3
+    const int g2r = warp - 6;
+    if (lane == 0 && !(role == 1 && g2r >= NG2)) {
       constexpr uint32_t IDESC1 = idesc_tf32(TILE, KP, 0);
       constexpr uint32_t IDESC2 = idesc_tf32(64, 32, 1);
       constexpr uint32_t IDESC3 = idesc_tf32(64, 8, 0);
       mbar_wait(smem_u32(&bars->m_full), 0);
       tc_fence_after();
-      // Descriptors are built once and advanced with one 64-bit add per MMA (the start-address field counts 16-byte units and
-      // never overflows its 14 bits inside the 227 KB window): the issuing thread is a serial bottleneck otherwise.
+      // Descriptors are built once and advanced with one 64-bit add per MMA (start-address field = 16-byte units).
       const uint64_t dM0 = umma_desc(s_m, 1024, LAYOUT_SW128);
       const uint64_t dOnes = umma_desc(s_ones, 1024, LAYOUT_SW128);
       const uint64_t dRingK = umma_desc(s_ring, 1024, LAYOUT_SW128);             // slab as K-major A (GEMM1)
       const uint64_t dRingMN = umma_desc_mn(s_ring, SLAB_BYTES, 512);            // slab as MN-major B (GEMM2)
       const uint64_t dE0 = umma_desc(s_e, 1024, LAYOUT_SW128);
       uint32_t ctr = 0;
-      auto gemm1 = [&](int it) {
-        const uint32_t d_s = tmem + COL_S + (it & 1) * 32;
-        for (int s = 0; s < NS; ++s, ++ctr) {
-          const int stage = (int)(ctr % (uint32_t)nst);
-          mbar_wait(smem_u32(&bars->slab_full[stage]), (ctr / (uint32_t)nst) & 1u);
-          tc_fence_after();
-          const uint64_t da = dRingK + (uint64_t)(stage * (SLAB_BYTES >> 4));
-          const uint64_t db = dM0 + (uint64_t)(s * ((KP * 128) >> 4));
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_ss(d_s, da + kk * 2, db + kk * 2, IDESC1, (s | kk) ? 1u : 0u);
-          umma_commit(smem_u32(&bars->slab_empty[stage]));
-        }
-        umma_commit(smem_u32(&bars->s_full[it & 1]));
+      auto wait_slot = [&]() -> int {                                             // observe the next ring fill
+        const int stage = (int)(ctr % (uint32_t)nst);
+        mbar_wait(smem_u32(&bars->slab_full[stage]), (ctr / (uint32_t)nst) & 1u);
+        ++ctr;
+        return stage;
       };
-      gemm1(0);
+      auto pass1 = [&](int it) {                                                  // the NS fills of P1(it)
+        const uint32_t d_s = tmem + COL_S + (it & 1) * 32;
+        for (int s = 0; s < NS; ++s) {
+          const int stage = wait_slot();
+          if (role == 0) {
+            tc_fence_after();
+            const uint64_t da = dRingK + (uint64_t)(stage * (SLAB_BYTES >> 4));
+            const uint64_t db = dM0 + (uint64_t)(s * ((KP * 128) >> 4));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_ss(d_s, da + kk * 2, db + kk * 2, IDESC1, (s | kk) ? 1u : 0u);
+            umma_commit(smem_u32(&bars->slab_empty[stage]));
+          }
+        }
+        if (role == 0) umma_commit(smem_u32(&bars->s_full[it & 1]));
+      };
+      pass1(0);
       for (int it = 0; it < ntiles; ++it) {
         const int buf = it & 1;
-        if (it + 1 < ntiles) gemm1(it + 1);                          // keeps the row warps fed while GEMM2(it) is pending
-        mbar_wait(smem_u32(&bars->e_full[buf]), (uint32_t)((it >> 1) & 1));
-        tc_fence_after();
+        if (it + 1 < ntiles) pass1(it + 1);                          // GEMM1 of the next tile keeps the row warps fed
         const uint64_t de = dE0 + (uint64_t)(buf * (CF::E_BYTES >> 4));
         const uint32_t acc0 = it ? 1u : 0u;
-        for (int s = 0; s < NS2; ++s, ++ctr) {
-          const int stage = (int)(ctr % (uint32_t)nst);
-          mbar_wait(smem_u32(&bars->slab_full[stage]), (ctr / (uint32_t)nst) & 1u);
+        if (role != 0) {
+          mbar_wait(smem_u32(&bars->e_full[buf]), (uint32_t)((it >> 1) & 1));
           tc_fence_after();
-          const uint64_t dx = dRingMN + (uint64_t)(stage * (SLAB_BYTES >> 4));
-          const uint32_t d2 = tmem + COL_D2 + s * 32;
-#pragma unroll
-          for (int kk = 0; kk < 16; ++kk)                           // 8 tokens (two 4-row swizzle atoms) per MMA
-            umma_ss(d2, de + (uint64_t)(((kk >> 2) * CF::E_CHUNK + (kk & 3) * 32) >> 4), dx + (uint64_t)(kk * 64), IDESC2,
-                    kk ? 1u : acc0);
-          umma_commit(smem_u32(&bars->slab_empty[stage]));          // slab recycled once everything issued so far is done
         }
+        if (role == 2) {
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk)
-          umma_ss(tmem + COL_D3, de + (uint64_t)(((kk >> 2) * CF::E_CHUNK + (kk & 3) * 32) >> 4), dOnes, IDESC3, kk ? 1u : acc0);
-        umma_commit(smem_u32(&bars->e_free[buf]));
+          for (int kk = 0; kk < 16; ++kk)
+            umma_ss(tmem + COL_D3, de + (uint64_t)(((kk >> 2) * CF::E_CHUNK + (kk & 3) * 32) >> 4), dOnes, IDESC3, kk ? 1u : acc0);
+        }
+        for (int s = 0; s < NS2; ++s) {                              // the NS2 fills of P2(it)
+          const int stage = wait_slot();
+          if (role == 1 && (s % NG2) == g2r) {
+            tc_fence_after();
+            const uint64_t dx = dRingMN + (uint64_t)(stage * (SLAB_BYTES >> 4));
+            const uint32_t d2 = tmem + COL_D2 + s * 32;
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk)                         // 8 tokens (two 4-row swizzle atoms) per MMA
+              umma_ss(d2, de + (uint64_t)(((kk >> 2) * CF::E_CHUNK + (kk & 3) * 32) >> 4), dx + (uint64_t)(kk * 64), IDESC2,
+                      kk ? 1u : acc0);
+            umma_commit(smem_u32(&bars->slab_empty[stage]));        // slab recycled once this issuer's MMAs are done
+          }
+        }
+        if (role != 0) umma_commit(smem_u32(&bars->e_free[buf]));
       }
-      umma_commit(smem_u32(&bars->done));
+      if (role != 0) umma_commit(smem_u32(&bars->done));
     }
   } else {
     // =============================== row warps ===============================
