@@ -218,6 +218,12 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       pass1(0);
       for (int it = 0; it < ntiles; ++it) {
         const int buf = it & 1;
+        if (role == 0 && it >= 1) {
+          // S[(it+1)&1] was read by the row warps for tile it-1; they arrive on e_full(it-1) after reading it.  (Waiting it
+          // every iteration also keeps this thread's parity bookkeeping of e_full in step.)
+          mbar_wait(smem_u32(&bars->e_full[buf ^ 1]), (uint32_t)(((it - 1) >> 1) & 1));
+          tc_fence_after();
+        }
         if (it + 1 < ntiles) pass1(it + 1);                          // GEMM1 of the next tile keeps the row warps fed
         const uint64_t de = dE0 + (uint64_t)(buf * (CF::E_BYTES >> 4));
         const uint32_t acc0 = it ? 1u : 0u;
