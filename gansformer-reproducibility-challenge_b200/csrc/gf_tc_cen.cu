@@ -17,8 +17,9 @@
 //   warp 1     GEMM1  S[128 tok, KP]   = X . M^T                      (M=128, as in stage T), runs one tile ahead
 //   warps 6-9  GEMM2  D2[KP->64, 32ch] += E^T[64, 128 tok] . X_slab   (M=64; A = E^T from smem, K-major); slab s -> warp 6 + s%4
 //   warp 10    GEMM3  D3[64, 8]        += E^T . 1                      (softmax denominators)
-//              Every issuer walks ALL ring fills in slot order (waiting on the ones that are not its own): a parity wait
-//              must never fall two phases behind its barrier.
+//              Every issuer walks ALL ring fills in slot order and arrives on slab_empty for each (the owner through
+//              tcgen05.commit, the others with a plain arrive; count = number of issuers): a stage is only refilled once every
+//              issuer has seen its current fill, so no parity wait can fall two phases behind its barrier.
 //   warps 2-5  row warps (thread = token): positional logits, S from TMEM, per-latent tile maximum (warp shuffles +
 //              shared memory), E = exp(S - m) rounded to TF32 and written TRANSPOSED into shared memory, lazy rescale of
 //              the TMEM accumulators when a running maximum moves by more than TAU, final flush of the partials.
@@ -93,6 +94,8 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_by
   return d;
 }
 
+__device__ __forceinline__ int ntiles_dbg(const Params& P, int sp) { const int per = (P.tiles_per_image + P.nsplit - 1) / P.nsplit; return min(P.tiles_per_image, sp * per + per) - sp * per; }
+
 template <int KP, int NS, int NS2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmX2,
@@ -107,6 +110,7 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   const uint32_t s_base = smem_u32(smem);
   const uint32_t s_m = s_base + CF::OFF_M, s_e = s_base + CF::OFF_E, s_ones = s_base + CF::OFF_ONES, s_ring = s_base + CF::OFF_RING;
   Bars* bars = reinterpret_cast<Bars*>(smem + CF::OFF_BARS);
+  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && g_dbg_buf) { g_dbg_buf[1] = smem_u32(bars); g_dbg_buf[2] = (unsigned)ntiles_dbg(P, blockIdx.x); }
   float* red = reinterpret_cast<float*>(smem + CF::OFF_SMALL);      // [4][KP]
   float* mref = red + 4 * KP;                                       // [KP]
   float* resc = mref + KP;                                          // [KP]
@@ -133,7 +137,7 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   if (threadIdx.x < 2) trigf[threadIdx.x] = 0;
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmX); prefetch_tmap(&tmX2); prefetch_tmap(&tmM);
-    for (int i = 0; i < nst; ++i) { mbar_init(smem_u32(&bars->slab_full[i]), 1); mbar_init(smem_u32(&bars->slab_empty[i]), 1); }
+    for (int i = 0; i < nst; ++i) { mbar_init(smem_u32(&bars->slab_full[i]), 1); mbar_init(smem_u32(&bars->slab_empty[i]), NG2 + 2); }
     mbar_init(smem_u32(&bars->m_full), 1); mbar_init(smem_u32(&bars->done), NG2 + 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars->s_full[i]), 1);
@@ -211,6 +215,8 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) umma_ss(d_s, da + kk * 2, db + kk * 2, IDESC1, (s | kk) ? 1u : 0u);
             umma_commit(smem_u32(&bars->slab_empty[stage]));
+          } else {
+            mbar_arrive(smem_u32(&bars->slab_empty[stage]));         // seen
           }
         }
         if (role == 0) umma_commit(smem_u32(&bars->s_full[it & 1]));
@@ -247,6 +253,8 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
               umma_ss(d2, de + (uint64_t)(((kk >> 2) * CF::E_CHUNK + (kk & 3) * 32) >> 4), dx + (uint64_t)(kk * 64), IDESC2,
                       kk ? 1u : acc0);
             umma_commit(smem_u32(&bars->slab_empty[stage]));        // slab recycled once this issuer's MMAs are done
+          } else {
+            mbar_arrive(smem_u32(&bars->slab_empty[stage]));         // seen
           }
         }
         if (role != 0) umma_commit(smem_u32(&bars->e_free[buf]));
@@ -426,6 +434,7 @@ static int launch(const Layout& L, const float* X, float* ws, cudaStream_t st) {
   P.n = L.n; P.H = L.H; P.W = L.W; P.k = L.k; P.nsplit = L.nsplit_cen; P.tiles_per_image = L.n / TILE;
   P.nstages = nst;
   const int smem_bytes = CF::FIXED_BYTES + nst * SLAB_BYTES + 1024;
+  if (const char* dbg = getenv("GF_DEBUG_PTR")) tc::set_debug_buffer(reinterpret_cast<unsigned int*>(strtoull(dbg, nullptr, 0)));
   auto kern = centroid_tc_kernel<KP, NS, NS2>;
   GF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   kern<<<dim3(L.nsplit_cen, L.B, NS / NS2), NUM_THREADS, smem_bytes, st>>>(tmX, tmX2, tmM, P);

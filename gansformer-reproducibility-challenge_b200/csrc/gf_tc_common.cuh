@@ -21,6 +21,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Debug aid: when the host sets this to a host-pinned (UVA) buffer, a watchdog timeout records where it happened before
+// trapping, so the hang site survives the dead context.  One copy per translation unit; set with set_debug_buffer().
+static __device__ unsigned int* g_dbg_buf = nullptr;
+static inline int set_debug_buffer(unsigned int* pinned) {
+  return cudaMemcpyToSymbol(g_dbg_buf, &pinned, sizeof(pinned)) == cudaSuccess ? 0 : -1;
+}
+
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   long long t0 = 0;
@@ -37,7 +44,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if ((++spins & 1023u) == 0) {            // watchdog: a protocol bug must trap, not hang the GPU
       const long long now = clock64();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ll) __trap();
+      else if (now - t0 > 4000000000ll) {
+        if (g_dbg_buf) {                         // record once, keep spinning a little so every stuck waiter gets to record
+          if (!(spins & 0x80000000u)) {
+            spins |= 0x80000000u;
+            const unsigned int slot = atomicAdd(g_dbg_buf, 1u);
+            if (slot < 62) {
+              volatile unsigned int* r = g_dbg_buf + 4 + slot * 4;
+              r[0] = blockIdx.x | (blockIdx.y << 12) | (blockIdx.z << 28); r[1] = threadIdx.x; r[2] = bar; r[3] = parity;
+            }
+            __threadfence_system();
+          }
+          if (now - t0 > 6000000000ll) __trap();
+        } else {
+          __trap();
+        }
+      }
     }
   }
 }
