@@ -386,46 +386,28 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         uint8_t* slab = smem + CF::OFF_RING + stage * SLAB_BYTES + row_off;
         const float4* isc = P.in_scale ? reinterpret_cast<const float4*>(P.in_scale + (size_t)b * P.in_ld + s * SLAB_CH) : nullptr;
         const float4* psc = P.post_scale ? reinterpret_cast<const float4*>(P.post_scale + (size_t)b * P.post_ld + s * SLAB_CH) : nullptr;
-        // element-wise part in packed fp32x2 arithmetic (two channels per instruction)
-        const f32x2 rstd2 = pack2(rstd, rstd), mr2 = pack2(mr, mr), pnz2 = pack2(pnz, pnz);
-        const f32x2 gain2 = pack2(P.pgain, P.pgain), slope2 = pack2(0.2f, 0.2f);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float4* px = reinterpret_cast<float4*>(slab + ((c ^ sw) << 4));
-          const float4 x = *px;
-          f32x2 v[2] = {pack2(x.x, x.y), pack2(x.z, x.w)};
-          if (isc) { const float4 d = __ldg(isc + c); v[0] = mul2(v[0], pack2(d.x, d.y)); v[1] = mul2(v[1], pack2(d.z, d.w)); }
-          f32x2 nb[2] = {0ull, 0ull}, gp[2] = {gain2, gain2};
+          float4 x = *px;
+          if (isc) { const float4 d = __ldg(isc + c); x.x *= d.x; x.y *= d.y; x.z *= d.z; x.w *= d.w; }
+          float xn0 = fmaf(x.x, rstd, mr), xn1 = fmaf(x.y, rstd, mr), xn2 = fmaf(x.z, rstd, mr), xn3 = fmaf(x.w, rstd, mr);
+          if constexpr (MODE == GF_INT_MUL) {
+            x.x = xn0 * gv[c * 4 + 0]; x.y = xn1 * gv[c * 4 + 1]; x.z = xn2 * gv[c * 4 + 2]; x.w = xn3 * gv[c * 4 + 3];
+          } else if constexpr (MODE == GF_INT_ADD) {
+            x.x = xn0 + gv[c * 4 + 0]; x.y = xn1 + gv[c * 4 + 1]; x.z = xn2 + gv[c * 4 + 2]; x.w = xn3 + gv[c * 4 + 3];
+          } else {
+            x.x = fmaf(xn0, gv[c * 4 + 0], bv[c * 4 + 0]); x.y = fmaf(xn1, gv[c * 4 + 1], bv[c * 4 + 1]);
+            x.z = fmaf(xn2, gv[c * 4 + 2], bv[c * 4 + 2]); x.w = fmaf(xn3, gv[c * 4 + 3], bv[c * 4 + 3]);
+          }
           if (P.has_post) {
             const float4 pb = *reinterpret_cast<const float4*>(pbias_s + s * SLAB_CH + c * 4);   // broadcast read
-            nb[0] = add2(pnz2, pack2(pb.x, pb.y)); nb[1] = add2(pnz2, pack2(pb.z, pb.w));
-            if (psc) { const float4 q4 = __ldg(psc + c); gp[0] = mul2(gain2, pack2(q4.x, q4.y)); gp[1] = mul2(gain2, pack2(q4.z, q4.w)); }
+            x.x += pnz + pb.x; x.y += pnz + pb.y; x.z += pnz + pb.z; x.w += pnz + pb.w;
+            if (P.pact == 1) { x.x = fmaxf(x.x, 0.2f * x.x); x.y = fmaxf(x.y, 0.2f * x.y); x.z = fmaxf(x.z, 0.2f * x.z); x.w = fmaxf(x.w, 0.2f * x.w); }
+            x.x *= P.pgain; x.y *= P.pgain; x.z *= P.pgain; x.w *= P.pgain;
+            if (psc) { const float4 q4 = __ldg(psc + c); x.x *= q4.x; x.y *= q4.y; x.z *= q4.z; x.w *= q4.w; }
           }
-#pragma unroll
-          for (int hlf = 0; hlf < 2; ++hlf) {
-            const f32x2 g2 = pack2(gv[c * 4 + hlf * 2], gv[c * 4 + hlf * 2 + 1]);
-            const f32x2 xn = fma2(v[hlf], rstd2, mr2);
-            f32x2 y;
-            if constexpr (MODE == GF_INT_MUL) y = P.has_post ? fma2(xn, g2, nb[hlf]) : mul2(xn, g2);
-            else if constexpr (MODE == GF_INT_ADD) y = P.has_post ? add2(add2(xn, g2), nb[hlf]) : add2(xn, g2);
-            else {
-              const f32x2 b2 = pack2(bv[c * 4 + hlf * 2], bv[c * 4 + hlf * 2 + 1]);
-              y = fma2(xn, g2, P.has_post ? add2(b2, nb[hlf]) : b2);
-            }
-            if (P.has_post) {
-              if (P.pact == 1) {
-                float y0, y1, t0, t1;
-                unpack2(y, y0, y1);
-                unpack2(mul2(y, slope2), t0, t1);
-                y = pack2(fmaxf(y0, t0), fmaxf(y1, t1));
-              }
-              y = mul2(y, gp[hlf]);
-            }
-            v[hlf] = y;
-          }
-          float4 o;
-          unpack2(v[0], o.x, o.y); unpack2(v[1], o.z, o.w);
-          *px = o;
+          *px = x;
         }
         fence_proxy_async();                       // generic-proxy writes -> visible to the TMA (async proxy)
         named_bar_sync(2 + g, 128);
