@@ -10,6 +10,7 @@ dev = torch.device("cuda:0")
 B = int(os.environ.get("AB_BATCH", 32)); k = int(os.environ.get("AB_K", 16)); D = 32
 integ = os.environ.get("AB_INT", "mul")
 duplex = bool(int(os.environ.get("AB_DUPLEX", "0")))
+with_post = bool(int(os.environ.get("AB_POST", "0")))   # fused demod + noise + bias + lrelu + style, as inside the generator
 layers = [(8, 512), (16, 512), (32, 512), (64, 512), (128, 256), (256, 128)]
 if os.environ.get("AB_ONLY"):
     layers = [l for l in layers if str(l[0]) in os.environ["AB_ONLY"].split(",")]
@@ -23,11 +24,15 @@ for res, C in layers:
     xs = [torch.randn(B, res, res, C, device=dev) for _ in range(nbuf)]
     y = torch.randn(B, k, D, device=dev)
     o = torch.empty_like(xs[0])
+    post = None
+    if with_post:
+        post = dict(bias=torch.randn(C, device=dev), noise=torch.randn(res, res, device=dev), strength=torch.tensor(0.1, device=dev), act='lrelu', gain=2 ** 0.5,
+                    in_scale=torch.rand(B, C, device=dev) + 0.5, post_scale=torch.rand(B, C, device=dev) + 0.5)
     for mode in modes:
         attn = gf.BipartiteAttention(C, D, k, integration=integ, kmeans=duplex, exact_fp32=(mode == "fp32")).to(dev)
         with torch.no_grad():
             for i in range(3):
-                attn(xs[i % nbuf], y, out=o)
+                attn(xs[i % nbuf], y, out=o, postop=post)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             # time the whole call (prologue + stage T) and, separately, stage T alone via the StageTimer hook
@@ -36,7 +41,7 @@ for res, C in layers:
             am.STAGE_TIMER = am.StageTimer()
             e0.record()
             for i in range(iters):
-                attn(xs[i % nbuf], y, out=o)
+                attn(xs[i % nbuf], y, out=o, postop=post)
             e1.record()
             torch.cuda.synchronize()
             t_call = e0.elapsed_time(e1) / iters
