@@ -140,6 +140,39 @@ def cpu_oracle_run(G_state, steps: int, warmup: int, sample_b: int):
     return sample_b / t, t, threads
 
 
+def duplex_attention_probe(device, peak_gbs: float, iters: int = 3):
+    """BASELINE configs[2] attention path (256x256 generator layers, duplex, K=32, batch 64): stage-T + pass A + the small
+    per-image products, CUDA-event timed per layer, inputs rotated so none is L2-resident.  ALG bytes as for simplex."""
+    import gansformer_b200 as gf
+    B, k, D = 64, 32, 32
+    layers = [(8, 512), (16, 512), (32, 512), (64, 512), (128, 256), (256, 128)]
+    tot_ms, tot_bytes, cen_path = 0.0, 0, "none"
+    for res, C in layers:
+        nbytes = 2 * 4 * B * res * res * C
+        xs = [torch.randn(B, res, res, C, device=device) for _ in range(2)]
+        y = torch.randn(B, k, D, device=device)
+        out = torch.empty_like(xs[0])
+        attn = gf.BipartiteAttention(C, D, k, kmeans=True).to(device)
+        with torch.no_grad():
+            for i in range(2):
+                attn(xs[i & 1], y, out=out)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(iters):
+                attn(xs[i & 1], y, out=out)
+            e1.record()
+            torch.cuda.synchronize()
+        tot_ms += 2 * e0.elapsed_time(e1) / iters            # two attention layers per resolution
+        tot_bytes += 2 * nbytes
+        if res == 256:
+            cen_path = gf._lib.last_centroid_path()
+        del xs, out, attn
+    achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
+    return {"workload": "BASELINE configs[2] attention path: 12 duplex layers of the 256x256 generator, K=32, batch 64 (whole layer call: "
+                        "pass A + centroid/key products + stage T)", "ms": tot_ms, "alg_bytes": tot_bytes, "achieved": achieved,
+            "unit": "GB/s", "frac": achieved / peak_gbs, "pass_a_path": cen_path}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -276,9 +309,13 @@ def run_ours(args):
                      "launches_timed": n_attn_launches, "alg_bytes_per_step": attn_bytes // max(args.steps, 1),
                      "attention_ms_per_step": attn_s / args.steps * 1e3,
                      "attention_share_of_step": attn_s / (ev0.elapsed_time(ev1) * 1e-3),
-                     "note": "attention launches timed in an eager pass of the same K steps; the step itself replays a CUDA graph"},
+                     "note": "attention launches timed in an eager pass of the same K steps; the step itself replays a CUDA graph. "
+                             "Inside the generator each launch also carries the fused demodulation scale, noise, bias, leaky-ReLU and "
+                             "next-layer style scale (SURVEY row f3), which are not counted in the algorithmic bytes"},
         "clocks": clocks,
     }
+    if world == 1 and not args.no_duplex_probe:
+        line["duplex_attention"] = duplex_attention_probe(device, peak)
     if world == 1 and not args.no_cpu_baseline:
         ips, t, cores = cpu_oracle_run(G.state_dict(), steps=2, warmup=1, sample_b=2)
         line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
@@ -297,6 +334,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true")
+    ap.add_argument("--no-duplex-probe", action="store_true")
     args = ap.parse_args()
     if args.impl == "ours":
         args.warmup = max(args.warmup, 3)

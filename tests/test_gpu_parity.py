@@ -307,6 +307,25 @@ def test_run_wrapper_minibatches(gf, cuda_dev):
     assert (imgs - ref).abs().max() <= 1e-4 * max(1.0, ref.abs().max().item())
 
 
+def test_cuda_graph_replay_matches_eager(gf, cuda_dev):
+    """Generator.graphed / run(cuda_graph=True): the captured graph reproduces the eager forward for new latents."""
+    G = _small_generator(gf, cuda_dev, False)
+    g = torch.Generator().manual_seed(3)
+    z1, z2 = torch.randn(4, 9, 32, generator=g), torch.randn(4, 9, 32, generator=g)
+    with torch.no_grad():
+        e1, e2 = G(z1.to(cuda_dev)).clone(), G(z2.to(cuda_dev)).clone()
+        replay = G.graphed(4)
+        r1 = replay(z1.to(cuda_dev)).clone()
+        r2 = replay(z2.to(cuda_dev)).clone()
+    # cuDNN may pick a different (capture-safe) TF32 algorithm inside the graph: TF32-level tolerance, not bit equality
+    tol = 1e-3 * max(1.0, e1.abs().max().item())
+    print(f"[graph] d1={(r1 - e1).abs().max().item():.3e} d2={(r2 - e2).abs().max().item():.3e} d12={(r1 - r2).abs().max().item():.3e} tol={tol:.3e}")
+    assert (r1 - e1).abs().max() <= tol and (r2 - e2).abs().max() <= tol
+    assert (r1 - r2).abs().max() > 20 * tol                   # the graph really recomputed for the new latents
+    host = G.run(z2.numpy(), minibatch_size=4, cuda_graph=True)
+    assert (host - e2.cpu()).abs().max() <= tol
+
+
 def test_autograd_matches_oracle(gf, cuda_dev):
     """Training path: forward = CUDA kernels, backward = autograd through the composite; gradients vs the fp64 oracle."""
     C, H, W, k, D, p = 64, 8, 16, 4, 16, 16
