@@ -6,23 +6,23 @@
 // streamed once over X with an online softmax (lazy rescaling), split over `nsplit` CTAs per image whose partials
 // (acc[KP][C], m[KP], l[KP]) are merged by centroid_merge_kernel (gf_simt.cu).
 //
-// grid (nsplit, B), 6 warps:
-//   warp 0     TMA producer: M (latent-query matrix, once) and the X slabs (128 tokens x 32 channels).  Every slab is
-//              fetched twice: with SWIZZLE_128B for GEMM1 (X is the K-major A operand: contraction over channels) and with
-//              SWIZZLE_128B_ATOM_32B for GEMM2 (X is the MN-major B operand: contraction over tokens; for 32-bit MN-major
-//              operands that swizzle -- UMMA layout SWIZZLE_128B_BASE32B -- is the only one the tensor core accepts).
-//              The second fetch hits L2; slot order in the ring: P1(0), [P1(i+1), P2(i)] for i = 0, 1, ...
-//   MMA issuers: one thread retires ~10 scalar instructions (~90 cycles) per tcgen05.mma whatever its shape
-//              (tools/probes/mma_probe.cu), and a tile needs 4*C/32 + 16*C/32 + 16 of them, so the issue is spread over warps:
-//   warp 1     GEMM1  S[128 tok, KP]   = X . M^T                      (M=128, as in stage T), runs one tile ahead
-//   warps 6-9  GEMM2  D2[KP->64, 32ch] += E^T[64, 128 tok] . X_slab   (M=64; A = E^T from smem, K-major); slab s -> warp 6 + s%4
-//   warp 10    GEMM3  D3[64, 8]        += E^T . 1                      (softmax denominators)
-//              Every issuer walks ALL ring fills in slot order and arrives on slab_empty for each (the owner through
-//              tcgen05.commit, the others with a plain arrive; count = number of issuers): a stage is only refilled once every
-//              issuer has seen its current fill, so no parity wait can fall two phases behind its barrier.
-//   warps 2-5  row warps (thread = token): positional logits, S from TMEM, per-latent tile maximum (warp shuffles +
-//              shared memory), E = exp(S - m) rounded to TF32 and written TRANSPOSED into shared memory, lazy rescale of
-//              the TMEM accumulators when a running maximum moves by more than TAU, final flush of the partials.
+// grid (nsplit, B, C/C2), 8 warps, one 128-token tile per step:
+//   warp 0   TMA producer of ring 1: the X slabs (128 tokens x 32 channels) with SWIZZLE_128B -- X as the K-major A operand
+//            of GEMM1 (contraction over channels).  This is the fetch that comes from HBM; the ring is deep and a slab is
+//            recycled as soon as its 4 MMAs have retired.
+//   warp 1   TMA producer of ring 2: the same data again (an L2 hit), 64 channels per stage, with
+//            SWIZZLE_128B_ATOM_32B -- X as the MN-major A operand of GEMM2 (contraction over tokens; for 32-bit MN-major
+//            operands that swizzle, UMMA layout SWIZZLE_128B_BASE32B, is the only one the tensor core accepts, and a
+//            K-major operand with it faults, so the two GEMMs cannot share one copy).
+//   warp 6   GEMM1  S[128 tok, KP]  = X . M^T                  (M=128, N=KP, K=8 per MMA; 4 MMAs per slab), up to two tiles ahead
+//   warp 7   GEMM2  D2[64 ch, KP]  += X_stage^T . E            (M=64 channels, N=KP, K=8 tokens per MMA; 16 MMAs per stage)
+//            Both issuers run warp-converged with every operand derived from kernel parameters / __shfl_sync so that the
+//            descriptors live in uniform registers and each tcgen05.mma is ONE instruction (elect.sync-predicated); issued
+//            from an `if (lane == 0)` branch the same MMA costs ~16 SASS instructions (tools/probes/mma_issue_probe.cu).
+//   warps 2-5 row warps (thread = token): positional logits, S from TMEM, lazy-rescale vote, E = 2^(s - m) rounded to TF32
+//            and written TRANSPOSED into shared memory (the K-major B operand of GEMM2), softmax denominators accumulated
+//            in registers (reduced once at the end), rare rescale of the TMEM accumulators, final flush of the partials.
+// Every mbarrier has exactly one waiting role, which observes every phase in order (the precondition of parity waits).
 // HBM traffic: X read once (+ one L2 re-read).
 #include <stdlib.h>
 #include "gf_common.cuh"
@@ -35,50 +35,51 @@ using namespace tc;
 
 constexpr int TILE = 128;
 constexpr int SLAB_CH = 32;
-constexpr int SLAB_BYTES = TILE * SLAB_CH * 4;
-constexpr int MAX_STAGES = 12;
-constexpr int NUM_THREADS = 352;     // warp 0 producer, 1 GEMM1, 2-5 row warps, 6-9 GEMM2 issuers, 10 GEMM3 (denominators)
-constexpr int TMEM_COLS = 512;
+constexpr int SLAB_BYTES = TILE * SLAB_CH * 4;      // 16 KB: ring-1 stage
+constexpr int HG_BYTES = 2 * SLAB_BYTES;            // 32 KB: ring-2 stage = 64 channels ("half group")
+constexpr int MAX_ST1 = 8, MAX_ST2 = 3;
+constexpr int NUM_THREADS = 256;     // warp 0 producer 1, warp 1 producer 2, 2-5 row warps, 6 GEMM1, 7 GEMM2
+constexpr int TMEM_COLS = 256;
 constexpr int COL_S = 0;          // S[2]: 2 x 32 columns
-constexpr int COL_D3 = 64;        // softmax denominators (8 columns used)
-constexpr int COL_D2 = 128;       // Xbar accumulators: C columns (C <= 256)
+constexpr int COL_D2 = 64;        // Xbar^T accumulators: one 32-column block per 64 channels (<= 4 blocks)
 constexpr float TAU = 8.f;        // lazy rescale threshold (natural-log units): exp(8) ~ 3e3 of headroom is harmless in fp32
 
 struct Params {
   const float* Rt; const float* Ct; float* part;
-  int n, H, W, k, nsplit, tiles_per_image, nstages;
+  int n, H, W, k, nsplit, tiles_per_image, nst1, nst2;
 };
 
 struct Bars {
-  uint64_t slab_full[MAX_STAGES], slab_empty[MAX_STAGES];
+  uint64_t full1[MAX_ST1], empty1[MAX_ST1];
+  uint64_t full2[MAX_ST2], empty2[MAX_ST2];
   uint64_t m_full, done;
-  uint64_t s_full[2], e_full[2], e_free[2];
+  uint64_t s_full[2], s_free[2], e_full[2], e_free[2];
   uint32_t tmem_base;
   uint32_t pad;
 };
 
 // NS = slabs of GEMM1 (all C channels); NS2 = slabs of GEMM2 handled by this CTA (C/32 or, for C = 512, half of them:
-// blockIdx.z selects the channel half, both CTAs recompute the cheap GEMM1 + softmax; TMEM holds NS2*32 accumulator columns)
+// blockIdx.z selects the channel half, both CTAs recompute the cheap GEMM1 + softmax)
 template <int KP, int NS, int NS2 = (NS > 8 ? NS / 2 : NS)>
 struct Cfg {
   static constexpr int C = NS * SLAB_CH;
+  static constexpr int NHG = NS2 / 2;                        // ring-2 stages per tile
   static constexpr int M_BYTES = KP * C * 4;                 // NS chunks of [KP rows x 128 B]
   static constexpr int E_CHUNK = KP * 128;                   // one 32-token chunk of E^T: [KP rows x 128 B]
   static constexpr int E_BYTES = 4 * E_CHUNK;                // 128 tokens
   static constexpr int OFF_M = 0;
   static constexpr int OFF_E = OFF_M + M_BYTES;              // 2 buffers
-  static constexpr int OFF_ONES = OFF_E + 2 * E_BYTES;       // 1 KB of 1.0f
-  static constexpr int OFF_SMALL = OFF_ONES + 1024;          // red[4][KP], mref[KP], resc[KP], flag
+  static constexpr int OFF_SMALL = OFF_E + 2 * E_BYTES;      // red[4][KP], mref[KP], resc[KP], flags
   static constexpr int SMALL_BYTES = (4 * KP + 2 * KP + 4) * 4;
   static constexpr int OFF_BARS = (OFF_SMALL + SMALL_BYTES + 15) / 16 * 16;
-  // the M=64 A descriptor of GEMM2 reads 64 rows from each E chunk: rows >= KP alias whatever follows (their D rows are
-  // never read); the ring behind keeps those reads inside the allocation.
   static constexpr int OFF_RING = (OFF_BARS + (int)sizeof(Bars) + 1023) / 1024 * 1024;
   static constexpr int FIXED_BYTES = OFF_RING;
 };
 
-__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int b_mn_major) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// kind::tf32, fp32 accumulate; a_mn / b_mn: operand is MN-major
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
 }
 // MN-major 32-bit operand, UMMA layout SWIZZLE_128B_BASE32B (= TMA SWIZZLE_128B_ATOM_32B, cute Swizzle<2,5,2>):
 // 32 contiguous MN elements (128 B) per K row, 4 K rows per 512-byte atom (32-byte chunks XOR row % 4);
@@ -94,8 +95,6 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_by
   return d;
 }
 
-__device__ __forceinline__ int ntiles_dbg(const Params& P, int sp) { const int per = (P.tiles_per_image + P.nsplit - 1) / P.nsplit; return min(P.tiles_per_image, sp * per + per) - sp * per; }
-
 template <int KP, int NS, int NS2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmX2,
@@ -103,20 +102,25 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   using CF = Cfg<KP, NS, NS2>;
   constexpr int C = CF::C;
   constexpr int C2 = NS2 * SLAB_CH;                  // accumulator channels of this CTA
-  constexpr int NG2 = NS2 < 4 ? NS2 : 4;             // GEMM2 issuer warps
+  constexpr int NHG = CF::NHG;
   const int zoff = blockIdx.z * C2;                   // first channel of this CTA's GEMM2 share
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const uint32_t s_base = smem_u32(smem);
-  const uint32_t s_m = s_base + CF::OFF_M, s_e = s_base + CF::OFF_E, s_ones = s_base + CF::OFF_ONES, s_ring = s_base + CF::OFF_RING;
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  const uint32_t s_base = smem_u32(smem_raw) + pad;
+  const uint32_t s_m = s_base + CF::OFF_M, s_e = s_base + CF::OFF_E, s_ring1 = s_base + CF::OFF_RING;
+  const int nst1 = P.nst1, nst2 = P.nst2;
+  const uint32_t s_ring2 = s_ring1 + (uint32_t)nst1 * SLAB_BYTES;
   Bars* bars = reinterpret_cast<Bars*>(smem + CF::OFF_BARS);
-  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && g_dbg_buf) { g_dbg_buf[1] = smem_u32(bars); g_dbg_buf[2] = (unsigned)ntiles_dbg(P, blockIdx.x); }
+  const uint32_t s_bars = s_base + CF::OFF_BARS;
+  auto bar = [&](const uint64_t* p) -> uint32_t { return s_bars + (uint32_t)((const uint8_t*)p - (const uint8_t*)bars); };
+  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && g_dbg_buf) g_dbg_buf[1] = s_bars;
   float* red = reinterpret_cast<float*>(smem + CF::OFF_SMALL);      // [4][KP]
   float* mref = red + 4 * KP;                                       // [KP]
   float* resc = mref + KP;                                          // [KP]
   volatile int* trigf = reinterpret_cast<volatile int*>(resc + KP);  // [2] per-tile-parity trigger flags
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nst = P.nstages;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
   const int b = blockIdx.y, sp = blockIdx.x;
   const int per = (P.tiles_per_image + P.nsplit - 1) / P.nsplit;
   const int tile_beg = sp * per, tile_end = min(P.tiles_per_image, tile_beg + per);
@@ -132,135 +136,121 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     return;
   }
 
-  for (int i = threadIdx.x; i < 256; i += NUM_THREADS) reinterpret_cast<float*>(smem + CF::OFF_ONES)[i] = 1.f;
   if (threadIdx.x < KP) { mref[threadIdx.x] = -INFINITY; resc[threadIdx.x] = 1.f; }
   if (threadIdx.x < 2) trigf[threadIdx.x] = 0;
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmX); prefetch_tmap(&tmX2); prefetch_tmap(&tmM);
-    for (int i = 0; i < nst; ++i) { mbar_init(smem_u32(&bars->slab_full[i]), 1); mbar_init(smem_u32(&bars->slab_empty[i]), NG2 + 2); }
-    mbar_init(smem_u32(&bars->m_full), 1); mbar_init(smem_u32(&bars->done), NG2 + 1);
+    for (int i = 0; i < nst1; ++i) { mbar_init(bar(&bars->full1[i]), 1); mbar_init(bar(&bars->empty1[i]), 1); }
+    for (int i = 0; i < nst2; ++i) { mbar_init(bar(&bars->full2[i]), 1); mbar_init(bar(&bars->empty2[i]), 1); }
+    mbar_init(bar(&bars->m_full), 1); mbar_init(bar(&bars->done), 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&bars->s_full[i]), 1);
-      mbar_init(smem_u32(&bars->e_full[i]), 4);
-      mbar_init(smem_u32(&bars->e_free[i]), NG2 + 1);
+      mbar_init(bar(&bars->s_full[i]), 1);
+      mbar_init(bar(&bars->s_free[i]), 4);
+      mbar_init(bar(&bars->e_full[i]), 4);
+      mbar_init(bar(&bars->e_free[i]), 1);
     }
     fence_barrier_init();
   }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "n"(TMEM_COLS) : "memory");
+  if (warp == 6) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bar((const uint64_t*)&bars->tmem_base)), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  fence_proxy_async();                        // the generic-proxy writes of `ones` must be visible to the tensor core
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = bars->tmem_base;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
 
   if (warp == 0) {
-    // =============================== TMA producer ===============================
+    // =============================== producer 1: HBM -> ring 1 (K-major copy for GEMM1) ===============================
     if (lane == 0) {
-      const uint32_t mb = smem_u32(&bars->m_full);
+      const uint32_t mb = bar(&bars->m_full);
       mbar_expect_tx(mb, (uint32_t)CF::M_BYTES);
 #pragma unroll
       for (int s = 0; s < NS; ++s) tma_load_2d(s_m + s * (KP * 128), &tmM, mb, s * SLAB_CH, b * KP);
-      uint32_t ctr = 0;
-      auto load_tile = [&](int it, const CUtensorMap* map, int nslabs, int c_first) {
+      int stage = 0; uint32_t ph = 0;
+      for (int it = 0; it < ntiles; ++it) {
         const int row0 = (b * P.tiles_per_image + tile_beg + it) * TILE;
-        for (int s = 0; s < nslabs; ++s, ++ctr) {
-          const int stage = (int)(ctr % (uint32_t)nst);
-          mbar_wait(smem_u32(&bars->slab_empty[stage]), ((ctr / (uint32_t)nst) & 1u) ^ 1u);
-          const uint32_t bar = smem_u32(&bars->slab_full[stage]);
-          mbar_expect_tx(bar, SLAB_BYTES);
-          tma_load_2d(s_ring + stage * SLAB_BYTES, map, bar, c_first + s * SLAB_CH, row0);
-        }
-      };
-      load_tile(0, &tmX, NS, 0);
-      for (int it = 0; it < ntiles; ++it) {
-        if (it + 1 < ntiles) load_tile(it + 1, &tmX, NS, 0);   // GEMM1 of the next tile runs ahead of GEMM2 of this one
-        load_tile(it, &tmX2, NS2, zoff);                        // second fetch (L2), MN-major swizzle, this CTA's channels
-      }
-    }
-  } else if (warp == 1 || warp >= 6) {
-    // =============================== MMA issuers ===============================
-    // ring slot order: P1(0) | P1(1) P2(0) | P1(2) P2(1) | ... ; slots before block `it`: NS + it*(NS+NS2)
-    const int role = warp == 1 ? 0 : (warp == 10 ? 2 : 1);         // 0: GEMM1, 1: GEMM2 share (warp - 6), 2: GEMM3
-    const int g2r = warp - 6;
-    if (lane == 0 && !(role == 1 && g2r >= NG2)) {
-      constexpr uint32_t IDESC1 = idesc_tf32(TILE, KP, 0);
-      constexpr uint32_t IDESC2 = idesc_tf32(64, 32, 1);
-      constexpr uint32_t IDESC3 = idesc_tf32(64, 8, 0);
-      mbar_wait(smem_u32(&bars->m_full), 0);
-      tc_fence_after();
-      // Descriptors are built once and advanced with one 64-bit add per MMA (start-address field = 16-byte units).
-      const uint64_t dM0 = umma_desc(s_m, 1024, LAYOUT_SW128);
-      const uint64_t dOnes = umma_desc(s_ones, 1024, LAYOUT_SW128);
-      const uint64_t dRingK = umma_desc(s_ring, 1024, LAYOUT_SW128);             // slab as K-major A (GEMM1)
-      const uint64_t dRingMN = umma_desc_mn(s_ring, SLAB_BYTES, 512);            // slab as MN-major B (GEMM2)
-      const uint64_t dE0 = umma_desc(s_e, 1024, LAYOUT_SW128);
-      uint32_t ctr = 0;
-      auto wait_slot = [&]() -> int {                                             // observe the next ring fill
-        const int stage = (int)(ctr % (uint32_t)nst);
-        mbar_wait(smem_u32(&bars->slab_full[stage]), (ctr / (uint32_t)nst) & 1u);
-        ++ctr;
-        return stage;
-      };
-      auto pass1 = [&](int it) {                                                  // the NS fills of P1(it)
-        const uint32_t d_s = tmem + COL_S + (it & 1) * 32;
         for (int s = 0; s < NS; ++s) {
-          const int stage = wait_slot();
-          if (role == 0) {
-            tc_fence_after();
-            const uint64_t da = dRingK + (uint64_t)(stage * (SLAB_BYTES >> 4));
-            const uint64_t db = dM0 + (uint64_t)(s * ((KP * 128) >> 4));
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_ss(d_s, da + kk * 2, db + kk * 2, IDESC1, (s | kk) ? 1u : 0u);
-            umma_commit(smem_u32(&bars->slab_empty[stage]));
-          } else {
-            mbar_arrive(smem_u32(&bars->slab_empty[stage]));         // seen
-          }
+          mbar_wait(bar(&bars->empty1[stage]), ph ^ 1u);
+          const uint32_t fb = bar(&bars->full1[stage]);
+          mbar_expect_tx(fb, SLAB_BYTES);
+          tma_load_2d(s_ring1 + stage * SLAB_BYTES, &tmX, fb, s * SLAB_CH, row0);
+          if (++stage == nst1) { stage = 0; ph ^= 1u; }
         }
-        if (role == 0) umma_commit(smem_u32(&bars->s_full[it & 1]));
-      };
-      pass1(0);
-      for (int it = 0; it < ntiles; ++it) {
-        const int buf = it & 1;
-        if (role == 0 && it >= 1) {
-          // S[(it+1)&1] was read by the row warps for tile it-1; they arrive on e_full(it-1) after reading it.  (Waiting it
-          // every iteration also keeps this thread's parity bookkeeping of e_full in step.)
-          mbar_wait(smem_u32(&bars->e_full[buf ^ 1]), (uint32_t)(((it - 1) >> 1) & 1));
-          tc_fence_after();
-        }
-        if (it + 1 < ntiles) pass1(it + 1);                          // GEMM1 of the next tile keeps the row warps fed
-        const uint64_t de = dE0 + (uint64_t)(buf * (CF::E_BYTES >> 4));
-        const uint32_t acc0 = it ? 1u : 0u;
-        if (role != 0) {
-          mbar_wait(smem_u32(&bars->e_full[buf]), (uint32_t)((it >> 1) & 1));
-          tc_fence_after();
-        }
-        if (role == 2) {
-#pragma unroll
-          for (int kk = 0; kk < 16; ++kk)
-            umma_ss(tmem + COL_D3, de + (uint64_t)(((kk >> 2) * CF::E_CHUNK + (kk & 3) * 32) >> 4), dOnes, IDESC3, kk ? 1u : acc0);
-        }
-        for (int s = 0; s < NS2; ++s) {                              // the NS2 fills of P2(it)
-          const int stage = wait_slot();
-          if (role == 1 && (s % NG2) == g2r) {
-            tc_fence_after();
-            const uint64_t dx = dRingMN + (uint64_t)(stage * (SLAB_BYTES >> 4));
-            const uint32_t d2 = tmem + COL_D2 + s * 32;
-#pragma unroll
-            for (int kk = 0; kk < 16; ++kk)                         // 8 tokens (two 4-row swizzle atoms) per MMA
-              umma_ss(d2, de + (uint64_t)(((kk >> 2) * CF::E_CHUNK + (kk & 3) * 32) >> 4), dx + (uint64_t)(kk * 64), IDESC2,
-                      kk ? 1u : acc0);
-            umma_commit(smem_u32(&bars->slab_empty[stage]));        // slab recycled once this issuer's MMAs are done
-          } else {
-            mbar_arrive(smem_u32(&bars->slab_empty[stage]));         // seen
-          }
-        }
-        if (role != 0) umma_commit(smem_u32(&bars->e_free[buf]));
       }
-      if (role != 0) umma_commit(smem_u32(&bars->done));
     }
+  } else if (warp == 1) {
+    // =============================== producer 2: L2 -> ring 2 (MN-major copy for GEMM2) ===============================
+    if (lane == 0) {
+      int stage = 0; uint32_t ph = 0;
+      for (int it = 0; it < ntiles; ++it) {
+        const int row0 = (b * P.tiles_per_image + tile_beg + it) * TILE;
+        for (int hg = 0; hg < NHG; ++hg) {
+          mbar_wait(bar(&bars->empty2[stage]), ph ^ 1u);
+          const uint32_t fb = bar(&bars->full2[stage]);
+          mbar_expect_tx(fb, HG_BYTES);
+          tma_load_2d(s_ring2 + stage * HG_BYTES, &tmX2, fb, zoff + hg * 64, row0);
+          tma_load_2d(s_ring2 + stage * HG_BYTES + SLAB_BYTES, &tmX2, fb, zoff + hg * 64 + SLAB_CH, row0);
+          if (++stage == nst2) { stage = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // =============================== GEMM1 issuer (warp-converged, uniform operands) ===============================
+    constexpr uint32_t IDESC1 = idesc_tf32(TILE, KP, 0, 0);
+    mbar_wait(bar(&bars->m_full), 0);
+    tc_fence_after();
+    const uint64_t dM0 = umma_desc(s_m, 1024, LAYOUT_SW128);
+    const uint64_t dRing = umma_desc(s_ring1, 1024, LAYOUT_SW128);
+    int stage = 0; uint32_t ph = 0;
+    for (int it = 0; it < ntiles; ++it) {
+      const int buf = it & 1;
+      if (it >= 2) {                                                  // S[buf] was read by the row warps for tile it-2
+        mbar_wait(bar(&bars->s_free[buf]), (uint32_t)(((it - 2) >> 1) & 1));
+        tc_fence_after();
+      }
+      const uint32_t d_s = tmem + COL_S + buf * 32;
+#pragma unroll 1
+      for (int s = 0; s < NS; ++s) {
+        mbar_wait(bar(&bars->full1[stage]), ph);
+        tc_fence_after();
+        const uint64_t da = dRing + (uint64_t)(stage * (SLAB_BYTES >> 4));
+        const uint64_t db = dM0 + (uint64_t)(s * ((KP * 128) >> 4));
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_ss_elect(d_s, da + kk * 2, db + kk * 2, IDESC1, (s | kk) ? 1u : 0u);
+        umma_commit_elect(bar(&bars->empty1[stage]));
+        if (++stage == nst1) { stage = 0; ph ^= 1u; }
+      }
+      umma_commit_elect(bar(&bars->s_full[buf]));
+    }
+  } else if (warp == 7) {
+    // =============================== GEMM2 issuer (warp-converged, uniform operands) ===============================
+    constexpr uint32_t IDESC2 = idesc_tf32(64, KP, 1, 0);             // A = X stage, MN-major; B = E^T, K-major
+    const uint64_t dRing = umma_desc_mn(s_ring2, SLAB_BYTES, 512);
+    const uint64_t dE0 = umma_desc(s_e, 1024, LAYOUT_SW128);
+    int stage = 0; uint32_t ph = 0;
+    for (int it = 0; it < ntiles; ++it) {
+      const int buf = it & 1;
+      mbar_wait(bar(&bars->e_full[buf]), (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const uint64_t de = dE0 + (uint64_t)(buf * (CF::E_BYTES >> 4));
+      const uint32_t acc0 = it ? 1u : 0u;
+#pragma unroll 1
+      for (int hg = 0; hg < NHG; ++hg) {
+        mbar_wait(bar(&bars->full2[stage]), ph);
+        tc_fence_after();
+        const uint64_t dx = dRing + (uint64_t)(stage * (HG_BYTES >> 4));
+        const uint32_t d2 = tmem + COL_D2 + hg * 32;
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk)                               // 8 tokens (two 4-row swizzle atoms) per MMA
+          umma_ss_elect(d2, dx + (uint64_t)(kk * 64), de + (uint64_t)(((kk >> 2) * CF::E_CHUNK + (kk & 3) * 32) >> 4), IDESC2,
+                        kk ? 1u : acc0);
+        umma_commit_elect(bar(&bars->empty2[stage]));
+        if (++stage == nst2) { stage = 0; ph ^= 1u; }
+      }
+      umma_commit_elect(bar(&bars->e_free[buf]));
+    }
+    umma_commit_elect(bar(&bars->done));
   } else {
     // =============================== row warps ===============================
     // One warp per scheduler and nothing to hide latency with: the loop is written for few instructions and no exposed
@@ -284,21 +274,25 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     };
     float pos[KP];                                                  // positional logits of the current tile
     float ml[KP];                                                   // running references * log2(e); padded latents: 0
+    float lsum[KP];                                                 // this token row's share of the softmax denominators
     load_pos(0, pos);
 #pragma unroll
-    for (int j = 0; j < KP; ++j) ml[j] = j < P.k ? -INFINITY : 0.f;
+    for (int j = 0; j < KP; ++j) { ml[j] = j < P.k ? -INFINITY : 0.f; lsum[j] = 0.f; }
     uint32_t soff[8];                                               // byte offset of this token inside row j of a chunk
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) soff[jj] = (uint32_t)((((lane >> 2) ^ jj) << 4) + (lane & 3) * 4);
     for (int it = 0; it < ntiles; ++it) {
       const int buf = it & 1;
       const uint32_t bph = (uint32_t)((it >> 1) & 1);
-      mbar_wait(smem_u32(&bars->s_full[buf]), bph);
+      mbar_wait(bar(&bars->s_full[buf]), bph);
       tc_fence_after();
       float sv[KP];
       tmem_ld16(tmem + lane_addr + COL_S + buf * 32, sv);
       if constexpr (KP == 32) tmem_ld16(tmem + lane_addr + COL_S + buf * 32 + 16, sv + 16);
       tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(&bars->s_free[buf]));          // GEMM1 of tile it+2 may overwrite S[buf]
       // t_j = (logit - reference) * log2(e); the trigger test needs only its maximum over this thread's latents
       float ex = -INFINITY;
 #pragma unroll
@@ -334,96 +328,112 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         }
         named_bar_sync(1, 128);
 #pragma unroll
-        for (int j = 0; j < KP; ++j) ml[j] = j < P.k ? mref[j] : 0.f;
+        for (int j = 0; j < KP; ++j) { ml[j] = j < P.k ? mref[j] : 0.f; lsum[j] *= resc[j]; }
       }
-      // ---- E = 2^(t_j), written transposed (E^T[latent][token], K-major SW128, 32-token chunks).  E is NOT rounded to
-      //      TF32: the tensor core's truncation bias hits numerator (D2) and denominator (D3) alike and cancels.
+      // ---- E = 2^(t_j) rounded to TF32 (so that the tensor core's operand truncation is exact and the register-side
+      //      denominators see the same values), written transposed (E^T[latent][token], K-major SW128, 32-token chunks).
       // buffer `buf` was last read by GEMM2(it-2), whose completion this thread observed during tile it-1 (below)
       uint8_t* eb = smem + CF::OFF_E + buf * CF::E_BYTES + q * CF::E_CHUNK;
 #pragma unroll
       for (int j = 0; j < KP; ++j) {
         float e;
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(sv[j] - ml[j]));
+        e = round_tf32_rn(e);
+        lsum[j] += e;
         *reinterpret_cast<float*>(eb + j * 128 + soff[j & 7]) = e;
       }
       // ---- every tile: observe the completion of GEMM2(it-1) (parity bookkeeping must not skip phases); then, if a
       //      running maximum moved, rescale the accumulators before GEMM2(it) adds to them
       if (it > 0) {
-        mbar_wait(smem_u32(&bars->e_free[buf ^ 1]), (uint32_t)(((it - 1) >> 1) & 1));
+        mbar_wait(bar(&bars->e_free[buf ^ 1]), (uint32_t)(((it - 1) >> 1) & 1));
         tc_fence_after();
       }
       if (full && it > 0) {
-        // M=64 accumulators: latent j lives in TMEM lane (j % 16) + 32 * (j / 16): lanes 0-15 of quadrants 0 (and 1)
-        if (q * 16 < KP) {
-          const float f = lane < 16 ? resc[q * 16 + lane] : 1.f;
-          float v[16];
+        // M=64 accumulators: channel c of a 64-channel block lives in TMEM lane (c % 16) + 32 * (c / 16): lanes 0-15 of
+        // every quadrant; columns = latents, so the factor varies along the columns
+        float v[16];
 #pragma unroll 1
-          for (int c0 = 0; c0 < C2; c0 += 16) {
-            tmem_ld16(tmem + lane_addr + COL_D2 + c0, v);
+        for (int c0 = 0; c0 < NHG * 32; c0 += 32) {
+#pragma unroll
+          for (int hh = 0; hh < KP / 16; ++hh) {
+            tmem_ld16(tmem + lane_addr + COL_D2 + c0 + hh * 16, v);
             tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] *= f;
-            tmem_st16(tmem + lane_addr + COL_D2 + c0, v);
+            for (int i = 0; i < 16; ++i) v[i] *= resc[hh * 16 + i];
+            tmem_st16(tmem + lane_addr + COL_D2 + c0 + hh * 16, v);
           }
-          tmem_ld16(tmem + lane_addr + COL_D3, v);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] *= f;
-          tmem_st16(tmem + lane_addr + COL_D3, v);
-          tmem_wait_st();
         }
+        tmem_wait_st();
       }
       fence_proxy_async();                                          // E^T (generic proxy) -> tensor core (async proxy)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars->e_full[buf]));
+      if (lane == 0) mbar_arrive(bar(&bars->e_full[buf]));
     }
     // ---- flush: partial accumulators, running maxima and denominators of this split
-    mbar_wait(smem_u32(&bars->done), 0);
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+      float v = lsum[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[(warp - 2) * KP + j] = v;
+    }
+    named_bar_sync(1, 128);
+    if (rtid < KP && blockIdx.z == 0) {
+      const int j = rtid;
+      part[(size_t)j * (C + 4) + C] = j < P.k ? mref[j] * 0.6931471805599453f : -INFINITY;   // log2 -> natural units
+      part[(size_t)j * (C + 4) + C + 1] = red[j] + red[KP + j] + red[2 * KP + j] + red[3 * KP + j];
+      part[(size_t)j * (C + 4) + C + 2] = 0.f;
+      part[(size_t)j * (C + 4) + C + 3] = 0.f;
+    }
+    mbar_wait(bar(&bars->done), 0);
     tc_fence_after();
-    if (q * 16 < KP) {
-      const int j = q * 16 + lane;                                  // valid for lane < 16
+    {
       float v[16];
 #pragma unroll 1
-      for (int c0 = 0; c0 < C2; c0 += 16) {
-        tmem_ld16(tmem + lane_addr + COL_D2 + c0, v);
-        tmem_wait_ld();
-        if (lane < 16) {
+      for (int hg = 0; hg < NHG; ++hg) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) part[(size_t)j * (C + 4) + zoff + c0 + i] = v[i] * 1.000352220f;   // X truncation bias (gf_fold.cu)
+        for (int hh = 0; hh < KP / 16; ++hh) {
+          tmem_ld16(tmem + lane_addr + COL_D2 + hg * 32 + hh * 16, v);
+          tmem_wait_ld();
+          if (lane < 16) {
+            float* dst = part + zoff + hg * 64 + q * 16 + lane;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dst[(size_t)(hh * 16 + i) * (C + 4)] = v[i] * 1.000352220f;   // X truncation bias (gf_fold.cu)
+          }
         }
-      }
-      tmem_ld16(tmem + lane_addr + COL_D3, v);
-      tmem_wait_ld();
-      if (lane < 16 && blockIdx.z == 0) {
-        part[(size_t)j * (C + 4) + C] = j < P.k ? mref[j] * 0.6931471805599453f : -INFINITY;   // log2 -> natural units
-        part[(size_t)j * (C + 4) + C + 1] = v[0];
-        part[(size_t)j * (C + 4) + C + 2] = 0.f;
-        part[(size_t)j * (C + 4) + C + 3] = 0.f;
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 6) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
   }
 }
 
 template <int KP, int NS>
-static int stages_for(int smem_limit) {
-  int st = (smem_limit - Cfg<KP, NS>::FIXED_BYTES - 1024) / SLAB_BYTES;
-  return st > MAX_STAGES ? MAX_STAGES : st;
+static void stages_for(int smem_limit, int* n1, int* n2) {
+  const int avail = smem_limit - Cfg<KP, NS>::FIXED_BYTES - 1024;
+  int s2 = 2, s1 = (avail - s2 * HG_BYTES) / SLAB_BYTES;
+  if (s1 > MAX_ST1) {                                         // room to spare: deepen ring 2 first
+    s2 = MAX_ST2;
+    s1 = (avail - s2 * HG_BYTES) / SLAB_BYTES;
+    if (s1 > MAX_ST1) s1 = MAX_ST1;
+    if (s1 < 6) { s2 = 2; s1 = (avail - s2 * HG_BYTES) / SLAB_BYTES; if (s1 > MAX_ST1) s1 = MAX_ST1; }
+  }
+  *n1 = s1; *n2 = s2;
 }
 
 template <int KP, int NS>
 static int launch(const Layout& L, const float* X, float* ws, cudaStream_t st) {
   using CF = Cfg<KP, NS>;
   constexpr int NS2 = NS > 8 ? NS / 2 : NS;
-  const int nst = stages_for<KP, NS>(device_smem_optin());
-  if (nst < 4) { set_error("tcgen05 centroid pass: shared memory too small for C=%d KP=%d", L.C, KP); return GF_ERR_UNSUPPORTED; }
+  int n1, n2;
+  stages_for<KP, NS>(device_smem_optin(), &n1, &n2);
+  if (n1 < 2) { set_error("tcgen05 centroid pass: shared memory too small for C=%d KP=%d", L.C, KP); return GF_ERR_UNSUPPORTED; }
   CUtensorMap tmX, tmX2, tmM;
   int rc;
   if ((rc = make_map(&tmX, X, (uint64_t)L.B * L.n, L.C, TILE, SLAB_CH, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
@@ -432,8 +442,8 @@ static int launch(const Layout& L, const float* X, float* ws, cudaStream_t st) {
   Params P;
   P.Rt = ws + L.w_Rt2; P.Ct = ws + L.w_Ct2; P.part = ws + L.w_PART;
   P.n = L.n; P.H = L.H; P.W = L.W; P.k = L.k; P.nsplit = L.nsplit_cen; P.tiles_per_image = L.n / TILE;
-  P.nstages = nst;
-  const int smem_bytes = CF::FIXED_BYTES + nst * SLAB_BYTES + 1024;
+  P.nst1 = n1; P.nst2 = n2;
+  const int smem_bytes = CF::FIXED_BYTES + n1 * SLAB_BYTES + n2 * HG_BYTES + 1024;
   if (const char* dbg = getenv("GF_DEBUG_PTR")) tc::set_debug_buffer(reinterpret_cast<unsigned int*>(strtoull(dbg, nullptr, 0)));
   auto kern = centroid_tc_kernel<KP, NS, NS2>;
   GF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -441,6 +451,9 @@ static int launch(const Layout& L, const float* X, float* ws, cudaStream_t st) {
   GF_LAUNCH_OK();
   return GF_OK;
 }
+
+template <int KP, int NS>
+static bool fits(int limit) { int n1, n2; stages_for<KP, NS>(limit, &n1, &n2); return n1 >= 2; }
 
 }  // namespace tcc
 
@@ -451,8 +464,8 @@ bool tc_centroid_supported(const Layout& L, const gf_attn_desc* d) {
   if (L.n % tcc::TILE != 0 || L.B > 65535) return false;
   const int limit = tc::device_smem_optin();
   const int ns = L.C / 32;
-  if (L.KP == 16) return (ns == 2 ? tcc::stages_for<16, 2>(limit) : ns == 4 ? tcc::stages_for<16, 4>(limit) : ns == 8 ? tcc::stages_for<16, 8>(limit) : tcc::stages_for<16, 16>(limit)) >= 4;
-  return (ns == 2 ? tcc::stages_for<32, 2>(limit) : ns == 4 ? tcc::stages_for<32, 4>(limit) : ns == 8 ? tcc::stages_for<32, 8>(limit) : tcc::stages_for<32, 16>(limit)) >= 4;
+  if (L.KP == 16) return ns == 2 ? tcc::fits<16, 2>(limit) : ns == 4 ? tcc::fits<16, 4>(limit) : ns == 8 ? tcc::fits<16, 8>(limit) : tcc::fits<16, 16>(limit);
+  return ns == 2 ? tcc::fits<32, 2>(limit) : ns == 4 ? tcc::fits<32, 4>(limit) : ns == 8 ? tcc::fits<32, 8>(limit) : tcc::fits<32, 16>(limit);
 }
 
 int centroid_pass_tc(const Layout& L, const gf_attn_desc* d, const float* X, float* ws, cudaStream_t st) {
