@@ -97,12 +97,14 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   float* pbias_s = reinterpret_cast<float*>(smem + CF::OFF_PBIAS);
   if (P.has_post)
     for (int i = threadIdx.x; i < C; i += NUM_THREADS) pbias_s[i] = P.pbias ? P.pbias[i] : 0.f;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
   const int nst = P.nstages;
 
   // contiguous tile range of this CTA
-  const long long tile_beg = (long long)blockIdx.x * P.total_tiles / gridDim.x;
-  const long long tile_end = (long long)(blockIdx.x + 1) * P.total_tiles / gridDim.x;
+  // (the 64-bit divisions are library calls: broadcast their results so the compiler knows the loop bounds are warp-uniform)
+  const long long tile_beg = __shfl_sync(0xffffffffu, (long long)blockIdx.x * P.total_tiles / gridDim.x, 0);
+  const long long tile_end = __shfl_sync(0xffffffffu, (long long)(blockIdx.x + 1) * P.total_tiles / gridDim.x, 0);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmX); prefetch_tmap(&tmO); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
@@ -125,7 +127,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = bars->tmem_base;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -161,70 +163,79 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // Warp-converged: all 32 lanes run the loop with operands derived from kernel parameters / __shfl_sync, so the
+    // descriptors stay in uniform registers and every tcgen05.mma / commit is one elect.sync-predicated instruction
+    // (issued from an `if (lane == 0)` branch each MMA costs ~16 SASS instructions, tools/probes/mma_issue_probe.cu).
+    {
       constexpr uint32_t IDESC1 = umma_idesc_tf32(TILE, KP);
       constexpr uint32_t IDESC2 = umma_idesc_tf32(TILE, 32);
       constexpr uint32_t V_LAYOUT = KP == 32 ? LAYOUT_SW128 : LAYOUT_SW64;
       constexpr uint32_t V_SBO = 8 * CF::V_ROW_BYTES;
-      uint32_t actr = 0;
-      int img_changes = 0, prev_b = -1;
+      int acc = 0; uint32_t acc_ph = 0;          // accumulator ring position
+      int stage = 0; uint32_t ph = 0;            // ring walker: every fill, in slot order
+      int img_changes = 0;
       uint32_t it = 0;
+      int b = __shfl_sync(0xffffffffu, (int)(tile_beg / P.tiles_per_image), 0);      // (division = library call: re-broadcast)
+      int t_in_img = __shfl_sync(0xffffffffu, (int)(tile_beg - (long long)b * P.tiles_per_image), 0);
+      bool new_img = true;
       // base descriptors, advanced with one 64-bit add per MMA (start-address field = 16-byte units)
       const uint64_t dRing = umma_desc(s_ring, 1024, LAYOUT_SW128);
       const uint64_t dKp = umma_desc(s_kp, 1024, LAYOUT_SW128);
       const uint64_t dV = umma_desc(s_v, V_SBO, V_LAYOUT);
       for (long long tile = tile_beg; tile < tile_end; ++tile, ++it) {
-        const int b = (int)(tile / P.tiles_per_image);
         const int buf = (int)(it & 1);
         const uint32_t bphase = (it >> 1) & 1u;
-        if (b != prev_b) {
+        if (new_img) {
           mbar_wait(smem_u32(&bars->kv_full), (uint32_t)(img_changes & 1));
           tc_fence_after();
-          prev_b = b;
           ++img_changes;
+          new_img = false;
         }
         // ---- GEMM1: S[buf] = X . K'^T over all slabs (pass 1 of a two-pass tile)
         const uint32_t d_s = tmem + COL_S + buf * 32;
+#pragma unroll 1
         for (int s = 0; s < NS; ++s) {
-          const uint32_t ctr = it * SPT + s;
-          const int stage = (int)(ctr % (uint32_t)nst);
-          mbar_wait(smem_u32(&bars->slab_full[stage]), (ctr / (uint32_t)nst) & 1u);
+          mbar_wait(smem_u32(&bars->slab_full[stage]), ph);
           tc_fence_after();
           const uint64_t da = dRing + (uint64_t)(stage * (SLAB_BYTES >> 4));
           const uint64_t db = dKp + (uint64_t)(s * ((KP * 128) >> 4));
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_ss(d_s, da + kk * 2, db + kk * 2, IDESC1, (s | kk) ? 1u : 0u);
-          if (TWO_PASS) umma_commit(smem_u32(&bars->slab_empty[stage]));    // slab may be recycled once these MMAs are done
+          for (int kk = 0; kk < 4; ++kk) umma_ss_elect(d_s, da + kk * 2, db + kk * 2, IDESC1, (s | kk) ? 1u : 0u);
+          if (TWO_PASS) umma_commit_elect(smem_u32(&bars->slab_empty[stage]));    // slab may be recycled once these MMAs are done
+          if (++stage == nst) { stage = 0; ph ^= 1u; }
         }
-        umma_commit(smem_u32(&bars->s_full[buf]));
+        umma_commit_elect(smem_u32(&bars->s_full[buf]));
         // ---- GEMM2: per slab, ACC = P[buf] . V^T (gain | bias)
         mbar_wait(smem_u32(&bars->p_full[buf]), bphase);
         tc_fence_after();
         const uint32_t a_p = tmem + COL_P + buf * 32;
-        for (int s = 0; s < NS; ++s, ++actr) {
-          const int a = (int)(actr % NACC);
+#pragma unroll 1
+        for (int s = 0; s < NS; ++s) {
           if (TWO_PASS) {
             // Parity waits are only valid if a waiter never falls two phases behind a barrier: every consumer walks the
             // fills of the ring in slot order.  Waiting the pass-2 fill here also makes acc_full(s) imply "slab s landed".
-            const uint32_t c2 = it * SPT + NS + s;
-            mbar_wait(smem_u32(&bars->slab_full[(int)(c2 % (uint32_t)nst)]), (c2 / (uint32_t)nst) & 1u);
+            mbar_wait(smem_u32(&bars->slab_full[stage]), ph);
+            if (++stage == nst) { stage = 0; ph ^= 1u; }
           }
-          mbar_wait(smem_u32(&bars->acc_empty[a]), ((actr / NACC) & 1u) ^ 1u);
+          mbar_wait(smem_u32(&bars->acc_empty[acc]), acc_ph ^ 1u);
           tc_fence_after();
-          const uint32_t d_acc = tmem + COL_ACC + a * 64;
+          const uint32_t d_acc = tmem + COL_ACC + acc * 64;
           const uint64_t dvg = dV + (uint64_t)((s * 32 * CF::V_ROW_BYTES) >> 4);
 #pragma unroll
-          for (int kk = 0; kk < KP / 8; ++kk) umma_ts(d_acc, a_p + kk * 8, dvg + kk * 2, IDESC2, kk ? 1u : 0u);
+          for (int kk = 0; kk < KP / 8; ++kk) umma_ts_elect(d_acc, a_p + kk * 8, dvg + kk * 2, IDESC2, kk ? 1u : 0u);
           if constexpr (MODE == GF_INT_BOTH) {
             const uint64_t dvb = dV + (uint64_t)(((C + s * 32) * CF::V_ROW_BYTES) >> 4);
 #pragma unroll
-            for (int kk = 0; kk < KP / 8; ++kk) umma_ts(d_acc + 32, a_p + kk * 8, dvb + kk * 2, IDESC2, kk ? 1u : 0u);
+            for (int kk = 0; kk < KP / 8; ++kk) umma_ts_elect(d_acc + 32, a_p + kk * 8, dvb + kk * 2, IDESC2, kk ? 1u : 0u);
           }
-          umma_commit(smem_u32(&bars->acc_full[a]));
+          umma_commit_elect(smem_u32(&bars->acc_full[acc]));
+          if (++acc == NACC) { acc = 0; acc_ph ^= 1u; }
         }
-        umma_commit(smem_u32(&bars->p_free[buf]));
-        const bool last = tile + 1 == tile_end;
-        if (!last && (int)((tile + 1) / P.tiles_per_image) != b) umma_commit(smem_u32(&bars->kv_free));
+        umma_commit_elect(smem_u32(&bars->p_free[buf]));
+        if (++t_in_img == P.tiles_per_image) {
+          t_in_img = 0; ++b; new_img = true;
+          if (tile + 1 < tile_end) umma_commit_elect(smem_u32(&bars->kv_free));
+        }
       }
     }
   } else if (warp >= 10) {
