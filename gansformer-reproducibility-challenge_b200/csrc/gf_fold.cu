@@ -342,11 +342,51 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
                                                        float* __restrict__ Rt, float* __restrict__ Ct,
                                                        int H, int W, int C, int k, int D, int p, int KP, int Cout, int LDK,
                                                        int tf32, int npos, const float* __restrict__ in_scale, int in_ld) {
-  const int b = blockIdx.y;
+  // grid (B, blocks): the role index is the slow grid dimension so that the longest-running role (V^T) is dispatched first
+  const int b = blockIdx.x;
   const float* kp = kpall + (size_t)b * k * LDK;
-  if ((int)blockIdx.x < npos) {
+  const int nvblk = Vt ? (Cout + 255) / 256 : 0;                 // V^T role: one thread per channel
+  const int blk = blockIdx.y;
+  if (blk < nvblk) {
+    // V^T[b, c, :] = (Y[b] . AV[:, c] + CV[c]) for the k latents (zero for the padded ones); AV reads coalesced over c
+    extern __shared__ float ysm[];                                // Y[b]: k x D
+    for (int i = threadIdx.x; i < k * D; i += blockDim.x) ysm[i] = Y[(size_t)b * k * D + i];
+    __syncthreads();
+    const int c = blk * 256 + threadIdx.x;
+    if (c >= Cout) return;
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    for (int d0 = 0; d0 < D; d0 += 32) {
+      float a[32];                                                // 32 independent loads in flight: one L2 latency, not 32
+#pragma unroll
+      for (int dd = 0; dd < 32; ++dd) a[dd] = d0 + dd < D ? AV[(size_t)(d0 + dd) * Cout + c] : 0.f;
+#pragma unroll
+      for (int dd = 0; dd < 32; ++dd) {
+        if (d0 + dd < D) {
+          const float* yr = ysm + d0 + dd;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j < k) acc[j] = fmaf(yr[j * D], a[dd], acc[j]);
+        }
+      }
+    }
+    const float cv = CV[c];
+    float* out = Vt + ((size_t)b * Cout + c) * KP;
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      if (j4 * 4 < KP) {
+        float4 r;
+        r.x = j4 * 4 + 0 < k ? acc[j4 * 4 + 0] + cv : 0.f; r.y = j4 * 4 + 1 < k ? acc[j4 * 4 + 1] + cv : 0.f;
+        r.z = j4 * 4 + 2 < k ? acc[j4 * 4 + 2] + cv : 0.f; r.w = j4 * 4 + 3 < k ? acc[j4 * 4 + 3] + cv : 0.f;
+        if (tf32) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
+        reinterpret_cast<float4*>(out)[j4] = r;                   // KP is 16 or 32: rows are 16-byte aligned
+      }
+    }
+    return;
+  }
+  if (blk < nvblk + npos) {
     const int half = p / 2;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (H + W) * KP; i += npos * blockDim.x) {
+    for (int i = (blk - nvblk) * blockDim.x + threadIdx.x; i < (H + W) * KP; i += npos * blockDim.x) {
       const int r = i / KP, j = i % KP;
       const bool is_row = r < H;
       float val;
@@ -356,9 +396,11 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
         const float* kj = kp + (size_t)j * LDK + C;
         float acc = 0.f;
         if (is_row) {
+#pragma unroll 8
           for (int q = 0; q < half; ++q) acc = fmaf(ROW[r * half + q], kj[q], acc);
           acc += kj[p];
         } else {
+#pragma unroll 8
           for (int q = 0; q < half; ++q) acc = fmaf(COL[(r - H) * half + q], kj[half + q], acc);
         }
         val = acc;
@@ -369,36 +411,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
     return;
   }
   const int nK = KP * C;
-  const int nvblk = Vt ? (Cout + 255) / 256 : 0;                 // V^T role: one thread per channel
-  const int role = blockIdx.x - npos;
-  if (role < nvblk) {
-    // V^T[b, c, :] = (Y[b] . AV[:, c] + CV[c]) for the k latents (zero for the padded ones); AV reads coalesced over c
-    extern __shared__ float ysm[];                                // Y[b]: k x D
-    for (int i = threadIdx.x; i < k * D; i += blockDim.x) ysm[i] = Y[(size_t)b * k * D + i];
-    __syncthreads();
-    const int c = role * 256 + threadIdx.x;
-    if (c >= Cout) return;
-    float acc[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-    for (int dd = 0; dd < D; ++dd) {
-      const float a = AV[(size_t)dd * Cout + c];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) if (j < k) acc[j] = fmaf(ysm[j * D + dd], a, acc[j]);
-    }
-    const float cv = CV[c];
-    float* out = Vt + ((size_t)b * Cout + c) * KP;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (j < KP) {
-        float r = j < k ? acc[j] + cv : 0.f;
-        out[j] = tf32 ? round_tf32(r) : r;
-      }
-    }
-    return;
-  }
-  const int stride = (gridDim.x - npos - nvblk) * blockDim.x;
-  for (int i = (role - nvblk) * blockDim.x + threadIdx.x; i < nK; i += stride) {
+  const int stride = (gridDim.y - npos - nvblk) * blockDim.x;
+  for (int i = (blk - nvblk - npos) * blockDim.x + threadIdx.x; i < nK; i += stride) {
     const int j = i / C, c = i % C;
     float v = j < k ? kp[(size_t)j * LDK + c] : 0.f;
     if (in_scale) v *= in_scale[(size_t)b * in_ld + c];      // x_in = x * in_scale: (x*d).K' == x.(K'*d)
@@ -417,8 +431,8 @@ int prologue(const Layout& L, const gf_attn_desc* d, const float* Y, const float
                  f + L.f_CK, L.LDK, L.k)))
     return rc;
   const int npos = ((L.H + L.W) * L.KP + 1023) / 1024;
-  const int nblk = npos + (L.Cout + 255) / 256 + (L.KP * L.C + 256 * 4 - 1) / (256 * 4);
-  finalize_kernel<<<dim3(nblk, L.B), 256, (size_t)L.k * L.D * sizeof(float), st>>>(ws + L.w_KPALL, Y, f + L.f_AV, f + L.f_CV, f + L.f_ROW, f + L.f_COL,
+  const int nblk = npos + (L.Cout + 255) / 256 + (L.KP * L.C + 256 * 8 - 1) / (256 * 8);
+  finalize_kernel<<<dim3(L.B, nblk), 256, (size_t)L.k * L.D * sizeof(float), st>>>(ws + L.w_KPALL, Y, f + L.f_AV, f + L.f_CV, f + L.f_ROW, f + L.f_COL,
                                                    ws + L.w_Kp, ws + L.w_Vt, ws + L.w_Rt, ws + L.w_Ct,
                                                    L.H, L.W, L.C, L.k, L.D, L.p, L.KP, L.Cout, L.LDK, tf32, npos, in_scale, in_scale_ld);
   GF_LAUNCH_OK();
@@ -433,8 +447,8 @@ int duplex_tables(const Layout& L, const gf_attn_desc* d, const float* Y, const 
                  f + L.f_CM, L.LDK, L.k)))
     return rc;
   const int npos = ((L.H + L.W) * L.KP + 1023) / 1024;
-  const int nblk = npos + (L.KP * L.C + 256 * 4 - 1) / (256 * 4);
-  finalize_kernel<<<dim3(nblk, L.B), 256, 0, st>>>(ws + L.w_MALL, Y, nullptr, nullptr, f + L.f_ROW, f + L.f_COL,
+  const int nblk = npos + (L.KP * L.C + 256 * 8 - 1) / (256 * 8);
+  finalize_kernel<<<dim3(L.B, nblk), 256, 0, st>>>(ws + L.w_MALL, Y, nullptr, nullptr, f + L.f_ROW, f + L.f_COL,
                                                    ws + L.w_M, nullptr, ws + L.w_Rt2, ws + L.w_Ct2,
                                                    L.H, L.W, L.C, L.k, L.D, L.p, L.KP, L.Cout, L.LDK, tf32, npos, nullptr, 0);
   GF_LAUNCH_OK();
