@@ -44,6 +44,7 @@ struct Params {
   int drain_each_tile;       // 1: release every slab at tile end (ring barely larger than a tile)
   long long total_tiles;
   int tiles_per_image;
+  int rows;                  // token rows per tile: TILE, or n when an image is smaller than a tile (8x8 grid)
   // fused epilogue (gf_attn_postop)
   const float* pbias; const float* pnoise; const float* pstrength; long long pnoise_bstride; int pact; float pgain; int has_post;
   const float* in_scale; const float* post_scale; int in_ld, post_ld;   // per-(b,c) load-side / store-side scales
@@ -149,14 +150,14 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           prev_b = b;
           ++img_changes;
         }
-        const int row0 = (int)(tile * TILE);
+        const int row0 = (int)(tile * P.rows);
         for (int ss = 0; ss < SPT; ++ss, ++ctr) {
           const int s = ss % NS;                     // two-pass: the same slabs are fetched again for the epilogue
           const int stage = (int)(ctr % (uint32_t)nst);
           const uint32_t phase = (ctr / (uint32_t)nst) & 1u;
           mbar_wait(smem_u32(&bars->slab_empty[stage]), phase ^ 1u);
           const uint32_t bar = smem_u32(&bars->slab_full[stage]);
-          mbar_expect_tx(bar, SLAB_BYTES);
+          mbar_expect_tx(bar, (uint32_t)P.rows * 128u);     // short tile: rows >= P.rows of the slab stay stale (never stored)
           tma_load_2d(s_ring + stage * SLAB_BYTES, &tmX, bar, s * SLAB_CH, row0);
         }
       }
@@ -250,7 +251,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const int b = (int)(tile / P.tiles_per_image);
       const int buf = (int)(it & 1);
       const uint32_t bphase = (it >> 1) & 1u;
-      const long long tok = (tile % P.tiles_per_image) * TILE + row;      // token index inside the image
+      const long long tok = min((tile % P.tiles_per_image) * P.rows + row, (long long)P.n - 1);   // token inside the image (clamped: rows past a short tile)
       // positional logits of this token (issued first: their L2 latency hides behind the statistics)
       float sv[KP];
       {
@@ -318,7 +319,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const float inv = 1.f / den;
 #pragma unroll
       for (int j = 0; j < KP; ++j) sv[j] *= inv;
-      if (P.att) {
+      if (P.att && row < P.rows) {
         float* a = P.att + ((size_t)b * P.n + tok) * P.k;
 #pragma unroll
         for (int j = 0; j < KP; ++j) if (j < P.k) a[j] = sv[j];
@@ -363,7 +364,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const uint32_t bphase = (it >> 1) & 1u;
       float pnz = 0.f;                               // post-op: per-token noise value
       if (P.has_post && P.pnoise) {
-        const long long tokp = (tile % P.tiles_per_image) * TILE + row;
+        const long long tokp = min((tile % P.tiles_per_image) * P.rows + row, (long long)P.n - 1);
         pnz = __ldg(P.pnoise + (size_t)b * P.pnoise_bstride + tokp) * (P.pstrength ? __ldg(P.pstrength) : 1.f);
       }
       // ---- row statistics from the row warps
@@ -423,7 +424,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         fence_proxy_async();                       // generic-proxy writes -> visible to the TMA (async proxy)
         named_bar_sync(2 + g, 128);
         if (leader) {
-          tma_store_2d(&tmO, s_ring + stage * SLAB_BYTES, s * SLAB_CH, (int)(tile * TILE));
+          tma_store_2d(&tmO, s_ring + stage * SLAB_BYTES, s * SLAB_CH, (int)(tile * P.rows));
           tma_commit();
           if (pending_stage >= 0) {
             tma_wait_read1();                      // the previous store has finished reading its slab
@@ -470,8 +471,9 @@ static int launch(const Layout& L, const gf_attn_desc* d, const float* X, float*
   CUtensorMap tmX, tmO, tmK, tmV;
   int rc;
   const uint64_t rows = (uint64_t)L.B * L.n;
-  if ((rc = make_map(&tmX, X, rows, L.C, TILE, SLAB_CH, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = make_map(&tmO, Xout, rows, L.C, TILE, SLAB_CH, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  const int trows = L.n < TILE ? L.n : TILE;                  // one image per tile when the grid is smaller than a tile
+  if ((rc = make_map(&tmX, X, rows, L.C, trows, SLAB_CH, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map(&tmO, Xout, rows, L.C, trows, SLAB_CH, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map(&tmK, ws + L.w_Kp, (uint64_t)L.B * KP, L.C, KP, SLAB_CH, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   const uint32_t vrows = CF::COUT < 256 ? CF::COUT : 256;
   if ((rc = make_map(&tmV, ws + L.w_Vt, (uint64_t)L.B * CF::COUT, KP, vrows, KP, KP == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
@@ -484,7 +486,8 @@ static int launch(const Layout& L, const gf_attn_desc* d, const float* X, float*
   // across a tile boundary that is only safe when the next tile never needs that slot: single-pass with nst >= NS + 2.
   // A two-pass tile wraps the ring several times, so it always drains at tile end.
   P.drain_each_tile = TWO ? 1 : (nst < NS + 2 ? 1 : 0);
-  P.tiles_per_image = L.n / TILE;
+  P.tiles_per_image = (L.n + TILE - 1) / TILE;
+  P.rows = trows;
   P.total_tiles = (long long)L.B * P.tiles_per_image;
   P.has_post = post ? 1 : 0;
   P.pbias = post ? post->bias : nullptr; P.pnoise = post ? post->noise : nullptr; P.pstrength = post ? post->strength : nullptr;
@@ -546,7 +549,7 @@ bool tc_supported(const Layout& L, const gf_attn_desc* d) {
   static const bool disabled = getenv("GF_DISABLE_TC") != nullptr;
   if (disabled) return false;
   if (L.C != 64 && L.C != 128 && L.C != 256 && L.C != 512) return false;
-  if (L.n % tc::TILE != 0) return false;
+  if (L.n % tc::TILE != 0 && !(L.n < tc::TILE && L.n % 8 == 0)) return false;   // whole tiles, or one short tile per image
   if (d->norm != GF_NORM_LAYER && d->norm != GF_NORM_NONE) return false;
   if ((long long)L.B * L.n > 0x7fffffffll) return false;
   const int limit = tc::device_smem_optin();

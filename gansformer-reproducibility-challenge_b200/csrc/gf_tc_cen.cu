@@ -169,7 +169,7 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       for (int s = 0; s < NS; ++s) tma_load_2d(s_m + s * (KP * 128), &tmM, mb, s * SLAB_CH, b * KP);
       int stage = 0; uint32_t ph = 0;
       for (int it = 0; it < ntiles; ++it) {
-        const int row0 = (b * P.tiles_per_image + tile_beg + it) * TILE;
+        const int row0 = b * P.n + (tile_beg + it) * TILE;       // short image (n < TILE): the box runs into the next image, masked below
         for (int s = 0; s < NS; ++s) {
           mbar_wait(bar(&bars->empty1[stage]), ph ^ 1u);
           const uint32_t fb = bar(&bars->full1[stage]);
@@ -184,7 +184,7 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     if (lane == 0) {
       int stage = 0; uint32_t ph = 0;
       for (int it = 0; it < ntiles; ++it) {
-        const int row0 = (b * P.tiles_per_image + tile_beg + it) * TILE;
+        const int row0 = b * P.n + (tile_beg + it) * TILE;
         for (int hg = 0; hg < NHG; ++hg) {
           mbar_wait(bar(&bars->empty2[stage]), ph ^ 1u);
           const uint32_t fb = bar(&bars->full2[stage]);
@@ -262,7 +262,7 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     const int rtid = (warp - 2) * 32 + lane;                        // 0..127 inside the row-warp group
     constexpr float LOG2E = 1.4426950408889634f;
     auto load_pos = [&](int it, float* dst) {
-      const int tok = (tile_beg + it) * TILE + row;
+      const int tok = min((tile_beg + it) * TILE + row, P.n - 1);   // clamped: rows past a short image are masked
       const int h = tok / P.W, w = tok - h * P.W;
       const float4* rt = reinterpret_cast<const float4*>(P.Rt + ((size_t)b * P.H + h) * KP);
       const float4* ct = reinterpret_cast<const float4*>(P.Ct + ((size_t)b * P.W + w) * KP);
@@ -295,9 +295,10 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       if (lane == 0) mbar_arrive(bar(&bars->s_free[buf]));          // GEMM1 of tile it+2 may overwrite S[buf]
       // t_j = (logit - reference) * log2(e); the trigger test needs only its maximum over this thread's latents
       float ex = -INFINITY;
+      const bool valid = (tile_beg + it) * TILE + row < P.n;        // false only for the rows past a short image: E = 0
 #pragma unroll
       for (int j = 0; j < KP; ++j) {
-        sv[j] = (sv[j] + pos[j]) * LOG2E;                           // logits in log2 units (padded latents: -inf)
+        sv[j] = valid ? (sv[j] + pos[j]) * LOG2E : -INFINITY;                           // logits in log2 units (padded latents: -inf)
         ex = fmaxf(ex, sv[j] - ml[j]);                              // first tile: +inf -> trigger
       }
       if (it + 1 < ntiles) load_pos(it + 1, pos);                   // prefetch: consumed one tile later
@@ -441,7 +442,7 @@ static int launch(const Layout& L, const float* X, float* ws, cudaStream_t st) {
   if ((rc = make_map(&tmM, ws + L.w_M, (uint64_t)L.B * KP, L.C, KP, SLAB_CH, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   Params P;
   P.Rt = ws + L.w_Rt2; P.Ct = ws + L.w_Ct2; P.part = ws + L.w_PART;
-  P.n = L.n; P.H = L.H; P.W = L.W; P.k = L.k; P.nsplit = L.nsplit_cen; P.tiles_per_image = L.n / TILE;
+  P.n = L.n; P.H = L.H; P.W = L.W; P.k = L.k; P.nsplit = L.nsplit_cen; P.tiles_per_image = (L.n + TILE - 1) / TILE;
   P.nst1 = n1; P.nst2 = n2;
   const int smem_bytes = CF::FIXED_BYTES + n1 * SLAB_BYTES + n2 * HG_BYTES + 1024;
   if (const char* dbg = getenv("GF_DEBUG_PTR")) tc::set_debug_buffer(reinterpret_cast<unsigned int*>(strtoull(dbg, nullptr, 0)));
@@ -461,7 +462,8 @@ bool tc_centroid_supported(const Layout& L, const gf_attn_desc* d) {
   static const bool disabled = getenv("GF_DISABLE_TC") != nullptr || getenv("GF_DISABLE_TC_CENTROID") != nullptr;
   if (disabled || (d->flags & GF_FLAG_FP32_EXACT)) return false;
   if (L.C != 64 && L.C != 128 && L.C != 256 && L.C != 512) return false;   // C = 512: two CTAs share the channels
-  if (L.n % tcc::TILE != 0 || L.B > 65535) return false;
+  if ((L.n % tcc::TILE != 0 && !(L.n < tcc::TILE && L.n % 8 == 0)) || L.B > 65535) return false;
+  if ((long long)L.B * L.n > 0x7fffffffll) return false;
   const int limit = tc::device_smem_optin();
   const int ns = L.C / 32;
   if (L.KP == 16) return ns == 2 ? tcc::fits<16, 2>(limit) : ns == 4 ? tcc::fits<16, 4>(limit) : ns == 8 ? tcc::fits<16, 8>(limit) : tcc::fits<16, 16>(limit);

@@ -167,6 +167,29 @@ def test_duplex_layer_vs_oracle(gf, cuda_dev, shape, exact):
     assert (out2 - out).abs().max() <= 1e-6 * max(1.0, out.abs().max().item())
 
 
+@pytest.mark.parametrize("duplex", [False, True], ids=["simplex", "duplex"])
+@pytest.mark.parametrize("C,H,W,k,B,integration", [(512, 8, 8, 32, 5, "mul"),     # res-8 layers of config 3: one 64-token image per tile
+                                                    (512, 8, 8, 16, 33, "both"),    # config 2, more images than a wave of two-pass CTAs needs
+                                                    (128, 4, 8, 8, 3, "add"),       # n = 32
+                                                    (64, 8, 8, 16, 150, "mul")])    # more short tiles than SMs
+def test_short_tiles_small_grid(gf, cuda_dev, C, H, W, k, B, integration, duplex):
+    """Grids smaller than one 128-token tile (8x8, 4x8) run on the tensor path with one image per tile: rows past the
+    image are never stored (stage T) / carry zero weight (pass A); the last image's box runs past the tensor (TMA zero fill)."""
+    D = p = 32
+    g = torch.Generator().manual_seed(C + B + k)
+    x = torch.randn(B, C, H, W, generator=g, dtype=torch.float64) * 1.2 + 0.1
+    y = torch.randn(B, k, D, generator=g, dtype=torch.float64)
+    w = ob.init_params(C, D, k, p, integration, duplex, seed=19, bias_std=0.3)
+    ref, ratt, rcen = ob.transformer_layer(x, y, w, integration=integration, duplex=duplex, return_att=True)
+    out, att, cen, path = run_layer(gf, cuda_dev, x, y, w, integration=integration, norm="layer", duplex=duplex, use_pos=True, exact=False)
+    assert path == "tcgen05_tf32"
+    check_close(out, ref.permute(0, 2, 3, 1), path, "short-tiles")
+    assert (att.cpu().double() - ratt).abs().max() <= 5e-3
+    if duplex:
+        assert gf._lib.last_centroid_path() == "tcgen05_tf32"
+        check_close(cen, rcen, "tcgen05_tf32", "short-tiles/centroids")
+
+
 def test_inplace_and_no_att(gf, cuda_dev):
     C, H, W, k, D, p = 128, 16, 16, 16, 32, 32
     g = torch.Generator().manual_seed(5)
