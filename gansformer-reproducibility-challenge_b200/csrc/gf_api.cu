@@ -158,7 +158,8 @@ int gf_attn_duplex_fwd_ex(const gf_attn_desc* desc, const float* X, const float*
   cudaStream_t st = (cudaStream_t)stream;
   if (!(desc->flags & GF_FLAG_CENTROIDS_IN)) {
     if ((rc = duplex_tables(L, desc, Y, folded, ws, st))) return rc;
-    if (tc_centroid_supported(L, desc)) {
+    const bool cen_tc = tc_centroid_supported(L, desc);
+    if (cen_tc) {
       if ((rc = centroid_pass_tc(L, desc, X, ws, st))) return rc;
       if ((rc = centroid_merge(L, ws, st))) return rc;
       set_centroid_path(GF_PATH_TCGEN05_TF32);
@@ -168,7 +169,7 @@ int gf_attn_duplex_fwd_ex(const gf_attn_desc* desc, const float* X, const float*
     }
     // centroids = Xbar @ Wv2_e + bv2
     if ((rc = gemm(st, L.B * L.k, L.C, L.C, ws + L.w_XBAR, L.C, false, folded + L.f_WV2, L.C, false, centroids_inout, L.C, 1.f,
-                   nullptr, 0, 1, folded + L.f_BV2)))
+                   nullptr, 0, 1, folded + L.f_BV2, cen_tc)))
       return rc;
   }
   if ((rc = prologue(L, desc, Y, centroids_inout, L.C, folded, ws, st))) return rc;

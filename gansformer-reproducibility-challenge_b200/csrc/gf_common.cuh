@@ -66,7 +66,12 @@ int prologue(const Layout& L, const gf_attn_desc* d, const float* Y, const float
 int duplex_tables(const Layout& L, const gf_attn_desc* d, const float* Y, const float* folded, float* ws, cudaStream_t st);
 // C[M,N] = alpha * opA(A) opB(B) + E[(m % emod), n] + v[n]
 int gemm(cudaStream_t st, int M, int N, int K, const float* A, int lda, bool ta, const float* B, int ldb, bool tb,
-         float* Cm, int ldc, float alpha, const float* E = nullptr, int lde = 0, int emod = 1, const float* v = nullptr);
+         float* Cm, int ldc, float alpha, const float* E = nullptr, int lde = 0, int emod = 1, const float* v = nullptr,
+         bool allow_tf32 = false);
+// tcgen05 TF32 version for dense row-major operands (gf_tc_gemm.cu); gemm() routes to it when allow_tf32 and the shape fits
+bool gemm_tc_ok(int M, int N, int K, const float* A, const float* B, const float* Cm, int ldc);
+int gemm_tc(cudaStream_t st, int M, int N, int K, const float* A, const float* B, float* Cm, int ldc, float alpha,
+            const float* E, int lde, int emod, const float* v);
 
 // ---- stage T kernels ----------------------------------------------------------------------------------
 int token_pass_simt(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, const gf_attn_postop* post, cudaStream_t st);

@@ -214,8 +214,10 @@ __global__ void __launch_bounds__(256) gemm64_kernel(int M, int N, int K, const 
 }
 
 int gemm(cudaStream_t st, int M, int N, int K, const float* A, int lda, bool ta, const float* B, int ldb, bool tb,
-         float* Cm, int ldc, float alpha, const float* E, int lde, int emod, const float* v) {
+         float* Cm, int ldc, float alpha, const float* E, int lde, int emod, const float* v, bool allow_tf32) {
   if (M <= 0 || N <= 0) return GF_OK;
+  if (allow_tf32 && !ta && !tb && lda == K && ldb == N && gemm_tc_ok(M, N, K, A, B, Cm, ldc))
+    return gemm_tc(st, M, N, K, A, B, Cm, ldc, alpha, E, lde, emod, v);
   if (!ta && !tb && M >= 256 && N >= 64 && K >= 64 && (lda & 3) == 0 && (ldb & 3) == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0) {
     if (emod < 1) emod = 1;
     gemm64_kernel<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, st>>>(M, N, K, A, lda, B, ldb, Cm, ldc, alpha, E, lde, emod, v);
@@ -428,7 +430,7 @@ int prologue(const Layout& L, const gf_attn_desc* d, const float* Y, const float
   const int tf32 = (!(d->flags & GF_FLAG_FP32_EXACT) && tc_supported(L, d)) ? 1 : 0;
   // KPALL [B*k, LDK] = key_source @ AK + CK
   if ((rc = gemm(st, L.B * L.k, L.LDK, kdim, key_source, kdim, false, f + L.f_AK, L.LDK, false, ws + L.w_KPALL, L.LDK, 1.f,
-                 f + L.f_CK, L.LDK, L.k)))
+                 f + L.f_CK, L.LDK, L.k, nullptr, tf32 != 0 && kdim >= 64)))   // K = D = 32 (simplex): tiny, stays fp32
     return rc;
   const int npos = ((L.H + L.W) * L.KP + 1023) / 1024;
   const int nblk = npos + (L.Cout + 255) / 256 + (L.KP * L.C + 256 * 8 - 1) / (256 * 8);
