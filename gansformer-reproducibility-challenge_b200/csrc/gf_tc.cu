@@ -247,35 +247,43 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const int sw = row & 7;
     const uint32_t row_off = (uint32_t)row * 128u;
     uint32_t it = 0;
+    int b = (int)(tile_beg / P.tiles_per_image);
+    int t_in_img = (int)(tile_beg - (long long)b * P.tiles_per_image);
+    int stage = 0; uint32_t ph = 0;                // ring walker: every fill, in slot order
+    // Positional logits of (image bb, tile tt), row `row`.  The column part (per token) is fetched one tile ahead, the row part
+    // (the same line for the whole tile when W >= 128) at the top of its tile and consumed after the statistics sweep, so
+    // that neither L2 latency is exposed; KP = 32 has no registers for prefetching both a tile ahead.
+    float4 pr[KP / 4], pc[KP / 4];
+    auto pos_ptrs = [&](int bb, int tt, const float4*& rt, const float4*& ct) {
+      const int tok = min(tt * P.rows + row, P.n - 1);               // clamped: rows past a short tile
+      const int h = tok / P.W, w = tok - h * P.W;
+      rt = reinterpret_cast<const float4*>(P.Rt + ((size_t)bb * P.H + h) * KP);
+      ct = reinterpret_cast<const float4*>(P.Ct + ((size_t)bb * P.W + w) * KP);
+    };
+    const float4 *rt_cur = nullptr, *ct_nxt = nullptr;
+    if (tile_beg < tile_end) {
+      pos_ptrs(b, t_in_img, rt_cur, ct_nxt);
+#pragma unroll
+      for (int j4 = 0; j4 < KP / 4; ++j4) pc[j4] = __ldg(ct_nxt + j4);
+    }
     for (long long tile = tile_beg; tile < tile_end; ++tile, ++it) {
-      const int b = (int)(tile / P.tiles_per_image);
       const int buf = (int)(it & 1);
       const uint32_t bphase = (it >> 1) & 1u;
-      const long long tok = min((tile % P.tiles_per_image) * P.rows + row, (long long)P.n - 1);   // token inside the image (clamped: rows past a short tile)
-      // positional logits of this token (issued first: their L2 latency hides behind the statistics)
-      float sv[KP];
-      {
-        const int h = (int)(tok / P.W), w = (int)(tok % P.W);
-        const float4* rt = reinterpret_cast<const float4*>(P.Rt + ((size_t)b * P.H + h) * KP);
-        const float4* ct = reinterpret_cast<const float4*>(P.Ct + ((size_t)b * P.W + w) * KP);
+      const int tok = min(t_in_img * P.rows + row, P.n - 1);         // token inside the image (for the attention-map store)
 #pragma unroll
-        for (int j4 = 0; j4 < KP / 4; ++j4) {
-          const float4 r = __ldg(rt + j4), c = __ldg(ct + j4);
-          sv[j4 * 4 + 0] = r.x + c.x; sv[j4 * 4 + 1] = r.y + c.y; sv[j4 * 4 + 2] = r.z + c.z; sv[j4 * 4 + 3] = r.w + c.w;
-        }
-      }
+      for (int j4 = 0; j4 < KP / 4; ++j4) pr[j4] = __ldg(rt_cur + j4);  // consumed after the statistics sweep (fence below)
+      const int b_cur = b;
+      if (++t_in_img == P.tiles_per_image) { t_in_img = 0; ++b; }
       // ---- LayerNorm statistics of the whole row (shifted sums)
       float mean = 0.f, rstd = 1.f;
       if (P.norm_layer || TWO_PASS) {
         float sh = 0.f, sum = 0.f, sumsq = 0.f;
 #pragma unroll 1
         for (int s = 0; s < NS; ++s) {
-          const uint32_t ctr = it * SPT + s;
-          const int stage = (int)(ctr % (uint32_t)nst);
-          mbar_wait(smem_u32(&bars->slab_full[stage]), (ctr / (uint32_t)nst) & 1u);
+          mbar_wait(smem_u32(&bars->slab_full[stage]), ph);
           if (P.norm_layer) {
             const uint8_t* slab = smem + CF::OFF_RING + stage * SLAB_BYTES + row_off;
-            const float4* isc = P.in_scale ? reinterpret_cast<const float4*>(P.in_scale + (size_t)b * P.in_ld + s * SLAB_CH) : nullptr;
+            const float4* isc = P.in_scale ? reinterpret_cast<const float4*>(P.in_scale + (size_t)b_cur * P.in_ld + s * SLAB_CH) : nullptr;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
               float4 x = *reinterpret_cast<const float4*>(slab + ((c ^ sw) << 4));
@@ -290,6 +298,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars->slab_empty[stage]));
           }
+          if (++stage == nst) { stage = 0; ph ^= 1u; }
         }
         if (P.norm_layer) {
           const float md = sum * (1.f / (float)C);
@@ -297,6 +306,22 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           mean = sh + md;
           rstd = rsqrtf(var + 1e-8f);
         }
+      } else {                                       // no statistics pass: skip this tile's fills
+        stage += NS;
+        while (stage >= nst) { stage -= nst; ph ^= 1u; }
+      }
+      // positional logits of this tile; then start the next tile's column-part loads (consumed one iteration later)
+      float sv[KP];
+#pragma unroll
+      for (int j4 = 0; j4 < KP / 4; ++j4) {
+        asm volatile("" : "+f"(pr[j4].x), "+f"(pr[j4].y), "+f"(pr[j4].z), "+f"(pr[j4].w));   // keeps the adds below the sweep
+        sv[j4 * 4 + 0] = pr[j4].x + pc[j4].x; sv[j4 * 4 + 1] = pr[j4].y + pc[j4].y;
+        sv[j4 * 4 + 2] = pr[j4].z + pc[j4].z; sv[j4 * 4 + 3] = pr[j4].w + pc[j4].w;
+      }
+      if (tile + 1 < tile_end) {
+        pos_ptrs(b, t_in_img, rt_cur, ct_nxt);
+#pragma unroll
+        for (int j4 = 0; j4 < KP / 4; ++j4) pc[j4] = __ldg(ct_nxt + j4);
       }
       mbar_wait(smem_u32(&bars->st_free[buf]), bphase ^ 1u);       // epilogue of the tile two iterations back has read its stats
       stats[(buf * TILE + row) * 2 + 0] = mean;
@@ -306,13 +331,15 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       // ---- softmax over the latents: S (TMEM) -> P (TMEM)
       mbar_wait(smem_u32(&bars->s_full[buf]), bphase);
       tc_fence_after();
-      float acc[KP];
-      tmem_ld16(tmem + lane_addr + COL_S + buf * 32, acc);
-      if constexpr (KP == 32) tmem_ld16(tmem + lane_addr + COL_S + buf * 32 + 16, acc + 16);
-      tmem_wait_ld();
       float mx = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < KP; ++j) { sv[j] += acc[j]; mx = fmaxf(mx, sv[j]); }
+      for (int hh = 0; hh < KP / 16; ++hh) {                        // 16 columns at a time: keeps the register peak down
+        float acc[16];
+        tmem_ld16(tmem + lane_addr + COL_S + buf * 32 + hh * 16, acc);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { sv[hh * 16 + j] += acc[j]; mx = fmaxf(mx, sv[hh * 16 + j]); }
+      }
       float den = 0.f;
 #pragma unroll
       for (int j = 0; j < KP; ++j) { sv[j] = exp2f((sv[j] - mx) * 1.4426950408889634f); den += sv[j]; }
@@ -320,7 +347,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
       for (int j = 0; j < KP; ++j) sv[j] *= inv;
       if (P.att && row < P.rows) {
-        float* a = P.att + ((size_t)b * P.n + tok) * P.k;
+        float* a = P.att + ((size_t)b_cur * P.n + tok) * P.k;
 #pragma unroll
         for (int j = 0; j < KP; ++j) if (j < P.k) a[j] = sv[j];
       }
@@ -342,8 +369,8 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       if (TWO_PASS) {   // observe the pass-2 fills too (see the MMA warp): keeps this thread's parity bookkeeping in step
 #pragma unroll 1
         for (int s = 0; s < NS; ++s) {
-          const uint32_t c2 = it * SPT + NS + s;
-          mbar_wait(smem_u32(&bars->slab_full[(int)(c2 % (uint32_t)nst)]), (c2 / (uint32_t)nst) & 1u);
+          mbar_wait(smem_u32(&bars->slab_full[stage]), ph);
+          if (++stage == nst) { stage = 0; ph ^= 1u; }
         }
       }
     }
@@ -358,15 +385,18 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const uint32_t row_off = (uint32_t)row * 128u;
     int pending_stage = -1;
     uint32_t it = 0;
+    int b_next = (int)(tile_beg / P.tiles_per_image);
+    int t_in_img = (int)(tile_beg - (long long)b_next * P.tiles_per_image);
     for (long long tile = tile_beg; tile < tile_end; ++tile, ++it) {
-      const int b = (int)(tile / P.tiles_per_image);
+      const int b = b_next;
       const int buf = (int)(it & 1);
       const uint32_t bphase = (it >> 1) & 1u;
       float pnz = 0.f;                               // post-op: per-token noise value
       if (P.has_post && P.pnoise) {
-        const long long tokp = min((tile % P.tiles_per_image) * P.rows + row, (long long)P.n - 1);
+        const int tokp = min(t_in_img * P.rows + row, P.n - 1);
         pnz = __ldg(P.pnoise + (size_t)b * P.pnoise_bstride + tokp) * (P.pstrength ? __ldg(P.pstrength) : 1.f);
       }
+      if (++t_in_img == P.tiles_per_image) { t_in_img = 0; ++b_next; }
       // ---- row statistics from the row warps
       mbar_wait(smem_u32(&bars->st_full[buf]), bphase);
       const float mean = stats[(buf * TILE + row) * 2 + 0], rstd = stats[(buf * TILE + row) * 2 + 1];
