@@ -59,6 +59,7 @@ struct Bars {
   uint64_t s_full[2], p_full[2], p_free[2];
   uint64_t st_full[2], st_free[2];
   uint64_t acc_full[NACC], acc_empty[NACC];
+  uint64_t sc_full[2], sc_free[2];       // per-image load/store-side scale vectors (double-buffered by image parity)
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -76,7 +77,9 @@ struct Cfg {
   static constexpr int OFF_V = OFF_KP + KP_BYTES;
   static constexpr int OFF_STATS = OFF_V + V_BYTES;
   static constexpr int OFF_PBIAS = OFF_STATS + STATS_BYTES;
-  static constexpr int OFF_BARS = OFF_PBIAS + PBIAS_BYTES;
+  static constexpr int SCALE_BYTES = 2 * 2 * C * 4;      // [image parity]{in_scale, post_scale}[C]
+  static constexpr int OFF_SCALE = OFF_PBIAS + PBIAS_BYTES;
+  static constexpr int OFF_BARS = OFF_SCALE + SCALE_BYTES;
   static constexpr int OFF_RING = (OFF_BARS + (int)sizeof(Bars) + 1023) / 1024 * 1024;
   static constexpr int FIXED_BYTES = OFF_RING;
 };
@@ -96,6 +99,9 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   Bars* bars = reinterpret_cast<Bars*>(smem + CF::OFF_BARS);
   float* stats = reinterpret_cast<float*>(smem + CF::OFF_STATS);
   float* pbias_s = reinterpret_cast<float*>(smem + CF::OFF_PBIAS);
+  const float* scale_s = reinterpret_cast<const float*>(smem + CF::OFF_SCALE);
+  const uint32_t s_scale = s_base + CF::OFF_SCALE;
+  const bool has_scales = P.in_scale != nullptr || P.post_scale != nullptr;
   if (P.has_post)
     for (int i = threadIdx.x; i < C; i += NUM_THREADS) pbias_s[i] = P.pbias ? P.pbias[i] : 0.f;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
@@ -119,6 +125,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       mbar_init(smem_u32(&bars->st_free[i]), 8);
     }
     for (int i = 0; i < NACC; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->sc_full[i]), 1); mbar_init(smem_u32(&bars->sc_free[i]), 12); }   // 4 row + 8 epilogue warps
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -147,6 +154,16 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           constexpr int VROWS = CF::COUT < 256 ? CF::COUT : 256;
 #pragma unroll
           for (int r0 = 0; r0 < CF::COUT; r0 += VROWS) tma_load_2d(s_v + r0 * CF::V_ROW_BYTES, &tmV, bar, 0, b * CF::COUT + r0);
+          if (has_scales) {
+            // per-(b,c) scale vectors of this image -> shared memory (the consumers read them once per slab: from global
+            // that was 8-16 dependent L2 round trips per slab on the critical path of the fused post-op)
+            const int par = img_changes & 1;
+            mbar_wait(smem_u32(&bars->sc_free[par]), (uint32_t)(((img_changes >> 1) & 1) ^ 1));
+            const uint32_t sb = smem_u32(&bars->sc_full[par]);
+            mbar_expect_tx(sb, (uint32_t)((P.in_scale ? C * 4 : 0) + (P.post_scale ? C * 4 : 0)));
+            if (P.in_scale) bulk_load_1d(s_scale + par * 2 * C * 4, P.in_scale + (size_t)b * P.in_ld, C * 4, sb);
+            if (P.post_scale) bulk_load_1d(s_scale + (par * 2 + 1) * C * 4, P.post_scale + (size_t)b * P.post_ld, C * 4, sb);
+          }
           prev_b = b;
           ++img_changes;
         }
@@ -260,6 +277,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       rt = reinterpret_cast<const float4*>(P.Rt + ((size_t)bb * P.H + h) * KP);
       ct = reinterpret_cast<const float4*>(P.Ct + ((size_t)bb * P.W + w) * KP);
     };
+    int imgc = 0;                                  // images this CTA has started (parity selects the scale buffer)
     const float4 *rt_cur = nullptr, *ct_nxt = nullptr;
     if (tile_beg < tile_end) {
       pos_ptrs(b, t_in_img, rt_cur, ct_nxt);
@@ -272,8 +290,11 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const int tok = min(t_in_img * P.rows + row, P.n - 1);         // token inside the image (for the attention-map store)
 #pragma unroll
       for (int j4 = 0; j4 < KP / 4; ++j4) pr[j4] = __ldg(rt_cur + j4);  // consumed after the statistics sweep (fence below)
-      const int b_cur = b;
+      const bool img_first = t_in_img == 0 || tile == tile_beg;
       if (++t_in_img == P.tiles_per_image) { t_in_img = 0; ++b; }
+      const bool img_last = t_in_img == 0;
+      const int spar = imgc & 1;
+      if (has_scales && img_first) mbar_wait(smem_u32(&bars->sc_full[spar]), (uint32_t)((imgc >> 1) & 1));
       // ---- LayerNorm statistics of the whole row (shifted sums)
       float mean = 0.f, rstd = 1.f;
       if (P.norm_layer || TWO_PASS) {
@@ -283,11 +304,11 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           mbar_wait(smem_u32(&bars->slab_full[stage]), ph);
           if (P.norm_layer) {
             const uint8_t* slab = smem + CF::OFF_RING + stage * SLAB_BYTES + row_off;
-            const float4* isc = P.in_scale ? reinterpret_cast<const float4*>(P.in_scale + (size_t)b_cur * P.in_ld + s * SLAB_CH) : nullptr;
+            const float4* isc = P.in_scale ? reinterpret_cast<const float4*>(scale_s + spar * 2 * C + s * SLAB_CH) : nullptr;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
               float4 x = *reinterpret_cast<const float4*>(slab + ((c ^ sw) << 4));
-              if (isc) { const float4 d = __ldg(isc + c); x.x *= d.x; x.y *= d.y; x.z *= d.z; x.w *= d.w; }   // warp-uniform address
+              if (isc) { const float4 d = isc[c]; x.x *= d.x; x.y *= d.y; x.z *= d.z; x.w *= d.w; }   // shared-memory broadcast
               if (s == 0 && c == 0) sh = x.x;
               const float d0 = x.x - sh, d1 = x.y - sh, d2 = x.z - sh, d3 = x.w - sh;
               sum += (d0 + d1) + (d2 + d3);
@@ -310,6 +331,11 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         stage += NS;
         while (stage >= nst) { stage -= nst; ph ^= 1u; }
       }
+      if (has_scales && img_last) {                  // this warp is done with the image's scale vectors
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->sc_free[spar]));
+      }
+      if (img_last) ++imgc;
       // positional logits of this tile; then start the next tile's column-part loads (consumed one iteration later)
       float sv[KP];
 #pragma unroll
@@ -347,7 +373,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
       for (int j = 0; j < KP; ++j) sv[j] *= inv;
       if (P.att && row < P.rows) {
-        float* a = P.att + ((size_t)b_cur * P.n + tok) * P.k;
+        float* a = P.att + ((size_t)(img_last ? b - 1 : b) * P.n + tok) * P.k;
 #pragma unroll
         for (int j = 0; j < KP; ++j) if (j < P.k) a[j] = sv[j];
       }
@@ -385,6 +411,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const uint32_t row_off = (uint32_t)row * 128u;
     int pending_stage = -1;
     uint32_t it = 0;
+    int imgc = 0;
     int b_next = (int)(tile_beg / P.tiles_per_image);
     int t_in_img = (int)(tile_beg - (long long)b_next * P.tiles_per_image);
     for (long long tile = tile_beg; tile < tile_end; ++tile, ++it) {
@@ -396,7 +423,11 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const int tokp = min(t_in_img * P.rows + row, P.n - 1);
         pnz = __ldg(P.pnoise + (size_t)b * P.pnoise_bstride + tokp) * (P.pstrength ? __ldg(P.pstrength) : 1.f);
       }
+      const bool img_first = t_in_img == 0 || tile == tile_beg;
       if (++t_in_img == P.tiles_per_image) { t_in_img = 0; ++b_next; }
+      const bool img_last = t_in_img == 0;
+      const int spar = imgc & 1;
+      if (has_scales && img_first) mbar_wait(smem_u32(&bars->sc_full[spar]), (uint32_t)((imgc >> 1) & 1));
       // ---- row statistics from the row warps
       mbar_wait(smem_u32(&bars->st_full[buf]), bphase);
       const float mean = stats[(buf * TILE + row) * 2 + 0], rstd = stats[(buf * TILE + row) * 2 + 1];
@@ -426,13 +457,13 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[a]));
         uint8_t* slab = smem + CF::OFF_RING + stage * SLAB_BYTES + row_off;
-        const float4* isc = P.in_scale ? reinterpret_cast<const float4*>(P.in_scale + (size_t)b * P.in_ld + s * SLAB_CH) : nullptr;
-        const float4* psc = P.post_scale ? reinterpret_cast<const float4*>(P.post_scale + (size_t)b * P.post_ld + s * SLAB_CH) : nullptr;
+        const float4* isc = P.in_scale ? reinterpret_cast<const float4*>(scale_s + spar * 2 * C + s * SLAB_CH) : nullptr;
+        const float4* psc = P.post_scale ? reinterpret_cast<const float4*>(scale_s + (spar * 2 + 1) * C + s * SLAB_CH) : nullptr;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float4* px = reinterpret_cast<float4*>(slab + ((c ^ sw) << 4));
           float4 x = *px;
-          if (isc) { const float4 d = __ldg(isc + c); x.x *= d.x; x.y *= d.y; x.z *= d.z; x.w *= d.w; }
+          if (isc) { const float4 d = isc[c]; x.x *= d.x; x.y *= d.y; x.z *= d.z; x.w *= d.w; }
           float xn0 = fmaf(x.x, rstd, mr), xn1 = fmaf(x.y, rstd, mr), xn2 = fmaf(x.z, rstd, mr), xn3 = fmaf(x.w, rstd, mr);
           if constexpr (MODE == GF_INT_MUL) {
             x.x = xn0 * gv[c * 4 + 0]; x.y = xn1 * gv[c * 4 + 1]; x.z = xn2 * gv[c * 4 + 2]; x.w = xn3 * gv[c * 4 + 3];
@@ -447,7 +478,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             x.x += pnz + pb.x; x.y += pnz + pb.y; x.z += pnz + pb.z; x.w += pnz + pb.w;
             if (P.pact == 1) { x.x = fmaxf(x.x, 0.2f * x.x); x.y = fmaxf(x.y, 0.2f * x.y); x.z = fmaxf(x.z, 0.2f * x.z); x.w = fmaxf(x.w, 0.2f * x.w); }
             x.x *= P.pgain; x.y *= P.pgain; x.z *= P.pgain; x.w *= P.pgain;
-            if (psc) { const float4 q4 = __ldg(psc + c); x.x *= q4.x; x.y *= q4.y; x.z *= q4.z; x.w *= q4.w; }
+            if (psc) { const float4 q4 = psc[c]; x.x *= q4.x; x.y *= q4.y; x.z *= q4.z; x.w *= q4.w; }
           }
           *px = x;
         }
@@ -463,6 +494,11 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           pending_stage = stage;
         }
       }
+      if (has_scales && img_last) {                  // this warp has read the image's scale vectors for the last time
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->sc_free[spar]));
+      }
+      if (img_last) ++imgc;
       if (leader && P.drain_each_tile && pending_stage >= 0) {   // small rings: no slab may stay held across tiles
         tma_wait_read0();
         mbar_arrive_n(smem_u32(&bars->slab_empty[pending_stage]), EMPTY_COUNT);
