@@ -414,17 +414,20 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     int imgc = 0;
     int b_next = (int)(tile_beg / P.tiles_per_image);
     int t_in_img = (int)(tile_beg - (long long)b_next * P.tiles_per_image);
+    // post-op noise: one value per token, fetched a tile ahead (its L2 latency sat on the epilogue's critical path)
+    const bool has_noise = P.has_post && P.pnoise != nullptr;
+    const float pstr = (has_noise && P.pstrength) ? __ldg(P.pstrength) : 1.f;
+    float pnz_next = 0.f;
+    if (has_noise && tile_beg < tile_end) pnz_next = __ldg(P.pnoise + (size_t)b_next * P.pnoise_bstride + min(t_in_img * P.rows + row, P.n - 1));
     for (long long tile = tile_beg; tile < tile_end; ++tile, ++it) {
       const int b = b_next;
       const int buf = (int)(it & 1);
       const uint32_t bphase = (it >> 1) & 1u;
-      float pnz = 0.f;                               // post-op: per-token noise value
-      if (P.has_post && P.pnoise) {
-        const int tokp = min(t_in_img * P.rows + row, P.n - 1);
-        pnz = __ldg(P.pnoise + (size_t)b * P.pnoise_bstride + tokp) * (P.pstrength ? __ldg(P.pstrength) : 1.f);
-      }
+      const float pnz = pnz_next * pstr;             // post-op: per-token noise value
       const bool img_first = t_in_img == 0 || tile == tile_beg;
       if (++t_in_img == P.tiles_per_image) { t_in_img = 0; ++b_next; }
+      if (has_noise && tile + 1 < tile_end)
+        pnz_next = __ldg(P.pnoise + (size_t)b_next * P.pnoise_bstride + min(t_in_img * P.rows + row, P.n - 1));
       const bool img_last = t_in_img == 0;
       const int spar = imgc & 1;
       if (has_scales && img_first) mbar_wait(smem_u32(&bars->sc_full[spar]), (uint32_t)((imgc >> 1) & 1));
