@@ -143,6 +143,85 @@ __global__ void __launch_bounds__(256) demod_coef_kernel(const float* __restrict
 
 using namespace gf;
 
+
+// ------------------------------------------------------------------------------------------------------
+// tRGB: 1x1 modulated convolution without demodulation, channels-last input -> planar image
+//   y[b,o,t] = sum_c x[b,t,c] * w[o,c] * styles[b,c] * wscale + bias[o]
+// One warp per 32 tokens: lane l owns the float4 channel chunks l, l+32, ... (its slice of the per-sample weights lives
+// in registers), 4 tokens in flight per step, butterfly reduction, lane i keeps token i -> coalesced planar stores.
+// ------------------------------------------------------------------------------------------------------
+template <int O, int NQ>
+__global__ void __launch_bounds__(256) torgb_kernel(const float4* __restrict__ x, const float* __restrict__ w, const float* __restrict__ styles,
+                                                    int s_ld, const float* __restrict__ bias, float wscale, float* __restrict__ y,
+                                                    int HW, int C4, int tok_per_cta) {
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 wr[O][NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int c4 = lane + q * 32;
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 < C4) s4 = *reinterpret_cast<const float4*>(styles + (size_t)b * s_ld + c4 * 4);
+#pragma unroll
+    for (int o = 0; o < O; ++o) {
+      float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c4 < C4) w4 = *reinterpret_cast<const float4*>(w + (size_t)o * C4 * 4 + c4 * 4);
+      wr[o][q] = make_float4(w4.x * s4.x * wscale, w4.y * s4.y * wscale, w4.z * s4.z * wscale, w4.w * s4.w * wscale);
+    }
+  }
+  const int t_beg = blockIdx.x * tok_per_cta, t_end = min(HW, t_beg + tok_per_cta);
+  const float4* xb = x + (size_t)b * HW * C4;
+  for (int t0 = t_beg + warp * 32; t0 < t_end; t0 += 8 * 32) {
+    float keep[O];
+#pragma unroll
+    for (int o = 0; o < O; ++o) keep[o] = 0.f;
+#pragma unroll 1
+    for (int i0 = 0; i0 < 32; i0 += 4) {
+      float acc[4][O];
+      float4 xv[4][NQ];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = t0 + i0 + u;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int c4 = lane + q * 32;
+          xv[u][q] = (t < t_end && c4 < C4) ? __ldg(xb + (size_t)t * C4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int o = 0; o < O; ++o) {
+          float a = 0.f;
+#pragma unroll
+          for (int q = 0; q < NQ; ++q)
+            a = fmaf(xv[u][q].x, wr[o][q].x, fmaf(xv[u][q].y, wr[o][q].y, fmaf(xv[u][q].z, wr[o][q].z, fmaf(xv[u][q].w, wr[o][q].w, a))));
+          acc[u][o] = a;
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int o = 0; o < O; ++o) acc[u][o] += __shfl_xor_sync(0xffffffffu, acc[u][o], off);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (lane == i0 + u) {
+#pragma unroll
+          for (int o = 0; o < O; ++o) keep[o] = acc[u][o];
+        }
+      }
+    }
+    const int t = t0 + lane;
+    if (t < t_end) {
+#pragma unroll
+      for (int o = 0; o < O; ++o) y[((size_t)b * O + o) * HW + t] = keep[o] + (bias ? bias[o] : 0.f);
+    }
+  }
+}
+
 extern "C" {
 
 int gf_chan_scale_nhwc(const float* x, const float* s, int s_ld, float* y, int B, int HW, int C, void* stream) {
@@ -193,6 +272,27 @@ int gf_demod_coef(const float* styles, int s_ld, const float* wsq, float* d, int
   if (B <= 0 || O <= 0 || I <= 0 || s_ld < I) { set_error("gf_demod_coef: bad shape"); return GF_ERR_INVALID; }
   const long long warps = (long long)B * O;
   demod_coef_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(styles, wsq, d, B, O, I, eps, s_ld);
+  GF_LAUNCH_OK();
+  return GF_OK;
+}
+
+int gf_torgb_nhwc(const float* x, const float* w, const float* styles, int s_ld, const float* bias, float wscale, float* y,
+                  int B, int HW, int C, void* stream) {
+  if (!x || !w || !styles || !y) { set_error("gf_torgb_nhwc: null pointer"); return GF_ERR_INVALID; }
+  if (B <= 0 || HW <= 0 || C <= 0 || (C & 3) || C > 512 || s_ld < C || (s_ld & 3) || B > 65535) {
+    set_error("gf_torgb_nhwc: unsupported arguments (C=%d s_ld=%d B=%d)", C, s_ld, B); return GF_ERR_UNSUPPORTED;
+  }
+  const int C4 = C >> 2, nq = (C4 + 31) / 32;
+  const int tok_per_cta = 1024;
+  dim3 grid((HW + tok_per_cta - 1) / tok_per_cta, B);
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (nq) {
+    case 1: torgb_kernel<3, 1><<<grid, 256, 0, st>>>(x4, w, styles, s_ld, bias, wscale, y, HW, C4, tok_per_cta); break;
+    case 2: torgb_kernel<3, 2><<<grid, 256, 0, st>>>(x4, w, styles, s_ld, bias, wscale, y, HW, C4, tok_per_cta); break;
+    case 3: torgb_kernel<3, 3><<<grid, 256, 0, st>>>(x4, w, styles, s_ld, bias, wscale, y, HW, C4, tok_per_cta); break;
+    default: torgb_kernel<3, 4><<<grid, 256, 0, st>>>(x4, w, styles, s_ld, bias, wscale, y, HW, C4, tok_per_cta); break;
+  }
   GF_LAUNCH_OK();
   return GF_OK;
 }

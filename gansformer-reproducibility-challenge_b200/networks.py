@@ -214,12 +214,7 @@ class ToRGB(nn.Module):
         activations are read once and no styled copy is written."""
         if styles is None:
             styles = self.affine(w_glob)                                # [B, C]
-        O, I = self.weight.shape[:2]
-        wm = self.weight.reshape(1, O, I) * styles[:, None, :] * (1.0 / math.sqrt(I))      # [B, 3, C]
-        B, C, H, W = x.shape
-        xl = x.permute(0, 2, 3, 1).reshape(B, H * W, C)
-        rgb = torch.matmul(xl, wm.transpose(1, 2)) + self.bias         # [B, HW, 3]
-        return rgb.transpose(1, 2).reshape(B, O, H, W)
+        return ops.torgb(x, self.weight, styles, self.bias)
 
 
 class SynthesisNetwork(nn.Module):

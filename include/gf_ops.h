@@ -41,6 +41,13 @@ int gf_bias_act_nhwc(const float* x, float* y, const float* bias, const float* n
  *   d[b,o] = rsqrt( sum_i styles[b*s_ld + i]^2 * wsq[o,i] + eps ),  wsq[o,i] = sum_{kh,kw} w_eff[o,i,kh,kw]^2 */
 int gf_demod_coef(const float* styles, int s_ld, const float* wsq, float* d, int B, int O, int I, float eps, void* stream);
 
+/* tRGB: 1x1 modulated convolution WITHOUT demodulation from channels-last activations to a planar image,
+ *   y[b,o,t] = sum_c x[b,t,c] * w[o*C + c] * styles[b*s_ld + c] * wscale + bias[o],   o < 3
+ * (modulated_conv2d_layer(..., demodulate=False, kernel=1) + bias of the reference's torgb); x is read once.
+ * C % 4 == 0, C <= 512; s_ld % 4 == 0; bias nullable. */
+int gf_torgb_nhwc(const float* x, const float* w, const float* styles, int s_ld, const float* bias, float wscale, float* y,
+                  int B, int HW, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

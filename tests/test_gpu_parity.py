@@ -421,7 +421,7 @@ def test_native_ops_match_definitions(gf, cuda_dev):
     ops = import_module("gansformer-reproducibility-challenge_b200.ops")
     g = torch.Generator().manual_seed(0)
     f = ops.fir_filter(cuda_dev)
-    for (B, C, H, W) in [(2, 64, 8, 8), (3, 128, 16, 12), (1, 32, 4, 4)]:
+    for (B, C, H, W) in [(2, 64, 8, 8), (3, 128, 16, 12), (1, 32, 4, 4), (2, 512, 40, 36), (2, 256, 33, 32)]:
         x = torch.randn(B, C, 2 * H + 1, 2 * W + 1, generator=g).to(cuda_dev).contiguous(memory_format=torch.channels_last)
         s = torch.rand(B, C, generator=g).to(cuda_dev) + 0.5
         with torch.no_grad():
@@ -447,6 +447,14 @@ def test_native_ops_match_definitions(gf, cuda_dev):
             nzb = torch.randn(B, 1, H, W, generator=g).to(cuda_dev)
             got = ops.bias_act(xs, bias, "linear", noise=nzb, strength=None)
             assert (got - (xs + nzb + bias[None, :, None, None])).abs().max() < 1e-5
+        with torch.no_grad():                                   # tRGB: 1x1 modulated conv, no demodulation, planar output
+            wrgb = torch.randn(3, C, 1, 1, generator=g).to(cuda_dev)
+            brgb = torch.randn(3, generator=g).to(cuda_dev)
+            got = ops.torgb(xs, wrgb, wide[:, 4:4 + C], brgb)
+            want = torch.einsum("bchw,oc,bc->bohw", xs.double(), wrgb.double().reshape(3, C), wide[:, 4:4 + C].double()) / math.sqrt(C) \
+                + brgb.double()[None, :, None, None]
+            assert got.shape == (B, 3, H, W) and got.is_contiguous()
+            assert (got.double() - want).abs().max() <= 1e-5 * max(1.0, want.abs().max().item())
         img = torch.randn(B, 3, H, W, generator=g).to(cuda_dev)
         add = torch.randn(B, 3, 2 * H, 2 * W, generator=g).to(cuda_dev)
         with torch.no_grad():
