@@ -173,6 +173,47 @@ def duplex_attention_probe(device, peak_gbs: float, iters: int = 3):
             "unit": "GB/s", "frac": achieved / peak_gbs, "pass_a_path": cen_path}
 
 
+def train_probe(device, rank, world, steps: int = 2, warmup: int = 1, B: int = 32):
+    """BASELINE configs[3]: one D + one G update of the 256x256 GANsformer (K = 16, simplex) on synthetic reals, batch 32 per
+    GPU, gradients averaged over ranks through one flat all-reduce per network (NCCL).  Attention forward = the CUDA
+    kernels, attention backward = composite torch autograd (autograd.py); convolutions and the discriminator = cuDNN."""
+    import gansformer_b200 as gf
+    from importlib import import_module
+    tr = import_module("gansformer-reproducibility-challenge_b200.training")
+    dist_mod = import_module("gansformer-reproducibility-challenge_b200.dist")
+    torch.manual_seed(0)
+    G = gf.Generator(resolution=RES, components_num=K_LATENTS, latent_size=512).to(device)
+    D = tr.Discriminator(RES).to(device)
+    trainer = tr.Trainer(G, D, world=world)
+    g = torch.Generator().manual_seed(4)
+    z = dist_mod.shard_batch(torch.randn(world * B, K_LATENTS + 1, G.latent_dim, generator=g), rank, world).to(device)
+    reals = dist_mod.shard_batch(torch.rand(world * B, 3, RES, RES, generator=g) * 2 - 1, rank, world).to(device)
+    for _ in range(warmup):
+        trainer.step(z, reals)
+    dist_mod.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ar_ms, ar_bytes, last = 0.0, 0.0, None
+    for _ in range(steps):
+        last = trainer.step(z, reals)
+        ar_ms += last.allreduce_ms
+        ar_bytes = last.allreduce_bytes
+    e1.record()
+    torch.cuda.synchronize()
+    dist_mod.barrier()
+    t = dist_mod.max_over_ranks(e0.elapsed_time(e1) * 1e-3, device=device)
+    out = {"workload": "BASELINE configs[3]: 256x256 G+D training step (logistic NS + lazy R1, Adam, EMA), synthetic reals, "
+                       f"batch {B}/GPU, data-parallel dp{world}", "images_per_s": world * B * steps / t, "ms_per_step": t / steps * 1e3,
+           "global_batch": world * B, "steps": steps, "warmup": warmup, "allreduce_ms_per_step": ar_ms / steps,
+           "allreduce_bytes_per_step": ar_bytes, "loss_g": last.loss_g, "loss_d": last.loss_d,
+           "peak_mem_gb": torch.cuda.max_memory_allocated(device) / 2 ** 30,
+           "backward": "attention: CUDA forward + composite torch-autograd backward; convolutions / discriminator: cuDNN"}
+    del trainer, G, D
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -287,6 +328,7 @@ def run_ours(args):
     dist_mod.barrier()
     t_e2e = dist_mod.max_over_ranks(e0.elapsed_time(e1) * 1e-3, device)
 
+    tp = train_probe(device, rank, world) if args.train_probe else None      # every rank takes part (gradient all-reduce)
     if rank != 0:
         return 0
     peak, peak_src = measured_peak_gbs()
@@ -314,6 +356,8 @@ def run_ours(args):
                              "next-layer style scale (SURVEY row f3), which are not counted in the algorithmic bytes"},
         "clocks": clocks,
     }
+    if tp is not None:
+        line["train_step"] = tp
     if world == 1 and not args.no_duplex_probe:
         line["duplex_attention"] = duplex_attention_probe(device, peak)
     if world == 1 and not args.no_cpu_baseline:
@@ -335,6 +379,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true")
     ap.add_argument("--no-duplex-probe", action="store_true")
+    ap.add_argument("--train-probe", action="store_true", help="also time BASELINE configs[3] (G+D training step) and add a train_step object")
     args = ap.parse_args()
     if args.impl == "ours":
         args.warmup = max(args.warmup, 3)

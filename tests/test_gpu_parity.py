@@ -461,3 +461,25 @@ def test_native_ops_match_definitions(gf, cuda_dev):
             got = ops.upsample2x(img, f, add=add)
         want = ops.upfirdn2d_ref(img.double(), f.double(), up=2, pad=(2, 1, 2, 1), gain=4.0) + add.double()
         assert (got.double() - want).abs().max() < 1e-5
+
+
+def test_training_step_runs_on_gpu(gf, cuda_dev):
+    """SURVEY row f2 / BASELINE configs[3] shape class at 64x64: one D + G update with the attention layers' CUDA forward
+    and composite backward; every generator parameter (attention weights included) receives a finite gradient."""
+    from importlib import import_module
+    tr = import_module("gansformer-reproducibility-challenge_b200.training")
+    torch.manual_seed(0)
+    G = gf.Generator(resolution=64, components_num=8, latent_dim=32, fmap_base=2048, fmap_max=128, mapping_layers=4).to(cuda_dev)
+    D = tr.Discriminator(64, fmap_base=2048, fmap_max=128).to(cuda_dev)
+    trainer = tr.Trainer(G, D)
+    g = torch.Generator().manual_seed(5)
+    z = torch.randn(4, 9, 32, generator=g).to(cuda_dev)
+    reals = (torch.rand(4, 3, 64, 64, generator=g) * 2 - 1).to(cuda_dev)
+    before = {n: p.detach().clone() for n, p in G.named_parameters()}
+    st = trainer.step(z, reals)
+    assert math.isfinite(st.loss_g) and math.isfinite(st.loss_d) and st.r1 > 0
+    moved = [n for n, p in G.named_parameters() if (p.detach() - before[n]).abs().max() > 0]
+    assert any(".attention." in n for n in moved), "attention parameters did not train"
+    assert all(torch.isfinite(p).all() for p in G.parameters())
+    st2 = trainer.step(z, reals)
+    assert math.isfinite(st2.loss_g) and st2.r1 == 0

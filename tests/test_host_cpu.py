@@ -174,3 +174,74 @@ def test_data_parallel_helpers_world2():
         assert ok_union
         assert torch.allclose(grad, expect, atol=1e-6)
         assert nbytes == (6 + 2) * 4 and mx == 2.0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# G/D training step: plumbing on CPU without attention layers (the attention op has no CPU form)
+# ---------------------------------------------------------------------------------------------------------
+def _tiny_gan(gf, seed=0):
+    from importlib import import_module
+    tr = import_module("gansformer-reproducibility-challenge_b200.training")
+    torch.manual_seed(seed)
+    G = gf.Generator(resolution=16, components_num=4, latent_dim=16, fmap_base=256, fmap_max=32, mapping_layers=2, transformer=False)
+    D = tr.Discriminator(16, fmap_base=256, fmap_max=32)
+    return tr, G, D
+
+
+def test_training_step_plumbing(gf):
+    tr, G, D = _tiny_gan(gf)
+    trainer = tr.Trainer(G, D, tr.TrainConfig(noise_mode="const"))
+    g = torch.Generator().manual_seed(3)
+    z, reals = torch.randn(4, 5, 16, generator=g), torch.rand(4, 3, 16, 16, generator=g) * 2 - 1
+    g0 = [p.detach().clone() for p in G.parameters()]
+    d0 = [p.detach().clone() for p in D.parameters()]
+    e0 = [p.detach().clone() for p in trainer.G_ema.parameters()]
+    s1 = trainer.step(z, reals)                    # iteration 0: includes the lazy R1 term
+    s2 = trainer.step(z, reals)
+    for s in (s1, s2):
+        assert all(map(lambda v: v == v and abs(v) < 1e6, (s.loss_g, s.loss_d, s.r1)))
+    assert s1.r1 > 0 and s2.r1 == 0
+    assert any((a - b.detach()).abs().max() > 0 for a, b in zip(g0, G.parameters()))
+    assert any((a - b.detach()).abs().max() > 0 for a, b in zip(d0, D.parameters()))
+    assert any((a - b).abs().max() > 0 for a, b in zip(e0, trainer.G_ema.parameters()))
+    assert D(reals).shape == (4,)
+
+
+def _train_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import gansformer_b200 as gf
+    from importlib import import_module
+    d = import_module("gansformer-reproducibility-challenge_b200.dist")
+    r, w, _ = d.init_distributed("gloo")
+    torch.set_num_threads(2)
+    tr, G, D = _tiny_gan(gf)
+    trainer = tr.Trainer(G, D, tr.TrainConfig(noise_mode="const", r1_gamma=0.0), world=w)
+    g = torch.Generator().manual_seed(3)
+    z, reals = torch.randn(4, 5, 16, generator=g), torch.rand(4, 3, 16, 16, generator=g) * 2 - 1
+    st = trainer.step(d.shard_batch(z, r, w), d.shard_batch(reals, r, w))
+    flat = lambda m: torch.cat([p.detach().reshape(-1) for p in m.parameters()]).numpy()      # by value: the worker exits first
+    q.put((r, flat(D), flat(G), st.allreduce_bytes))
+    d.barrier()
+    dist.destroy_process_group()
+
+
+def test_training_step_world2_keeps_replicas_identical(gf):
+    """world_size-2 gloo: after one step on disjoint shards both ranks hold identical G and D weights, and the flat-buffer
+    all-reduce moved every gradient once per network."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    (_, d0, g0, nb0), (_, d1, g1, nb1) = res
+    assert (d0 == d1).all() and (g0 == g1).all()
+    tr, G, D = _tiny_gan(gf)
+    nparams = sum(p.numel() for p in D.parameters()) + sum(p.numel() for p in G.parameters() if p.requires_grad)
+    assert nb0 == nb1 and 0 < nb0 <= 4 * nparams
+    assert (torch.from_numpy(d0) - torch.cat([p.detach().reshape(-1) for p in D.parameters()])).abs().max() > 0   # and they did move
