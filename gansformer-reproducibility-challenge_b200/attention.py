@@ -83,20 +83,33 @@ def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[s
                                 integration: str = "mul", norm: Optional[str] = "layer", duplex: bool = False,
                                 num_heads: int = 1, use_pos: bool = True, return_att: bool = False,
                                 centroids: Optional[torch.Tensor] = None, exact_fp32: bool = False,
-                                out: Optional[torch.Tensor] = None, weights_version=None, postop: Optional[dict] = None):
+                                out: Optional[torch.Tensor] = None, weights_version=None, postop: Optional[dict] = None,
+                                stage: str = "all", x_shape: Optional[Tuple[int, int, int, int]] = None):
     """x [B,H,W,C] channels-last fp32 (CUDA), y [B,k,D].  Returns (x', att [B,k,H,W] | None, centroids | None).
 
     postop (optional): dict(bias [C] | None, noise [H*W] or [B,H*W] | None, strength 0-d tensor | None, act 'lrelu' |
     'linear', gain float, in_scale [B,C] | None, post_scale [B,C] | None) -- the demodulation scale of the preceding
     convolution (load side) and the noise + fused_bias_act step + next-layer style scale (store side), fused into the
-    kernel."""
+    kernel.
+
+    stage: "all" | "prologue" | "token" (simplex only).  "prologue" runs stages W + I for a layer whose activations do
+    not exist yet (x may be None, give x_shape; postop needs only in_scale) -- they depend on the latents alone, so a
+    caller can hoist them onto a side stream; "token" then runs stage T on the prepared workspace."""
     lib = _lib.load()
-    if x.dim() != 4:
-        raise ValueError("x must be [B, H, W, C] (channels-last)")
-    dev = x.device
-    _check_tensor(x, "x", dev)
+    if stage not in ("all", "prologue", "token") or (stage != "all" and duplex):
+        raise ValueError("stage must be 'all', or 'prologue' / 'token' for a simplex layer")
+    if x is None:
+        if stage != "prologue" or x_shape is None:
+            raise ValueError("x may only be omitted (with x_shape) for stage='prologue'")
+        B, H, W, C = x_shape
+        dev = y.device
+    else:
+        if x.dim() != 4:
+            raise ValueError("x must be [B, H, W, C] (channels-last)")
+        dev = x.device
+        _check_tensor(x, "x", dev)
+        B, H, W, C = x.shape
     _check_tensor(y, "y", dev)
-    B, H, W, C = x.shape
     if y.dim() != 3 or y.shape[0] != B:
         raise ValueError(f"y must be [B, k, D] with B={B}, got {tuple(y.shape)}")
     k, D = y.shape[1], y.shape[2]
@@ -130,11 +143,12 @@ def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[s
         if ws is None:
             ws = torch.empty(_lib.workspace_bytes(desc), dtype=torch.uint8, device=dev)
             plan.ws[wkey] = ws
-        if out is None:
-            out = torch.empty_like(x)
-        else:
-            _check_tensor(out, "out", dev)
-        att = torch.empty((B, H * W, k), dtype=torch.float32, device=dev) if return_att else None
+        if stage != "prologue":
+            if out is None:
+                out = torch.empty_like(x)
+            else:
+                _check_tensor(out, "out", dev)
+        att = torch.empty((B, H * W, k), dtype=torch.float32, device=dev) if (return_att and stage != "prologue") else None
         post_ref = None
         if postop is not None:
             pst = _lib.GfAttnPostop()
@@ -183,8 +197,11 @@ def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[s
                        "gf_attn_duplex_fwd_ex")
         else:
             cen = None
-            _lib.check(lib.gf_attn_prologue_ex(ctypes.byref(desc), y.data_ptr(), plan.folded.data_ptr(), ws.data_ptr(), post_ref, stream),
-                       "gf_attn_prologue_ex")
+            if stage != "token":
+                _lib.check(lib.gf_attn_prologue_ex(ctypes.byref(desc), y.data_ptr(), plan.folded.data_ptr(), ws.data_ptr(), post_ref, stream),
+                           "gf_attn_prologue_ex")
+            if stage == "prologue":
+                return None, None, None
             if timer is not None:
                 ev0.record()
             _lib.check(lib.gf_attn_simplex_fwd_ex(ctypes.byref(desc), x.data_ptr(), out.data_ptr(), _ptr(att), ws.data_ptr(),
@@ -225,8 +242,10 @@ class BipartiteAttention(nn.Module):
         return {n: p for n, p in self.named_parameters(recurse=False)}
 
     def forward(self, x: torch.Tensor, y: torch.Tensor, centroids: Optional[torch.Tensor] = None,
-                return_att: bool = False, out: Optional[torch.Tensor] = None, postop: Optional[dict] = None):
-        """x [B,H,W,C] channels-last, y [B,k,D] -> (x', att [B,k,H,W] | None, centroids [B,k,C] | None)."""
+                return_att: bool = False, out: Optional[torch.Tensor] = None, postop: Optional[dict] = None,
+                stage: str = "all"):
+        """x [B,H,W,C] channels-last, y [B,k,D] -> (x', att [B,k,H,W] | None, centroids [B,k,C] | None).
+        stage="token": the per-image tables were already built by ``prepare`` (same y, same in_scale)."""
         if torch.is_grad_enabled() and (x.requires_grad or y.requires_grad or any(p.requires_grad for p in self.parameters())):
             if postop is not None:
                 raise RuntimeError("the fused post-op is inference-only; apply noise/bias/activation outside when training")
@@ -235,7 +254,16 @@ class BipartiteAttention(nn.Module):
         return bipartite_attention_forward(x, y, self.param_dict(), self._plan, integration=self.integration,
                                            norm=self.norm, duplex=self.duplex, num_heads=self.num_heads,
                                            use_pos=self.use_pos, return_att=return_att, centroids=centroids,
-                                           exact_fp32=self.exact_fp32, out=out, postop=postop)
+                                           exact_fp32=self.exact_fp32, out=out, postop=postop, stage=stage)
+
+    @torch.no_grad()
+    def prepare(self, y: torch.Tensor, x_shape: Tuple[int, int, int, int], in_scale: Optional[torch.Tensor] = None):
+        """Stages W + I of a simplex layer (weights fold + per-image K', V^T, positional tables): they depend on the latents
+        (and the demodulation scale folded into K') only, so the generator runs them for every layer up front on a side stream."""
+        post = dict(in_scale=in_scale) if in_scale is not None else None
+        bipartite_attention_forward(None, y, self.param_dict(), self._plan, integration=self.integration, norm=self.norm,
+                                    duplex=self.duplex, num_heads=self.num_heads, use_pos=self.use_pos,
+                                    exact_fp32=self.exact_fp32, postop=post, stage="prologue", x_shape=x_shape)
 
 
 _FUNCTIONAL_PLANS: Dict[int, _Plan] = {}

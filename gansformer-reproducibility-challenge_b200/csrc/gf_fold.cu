@@ -3,6 +3,7 @@
 // Replaces, on the reference side (expected src/training/network.py, not in the checkout): dense_layer /
 // get_weight (equalised-LR scaling), the K and V dense layers of transformer_layer, and
 // get_positional_embeddings.  Buffer layouts mirror oracle/folded.py: fold_weights(), prologue().
+#include <stdlib.h>
 #include "gf_common.cuh"
 
 namespace gf {
@@ -29,7 +30,7 @@ int make_layout(const gf_attn_desc* d, Layout* L) {
   l.B = d->B; l.H = d->H; l.W = d->W; l.C = d->C; l.k = d->k; l.D = d->D; l.p = d->pos_dim;
   l.KP = pad_k(d->k);
   l.Cout = d->integration == GF_INT_BOTH ? 2 * d->C : d->C;
-  l.LDK = d->C + d->pos_dim + 4;
+  l.LDK = (d->C + d->pos_dim + 4 + 3) & ~3;          // rows of the [.., LDK] matrices are read as float4
   l.n = d->H * d->W;
   l.duplex = d->duplex ? 1 : 0;
   const size_t C = l.C, k = l.k, D = l.D, p = l.p, LDK = l.LDK;
@@ -61,17 +62,21 @@ int make_layout(const gf_attn_desc* d, Layout* L) {
   int want = (2 * 148 + l.B - 1) / l.B;
   l.nsplit_norm = want; if (l.nsplit_norm > (l.n + 63) / 64) l.nsplit_norm = (l.n + 63) / 64; if (l.nsplit_norm < 1) l.nsplit_norm = 1;
   {
-    // centroid splits: one CTA per SM; pick the split count (<= 16) whose grid B*nsplit fills whole waves of 148 SMs best
+    // centroid splits: one CTA per SM.  Cost model in tile units: every CTA pays a fixed cost (TMEM allocation, loading M,
+    // flushing its [KP, C] partial -- about two tiles' worth) plus its share of the image's tiles, and the grid runs in
+    // ceil(CTAs / 148) rounds.  Small images therefore get ONE split (a 32x32 grid used to be cut into 8 one-tile CTAs, each
+    // moving as many bytes of M and partials as of X).
     const int tiles = (l.n + 127) / 128;
+    const int z = l.C == 512 ? 2 : 1;                   // C = 512: two CTAs per split (channel halves)
     int best = 1;
-    double best_u = -1.0;
+    long long best_cost = -1;
     for (int ns = 1; ns <= 16 && ns <= tiles; ++ns) {
-      const double waves = (double)l.B * ns * (l.C == 512 ? 2 : 1) / 148.0;   // C = 512: two CTAs per split (channel halves)
-      double u = waves / ceil(waves);
-      if (waves < 1.0) u = waves;                       // under one wave: utilisation is just the fill
-      if (u > best_u + 1e-9) { best_u = u; best = ns; }
+      const long long rounds = ((long long)l.B * ns * z + 147) / 148;
+      const long long cost = rounds * ((tiles + ns - 1) / ns + 2);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = ns; }
     }
     l.nsplit_cen = best;
+    if (const char* e = getenv("GF_NSPLIT_CEN")) { const int v = atoi(e); if (v >= 1 && v <= 16 && v <= tiles) l.nsplit_cen = v; }   // tuning aid
   }
 
   o = 0;
@@ -412,14 +417,36 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
     }
     return;
   }
-  const int nK = KP * C;
+  // K' role: float4 elements, four independent loads in flight per thread (one L2 round trip per batch instead of per element)
+  const int C4 = C >> 2, nK4 = KP * C4;
   const int stride = (gridDim.y - npos - nvblk) * blockDim.x;
-  for (int i = (blk - nvblk - npos) * blockDim.x + threadIdx.x; i < nK; i += stride) {
-    const int j = i / C, c = i % C;
-    float v = j < k ? kp[(size_t)j * LDK + c] : 0.f;
-    if (in_scale) v *= in_scale[(size_t)b * in_ld + c];      // x_in = x * in_scale: (x*d).K' == x.(K'*d)
-    if (tf32) v = round_tf32(v * GF_TF32_TRUNC_COMP);
-    Kp[(size_t)b * nK + i] = v;
+  const float4* isc4 = in_scale ? reinterpret_cast<const float4*>(in_scale + (size_t)b * in_ld) : nullptr;
+  float4* Kp4 = reinterpret_cast<float4*>(Kp + (size_t)b * KP * C);
+  for (int i0 = (blk - nvblk - npos) * blockDim.x + threadIdx.x; i0 < nK4; i0 += 4 * stride) {
+    float4 v[4], d[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * stride;
+      const int j = i / C4, c4 = i - j * C4;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      d[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (i < nK4 && j < k) {
+        v[u] = *reinterpret_cast<const float4*>(kp + (size_t)j * LDK + c4 * 4);
+        if (isc4) d[u] = isc4[c4];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * stride;
+      if (i < nK4) {
+        float4 r = make_float4(v[u].x * d[u].x, v[u].y * d[u].y, v[u].z * d[u].z, v[u].w * d[u].w);   // x_in = x * in_scale: (x*d).K' == x.(K'*d)
+        if (tf32) {
+          r.x = round_tf32(r.x * GF_TF32_TRUNC_COMP); r.y = round_tf32(r.y * GF_TF32_TRUNC_COMP);
+          r.z = round_tf32(r.z * GF_TF32_TRUNC_COMP); r.w = round_tf32(r.w * GF_TF32_TRUNC_COMP);
+        }
+        Kp4[i] = r;
+      }
+    }
   }
 }
 

@@ -12,6 +12,7 @@ choices the reference source cannot arbitrate are frozen in SURVEY.md A.4 ([SPEC
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional
 
 import numpy as np
@@ -50,7 +51,8 @@ def nf(res: int, fmap_base: int = 16384, fmap_max: int = 512) -> int:
 
 def modulated_conv2d(x: torch.Tensor, weight: torch.Tensor, styles: torch.Tensor, *, demodulate: bool = True,
                      up: int = 1, f: Optional[torch.Tensor] = None, w_eff: Optional[torch.Tensor] = None,
-                     wsq: Optional[torch.Tensor] = None, prescaled: bool = False, defer_demod: bool = False):
+                     wsq: Optional[torch.Tensor] = None, prescaled: bool = False, defer_demod: bool = False,
+                     d: Optional[torch.Tensor] = None):
     """StyleGAN2 modulated convolution in its activation-scaling form: (x * s) conv w, then * demod.
 
     Identical in exact arithmetic to modulating the weights per sample (the reference's grouped-conv form);
@@ -64,8 +66,7 @@ def modulated_conv2d(x: torch.Tensor, weight: torch.Tensor, styles: torch.Tensor
         w_eff = weight * (1.0 / math.sqrt(I * kh * kw))
         if up != 1:
             w_eff = w_eff.transpose(0, 1)
-    d = None
-    if demodulate:
+    if demodulate and d is None:
         if wsq is None:
             wsq = (weight * (1.0 / math.sqrt(I * kh * kw))).square().sum(dim=[2, 3])    # [O, I]
         d = ops.demod_coef(styles, wsq)                                                  # [B, O]
@@ -162,7 +163,7 @@ class SynthesisLayer(nn.Module):
                 and _inference(self.weight, self.bias, self.noise_strength, *a.parameters()))
 
     def forward(self, x, w_glob, y, noise_mode="const", centroids=None, return_att=False, styles=None,
-                prescaled=False, post_scale=None):
+                prescaled=False, post_scale=None, prepared=None):
         """prescaled: x already carries this layer's style scale.  post_scale [B,C]: the NEXT convolution's style scale,
         folded into this layer's store (only honoured -- and only passed by SynthesisNetwork -- when `fusable`)."""
         if styles is None:
@@ -172,9 +173,12 @@ class SynthesisLayer(nn.Module):
             w_eff, wsq = _cached(self, "conv", (self.weight,), self._conv_weights)
         fused = self.fusable(x)
         in_scale = None
+        # prepared = (event, demod): SynthesisNetwork already ran this layer's attention prologue on its side stream
+        if prepared is not None and not fused:
+            raise RuntimeError("internal: prepared prologue for a layer that does not take the fused path")
         if fused and not self.up:      # demodulation rides on the attention kernel's load side (folded into K')
             x, in_scale = modulated_conv2d(x, self.weight, styles, up=1, f=self.fir, w_eff=w_eff, wsq=wsq,
-                                           prescaled=prescaled, defer_demod=True)
+                                           prescaled=prescaled, defer_demod=True, d=prepared[1] if prepared is not None else None)
         else:
             x = modulated_conv2d(x, self.weight, styles, up=2 if self.up else 1, f=self.fir, w_eff=w_eff, wsq=wsq,
                                  prescaled=prescaled)
@@ -192,7 +196,10 @@ class SynthesisLayer(nn.Module):
             if fused:   # demod (load side) + noise + bias + leaky-ReLU + next style (store side) ride on the attention kernel
                 post = dict(bias=self.bias, noise=noise, strength=self.noise_strength, act="lrelu", gain=SQRT2,
                             in_scale=in_scale, post_scale=post_scale)
-                xo, att, centroids = self.attention(xl, y, centroids=centroids, return_att=return_att, postop=post)
+                if prepared is not None:
+                    torch.cuda.current_stream(x.device).wait_event(prepared[0])
+                xo, att, centroids = self.attention(xl, y, centroids=centroids, return_att=return_att, postop=post,
+                                                    stage="token" if prepared is not None else "all")
                 return xo.permute(0, 3, 1, 2), att, centroids
             xo, att, centroids = self.attention(xl, y, centroids=centroids, return_att=return_att)
             x = xo.permute(0, 3, 1, 2)                                  # back to an NCHW view of channels-last data
@@ -263,6 +270,31 @@ class SynthesisNetwork(nn.Module):
                 return torch.cat(ws_, dim=1).contiguous(), torch.cat(bs_)
             wt_cat, b_cat = _cached(self, "affines", aff_params, cat_affines)
             styles_all = torch.addmm(b_cat, w_glob, wt_cat).split([a.weight.shape[0] for a in aff], dim=1)
+        # Attention prologues (weights fold, per-image K' / V^T / positional tables) depend only on the latents and the styles:
+        # optionally run them for every fused layer on a side stream, overlapped with the convolutions (inside a CUDA graph: a
+        # parallel branch).  Each layer waits for its own event right before its token pass.
+        prepared = [None] * len(self.layers)
+        if x.is_cuda and styles_all[0] is not None and os.environ.get("GF_HOIST_PROLOGUE"):   # opt-in: a same-box A/B showed no gain
+            cur = torch.cuda.current_stream(x.device)
+            side = self.__dict__.get("_side_stream")
+            if side is None or side.device != x.device:
+                side = self.__dict__["_side_stream"] = torch.cuda.Stream(device=x.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for li_, layer in enumerate(self.layers):
+                    if not layer.fusable(x):
+                        continue
+                    d_ = None
+                    if not layer.up:
+                        _, wsq_ = _cached(layer, "conv", (layer.weight,), layer._conv_weights)
+                        d_ = ops.demod_coef(styles_all[li_], wsq_)
+                        d_.record_stream(cur)                            # produced on the side stream, consumed on the main one
+                    C_ = layer.weight.shape[0]
+                    layer.attention.prepare(y, (B, layer.resolution, layer.resolution, C_), in_scale=d_)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    prepared[li_] = (ev, d_)
+            # (tensors allocated on the side stream are kept alive by the layers' plans / this list until the step ends)
         img = None
         atts = []
         li = 0
@@ -276,7 +308,7 @@ class SynthesisNetwork(nn.Module):
                 if j == 0 and nl == 2 and styles_all[li + 1] is not None and layer.fusable(x):
                     post_scale = styles_all[li + 1]
                 x, att, _ = layer(x, w_glob, y, noise_mode=noise_mode, return_att=return_att, styles=styles_all[li],
-                                  prescaled=prescaled, post_scale=post_scale)
+                                  prescaled=prescaled, post_scale=post_scale, prepared=prepared[li])
                 prescaled = post_scale is not None
                 li += 1
                 if att is not None:

@@ -190,6 +190,24 @@ def test_short_tiles_small_grid(gf, cuda_dev, C, H, W, k, B, integration, duplex
         check_close(cen, rcen, "tcgen05_tf32", "short-tiles/centroids")
 
 
+def test_prepare_then_token_stage_equals_one_call(gf, cuda_dev):
+    """BipartiteAttention.prepare (stages W + I, needs only the latents) followed by stage='token' reproduces the single call
+    bit for bit, including the folded load-side scale."""
+    torch.manual_seed(4)
+    attn = gf.BipartiteAttention(128, 32, 16).to(cuda_dev)
+    x = torch.randn(3, 16, 16, 128, device=cuda_dev)
+    y = torch.randn(3, 16, 32, device=cuda_dev)
+    d = torch.rand(3, 128, device=cuda_dev) + 0.5
+    post = dict(bias=torch.randn(128, device=cuda_dev), act="lrelu", gain=1.4, in_scale=d)
+    with torch.no_grad():
+        want, _, _ = attn(x, y, postop=post)
+        want = want.clone()
+        attn.prepare(y * 0 + 1.0, tuple(x.shape), in_scale=d)          # clobber the tables, then prepare for real
+        attn.prepare(y, tuple(x.shape), in_scale=d)
+        got, _, _ = attn(x, y, postop=post, stage="token")
+    assert torch.equal(got, want)
+
+
 def test_inplace_and_no_att(gf, cuda_dev):
     C, H, W, k, D, p = 128, 16, 16, 16, 32, 32
     g = torch.Generator().manual_seed(5)
