@@ -28,24 +28,24 @@ __global__ void __launch_bounds__(256) chan_scale_kernel(const float4* __restric
 // fly, vertical pass over a sliding window of 4 horizontally filtered rows.
 template <int ROWS>
 __global__ void __launch_bounds__(256) blur_up_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                      const float* __restrict__ scale, int Hout, int Wout, int C, float gain) {
+                                                      const float* __restrict__ scale, int Hout, int Wout, int C, float gain, int pad) {
   const int c4n = C >> 2;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= Wout * c4n) return;
   const int w = t / c4n, c = (t % c4n) * 4;
   const int h0 = blockIdx.y * ROWS, b = blockIdx.z;
-  const int Hin = Hout + 1, Win = Wout + 1;
+  const int Hin = Hout + 3 - 2 * pad, Win = Wout + 3 - 2 * pad;   // pad 1: the blur after an upsampling conv; pad 2: its adjoint
   const float f0 = 0.125f, f1 = 0.375f;
   const float* xb = x + (size_t)b * Hin * Win * C;
   float4 win[4];
-  auto hrow = [&](int u) -> float4 {            // u: row of the padded input, x_pad[u][v] = x[u-1][v-1]
-    const int r = u - 1;
+  auto hrow = [&](int u) -> float4 {            // u: row of the padded input, x_pad[u][v] = x[u-pad][v-pad]
+    const int r = u - pad;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < 0 || r >= Hin) return a;
     const float* row = xb + (size_t)r * Win * C + c;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int v = w + j - 1;
+      const int v = w + j - pad;
       if (v >= 0 && v < Win) {
         const float4 q = __ldg(reinterpret_cast<const float4*>(row + (size_t)v * C));
         const float f = (j == 0 || j == 3) ? f0 : f1;
@@ -242,7 +242,20 @@ int gf_blur_up_nhwc(const float* x, float* y, const float* scale, int B, int Hou
   if (B <= 0 || Hout <= 0 || Wout <= 0 || C <= 0 || (C & 3) || B > 65535) { set_error("gf_blur_up_nhwc: bad shape (B=%d Hout=%d Wout=%d C=%d)", B, Hout, Wout, C); return GF_ERR_UNSUPPORTED; }
   constexpr int ROWS = 8;
   dim3 grid((Wout * (C >> 2) + 255) / 256, (Hout + ROWS - 1) / ROWS, B);
-  blur_up_kernel<ROWS><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, scale, Hout, Wout, C, gain);
+  blur_up_kernel<ROWS><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, scale, Hout, Wout, C, gain, 1);
+  GF_LAUNCH_OK();
+  return GF_OK;
+}
+
+int gf_fir4_nhwc(const float* x, float* y, int B, int Hin, int Win, int C, int pad, float gain, void* stream) {
+  if (!x || !y) { set_error("gf_fir4_nhwc: null pointer"); return GF_ERR_INVALID; }
+  const int Hout = Hin + 2 * pad - 3, Wout = Win + 2 * pad - 3;
+  if (B <= 0 || Hout <= 0 || Wout <= 0 || C <= 0 || (C & 3) || B > 65535 || pad < 0 || pad > 3) {
+    set_error("gf_fir4_nhwc: bad arguments (B=%d Hin=%d Win=%d C=%d pad=%d)", B, Hin, Win, C, pad); return GF_ERR_UNSUPPORTED;
+  }
+  constexpr int ROWS = 8;
+  dim3 grid((Wout * (C >> 2) + 255) / 256, (Hout + ROWS - 1) / ROWS, B);
+  blur_up_kernel<ROWS><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, nullptr, Hout, Wout, C, gain, pad);
   GF_LAUNCH_OK();
   return GF_OK;
 }

@@ -77,6 +77,34 @@ def chan_scale(x: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
     return x * s[:, :, None, None].to(x.dtype)
 
 
+class _Fir4(torch.autograd.Function):
+    """Native [1,3,3,1]^2/64 FIR with symmetric padding (gf_fir4_nhwc), differentiable to any order: the filter is symmetric,
+    so the gradient of a pad-p blur is the pad-(3-p) blur of the incoming gradient -- the same op again."""
+
+    @staticmethod
+    def forward(ctx, x, pad, gain):
+        ctx.pad, ctx.gain = pad, gain
+        xv = _nhwc_view(x.detach())
+        B, H, W, C = xv.shape
+        y = torch.empty((B, H + 2 * pad - 3, W + 2 * pad - 3, C), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().gf_fir4_nhwc(xv.data_ptr(), y.data_ptr(), B, H, W, C, pad, ctypes.c_float(gain), _stream(x.device)),
+                       "gf_fir4_nhwc")
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        return _Fir4.apply(gy, 3 - ctx.pad, ctx.gain), None, None
+
+
+def fir4(x: torch.Tensor, f: torch.Tensor, pad: int, gain: float = 1.0) -> torch.Tensor:
+    """Stride-1 FIR blur with the [1,3,3,1] filter and symmetric padding `pad`: x [B,C,H,W] -> [B,C,H+2p-3,W+2p-3].
+    CUDA fp32 tensors use the native kernel in both directions (autograd included); anything else the torch definition."""
+    if x.is_cuda and x.dtype == torch.float32 and x.shape[1] % 4 == 0 and 0 <= pad <= 3 and min(x.shape[2:]) + 2 * pad > 3:
+        return _Fir4.apply(x, int(pad), float(gain))
+    return upfirdn2d_ref(x, f.to(x.dtype), pad=(pad, pad, pad, pad), gain=gain)
+
+
 def blur_up(x: torch.Tensor, f: torch.Tensor, scale: Optional[torch.Tensor] = None, gain: float = 4.0) -> torch.Tensor:
     """FIR blur after a stride-2 transposed conv: x [B,C,2H+1,2W+1] -> [B,C,2H,2W] (pad 1), optional * scale [B,C]."""
     if _use_cuda(x, scale) and x.shape[1] % 4 == 0:
@@ -87,7 +115,7 @@ def blur_up(x: torch.Tensor, f: torch.Tensor, scale: Optional[torch.Tensor] = No
             _lib.check(_lib.load().gf_blur_up_nhwc(xv.data_ptr(), y.data_ptr(), None if scale is None else scale.contiguous().data_ptr(),
                                                    B, Hin - 1, Win - 1, C, float(gain), _stream(x.device)), "gf_blur_up_nhwc")
         return y.permute(0, 3, 1, 2)
-    y = upfirdn2d_ref(x, f, pad=(1, 1, 1, 1), gain=gain)
+    y = fir4(x, f, 1, gain=gain)                                        # training: native FIR both ways, scale in torch
     return y if scale is None else y * scale[:, :, None, None].to(y.dtype)
 
 

@@ -24,7 +24,7 @@ import torch.nn.functional as F
 
 from . import dist as gdist
 from .networks import FullyConnected, nf
-from .ops import fir_filter, upfirdn2d_ref
+from .ops import fir4, fir_filter, upfirdn2d_ref
 
 SQRT2 = math.sqrt(2.0)
 
@@ -44,7 +44,10 @@ class EqConv2d(nn.Module):
         w = self.weight * self.wgain
         if self.down:
             p = (self.fir.shape[0] - 2) + (self.kernel - 1)          # upfirdn padding of StyleGAN2's conv_downsample_2d
-            x = upfirdn2d_ref(x, self.fir.to(x.dtype), pad=((p + 1) // 2, p // 2, (p + 1) // 2, p // 2))
+            if p % 2 == 0:
+                x = fir4(x, self.fir, p // 2)                          # native FIR (forward, backward, double backward for R1)
+            else:
+                x = upfirdn2d_ref(x, self.fir.to(x.dtype), pad=((p + 1) // 2, p // 2, (p + 1) // 2, p // 2))
             x = F.conv2d(x, w, stride=2)
         else:
             x = F.conv2d(x, w, padding=self.kernel // 2)

@@ -27,6 +27,12 @@ int gf_chan_scale_nhwc(const float* x, const float* s, int s_ld, float* y, int B
  * (4 after an upsampling conv), zero padding 1 on every side; optional per-(b,c) scale (demodulation). C % 4 == 0. */
 int gf_blur_up_nhwc(const float* x, float* y, const float* scale, int B, int Hout, int Wout, int C, float gain, void* stream);
 
+/* upfirdn_2d, general stride-1 form with the [1,3,3,1]^2/64 filter and symmetric zero padding `pad` in 0..3:
+ * x [B,Hin,Win,C] -> y [B,Hin+2*pad-3,Win+2*pad-3,C] times `gain`.  pad 1 = use (a); pad 2 = its adjoint (the backward pass:
+ * the filter is symmetric, so d/dx of a pad-p blur is a pad-(3-p) blur of the incoming gradient) and the blur in front of the
+ * discriminator's stride-2 3x3 convolutions; pad 1 also serves the discriminator's 1x1 skip path.  C % 4 == 0. */
+int gf_fir4_nhwc(const float* x, float* y, int B, int Hin, int Win, int C, int pad, float gain, void* stream);
+
 /* upfirdn_2d, use (b): 2x upsampling of an NCHW image (skip connection of the tRGB outputs):
  * zero-insert, pad (2,1,2,1), FIR [1,3,3,1]^2/64 * 4.  y [B,C,2H,2W] = up(x [B,C,H,W]) (+ add, nullable, same shape as y). */
 int gf_upsample2x_nchw(const float* x, const float* add, float* y, int B, int C, int H, int W, void* stream);

@@ -473,6 +473,18 @@ def test_native_ops_match_definitions(gf, cuda_dev):
                 + brgb.double()[None, :, None, None]
             assert got.shape == (B, 3, H, W) and got.is_contiguous()
             assert (got.double() - want).abs().max() <= 1e-5 * max(1.0, want.abs().max().item())
+        for pad in (1, 2):                                      # differentiable FIR: value, gradient and second-order term
+            xf = xs.clone().requires_grad_(True)
+            xr = xs.double().clone().requires_grad_(True)
+            yf, yr = ops.fir4(xf, f, pad, gain=2.0), ops.upfirdn2d_ref(xr, f.double(), pad=(pad,) * 4, gain=2.0)
+            assert yf.shape == yr.shape and (yf.double() - yr).abs().max() < 1e-5
+            gyf = torch.randn(yf.shape, generator=g).to(cuda_dev)
+            (gf1,) = torch.autograd.grad((yf * gyf).sum() + yf.square().sum(), xf, create_graph=True)
+            (gr1,) = torch.autograd.grad((yr * gyf.double()).sum() + yr.square().sum(), xr, create_graph=True)
+            assert (gf1.double() - gr1).abs().max() < 1e-4
+            (gf2,) = torch.autograd.grad(gf1.square().sum(), xf)
+            (gr2,) = torch.autograd.grad(gr1.square().sum(), xr)
+            assert (gf2.double() - gr2).abs().max() < 1e-3 * max(1.0, gr2.abs().max().item())
         img = torch.randn(B, 3, H, W, generator=g).to(cuda_dev)
         add = torch.randn(B, 3, 2 * H, 2 * W, generator=g).to(cuda_dev)
         with torch.no_grad():
