@@ -75,6 +75,69 @@ __global__ void __launch_bounds__(256) blur_up_kernel(const float* __restrict__ 
   }
 }
 
+// The same blur, reading the stride-2 transposed convolution's output T [2H+1, 2W+1] as its four polyphase components
+// P[a][b][i, j] = T[2i + a, 2j + b] (sizes (H+1-a) x (W+1-b)): the host computes them as four stride-1 convolutions of
+// the low-resolution input (cuDNN fprop kernels: 1.3-1.7x faster than its strided dgrad) and never interleaves them.
+struct PhasePtrs { const float* p[2][2]; };
+template <int ROWS>
+__global__ void __launch_bounds__(256) blur_up_phases_kernel(const PhasePtrs P, float* __restrict__ y, const float* __restrict__ scale,
+                                                             int Hout, int Wout, int C, float gain) {
+  const int c4n = C >> 2;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Wout * c4n) return;
+  const int w = t / c4n, c = (t % c4n) * 4;
+  const int h0 = blockIdx.y * ROWS, b = blockIdx.z;
+  const int H = Hout >> 1, W = Wout >> 1;          // low-resolution grid; T is (2H+1) x (2W+1)
+  const float f0 = 0.125f, f1 = 0.375f;
+  float4 win[4];
+  // per-thread tap table: column v = w + j - 1 of T lives in column-phase pb = v & 1 at column v >> 1
+  int toff[4]; bool tval[4], todd[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int v = w + j - 1;
+    tval[j] = v >= 0 && v <= 2 * W;
+    todd[j] = (v & 1) != 0;
+    toff[j] = (v >> 1) * C;
+  }
+  auto hrow = [&](int u) -> float4 {            // u: row of the padded T, T_pad[u][v] = T[u-1][v-1]
+    const int r = u - 1;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < 0 || r > 2 * H) return a;
+    const int pa = r & 1, ri = r >> 1, Hp = H + 1 - pa;
+    const size_t rowi = (size_t)b * Hp + ri;
+    const float* rb0 = (pa ? P.p[1][0] : P.p[0][0]) + rowi * (size_t)(W + 1) * C + c;   // even columns: W + 1 of them
+    const float* rb1 = (pa ? P.p[1][1] : P.p[0][1]) + rowi * (size_t)W * C + c;         // odd columns: W
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (tval[j]) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>((todd[j] ? rb1 : rb0) + toff[j]));
+        const float f = (j == 0 || j == 3) ? f0 : f1;
+        a.x = fmaf(f, q.x, a.x); a.y = fmaf(f, q.y, a.y); a.z = fmaf(f, q.z, a.z); a.w = fmaf(f, q.w, a.w);
+      }
+    }
+    return a;
+  };
+  win[0] = hrow(h0); win[1] = hrow(h0 + 1); win[2] = hrow(h0 + 2);
+  float4 sc = make_float4(gain, gain, gain, gain);
+  if (scale) {
+    const float4 s = __ldg(reinterpret_cast<const float4*>(scale + (size_t)b * C + c));
+    sc = make_float4(gain * s.x, gain * s.y, gain * s.z, gain * s.w);
+  }
+#pragma unroll
+  for (int i = 0; i < ROWS; ++i) {
+    const int h = h0 + i;
+    if (h >= Hout) break;
+    win[3] = hrow(h + 3);
+    float4 o;
+    o.x = (f0 * (win[0].x + win[3].x) + f1 * (win[1].x + win[2].x)) * sc.x;
+    o.y = (f0 * (win[0].y + win[3].y) + f1 * (win[1].y + win[2].y)) * sc.y;
+    o.z = (f0 * (win[0].z + win[3].z) + f1 * (win[1].z + win[2].z)) * sc.z;
+    o.w = (f0 * (win[0].w + win[3].w) + f1 * (win[1].w + win[2].w)) * sc.w;
+    *reinterpret_cast<float4*>(y + (((size_t)b * Hout + h) * Wout + w) * C + c) = o;
+    win[0] = win[1]; win[1] = win[2]; win[2] = win[3];
+  }
+}
+
 __global__ void __launch_bounds__(256) upsample2x_nchw_kernel(const float* __restrict__ x, const float* __restrict__ add,
                                                               float* __restrict__ y, int planes, int H, int W) {
   const int OW = 2 * W, OH = 2 * H;
@@ -243,6 +306,21 @@ int gf_blur_up_nhwc(const float* x, float* y, const float* scale, int B, int Hou
   constexpr int ROWS = 8;
   dim3 grid((Wout * (C >> 2) + 255) / 256, (Hout + ROWS - 1) / ROWS, B);
   blur_up_kernel<ROWS><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, scale, Hout, Wout, C, gain, 1);
+  GF_LAUNCH_OK();
+  return GF_OK;
+}
+
+int gf_blur_up_phases_nhwc(const float* p00, const float* p01, const float* p10, const float* p11, float* y, const float* scale,
+                           int B, int Hout, int Wout, int C, float gain, void* stream) {
+  if (!p00 || !p01 || !p10 || !p11 || !y) { set_error("gf_blur_up_phases_nhwc: null pointer"); return GF_ERR_INVALID; }
+  if (B <= 0 || Hout <= 0 || Wout <= 0 || (Hout & 1) || (Wout & 1) || C <= 0 || (C & 3) || B > 65535) {
+    set_error("gf_blur_up_phases_nhwc: bad shape (B=%d Hout=%d Wout=%d C=%d)", B, Hout, Wout, C); return GF_ERR_UNSUPPORTED;
+  }
+  constexpr int ROWS = 8;
+  PhasePtrs P;
+  P.p[0][0] = p00; P.p[0][1] = p01; P.p[1][0] = p10; P.p[1][1] = p11;
+  dim3 grid((Wout * (C >> 2) + 255) / 256, (Hout + ROWS - 1) / ROWS, B);
+  blur_up_phases_kernel<ROWS><<<grid, 256, 0, (cudaStream_t)stream>>>(P, y, scale, Hout, Wout, C, gain);
   GF_LAUNCH_OK();
   return GF_OK;
 }

@@ -52,7 +52,7 @@ def nf(res: int, fmap_base: int = 16384, fmap_max: int = 512) -> int:
 def modulated_conv2d(x: torch.Tensor, weight: torch.Tensor, styles: torch.Tensor, *, demodulate: bool = True,
                      up: int = 1, f: Optional[torch.Tensor] = None, w_eff: Optional[torch.Tensor] = None,
                      wsq: Optional[torch.Tensor] = None, prescaled: bool = False, defer_demod: bool = False,
-                     d: Optional[torch.Tensor] = None):
+                     d: Optional[torch.Tensor] = None, phases=None):
     """StyleGAN2 modulated convolution in its activation-scaling form: (x * s) conv w, then * demod.
 
     Identical in exact arithmetic to modulating the weights per sample (the reference's grouped-conv form);
@@ -78,6 +78,8 @@ def modulated_conv2d(x: torch.Tensor, weight: torch.Tensor, styles: torch.Tensor
             return x, d
         if d is not None:
             x = ops.chan_scale(x, d)
+    elif phases is not None and ops._use_cuda(x, d) and O % 4 == 0 and not os.environ.get("GF_NO_PHASES"):
+        x = ops.upconv_blur_phases(x, phases, scale=d, gain=4.0)       # four polyphase stride-1 convolutions + blur
     else:
         x = F.conv_transpose2d(x, w_eff, stride=2)                    # [B, O, 2H+1, 2W+1]
         x = ops.blur_up(x, f, scale=d, gain=4.0)                       # -> [B, O, 2H, 2W], demodulated
@@ -152,9 +154,10 @@ class SynthesisLayer(nn.Module):
         O, I, kh, kw = self.weight.shape
         w = self.weight * (1.0 / math.sqrt(I * kh * kw))
         wsq = w.square().sum(dim=[2, 3])
+        phases = ops.upconv_phase_weights(w) if self.up else None
         if self.up:
             w = w.transpose(0, 1)
-        return w.contiguous(memory_format=torch.channels_last), wsq.contiguous()
+        return w.contiguous(memory_format=torch.channels_last), wsq.contiguous(), phases
 
     def fusable(self, x) -> bool:
         """Inference on CUDA with an attention block whose norm the kernels can fuse around."""
@@ -168,9 +171,9 @@ class SynthesisLayer(nn.Module):
         folded into this layer's store (only honoured -- and only passed by SynthesisNetwork -- when `fusable`)."""
         if styles is None:
             styles = self.affine(w_glob)
-        w_eff = wsq = None
+        w_eff = wsq = phases = None
         if _inference(self.weight) and x.is_cuda:
-            w_eff, wsq = _cached(self, "conv", (self.weight,), self._conv_weights)
+            w_eff, wsq, phases = _cached(self, "conv", (self.weight,), self._conv_weights)
         fused = self.fusable(x)
         in_scale = None
         # prepared = (event, demod): SynthesisNetwork already ran this layer's attention prologue on its side stream
@@ -181,7 +184,7 @@ class SynthesisLayer(nn.Module):
                                            prescaled=prescaled, defer_demod=True, d=prepared[1] if prepared is not None else None)
         else:
             x = modulated_conv2d(x, self.weight, styles, up=2 if self.up else 1, f=self.fir, w_eff=w_eff, wsq=wsq,
-                                 prescaled=prescaled)
+                                 prescaled=prescaled, phases=phases)
         if noise_mode == "const":
             noise = self.noise_const
         elif noise_mode == "random":
@@ -286,7 +289,7 @@ class SynthesisNetwork(nn.Module):
                         continue
                     d_ = None
                     if not layer.up:
-                        _, wsq_ = _cached(layer, "conv", (layer.weight,), layer._conv_weights)
+                        _, wsq_, _ = _cached(layer, "conv", (layer.weight,), layer._conv_weights)
                         d_ = ops.demod_coef(styles_all[li_], wsq_)
                         d_.record_stream(cur)                            # produced on the side stream, consumed on the main one
                     C_ = layer.weight.shape[0]

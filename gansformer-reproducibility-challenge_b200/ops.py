@@ -119,6 +119,31 @@ def blur_up(x: torch.Tensor, f: torch.Tensor, scale: Optional[torch.Tensor] = No
     return y if scale is None else y * scale[:, :, None, None].to(y.dtype)
 
 
+def upconv_phase_weights(w: torch.Tensor):
+    """w [O,I,3,3] (already equalised-LR scaled) -> the four (kernel, padding) pairs whose stride-1 convolutions of the
+    low-resolution input give the polyphase components T[2i+a, 2j+b] of conv_transpose2d(x, w^T, stride=2)."""
+    out = []
+    for a in (0, 1):
+        for b in (0, 1):
+            ky = [2, 0] if a == 0 else [1]
+            kx = [2, 0] if b == 0 else [1]
+            out.append((w[:, :, ky][:, :, :, kx].contiguous(memory_format=torch.channels_last), (1 - a, 1 - b)))
+    return out
+
+
+def upconv_blur_phases(x: torch.Tensor, phases, scale: Optional[torch.Tensor] = None, gain: float = 4.0) -> torch.Tensor:
+    """Stride-2 transposed 3x3 convolution + FIR blur (+ demodulation scale) of the upsampling layers, inference on CUDA:
+    four stride-1 convolutions (cuDNN fprop) feeding the polyphase blur kernel.  x [B,I,H,W] -> [B,O,2H,2W]."""
+    ps = [_nhwc_view(F.conv2d(x, wk, padding=pad)) for wk, pad in phases]
+    B, H, W, C = ps[3].shape
+    y = torch.empty((B, 2 * H, 2 * W, C), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().gf_blur_up_phases_nhwc(ps[0].data_ptr(), ps[1].data_ptr(), ps[2].data_ptr(), ps[3].data_ptr(), y.data_ptr(),
+                                                      None if scale is None else scale.contiguous().data_ptr(), B, 2 * H, 2 * W, C,
+                                                      float(gain), _stream(x.device)), "gf_blur_up_phases_nhwc")
+    return y.permute(0, 3, 1, 2)
+
+
 def upsample2x(x: torch.Tensor, f: torch.Tensor, add: Optional[torch.Tensor] = None) -> torch.Tensor:
     """2x FIR upsampling of an NCHW image (tRGB skip connection), optionally + add."""
     if _use_cuda(x, add):

@@ -473,6 +473,13 @@ def test_native_ops_match_definitions(gf, cuda_dev):
                 + brgb.double()[None, :, None, None]
             assert got.shape == (B, 3, H, W) and got.is_contiguous()
             assert (got.double() - want).abs().max() <= 1e-5 * max(1.0, want.abs().max().item())
+        with torch.no_grad():                                   # upsampling conv as four polyphase convolutions + blur
+            wup = torch.randn(C, C, 3, 3, generator=g).to(cuda_dev) / math.sqrt(9 * C)
+            got = ops.upconv_blur_phases(xs, ops.upconv_phase_weights(wup), scale=s, gain=4.0)
+            T = torch.nn.functional.conv_transpose2d(xs.double(), wup.double().transpose(0, 1), stride=2)
+            want = ops.upfirdn2d_ref(T, f.double(), pad=(1, 1, 1, 1), gain=4.0) * s.double()[:, :, None, None]
+            assert got.shape == (B, C, 2 * H, 2 * W)
+            assert (got.double() - want).abs().max() <= 2e-3 * max(1.0, want.abs().max().item())      # TF32 convolutions
         for pad in (1, 2):                                      # differentiable FIR: value, gradient and second-order term
             xf = xs.clone().requires_grad_(True)
             xr = xs.double().clone().requires_grad_(True)
