@@ -82,42 +82,41 @@ struct PhasePtrs { const float* p[2][2]; };
 template <int ROWS>
 __global__ void __launch_bounds__(256) blur_up_phases_kernel(const PhasePtrs P, float* __restrict__ y, const float* __restrict__ scale,
                                                              int Hout, int Wout, int C, float gain) {
+  // One thread: 4 channels of the output column PAIR (2q, 2q+1) for ROWS consecutive rows.  The pair needs T columns
+  // 2q-1 .. 2q+3: three from the odd-column phase (q-1, q, q+1) and two from the even one (q, q+1) -- 5 loads per T row for
+  // two outputs instead of 8; the kernel is load-issue bound, not DRAM bound.
   const int c4n = C >> 2;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= Wout * c4n) return;
-  const int w = t / c4n, c = (t % c4n) * 4;
-  const int h0 = blockIdx.y * ROWS, b = blockIdx.z;
   const int H = Hout >> 1, W = Wout >> 1;          // low-resolution grid; T is (2H+1) x (2W+1)
+  if (t >= W * c4n) return;
+  const int q = t / c4n, c = (t % c4n) * 4;
+  const int h0 = blockIdx.y * ROWS, b = blockIdx.z;
   const float f0 = 0.125f, f1 = 0.375f;
-  float4 win[4];
-  // per-thread tap table: column v = w + j - 1 of T lives in column-phase pb = v & 1 at column v >> 1
-  int toff[4]; bool tval[4], todd[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int v = w + j - 1;
-    tval[j] = v >= 0 && v <= 2 * W;
-    todd[j] = (v & 1) != 0;
-    toff[j] = (v >> 1) * C;
-  }
-  auto hrow = [&](int u) -> float4 {            // u: row of the padded T, T_pad[u][v] = T[u-1][v-1]
+  const bool has_m1 = q >= 1;                      // odd column 2q-1 exists (otherwise it is the zero padding)
+  // T has columns 0..2W: odd phase column q+1 (= T column 2q+3) exists iff q+1 <= W-1; even phase column q+1 (T column 2q+2) always (<= 2W)
+  const bool has_p3 = q + 1 < W;
+  float4 wa[4], wb[4];                             // horizontally filtered rows of the two outputs (sliding window over 4 T rows)
+  auto hrow = [&](int u, float4& oa, float4& ob) { // u: row of the padded T, T_pad[u] = T[u-1]
     const int r = u - 1;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < 0 || r > 2 * H) return a;
+    oa = ob = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < 0 || r > 2 * H) return;
     const int pa = r & 1, ri = r >> 1, Hp = H + 1 - pa;
     const size_t rowi = (size_t)b * Hp + ri;
-    const float* rb0 = (pa ? P.p[1][0] : P.p[0][0]) + rowi * (size_t)(W + 1) * C + c;   // even columns: W + 1 of them
-    const float* rb1 = (pa ? P.p[1][1] : P.p[0][1]) + rowi * (size_t)W * C + c;         // odd columns: W
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (tval[j]) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>((todd[j] ? rb1 : rb0) + toff[j]));
-        const float f = (j == 0 || j == 3) ? f0 : f1;
-        a.x = fmaf(f, q.x, a.x); a.y = fmaf(f, q.y, a.y); a.z = fmaf(f, q.z, a.z); a.w = fmaf(f, q.w, a.w);
-      }
-    }
-    return a;
+    const float* rb0 = (pa ? P.p[1][0] : P.p[0][0]) + (rowi * (size_t)(W + 1) + q) * C + c;   // even columns 2q, 2q+2
+    const float* rb1 = (pa ? P.p[1][1] : P.p[0][1]) + (rowi * (size_t)W + q) * C + c;         // odd columns 2q-1, 2q+1, 2q+3
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 e0 = __ldg(reinterpret_cast<const float4*>(rb0));
+    const float4 e1 = __ldg(reinterpret_cast<const float4*>(rb0 + C));
+    const float4 o0 = has_m1 ? __ldg(reinterpret_cast<const float4*>(rb1 - C)) : z;
+    const float4 o1 = __ldg(reinterpret_cast<const float4*>(rb1));
+    const float4 o2 = has_p3 ? __ldg(reinterpret_cast<const float4*>(rb1 + C)) : z;
+    // output 2q  : T columns 2q-1, 2q, 2q+1, 2q+2  = o0, e0, o1, e1 ;  output 2q+1: 2q, 2q+1, 2q+2, 2q+3 = e0, o1, e1, o2
+    oa.x = f0 * (o0.x + e1.x) + f1 * (e0.x + o1.x); oa.y = f0 * (o0.y + e1.y) + f1 * (e0.y + o1.y);
+    oa.z = f0 * (o0.z + e1.z) + f1 * (e0.z + o1.z); oa.w = f0 * (o0.w + e1.w) + f1 * (e0.w + o1.w);
+    ob.x = f0 * (e0.x + o2.x) + f1 * (o1.x + e1.x); ob.y = f0 * (e0.y + o2.y) + f1 * (o1.y + e1.y);
+    ob.z = f0 * (e0.z + o2.z) + f1 * (o1.z + e1.z); ob.w = f0 * (e0.w + o2.w) + f1 * (o1.w + e1.w);
   };
-  win[0] = hrow(h0); win[1] = hrow(h0 + 1); win[2] = hrow(h0 + 2);
+  hrow(h0, wa[0], wb[0]); hrow(h0 + 1, wa[1], wb[1]); hrow(h0 + 2, wa[2], wb[2]);
   float4 sc = make_float4(gain, gain, gain, gain);
   if (scale) {
     const float4 s = __ldg(reinterpret_cast<const float4*>(scale + (size_t)b * C + c));
@@ -127,14 +126,17 @@ __global__ void __launch_bounds__(256) blur_up_phases_kernel(const PhasePtrs P, 
   for (int i = 0; i < ROWS; ++i) {
     const int h = h0 + i;
     if (h >= Hout) break;
-    win[3] = hrow(h + 3);
+    hrow(h + 3, wa[3], wb[3]);
     float4 o;
-    o.x = (f0 * (win[0].x + win[3].x) + f1 * (win[1].x + win[2].x)) * sc.x;
-    o.y = (f0 * (win[0].y + win[3].y) + f1 * (win[1].y + win[2].y)) * sc.y;
-    o.z = (f0 * (win[0].z + win[3].z) + f1 * (win[1].z + win[2].z)) * sc.z;
-    o.w = (f0 * (win[0].w + win[3].w) + f1 * (win[1].w + win[2].w)) * sc.w;
-    *reinterpret_cast<float4*>(y + (((size_t)b * Hout + h) * Wout + w) * C + c) = o;
-    win[0] = win[1]; win[1] = win[2]; win[2] = win[3];
+    float* dst = y + (((size_t)b * Hout + h) * Wout + 2 * q) * C + c;
+    o.x = (f0 * (wa[0].x + wa[3].x) + f1 * (wa[1].x + wa[2].x)) * sc.x; o.y = (f0 * (wa[0].y + wa[3].y) + f1 * (wa[1].y + wa[2].y)) * sc.y;
+    o.z = (f0 * (wa[0].z + wa[3].z) + f1 * (wa[1].z + wa[2].z)) * sc.z; o.w = (f0 * (wa[0].w + wa[3].w) + f1 * (wa[1].w + wa[2].w)) * sc.w;
+    *reinterpret_cast<float4*>(dst) = o;
+    o.x = (f0 * (wb[0].x + wb[3].x) + f1 * (wb[1].x + wb[2].x)) * sc.x; o.y = (f0 * (wb[0].y + wb[3].y) + f1 * (wb[1].y + wb[2].y)) * sc.y;
+    o.z = (f0 * (wb[0].z + wb[3].z) + f1 * (wb[1].z + wb[2].z)) * sc.z; o.w = (f0 * (wb[0].w + wb[3].w) + f1 * (wb[1].w + wb[2].w)) * sc.w;
+    *reinterpret_cast<float4*>(dst + C) = o;
+    wa[0] = wa[1]; wa[1] = wa[2]; wa[2] = wa[3];
+    wb[0] = wb[1]; wb[1] = wb[2]; wb[2] = wb[3];
   }
 }
 
@@ -319,7 +321,7 @@ int gf_blur_up_phases_nhwc(const float* p00, const float* p01, const float* p10,
   constexpr int ROWS = 8;
   PhasePtrs P;
   P.p[0][0] = p00; P.p[0][1] = p01; P.p[1][0] = p10; P.p[1][1] = p11;
-  dim3 grid((Wout * (C >> 2) + 255) / 256, (Hout + ROWS - 1) / ROWS, B);
+  dim3 grid(((Wout >> 1) * (C >> 2) + 255) / 256, (Hout + ROWS - 1) / ROWS, B);
   blur_up_phases_kernel<ROWS><<<grid, 256, 0, (cudaStream_t)stream>>>(P, y, scale, Hout, Wout, C, gain);
   GF_LAUNCH_OK();
   return GF_OK;
