@@ -173,6 +173,46 @@ def duplex_attention_probe(device, peak_gbs: float, iters: int = 3):
             "unit": "GB/s", "frac": achieved / peak_gbs, "pass_a_path": cen_path}
 
 
+def duplex_generator_probe(device, steps: int = 5, warmup: int = 2, B: int = 64, k: int = 32, with_cpu: bool = True):
+    """BASELINE configs[2] end to end: the 256x256 generator with duplex attention (kmeans=True), K = 32 latents, batch 64,
+    CUDA-graph replay with the latents resident; next to the CPU oracle on a 2-image sample of the same network."""
+    import gansformer_b200 as gf
+    torch.manual_seed(0)
+    G = gf.Generator(resolution=RES, components_num=k, latent_dim=32, kmeans=True).to(device).eval()
+    g = torch.Generator().manual_seed(1)
+    z = torch.randn(B, k + 1, 32, generator=g).to(device)
+    with torch.no_grad():
+        for _ in range(2):
+            G(z)
+        replay = G.graphed(B)
+        for _ in range(warmup):
+            replay(z)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            replay(z)
+        e1.record()
+        torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3
+    out = {"workload": f"BASELINE configs[2]: 256x256 generator, duplex attention (kmeans), K={k} latents, batch {B}, 12 attention layers",
+           "images_per_s": B * steps / t, "ms_per_step": t / steps * 1e3, "steps": steps, "warmup": warmup,
+           "attention_path": gf._lib.last_path(), "pass_a_path": gf._lib.last_centroid_path()}
+    if with_cpu:
+        from oracle import generator as og
+        sd = {n: v.detach().cpu() for n, v in G.state_dict().items()}
+        zc = z[:2].cpu()
+        torch.set_num_threads(pick_cpu_threads())
+        t0 = time.perf_counter()
+        og.generator_forward(sd, zc, resolution=RES, components_num=k, latent_dim=32, duplex=True, dtype=torch.float32)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 2 / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": "1 step x 2 images of the same duplex generator, oracle/generator.py fp32"}
+    del replay, G
+    torch.cuda.empty_cache()
+    return out
+
+
 def train_probe(device, rank, world, steps: int = 2, warmup: int = 1, B: int = 32):
     """BASELINE configs[3]: one D + one G update of the 256x256 GANsformer (K = 16, simplex) on synthetic reals, batch 32 per
     GPU, gradients averaged over ranks through one flat all-reduce per network (NCCL).  Attention forward = the CUDA
@@ -360,6 +400,7 @@ def run_ours(args):
         line["train_step"] = tp
     if world == 1 and not args.no_duplex_probe:
         line["duplex_attention"] = duplex_attention_probe(device, peak)
+        line["duplex_generator"] = duplex_generator_probe(device, with_cpu=not args.no_cpu_baseline)
     if world == 1 and not args.no_cpu_baseline:
         ips, t, cores = cpu_oracle_run(G.state_dict(), steps=2, warmup=1, sample_b=2)
         line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",

@@ -44,7 +44,6 @@ static int token_pass(const Layout& L, const gf_attn_desc* d, const float* X, fl
   if (post && (post->act < 0 || post->act > 1)) { set_error("postop: act must be 0 (linear) or 1 (lrelu), got %d", post->act); return GF_ERR_INVALID; }
   if (post && (post->in_scale || post->post_scale)) {
     if (d->norm != GF_NORM_LAYER && d->norm != GF_NORM_NONE) { set_error("postop: in_scale/post_scale need norm layer or none"); return GF_ERR_UNSUPPORTED; }
-    if (d->duplex && post->in_scale) { set_error("postop: in_scale is not supported for duplex layers"); return GF_ERR_UNSUPPORTED; }
     if ((post->in_scale && (post->in_scale_ld < L.C || (post->in_scale_ld & 3) || ((uintptr_t)post->in_scale & 15))) ||
         (post->post_scale && (post->post_scale_ld < L.C || (post->post_scale_ld & 3) || ((uintptr_t)post->post_scale & 15)))) {
       set_error("postop: scale rows must be 16-byte aligned with ld >= C and ld %% 4 == 0");
@@ -157,14 +156,17 @@ int gf_attn_duplex_fwd_ex(const gf_attn_desc* desc, const float* X, const float*
   float* ws = (float*)ws_;
   cudaStream_t st = (cudaStream_t)stream;
   if (!(desc->flags & GF_FLAG_CENTROIDS_IN)) {
-    if ((rc = duplex_tables(L, desc, Y, folded, ws, st))) return rc;
+    // load-side scale d (x_in = x * d): pass A sees x only through x.M^T and A.x, so d is folded into M and into Xbar
+    const float* isc = post ? post->in_scale : nullptr;
+    const int isc_ld = post ? post->in_scale_ld : 0;
+    if ((rc = duplex_tables(L, desc, Y, folded, ws, st, isc, isc_ld))) return rc;
     const bool cen_tc = tc_centroid_supported(L, desc);
     if (cen_tc) {
       if ((rc = centroid_pass_tc(L, desc, X, ws, st))) return rc;
-      if ((rc = centroid_merge(L, ws, st))) return rc;
+      if ((rc = centroid_merge(L, ws, st, isc, isc_ld))) return rc;
       set_centroid_path(GF_PATH_TCGEN05_TF32);
     } else {
-      if ((rc = centroid_pass_simt(L, desc, X, ws, st))) return rc;
+      if ((rc = centroid_pass_simt(L, desc, X, ws, st, isc, isc_ld))) return rc;
       set_centroid_path(GF_PATH_SIMT_FP32);
     }
     // centroids = Xbar @ Wv2_e + bv2
@@ -172,7 +174,7 @@ int gf_attn_duplex_fwd_ex(const gf_attn_desc* desc, const float* X, const float*
                    nullptr, 0, 1, folded + L.f_BV2, cen_tc)))
       return rc;
   }
-  if ((rc = prologue(L, desc, Y, centroids_inout, L.C, folded, ws, st))) return rc;
+  if ((rc = prologue(L, desc, Y, centroids_inout, L.C, folded, ws, st, post ? post->in_scale : nullptr, post ? post->in_scale_ld : 0))) return rc;
   return token_pass(L, desc, X, Xout, att, ws, post, st);
 }
 

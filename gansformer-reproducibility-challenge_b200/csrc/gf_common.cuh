@@ -63,7 +63,8 @@ int fold_weights(const Layout& L, const gf_attn_desc* d, const gf_attn_weights* 
 // key_source: Y [B*k, D] (simplex) or centroids [B*k, C] (duplex); kdim = D or C.
 int prologue(const Layout& L, const gf_attn_desc* d, const float* Y, const float* key_source, int kdim,
              const float* folded, float* ws, cudaStream_t st, const float* in_scale = nullptr, int in_scale_ld = 0);
-int duplex_tables(const Layout& L, const gf_attn_desc* d, const float* Y, const float* folded, float* ws, cudaStream_t st);
+int duplex_tables(const Layout& L, const gf_attn_desc* d, const float* Y, const float* folded, float* ws, cudaStream_t st,
+                  const float* in_scale = nullptr, int in_scale_ld = 0);
 // C[M,N] = alpha * opA(A) opB(B) + E[(m % emod), n] + v[n]
 int gemm(cudaStream_t st, int M, int N, int K, const float* A, int lda, bool ta, const float* B, int ldb, bool tb,
          float* Cm, int ldc, float alpha, const float* E = nullptr, int lde = 0, int emod = 1, const float* v = nullptr,
@@ -76,8 +77,10 @@ int gemm_tc(cudaStream_t st, int M, int N, int K, const float* A, const float* B
 // ---- stage T kernels ----------------------------------------------------------------------------------
 int token_pass_simt(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, const gf_attn_postop* post, cudaStream_t st);
 int norm_stats(const Layout& L, const gf_attn_desc* d, const float* X, float* ws, cudaStream_t st);
-int centroid_pass_simt(const Layout& L, const gf_attn_desc* d, const float* X, float* ws, cudaStream_t st);
-int centroid_merge(const Layout& L, float* ws, cudaStream_t st);
+int centroid_pass_simt(const Layout& L, const gf_attn_desc* d, const float* X, float* ws, cudaStream_t st,
+                       const float* in_scale = nullptr, int in_scale_ld = 0);
+// Xbar = merge of the split partials (times the load-side scale, when given)
+int centroid_merge(const Layout& L, float* ws, cudaStream_t st, const float* in_scale = nullptr, int in_scale_ld = 0);
 // tcgen05 duplex pass A (gf_tc_cen.cu): partials into ws (same format as the CUDA-core kernel), then centroid_merge
 bool tc_centroid_supported(const Layout& L, const gf_attn_desc* d);
 int centroid_pass_tc(const Layout& L, const gf_attn_desc* d, const float* X, float* ws, cudaStream_t st);

@@ -469,7 +469,8 @@ int prologue(const Layout& L, const gf_attn_desc* d, const float* Y, const float
 }
 
 // duplex pass A tables: M [B,KP,C] and the positional logit tables of the latent queries
-int duplex_tables(const Layout& L, const gf_attn_desc* d, const float* Y, const float* f, float* ws, cudaStream_t st) {
+int duplex_tables(const Layout& L, const gf_attn_desc* d, const float* Y, const float* f, float* ws, cudaStream_t st,
+                  const float* in_scale, int in_scale_ld) {
   int rc;
   const int tf32 = tc_centroid_supported(L, d) ? 1 : 0;      // M is an operand of the tcgen05 pass-A kernel: pre-round it
   if ((rc = gemm(st, L.B * L.k, L.LDK, L.D, Y, L.D, false, f + L.f_AM, L.LDK, false, ws + L.w_MALL, L.LDK, 1.f,
@@ -479,7 +480,7 @@ int duplex_tables(const Layout& L, const gf_attn_desc* d, const float* Y, const 
   const int nblk = npos + (L.KP * L.C + 256 * 8 - 1) / (256 * 8);
   finalize_kernel<<<dim3(L.B, nblk), 256, 0, st>>>(ws + L.w_MALL, Y, nullptr, nullptr, f + L.f_ROW, f + L.f_COL,
                                                    ws + L.w_M, nullptr, ws + L.w_Rt2, ws + L.w_Ct2,
-                                                   L.H, L.W, L.C, L.k, L.D, L.p, L.KP, L.Cout, L.LDK, tf32, npos, nullptr, 0);
+                                                   L.H, L.W, L.C, L.k, L.D, L.p, L.KP, L.Cout, L.LDK, tf32, npos, in_scale, in_scale_ld);
   GF_LAUNCH_OK();
   return GF_OK;
 }

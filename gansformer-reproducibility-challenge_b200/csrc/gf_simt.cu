@@ -382,7 +382,8 @@ __global__ void __launch_bounds__(TM) centroid_simt_kernel(const CenParams P) {
 }
 
 // xbar[b,j,c] = sum_sp exp(m_sp - m) acc_sp[j][c] / sum_sp exp(m_sp - m) l_sp
-__global__ void centroid_merge_kernel(const float* __restrict__ part, float* __restrict__ xbar, int B, int k, int KP, int C, int nsplit) {
+__global__ void centroid_merge_kernel(const float* __restrict__ part, float* __restrict__ xbar, int B, int k, int KP, int C, int nsplit,
+                                      const float* __restrict__ in_scale, int in_ld) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * k * C) return;
   const int c = i % C, j = (i / C) % k, b = i / (C * k);
@@ -397,10 +398,10 @@ __global__ void centroid_merge_kernel(const float* __restrict__ part, float* __r
     num = fmaf(wgt, o[c], num);
     den = fmaf(wgt, o[C + 1], den);
   }
-  xbar[i] = num / den;
+  xbar[i] = num / den * (in_scale ? in_scale[(size_t)b * in_ld + c] : 1.f);     // Xbar of x_in = x * d
 }
 
-int centroid_pass_simt(const Layout& L, const gf_attn_desc* d, const float* X, float* ws, cudaStream_t st) {
+int centroid_pass_simt(const Layout& L, const gf_attn_desc* d, const float* X, float* ws, cudaStream_t st, const float* in_scale, int in_scale_ld) {
   (void)d;
   CenParams P;
   P.X = X; P.M = ws + L.w_M; P.Rt = ws + L.w_Rt2; P.Ct = ws + L.w_Ct2; P.part = ws + L.w_PART;
@@ -415,12 +416,12 @@ int centroid_pass_simt(const Layout& L, const gf_attn_desc* d, const float* X, f
     centroid_simt_kernel<32><<<grid, TM, dyn, st>>>(P);
   }
   GF_LAUNCH_OK();
-  return centroid_merge(L, ws, st);
+  return centroid_merge(L, ws, st, in_scale, in_scale_ld);
 }
 
-int centroid_merge(const Layout& L, float* ws, cudaStream_t st) {
+int centroid_merge(const Layout& L, float* ws, cudaStream_t st, const float* in_scale, int in_scale_ld) {
   const int tot = L.B * L.k * L.C;
-  centroid_merge_kernel<<<(tot + 255) / 256, 256, 0, st>>>(ws + L.w_PART, ws + L.w_XBAR, L.B, L.k, L.KP, L.C, L.nsplit_cen);
+  centroid_merge_kernel<<<(tot + 255) / 256, 256, 0, st>>>(ws + L.w_PART, ws + L.w_XBAR, L.B, L.k, L.KP, L.C, L.nsplit_cen, in_scale, in_scale_ld);
   GF_LAUNCH_OK();
   return GF_OK;
 }

@@ -162,7 +162,7 @@ class SynthesisLayer(nn.Module):
     def fusable(self, x) -> bool:
         """Inference on CUDA with an attention block whose norm the kernels can fuse around."""
         a = self.attention
-        return (a is not None and x.is_cuda and a.norm in ("layer", None, "none") and not a.duplex
+        return (a is not None and x.is_cuda and a.norm in ("layer", None, "none")
                 and _inference(self.weight, self.bias, self.noise_strength, *a.parameters()))
 
     def forward(self, x, w_glob, y, noise_mode="const", centroids=None, return_att=False, styles=None,
@@ -285,7 +285,7 @@ class SynthesisNetwork(nn.Module):
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 for li_, layer in enumerate(self.layers):
-                    if not layer.fusable(x):
+                    if not layer.fusable(x) or layer.attention.duplex:
                         continue
                     d_ = None
                     if not layer.up:

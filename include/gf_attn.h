@@ -66,8 +66,9 @@ typedef struct gf_attn_desc {
  *   load side :  x_in = X * in_scale[b,c]            (StyleGAN2 demodulation of the preceding convolution's output)
  *   store side:  x'' = act(x' + noise[b*noise_bstride + t] * (*strength) + bias[c]) * gain * post_scale[b,c]
  *                (noise input + fused_bias_act, then the style modulation of the NEXT convolution's input)
- * in_scale must be given to BOTH gf_attn_prologue_ex (it is folded into K') and gf_attn_simplex_fwd_ex.
- * Supported with norm layer/none, simplex; every member may be NULL. */
+ * in_scale must be given to BOTH gf_attn_prologue_ex (it is folded into K') and gf_attn_simplex_fwd_ex; gf_attn_duplex_fwd_ex
+ * additionally folds it into the pass-A query matrix and the centroid means (the latents see x_in too).
+ * The scales need norm layer/none; every member may be NULL. */
 typedef struct gf_attn_postop {
   const float* bias;         /* [C] or NULL */
   const float* noise;        /* [H*W] (noise_bstride = 0: shared by the batch) or [B][H*W]; NULL = no noise */

@@ -397,8 +397,9 @@ def test_autograd_matches_oracle(gf, cuda_dev):
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("exact", [True, False], ids=["fp32", "default"])
 @pytest.mark.parametrize("scales", [False, True], ids=["plain", "scales"])
+@pytest.mark.parametrize("duplex", [False, True], ids=["simplex", "duplex"])
 @pytest.mark.parametrize("C,H,W,k,random_noise", [(128, 16, 16, 16, False), (256, 16, 8, 8, True), (512, 8, 8, 4, False), (512, 16, 16, 16, False)])
-def test_attention_postop(gf, cuda_dev, C, H, W, k, random_noise, exact, scales):
+def test_attention_postop(gf, cuda_dev, C, H, W, k, random_noise, exact, scales, duplex):
     """Fused load side (demodulation scale) and store side (noise + bias + lrelu + next style scale) vs the oracle."""
     D = p = 16
     B = 3
@@ -413,13 +414,13 @@ def test_attention_postop(gf, cuda_dev, C, H, W, k, random_noise, exact, scales)
     bias = torch.randn(C, generator=g, dtype=torch.float64) * 0.5
     noise = torch.randn((B, 1, H, W) if random_noise else (H, W), generator=g, dtype=torch.float64)
     strength = torch.tensor(0.37, dtype=torch.float64)
-    w = ob.init_params(C, D, k, p, "both", False, seed=5, bias_std=0.3)
-    ref, _, _ = ob.transformer_layer(x64, y64, w, integration="both")
+    w = ob.init_params(C, D, k, p, "both", duplex, seed=5, bias_std=0.3)
+    ref, _, rcen = ob.transformer_layer(x64, y64, w, integration="both", duplex=duplex)
     ref = ref + noise * strength + bias[None, :, None, None]
     ref = torch.nn.functional.leaky_relu(ref, 0.2) * math.sqrt(2.0)
     if scales:
         ref = ref * ps[:, :, None, None]
-    attn = make_layer(gf, cuda_dev, C, D, k, p, "both", "layer", False, True, exact, w)
+    attn = make_layer(gf, cuda_dev, C, D, k, p, "both", "layer", duplex, True, exact, w)
     post = dict(bias=bias.float().to(cuda_dev), noise=noise.float().to(cuda_dev), strength=strength.float().to(cuda_dev),
                 act="lrelu", gain=math.sqrt(2.0))
     if scales:   # pass them as column slices of a wider matrix, as the generator does (row stride != C)
@@ -428,9 +429,13 @@ def test_attention_postop(gf, cuda_dev, C, H, W, k, random_noise, exact, scales)
         wide[:, 8 + C:] = ps.float().to(cuda_dev)
         post.update(in_scale=wide[:, 8:8 + C], post_scale=wide[:, 8 + C:])
     with torch.no_grad():
-        out, _, _ = attn(x_raw.permute(0, 2, 3, 1).contiguous().float().to(cuda_dev), y64.float().to(cuda_dev), postop=post)
+        out, _, cen = attn(x_raw.permute(0, 2, 3, 1).contiguous().float().to(cuda_dev), y64.float().to(cuda_dev), postop=post)
     # with the per-channel scales the error of the block is multiplied by |post_scale| (up to ~4): tolerance x2
-    check_close(out, ref.permute(0, 2, 3, 1), gf._lib.last_path(), "postop", tol_scale=2.0 if scales else 1.0)
+    # (x2 again for duplex in fp32 mode: two chained [B*k, C] x [C, C] products between pass A and the keys)
+    check_close(out, ref.permute(0, 2, 3, 1), gf._lib.last_path(), "postop",
+                tol_scale=(2.0 if scales else 1.0) * (2.0 if (duplex and exact) else 1.0))
+    if duplex:                                   # the load-side scale reaches the latents' view of the image too
+        check_close(cen, rcen, gf._lib.last_centroid_path(), "postop/centroids")
 
 
 def test_native_ops_match_definitions(gf, cuda_dev):
