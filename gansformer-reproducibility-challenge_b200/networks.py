@@ -390,13 +390,40 @@ class Generator(nn.Module):
         n = lat.shape[0]
         noise_mode = "random" if randomize_noise else "const"
         res = out if out is not None else torch.empty((n, 3, self.resolution, self.resolution), dtype=torch.float32)
-        for i in range(0, n, minibatch_size):
+        if dev.type != "cuda":
+            for i in range(0, n, minibatch_size):
+                z = lat[i:i + minibatch_size].to(dev)
+                res[i:i + z.shape[0]].copy_(self(z, truncation_psi=truncation_psi, noise_mode=noise_mode))
+            return res
+        # CUDA: the device->host copy of minibatch i runs on a copy stream while minibatch i+1 computes (two staging buffers;
+        # effective with pinned `out` / latents)
+        main = torch.cuda.current_stream(dev)
+        copy_stream = self.__dict__.get("_copy_stream")
+        if copy_stream is None or copy_stream.device != dev:
+            copy_stream = self.__dict__["_copy_stream"] = torch.cuda.Stream(device=dev)
+        skey = ("_staging", minibatch_size)
+        staging = self.__dict__.get(skey)
+        if staging is None or staging[0].device != dev:
+            staging = self.__dict__[skey] = [torch.empty((minibatch_size, 3, self.resolution, self.resolution), device=dev) for _ in range(2)]
+        d2h_done = [None, None]
+        for idx, i in enumerate(range(0, n, minibatch_size)):
             z = lat[i:i + minibatch_size].to(dev, non_blocking=True)
-            if cuda_graph and dev.type == "cuda" and z.shape[0] == minibatch_size:
+            m = z.shape[0]
+            if cuda_graph and m == minibatch_size:
                 img = self.graphed(minibatch_size, truncation_psi, noise_mode)(z)
             else:
                 img = self(z, truncation_psi=truncation_psi, noise_mode=noise_mode)
-            res[i:i + z.shape[0]].copy_(img, non_blocking=True)
-        if dev.type == "cuda":
-            torch.cuda.current_stream(dev).synchronize()
+            sidx = idx & 1
+            if d2h_done[sidx] is not None:
+                main.wait_event(d2h_done[sidx])                 # the copy that last read this staging buffer has finished
+            staging[sidx][:m].copy_(img)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ready)
+                res[i:i + m].copy_(staging[sidx][:m], non_blocking=True)
+                d2h_done[sidx] = torch.cuda.Event()
+                d2h_done[sidx].record(copy_stream)
+        copy_stream.synchronize()
+        main.synchronize()
         return res
