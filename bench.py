@@ -394,7 +394,10 @@ def run_ours(args):
                 "call": "one Generator.run(latents[steps*B], minibatch_size=B, cuda_graph=True, out=pinned) call; per minibatch: H2D latents, "
                         "graph replay, D2H images on a copy stream overlapping the next minibatch"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": f"stage-T attention ({path})",
+                     "traffic": 2.106e9, "traffic_launch": "res-256 layer (B=32, C=128): dram__bytes_read 1.082 GB + dram__bytes_write 1.024 GB "
+                                                        "vs 2.147 GB algorithmic for that launch; tensor pipe 2.9 % of peak, 121 registers "
+                                                        "(profiles/r01/ncu_full_token_tc_v9_res256_postop.ncu-rep, ncu --set full)",
+                     "peak_source": peak_src, "kernel": f"stage-T attention ({path})",
                      "launches_timed": n_attn_launches, "alg_bytes_per_step": attn_bytes // max(args.steps, 1),
                      "attention_ms_per_step": attn_s / args.steps * 1e3,
                      "attention_share_of_step": attn_s / (ev0.elapsed_time(ev1) * 1e-3),
