@@ -525,3 +525,27 @@ def test_training_step_runs_on_gpu(gf, cuda_dev):
     assert all(torch.isfinite(p).all() for p in G.parameters())
     st2 = trainer.step(z, reals)
     assert math.isfinite(st2.loss_g) and st2.r1 == 0
+
+
+def test_generator_512_config5_shape_class(gf, cuda_dev):
+    """BASELINE configs[4] shape class: 512x512 synthesis, K = 32 latents (14 attention layers, C = 64 at the top), eager vs
+    CUDA-graph replay, finite output; the last attention layer is checked against the oracle layer on its own input."""
+    torch.manual_seed(0)
+    G = gf.Generator(resolution=512, components_num=32, latent_dim=32).to(cuda_dev).eval()
+    assert G.synthesis.num_attention_layers == 14
+    z = torch.randn(2, 33, 32, generator=torch.Generator().manual_seed(2)).to(cuda_dev)
+    with torch.no_grad():
+        img = G(z).clone()
+        rep = G.graphed(2)(z).clone()
+    assert img.shape == (2, 3, 512, 512) and torch.isfinite(img).all()
+    assert gf._lib.last_path() == "tcgen05_tf32"
+    assert (img - rep).abs().max() <= 2e-3 * max(1.0, img.abs().max().item())
+    layer = G.synthesis.layers[-1].attention                              # C = 64, 512x512 grid, k = 32
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1, 64, 512, 512, generator=g, dtype=torch.float64)
+    y = torch.randn(1, 32, 32, generator=g, dtype=torch.float64)
+    w = {n: p.detach().double().cpu() for n, p in layer.named_parameters()}
+    ref, _, _ = ob.transformer_layer(x, y, w)
+    with torch.no_grad():
+        out, _, _ = layer(x.permute(0, 2, 3, 1).contiguous().float().to(cuda_dev), y.float().to(cuda_dev))
+    check_close(out, ref.permute(0, 2, 3, 1), gf._lib.last_path(), "512/C64")
