@@ -213,7 +213,7 @@ def duplex_generator_probe(device, steps: int = 5, warmup: int = 2, B: int = 64,
     return out
 
 
-def train_probe(device, rank, world, steps: int = 2, warmup: int = 1, B: int = 32):
+def train_probe(device, rank, world, steps: int = 3, warmup: int = 1, B: int = 32, graphed: bool = True):
     """BASELINE configs[3]: one D + one G update of the 256x256 GANsformer (K = 16, simplex) on synthetic reals, batch 32 per
     GPU, gradients averaged over ranks through one flat all-reduce per network (NCCL).  Attention forward = the CUDA
     kernels, attention backward = composite torch autograd (autograd.py); convolutions and the discriminator = cuDNN."""
@@ -228,27 +228,44 @@ def train_probe(device, rank, world, steps: int = 2, warmup: int = 1, B: int = 3
     g = torch.Generator().manual_seed(4)
     z = dist_mod.shard_batch(torch.randn(world * B, K_LATENTS + 1, G.latent_dim, generator=g), rank, world).to(device)
     reals = dist_mod.shard_batch(torch.rand(world * B, 3, RES, RES, generator=g) * 2 - 1, rank, world).to(device)
+    do_step = trainer.step_graphed if graphed else trainer.step
+    trainer.it = 1                                   # timed steps are the common case (no lazy R1 term: 15 of 16 steps)
     for _ in range(warmup):
-        trainer.step(z, reals)
+        do_step(z, reals)
+        trainer.it = 1
     dist_mod.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    ar_ms, ar_bytes, last = 0.0, 0.0, None
+    last = None
     for _ in range(steps):
-        last = trainer.step(z, reals)
-        ar_ms += last.allreduce_ms
-        ar_bytes = last.allreduce_bytes
+        last = do_step(z, reals)
+        trainer.it = 1
     e1.record()
     torch.cuda.synchronize()
     dist_mod.barrier()
     t = dist_mod.max_over_ranks(e0.elapsed_time(e1) * 1e-3, device=device)
+    # the collective on its own (inside a replayed graph it cannot be bracketed by events): both networks' flat buffers
+    ar_ms, ar_bytes = 0.0, 0.0
+    if world > 1:
+        for p in list(G.parameters()) + list(D.parameters()):
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist_mod.barrier()
+        a0.record()
+        ar_bytes = dist_mod.allreduce_gradients(D.parameters(), world) + dist_mod.allreduce_gradients(G.parameters(), world)
+        a1.record()
+        torch.cuda.synchronize()
+        ar_ms = a0.elapsed_time(a1) * steps
     out = {"workload": "BASELINE configs[3]: 256x256 G+D training step (logistic NS + lazy R1, Adam, EMA), synthetic reals, "
                        f"batch {B}/GPU, data-parallel dp{world}", "images_per_s": world * B * steps / t, "ms_per_step": t / steps * 1e3,
            "global_batch": world * B, "steps": steps, "warmup": warmup, "allreduce_ms_per_step": ar_ms / steps,
            "allreduce_bytes_per_step": ar_bytes, "loss_g": last.loss_g, "loss_d": last.loss_d,
            "peak_mem_gb": torch.cuda.max_memory_allocated(device) / 2 ** 30,
-           "backward": "attention: CUDA forward + composite torch-autograd backward; convolutions / discriminator: cuDNN"}
+           "cuda_graph": bool(graphed),
+           "backward": "attention: CUDA forward + composite torch-autograd backward; FIR filters: native (self-adjoint) kernel; "
+                       "convolutions / discriminator: cuDNN"}
     del trainer, G, D
     torch.cuda.empty_cache()
     return out
@@ -373,7 +390,7 @@ def run_ours(args):
     dist_mod.barrier()
     t_e2e = dist_mod.max_over_ranks(e0.elapsed_time(e1) * 1e-3, device)
 
-    tp = train_probe(device, rank, world) if args.train_probe else None      # every rank takes part (gradient all-reduce)
+    tp = train_probe(device, rank, world, graphed=not args.no_cuda_graph) if args.train_probe else None      # every rank takes part (gradient all-reduce)
     if rank != 0:
         return 0
     peak, peak_src = measured_peak_gbs()

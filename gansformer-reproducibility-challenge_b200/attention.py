@@ -55,6 +55,9 @@ class StageTimer:
 STAGE_TIMER: Optional[StageTimer] = None
 
 
+FORCE_REFOLD = False      # set by training.Trainer while it captures a CUDA graph (see networks.CACHE_BYPASS)
+
+
 class _Plan:
     """Folded weights + workspace for one (shape, config); owns the device buffers the library writes into."""
 
@@ -125,7 +128,7 @@ def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[s
         if weights_version is None:
             weights_version = tuple((params[n].data_ptr(), params[n]._version) for n in names)
         fkey = (H, W, k, D, C, pos_dim, integration, duplex, str(dev), weights_version)
-        if plan.folded is None or plan.folded_key != fkey:
+        if plan.folded is None or plan.folded_key != fkey or FORCE_REFOLD:
             nfl = _lib.folded_floats(desc)
             if plan.folded is None or plan.folded.numel() != nfl or plan.folded.device != dev:
                 plan.folded = torch.empty(nfl, dtype=torch.float32, device=dev)

@@ -32,8 +32,15 @@ def _inference(*params) -> bool:
     return not (torch.is_grad_enabled() and any(p.requires_grad for p in params))
 
 
+CACHE_BYPASS = False      # set by training.Trainer while it captures a CUDA graph: weight-derived tensors must be recomputed
+                          # inside the graph on every replay (a replay runs no Python, so a version-keyed cache would go stale)
+
+
 def _cached(module: nn.Module, key: str, params, fn):
     """Cache `fn()` on `module` until one of `params` changes (version counter / storage / device)."""
+    if CACHE_BYPASS:
+        with torch.no_grad():
+            return fn()
     ver = tuple((p.data_ptr(), p._version, str(p.device), p.dtype) for p in params)
     store = module.__dict__.setdefault("_icache", {})
     ent = store.get(key)

@@ -125,9 +125,9 @@ def upconv_phase_weights(w: torch.Tensor):
     out = []
     for a in (0, 1):
         for b in (0, 1):
-            ky = [2, 0] if a == 0 else [1]
-            kx = [2, 0] if b == 0 else [1]
-            out.append((w[:, :, ky][:, :, :, kx].contiguous(memory_format=torch.channels_last), (1 - a, 1 - b)))
+            wy = w[:, :, 0::2].flip(2) if a == 0 else w[:, :, 1:2]        # taps (2, 0) / (1,) -- slices, no host index tensors
+            wk = wy[:, :, :, 0::2].flip(3) if b == 0 else wy[:, :, :, 1:2]   # (capturable in a CUDA graph)
+            out.append((wk.contiguous(memory_format=torch.channels_last), (1 - a, 1 - b)))
     return out
 
 

@@ -123,15 +123,16 @@ class Trainer:
         self.G, self.D, self.cfg, self.world = G, D, cfg or TrainConfig(), world
         self.G_ema = copy.deepcopy(G).eval().requires_grad_(False)
         c = self.cfg.d_reg_interval / (self.cfg.d_reg_interval + 1.0)  # lazy regularisation: rescale lr and betas
-        self.opt_g = torch.optim.Adam(G.parameters(), lr=self.cfg.lr, betas=(0.0, 0.99), eps=1e-8)
-        self.opt_d = torch.optim.Adam(D.parameters(), lr=self.cfg.lr * c, betas=(0.0 ** c, 0.99 ** c), eps=1e-8)
+        cap = next(G.parameters()).is_cuda                              # capturable: the step can be replayed from a CUDA graph
+        self.opt_g = torch.optim.Adam(G.parameters(), lr=self.cfg.lr, betas=(0.0, 0.99), eps=1e-8, capturable=cap)
+        self.opt_d = torch.optim.Adam(D.parameters(), lr=self.cfg.lr * c, betas=(0.0 ** c, 0.99 ** c), eps=1e-8, capturable=cap)
         self.it = 0
 
     def _allreduce(self, module: nn.Module, stats: StepStats):
         if self.world <= 1:
             return
         dev = next(module.parameters()).device
-        if dev.type == "cuda":
+        if dev.type == "cuda" and not torch.cuda.is_current_stream_capturing():
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             stats.allreduce_bytes += gdist.allreduce_gradients(module.parameters(), self.world)
@@ -140,23 +141,23 @@ class Trainer:
         else:
             stats.allreduce_bytes += gdist.allreduce_gradients(module.parameters(), self.world)
 
-    def step(self, z: torch.Tensor, reals: torch.Tensor) -> StepStats:
+    def _step_tensors(self, z: torch.Tensor, reals: torch.Tensor, do_r1: bool, stats: Optional[StepStats] = None):
+        """One D update + one G update; returns (loss_d, loss_g, r1) as device tensors without synchronising (capturable)."""
         G, D, cfg = self.G, self.D, self.cfg
-        stats = StepStats()
+        stats = stats if stats is not None else StepStats()
         # ---- discriminator: logistic loss (+ lazy R1 on the reals)
         G.requires_grad_(False); D.requires_grad_(True)
         self.opt_d.zero_grad(set_to_none=True)
         with torch.no_grad():
             fakes = G(z, noise_mode=cfg.noise_mode)
-        do_r1 = cfg.r1_gamma > 0 and self.it % cfg.d_reg_interval == 0
         reals_in = reals.detach().requires_grad_(do_r1)
         logit_real, logit_fake = D(reals_in), D(fakes)
         loss_d = F.softplus(logit_fake).mean() + F.softplus(-logit_real).mean()
+        r1 = torch.zeros((), device=z.device)
         if do_r1:
             (grad,) = torch.autograd.grad(logit_real.sum(), reals_in, create_graph=True)
             r1 = grad.square().sum(dim=[1, 2, 3]).mean()
             loss_d = loss_d + r1 * (cfg.r1_gamma * 0.5 * cfg.d_reg_interval)
-            stats.r1 = float(r1.detach())
         loss_d.backward()
         self._allreduce(D, stats)
         self.opt_d.step()
@@ -174,9 +175,52 @@ class Trainer:
                 pe.lerp_(p.detach(), 1.0 - beta)
             for be, b in zip(self.G_ema.buffers(), G.buffers()):
                 be.copy_(b)
-        stats.loss_d, stats.loss_g = float(loss_d.detach()), float(loss_g.detach())
+        return loss_d.detach(), loss_g.detach(), r1.detach()
+
+    def step(self, z: torch.Tensor, reals: torch.Tensor) -> StepStats:
+        stats = StepStats()
+        do_r1 = self.cfg.r1_gamma > 0 and self.it % self.cfg.d_reg_interval == 0
+        loss_d, loss_g, r1 = self._step_tensors(z, reals, do_r1, stats)
+        stats.loss_d, stats.loss_g, stats.r1 = float(loss_d), float(loss_g), float(r1)
         for e0, e1 in stats.extra.pop("_events", []):
             e1.synchronize()
             stats.allreduce_ms += e0.elapsed_time(e1)
         self.it += 1
         return stats
+
+    def step_graphed(self, z: torch.Tensor, reals: torch.Tensor) -> StepStats:
+        """The same step replayed from a CUDA graph (one graph with the lazy R1 term, one without): the eager step is bound by
+        the host launching ~5000 small kernels.  Shapes are fixed by the first call; the first calls warm up eagerly."""
+        from . import attention as _att, networks as _nets
+        cfg = self.cfg
+        do_r1 = cfg.r1_gamma > 0 and self.it % cfg.d_reg_interval == 0
+        st = self.__dict__.setdefault("_graphs", {})
+        _nets.CACHE_BYPASS = _att.FORCE_REFOLD = True                  # weight-derived tensors are recomputed inside the graph
+        try:
+            return self._step_graphed(z, reals, do_r1, st)
+        finally:
+            _nets.CACHE_BYPASS = _att.FORCE_REFOLD = False
+
+    def _step_graphed(self, z, reals, do_r1, st) -> StepStats:
+        cfg = self.cfg
+        if "z" not in st:
+            st["z"], st["reals"] = torch.empty_like(z), torch.empty_like(reals)
+            st["z"].copy_(z); st["reals"].copy_(reals)
+            side = torch.cuda.Stream(device=z.device)                 # warm-up off the capture stream: cuDNN autotune, workspaces
+            side.wait_stream(torch.cuda.current_stream(z.device))
+            with torch.cuda.stream(side):
+                for r in ([True, False] if cfg.r1_gamma > 0 else [False]):
+                    self._step_tensors(st["z"], st["reals"], r)
+            torch.cuda.current_stream(z.device).wait_stream(side)
+            torch.cuda.synchronize(z.device)
+        st["z"].copy_(z); st["reals"].copy_(reals)
+        if do_r1 not in st:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                outs = self._step_tensors(st["z"], st["reals"], do_r1)
+            st[do_r1] = (graph, outs)
+            # (capture does not execute: fall through to the replay below)
+        graph, (loss_d, loss_g, r1) = st[do_r1]
+        graph.replay()
+        self.it += 1
+        return StepStats(loss_g=float(loss_g), loss_d=float(loss_d), r1=float(r1))

@@ -549,3 +549,27 @@ def test_generator_512_config5_shape_class(gf, cuda_dev):
     with torch.no_grad():
         out, _, _ = layer(x.permute(0, 2, 3, 1).contiguous().float().to(cuda_dev), y.float().to(cuda_dev))
     check_close(out, ref.permute(0, 2, 3, 1), gf._lib.last_path(), "512/C64")
+
+
+def test_training_step_graph_replay(gf, cuda_dev):
+    """Trainer.step_graphed: the captured step (with and without the lazy R1 term) trains -- weights keep moving across
+    replays (weight-derived tensors are recomputed inside the graph) and losses stay finite."""
+    from importlib import import_module
+    tr = import_module("gansformer-reproducibility-challenge_b200.training")
+    torch.manual_seed(0)
+    G = gf.Generator(resolution=64, components_num=8, latent_dim=32, fmap_base=2048, fmap_max=128, mapping_layers=4).to(cuda_dev)
+    D = tr.Discriminator(64, fmap_base=2048, fmap_max=128).to(cuda_dev)
+    trainer = tr.Trainer(G, D, tr.TrainConfig(d_reg_interval=2))
+    g = torch.Generator().manual_seed(5)
+    z = torch.randn(4, 9, 32, generator=g).to(cuda_dev)
+    reals = (torch.rand(4, 3, 64, 64, generator=g) * 2 - 1).to(cuda_dev)
+    snaps, stats = [], []
+    for i in range(5):
+        stats.append(trainer.step_graphed(z, reals))
+        snaps.append(torch.cat([p.detach().reshape(-1) for p in G.synthesis.layers[2].attention.parameters()]).clone())
+    assert all(math.isfinite(s.loss_g) and math.isfinite(s.loss_d) for s in stats)
+    assert [s.r1 > 0 for s in stats] == [True, False, True, False, True]
+    for a, b in zip(snaps, snaps[1:]):
+        assert (a - b).abs().max() > 0                       # every replay updates the attention weights
+    # the fakes of the D step follow the updated generator: the fake logits' loss changes from replay to replay
+    assert len({round(s.loss_d, 6) for s in stats}) > 1
