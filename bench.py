@@ -155,11 +155,11 @@ def duplex_attention_probe(device, peak_gbs: float, iters: int = 3):
         attn = gf.BipartiteAttention(C, D, k, kmeans=True).to(device)
         with torch.no_grad():
             for i in range(2):
-                attn(xs[i & 1], y, out=out)
+                attn(xs[i & 1], y, out=out, need_centroids=False)      # as the synthesis network calls it
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for i in range(iters):
-                attn(xs[i & 1], y, out=out)
+                attn(xs[i & 1], y, out=out, need_centroids=False)
             e1.record()
             torch.cuda.synchronize()
         tot_ms += 2 * e0.elapsed_time(e1) / iters            # two attention layers per resolution

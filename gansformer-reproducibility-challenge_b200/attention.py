@@ -87,7 +87,8 @@ def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[s
                                 num_heads: int = 1, use_pos: bool = True, return_att: bool = False,
                                 centroids: Optional[torch.Tensor] = None, exact_fp32: bool = False,
                                 out: Optional[torch.Tensor] = None, weights_version=None, postop: Optional[dict] = None,
-                                stage: str = "all", x_shape: Optional[Tuple[int, int, int, int]] = None):
+                                stage: str = "all", x_shape: Optional[Tuple[int, int, int, int]] = None,
+                                need_centroids: bool = True):
     """x [B,H,W,C] channels-last fp32 (CUDA), y [B,k,D].  Returns (x', att [B,k,H,W] | None, centroids | None).
 
     postop (optional): dict(bias [C] | None, noise [H*W] or [B,H*W] | None, strength 0-d tensor | None, act 'lrelu' |
@@ -191,12 +192,14 @@ def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[s
             if timer is not None:
                 ev0.record()
             if centroids is None:
-                cen = torch.empty((B, k, C), dtype=torch.float32, device=dev)
+                # need_centroids=False: the keys are built straight from the attention-weighted means (Wv2 / bv2 folded into
+                # the key projection), one [B*k, C] x [C, C] product less on the critical path
+                cen = torch.empty((B, k, C), dtype=torch.float32, device=dev) if need_centroids else None
             else:
                 _check_tensor(centroids, "centroids", dev)
                 cen = centroids
             _lib.check(lib.gf_attn_duplex_fwd_ex(ctypes.byref(desc), x.data_ptr(), y.data_ptr(), plan.folded.data_ptr(),
-                                                 out.data_ptr(), _ptr(att), cen.data_ptr(), ws.data_ptr(), post_ref, stream),
+                                                 out.data_ptr(), _ptr(att), _ptr(cen), ws.data_ptr(), post_ref, stream),
                        "gf_attn_duplex_fwd_ex")
         else:
             cen = None
@@ -246,7 +249,7 @@ class BipartiteAttention(nn.Module):
 
     def forward(self, x: torch.Tensor, y: torch.Tensor, centroids: Optional[torch.Tensor] = None,
                 return_att: bool = False, out: Optional[torch.Tensor] = None, postop: Optional[dict] = None,
-                stage: str = "all"):
+                stage: str = "all", need_centroids: bool = True):
         """x [B,H,W,C] channels-last, y [B,k,D] -> (x', att [B,k,H,W] | None, centroids [B,k,C] | None).
         stage="token": the per-image tables were already built by ``prepare`` (same y, same in_scale)."""
         if torch.is_grad_enabled() and (x.requires_grad or y.requires_grad or any(p.requires_grad for p in self.parameters())):
@@ -257,7 +260,8 @@ class BipartiteAttention(nn.Module):
         return bipartite_attention_forward(x, y, self.param_dict(), self._plan, integration=self.integration,
                                            norm=self.norm, duplex=self.duplex, num_heads=self.num_heads,
                                            use_pos=self.use_pos, return_att=return_att, centroids=centroids,
-                                           exact_fp32=self.exact_fp32, out=out, postop=postop, stage=stage)
+                                           exact_fp32=self.exact_fp32, out=out, postop=postop, stage=stage,
+                                           need_centroids=need_centroids)
 
     @torch.no_grad()
     def prepare(self, y: torch.Tensor, x_shape: Tuple[int, int, int, int], in_scale: Optional[torch.Tensor] = None):

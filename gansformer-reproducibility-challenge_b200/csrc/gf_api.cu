@@ -151,7 +151,8 @@ int gf_attn_duplex_fwd_ex(const gf_attn_desc* desc, const float* X, const float*
   int rc = make_layout(desc, &L);
   if (rc) return rc;
   if (!L.duplex) { set_error("gf_attn_duplex_fwd: desc.duplex is 0"); return GF_ERR_INVALID; }
-  if (!X || !Y || !folded || !Xout || !centroids_inout || !ws_) { set_error("gf_attn_duplex_fwd: null pointer"); return GF_ERR_INVALID; }
+  if (!X || !Y || !folded || !Xout || !ws_) { set_error("gf_attn_duplex_fwd: null pointer"); return GF_ERR_INVALID; }
+  if (!centroids_inout && (desc->flags & GF_FLAG_CENTROIDS_IN)) { set_error("gf_attn_duplex_fwd: GF_FLAG_CENTROIDS_IN without centroids"); return GF_ERR_INVALID; }
   if ((rc = check_device())) return rc;
   float* ws = (float*)ws_;
   cudaStream_t st = (cudaStream_t)stream;
@@ -162,19 +163,21 @@ int gf_attn_duplex_fwd_ex(const gf_attn_desc* desc, const float* X, const float*
     if ((rc = duplex_tables(L, desc, Y, folded, ws, st, isc, isc_ld))) return rc;
     const bool cen_tc = tc_centroid_supported(L, desc);
     if (cen_tc) {
-      if ((rc = centroid_pass_tc(L, desc, X, ws, st))) return rc;
-      if ((rc = centroid_merge(L, ws, st, isc, isc_ld))) return rc;
+      if ((rc = centroid_pass_tc(L, desc, X, ws, st, isc, isc_ld))) return rc;
+      if (L.nsplit_cen > 1 && (rc = centroid_merge(L, ws, st, isc, isc_ld))) return rc;   // one split: the kernel wrote Xbar itself
       set_centroid_path(GF_PATH_TCGEN05_TF32);
     } else {
       if ((rc = centroid_pass_simt(L, desc, X, ws, st, isc, isc_ld))) return rc;
       set_centroid_path(GF_PATH_SIMT_FP32);
     }
-    // centroids = Xbar @ Wv2_e + bv2
-    if ((rc = gemm(st, L.B * L.k, L.C, L.C, ws + L.w_XBAR, L.C, false, folded + L.f_WV2, L.C, false, centroids_inout, L.C, 1.f,
+    // centroids = Xbar @ Wv2_e + bv2 (skipped when the caller does not want them: the keys then come straight from Xbar)
+    if (centroids_inout && (rc = gemm(st, L.B * L.k, L.C, L.C, ws + L.w_XBAR, L.C, false, folded + L.f_WV2, L.C, false, centroids_inout, L.C, 1.f,
                    nullptr, 0, 1, folded + L.f_BV2, cen_tc)))
       return rc;
   }
-  if ((rc = prologue(L, desc, Y, centroids_inout, L.C, folded, ws, st, post ? post->in_scale : nullptr, post ? post->in_scale_ld : 0))) return rc;
+  if ((rc = prologue(L, desc, Y, centroids_inout ? centroids_inout : ws + L.w_XBAR, L.C, folded, ws, st, post ? post->in_scale : nullptr,
+                     post ? post->in_scale_ld : 0, centroids_inout == nullptr)))
+    return rc;
   return token_pass(L, desc, X, Xout, att, ws, post, st);
 }
 

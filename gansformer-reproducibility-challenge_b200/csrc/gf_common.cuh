@@ -48,6 +48,7 @@ struct Layout {
   size_t w_KPALL, w_Kp, w_Vt, w_Rt, w_Ct;             // keys / values / positional logit tables
   size_t w_NSCALE, w_NSHIFT, w_NPART;                 // instance/batch norm statistics
   size_t w_MALL, w_M, w_Rt2, w_Ct2, w_PART, w_XBAR;   // duplex pass A
+  size_t f_AK2, f_CK2;                                // duplex: keys straight from Xbar (Wv2 and bv2 folded into AK / CK)
   size_t w_total;
   int nsplit_norm, nsplit_cen;
 };
@@ -62,7 +63,8 @@ int make_layout(const gf_attn_desc* d, Layout* L);
 int fold_weights(const Layout& L, const gf_attn_desc* d, const gf_attn_weights* w, float* folded, cudaStream_t st);
 // key_source: Y [B*k, D] (simplex) or centroids [B*k, C] (duplex); kdim = D or C.
 int prologue(const Layout& L, const gf_attn_desc* d, const float* Y, const float* key_source, int kdim,
-             const float* folded, float* ws, cudaStream_t st, const float* in_scale = nullptr, int in_scale_ld = 0);
+             const float* folded, float* ws, cudaStream_t st, const float* in_scale = nullptr, int in_scale_ld = 0,
+             bool keys_from_xbar = false);
 int duplex_tables(const Layout& L, const gf_attn_desc* d, const float* Y, const float* folded, float* ws, cudaStream_t st,
                   const float* in_scale = nullptr, int in_scale_ld = 0);
 // C[M,N] = alpha * opA(A) opB(B) + E[(m % emod), n] + v[n]
@@ -83,7 +85,9 @@ int centroid_pass_simt(const Layout& L, const gf_attn_desc* d, const float* X, f
 int centroid_merge(const Layout& L, float* ws, cudaStream_t st, const float* in_scale = nullptr, int in_scale_ld = 0);
 // tcgen05 duplex pass A (gf_tc_cen.cu): partials into ws (same format as the CUDA-core kernel), then centroid_merge
 bool tc_centroid_supported(const Layout& L, const gf_attn_desc* d);
-int centroid_pass_tc(const Layout& L, const gf_attn_desc* d, const float* X, float* ws, cudaStream_t st);
+// in_scale: only used when the split count is 1 and the kernel writes the normalised Xbar itself (no merge kernel)
+int centroid_pass_tc(const Layout& L, const gf_attn_desc* d, const float* X, float* ws, cudaStream_t st,
+                     const float* in_scale = nullptr, int in_scale_ld = 0);
 // tcgen05 / TMA path (gf_tc.cu).  tc_supported() says whether the shape is served by it.
 bool tc_supported(const Layout& L, const gf_attn_desc* d);
 int token_pass_tc(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, const gf_attn_postop* post, cudaStream_t st);

@@ -49,12 +49,14 @@ int make_layout(const gf_attn_desc* d, Layout* L) {
   if (l.duplex) {
     l.f_WV2 = take(C * C);
     l.f_BV2 = take(C);
+    l.f_AK2 = take(C * LDK);
+    l.f_CK2 = take(k * LDK);
     l.f_AM = take(D * LDK);
     l.f_CM = take(k * LDK);
     l.f_MFOLD = take(C * LDK);
     l.f_QCONST = take(k * C);
   } else {
-    l.f_WV2 = l.f_BV2 = l.f_AM = l.f_CM = l.f_MFOLD = l.f_QCONST = 0;
+    l.f_WV2 = l.f_BV2 = l.f_AM = l.f_CM = l.f_MFOLD = l.f_QCONST = l.f_AK2 = l.f_CK2 = 0;
   }
   l.f_total = o;
 
@@ -273,6 +275,14 @@ __global__ void pos_axis_kernel(float* __restrict__ out, int length, int dim) {
   }
 }
 
+// out[j, :] = row0(out) + add[j, :] for j = k-1 .. 0 (row 0 last: it is the source)
+__global__ void bias_rows_kernel(float* __restrict__ out, const float* __restrict__ add, int k, int ld) {
+  for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < (size_t)ld; c += (size_t)gridDim.x * blockDim.x) {
+    const float r0 = out[c];
+    for (int j = k - 1; j >= 0; --j) out[(size_t)j * ld + c] = r0 + add[(size_t)j * ld + c];
+  }
+}
+
 static inline int blocks_for(size_t nel) { size_t b = (nel + 255) / 256; return (int)(b > 1184 ? 1184 : (b < 1 ? 1 : b)); }
 
 int fold_weights(const Layout& L, const gf_attn_desc* d, const gf_attn_weights* w, float* f, cudaStream_t st) {
@@ -300,6 +310,11 @@ int fold_weights(const Layout& L, const gf_attn_desc* d, const gf_attn_weights* 
     scale_copy_kernel<<<blocks_for((size_t)C * C), 256, 0, st>>>(f + L.f_WV2, w->wv2, (size_t)C * C, rC, 0.f, 0);
     GF_LAUNCH_OK();
     scale_copy_kernel<<<blocks_for(C), 256, 0, st>>>(f + L.f_BV2, w->bv2, C, 1.f, 0.f, 0);
+    GF_LAUNCH_OK();
+    // keys straight from Xbar when the caller does not ask for the centroids: (Xbar Wv2 + bv2) AK + CK = Xbar AK2 + CK2
+    if ((rc = gemm(st, C, LDK, C, f + L.f_WV2, C, false, f + L.f_AK, LDK, false, f + L.f_AK2, LDK, 1.f))) return rc;
+    if ((rc = gemm(st, 1, LDK, C, f + L.f_BV2, C, false, f + L.f_AK, LDK, false, f + L.f_CK2, LDK, 1.f))) return rc;      // row 0 = bv2 AK
+    bias_rows_kernel<<<blocks_for((size_t)k * LDK), 256, 0, st>>>(f + L.f_CK2, f + L.f_CK, k, LDK);
     GF_LAUNCH_OK();
     // pass A: mfold [C, LDK] (no bias column: the bk2 term is constant over n and cancels in softmax_n)
     build_fold_kernel<<<blocks_for((size_t)C * LDK), 256, 0, st>>>(f + L.f_MFOLD, w->wk2, pos ? w->wpk2 : nullptr, nullptr, C, p, LDK, s * rC, s * rp, 0.f);
@@ -451,13 +466,15 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
 }
 
 int prologue(const Layout& L, const gf_attn_desc* d, const float* Y, const float* key_source, int kdim,
-             const float* f, float* ws, cudaStream_t st, const float* in_scale, int in_scale_ld) {
+             const float* f, float* ws, cudaStream_t st, const float* in_scale, int in_scale_ld, bool keys_from_xbar) {
   int rc;
+  const float* AK = f + (keys_from_xbar ? L.f_AK2 : L.f_AK);
+  const float* CK = f + (keys_from_xbar ? L.f_CK2 : L.f_CK);
   // operands of the tcgen05 TF32 contractions are pre-rounded here; the fp32-FMA kernel gets them untouched
   const int tf32 = (!(d->flags & GF_FLAG_FP32_EXACT) && tc_supported(L, d)) ? 1 : 0;
   // KPALL [B*k, LDK] = key_source @ AK + CK
-  if ((rc = gemm(st, L.B * L.k, L.LDK, kdim, key_source, kdim, false, f + L.f_AK, L.LDK, false, ws + L.w_KPALL, L.LDK, 1.f,
-                 f + L.f_CK, L.LDK, L.k, nullptr, tf32 != 0 && kdim >= 64)))   // K = D = 32 (simplex): tiny, stays fp32
+  if ((rc = gemm(st, L.B * L.k, L.LDK, kdim, key_source, kdim, false, AK, L.LDK, false, ws + L.w_KPALL, L.LDK, 1.f,
+                 CK, L.LDK, L.k, nullptr, tf32 != 0 && kdim >= 64)))   // K = D = 32 (simplex): tiny, stays fp32
     return rc;
   const int npos = ((L.H + L.W) * L.KP + 1023) / 1024;
   const int nblk = npos + (L.Cout + 255) / 256 + (L.KP * L.C + 256 * 8 - 1) / (256 * 8);

@@ -46,6 +46,7 @@ constexpr float TAU = 8.f;        // lazy rescale threshold (natural-log units):
 
 struct Params {
   const float* Rt; const float* Ct; float* part;
+  float* xbar; const float* in_scale; int in_ld;     // one split per image: the kernel writes the normalised Xbar [B,k,C] itself
   int n, H, W, k, nsplit, tiles_per_image, nst1, nst2;
 };
 
@@ -380,13 +381,18 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       if (lane == 0) red[(warp - 2) * KP + j] = v;
     }
     named_bar_sync(1, 128);
-    if (rtid < KP && blockIdx.z == 0) {
+    if (rtid < KP) {
       const int j = rtid;
-      part[(size_t)j * (C + 4) + C] = j < P.k ? mref[j] * 0.6931471805599453f : -INFINITY;   // log2 -> natural units
-      part[(size_t)j * (C + 4) + C + 1] = red[j] + red[KP + j] + red[2 * KP + j] + red[3 * KP + j];
-      part[(size_t)j * (C + 4) + C + 2] = 0.f;
-      part[(size_t)j * (C + 4) + C + 3] = 0.f;
+      const float lj = red[j] + red[KP + j] + red[2 * KP + j] + red[3 * KP + j];
+      if (blockIdx.z == 0) {
+        part[(size_t)j * (C + 4) + C] = j < P.k ? mref[j] * 0.6931471805599453f : -INFINITY;   // log2 -> natural units
+        part[(size_t)j * (C + 4) + C + 1] = lj;
+        part[(size_t)j * (C + 4) + C + 2] = 0.f;
+        part[(size_t)j * (C + 4) + C + 3] = 0.f;
+      }
+      resc[j] = 1.f / lj;                          // (resc is free now) normalisation for the direct Xbar write
     }
+    named_bar_sync(1, 128);
     mbar_wait(bar(&bars->done), 0);
     tc_fence_after();
     {
@@ -398,9 +404,18 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           tmem_ld16(tmem + lane_addr + COL_D2 + hg * 32 + hh * 16, v);
           tmem_wait_ld();
           if (lane < 16) {
-            float* dst = part + zoff + hg * 64 + q * 16 + lane;
+            const int ch = zoff + hg * 64 + q * 16 + lane;
+            if (P.xbar) {        // single split: Xbar = acc / l (* load-side scale), no merge kernel
+              const float sc = 1.000352220f * (P.in_scale ? P.in_scale[(size_t)b * P.in_ld + ch] : 1.f);
+              float* dst = P.xbar + (size_t)b * P.k * C + ch;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) dst[(size_t)(hh * 16 + i) * (C + 4)] = v[i] * 1.000352220f;   // X truncation bias (gf_fold.cu)
+              for (int i = 0; i < 16; ++i)
+                if (hh * 16 + i < P.k) dst[(size_t)(hh * 16 + i) * C] = v[i] * sc * resc[hh * 16 + i];
+            } else {
+              float* dst = part + ch;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) dst[(size_t)(hh * 16 + i) * (C + 4)] = v[i] * 1.000352220f;   // X truncation bias (gf_fold.cu)
+            }
           }
         }
       }
@@ -429,7 +444,7 @@ static void stages_for(int smem_limit, int* n1, int* n2) {
 }
 
 template <int KP, int NS>
-static int launch(const Layout& L, const float* X, float* ws, cudaStream_t st) {
+static int launch(const Layout& L, const float* X, float* ws, cudaStream_t st, const float* in_scale, int in_scale_ld) {
   using CF = Cfg<KP, NS>;
   constexpr int NS2 = NS > 8 ? NS / 2 : NS;
   int n1, n2;
@@ -442,6 +457,7 @@ static int launch(const Layout& L, const float* X, float* ws, cudaStream_t st) {
   if ((rc = make_map(&tmM, ws + L.w_M, (uint64_t)L.B * KP, L.C, KP, SLAB_CH, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   Params P;
   P.Rt = ws + L.w_Rt2; P.Ct = ws + L.w_Ct2; P.part = ws + L.w_PART;
+  P.xbar = L.nsplit_cen == 1 ? ws + L.w_XBAR : nullptr; P.in_scale = in_scale; P.in_ld = in_scale_ld;
   P.n = L.n; P.H = L.H; P.W = L.W; P.k = L.k; P.nsplit = L.nsplit_cen; P.tiles_per_image = (L.n + TILE - 1) / TILE;
   P.nst1 = n1; P.nst2 = n2;
   const int smem_bytes = CF::FIXED_BYTES + n1 * SLAB_BYTES + n2 * HG_BYTES + 1024;
@@ -470,11 +486,11 @@ bool tc_centroid_supported(const Layout& L, const gf_attn_desc* d) {
   return ns == 2 ? tcc::fits<32, 2>(limit) : ns == 4 ? tcc::fits<32, 4>(limit) : ns == 8 ? tcc::fits<32, 8>(limit) : tcc::fits<32, 16>(limit);
 }
 
-int centroid_pass_tc(const Layout& L, const gf_attn_desc* d, const float* X, float* ws, cudaStream_t st) {
+int centroid_pass_tc(const Layout& L, const gf_attn_desc* d, const float* X, float* ws, cudaStream_t st, const float* in_scale, int in_scale_ld) {
   (void)d;
   const int ns = L.C / 32;
-  if (L.KP == 16) return ns == 2 ? tcc::launch<16, 2>(L, X, ws, st) : ns == 4 ? tcc::launch<16, 4>(L, X, ws, st) : ns == 8 ? tcc::launch<16, 8>(L, X, ws, st) : tcc::launch<16, 16>(L, X, ws, st);
-  return ns == 2 ? tcc::launch<32, 2>(L, X, ws, st) : ns == 4 ? tcc::launch<32, 4>(L, X, ws, st) : ns == 8 ? tcc::launch<32, 8>(L, X, ws, st) : tcc::launch<32, 16>(L, X, ws, st);
+  if (L.KP == 16) return ns == 2 ? tcc::launch<16, 2>(L, X, ws, st, in_scale, in_scale_ld) : ns == 4 ? tcc::launch<16, 4>(L, X, ws, st, in_scale, in_scale_ld) : ns == 8 ? tcc::launch<16, 8>(L, X, ws, st, in_scale, in_scale_ld) : tcc::launch<16, 16>(L, X, ws, st, in_scale, in_scale_ld);
+  return ns == 2 ? tcc::launch<32, 2>(L, X, ws, st, in_scale, in_scale_ld) : ns == 4 ? tcc::launch<32, 4>(L, X, ws, st, in_scale, in_scale_ld) : ns == 8 ? tcc::launch<32, 8>(L, X, ws, st, in_scale, in_scale_ld) : tcc::launch<32, 16>(L, X, ws, st, in_scale, in_scale_ld);
 }
 
 }  // namespace gf

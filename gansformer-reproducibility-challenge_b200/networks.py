@@ -209,7 +209,8 @@ class SynthesisLayer(nn.Module):
                 if prepared is not None:
                     torch.cuda.current_stream(x.device).wait_event(prepared[0])
                 xo, att, centroids = self.attention(xl, y, centroids=centroids, return_att=return_att, postop=post,
-                                                    stage="token" if prepared is not None else "all")
+                                                    stage="token" if prepared is not None else "all",
+                                                    need_centroids=False)     # the synthesis network never reads them back
                 return xo.permute(0, 3, 1, 2), att, centroids
             xo, att, centroids = self.attention(xl, y, centroids=centroids, return_att=return_att)
             x = xo.permute(0, 3, 1, 2)                                  # back to an NCHW view of channels-last data

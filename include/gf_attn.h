@@ -137,7 +137,8 @@ int gf_attn_simplex_fwd_ex(const gf_attn_desc* desc, const float* X, float* Xout
 
 /* Duplex (kmeans) layer: pass A (latents attend to the grid, softmax over n, centroids [B,k,C]) then
  * prologue with keys from the centroids, then stage T.  centroids_inout: output (and input when
- * GF_FLAG_CENTROIDS_IN). */
+ * GF_FLAG_CENTROIDS_IN); may be NULL when the caller does not need the centroids -- the keys are then built straight from
+ * the attention-weighted means (the centroid projection is folded into the key projection at stage W). */
 int gf_attn_duplex_fwd(const gf_attn_desc* desc, const float* X, const float* Y, const float* folded,
                        float* Xout, float* att, float* centroids_inout, void* ws, void* stream);
 

@@ -165,6 +165,12 @@ def test_duplex_layer_vs_oracle(gf, cuda_dev, shape, exact):
                                  centroids=cen.clone())
     assert torch.equal(cen2, cen)
     assert (out2 - out).abs().max() <= 1e-6 * max(1.0, out.abs().max().item())
+    # need_centroids=False: keys straight from the attention-weighted means (centroid projection folded at stage W)
+    attn = make_layer(gf, cuda_dev, C, D, k, p, integration, nrm, True, True, exact, w)
+    with torch.no_grad():
+        out3, _, cen3 = attn(x.permute(0, 2, 3, 1).contiguous().float().to(cuda_dev), y.float().to(cuda_dev), need_centroids=False)
+    assert cen3 is None
+    check_close(out3, ref.permute(0, 2, 3, 1), path, "duplex/no-centroids", tol_scale=2.0 if path == "simt_fp32" else 1.0)
 
 
 @pytest.mark.parametrize("duplex", [False, True], ids=["simplex", "duplex"])

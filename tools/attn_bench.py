@@ -32,7 +32,7 @@ for res, C in layers:
         attn = gf.BipartiteAttention(C, D, k, integration=integ, kmeans=duplex, exact_fp32=(mode == "fp32")).to(dev)
         with torch.no_grad():
             for i in range(3):
-                attn(xs[i % nbuf], y, out=o, postop=post)
+                attn(xs[i % nbuf], y, out=o, postop=post, need_centroids=not bool(int(os.environ.get('AB_NOCEN', '1'))))
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             # time the whole call (prologue + stage T) and, separately, stage T alone via the StageTimer hook
@@ -41,7 +41,7 @@ for res, C in layers:
             am.STAGE_TIMER = am.StageTimer()
             e0.record()
             for i in range(iters):
-                attn(xs[i % nbuf], y, out=o, postop=post)
+                attn(xs[i % nbuf], y, out=o, postop=post, need_centroids=not bool(int(os.environ.get('AB_NOCEN', '1'))))
             e1.record()
             torch.cuda.synchronize()
             t_call = e0.elapsed_time(e1) / iters
