@@ -357,7 +357,7 @@ __device__ __forceinline__ float round_tf32(float v) {
 // mantissa); K' is scaled up by that factor so the logits are unbiased.
 #define GF_TF32_TRUNC_COMP 1.000352220f
 
-__global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ kpall, const float* __restrict__ Y,
+__global__ void __launch_bounds__(256, 4) finalize_kernel(const float* __restrict__ kpall, const float* __restrict__ Y,
                                                        const float* __restrict__ AV, const float* __restrict__ CV,
                                                        const float* __restrict__ ROW, const float* __restrict__ COL,
                                                        float* __restrict__ Kp, float* __restrict__ Vt,
@@ -376,32 +376,34 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
     __syncthreads();
     const int c = blk * 256 + threadIdx.x;
     if (c >= Cout) return;
-    float acc[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-    for (int d0 = 0; d0 < D; d0 += 32) {
-      float a[32];                                                // 32 independent loads in flight: one L2 latency, not 32
-#pragma unroll
-      for (int dd = 0; dd < 32; ++dd) a[dd] = d0 + dd < D ? AV[(size_t)(d0 + dd) * Cout + c] : 0.f;
-#pragma unroll
-      for (int dd = 0; dd < 32; ++dd) {
-        if (d0 + dd < D) {
-          const float* yr = ysm + d0 + dd;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (j < k) acc[j] = fmaf(yr[j * D], a[dd], acc[j]);
-        }
-      }
-    }
+    // 16 latents at a time: keeps the whole kernel at <= 64 registers (every role shares one register allocation, and at 144
+    // registers only ONE 256-thread CTA fitted an SM: the ~700 latency-bound CTAs of a launch ran in five rounds)
     const float cv = CV[c];
     float* out = Vt + ((size_t)b * Cout + c) * KP;
+    for (int j0 = 0; j0 < KP; j0 += 16) {
+      float acc[16];
 #pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) {
-      if (j4 * 4 < KP) {
+      for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+      for (int d0 = 0; d0 < D; d0 += 16) {
+        float a[16];                                              // 16 independent loads in flight per batch
+#pragma unroll
+        for (int dd = 0; dd < 16; ++dd) a[dd] = d0 + dd < D ? AV[(size_t)(d0 + dd) * Cout + c] : 0.f;
+#pragma unroll
+        for (int dd = 0; dd < 16; ++dd) {
+          if (d0 + dd < D) {
+            const float* yr = ysm + (size_t)j0 * D + d0 + dd;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (j0 + j < k) acc[j] = fmaf(yr[j * D], a[dd], acc[j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
         float4 r;
-        r.x = j4 * 4 + 0 < k ? acc[j4 * 4 + 0] + cv : 0.f; r.y = j4 * 4 + 1 < k ? acc[j4 * 4 + 1] + cv : 0.f;
-        r.z = j4 * 4 + 2 < k ? acc[j4 * 4 + 2] + cv : 0.f; r.w = j4 * 4 + 3 < k ? acc[j4 * 4 + 3] + cv : 0.f;
+        r.x = j0 + j4 * 4 + 0 < k ? acc[j4 * 4 + 0] + cv : 0.f; r.y = j0 + j4 * 4 + 1 < k ? acc[j4 * 4 + 1] + cv : 0.f;
+        r.z = j0 + j4 * 4 + 2 < k ? acc[j4 * 4 + 2] + cv : 0.f; r.w = j0 + j4 * 4 + 3 < k ? acc[j4 * 4 + 3] + cv : 0.f;
         if (tf32) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
-        reinterpret_cast<float4*>(out)[j4] = r;                   // KP is 16 or 32: rows are 16-byte aligned
+        reinterpret_cast<float4*>(out)[j0 / 4 + j4] = r;          // KP is 16 or 32: rows are 16-byte aligned
       }
     }
     return;
@@ -491,7 +493,7 @@ int duplex_tables(const Layout& L, const gf_attn_desc* d, const float* Y, const 
   int rc;
   const int tf32 = tc_centroid_supported(L, d) ? 1 : 0;      // M is an operand of the tcgen05 pass-A kernel: pre-round it
   if ((rc = gemm(st, L.B * L.k, L.LDK, L.D, Y, L.D, false, f + L.f_AM, L.LDK, false, ws + L.w_MALL, L.LDK, 1.f,
-                 f + L.f_CM, L.LDK, L.k)))
+                 f + L.f_CM, L.LDK, L.k, nullptr, tf32 != 0)))   // pass-A logits: M is TF32-rounded right after anyway
     return rc;
   const int npos = ((L.H + L.W) * L.KP + 1023) / 1024;
   const int nblk = npos + (L.KP * L.C + 256 * 8 - 1) / (256 * 8);
