@@ -1,8 +1,10 @@
 """Differentiable wrapper of the fused attention op (needed by the G/D training step).
 
-Forward = the C-ABI CUDA kernels.  Backward = PyTorch autograd through a recomputation of the same folded
-algebra with torch ops on the GPU ("first via PyTorch autograd on the oracle-equivalent
-composite"); a hand-written backward kernel is the follow-up.
+Forward = the C-ABI CUDA kernels.  Backward of a simplex layer with layer norm (or none): the hand-written stage-T
+backward kernel ``gf_attn_simplex_bwd`` (activation gradient + the per-token gradients of logits / control signal), two
+batched GEMMs for the reductions over tokens, and torch autograd through the tiny per-image tables of stages W and I
+(``folded_tables``).  Everything else (duplex, instance / batch norm, CPU tensors): PyTorch autograd through a
+recomputation of the direct-form algebra with torch ops (``composite_forward``).
 """
 from __future__ import annotations
 
@@ -75,6 +77,48 @@ def composite_forward(x, y, p, *, integration, norm, duplex, use_pos, centroids=
     return out.reshape(B, H, W, C), cen
 
 
+def folded_tables(y, p, *, H, W, C, integration, use_pos):
+    """Stages W + I in differentiable torch ops: (latents y [B,k,D], raw parameters) -> the per-image tables stage T and its
+    backward consume, in the workspace layout: Kp [B,KP,C], Vt [B,Cout,KP], Rt [B,H,KP] (-inf in the padded latents),
+    Ct [B,W,KP].  Same algebra as csrc/gf_fold.cu (simplex)."""
+    B, k, _ = y.shape
+    KP = 16 if k <= 16 else 32
+    s = 1.0 / math.sqrt(C)
+    cols = [_e(p["wq"]).t() * s]
+    pd = p["pos_latent"].shape[1] if use_pos else 0
+    if use_pos:
+        cols.append(_e(p["wpq"]).t() * s)
+    cols.append((p["bq"] * s)[:, None])
+    qfold = torch.cat(cols, dim=1)                                       # [C, C + pd + 1]
+    kconst = p["bk"][None, :].expand(k, C)
+    if use_pos:
+        kconst = kconst + p["pos_latent"] @ _e(p["wpk"])
+    kp_all = y @ (_e(p["wk"]) @ qfold) + (kconst @ qfold)[None]          # [B, k, C + pd + 1]
+    Kp = torch.nn.functional.pad(kp_all[:, :, :C], (0, 0, 0, KP - k))
+    kap0 = kp_all[:, :, C + pd]
+    if use_pos:
+        half = pd // 2
+        row, col = _axis(H, half, y.device), _axis(W, half, y.device)
+        rt = torch.einsum("hp,bjp->bhj", row, kp_all[:, :, C:C + half]) + kap0[:, None, :]
+        ct = torch.einsum("wp,bjp->bwj", col, kp_all[:, :, C + half:C + pd])
+    else:
+        rt = kap0[:, None, :].expand(B, H, k)
+        ct = torch.zeros(B, W, k, device=y.device, dtype=y.dtype)
+    Rt = torch.cat([rt, torch.full((B, H, KP - k), -math.inf, device=y.device, dtype=y.dtype)], dim=2) if KP > k else rt
+    Ct = torch.nn.functional.pad(ct, (0, KP - k))
+    wo = _e(p["wo"])
+    cv = p["bv"] @ wo + p["bo"]
+    if integration in ("mul", "both"):
+        cv = cv + torch.cat([torch.ones(C, device=y.device, dtype=y.dtype), torch.zeros(cv.numel() - C, device=y.device, dtype=y.dtype)])
+    v = y @ (_e(p["wv"]) @ wo) + cv                                      # [B, k, Cout]
+    Vt = torch.nn.functional.pad(v.transpose(1, 2), (0, KP - k))
+    return Kp.contiguous(), Vt.contiguous(), Rt.contiguous(), Ct.contiguous()
+
+
+def _kernel_backward_ok(m, x) -> bool:
+    return (not m.duplex) and m.norm in ("layer", None, "none") and m.num_heads == 1 and x.is_cuda and x.dtype == torch.float32
+
+
 class _FusedAttention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, centroids, return_att, names, x, y, *params):
@@ -94,6 +138,8 @@ class _FusedAttention(torch.autograd.Function):
     def backward(ctx, g_out, g_att, g_cen):
         m = ctx.module
         x, y, *params = ctx.saved_tensors
+        if _kernel_backward_ok(m, x):
+            return (None, None, None, None, *_kernel_backward(m, ctx.names, x, y, params, g_out))
         with torch.enable_grad():
             xs = x.detach().requires_grad_(True)
             ys = y.detach().requires_grad_(True)
@@ -102,6 +148,38 @@ class _FusedAttention(torch.autograd.Function):
                                        duplex=m.duplex, use_pos=m.use_pos, centroids=ctx.centroids)
             grads = torch.autograd.grad(out, [xs, ys, *ps], g_out, allow_unused=True)
         return (None, None, None, None, *grads)
+
+
+def _kernel_backward(m, names, x, y, params, g_out):
+    """d(loss)/d(x, y, params) of a simplex layer through gf_attn_simplex_bwd (see the module docstring)."""
+    import ctypes
+    from . import _lib
+    B, H, W, C = x.shape
+    n, k = H * W, y.shape[1]
+    with torch.enable_grad():
+        ys = y.detach().requires_grad_(True)
+        ps = [p.detach().requires_grad_(True) for p in params]
+        Kp, Vt, Rt, Ct = folded_tables(ys, dict(zip(names, ps)), H=H, W=W, C=C, integration=m.integration, use_pos=m.use_pos)
+    KP, Cout = Kp.shape[1], Vt.shape[1]
+    xc, gc = x.detach().contiguous(), g_out.detach().contiguous()
+    dX = torch.empty_like(xc)
+    dS = torch.empty((B, n, KP), dtype=torch.float32, device=x.device)
+    P = torch.empty_like(dS)
+    dCtl = torch.empty((B, n, Cout), dtype=torch.float32, device=x.device)
+    desc = _lib.make_desc(B, H, W, C, k, y.shape[2], heads=1, norm=m.norm, integration=m.integration,
+                          pos_dim=m.pos_dim if m.use_pos else 0, duplex=False, flags=0)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().gf_attn_simplex_bwd(ctypes.byref(desc), xc.data_ptr(), gc.data_ptr(), Kp.data_ptr(), Vt.data_ptr(),
+                                                   Rt.data_ptr(), Ct.data_ptr(), dX.data_ptr(), dS.data_ptr(), P.data_ptr(),
+                                                   dCtl.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)),
+                   "gf_attn_simplex_bwd")
+    # reductions over the tokens: plain batched GEMMs / sums
+    dKp = torch.bmm(dS.transpose(1, 2), xc.reshape(B, n, C))             # [B, KP, C]
+    dVt = torch.bmm(dCtl.transpose(1, 2), P)                             # [B, Cout, KP]
+    dS4 = dS.reshape(B, H, W, KP)
+    dRt, dCt = dS4.sum(dim=2), dS4.sum(dim=1)
+    gy, *gp = torch.autograd.grad([Kp, Vt, Rt, Ct], [ys, *ps], [dKp, dVt, dRt, dCt], allow_unused=True)
+    return (dX, gy, *gp)
 
 
 def bipartite_attention_autograd(module, x, y, centroids, return_att):

@@ -22,7 +22,7 @@ static std::atomic<long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // The library is sm_100a-only: refuse anything else loudly instead of failing at launch.
-static int check_device() {
+int check_device() {
   static thread_local int checked_dev = -1;
   int dev = -1;
   GF_CUDA_OK(cudaGetDevice(&dev));

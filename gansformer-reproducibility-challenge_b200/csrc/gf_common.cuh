@@ -58,6 +58,7 @@ inline int pad_k(int k) { return k <= 16 ? 16 : 32; }
 
 // Fills L; returns GF_OK or an error (message set).
 int make_layout(const gf_attn_desc* d, Layout* L);
+int check_device();          // GF_OK on a compute-capability-10.x device, an error otherwise (gf_api.cu)
 
 // ---- stage W / I kernels (gf_fold.cu) ---------------------------------------------------------------
 int fold_weights(const Layout& L, const gf_attn_desc* d, const gf_attn_weights* w, float* folded, cudaStream_t st);

@@ -149,6 +149,16 @@ int gf_attn_duplex_fwd_ex(const gf_attn_desc* desc, const float* X, const float*
  * (called internally by the forward entry points; exported for tests). */
 int gf_attn_norm_stats(const gf_attn_desc* desc, const float* X, void* ws, void* stream);
 
+/* Backward of stage T for simplex layers with norm layer/none -- replaces what TensorFlow's autodiff derives
+ * for transformer_layer()/integrate().  Inputs: X and the incoming gradient dOut [B,n,C]; the per-image tables of stage I in
+ * the workspace layout (Kp [B,KP,C], Vt [B,Cout,KP], Rt [B,H,KP] with -inf in the padded latents, Ct [B,W,KP]; KP = 16 for
+ * k <= 16, else 32), fp32, un-rounded.  Outputs: dX [B,n,C]; dS [B,n,KP] = gradient w.r.t. the logits; P [B,n,KP] = the
+ * probabilities; dCtl [B,n,Cout] = gradient w.r.t. the control signal (gain half | bias half).  The reductions over the
+ * tokens that remain are plain batched products the caller runs with its GEMM library:
+ *   dKp[b] = dS[b]^T X[b],  dVt[b] = dCtl[b]^T P[b],  dRt[b,h,:] = sum_w dS[b,h,w,:],  dCt[b,w,:] = sum_h dS[b,h,w,:]. */
+int gf_attn_simplex_bwd(const gf_attn_desc* desc, const float* X, const float* dOut, const float* Kp, const float* Vt,
+                        const float* Rt, const float* Ct, float* dX, float* dS, float* P, float* dCtl, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
