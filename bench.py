@@ -227,7 +227,7 @@ def duplex_generator_probe(device, steps: int = 5, warmup: int = 2, B: int = 64,
 def train_probe(device, rank, world, steps: int = 3, warmup: int = 1, B: int = 32, graphed: bool = True):
     """BASELINE configs[3]: one D + one G update of the 256x256 GANsformer (K = 16, simplex) on synthetic reals, batch 32 per
     GPU, gradients averaged over ranks through one flat all-reduce per network (NCCL).  Attention forward = the CUDA
-    kernels, attention backward = composite torch autograd (autograd.py); convolutions and the discriminator = cuDNN."""
+    kernels, attention backward = the stage-T backward kernel + batched GEMMs (autograd.py); convolutions and the discriminator = cuDNN."""
     import gansformer_b200 as gf
     from importlib import import_module
     tr = import_module("gansformer-reproducibility-challenge_b200.training")
@@ -275,8 +275,8 @@ def train_probe(device, rank, world, steps: int = 3, warmup: int = 1, B: int = 3
            "allreduce_bytes_per_step": ar_bytes, "loss_g": last.loss_g, "loss_d": last.loss_d,
            "peak_mem_gb": torch.cuda.max_memory_allocated(device) / 2 ** 30,
            "cuda_graph": bool(graphed),
-           "backward": "attention: CUDA forward + composite torch-autograd backward; FIR filters: native (self-adjoint) kernel; "
-                       "convolutions / discriminator: cuDNN"}
+           "backward": "attention: CUDA forward + hand-written stage-T backward kernel (gf_attn_simplex_bwd) + batched GEMMs for the "
+                       "token reductions; FIR filters: native (self-adjoint) kernel; convolutions / discriminator: cuDNN"}
     del trainer, G, D
     torch.cuda.empty_cache()
     return out
