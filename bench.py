@@ -402,7 +402,9 @@ def run_ours(args):
     t_e2e = dist_mod.max_over_ranks(e0.elapsed_time(e1) * 1e-3, device)
 
     tp = None
-    if not args.no_train_probe:
+    # default on for a single GPU; under torchrun only on request (--train-probe): a rank failing inside the probe's collectives
+    # would leave the others waiting and cost the headline line
+    if not args.no_train_probe and (world == 1 or args.train_probe):
         try:
             tp = train_probe(device, rank, world, graphed=not args.no_cuda_graph)
         except Exception as exc:                     # the probe must never take the headline line down with it
@@ -468,7 +470,7 @@ def main():
     ap.add_argument("--no-cuda-graph", action="store_true")
     ap.add_argument("--no-duplex-probe", action="store_true")
     ap.add_argument("--no-train-probe", action="store_true", help="skip the BASELINE configs[3] probe (G+D training step, train_step object)")
-    ap.add_argument("--train-probe", action="store_true", help="(default on; kept for compatibility)")
+    ap.add_argument("--train-probe", action="store_true", help="run the training-step probe also under torchrun (N > 1); default on for N = 1")
     args = ap.parse_args()
     if args.impl == "ours":
         args.warmup = max(args.warmup, 3)
