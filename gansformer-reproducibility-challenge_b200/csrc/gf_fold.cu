@@ -356,6 +356,7 @@ __device__ __forceinline__ float round_tf32(float v) {
 // Truncation of X toward zero biases every product x*K' by E[eps] = 2^-11 / ln 2 * (1/2) = 0.7213 * 2^-11 (log-uniform
 // mantissa); K' is scaled up by that factor so the logits are unbiased.
 #define GF_TF32_TRUNC_COMP 1.000352220f
+#define GF_LOG2E 1.4426950408889634f
 
 __global__ void __launch_bounds__(256, 4) finalize_kernel(const float* __restrict__ kpall, const float* __restrict__ Y,
                                                        const float* __restrict__ AV, const float* __restrict__ CV,
@@ -427,7 +428,7 @@ __global__ void __launch_bounds__(256, 4) finalize_kernel(const float* __restric
 #pragma unroll 8
           for (int q = 0; q < half; ++q) acc = fmaf(COL[(r - H) * half + q], kj[half + q], acc);
         }
-        val = acc;
+        val = tf32 ? acc * GF_LOG2E : acc;           // tensor-path kernels take their logits in log2 units (one ex2 per latent)
       }
       if (is_row) Rt[((size_t)b * H + r) * KP + j] = val;
       else Ct[((size_t)b * W + (r - H)) * KP + j] = val;
@@ -458,8 +459,8 @@ __global__ void __launch_bounds__(256, 4) finalize_kernel(const float* __restric
       if (i < nK4) {
         float4 r = make_float4(v[u].x * d[u].x, v[u].y * d[u].y, v[u].z * d[u].z, v[u].w * d[u].w);   // x_in = x * in_scale: (x*d).K' == x.(K'*d)
         if (tf32) {
-          r.x = round_tf32(r.x * GF_TF32_TRUNC_COMP); r.y = round_tf32(r.y * GF_TF32_TRUNC_COMP);
-          r.z = round_tf32(r.z * GF_TF32_TRUNC_COMP); r.w = round_tf32(r.w * GF_TF32_TRUNC_COMP);
+          constexpr float kf = GF_TF32_TRUNC_COMP * GF_LOG2E;
+          r.x = round_tf32(r.x * kf); r.y = round_tf32(r.y * kf); r.z = round_tf32(r.z * kf); r.w = round_tf32(r.w * kf);
         }
         Kp4[i] = r;
       }

@@ -368,7 +368,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       }
       float den = 0.f;
 #pragma unroll
-      for (int j = 0; j < KP; ++j) { sv[j] = exp2f((sv[j] - mx) * 1.4426950408889634f); den += sv[j]; }
+      for (int j = 0; j < KP; ++j) { sv[j] = exp2f(sv[j] - mx); den += sv[j]; }   // logits arrive in log2 units (gf_fold.cu folds log2 e into K' / Rt / Ct)
       const float inv = 1.f / den;
 #pragma unroll
       for (int j = 0; j < KP; ++j) sv[j] *= inv;
@@ -379,11 +379,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       }
       // round P to the nearest TF32 so the tensor core's operand truncation is exact (see gf_fold.cu: round_tf32)
 #pragma unroll
-      for (int j = 0; j < KP; ++j) {
-        uint32_t bits = __float_as_uint(sv[j]);
-        bits = (bits + 0xFFFu + ((bits >> 13) & 1u)) & 0xFFFFE000u;
-        sv[j] = __uint_as_float(bits);
-      }
+      for (int j = 0; j < KP; ++j) sv[j] = cvt_tf32(sv[j]);
       mbar_wait(smem_u32(&bars->p_free[buf]), bphase ^ 1u);       // GEMM2 of the tile two iterations back is done
       tc_fence_after();
       tmem_st16(tmem + lane_addr + COL_P + buf * 32, sv);

@@ -299,7 +299,7 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       const bool valid = (tile_beg + it) * TILE + row < P.n;        // false only for the rows past a short image: E = 0
 #pragma unroll
       for (int j = 0; j < KP; ++j) {
-        sv[j] = valid ? (sv[j] + pos[j]) * LOG2E : -INFINITY;                           // logits in log2 units (padded latents: -inf)
+        sv[j] = valid ? sv[j] + pos[j] : -INFINITY;      // logits in log2 units: log2 e is folded into M / Rt2 / Ct2 (gf_fold.cu)
         ex = fmaxf(ex, sv[j] - ml[j]);                              // first tile: +inf -> trigger
       }
       if (it + 1 < ntiles) load_pos(it + 1, pos);                   // prefetch: consumed one tile later
@@ -340,7 +340,7 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       for (int j = 0; j < KP; ++j) {
         float e;
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(sv[j] - ml[j]));
-        e = round_tf32_rn(e);
+        e = cvt_tf32(e);
         lsum[j] += e;
         *reinterpret_cast<float*>(eb + j * 128 + soff[j & 7]) = e;
       }

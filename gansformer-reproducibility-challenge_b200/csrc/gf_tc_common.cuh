@@ -196,6 +196,12 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+// one-instruction rounding to the nearest TF32 value (ties away from zero), result as an fp32 bit pattern
+__device__ __forceinline__ float cvt_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ float round_tf32_rn(float v) {     // nearest-even TF32; the tensor core's truncation is then exact
   uint32_t b = __float_as_uint(v);
   b = (b + 0xFFFu + ((b >> 13) & 1u)) & 0xFFFFE000u;
