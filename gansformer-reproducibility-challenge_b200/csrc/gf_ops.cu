@@ -218,12 +218,15 @@ using namespace gf;
 template <int O, int NQ>
 __global__ void __launch_bounds__(256) torgb_kernel(const float4* __restrict__ x, const float* __restrict__ w, const float* __restrict__ styles,
                                                     int s_ld, const float* __restrict__ bias, float wscale, float* __restrict__ y,
-                                                    int HW, int C4, int tok_per_cta) {
+                                                    int HW, int C4, int tok_per_cta, const float* __restrict__ s2, int s2_ld,
+                                                    float4* __restrict__ xs_out) {
   const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4 wr[O][NQ];
+  float4 s2r[NQ];                                  // optional second output: x * s2 (the next convolution's style modulation)
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     const int c4 = lane + q * 32;
+    s2r[q] = (xs_out && c4 < C4) ? *reinterpret_cast<const float4*>(s2 + (size_t)b * s2_ld + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c4 < C4) s4 = *reinterpret_cast<const float4*>(styles + (size_t)b * s_ld + c4 * 4);
 #pragma unroll
@@ -250,6 +253,8 @@ __global__ void __launch_bounds__(256) torgb_kernel(const float4* __restrict__ x
         for (int q = 0; q < NQ; ++q) {
           const int c4 = lane + q * 32;
           xv[u][q] = (t < t_end && c4 < C4) ? __ldg(xb + (size_t)t * C4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (xs_out && t < t_end && c4 < C4)
+            xs_out[((size_t)b * HW + t) * C4 + c4] = make_float4(xv[u][q].x * s2r[q].x, xv[u][q].y * s2r[q].y, xv[u][q].z * s2r[q].z, xv[u][q].w * s2r[q].w);
         }
       }
 #pragma unroll
@@ -371,7 +376,15 @@ int gf_demod_coef(const float* styles, int s_ld, const float* wsq, float* d, int
 
 int gf_torgb_nhwc(const float* x, const float* w, const float* styles, int s_ld, const float* bias, float wscale, float* y,
                   int B, int HW, int C, void* stream) {
+  return gf_torgb_scale_nhwc(x, w, styles, s_ld, bias, wscale, y, nullptr, 0, nullptr, B, HW, C, stream);
+}
+
+int gf_torgb_scale_nhwc(const float* x, const float* w, const float* styles, int s_ld, const float* bias, float wscale, float* y,
+                        const float* s2, int s2_ld, float* xs_out, int B, int HW, int C, void* stream) {
   if (!x || !w || !styles || !y) { set_error("gf_torgb_nhwc: null pointer"); return GF_ERR_INVALID; }
+  if ((xs_out != nullptr) != (s2 != nullptr) || (xs_out && (s2_ld < C || (s2_ld & 3) || ((uintptr_t)s2 & 15) || ((uintptr_t)xs_out & 15)))) {
+    set_error("gf_torgb_scale_nhwc: s2 / xs_out must both be given, 16-byte aligned, s2_ld >= C and %% 4 == 0"); return GF_ERR_INVALID;
+  }
   if (B <= 0 || HW <= 0 || C <= 0 || (C & 3) || C > 512 || s_ld < C || (s_ld & 3) || B > 65535) {
     set_error("gf_torgb_nhwc: unsupported arguments (C=%d s_ld=%d B=%d)", C, s_ld, B); return GF_ERR_UNSUPPORTED;
   }
@@ -381,10 +394,10 @@ int gf_torgb_nhwc(const float* x, const float* w, const float* styles, int s_ld,
   const float4* x4 = reinterpret_cast<const float4*>(x);
   cudaStream_t st = (cudaStream_t)stream;
   switch (nq) {
-    case 1: torgb_kernel<3, 1><<<grid, 256, 0, st>>>(x4, w, styles, s_ld, bias, wscale, y, HW, C4, tok_per_cta); break;
-    case 2: torgb_kernel<3, 2><<<grid, 256, 0, st>>>(x4, w, styles, s_ld, bias, wscale, y, HW, C4, tok_per_cta); break;
-    case 3: torgb_kernel<3, 3><<<grid, 256, 0, st>>>(x4, w, styles, s_ld, bias, wscale, y, HW, C4, tok_per_cta); break;
-    default: torgb_kernel<3, 4><<<grid, 256, 0, st>>>(x4, w, styles, s_ld, bias, wscale, y, HW, C4, tok_per_cta); break;
+    case 1: torgb_kernel<3, 1><<<grid, 256, 0, st>>>(x4, w, styles, s_ld, bias, wscale, y, HW, C4, tok_per_cta, s2, s2_ld, reinterpret_cast<float4*>(xs_out)); break;
+    case 2: torgb_kernel<3, 2><<<grid, 256, 0, st>>>(x4, w, styles, s_ld, bias, wscale, y, HW, C4, tok_per_cta, s2, s2_ld, reinterpret_cast<float4*>(xs_out)); break;
+    case 3: torgb_kernel<3, 3><<<grid, 256, 0, st>>>(x4, w, styles, s_ld, bias, wscale, y, HW, C4, tok_per_cta, s2, s2_ld, reinterpret_cast<float4*>(xs_out)); break;
+    default: torgb_kernel<3, 4><<<grid, 256, 0, st>>>(x4, w, styles, s_ld, bias, wscale, y, HW, C4, tok_per_cta, s2, s2_ld, reinterpret_cast<float4*>(xs_out)); break;
   }
   GF_LAUNCH_OK();
   return GF_OK;

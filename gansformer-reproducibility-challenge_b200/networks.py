@@ -227,12 +227,13 @@ class ToRGB(nn.Module):
         self.weight = nn.Parameter(torch.randn(img_channels, in_ch, 1, 1))
         self.bias = nn.Parameter(torch.zeros(img_channels))
 
-    def forward(self, x, w_glob, styles=None):
+    def forward(self, x, w_glob, styles=None, next_styles=None):
         """1x1 modulated conv without demodulation: the style is folded into per-sample [3, C] weights, so the
-        activations are read once and no styled copy is written."""
+        activations are read once and no styled copy is written.  next_styles: also return x * next_styles (the next
+        block's modulated input) from the same read."""
         if styles is None:
             styles = self.affine(w_glob)                                # [B, C]
-        return ops.torgb(x, self.weight, styles, self.bias)
+        return ops.torgb(x, self.weight, styles, self.bias, next_styles=next_styles)
 
 
 class SynthesisNetwork(nn.Module):
@@ -309,9 +310,10 @@ class SynthesisNetwork(nn.Module):
         img = None
         atts = []
         li = 0
+        block_prescaled = False
         for bi, res in enumerate(self.block_resolutions):
             nl = 1 if res == 4 else 2
-            prescaled = False
+            prescaled = block_prescaled
             for j in range(nl):
                 layer = self.layers[li]
                 # conv0 -> conv1 inside a block has a single consumer: conv1's style scale is folded into conv0's store
@@ -324,7 +326,13 @@ class SynthesisNetwork(nn.Module):
                 li += 1
                 if att is not None:
                     atts.append(att)
-            rgb = self.torgbs[bi](x, w_glob, styles=styles_all[len(self.layers) + bi])
+            # the tRGB pass reads x anyway: let it also write the next block's style-modulated input (inference only)
+            nxt = styles_all[li] if (li < len(self.layers) and styles_all[li] is not None and x.is_cuda
+                                     and not os.environ.get("GF_NO_TORGB_FUSE")) else None
+            rgb = self.torgbs[bi](x, w_glob, styles=styles_all[len(self.layers) + bi], next_styles=nxt)
+            block_prescaled = nxt is not None
+            if block_prescaled:
+                rgb, x = rgb
             img = rgb if img is None else ops.upsample2x(img, self.fir, add=rgb)
         return (img, atts) if return_att else img
 

@@ -198,26 +198,36 @@ def demod_coef(styles: torch.Tensor, wsq: torch.Tensor, eps: float = 1e-8) -> to
     return torch.rsqrt(styles.square() @ wsq.t() + eps)
 
 
-def torgb(x: torch.Tensor, weight: torch.Tensor, styles: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+def torgb(x: torch.Tensor, weight: torch.Tensor, styles: torch.Tensor, bias: Optional[torch.Tensor],
+          next_styles: Optional[torch.Tensor] = None):
     """tRGB: 1x1 modulated convolution without demodulation.  x [B,C,H,W], weight [3,C,1,1] (raw; equalised-LR scale
-    1/sqrt(C) applied here), styles [B,C], bias [3] -> [B,3,H,W] (planar)."""
+    1/sqrt(C) applied here), styles [B,C], bias [3] -> [B,3,H,W] (planar).  With next_styles [B,C] (inference on CUDA) the same
+    read of x also produces x * next_styles (the next block's modulated input) and the call returns (rgb, x_scaled)."""
     O, I = weight.shape[:2]
     wscale = 1.0 / math.sqrt(I)
-    if _use_cuda(x, weight, styles, bias) and O == 3 and I % 4 == 0 and I <= 512:
+    if _use_cuda(x, weight, styles, bias, next_styles) and O == 3 and I % 4 == 0 and I <= 512:
         xv = _nhwc_view(x)
         B, H, W, C = xv.shape
         y = torch.empty((B, O, H, W), device=x.device, dtype=torch.float32)
         sr, ld = _rows(styles)
         wv = weight.reshape(O, I).contiguous()
+        xs = s2 = None
+        ld2 = 0
+        if next_styles is not None:
+            s2, ld2 = _rows(next_styles)
+            xs = torch.empty_like(xv)
         with torch.cuda.device(x.device):
-            _lib.check(_lib.load().gf_torgb_nhwc(xv.data_ptr(), wv.data_ptr(), sr.data_ptr(), ld,
-                                                 bias.data_ptr() if bias is not None else None, ctypes.c_float(wscale),
-                                                 y.data_ptr(), B, H * W, C, _stream(x.device)), "gf_torgb_nhwc")
-        return y
+            _lib.check(_lib.load().gf_torgb_scale_nhwc(xv.data_ptr(), wv.data_ptr(), sr.data_ptr(), ld,
+                                                       bias.data_ptr() if bias is not None else None, ctypes.c_float(wscale),
+                                                       y.data_ptr(), None if s2 is None else s2.data_ptr(), ld2,
+                                                       None if xs is None else xs.data_ptr(), B, H * W, C, _stream(x.device)),
+                       "gf_torgb_scale_nhwc")
+        return y if next_styles is None else (y, xs.permute(0, 3, 1, 2))
     wm = weight.reshape(1, O, I).to(x.dtype) * styles[:, None, :].to(x.dtype) * wscale           # [B, 3, C]
     B, C, H, W = x.shape
     xl = x.permute(0, 2, 3, 1).reshape(B, H * W, C)
     rgb = torch.matmul(xl, wm.transpose(1, 2))
     if bias is not None:
         rgb = rgb + bias.to(x.dtype)
-    return rgb.transpose(1, 2).reshape(B, O, H, W)
+    rgb = rgb.transpose(1, 2).reshape(B, O, H, W)
+    return rgb if next_styles is None else (rgb, x * next_styles[:, :, None, None].to(x.dtype))

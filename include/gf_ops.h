@@ -61,6 +61,12 @@ int gf_demod_coef(const float* styles, int s_ld, const float* wsq, float* d, int
 int gf_torgb_nhwc(const float* x, const float* w, const float* styles, int s_ld, const float* bias, float wscale, float* y,
                   int B, int HW, int C, void* stream);
 
+/* gf_torgb_nhwc with a second output from the same read of x: xs_out[b,t,c] = x[b,t,c] * s2[b*s2_ld + c] -- the style modulation
+ * of the NEXT block's first convolution (replaces a gf_chan_scale_nhwc pass over the same tensor).  s2 / xs_out both NULL or both
+ * given. */
+int gf_torgb_scale_nhwc(const float* x, const float* w, const float* styles, int s_ld, const float* bias, float wscale, float* y,
+                        const float* s2, int s2_ld, float* xs_out, int B, int HW, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -501,6 +501,8 @@ def test_native_ops_match_definitions(gf, cuda_dev):
                 + brgb.double()[None, :, None, None]
             assert got.shape == (B, 3, H, W) and got.is_contiguous()
             assert (got.double() - want).abs().max() <= 1e-5 * max(1.0, want.abs().max().item())
+            got2, xs2 = ops.torgb(xs, wrgb, wide[:, 4:4 + C], brgb, next_styles=s)     # second output from the same read
+            assert torch.equal(got2, got) and torch.equal(xs2, xs * s[:, :, None, None])
         with torch.no_grad():                                   # upsampling conv as four polyphase convolutions + blur
             wup = torch.randn(C, C, 3, 3, generator=g).to(cuda_dev) / math.sqrt(9 * C)
             got = ops.upconv_blur_phases(xs, ops.upconv_phase_weights(wup), scale=s, gain=4.0)
