@@ -159,10 +159,53 @@ def upsample2x(x: torch.Tensor, f: torch.Tensor, add: Optional[torch.Tensor] = N
     return y if add is None else y + add
 
 
+def _bias_act_native(x, bias, act, noise, strength, gain):
+    xv = _nhwc_view(x)
+    B, H, W, C = xv.shape
+    y = torch.empty_like(xv)
+    nz = None if noise is None else noise.contiguous()
+    bstride = H * W if (nz is not None and nz.numel() == B * H * W and B > 1) else 0
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().gf_bias_act_nhwc(xv.data_ptr(), y.data_ptr(), None if bias is None else bias.contiguous().data_ptr(),
+                                                None if nz is None else nz.data_ptr(),
+                                                None if strength is None else strength.data_ptr(), bstride, B, H * W, C,
+                                                1 if act == "lrelu" else 0, float(gain), _stream(x.device)), "gf_bias_act_nhwc")
+    return y.permute(0, 3, 1, 2)
+
+
+class _BiasAct(torch.autograd.Function):
+    """Training form of bias_act on CUDA: native forward; backward = one masked scaling of the incoming gradient (the sign of
+    the pre-activation is the sign of the output) plus the bias / noise-strength reductions -- instead of autograd through
+    five separate elementwise ops with their saved tensors."""
+
+    @staticmethod
+    def forward(ctx, x, bias, noise, strength, act, gain):
+        y = _bias_act_native(x.detach(), None if bias is None else bias.detach(), act, noise,
+                             None if strength is None else strength.detach(), gain)
+        ctx.act, ctx.gain = act, gain
+        ctx.has_bias, ctx.has_strength = bias is not None, strength is not None and noise is not None
+        ctx.save_for_backward(y, noise if noise is not None else y.new_empty(0))
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        y, noise = ctx.saved_tensors
+        g = gy * ctx.gain if ctx.act != "lrelu" else gy * torch.where(y > 0, ctx.gain, 0.2 * ctx.gain)
+        gb = g.sum(dim=(0, 2, 3)) if ctx.has_bias else None
+        gs = None
+        if ctx.has_strength:
+            gs = (g.sum(dim=1, keepdim=True) * noise.reshape((-1, 1) + tuple(g.shape[2:]))).sum()
+        return g, gb, None, gs, None, None
+
+
 def bias_act(x: torch.Tensor, bias: Optional[torch.Tensor], act: str = "lrelu", noise: Optional[torch.Tensor] = None,
              strength: Optional[torch.Tensor] = None) -> torch.Tensor:
     """act(x + noise * strength + bias[c]) * gain; x [B,C,H,W]; noise [H,W] (shared) or [B,1,H,W]; lrelu gain sqrt(2)."""
     gain = SQRT2 if act == "lrelu" else 1.0
+    cuda32 = all(t is None or (t.is_cuda and t.dtype == torch.float32) for t in (x, bias, noise, strength))
+    if cuda32 and x.shape[1] % 4 == 0 and torch.is_grad_enabled() and (noise is None or not noise.requires_grad) \
+            and any(t is not None and t.requires_grad for t in (x, bias, strength)):
+        return _BiasAct.apply(x, bias, noise, strength, act, gain)
     if _use_cuda(x, bias, noise, strength) and x.shape[1] % 4 == 0:
         xv = _nhwc_view(x)
         B, H, W, C = xv.shape

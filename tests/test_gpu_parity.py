@@ -490,6 +490,17 @@ def test_native_ops_match_definitions(gf, cuda_dev):
             got = ops.bias_act(xs, bias, "lrelu", noise=nz, strength=st)
             want = torch.nn.functional.leaky_relu(xs + nz * st + bias[None, :, None, None], 0.2) * math.sqrt(2.0)
             assert (got - want).abs().max() < 1e-5
+            # training form: native forward, masked-gradient backward (vs torch autograd through the definition)
+        xg, bg, sg = xs.clone().requires_grad_(True), bias.clone().requires_grad_(True), st.clone().requires_grad_(True)
+        yg = ops.bias_act(xg, bg, "lrelu", noise=nz, strength=sg)
+        xr, br, sr = xs.double().clone().requires_grad_(True), bias.double().clone().requires_grad_(True), st.double().clone().requires_grad_(True)
+        yr = torch.nn.functional.leaky_relu(xr + nz.double() * sr + br[None, :, None, None], 0.2) * math.sqrt(2.0)
+        gyy = torch.randn(yg.shape, generator=g).to(cuda_dev)
+        yg.backward(gyy); yr.backward(gyy.double())
+        assert (yg.double() - yr).abs().max() < 1e-5 and (xg.grad.double() - xr.grad).abs().max() < 1e-5
+        assert (bg.grad.double() - br.grad).abs().max() < 1e-3 * max(1.0, br.grad.abs().max().item())
+        assert abs(sg.grad.item() - sr.grad.item()) < 1e-3 * max(1.0, abs(sr.grad.item()))
+        with torch.no_grad():
             nzb = torch.randn(B, 1, H, W, generator=g).to(cuda_dev)
             got = ops.bias_act(xs, bias, "linear", noise=nzb, strength=None)
             assert (got - (xs + nzb + bias[None, :, None, None])).abs().max() < 1e-5
