@@ -21,7 +21,7 @@ def _axis(length, dim, device):
     pos = (torch.arange(length, dtype=torch.float64, device=device) + 0.5) / length * 2.0 - 1.0
     freq = (math.pi / 2.0) * torch.pow(2.0, torch.arange(dim // 2, dtype=torch.float64, device=device))
     ang = pos[:, None] * freq[None, :]
-    return torch.cat([torch.sin(ang), torch.cos(ang)], dim=1).float()
+    return torch.cat([torch.sin(ang), torch.cos(ang)], dim=1)            # float64: callers cast to their dtype
 
 
 def composite_forward(x, y, p, *, integration, norm, duplex, use_pos, centroids=None):
@@ -33,7 +33,7 @@ def composite_forward(x, y, p, *, integration, norm, duplex, use_pos, centroids=
     if use_pos:
         pd = p["pos_latent"].shape[1]
         half = pd // 2
-        row, col = _axis(H, half, x.device), _axis(W, half, x.device)
+        row, col = _axis(H, half, x.device).to(x.dtype), _axis(W, half, x.device).to(x.dtype)
         Pg = torch.cat([row[:, None, :].expand(H, W, half), col[None, :, :].expand(H, W, half)], dim=2).reshape(n, pd)
         Pl = p["pos_latent"]
     cen = None
@@ -98,7 +98,7 @@ def folded_tables(y, p, *, H, W, C, integration, use_pos):
     kap0 = kp_all[:, :, C + pd]
     if use_pos:
         half = pd // 2
-        row, col = _axis(H, half, y.device), _axis(W, half, y.device)
+        row, col = _axis(H, half, y.device).to(y.dtype), _axis(W, half, y.device).to(y.dtype)
         rt = torch.einsum("hp,bjp->bhj", row, kp_all[:, :, C:C + half]) + kap0[:, None, :]
         ct = torch.einsum("wp,bjp->bwj", col, kp_all[:, :, C + half:C + pd])
     else:

@@ -245,3 +245,30 @@ def test_training_step_world2_keeps_replicas_identical(gf):
     nparams = sum(p.numel() for p in D.parameters()) + sum(p.numel() for p in G.parameters() if p.requires_grad)
     assert nb0 == nb1 and 0 < nb0 <= 4 * nparams
     assert (torch.from_numpy(d0) - torch.cat([p.detach().reshape(-1) for p in D.parameters()])).abs().max() > 0   # and they did move
+
+
+# ---------------------------------------------------------------------------------------------------------
+# training path: the differentiable per-image tables (stages W + I in torch) equal the oracle's folded prologue
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C,H,W,k,D,p,integration,use_pos", [(64, 8, 16, 4, 16, 16, "both", True), (96, 10, 13, 20, 12, 8, "mul", True),
+                                                              (32, 4, 4, 3, 8, 4, "add", False)])
+def test_folded_tables_match_oracle_prologue(gf, C, H, W, k, D, p, integration, use_pos):
+    from importlib import import_module
+    from oracle import folded as of
+    ag = import_module("gansformer-reproducibility-challenge_b200.autograd")
+    w = ob.init_params(C, D, k, p, integration, False, seed=3, bias_std=0.4)
+    y = torch.randn(2, k, D, generator=torch.Generator().manual_seed(9), dtype=torch.float64)
+    f = of.fold_weights(w, C=C, k=k, integration=integration, duplex=False, use_pos=use_pos)
+    Kp, Vt, Rt, Ct = of.prologue(y, f, C=C, H=H, W=W, p=p, use_pos=use_pos)
+    gKp, gVt, gRt, gCt = ag.folded_tables(y, w, H=H, W=W, C=C, integration=integration, use_pos=use_pos)
+    for got, want in ((gKp, Kp), (gVt, Vt), (gCt, Ct)):
+        assert got.shape == want.shape and (got - want).abs().max() < 1e-11 * max(1.0, want.abs().max().item())
+    fin = torch.isfinite(Rt)
+    assert torch.equal(torch.isfinite(gRt), fin) and (gRt[fin] - Rt[fin]).abs().max() < 1e-11 * max(1.0, Rt[fin].abs().max().item())
+    # and they are differentiable end to end (padded -inf columns carry no gradient)
+    ys = y.clone().requires_grad_(True)
+    ws = {n: t.clone().requires_grad_(True) for n, t in w.items()}
+    tabs = ag.folded_tables(ys, ws, H=H, W=W, C=C, integration=integration, use_pos=use_pos)
+    loss = sum((t[torch.isfinite(t)] ** 2).sum() for t in tabs)
+    loss.backward()
+    assert torch.isfinite(ys.grad).all() and all(torch.isfinite(t.grad).all() for t in ws.values() if t.grad is not None)
