@@ -272,3 +272,22 @@ def test_folded_tables_match_oracle_prologue(gf, C, H, W, k, D, p, integration, 
     loss = sum((t[torch.isfinite(t)] ** 2).sum() for t in tabs)
     loss.backward()
     assert torch.isfinite(ys.grad).all() and all(torch.isfinite(t.grad).all() for t in ws.values() if t.grad is not None)
+
+
+def test_upconv_polyphase_decomposition_cpu(gf):
+    """The four stride-1 convolutions of ops.upconv_phase_weights are the polyphase components of the stride-2 transposed 3x3
+    convolution (what the inference path feeds the polyphase blur kernel with)."""
+    from importlib import import_module
+    ops = import_module("gansformer-reproducibility-challenge_b200.ops")
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 8, 5, 7, generator=g, dtype=torch.float64)
+    w = torch.randn(12, 8, 3, 3, generator=g, dtype=torch.float64)
+    T = torch.nn.functional.conv_transpose2d(x, w.transpose(0, 1), stride=2)                 # [2, 12, 11, 15]
+    for (a, b), (wk, pad) in zip(((0, 0), (0, 1), (1, 0), (1, 1)), ops.upconv_phase_weights(w)):
+        ph = torch.nn.functional.conv2d(x, wk, padding=pad)
+        assert ph.shape == T[:, :, a::2, b::2].shape
+        assert (ph - T[:, :, a::2, b::2]).abs().max() < 1e-12
+    # tRGB definition with the fused second output (torch form)
+    wr, st, s2 = torch.randn(3, 8, 1, 1, generator=g, dtype=torch.float64), torch.rand(2, 8, generator=g, dtype=torch.float64), torch.rand(2, 8, generator=g, dtype=torch.float64)
+    rgb, xs = ops.torgb(x, wr, st, None, next_styles=s2)
+    assert torch.equal(xs, x * s2[:, :, None, None]) and torch.equal(rgb, ops.torgb(x, wr, st, None))
