@@ -531,7 +531,8 @@ template <int KP, int NS, int MODE>
 static int launch(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, const gf_attn_postop* post, cudaStream_t st) {
   using CF = Cfg<KP, NS, MODE>;
   constexpr bool TWO = two_pass_shape<NS>();
-  const int nst = stages_for<KP, NS, MODE>(device_smem_optin());
+  int nst = stages_for<KP, NS, MODE>(device_smem_optin());
+  if (const char* e = getenv("GF_TC_MAX_STAGES")) { const int v = atoi(e); if (v >= min_stages<NS>() && v < nst) nst = v; }   // tuning aid: ring-depth sensitivity
   if (nst < min_stages<NS>()) { set_error("tcgen05 path: shared memory too small for C=%d KP=%d mode=%d", L.C, KP, MODE); return GF_ERR_UNSUPPORTED; }
   CUtensorMap tmX, tmO, tmK, tmV;
   int rc;
