@@ -291,3 +291,22 @@ def test_upconv_polyphase_decomposition_cpu(gf):
     wr, st, s2 = torch.randn(3, 8, 1, 1, generator=g, dtype=torch.float64), torch.rand(2, 8, generator=g, dtype=torch.float64), torch.rand(2, 8, generator=g, dtype=torch.float64)
     rgb, xs = ops.torgb(x, wr, st, None, next_styles=s2)
     assert torch.equal(xs, x * s2[:, :, None, None]) and torch.equal(rgb, ops.torgb(x, wr, st, None))
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (the CPU oracle port timed on the host cores) runs without a GPU and prints ONE JSON line
+    carrying the keys of the bench contract."""
+    import json
+    import subprocess
+    import sys
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "images/s" and line["higher_is_better"] is True
+    for key in ("metric", "value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config",
+                "e2e", "cpu_baseline"):
+        assert key in line, key
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"] and "model" not in line["config"]
