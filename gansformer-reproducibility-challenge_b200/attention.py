@@ -16,7 +16,6 @@ only; all arithmetic of the block happens inside the C-ABI calls.  No CPU path e
 from __future__ import annotations
 
 import ctypes
-import math
 from typing import Dict, Optional, Tuple
 
 import torch

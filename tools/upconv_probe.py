@@ -1,6 +1,6 @@
 """cuDNN stride-2 transposed 3x3 convolution vs its 4-phase decomposition into stride-1 convolutions (2x2, 2x1, 1x2, 1x1
 taps) on the low-resolution input: same flops, but the phases run cuDNN's fprop kernels instead of strided dgrad."""
-import torch, torch.nn.functional as F, time
+import torch, torch.nn.functional as F
 torch.backends.cudnn.allow_tf32 = True; torch.backends.cudnn.benchmark = True
 dev = torch.device("cuda:0")
 def timeit(fn, n=10):
