@@ -165,8 +165,7 @@ int gemm_tc(cudaStream_t st, int M, int N, int K, const float* A, const float* B
   if ((rc = tc::make_map(&tmA, A, (uint64_t)M, (uint64_t)K, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = tc::make_map(&tmB, B, (uint64_t)K, (uint64_t)N, BK, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
   const int smem_bytes = NSTAGES * STAGE_BYTES + (int)sizeof(Bars) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) { GF_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); attr_set = true; }
+  GF_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));   // per device: set on every call
   if (emod < 1) emod = 1;
   // both operands are truncated to TF32 by the tensor core: compensate the mean truncation bias of each (0.7213 * 2^-11)
   const float comp = 1.000352220f * 1.000352220f;
