@@ -14,10 +14,10 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libgf_attn.so"
 SOURCES = ["gf_api.cu", "gf_fold.cu", "gf_simt.cu", "gf_tc.cu", "gf_tc_cen.cu", "gf_tc_gemm.cu", "gf_bwd.cu", "gf_ops.cu"]
-NVCC_FLAGS = [
+COMPILE_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
 
 
@@ -36,17 +36,42 @@ def _stale() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build_extension(force: bool = False, verbose: bool = False) -> Path:
-    """Compile csrc/*.cu into libgf_attn.so next to this file.  No-op when up to date."""
-    if not force and not _stale():
-        return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB_PATH)] + [str(CSRC / s) for s in SOURCES]
+def _compile_one(nvcc: str, src: Path, obj: Path, verbose: bool) -> str:
+    cmd = [nvcc, *COMPILE_FLAGS, *os.environ.get("GF_NVCC_DEFS", "").split(), "-c", str(src), "-o", str(obj)]
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
+        cmd[1:1] = ["-Xptxas", "-v"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return res.stderr
+
+
+def build_extension(force: bool = False, verbose: bool = False) -> Path:
+    """Compile csrc/*.cu into libgf_attn.so next to this file (one object per source, compiled in parallel, re-used while
+    neither the source nor any header changed).  No-op when up to date."""
+    if not force and not _stale():
+        return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = _nvcc()
+    objdir = PKG_DIR / "build"
+    objdir.mkdir(exist_ok=True)
+    tag = objdir / ".flags"
+    flags_now = " ".join(COMPILE_FLAGS) + "|" + os.environ.get("GF_NVCC_DEFS", "")
+    if not tag.exists() or tag.read_text() != flags_now:
+        force = True
+    hdr_time = max(d.stat().st_mtime for d in list(CSRC.glob("*.cuh")) + list((PKG_DIR.parent / "include").glob("*.h")))
+    jobs = []
+    for name in SOURCES:
+        src, obj = CSRC / name, objdir / (name[:-3] + ".o")
+        if force or verbose or not obj.exists() or obj.stat().st_mtime < max(src.stat().st_mtime, hdr_time):
+            jobs.append((src, obj))
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as pool:
+        logs = list(pool.map(lambda j: _compile_one(nvcc, j[0], j[1], verbose), jobs))
+    tag.write_text(flags_now)
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB_PATH)] + [str(objdir / (n[:-3] + ".o")) for n in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc link failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stderr)
+        print("\n".join(logs))
     return LIB_PATH

@@ -22,6 +22,7 @@ import torch
 from torch import nn
 
 from . import _lib
+from ._state import weights_epoch
 
 SIMPLEX_PARAMS = ("wq", "bq", "wpq", "wk", "bk", "wpk", "wv", "bv", "wo", "bo", "pos_latent")
 DUPLEX_PARAMS = ("wq2", "bq2", "wpq2", "wk2", "bk2", "wpk2", "wv2", "bv2", "wkc")
@@ -127,7 +128,7 @@ def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[s
         names = SIMPLEX_PARAMS + (DUPLEX_PARAMS if duplex else ())
         if weights_version is None:
             weights_version = tuple((params[n].data_ptr(), params[n]._version) for n in names)
-        fkey = (H, W, k, D, C, pos_dim, integration, duplex, str(dev), weights_version)
+        fkey = (H, W, k, D, C, pos_dim, integration, duplex, str(dev), weights_version, weights_epoch())
         if plan.folded is None or plan.folded_key != fkey or FORCE_REFOLD:
             nfl = _lib.folded_floats(desc)
             if plan.folded is None or plan.folded.numel() != nfl or plan.folded.device != dev:

@@ -53,6 +53,17 @@ struct Layout {
   int nsplit_norm, nsplit_cen;
 };
 
+// SM count of the current device (B200: 148), queried once per process; grids and split models are sized from it.
+inline int num_sms() {
+  static int v = -1;
+  if (v < 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) v = n;
+    else return 148;          // no device visible (host-only layout queries): the B200 figure, not cached
+  }
+  return v;
+}
+
 inline size_t align64(size_t x) { return (x + 63) & ~size_t(63); }
 inline int pad_k(int k) { return k <= 16 ? 16 : 32; }
 

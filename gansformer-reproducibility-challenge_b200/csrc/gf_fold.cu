@@ -60,25 +60,27 @@ int make_layout(const gf_attn_desc* d, Layout* L) {
   }
   l.f_total = o;
 
-  // statistics / centroid splits: about two waves of CTAs over 148 SMs
-  int want = (2 * 148 + l.B - 1) / l.B;
+  // statistics / centroid splits: about two waves of CTAs over the device's SMs
+  const int sms = num_sms();
+  int want = (2 * sms + l.B - 1) / l.B;
   l.nsplit_norm = want; if (l.nsplit_norm > (l.n + 63) / 64) l.nsplit_norm = (l.n + 63) / 64; if (l.nsplit_norm < 1) l.nsplit_norm = 1;
   {
     // centroid splits: one CTA per SM.  Cost model in tile units: every CTA pays a fixed cost (TMEM allocation, loading M,
     // flushing its [KP, C] partial -- about two tiles' worth) plus its share of the image's tiles, and the grid runs in
-    // ceil(CTAs / 148) rounds.  Small images therefore get ONE split (a 32x32 grid used to be cut into 8 one-tile CTAs, each
+    // ceil(CTAs / SMs) rounds.  Small images therefore get ONE split (a 32x32 grid used to be cut into 8 one-tile CTAs, each
     // moving as many bytes of M and partials as of X).
     const int tiles = (l.n + 127) / 128;
     const int z = l.C == 512 ? 2 : 1;                   // C = 512: two CTAs per split (channel halves)
     int best = 1;
     long long best_cost = -1;
     for (int ns = 1; ns <= 16 && ns <= tiles; ++ns) {
-      const long long rounds = ((long long)l.B * ns * z + 147) / 148;
+      const long long rounds = ((long long)l.B * ns * z + sms - 1) / sms;
       const long long cost = rounds * ((tiles + ns - 1) / ns + 2);
       if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = ns; }
     }
     l.nsplit_cen = best;
-    if (const char* e = getenv("GF_NSPLIT_CEN")) { const int v = atoi(e); if (v >= 1 && v <= 16 && v <= tiles) l.nsplit_cen = v; }   // tuning aid
+    static const int forced = []() { const char* e = getenv("GF_NSPLIT_CEN"); return e ? atoi(e) : 0; }();   // tuning aid, read once per process
+    if (forced >= 1 && forced <= 16 && forced <= tiles) l.nsplit_cen = forced;
   }
 
   o = 0;

@@ -3,7 +3,7 @@
 //
 // B200-native equivalents of the reference's native ops dnnlib/tflib/ops/{fused_bias_act,upfirdn_2d}.cu (expected
 // upstream; not in the checkout).  All are pure streaming kernels: float4 accesses on channels-last rows, grids
-// sized to a few waves of 148 SMs, no shared memory (the FIR reuse is served by L1/L2).
+// sized to a few waves of the device's SMs, no shared memory (the FIR reuse is served by L1/L2).
 #include "gf_common.cuh"
 #include "../../include/gf_ops.h"
 
@@ -11,7 +11,7 @@ namespace gf {
 
 static inline int grid_for(size_t work_items, int threads) {
   size_t b = (work_items + threads - 1) / threads;
-  const size_t cap = 148 * 16;
+  const size_t cap = (size_t)num_sms() * 16;
   return (int)(b > cap ? cap : (b < 1 ? 1 : b));
 }
 

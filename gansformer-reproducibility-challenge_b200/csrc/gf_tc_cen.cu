@@ -115,7 +115,11 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   Bars* bars = reinterpret_cast<Bars*>(smem + CF::OFF_BARS);
   const uint32_t s_bars = s_base + CF::OFF_BARS;
   auto bar = [&](const uint64_t* p) -> uint32_t { return s_bars + (uint32_t)((const uint8_t*)p - (const uint8_t*)bars); };
+#ifdef GF_DEBUG_WATCHDOG
+#ifdef GF_DEBUG_WATCHDOG     // bring-up builds only: record where a barrier wait timed out (tools/hang_debug.py)
   if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && g_dbg_buf) g_dbg_buf[1] = s_bars;
+#endif
+#endif
   float* red = reinterpret_cast<float*>(smem + CF::OFF_SMALL);      // [4][KP]
   float* mref = red + 4 * KP;                                       // [KP]
   float* resc = mref + KP;                                          // [KP]
@@ -461,7 +465,11 @@ static int launch(const Layout& L, const float* X, float* ws, cudaStream_t st, c
   P.n = L.n; P.H = L.H; P.W = L.W; P.k = L.k; P.nsplit = L.nsplit_cen; P.tiles_per_image = (L.n + TILE - 1) / TILE;
   P.nst1 = n1; P.nst2 = n2;
   const int smem_bytes = CF::FIXED_BYTES + n1 * SLAB_BYTES + n2 * HG_BYTES + 1024;
+#ifdef GF_DEBUG_WATCHDOG     // bring-up builds only (-DGF_DEBUG_WATCHDOG): a host-pinned buffer that records where a barrier wait timed out
+#ifdef GF_DEBUG_WATCHDOG     // bring-up builds only: record where a barrier wait timed out (tools/hang_debug.py)
   if (const char* dbg = getenv("GF_DEBUG_PTR")) tc::set_debug_buffer(reinterpret_cast<unsigned int*>(strtoull(dbg, nullptr, 0)));
+#endif
+#endif
   auto kern = centroid_tc_kernel<KP, NS, NS2>;
   GF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   kern<<<dim3(L.nsplit_cen, L.B, NS / NS2), NUM_THREADS, smem_bytes, st>>>(tmX, tmX2, tmM, P);

@@ -21,12 +21,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Debug aid: when the host sets this to a host-pinned (UVA) buffer, a watchdog timeout records where it happened before
-// trapping, so the hang site survives the dead context.  One copy per translation unit; set with set_debug_buffer().
+// A protocol bug must trap, not hang the GPU: every wait carries a watchdog (~2 s of clock64 ticks).  Bring-up builds
+// (-DGF_DEBUG_WATCHDOG) additionally record where the wait timed out into a host-pinned buffer before trapping.
+#ifdef GF_DEBUG_WATCHDOG
 static __device__ unsigned int* g_dbg_buf = nullptr;
 static inline int set_debug_buffer(unsigned int* pinned) {
   return cudaMemcpyToSymbol(g_dbg_buf, &pinned, sizeof(pinned)) == cudaSuccess ? 0 : -1;
 }
+#endif
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
@@ -41,10 +43,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) break;
-    if ((++spins & 1023u) == 0) {            // watchdog: a protocol bug must trap, not hang the GPU
+    if ((++spins & 1023u) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
       else if (now - t0 > 4000000000ll) {
+#ifdef GF_DEBUG_WATCHDOG
         if (g_dbg_buf) {                         // record once, keep spinning a little so every stuck waiter gets to record
           if (!(spins & 0x80000000u)) {
             spins |= 0x80000000u;
@@ -56,9 +59,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             __threadfence_system();
           }
           if (now - t0 > 6000000000ll) __trap();
-        } else {
-          __trap();
+          continue;
         }
+#endif
+        __trap();
       }
     }
   }

@@ -20,8 +20,9 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .attention import BipartiteAttention
+from .attention import BipartiteAttention, _Plan
 from . import ops
+from ._state import weights_epoch, bump_weights_epoch
 from .ops import fir_filter
 
 SQRT2 = math.sqrt(2.0)
@@ -41,7 +42,7 @@ def _cached(module: nn.Module, key: str, params, fn):
     if CACHE_BYPASS:
         with torch.no_grad():
             return fn()
-    ver = tuple((p.data_ptr(), p._version, str(p.device), p.dtype) for p in params)
+    ver = (weights_epoch(),) + tuple((p.data_ptr(), p._version, str(p.device), p.dtype) for p in params)
     store = module.__dict__.setdefault("_icache", {})
     ent = store.get(key)
     if ent is None or ent[0] != ver:
@@ -49,6 +50,20 @@ def _cached(module: nn.Module, key: str, params, fn):
             ent = (ver, fn())
         store[key] = ent
     return ent[1]
+
+
+RUNTIME_KEYS = ("_icache", "_graphs", "_side_stream", "_copy_stream")
+
+
+def drop_runtime_state(module: nn.Module) -> nn.Module:
+    """Remove everything derived from the weights or bound to a device context (caches, captured graphs, streams, staging
+    buffers, attention plans) from `module` and its children -- after a deep copy, a device move or a weight load."""
+    for m in module.modules():
+        for key in [k for k in m.__dict__ if k in RUNTIME_KEYS or (isinstance(k, tuple) and k and k[0] == "_staging")]:
+            del m.__dict__[key]
+        if isinstance(m, BipartiteAttention):
+            m._plan = _Plan()
+    return module
 
 
 def nf(res: int, fmap_base: int = 16384, fmap_max: int = 512) -> int:
@@ -251,7 +266,12 @@ class SynthesisNetwork(nn.Module):
         self.layers = nn.ModuleList()
         self.torgbs = nn.ModuleList()
         self.layer_res: List[int] = []
-        self.iterative = bool(attn_kwargs.pop("iterative", False))
+        if attn_kwargs.pop("iterative", False):
+            # `iterative` carries the centroids of one layer into the next layer's k-means initialisation.  The
+            # channel width changes between resolutions and the reference source that would define the carry is not
+            # available, so the option is refused instead of being silently ignored.
+            raise NotImplementedError("iterative=True (cross-layer centroid carry) is not implemented; use iterative=False "
+                                      "(BipartiteAttention.forward(centroids=...) skips pass A for a caller-managed carry)")
         for res in self.block_resolutions:
             out_ch = nf(res, fmap_base, fmap_max)
             use_att = transformer and components_num > 0 and g_start_res <= res <= g_end_res
@@ -360,6 +380,24 @@ class Generator(nn.Module):
         ws = self.mapping(z, truncation_psi=truncation_psi)
         return self.synthesis(ws, noise_mode=noise_mode, return_att=return_att)
 
+    def __deepcopy__(self, memo):
+        """Copies parameters and buffers only: caches, captured graphs, streams and attention plans stay with the original
+        (a copied graph closure would replay the ORIGINAL module's weights)."""
+        import copy as _copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k_, v_ in self.__dict__.items():
+            if k_ in RUNTIME_KEYS or isinstance(k_, tuple):
+                continue
+            new.__dict__[k_] = _copy.deepcopy(v_, memo)
+        return drop_runtime_state(new)
+
+    def load_state_dict(self, *args, **kwargs):
+        res = super().load_state_dict(*args, **kwargs)
+        bump_weights_epoch()
+        drop_runtime_state(self)
+        return res
+
     # ------------------------------------------------------------------------------------------------------------
     # CUDA-graph replay of the whole forward (the step is ~370 small launches; graphs remove the launch overhead)
     # ------------------------------------------------------------------------------------------------------------
@@ -367,12 +405,15 @@ class Generator(nn.Module):
     def graphed(self, batch_size: int, truncation_psi: float = 1.0, noise_mode: str = "const"):
         """Returns ``fn(z_device) -> img`` replaying a captured CUDA graph of ``self(z)`` for this batch size.
 
-        The returned image tensor is a static buffer overwritten by the next replay.  Weights are read at replay
-        time, except the folded attention weights, which are baked at capture: re-capture after a weight update."""
-        key = (batch_size, float(truncation_psi), noise_mode)
+        The returned image tensor is a static buffer overwritten by the next replay.  Weight-derived tensors (folded
+        attention weights, scaled conv weights) are baked at capture, so the graph is keyed on the parameters' storage,
+        version counters and the process-wide weights epoch: any weight update re-captures."""
+        key = (batch_size, float(truncation_psi), noise_mode, weights_epoch(),
+               tuple((p.data_ptr(), p._version) for p in self.parameters()))
         cache = self.__dict__.setdefault("_graphs", {})
         if key in cache:
             return cache[key]
+        cache.clear()                                   # a stale graph holds a full set of activations: drop it
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("CUDA graphs need the generator on a CUDA device")

@@ -24,6 +24,7 @@ import torch.nn.functional as F
 
 from . import dist as gdist
 from .networks import FullyConnected, nf
+from ._state import bump_weights_epoch
 from .ops import fir4, fir_filter, upfirdn2d_ref
 
 SQRT2 = math.sqrt(2.0)
@@ -104,6 +105,7 @@ class TrainConfig:
     d_reg_interval: int = 16            # lazy R1: every 16th discriminator step
     ema_kimg: float = 10.0
     noise_mode: str = "random"
+    w_avg_beta: float = 0.995           # decay of the running mean of the mapping outputs (truncation trick)
 
 
 @dataclass
@@ -168,8 +170,13 @@ class Trainer:
         loss_g.backward()
         self._allreduce(G, stats)
         self.opt_g.step()
-        # ---- moving average of the generator
+        # ---- moving average of the generator (and of the mapping outputs: the truncation trick's w_avg)
         with torch.no_grad():
+            if hasattr(G, "mapping") and hasattr(G.mapping, "w_avg"):
+                ws = G.mapping(z)
+                k_ = G.mapping.components_num
+                cur = torch.stack([ws[:, :k_].mean(dim=(0, 1)), ws[:, k_:].mean(dim=(0, 1))])
+                G.mapping.w_avg.lerp_(cur, 1.0 - cfg.w_avg_beta)
             beta = 0.5 ** (z.shape[0] * self.world / (cfg.ema_kimg * 1000.0))
             for pe, p in zip(self.G_ema.parameters(), G.parameters()):
                 pe.lerp_(p.detach(), 1.0 - beta)
@@ -182,6 +189,7 @@ class Trainer:
         do_r1 = self.cfg.r1_gamma > 0 and self.it % self.cfg.d_reg_interval == 0
         loss_d, loss_g, r1 = self._step_tensors(z, reals, do_r1, stats)
         stats.loss_d, stats.loss_g, stats.r1 = float(loss_d), float(loss_g), float(r1)
+        bump_weights_epoch()
         for e0, e1 in stats.extra.pop("_events", []):
             e1.synchronize()
             stats.allreduce_ms += e0.elapsed_time(e1)
@@ -222,5 +230,6 @@ class Trainer:
             # (capture does not execute: fall through to the replay below)
         graph, (loss_d, loss_g, r1) = st[do_r1]
         graph.replay()
+        bump_weights_epoch()          # the replay moved G / D / G_ema weights without touching their version counters
         self.it += 1
         return StepStats(loss_g=float(loss_g), loss_d=float(loss_d), r1=float(r1))

@@ -310,3 +310,56 @@ def test_bench_reference_arm_json_contract():
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_alias_package_shares_module_objects(gf):
+    """``gansformer_b200.x`` must BE ``gansformer-reproducibility-challenge_b200.x`` (one copy of every module-level switch)."""
+    import importlib
+    real = importlib.import_module("gansformer-reproducibility-challenge_b200")
+    assert gf is real
+    for sub in ("training", "networks", "attention", "_lib", "ops", "dist", "_state"):
+        a = importlib.import_module("gansformer_b200." + sub)
+        b = importlib.import_module("gansformer-reproducibility-challenge_b200." + sub)
+        assert a is b, sub
+    from gansformer_b200.training import Trainer
+    assert Trainer is gf.Trainer
+    import gansformer_b200.networks as nets
+    nets.CACHE_BYPASS = True
+    try:
+        assert importlib.import_module("gansformer-reproducibility-challenge_b200.networks").CACHE_BYPASS is True
+    finally:
+        nets.CACHE_BYPASS = False
+
+
+def test_weight_caches_follow_the_weights_epoch(gf):
+    """A parameter changed behind autograd's back (CUDA-graph replay of an optimizer step: no version bump) must not be
+    served from the weight-derived caches once the weights epoch moves; deep copies carry no caches or plans."""
+    import copy
+    import importlib
+    nets = importlib.import_module("gansformer_b200.networks")
+    state = importlib.import_module("gansformer_b200._state")
+    fc = nets.FullyConnected(8, 4)
+    x = torch.randn(3, 8)
+    with torch.no_grad():
+        y0 = fc(x).clone()
+        fc.weight.data.mul_(2.0)                      # .data: no version bump, like a graph replay
+        assert torch.equal(fc(x), y0)                 # stale by construction ...
+        state.bump_weights_epoch()
+        y1 = fc(x)
+        assert not torch.equal(y1, y0)                # ... until the epoch moves
+    G = gf.Generator(resolution=16, components_num=2, latent_dim=8, fmap_base=64, fmap_max=16, mapping_layers=1)
+    with torch.no_grad():
+        G.mapping(torch.randn(2, 3, 8))
+    G.__dict__["_graphs"] = {"k": object()}
+    assert any("_icache" in m.__dict__ for m in G.modules())
+    plan0 = G.synthesis.layers[1].attention._plan
+    G2 = copy.deepcopy(G)
+    assert "_graphs" not in G2.__dict__ and not any("_icache" in m.__dict__ for m in G2.modules())
+    assert G2.synthesis.layers[1].attention._plan is not plan0 and G.synthesis.layers[1].attention._plan is plan0
+    for (n1, p1), (n2, p2) in zip(G.named_parameters(), G2.named_parameters()):
+        assert n1 == n2 and torch.equal(p1, p2) and p1.data_ptr() != p2.data_ptr()
+    e0 = state.weights_epoch()
+    G2.load_state_dict(G.state_dict())
+    assert state.weights_epoch() == e0 + 1
+    with pytest.raises(NotImplementedError, match="iterative"):
+        gf.Generator(resolution=16, components_num=2, latent_dim=8, fmap_base=64, fmap_max=16, kmeans=True, iterative=True)
