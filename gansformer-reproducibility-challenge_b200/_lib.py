@@ -17,6 +17,7 @@ NORM = {None: 0, "none": 0, "layer": 1, "instance": 2, "batch": 3}
 INTEGRATION = {"mul": 0, "add": 1, "both": 2}
 FLAG_FP32_EXACT = 1
 FLAG_CENTROIDS_IN = 2
+FLAG_TABLES_READY = 4
 PATH_NAMES = {0: "none", 1: "simt_fp32", 2: "tcgen05_tf32"}
 
 WEIGHT_FIELDS = ("wq", "bq", "wpq", "wk", "bk", "wpk", "wv", "bv", "wo", "bo", "pos_latent",
@@ -26,7 +27,8 @@ WEIGHT_FIELDS = ("wq", "bq", "wpq", "wk", "bk", "wpk", "wv", "bv", "wo", "bo", "
 EXPORTS = ("gf_attn_abi_version", "gf_last_error", "gf_attn_last_path", "gf_attn_folded_floats",
            "gf_attn_fold_weights", "gf_attn_workspace_bytes", "gf_attn_prologue", "gf_attn_simplex_fwd",
            "gf_attn_duplex_fwd", "gf_attn_norm_stats", "gf_attn_launch_count",
-           "gf_attn_simplex_fwd_ex", "gf_attn_duplex_fwd_ex", "gf_attn_prologue_ex", "gf_attn_simplex_bwd", "gf_attn_last_centroid_path", "gf_attn_debug_layout")
+           "gf_attn_simplex_fwd_ex", "gf_attn_duplex_fwd_ex", "gf_attn_prologue_ex", "gf_attn_simplex_bwd", "gf_attn_last_centroid_path", "gf_attn_debug_layout",
+           "gf_attn_prologue_batch")
 # include/gf_ops.h
 OPS_EXPORTS = ("gf_chan_scale_nhwc", "gf_blur_up_nhwc", "gf_upsample2x_nchw", "gf_bias_act_nhwc", "gf_demod_coef", "gf_torgb_nhwc", "gf_fir4_nhwc", "gf_blur_up_phases_nhwc", "gf_torgb_scale_nhwc")
 
@@ -81,6 +83,7 @@ def load() -> ctypes.CDLL:
     lib.gf_attn_simplex_fwd_ex.argtypes = [POINTER(GfAttnDesc), c_void_p, c_void_p, c_void_p, c_void_p, POINTER(GfAttnPostop), c_void_p]
     lib.gf_attn_duplex_fwd_ex.argtypes = [POINTER(GfAttnDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_void_p, POINTER(GfAttnPostop), c_void_p]
+    lib.gf_attn_prologue_batch.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.gf_attn_simplex_bwd.argtypes = [POINTER(GfAttnDesc)] + [c_void_p] * 11
     lib.gf_chan_scale_nhwc.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]
     lib.gf_blur_up_nhwc.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, ctypes.c_float, c_void_p]

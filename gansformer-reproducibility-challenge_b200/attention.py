@@ -41,15 +41,18 @@ def param_shapes(dim: int, latent_dim: int, components_num: int, pos_dim: int, i
 
 
 class StageTimer:
-    """Optional CUDA-event timer around the stage-T launch (the dominant kernel); bench.py installs one.
+    """Optional CUDA-event timer around the attention launches; bench.py installs one.
 
-    Events are recorded on the stream the kernel is launched on; `records` holds (start, end, alg_bytes)."""
+    Events are recorded on the stream the kernels are launched on.  Whole call = stages I + T (start-of-call event ->
+    end); stage T alone = the dominant kernel."""
 
     def __init__(self):
-        self.records = []
+        self.records = []            # (stage-T start, end, algorithmic bytes, start of the whole call)
+        self.batch_records = []      # (start, end) of batched stage-I launches (prologue_batch)
 
     def reset(self):
         self.records = []
+        self.batch_records = []
 
 
 STAGE_TIMER: Optional[StageTimer] = None
@@ -82,6 +85,76 @@ def _check_tensor(t: torch.Tensor, name: str, device) -> None:
         raise RuntimeError(f"{name} must be contiguous")
 
 
+def _make_postop(postop: Optional[dict], B: int, H: int, W: int, C: int, dev):
+    """dict -> (GfAttnPostop | None, tensors to keep alive until the launch is enqueued)."""
+    if postop is None:
+        return None, []
+    pst = _lib.GfAttnPostop()
+    keep = []
+    for fld in ("bias", "noise", "strength"):
+        t = postop.get(fld)
+        if t is not None:
+            t = t.detach()
+            _check_tensor(t, "postop." + fld, dev)
+            keep.append(t)
+            setattr(pst, fld, t.data_ptr())
+    nz = postop.get("noise")
+    if nz is not None and nz.numel() not in (H * W, B * H * W):
+        raise ValueError("postop.noise must have H*W or B*H*W elements")
+    if postop.get("bias") is not None and postop["bias"].numel() != C:
+        raise ValueError("postop.bias must have C elements")
+    pst.noise_bstride = H * W if (nz is not None and nz.numel() == B * H * W and B > 1) else 0
+    pst.act = {"linear": 0, "lrelu": 1}[postop.get("act", "lrelu")]
+    pst.gain = float(postop.get("gain", 1.0))
+    for fld in ("in_scale", "post_scale"):
+        t = postop.get(fld)
+        if t is None:
+            continue
+        t = t.detach()
+        if t.shape != (B, C) or t.dtype != torch.float32 or t.device != dev:
+            raise ValueError(f"postop.{fld} must be a float32 [B, C] tensor on {dev}")
+        if not (t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.stride(0) >= C and t.data_ptr() % 16 == 0):
+            t = t.contiguous()
+        keep.append(t)
+        setattr(pst, fld, t.data_ptr())
+        setattr(pst, fld + "_ld", t.stride(0))
+    return pst, keep
+
+
+def _plan_call(lib, shape, y: torch.Tensor, params: Dict[str, torch.Tensor], plan: _Plan, *, integration, norm, duplex, num_heads,
+               use_pos, flags, weights_version=None):
+    """Descriptor + folded weights (stage W runs here when a parameter changed) + workspace of one layer call."""
+    B, H, W, C = shape
+    dev = y.device
+    k, D = y.shape[1], y.shape[2]
+    pos_dim = params["pos_latent"].shape[1] if use_pos else 0
+    desc = _lib.make_desc(B, H, W, C, k, D, heads=num_heads, norm=norm, integration=integration, pos_dim=pos_dim,
+                          duplex=duplex, flags=flags)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    names = SIMPLEX_PARAMS + (DUPLEX_PARAMS if duplex else ())
+    if weights_version is None:
+        weights_version = tuple((params[n].data_ptr(), params[n]._version) for n in names)
+    fkey = (H, W, k, D, C, pos_dim, integration, duplex, str(dev), weights_version, weights_epoch())
+    if plan.folded is None or plan.folded_key != fkey or FORCE_REFOLD:
+        nfl = _lib.folded_floats(desc)
+        if plan.folded is None or plan.folded.numel() != nfl or plan.folded.device != dev:
+            plan.folded = torch.empty(nfl, dtype=torch.float32, device=dev)
+        wstruct = _lib.GfAttnWeights()
+        for n in names:
+            t = params[n].detach()
+            _check_tensor(t, n, dev)
+            setattr(wstruct, n, t.data_ptr())
+        _lib.check(lib.gf_attn_fold_weights(ctypes.byref(desc), ctypes.byref(wstruct), plan.folded.data_ptr(), stream),
+                   "gf_attn_fold_weights")
+        plan.folded_key = fkey
+    wkey = (B, H, W, C, k, D, pos_dim, integration, norm, duplex, str(dev))
+    ws = plan.ws.get(wkey)
+    if ws is None:
+        ws = torch.empty(_lib.workspace_bytes(desc), dtype=torch.uint8, device=dev)
+        plan.ws[wkey] = ws
+    return desc, ws, stream
+
+
 def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[str, torch.Tensor], plan: _Plan, *,
                                 integration: str = "mul", norm: Optional[str] = "layer", duplex: bool = False,
                                 num_heads: int = 1, use_pos: bool = True, return_att: bool = False,
@@ -96,12 +169,13 @@ def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[s
     convolution (load side) and the noise + fused_bias_act step + next-layer style scale (store side), fused into the
     kernel.
 
-    stage: "all" | "prologue" | "token" (simplex only).  "prologue" runs stages W + I for a layer whose activations do
-    not exist yet (x may be None, give x_shape; postop needs only in_scale) -- they depend on the latents alone, so a
-    caller can hoist them onto a side stream; "token" then runs stage T on the prepared workspace."""
+    stage: "all" | "prologue" | "token".  "prologue" runs stages W + I for a layer whose activations do not exist yet (x may
+    be None, give x_shape; postop needs only in_scale) -- they depend on the latents alone (see ``prologue_batch`` for all
+    layers of a network in one launch); "token" then runs the rest on the prepared workspace: stage T for a simplex layer;
+    pass A + centroid keys + stage T for a duplex layer (its query tables and V^T are the prepared part)."""
     lib = _lib.load()
-    if stage not in ("all", "prologue", "token") or (stage != "all" and duplex):
-        raise ValueError("stage must be 'all', or 'prologue' / 'token' for a simplex layer")
+    if stage not in ("all", "prologue", "token") or (stage == "prologue" and duplex):
+        raise ValueError("stage must be 'all' | 'token', or 'prologue' for a simplex layer (duplex layers: prologue_batch)")
     if x is None:
         if stage != "prologue" or x_shape is None:
             raise ValueError("x may only be omitted (with x_shape) for stage='prologue'")
@@ -116,78 +190,25 @@ def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[s
     _check_tensor(y, "y", dev)
     if y.dim() != 3 or y.shape[0] != B:
         raise ValueError(f"y must be [B, k, D] with B={B}, got {tuple(y.shape)}")
-    k, D = y.shape[1], y.shape[2]
-    pos_dim = params["pos_latent"].shape[1] if use_pos else 0
-    flags = (_lib.FLAG_FP32_EXACT if exact_fp32 else 0) | (_lib.FLAG_CENTROIDS_IN if (duplex and centroids is not None) else 0)
-    desc = _lib.make_desc(B, H, W, C, k, D, heads=num_heads, norm=norm, integration=integration, pos_dim=pos_dim,
-                          duplex=duplex, flags=flags)
-    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    k = y.shape[1]
+    flags = ((_lib.FLAG_FP32_EXACT if exact_fp32 else 0) | (_lib.FLAG_CENTROIDS_IN if (duplex and centroids is not None) else 0)
+             | (_lib.FLAG_TABLES_READY if (duplex and stage == "token") else 0))
 
     with torch.cuda.device(dev):
-        # stage W: fold weights (cached until a parameter changes)
-        names = SIMPLEX_PARAMS + (DUPLEX_PARAMS if duplex else ())
-        if weights_version is None:
-            weights_version = tuple((params[n].data_ptr(), params[n]._version) for n in names)
-        fkey = (H, W, k, D, C, pos_dim, integration, duplex, str(dev), weights_version, weights_epoch())
-        if plan.folded is None or plan.folded_key != fkey or FORCE_REFOLD:
-            nfl = _lib.folded_floats(desc)
-            if plan.folded is None or plan.folded.numel() != nfl or plan.folded.device != dev:
-                plan.folded = torch.empty(nfl, dtype=torch.float32, device=dev)
-            wstruct = _lib.GfAttnWeights()
-            for n in names:
-                t = params[n].detach()
-                _check_tensor(t, n, dev)
-                setattr(wstruct, n, t.data_ptr())
-            _lib.check(lib.gf_attn_fold_weights(ctypes.byref(desc), ctypes.byref(wstruct), plan.folded.data_ptr(), stream),
-                       "gf_attn_fold_weights")
-            plan.folded_key = fkey
-        # workspace
-        wkey = (B, H, W, C, k, D, pos_dim, integration, norm, duplex, str(dev))
-        ws = plan.ws.get(wkey)
-        if ws is None:
-            ws = torch.empty(_lib.workspace_bytes(desc), dtype=torch.uint8, device=dev)
-            plan.ws[wkey] = ws
+        desc, ws, stream = _plan_call(lib, (B, H, W, C), y, params, plan, integration=integration, norm=norm, duplex=duplex,
+                                      num_heads=num_heads, use_pos=use_pos, flags=flags, weights_version=weights_version)
         if stage != "prologue":
             if out is None:
                 out = torch.empty_like(x)
             else:
                 _check_tensor(out, "out", dev)
         att = torch.empty((B, H * W, k), dtype=torch.float32, device=dev) if (return_att and stage != "prologue") else None
-        post_ref = None
-        if postop is not None:
-            pst = _lib.GfAttnPostop()
-            keep = []
-            for fld in ("bias", "noise", "strength"):
-                t = postop.get(fld)
-                if t is not None:
-                    t = t.detach()
-                    _check_tensor(t, "postop." + fld, dev)
-                    keep.append(t)
-                    setattr(pst, fld, t.data_ptr())
-            nz = postop.get("noise")
-            if nz is not None and nz.numel() not in (H * W, B * H * W):
-                raise ValueError("postop.noise must have H*W or B*H*W elements")
-            if postop.get("bias") is not None and postop["bias"].numel() != C:
-                raise ValueError("postop.bias must have C elements")
-            pst.noise_bstride = H * W if (nz is not None and nz.numel() == B * H * W and B > 1) else 0
-            pst.act = {"linear": 0, "lrelu": 1}[postop.get("act", "lrelu")]
-            pst.gain = float(postop.get("gain", 1.0))
-            for fld in ("in_scale", "post_scale"):
-                t = postop.get(fld)
-                if t is None:
-                    continue
-                t = t.detach()
-                if t.shape != (B, C) or t.dtype != torch.float32 or t.device != dev:
-                    raise ValueError(f"postop.{fld} must be a float32 [B, C] tensor on {dev}")
-                if not (t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.stride(0) >= C and t.data_ptr() % 16 == 0):
-                    t = t.contiguous()
-                keep.append(t)
-                setattr(pst, fld, t.data_ptr())
-                setattr(pst, fld + "_ld", t.stride(0))
-            post_ref = ctypes.byref(pst)
+        pst, keep = _make_postop(postop, B, H, W, C, dev)
+        post_ref = ctypes.byref(pst) if pst is not None else None
         timer = STAGE_TIMER
         if timer is not None:
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0, ev1, evc = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            evc.record()                                # start of the whole call (stage I + stage T)
         if duplex:
             if timer is not None:
                 ev0.record()
@@ -215,9 +236,55 @@ def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[s
                        "gf_attn_simplex_fwd_ex")
         if timer is not None:
             ev1.record()
-            timer.records.append((ev0, ev1, 2 * 4 * B * H * W * C))
+            timer.records.append((ev0, ev1, 2 * 4 * B * H * W * C, evc))
+        del keep
     att_map = att.view(B, H, W, k).permute(0, 3, 1, 2) if att is not None else None   # [B,k,H,W] view
     return out, att_map, cen
+
+
+@torch.no_grad()
+def prologue_batch(items) -> None:
+    """Stage I of several layers in ONE launch (``gf_attn_prologue_batch``).  items: iterable of
+    (module: BipartiteAttention, y [B,k,D], x_shape (B,H,W,C), in_scale [B,C] | None).  Afterwards call each module with
+    ``stage="token"`` (same y, same in_scale).  Stage W (weight folding) of a layer runs first if its parameters changed."""
+    lib = _lib.load()
+    items = list(items)
+    if not items:
+        return
+    dev = items[0][1].device
+    n = len(items)
+    descs, keep = [], []
+    arr_d = (ctypes.c_void_p * n)()
+    arr_y = (ctypes.c_void_p * n)()
+    arr_f = (ctypes.c_void_p * n)()
+    arr_w = (ctypes.c_void_p * n)()
+    arr_p = (ctypes.c_void_p * n)()
+    timer = STAGE_TIMER
+    with torch.cuda.device(dev):
+        if timer is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stream = None
+        for i, (m, y, shape, in_scale) in enumerate(items):
+            _check_tensor(y, "y", dev)
+            flags = _lib.FLAG_FP32_EXACT if m.exact_fp32 else 0
+            desc, ws, stream = _plan_call(lib, tuple(shape), y, m.param_dict(), m._plan, integration=m.integration, norm=m.norm,
+                                          duplex=m.duplex, num_heads=m.num_heads, use_pos=m.use_pos, flags=flags)
+            pst, kp = _make_postop(dict(in_scale=in_scale) if in_scale is not None else None, shape[0], shape[1], shape[2], shape[3], dev)
+            descs.append(desc)
+            keep.extend(kp)
+            keep.append(pst)
+            arr_d[i] = ctypes.addressof(desc)
+            arr_y[i] = y.data_ptr()
+            arr_f[i] = m._plan.folded.data_ptr()
+            arr_w[i] = ws.data_ptr()
+            arr_p[i] = ctypes.addressof(pst) if pst is not None else None
+        if timer is not None:
+            e0.record()
+        _lib.check(lib.gf_attn_prologue_batch(n, arr_d, arr_y, arr_f, arr_w, arr_p, stream), "gf_attn_prologue_batch")
+        if timer is not None:
+            e1.record()
+            timer.batch_records.append((e0, e1))
+    del keep, descs
 
 
 class BipartiteAttention(nn.Module):
@@ -251,7 +318,7 @@ class BipartiteAttention(nn.Module):
                 return_att: bool = False, out: Optional[torch.Tensor] = None, postop: Optional[dict] = None,
                 stage: str = "all", need_centroids: bool = True):
         """x [B,H,W,C] channels-last, y [B,k,D] -> (x', att [B,k,H,W] | None, centroids [B,k,C] | None).
-        stage="token": the per-image tables were already built by ``prepare`` (same y, same in_scale)."""
+        stage="token": the latent-only tables were already built by ``prepare`` / ``prologue_batch`` (same y, same in_scale)."""
         if torch.is_grad_enabled() and (x.requires_grad or y.requires_grad or any(p.requires_grad for p in self.parameters())):
             if postop is not None:
                 raise RuntimeError("the fused post-op is inference-only; apply noise/bias/activation outside when training")

@@ -117,6 +117,24 @@ int gf_attn_prologue_ex(const gf_attn_desc* desc, const float* Y, const float* f
   return prologue(L, desc, Y, Y, L.D, folded, (float*)ws, (cudaStream_t)stream, post ? post->in_scale : nullptr, post ? post->in_scale_ld : 0);
 }
 
+int gf_attn_prologue_batch(int n, const gf_attn_desc* const* descs, const float* const* Y, const float* const* folded, void* const* ws,
+                           const gf_attn_postop* const* posts, void* stream) {
+  if (n <= 0) return GF_OK;
+  if (n > 64) { set_error("gf_attn_prologue_batch: at most 64 layers per call, got %d", n); return GF_ERR_INVALID; }
+  if (!descs || !Y || !folded || !ws) { set_error("gf_attn_prologue_batch: null pointer"); return GF_ERR_INVALID; }
+  Layout Ls[64];
+  float* wsf[64];
+  int rc;
+  for (int i = 0; i < n; ++i) {
+    if (!descs[i] || !Y[i] || !folded[i] || !ws[i]) { set_error("gf_attn_prologue_batch: null pointer in layer %d", i); return GF_ERR_INVALID; }
+    if ((rc = make_layout(descs[i], &Ls[i]))) return rc;
+    if (descs[i]->flags & GF_FLAG_CENTROIDS_IN) { set_error("gf_attn_prologue_batch: layer %d takes its centroids as input (no pass-A tables to build)", i); return GF_ERR_INVALID; }
+    wsf[i] = (float*)ws[i];
+  }
+  if ((rc = check_device())) return rc;
+  return prologue_batch(n, Ls, descs, Y, folded, wsf, posts, (cudaStream_t)stream);
+}
+
 int gf_attn_norm_stats(const gf_attn_desc* desc, const float* X, void* ws, void* stream) {
   Layout L;
   int rc = make_layout(desc, &L);
@@ -160,7 +178,7 @@ int gf_attn_duplex_fwd_ex(const gf_attn_desc* desc, const float* X, const float*
     // load-side scale d (x_in = x * d): pass A sees x only through x.M^T and A.x, so d is folded into M and into Xbar
     const float* isc = post ? post->in_scale : nullptr;
     const int isc_ld = post ? post->in_scale_ld : 0;
-    if ((rc = duplex_tables(L, desc, Y, folded, ws, st, isc, isc_ld))) return rc;
+    if (!(desc->flags & GF_FLAG_TABLES_READY) && (rc = duplex_tables(L, desc, Y, folded, ws, st, isc, isc_ld))) return rc;
     const bool cen_tc = tc_centroid_supported(L, desc);
     if (cen_tc) {
       if ((rc = centroid_pass_tc(L, desc, X, ws, st, isc, isc_ld))) return rc;
@@ -175,8 +193,9 @@ int gf_attn_duplex_fwd_ex(const gf_attn_desc* desc, const float* X, const float*
                    nullptr, 0, 1, folded + L.f_BV2, cen_tc)))
       return rc;
   }
+  // V^T depends on the latents only: duplex_tables() already built it, unless pass A was skipped (GF_FLAG_CENTROIDS_IN)
   if ((rc = prologue(L, desc, Y, centroids_inout ? centroids_inout : ws + L.w_XBAR, L.C, folded, ws, st, post ? post->in_scale : nullptr,
-                     post ? post->in_scale_ld : 0, centroids_inout == nullptr)))
+                     post ? post->in_scale_ld : 0, centroids_inout == nullptr, (desc->flags & GF_FLAG_CENTROIDS_IN) != 0)))
     return rc;
   return token_pass(L, desc, X, Xout, att, ws, post, st);
 }

@@ -76,7 +76,9 @@ int fold_weights(const Layout& L, const gf_attn_desc* d, const gf_attn_weights* 
 // key_source: Y [B*k, D] (simplex) or centroids [B*k, C] (duplex); kdim = D or C.
 int prologue(const Layout& L, const gf_attn_desc* d, const float* Y, const float* key_source, int kdim,
              const float* folded, float* ws, cudaStream_t st, const float* in_scale = nullptr, int in_scale_ld = 0,
-             bool keys_from_xbar = false);
+             bool keys_from_xbar = false, bool with_v = true);
+int prologue_batch(int n, const Layout* Ls, const gf_attn_desc* const* ds, const float* const* Ys, const float* const* fs, float* const* wss,
+                   const gf_attn_postop* const* posts, cudaStream_t st);
 int duplex_tables(const Layout& L, const gf_attn_desc* d, const float* Y, const float* folded, float* ws, cudaStream_t st,
                   const float* in_scale = nullptr, int in_scale_ld = 0);
 // C[M,N] = alpha * opA(A) opB(B) + E[(m % emod), n] + v[n]

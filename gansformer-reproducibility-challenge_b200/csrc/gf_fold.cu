@@ -470,40 +470,256 @@ __global__ void __launch_bounds__(256, 4) finalize_kernel(const float* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// stage I in ONE launch for everything that depends on the latents only (the K = D product, the TF32 rounding, the
+// positional-logit tables and V^T): replaces gemm_kernel + finalize_kernel for the simplex keys and for the duplex pass-A
+// query tables.  Up to STAGE_I_MAX_JOBS layers per launch (the generator batches every layer's prologue of a step into
+// one launch: they all read the same latents).  Arithmetic and operation order are those of gemm_kernel + finalize_kernel
+// (fp32 FMA chain over d ascending, + constant row, * in_scale, * kf, round), so both routes produce the same bits.
+// ------------------------------------------------------------------------------------------------------
+constexpr int STAGE_I_MAX_JOBS = 16;
+struct StageIJob {
+  const float *Y, *A, *Cst, *AV, *CV, *ROW, *COL, *in_scale;
+  float *Kp, *Vt, *Rt, *Ct;
+  int H, W, C, k, D, p, KP, Cout, LDK, in_ld;
+  int tf32_k, tf32_v;            // round K' (and take the logits in log2 units) / round V^T for the tcgen05 kernels
+  int nvblk, npos, nkblk;        // CTAs per image and role
+  int blk_begin;                 // first blockIdx.y of this job
+};
+struct StageIBatch { StageIJob job[STAGE_I_MAX_JOBS]; int njobs; };
+
+__global__ void __launch_bounds__(256, 4) stage_i_kernel(const __grid_constant__ StageIBatch batch) {
+  int ji = 0;
+#pragma unroll 1
+  while (ji + 1 < batch.njobs && (int)blockIdx.y >= batch.job[ji + 1].blk_begin) ++ji;
+  const StageIJob& J = batch.job[ji];
+  const int b = blockIdx.x, blk = (int)blockIdx.y - J.blk_begin;
+  const int k = J.k, D = J.D, C = J.C, KP = J.KP, LDK = J.LDK, p = J.p;
+  extern __shared__ float ysm[];                                  // Y[b]: k x D, then kap: k x (p + 1)
+  for (int i = threadIdx.x; i < k * D; i += blockDim.x) ysm[i] = J.Y[(size_t)b * k * D + i];
+  __syncthreads();
+  if (blk < J.nvblk) {
+    // ---- V^T[b, c, :] = Y[b] . AV[:, c] + CV[c]  (zero for the padded latents); one thread per channel
+    const int Cout = J.Cout;
+    const int c = blk * 256 + threadIdx.x;
+    if (c >= Cout) return;
+    const float cv = J.CV[c];
+    float* out = J.Vt + ((size_t)b * Cout + c) * KP;
+    for (int j0 = 0; j0 < KP; j0 += 16) {
+      float acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+      for (int d0 = 0; d0 < D; d0 += 16) {
+        float a[16];
+#pragma unroll
+        for (int dd = 0; dd < 16; ++dd) a[dd] = d0 + dd < D ? J.AV[(size_t)(d0 + dd) * Cout + c] : 0.f;
+#pragma unroll
+        for (int dd = 0; dd < 16; ++dd) {
+          if (d0 + dd < D) {
+            const float* yr = ysm + (size_t)j0 * D + d0 + dd;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (j0 + j < k) acc[j] = fmaf(yr[j * D], a[dd], acc[j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        float4 r;
+        r.x = j0 + j4 * 4 + 0 < k ? acc[j4 * 4 + 0] + cv : 0.f; r.y = j0 + j4 * 4 + 1 < k ? acc[j4 * 4 + 1] + cv : 0.f;
+        r.z = j0 + j4 * 4 + 2 < k ? acc[j4 * 4 + 2] + cv : 0.f; r.w = j0 + j4 * 4 + 3 < k ? acc[j4 * 4 + 3] + cv : 0.f;
+        if (J.tf32_v) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
+        reinterpret_cast<float4*>(out)[j0 / 4 + j4] = r;
+      }
+    }
+    return;
+  }
+  if (blk < J.nvblk + J.npos) {
+    // ---- positional logit tables: kap[j, q] = (Y[b] . A + Cst)[j, C + q], q <= p (the last one is the bias column)
+    float* kap = ysm + k * D;
+    const int pw = p + 1;
+    for (int i = threadIdx.x; i < k * pw; i += blockDim.x) {
+      const int j = i / pw, q = i - j * pw;
+      float acc = 0.f;
+      for (int d0 = 0; d0 < D; d0 += 8) {                 // 8 independent loads in flight (one L2 round trip per batch)
+        float a[8];
+#pragma unroll
+        for (int dd = 0; dd < 8; ++dd) a[dd] = d0 + dd < D ? J.A[(size_t)(d0 + dd) * LDK + C + q] : 0.f;
+#pragma unroll
+        for (int dd = 0; dd < 8; ++dd) if (d0 + dd < D) acc = fmaf(ysm[j * D + d0 + dd], a[dd], acc);
+      }
+      kap[i] = acc + J.Cst[(size_t)j * LDK + C + q];
+    }
+    __syncthreads();
+    const int half = p / 2, H = J.H, W = J.W;
+    for (int i = (blk - J.nvblk) * blockDim.x + threadIdx.x; i < (H + W) * KP; i += J.npos * blockDim.x) {
+      const int r = i / KP, j = i % KP;
+      const bool is_row = r < H;
+      float val;
+      if (j >= k) {
+        val = is_row ? -INFINITY : 0.f;
+      } else {
+        const float* kj = kap + j * pw;
+        float acc = 0.f;
+        if (is_row) {
+#pragma unroll 8
+          for (int q = 0; q < half; ++q) acc = fmaf(J.ROW[r * half + q], kj[q], acc);
+          acc += kj[p];
+        } else {
+#pragma unroll 8
+          for (int q = 0; q < half; ++q) acc = fmaf(J.COL[(r - H) * half + q], kj[half + q], acc);
+        }
+        val = J.tf32_k ? acc * GF_LOG2E : acc;
+      }
+      if (is_row) J.Rt[((size_t)b * H + r) * KP + j] = val;
+      else J.Ct[((size_t)b * W + (r - H)) * KP + j] = val;
+    }
+    return;
+  }
+  // ---- K' role: one thread = 4 channels x 8 latents; the D rows of A are loaded once per thread (4 in flight)
+  const int C4 = C >> 2, groups = KP / 8;
+  const float4* isc4 = J.in_scale ? reinterpret_cast<const float4*>(J.in_scale + (size_t)b * J.in_ld) : nullptr;
+  float4* Kp4 = reinterpret_cast<float4*>(J.Kp + (size_t)b * KP * C);
+  for (int item = (blk - J.nvblk - J.npos) * blockDim.x + threadIdx.x; item < C4 * groups; item += J.nkblk * blockDim.x) {
+    const int g = item / C4, c4 = item - g * C4, j0 = g * 8;
+    float4 acc[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) acc[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j0 < k) {
+      for (int d0 = 0; d0 < D; d0 += 4) {
+        float4 a[4];
+#pragma unroll
+        for (int dd = 0; dd < 4; ++dd) a[dd] = d0 + dd < D ? *reinterpret_cast<const float4*>(J.A + (size_t)(d0 + dd) * LDK + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int dd = 0; dd < 4; ++dd) {
+          if (d0 + dd < D) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              if (j0 + jj < k) {
+                const float y = ysm[(j0 + jj) * D + d0 + dd];
+                acc[jj].x = fmaf(y, a[dd].x, acc[jj].x); acc[jj].y = fmaf(y, a[dd].y, acc[jj].y);
+                acc[jj].z = fmaf(y, a[dd].z, acc[jj].z); acc[jj].w = fmaf(y, a[dd].w, acc[jj].w);
+              }
+            }
+          }
+        }
+      }
+    }
+    const float4 d = isc4 ? isc4[c4] : make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j0 + jj < k) {
+        const float4 cst = *reinterpret_cast<const float4*>(J.Cst + (size_t)(j0 + jj) * LDK + c4 * 4);
+        r = make_float4((acc[jj].x + cst.x) * d.x, (acc[jj].y + cst.y) * d.y, (acc[jj].z + cst.z) * d.z, (acc[jj].w + cst.w) * d.w);
+        if (J.tf32_k) {
+          constexpr float kf = GF_TF32_TRUNC_COMP * GF_LOG2E;
+          r.x = round_tf32(r.x * kf); r.y = round_tf32(r.y * kf); r.z = round_tf32(r.z * kf); r.w = round_tf32(r.w * kf);
+        }
+      }
+      Kp4[(size_t)(j0 + jj) * C4 + c4] = r;
+    }
+  }
+}
+
+static void stage_i_fill(StageIJob& J, const Layout& L, const float* Y, const float* A, const float* Cst, const float* AV, const float* CV,
+                         const float* f, float* Kp, float* Vt, float* Rt, float* Ct, const float* in_scale, int in_ld, int tf32_k, int tf32_v) {
+  J.Y = Y; J.A = A; J.Cst = Cst; J.AV = AV; J.CV = CV; J.ROW = f + L.f_ROW; J.COL = f + L.f_COL; J.in_scale = in_scale;
+  J.Kp = Kp; J.Vt = Vt; J.Rt = Rt; J.Ct = Ct;
+  J.H = L.H; J.W = L.W; J.C = L.C; J.k = L.k; J.D = L.D; J.p = L.p; J.KP = L.KP; J.Cout = L.Cout; J.LDK = L.LDK; J.in_ld = in_ld;
+  J.tf32_k = tf32_k; J.tf32_v = tf32_v;
+  J.nvblk = Vt ? (L.Cout + 255) / 256 : 0;
+  J.npos = ((L.H + L.W) * L.KP + 1023) / 1024;
+  J.nkblk = ((L.C / 4) * (L.KP / 8) + 255) / 256;
+  J.blk_begin = 0;
+}
+
+static int stage_i_launch(StageIBatch& batch, int B, cudaStream_t st) {
+  int total = 0;
+  size_t smem = 0;
+  for (int i = 0; i < batch.njobs; ++i) {
+    StageIJob& J = batch.job[i];
+    J.blk_begin = total;
+    total += J.nvblk + J.npos + J.nkblk;
+    const size_t need = ((size_t)J.k * J.D + (size_t)J.k * (J.p + 1)) * sizeof(float);
+    if (need > smem) smem = need;
+  }
+  if (smem > 48 * 1024) { set_error("stage I: k * (D + p + 1) floats exceed 48 KB of shared memory"); return GF_ERR_UNSUPPORTED; }
+  stage_i_kernel<<<dim3(B, total), 256, smem, st>>>(batch);
+  GF_LAUNCH_OK();
+  return GF_OK;
+}
+
 int prologue(const Layout& L, const gf_attn_desc* d, const float* Y, const float* key_source, int kdim,
-             const float* f, float* ws, cudaStream_t st, const float* in_scale, int in_scale_ld, bool keys_from_xbar) {
+             const float* f, float* ws, cudaStream_t st, const float* in_scale, int in_scale_ld, bool keys_from_xbar, bool with_v) {
   int rc;
   const float* AK = f + (keys_from_xbar ? L.f_AK2 : L.f_AK);
   const float* CK = f + (keys_from_xbar ? L.f_CK2 : L.f_CK);
   // operands of the tcgen05 TF32 contractions are pre-rounded here; the fp32-FMA kernel gets them untouched
   const int tf32 = (!(d->flags & GF_FLAG_FP32_EXACT) && tc_supported(L, d)) ? 1 : 0;
-  // KPALL [B*k, LDK] = key_source @ AK + CK
+  if (!L.duplex) {
+    // simplex: keys from the latents (inner dimension D): the whole of stage I is one launch
+    StageIBatch batch;
+    batch.njobs = 1;
+    stage_i_fill(batch.job[0], L, Y, AK, CK, f + L.f_AV, f + L.f_CV, f, ws + L.w_Kp, ws + L.w_Vt, ws + L.w_Rt, ws + L.w_Ct,
+                 in_scale, in_scale_ld, tf32, tf32);
+    return stage_i_launch(batch, L.B, st);
+  }
+  // duplex: KPALL [B*k, LDK] = key_source @ AK + CK with key_source = Xbar or the centroids (inner dimension C): tensor cores
   if ((rc = gemm(st, L.B * L.k, L.LDK, kdim, key_source, kdim, false, AK, L.LDK, false, ws + L.w_KPALL, L.LDK, 1.f,
-                 CK, L.LDK, L.k, nullptr, tf32 != 0 && kdim >= 64)))   // K = D = 32 (simplex): tiny, stays fp32
+                 CK, L.LDK, L.k, nullptr, tf32 != 0 && kdim >= 64)))
     return rc;
   const int npos = ((L.H + L.W) * L.KP + 1023) / 1024;
-  const int nblk = npos + (L.Cout + 255) / 256 + (L.KP * L.C + 256 * 8 - 1) / (256 * 8);
+  const int nblk = npos + (with_v ? (L.Cout + 255) / 256 : 0) + (L.KP * L.C + 256 * 8 - 1) / (256 * 8);
   finalize_kernel<<<dim3(L.B, nblk), 256, (size_t)L.k * L.D * sizeof(float), st>>>(ws + L.w_KPALL, Y, f + L.f_AV, f + L.f_CV, f + L.f_ROW, f + L.f_COL,
-                                                   ws + L.w_Kp, ws + L.w_Vt, ws + L.w_Rt, ws + L.w_Ct,
+                                                   ws + L.w_Kp, with_v ? ws + L.w_Vt : nullptr, ws + L.w_Rt, ws + L.w_Ct,
                                                    L.H, L.W, L.C, L.k, L.D, L.p, L.KP, L.Cout, L.LDK, tf32, npos, in_scale, in_scale_ld);
   GF_LAUNCH_OK();
   return GF_OK;
 }
 
-// duplex pass A tables: M [B,KP,C] and the positional logit tables of the latent queries
+// duplex pass A tables: M [B,KP,C] and the positional logit tables of the latent queries -- plus V^T of stage T, which
+// depends on the latents only (one launch for everything that does not need the centroids)
 int duplex_tables(const Layout& L, const gf_attn_desc* d, const float* Y, const float* f, float* ws, cudaStream_t st,
                   const float* in_scale, int in_scale_ld) {
-  int rc;
   const int tf32 = tc_centroid_supported(L, d) ? 1 : 0;      // M is an operand of the tcgen05 pass-A kernel: pre-round it
-  if ((rc = gemm(st, L.B * L.k, L.LDK, L.D, Y, L.D, false, f + L.f_AM, L.LDK, false, ws + L.w_MALL, L.LDK, 1.f,
-                 f + L.f_CM, L.LDK, L.k, nullptr, tf32 != 0)))   // pass-A logits: M is TF32-rounded right after anyway
-    return rc;
-  const int npos = ((L.H + L.W) * L.KP + 1023) / 1024;
-  const int nblk = npos + (L.KP * L.C + 256 * 8 - 1) / (256 * 8);
-  finalize_kernel<<<dim3(L.B, nblk), 256, 0, st>>>(ws + L.w_MALL, Y, nullptr, nullptr, f + L.f_ROW, f + L.f_COL,
-                                                   ws + L.w_M, nullptr, ws + L.w_Rt2, ws + L.w_Ct2,
-                                                   L.H, L.W, L.C, L.k, L.D, L.p, L.KP, L.Cout, L.LDK, tf32, npos, in_scale, in_scale_ld);
-  GF_LAUNCH_OK();
+  const int tf32_v = (!(d->flags & GF_FLAG_FP32_EXACT) && tc_supported(L, d)) ? 1 : 0;
+  StageIBatch batch;
+  batch.njobs = 1;
+  stage_i_fill(batch.job[0], L, Y, f + L.f_AM, f + L.f_CM, f + L.f_AV, f + L.f_CV, f, ws + L.w_M, ws + L.w_Vt, ws + L.w_Rt2, ws + L.w_Ct2,
+               in_scale, in_scale_ld, tf32, tf32_v);
+  return stage_i_launch(batch, L.B, st);
+}
+
+// Stage I of several layers (same batch size, same latents or not) in ONE launch: simplex layers get their keys, V^T and
+// positional tables; duplex layers their pass-A query tables and V^T (everything that does not depend on the activations).
+int prologue_batch(int n, const Layout* Ls, const gf_attn_desc* const* ds, const float* const* Ys, const float* const* fs, float* const* wss,
+                   const gf_attn_postop* const* posts, cudaStream_t st) {
+  int done = 0;
+  while (done < n) {
+    StageIBatch batch;
+    batch.njobs = 0;
+    const int B = Ls[done].B;
+    while (done < n && batch.njobs < STAGE_I_MAX_JOBS && Ls[done].B == B) {
+      const Layout& L = Ls[done];
+      const gf_attn_desc* d = ds[done];
+      const float* f = fs[done];
+      float* ws = wss[done];
+      const gf_attn_postop* post = posts ? posts[done] : nullptr;
+      const float* isc = post ? post->in_scale : nullptr;
+      const int isc_ld = post ? post->in_scale_ld : 0;
+      const int tf32_t = (!(d->flags & GF_FLAG_FP32_EXACT) && tc_supported(L, d)) ? 1 : 0;
+      StageIJob& J = batch.job[batch.njobs++];
+      if (L.duplex)
+        stage_i_fill(J, L, Ys[done], f + L.f_AM, f + L.f_CM, f + L.f_AV, f + L.f_CV, f, ws + L.w_M, ws + L.w_Vt, ws + L.w_Rt2, ws + L.w_Ct2,
+                     isc, isc_ld, tc_centroid_supported(L, d) ? 1 : 0, tf32_t);
+      else
+        stage_i_fill(J, L, Ys[done], f + L.f_AK, f + L.f_CK, f + L.f_AV, f + L.f_CV, f, ws + L.w_Kp, ws + L.w_Vt, ws + L.w_Rt, ws + L.w_Ct,
+                     isc, isc_ld, tf32_t, tf32_t);
+      ++done;
+    }
+    int rc = stage_i_launch(batch, B, st);
+    if (rc) return rc;
+  }
   return GF_OK;
 }
 

@@ -48,6 +48,7 @@ struct Params {
   const float* Rt; const float* Ct; float* part;
   float* xbar; const float* in_scale; int in_ld;     // one split per image: the kernel writes the normalised Xbar [B,k,C] itself
   int n, H, W, k, nsplit, tiles_per_image, nst1, nst2;
+  int lead;                  // ring 1 may run at most `lead` tiles ahead of the completed GEMM2s (L2 reuse distance of ring 2)
 };
 
 struct Bars {
@@ -124,6 +125,7 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   float* mref = red + 4 * KP;                                       // [KP]
   float* resc = mref + KP;                                          // [KP]
   volatile int* trigf = reinterpret_cast<volatile int*>(resc + KP);  // [2] per-tile-parity trigger flags
+  volatile int* g2done = trigf + 2;                                  // tiles whose GEMM2 is known complete (row warps -> producer 1)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.y, sp = blockIdx.x;
@@ -142,11 +144,13 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   }
 
   if (threadIdx.x < KP) { mref[threadIdx.x] = -INFINITY; resc[threadIdx.x] = 1.f; }
-  if (threadIdx.x < 2) trigf[threadIdx.x] = 0;
+  if (threadIdx.x < 3) trigf[threadIdx.x] = 0;                       // trigf[0..1] and g2done
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmX); prefetch_tmap(&tmX2); prefetch_tmap(&tmM);
-    for (int i = 0; i < nst1; ++i) { mbar_init(bar(&bars->full1[i]), 1); mbar_init(bar(&bars->empty1[i]), 1); }
-    for (int i = 0; i < nst2; ++i) { mbar_init(bar(&bars->full2[i]), 1); mbar_init(bar(&bars->empty2[i]), 1); }
+#pragma unroll
+    for (int i = 0; i < MAX_ST1; ++i) { mbar_init(bar(&bars->full1[i]), 1); mbar_init(bar(&bars->empty1[i]), 1); }
+#pragma unroll
+    for (int i = 0; i < MAX_ST2; ++i) { mbar_init(bar(&bars->full2[i]), 1); mbar_init(bar(&bars->empty2[i]), 1); }
     mbar_init(bar(&bars->m_full), 1); mbar_init(bar(&bars->done), 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(&bars->s_full[i]), 1);
@@ -175,6 +179,14 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       int stage = 0; uint32_t ph = 0;
       for (int it = 0; it < ntiles; ++it) {
         const int row0 = b * P.n + (tile_beg + it) * TILE;       // short image (n < TILE): the box runs into the next image, masked below
+        // Bound the run-ahead: ring 2 (warp 1) fetches the same bytes again right before GEMM2 and must find them in L2.  The
+        // reuse distance is (lead of this fetch over GEMM2) x tile bytes x resident CTAs; beyond ~48 MB the B200's L2 has
+        // dropped the lines (tools/probes/l2_reuse_probe.cu) and X is read from HBM twice (1.7x at res 128 before this bound).
+        if (it - *g2done > P.lead) {
+          const long long t0 = clock64();
+          while (it - *g2done > P.lead)
+            if (clock64() - t0 > 4000000000ll) __trap();          // a protocol bug must trap, not hang the GPU
+        }
         for (int s = 0; s < NS; ++s) {
           mbar_wait(bar(&bars->empty1[stage]), ph ^ 1u);
           const uint32_t fb = bar(&bars->full1[stage]);
@@ -353,6 +365,7 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       if (it > 0) {
         mbar_wait(bar(&bars->e_free[buf ^ 1]), (uint32_t)(((it - 1) >> 1) & 1));
         tc_fence_after();
+        if (rtid == 0) *g2done = it;                                  // GEMM2 of tiles < it complete: producer 1 may fetch tile it + lead
       }
       if (full && it > 0) {
         // M=64 accumulators: channel c of a 64-channel block lives in TMEM lane (c % 16) + 32 * (c / 16): lanes 0-15 of
@@ -464,6 +477,15 @@ static int launch(const Layout& L, const float* X, float* ws, cudaStream_t st, c
   P.xbar = L.nsplit_cen == 1 ? ws + L.w_XBAR : nullptr; P.in_scale = in_scale; P.in_ld = in_scale_ld;
   P.n = L.n; P.H = L.H; P.W = L.W; P.k = L.k; P.nsplit = L.nsplit_cen; P.tiles_per_image = (L.n + TILE - 1) / TILE;
   P.nst1 = n1; P.nst2 = n2;
+  {
+    // L2 reuse-distance budget of the ring-2 re-fetch: (lead - 1/2) tiles x tile bytes x resident CTAs <= ~30 MB
+    static const int forced = []() { const char* e = getenv("GF_CEN_LEAD"); return e ? atoi(e) : 0; }();   // tuning aid, read once
+    const long long ctas = (long long)L.nsplit_cen * L.B * (NS / NS2);
+    const double resident = (double)(ctas < num_sms() ? ctas : num_sms());
+    int lead = (int)(30.0e6 / ((double)TILE * L.C * 4 * resident) + 0.5);
+    if (NS > 8) lead = 1 << 20;            // C = 512: ring 1 holds half a tile and cannot run ahead (measured: no re-fetch misses)
+    P.lead = forced > 0 ? forced : (lead < 2 ? 2 : (lead > 8 && NS <= 8 ? 8 : lead));
+  }
   const int smem_bytes = CF::FIXED_BYTES + n1 * SLAB_BYTES + n2 * HG_BYTES + 1024;
 #ifdef GF_DEBUG_WATCHDOG     // bring-up builds only (-DGF_DEBUG_WATCHDOG): a host-pinned buffer that records where a barrier wait timed out
 #ifdef GF_DEBUG_WATCHDOG     // bring-up builds only: record where a barrier wait timed out (tools/hang_debug.py)

@@ -20,7 +20,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .attention import BipartiteAttention, _Plan
+from .attention import BipartiteAttention, _Plan, prologue_batch
 from . import ops
 from ._state import weights_epoch, bump_weights_epoch
 from .ops import fir_filter
@@ -198,7 +198,7 @@ class SynthesisLayer(nn.Module):
             w_eff, wsq, phases = _cached(self, "conv", (self.weight,), self._conv_weights)
         fused = self.fusable(x)
         in_scale = None
-        # prepared = (event, demod): SynthesisNetwork already ran this layer's attention prologue on its side stream
+        # prepared = (event | None, demod): SynthesisNetwork already ran this layer's stage I (batched launch)
         if prepared is not None and not fused:
             raise RuntimeError("internal: prepared prologue for a layer that does not take the fused path")
         if fused and not self.up:      # demodulation rides on the attention kernel's load side (folded into K')
@@ -221,7 +221,7 @@ class SynthesisLayer(nn.Module):
             if fused:   # demod (load side) + noise + bias + leaky-ReLU + next style (store side) ride on the attention kernel
                 post = dict(bias=self.bias, noise=noise, strength=self.noise_strength, act="lrelu", gain=SQRT2,
                             in_scale=in_scale, post_scale=post_scale)
-                if prepared is not None:
+                if prepared is not None and prepared[0] is not None:
                     torch.cuda.current_stream(x.device).wait_event(prepared[0])
                 xo, att, centroids = self.attention(xl, y, centroids=centroids, return_att=return_att, postop=post,
                                                     stage="token" if prepared is not None else "all",
@@ -285,7 +285,11 @@ class SynthesisNetwork(nn.Module):
         self.register_buffer("fir", fir_filter())
         self.num_attention_layers = sum(1 for l in self.layers if l.attention is not None)
 
-    def forward(self, ws: torch.Tensor, noise_mode: str = "const", return_att: bool = False):
+    def forward(self, ws: torch.Tensor, noise_mode: str = "const", return_att: bool = False, return_features: bool = False):
+        """return_features: also return, per attention layer, the layer's activation after noise + bias + leaky-ReLU and
+        before the next convolution's style scale, as NCHW views (parity checks against oracle.generator, which returns the
+        same quantity).  The store-side fusion of the NEXT layer's style scale is switched off for such a call, so that the
+        captured activations are exactly the layer outputs; everything else takes the same kernels."""
         k = self.components_num
         B = ws.shape[0]
         y = ws[:, :k].contiguous()
@@ -302,33 +306,26 @@ class SynthesisNetwork(nn.Module):
                 return torch.cat(ws_, dim=1).contiguous(), torch.cat(bs_)
             wt_cat, b_cat = _cached(self, "affines", aff_params, cat_affines)
             styles_all = torch.addmm(b_cat, w_glob, wt_cat).split([a.weight.shape[0] for a in aff], dim=1)
-        # Attention prologues (weights fold, per-image K' / V^T / positional tables) depend only on the latents and the styles:
-        # optionally run them for every fused layer on a side stream, overlapped with the convolutions (inside a CUDA graph: a
-        # parallel branch).  Each layer waits for its own event right before its token pass.
+        # Stage I of every attention layer (keys / V^T / positional tables of a simplex layer, pass-A query tables + V^T of a
+        # duplex layer) depends only on the latents and the styles: ONE batched launch for the whole network
+        # (gf_attn_prologue_batch) instead of two small launches in front of every layer's token pass.
         prepared = [None] * len(self.layers)
-        if x.is_cuda and styles_all[0] is not None and os.environ.get("GF_HOIST_PROLOGUE"):   # opt-in: a same-box A/B showed no gain
-            cur = torch.cuda.current_stream(x.device)
-            side = self.__dict__.get("_side_stream")
-            if side is None or side.device != x.device:
-                side = self.__dict__["_side_stream"] = torch.cuda.Stream(device=x.device)
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
-                for li_, layer in enumerate(self.layers):
-                    if not layer.fusable(x) or layer.attention.duplex:
-                        continue
-                    d_ = None
-                    if not layer.up:
-                        _, wsq_, _ = _cached(layer, "conv", (layer.weight,), layer._conv_weights)
-                        d_ = ops.demod_coef(styles_all[li_], wsq_)
-                        d_.record_stream(cur)                            # produced on the side stream, consumed on the main one
-                    C_ = layer.weight.shape[0]
-                    layer.attention.prepare(y, (B, layer.resolution, layer.resolution, C_), in_scale=d_)
-                    ev = torch.cuda.Event()
-                    ev.record(side)
-                    prepared[li_] = (ev, d_)
-            # (tensors allocated on the side stream are kept alive by the layers' plans / this list until the step ends)
+        if x.is_cuda and styles_all[0] is not None and not os.environ.get("GF_NO_BATCH_PROLOGUE"):
+            items = []
+            for li_, layer in enumerate(self.layers):
+                if not layer.fusable(x):
+                    continue
+                d_ = None
+                if not layer.up:        # the demodulation of a stride-1 convolution rides on the attention kernel's load side
+                    _, wsq_, _ = _cached(layer, "conv", (layer.weight,), layer._conv_weights)
+                    d_ = ops.demod_coef(styles_all[li_], wsq_)
+                C_ = layer.weight.shape[0]
+                items.append((layer.attention, y, (B, layer.resolution, layer.resolution, C_), d_))
+                prepared[li_] = (None, d_)
+            prologue_batch(items)
         img = None
         atts = []
+        feats = []
         li = 0
         block_prescaled = False
         for bi, res in enumerate(self.block_resolutions):
@@ -338,7 +335,7 @@ class SynthesisNetwork(nn.Module):
                 layer = self.layers[li]
                 # conv0 -> conv1 inside a block has a single consumer: conv1's style scale is folded into conv0's store
                 post_scale = None
-                if j == 0 and nl == 2 and styles_all[li + 1] is not None and layer.fusable(x):
+                if j == 0 and nl == 2 and styles_all[li + 1] is not None and layer.fusable(x) and not return_features:
                     post_scale = styles_all[li + 1]
                 x, att, _ = layer(x, w_glob, y, noise_mode=noise_mode, return_att=return_att, styles=styles_all[li],
                                   prescaled=prescaled, post_scale=post_scale, prepared=prepared[li])
@@ -346,15 +343,18 @@ class SynthesisNetwork(nn.Module):
                 li += 1
                 if att is not None:
                     atts.append(att)
+                if return_features and layer.attention is not None:
+                    feats.append(x)
             # the tRGB pass reads x anyway: let it also write the next block's style-modulated input (inference only)
-            nxt = styles_all[li] if (li < len(self.layers) and styles_all[li] is not None and x.is_cuda
+            nxt = styles_all[li] if (li < len(self.layers) and styles_all[li] is not None and x.is_cuda and not return_features
                                      and not os.environ.get("GF_NO_TORGB_FUSE")) else None
             rgb = self.torgbs[bi](x, w_glob, styles=styles_all[len(self.layers) + bi], next_styles=nxt)
             block_prescaled = nxt is not None
             if block_prescaled:
                 rgb, x = rgb
             img = rgb if img is None else ops.upsample2x(img, self.fir, add=rgb)
-        return (img, atts) if return_att else img
+        out = (img,) + ((atts,) if return_att else ()) + ((feats,) if return_features else ())
+        return out[0] if len(out) == 1 else out
 
 
 class Generator(nn.Module):
@@ -376,9 +376,10 @@ class Generator(nn.Module):
                                           g_start_res=g_start_res, g_end_res=g_end_res, transformer=transformer,
                                           attn_kwargs=attn_kwargs)
 
-    def forward(self, z: torch.Tensor, c=None, truncation_psi: float = 1.0, noise_mode: str = "const", return_att: bool = False):
+    def forward(self, z: torch.Tensor, c=None, truncation_psi: float = 1.0, noise_mode: str = "const", return_att: bool = False,
+                return_features: bool = False):
         ws = self.mapping(z, truncation_psi=truncation_psi)
-        return self.synthesis(ws, noise_mode=noise_mode, return_att=return_att)
+        return self.synthesis(ws, noise_mode=noise_mode, return_att=return_att, return_features=return_features)
 
     def __deepcopy__(self, memo):
         """Copies parameters and buffers only: caches, captured graphs, streams and attention plans stay with the original

@@ -44,7 +44,8 @@ enum { GF_INT_MUL = 0, GF_INT_ADD = 1, GF_INT_BOTH = 2 };
 /* desc.flags */
 enum {
   GF_FLAG_FP32_EXACT = 1,   /* force the CUDA-core fp32-FMA kernel (tight-tolerance mode); default = tcgen05 TF32 */
-  GF_FLAG_CENTROIDS_IN = 2  /* duplex: skip pass A, take centroids_inout as input (iterative=True upstream) */
+  GF_FLAG_CENTROIDS_IN = 2, /* duplex: skip pass A, take centroids_inout as input (iterative=True upstream) */
+  GF_FLAG_TABLES_READY = 4  /* duplex: the pass-A query tables and V^T are already in ws (gf_attn_prologue_batch ran for this layer) */
 };
 /* which kernel family served the last forward on this thread (gf_attn_last_path) */
 enum { GF_PATH_NONE = 0, GF_PATH_SIMT_FP32 = 1, GF_PATH_TCGEN05_TF32 = 2 };
@@ -125,6 +126,13 @@ int gf_attn_prologue(const gf_attn_desc* desc, const float* Y, const float* fold
 
 /* gf_attn_prologue with the load-side fusion: K' is additionally scaled by post->in_scale (post may be NULL). */
 int gf_attn_prologue_ex(const gf_attn_desc* desc, const float* Y, const float* folded, void* ws, const gf_attn_postop* post, void* stream);
+
+/* Stage I of n layers in ONE launch (same batch size): everything that depends on the latents only -- for a simplex layer
+ * what gf_attn_prologue_ex builds, for a duplex layer the pass-A query tables and V^T (then call gf_attn_duplex_fwd_ex with
+ * GF_FLAG_TABLES_READY).  The reference's G_synthesis calls transformer_layer once per layer with the same latents; the
+ * per-layer K/V dense layers it runs each time are batched here.  posts may be NULL, and so may any posts[i]. */
+int gf_attn_prologue_batch(int n, const gf_attn_desc* const* descs, const float* const* Y, const float* const* folded, void* const* ws,
+                           const gf_attn_postop* const* posts, void* stream);
 
 /* Stage T -- replaces the body of transformer_layer() + integrate() + att_norm() for simplex attention:
  * one read of X, one write of Xout (may alias X).  att (nullable) receives softmax probabilities [B,n,k].

@@ -107,15 +107,18 @@ def generator_forward(sd: Dict[str, torch.Tensor], z: torch.Tensor, *, resolutio
                 w = {n[len(pre) + 11:]: t for n, t in sd.items() if n.startswith(pre + ".attention.")}
                 x, att, _ = transformer_layer(x, y, w, integration=integration, norm=norm, duplex=duplex,
                                               num_heads=num_heads, use_pos=use_pos, return_att=return_att)
-                if return_features:
-                    feats.append(x)
                 if att is not None:
                     atts.append(att)
+                has_att = True
+            else:
+                has_att = False
             if noise_mode == "const":
                 x = x + sd[pre + ".noise_const"] * sd[pre + ".noise_strength"]
             elif noise_mode != "none":
                 raise ValueError("the oracle supports noise_mode 'const' or 'none' (random noise is not reproducible)")
             x = F.leaky_relu(x + sd[pre + ".bias"][None, :, None, None], 0.2) * SQRT2
+            if return_features and has_att:           # the layer's activation: attention -> noise -> bias -> leaky-ReLU
+                feats.append(x)
             del in_ch
         pre = f"synthesis.torgbs.{bi}"
         styles = _fc(w_glob, sd, pre + ".affine", D)

@@ -45,7 +45,7 @@ for res, C in layers:
             e1.record()
             torch.cuda.synchronize()
             t_call = e0.elapsed_time(e1) / iters
-            t_stage = sum(a.elapsed_time(b) for a, b, _ in am.STAGE_TIMER.records) / iters
+            t_stage = sum(a.elapsed_time(b) for a, b, *_ in am.STAGE_TIMER.records) / iters
             am.STAGE_TIMER = None
         path = gf._lib.last_path()
         gbs = nbytes / (t_stage * 1e-3) / 1e9
