@@ -52,7 +52,8 @@ def check_close(got, ref64, path, what="", tol_scale=1.0, e_ref=0.0):
     rel_rms = (err.pow(2).mean().sqrt() / ref64.pow(2).mean().sqrt().clamp_min(1e-30)).item()
     print(f"[parity] {what} path={path} max_abs={err.max().item():.3e} max_ratio={ratio:.3f} contract_ratio={contract_ratio:.3f} rel_rms={rel_rms:.3e}")
     _log_parity(dict(what=what, path=path, max_abs=err.max().item(), ratio=ratio, contract_ratio=contract_ratio, rel_rms=rel_rms,
-                     ref_absmax=ref64.abs().max().item(), numel=ref64.numel(), tol_scale=tol_scale))
+                     ref_absmax=ref64.abs().max().item(), numel=ref64.numel(), tol_scale=tol_scale,
+                     need_atol_rtol2e3=(err - 2e-3 * ref64.abs()).max().item(), need_atol_rtol1e4=(err - 1e-4 * ref64.abs()).max().item()))
     assert ratio <= 1.0, f"{what}: path={path} max |err|/bound = {ratio:.3f} (max_abs {err.max().item():.3e})"
     assert rel_rms <= rrms, f"{what}: path={path} rel_rms {rel_rms:.3e} > {rrms}"
 

@@ -59,7 +59,7 @@ def measured(log):
     for r in recs:
         s = summ.setdefault(r["path"], dict(n=0))
         s["n"] += 1
-        for key in ("contract_ratio", "ratio", "rel_rms", "max_abs"):
+        for key in ("contract_ratio", "ratio", "rel_rms", "max_abs", "need_atol_rtol2e3", "need_atol_rtol1e4"):
             if key in r:
                 if r[key] >= s.get("max_" + key, -1):
                     s["max_" + key] = r[key]
