@@ -1,18 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- images/sec of 256x256 GANsformer synthesis (BASELINE.json configs[1]) + attention roofline.
+"""bench.py -- images/sec of GANsformer synthesis (BASELINE.json configs, default configs[1]: 256x256, K=16, batch 32/GPU)
++ attention roofline.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1|2|3|5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-A "step" is one generator forward over one batch of synthetic latents (B = 32 per GPU; weak scaling: every rank
-runs its own slice of a globally seeded batch, no data-path collective -- SURVEY 8e).  Rank 0 prints ONE JSON line.
+A "step" is one generator forward over one batch of synthetic latents (weak scaling: every rank runs its own slice of a
+globally seeded batch, no data-path collective -- SURVEY 8e).  Rank 0 prints ONE JSON line.
 
-  value        images/s with latents resident in HBM (CUDA events, max over ranks)
-  e2e          images/s through the public ``Generator.run``-shaped call: pinned host latents -> H2D -> forward ->
-               D2H of the images, every step
-  roofline     the stage-T attention kernel (dominant kernel of the hot path): ALGORITHMIC bytes (read X once +
-               write X' once per layer) / CUDA-event time of those launches, vs MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline the CPU oracle (oracle/generator.py, fp32, all host threads) on a bounded sample, rank 0, N = 1 only
+  value            images/s with latents resident in HBM (CUDA events, max over ranks); value_fp32_convs: the same steps with
+                   fp32 (not TF32) cuDNN convolutions
+  e2e              images/s through the public ``Generator.run``-shaped call: pinned host latents -> H2D -> forward ->
+                   D2H of the images, every step
+  roofline         the WHOLE attention path of the step (batched stage I + every layer call): ALGORITHMIC bytes (read X once +
+                   write X' once per layer) / CUDA-event time, vs MEASURED_PEAKS.json hbm_gbs; stage_T = the
+                   dominant kernel alone; traffic = DRAM bytes of the largest stage-T launch parsed from the tracked
+                   profiles/r02/traffic_config<N>.csv (tools/traffic_capture.sh, ncu on the current build)
+  roofline_duplex  BASELINE's second named metric: the 12 duplex layer calls of configs[2] (K=32, batch 64), same formula
+  train_step       BASELINE configs[3]: G+D training step, data-parallel with the NCCL gradient all-reduce, at every N
+  cpu_baseline     the CPU oracle (oracle/generator.py, fp32, pinned thread count, median of 3) on a bounded sample, N = 1 only
 
 --impl reference times the reference arm: the reference's own implementation cannot be installed (no source in
 /root/reference, TensorFlow 1.14 unavailable -- DESIGN.md), so per the tier contract the arm is the CPU oracle port.
@@ -34,9 +40,26 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-RES, K_LATENTS, LATENT_SIZE, B_PER_GPU = 256, 16, 512, 32
+# BASELINE.json configs, numbered as in SURVEY.md 8d (config N = configs[N-1]).  The default (and the driver's) line is config 2.
+CONFIGS = {
+    1: dict(res=64, k=8, batch=4, duplex=False, layers=8, label="BASELINE configs[0]: GANsformer generator forward, 64x64, K=8 latents, batch 4 (the reference's CPU-runnable case)"),
+    2: dict(res=256, k=16, batch=32, duplex=False, layers=12, label="BASELINE configs[1]: 256x256 synthesis, K=16 latents, 12 attention layers, batch 32 per GPU, simplex"),
+    3: dict(res=256, k=32, batch=64, duplex=True, layers=12, label="BASELINE configs[2]: 256x256 duplex-attention variant, K=32 latents, batch 64 per GPU"),
+    5: dict(res=512, k=32, batch=16, duplex=False, layers=14, label="BASELINE configs[4]: 512x512 synthesis, K=32 latents, batch 16 per GPU (128 over 8 GPUs), 14 attention layers"),
+}
+RES, K_LATENTS, LATENT_DIM, B_PER_GPU, DUPLEX = 256, 16, 32, 32, False
 METRIC = "images/sec @256^2 synth (GANsformer generator forward, K=16 latents, 12 attention layers, batch 32/GPU)"
 UNIT = "images/s"
+CPU_THREADS_CAP = 32          # MKL-DNN convolutions collapse beyond ~32 threads on the 64/128-thread hosts of this pool
+
+
+def select_config(n: int):
+    global RES, K_LATENTS, B_PER_GPU, DUPLEX, METRIC
+    c = CONFIGS[n]
+    RES, K_LATENTS, B_PER_GPU, DUPLEX = c["res"], c["k"], c["batch"], c["duplex"]
+    METRIC = (f"images/sec @{RES}^2 synth (GANsformer generator forward, K={K_LATENTS} latents, {c['layers']} attention layers, "
+              f"batch {B_PER_GPU}/GPU{', duplex' if DUPLEX else ''})")
+    return c
 
 
 def measured_peak_gbs():
@@ -94,46 +117,31 @@ class ClockSampler:
 def build_generator(device):
     import gansformer_b200 as gf
     torch.manual_seed(0)                                   # weights seed 0, N(0,1), biases 0
-    G = gf.Generator(resolution=RES, components_num=K_LATENTS, latent_size=LATENT_SIZE)
+    G = gf.Generator(resolution=RES, components_num=K_LATENTS, latent_dim=LATENT_DIM, kmeans=DUPLEX)
     return G.to(device).eval()
 
 
 def global_latents(world: int):
     g = torch.Generator().manual_seed(1)                   # latents seed 1, generated on CPU
-    return torch.randn(B_PER_GPU * world, K_LATENTS + 1, LATENT_SIZE // K_LATENTS, generator=g)
+    return torch.randn(B_PER_GPU * world, K_LATENTS + 1, LATENT_DIM, generator=g)
 
 
-def pick_cpu_threads() -> int:
-    """MKL-DNN convolutions stop scaling (and can collapse) well below the core count of a 128-core host: time one
-    representative grouped convolution at a few thread counts and keep the fastest."""
-    import torch.nn.functional as F
-    cores = os.cpu_count() or 1
-    cands = sorted({c for c in (cores, 64, 32, 16, 8) if c <= cores}, reverse=True)
-    x = torch.randn(1, 2 * 128, 128, 128)
-    w = torch.randn(2 * 128, 128, 3, 3)
-    best, best_t = cands[-1], float("inf")
-    for c in cands:
-        torch.set_num_threads(c)
-        F.conv2d(x, w, padding=1, groups=2)
-        t0 = time.perf_counter()
-        F.conv2d(x, w, padding=1, groups=2)
-        t = time.perf_counter() - t0
-        if t < best_t:
-            best, best_t = c, t
-    return best
+def cpu_threads() -> int:
+    """Thread count of the CPU arm: pinned (no per-run search -- the r01 picker made the same work move 0.9 -> 1.7 img/s)."""
+    return max(1, min(os.cpu_count() or 1, CPU_THREADS_CAP))
 
 
-def cpu_oracle_run(G_state, steps: int, warmup: int, sample_b: int):
-    """Times the CPU oracle generator (fp32, NCHW, direct op order) on `sample_b` images per step."""
+def cpu_oracle_run(G_state, steps: int, warmup: int, sample_b: int, duplex: bool = None):
+    """Times the CPU oracle generator (fp32, NCHW, direct op order) on `sample_b` images per step: median of `steps` (>= 3)."""
     from oracle import generator as og
-    threads = pick_cpu_threads()
+    threads = cpu_threads()
     torch.set_num_threads(threads)
     z = global_latents(1)[:sample_b]
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        og.generator_forward(G_state, z, resolution=RES, components_num=K_LATENTS, latent_dim=LATENT_SIZE // K_LATENTS,
-                             dtype=torch.float32)
+        og.generator_forward(G_state, z, resolution=RES, components_num=K_LATENTS, latent_dim=LATENT_DIM,
+                             duplex=DUPLEX if duplex is None else duplex, dtype=torch.float32)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     t = statistics.median(times)
@@ -189,7 +197,7 @@ def duplex_generator_probe(device, steps: int = 5, warmup: int = 2, B: int = 64,
     CUDA-graph replay with the latents resident; next to the CPU oracle on a 2-image sample of the same network."""
     import gansformer_b200 as gf
     torch.manual_seed(0)
-    G = gf.Generator(resolution=RES, components_num=k, latent_dim=32, kmeans=True).to(device).eval()
+    G = gf.Generator(resolution=256, components_num=k, latent_dim=32, kmeans=True).to(device).eval()
     g = torch.Generator().manual_seed(1)
     z = torch.randn(B, k + 1, 32, generator=g).to(device)
     with torch.no_grad():
@@ -213,12 +221,14 @@ def duplex_generator_probe(device, steps: int = 5, warmup: int = 2, B: int = 64,
         from oracle import generator as og
         sd = {n: v.detach().cpu() for n, v in G.state_dict().items()}
         zc = z[:2].cpu()
-        torch.set_num_threads(pick_cpu_threads())
-        t0 = time.perf_counter()
-        og.generator_forward(sd, zc, resolution=RES, components_num=k, latent_dim=32, duplex=True, dtype=torch.float32)
-        dt = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": 2 / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                               "sample": "1 step x 2 images of the same duplex generator, oracle/generator.py fp32"}
+        torch.set_num_threads(cpu_threads())
+        dts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            og.generator_forward(sd, zc, resolution=256, components_num=k, latent_dim=32, duplex=True, dtype=torch.float32)
+            dts.append(time.perf_counter() - t0)
+        out["cpu_baseline"] = {"value": 2 / statistics.median(dts), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": "median of 3 steps x 2 images of the same duplex generator, oracle/generator.py fp32"}
     del replay, G
     torch.cuda.empty_cache()
     return out
@@ -233,12 +243,13 @@ def train_probe(device, rank, world, steps: int = 3, warmup: int = 1, B: int = 3
     tr = import_module("gansformer-reproducibility-challenge_b200.training")
     dist_mod = import_module("gansformer-reproducibility-challenge_b200.dist")
     torch.manual_seed(0)
-    G = gf.Generator(resolution=RES, components_num=K_LATENTS, latent_size=512).to(device)
-    D = tr.Discriminator(RES).to(device)
+    TR_RES, TR_K = 256, 16                           # configs[3] is quoted on the 256x256 K=16 simplex network
+    G = gf.Generator(resolution=TR_RES, components_num=TR_K, latent_dim=LATENT_DIM).to(device)
+    D = tr.Discriminator(TR_RES).to(device)
     trainer = tr.Trainer(G, D, world=world)
     g = torch.Generator().manual_seed(4)
-    z = dist_mod.shard_batch(torch.randn(world * B, K_LATENTS + 1, G.latent_dim, generator=g), rank, world).to(device)
-    reals = dist_mod.shard_batch(torch.rand(world * B, 3, RES, RES, generator=g) * 2 - 1, rank, world).to(device)
+    z = dist_mod.shard_batch(torch.randn(world * B, TR_K + 1, G.latent_dim, generator=g), rank, world).to(device)
+    reals = dist_mod.shard_batch(torch.rand(world * B, 3, TR_RES, TR_RES, generator=g) * 2 - 1, rank, world).to(device)
     do_step = trainer.step_graphed if graphed else trainer.step
     trainer.it = 1                                   # timed steps are the common case (no lazy R1 term: 15 of 16 steps)
     for _ in range(warmup):
@@ -283,24 +294,57 @@ def train_probe(device, rank, world, steps: int = 3, warmup: int = 1, B: int = 3
 
 
 def run_reference(args):
+    """The reference arm: the reference's own implementation cannot be installed or run (no source under /root/reference,
+    TensorFlow 1.14 unavailable), so per the tier contract this times the CPU oracle port on the host cores: pinned thread
+    count, median of >= 3 steps of a bounded sample (2 images per step; config 1: its exact batch of 4)."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return 0
+    cfg = select_config(args.config)
     torch.manual_seed(0)
     import gansformer_b200 as gf
-    G = gf.Generator(resolution=RES, components_num=K_LATENTS, latent_size=LATENT_SIZE)
-    sample_b = 2
-    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    G = gf.Generator(resolution=RES, components_num=K_LATENTS, latent_dim=LATENT_DIM, kmeans=DUPLEX)
+    sample_b = B_PER_GPU if args.config == 1 else (1 if RES >= 512 else 2)
+    steps, warmup = max(3, min(args.steps, 5)), 1
     ips, t, cores = cpu_oracle_run(G.state_dict(), steps, warmup, sample_b)
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: 256x256 synthesis, K=16 latents, 12 attention layers", "batch_per_step": sample_b,
-                       "note": "reference source absent from /root/reference and TF1.14 unavailable: CPU oracle port (parity unpinned)"},
+            "config": {"workload": cfg["label"], "batch_per_step": sample_b,
+                       "note": "reference source absent from /root/reference and TF1.14 unavailable: CPU oracle port (parity unpinned); "
+                               f"{cores} pinned threads, median of {steps} steps"},
             "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{sample_b} images/step x {steps} steps of the config-2 generator forward (oracle/generator.py, fp32)"},
+                             "sample": f"median of {steps} steps x {sample_b} images of the same generator forward (oracle/generator.py, fp32)"},
             "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
     return 0
+
+
+def parse_traffic(config_n: int):
+    """roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch, read from the TRACKED csv that
+    tools/traffic_capture.sh produced with ncu on the current build (profiles/r02/traffic_config<N>.csv); None if absent."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r02", f"traffic_config{config_n}.csv")
+    if not os.path.exists(path):
+        return None, None
+    best = None
+    try:
+        with open(path) as f:
+            rows = list(csv.DictReader(l for l in f if not l.startswith("==")))
+        per = {}
+        for r in rows:
+            if not r["Metric Name"].startswith("dram__bytes"):
+                continue
+            v = float(r["Metric Value"].replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[r["Metric Unit"]]
+            e = per.setdefault(r["ID"], {"name": r["Kernel Name"], "bytes": 0.0})
+            e["bytes"] += v
+        for e in per.values():
+            if ("token_tc_kernel" in e["name"] or "token_simt" in e["name"]) and (best is None or e["bytes"] > best["bytes"]):
+                best = e
+    except Exception:
+        return None, None
+    if best is None:
+        return None, None
+    return best["bytes"], f"profiles/r02/traffic_config{config_n}.csv ({best['name'][:60]}: largest stage-T launch of one eager step)"
 
 
 def run_ours(args):
@@ -310,12 +354,14 @@ def run_ours(args):
     attn_mod = import_module("gansformer-reproducibility-challenge_b200.attention")
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py --impl ours needs a CUDA device: the product has no CPU path")
+    cfg = select_config(args.config)
     rank, world, local = dist_mod.init_distributed("nccl")
     if world != args.gpus:
         raise RuntimeError(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
-    # surrounding cuDNN convolutions (plumbing, SURVEY row f1 is "next"): TF32 tensor-core math, fp32 storage
+    # surrounding cuDNN convolutions (plumbing, SURVEY row f1 is "next"): TF32 tensor-core math, fp32 storage; the same steps are
+    # also timed with true-fp32 convolutions (value_fp32_convs) -- the reference's precision for them
     torch.backends.cudnn.allow_tf32 = True
     torch.backends.cuda.matmul.allow_tf32 = True
     torch.backends.cudnn.benchmark = True
@@ -345,7 +391,7 @@ def run_ours(args):
     # the public Gs.run-shaped call: host latents in, host images out.  ONE call over steps x B latents with minibatch B: every
     # step (= minibatch) copies its latents host->device and its images device->host inside the timed region; run() overlaps
     # the device->host copy of a minibatch with the next minibatch's compute.
-    e2e_chunk = min(args.steps, 10)                  # minibatches per run() call (bounds the pinned host buffers: 25 MB each)
+    e2e_chunk = min(args.steps, 10)                  # minibatches per run() call (bounds the pinned host buffers)
     z_host_all = z_host.repeat(e2e_chunk, 1, 1).pin_memory()
     img_host_all = torch.empty((e2e_chunk * B, 3, RES, RES), dtype=torch.float32).pin_memory()
 
@@ -357,8 +403,9 @@ def run_ours(args):
         step_e2e()
     torch.cuda.synchronize()
 
-    # ---- attention-kernel timing (eager: CUDA events around each stage-T launch cannot live inside a graph replay;
-    #      the kernels and their inputs are the same ones the graph replays) ---------------------------------------
+    # ---- attention timing (eager: CUDA events around the launches cannot live inside a graph replay; the kernels and their
+    #      inputs are the same ones the graph replays).  Whole attention = the batched stage-I launch of the step + every
+    #      layer call (pass A + key products for duplex, stage T); stage T alone is reported next to it. -------------------
     attn_mod.STAGE_TIMER = timer
     timer.reset()
     launches0 = gf._lib.launch_count()
@@ -386,9 +433,10 @@ def run_ours(args):
     dist_mod.barrier()
     clocks = sampler.stop() if rank == 0 else None
     t_total = dist_mod.max_over_ranks(ev0.elapsed_time(ev1) * 1e-3, device)
-    attn_s = sum(a.elapsed_time(b) for a, b, _ in timer.records) * 1e-3
-    attn_bytes = sum(nb for _, _, nb in timer.records)
-    n_attn_launches = len(timer.records)
+    stage_t_s = sum(r[0].elapsed_time(r[1]) for r in timer.records) * 1e-3
+    call_s = sum(r[3].elapsed_time(r[1]) for r in timer.records) * 1e-3 + sum(a.elapsed_time(b) for a, b in timer.batch_records) * 1e-3
+    attn_bytes = sum(r[2] for r in timer.records)
+    n_attn_calls = len(timer.records)
     path = gf._lib.last_path()
 
     # ---- timed region 2: end to end through the public call (H2D + forward + D2H every step) -----------------
@@ -406,62 +454,114 @@ def run_ours(args):
     dist_mod.barrier()
     t_e2e = dist_mod.max_over_ranks(e0.elapsed_time(e1) * 1e-3, device)
 
+    # ---- the same resident steps with true-fp32 cuDNN convolutions (the reference's convolution precision) ----
+    t_fp32 = None
+    if not args.no_fp32_convs:
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        with torch.no_grad():
+            G(z_dev)
+        replay32 = G.graphed(B) if use_graph else None          # graph key includes the TF32 switches: a new capture
+        n32 = max(3, min(args.steps, 10))
+        for _ in range(2):
+            replay32(z_dev) if replay32 is not None else step_eager()
+        dist_mod.barrier()
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(n32):
+            replay32(z_dev) if replay32 is not None else step_eager()
+        f1.record()
+        torch.cuda.synchronize()
+        dist_mod.barrier()
+        t_fp32 = dist_mod.max_over_ranks(f0.elapsed_time(f1) * 1e-3, device) / n32
+        torch.backends.cudnn.allow_tf32 = True
+        torch.backends.cuda.matmul.allow_tf32 = True
+        del replay32
+
+    # ---- BASELINE configs[3]: the training step (the only collective of the system: the gradient all-reduce).  Runs at every N
+    #      (SCALE carries it); a watchdog prints the headline line without it if a rank hangs inside the probe.
     tp = None
-    # default on for a single GPU; under torchrun only on request (--train-probe): a rank failing inside the probe's collectives
-    # would leave the others waiting and cost the headline line
-    if not args.no_train_probe and (world == 1 or args.train_probe):
-        try:
-            tp = train_probe(device, rank, world, graphed=not args.no_cuda_graph)
-        except Exception as exc:                     # the probe must never take the headline line down with it
-            tp = {"error": f"{type(exc).__name__}: {exc}"[:300]}      # every rank takes part (gradient all-reduce)
-    if rank != 0:
-        return 0
-    peak, peak_src = measured_peak_gbs()
-    achieved = attn_bytes / attn_s / 1e9 if attn_s > 0 else 0.0
-    line = {
-        "metric": METRIC, "value": world * B * args.steps / t_total, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": t_total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "tf32 (fp32 storage; tcgen05 kind::tf32 attention, TF32 cuDNN convs)" if path == "tcgen05_tf32" else "f32 (CUDA-core attention; TF32 cuDNN convs)",
-        "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: 256x256 synthesis, K=16 latents, 12 attention layers, batch 32 per GPU, simplex, "
-                               "integration=mul, norm=layer, random-init weights (seed 0), latents seed 1",
-                   "global_batch": world * B, "parallelism": f"dp{world} (images sharded, no data-path collective)",
-                   "l2_policy": "activations per layer (up to 1.07 GB) exceed the 126 MB L2; no flush needed",
-                   "attention_path": path, "cuda_graph": bool(use_graph)},
-        "gpu_launches": int(launches) * args.steps,
-        "e2e": {"value": world * B * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(z_host.numel() * 4 * world),
-                "d2h_bytes_per_step": int(img_host.numel() * 4 * world), "ms_per_step": t_e2e / args.steps * 1e3,
-                "call": "Generator.run(latents[m*B], minibatch_size=B, cuda_graph=True, out=pinned) over the K steps in calls of m <= 10 minibatches; per minibatch: H2D latents, "
-                        "graph replay, D2H images on a copy stream overlapping the next minibatch"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": 2.106e9, "traffic_launch": "res-256 layer (B=32, C=128): dram__bytes_read 1.082 GB + dram__bytes_write 1.024 GB "
-                                                        "vs 2.147 GB algorithmic for that launch; tensor pipe 2.9 % of peak, 121 registers "
-                                                        "(profiles/r01/ncu_full_token_tc_v9_res256_postop.ncu-rep, ncu --set full)",
-                     "peak_source": peak_src, "kernel": f"stage-T attention ({path})",
-                     "launches_timed": n_attn_launches, "alg_bytes_per_step": attn_bytes // max(args.steps, 1),
-                     "attention_ms_per_step": attn_s / args.steps * 1e3,
-                     "attention_share_of_step": attn_s / (ev0.elapsed_time(ev1) * 1e-3),
-                     "note": "attention launches timed in an eager pass of the same K steps; the step itself replays a CUDA graph. "
-                             "Inside the generator each launch also carries the fused demodulation scale, noise, bias, leaky-ReLU and "
-                             "next-layer style scale (SURVEY row f3), which are not counted in the algorithmic bytes"},
-        "clocks": clocks,
-    }
-    if tp is not None:
-        line["train_step"] = tp
-    if world == 1 and not args.no_duplex_probe:
+    want_train = (not args.no_train_probe) and args.config == 2
+    state = {"line": None}
+
+    def finish(tp_obj):
+        if rank != 0:
+            return
+        line = state["line"]
+        if tp_obj is not None:
+            line["train_step"] = tp_obj
+        print(json.dumps(line), flush=True)
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        achieved = attn_bytes / call_s / 1e9 if call_s > 0 else 0.0
+        achieved_t = attn_bytes / stage_t_s / 1e9 if stage_t_s > 0 else 0.0
+        traffic, traffic_src = parse_traffic(args.config)
+        line = {
+            "metric": METRIC, "value": world * B * args.steps / t_total, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "tf32 (fp32 storage; tcgen05 kind::tf32 attention, TF32 cuDNN convs; value_fp32_convs = the same with fp32 convs)" if path == "tcgen05_tf32" else "f32 (CUDA-core attention; TF32 cuDNN convs)",
+            "data": "synthetic",
+            "config": {"workload": cfg["label"] + ", integration=mul, norm=layer, random-init weights (seed 0), latents seed 1",
+                       "global_batch": world * B, "parallelism": f"dp{world} (images sharded, no data-path collective)",
+                       "l2_policy": "activations per layer (up to 1.07 GB) exceed the 126 MB L2; no flush needed",
+                       "attention_path": path, "cuda_graph": bool(use_graph)},
+            "gpu_launches": int(launches) * args.steps,
+            "e2e": {"value": world * B * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(z_host.numel() * 4 * world),
+                    "d2h_bytes_per_step": int(img_host.numel() * 4 * world), "ms_per_step": t_e2e / args.steps * 1e3,
+                    "call": "Generator.run(latents[m*B], minibatch_size=B, cuda_graph=True, out=pinned) over the K steps in calls of m <= 10 minibatches; per minibatch: H2D latents, "
+                            "graph replay, D2H images on a copy stream overlapping the next minibatch"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src,
+                         "kernel": f"whole attention path of the step: stage I (one batched launch) + {'pass A + key products + ' if DUPLEX else ''}stage T ({path})",
+                         "calls_timed": n_attn_calls, "alg_bytes_per_step": attn_bytes // max(args.steps, 1),
+                         "attention_ms_per_step": call_s / args.steps * 1e3,
+                         "attention_share_of_step": call_s / (ev0.elapsed_time(ev1) * 1e-3),
+                         "stage_T": {"achieved": achieved_t, "frac": achieved_t / peak, "ms_per_step": stage_t_s / args.steps * 1e3,
+                                     "note": "the dominant kernel alone (token_tc_kernel launches of the step)"},
+                         "note": "timed in an eager pass of the same K steps (CUDA events on the launch stream); the step itself replays a "
+                                 "CUDA graph. Each stage-T launch also carries the fused demodulation scale, noise, bias, leaky-ReLU and "
+                                 "next-layer style scale (SURVEY row f3), which are not counted in the algorithmic bytes"},
+            "clocks": clocks,
+        }
+        if t_fp32 is not None:
+            line["value_fp32_convs"] = {"value": world * B / t_fp32, "unit": UNIT, "ms_per_step": t_fp32 * 1e3,
+                                        "note": "same step, torch.backends.cudnn.allow_tf32 = False (fp32 cuDNN convolutions); attention unchanged"}
+        state["line"] = line
+    if world == 1 and not args.no_duplex_probe and args.config == 2:
+        peak, _ = measured_peak_gbs()
         for key, fn in (("duplex_attention", lambda: duplex_attention_probe(device, peak)),
                         ("duplex_generator", lambda: duplex_generator_probe(device, with_cpu=not args.no_cpu_baseline))):
             try:
-                line[key] = fn()
+                state["line"][key] = fn()
             except Exception as exc:
-                line[key] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+                state["line"][key] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        da = state["line"].get("duplex_attention", {})
+        if "frac" in da:      # BASELINE's second named metric ("duplex-attn %HBM-peak") in roofline form
+            state["line"]["roofline_duplex"] = {"bound": "hbm", "achieved": da["achieved"], "peak": peak, "unit": "GB/s", "frac": da["frac"],
+                                                "traffic": None, "kernel": "12 duplex layer calls of configs[2] (stage I + pass A + key products + stage T)"}
     if world == 1 and not args.no_cpu_baseline:
-        ips, t, cores = cpu_oracle_run(G.state_dict(), steps=2, warmup=1, sample_b=2)
-        line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "2 images/step x 2 steps (+1 warm-up) of the same 256x256 K=16 generator forward, "
-                                          "oracle/generator.py fp32 on all host threads; oracle = in-repo restatement, "
-                                          "reference source unavailable, parity unpinned"}
-    print(json.dumps(line), flush=True)
+        ips, t, cores = cpu_oracle_run(G.state_dict(), steps=3, warmup=1, sample_b=B_PER_GPU if args.config == 1 else (1 if RES >= 512 else 2))
+        state["line"]["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
+                                         "sample": f"median of 3 steps (+1 warm-up) x {B_PER_GPU if args.config == 1 else (1 if RES >= 512 else 2)} images of the same generator forward, "
+                                                   f"oracle/generator.py fp32 on {cores} pinned host threads; oracle = in-repo restatement, "
+                                                   "reference source unavailable, parity unpinned"}
+    if want_train:
+        done_evt = threading.Event()
+
+        def watchdog():
+            if not done_evt.wait(args.train_timeout):
+                finish({"error": f"training probe did not finish within {args.train_timeout} s (rank {rank}); headline line printed without it"})
+                os._exit(0)
+        threading.Thread(target=watchdog, daemon=True).start()
+        try:
+            tp = train_probe(device, rank, world, graphed=not args.no_cuda_graph)
+        except Exception as exc:                     # the probe must never take the headline line down with it
+            tp = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        done_evt.set()
+    finish(tp)
     return 0
 
 
@@ -471,11 +571,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS),
+                    help="BASELINE.json config (SURVEY 8d numbering): 1 = 64^2 K=8 B=4, 2 = 256^2 K=16 B=32 (default, the driver's line), "
+                         "3 = 256^2 duplex K=32 B=64, 5 = 512^2 K=32 B=16/GPU; config 4 (training step) is the train_step object of config 2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true")
     ap.add_argument("--no-duplex-probe", action="store_true")
+    ap.add_argument("--no-fp32-convs", action="store_true", help="skip the value_fp32_convs variant")
     ap.add_argument("--no-train-probe", action="store_true", help="skip the BASELINE configs[3] probe (G+D training step, train_step object)")
-    ap.add_argument("--train-probe", action="store_true", help="run the training-step probe also under torchrun (N > 1); default on for N = 1")
+    ap.add_argument("--train-probe", action="store_true", help="(kept for compatibility: the probe now runs at every N by default)")
+    ap.add_argument("--train-timeout", type=float, default=240.0, help="watchdog of the training probe in seconds")
     args = ap.parse_args()
     if args.impl == "ours":
         args.warmup = max(args.warmup, 3)

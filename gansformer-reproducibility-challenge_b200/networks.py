@@ -409,7 +409,7 @@ class Generator(nn.Module):
         The returned image tensor is a static buffer overwritten by the next replay.  Weight-derived tensors (folded
         attention weights, scaled conv weights) are baked at capture, so the graph is keyed on the parameters' storage,
         version counters and the process-wide weights epoch: any weight update re-captures."""
-        key = (batch_size, float(truncation_psi), noise_mode, weights_epoch(),
+        key = (batch_size, float(truncation_psi), noise_mode, weights_epoch(), bool(torch.backends.cudnn.allow_tf32),
                tuple((p.data_ptr(), p._version) for p in self.parameters()))
         cache = self.__dict__.setdefault("_graphs", {})
         if key in cache:

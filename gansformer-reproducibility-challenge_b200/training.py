@@ -105,6 +105,7 @@ class TrainConfig:
     d_reg_interval: int = 16            # lazy R1: every 16th discriminator step
     ema_kimg: float = 10.0
     noise_mode: str = "random"
+    bucket_mb: float = 32.0             # gradient all-reduce bucket size (MB of fp32 gradients)
     w_avg_beta: float = 0.995           # decay of the running mean of the mapping outputs (truncation trick)
 
 
@@ -129,19 +130,19 @@ class Trainer:
         self.opt_g = torch.optim.Adam(G.parameters(), lr=self.cfg.lr, betas=(0.0, 0.99), eps=1e-8, capturable=cap)
         self.opt_d = torch.optim.Adam(D.parameters(), lr=self.cfg.lr * c, betas=(0.0 ** c, 0.99 ** c), eps=1e-8, capturable=cap)
         self.it = 0
+        # data parallel: gradients live in one flat buffer per network, reduced bucket by bucket while backward still runs
+        self.buckets_g = gdist.GradBuckets(G.parameters(), world, self.cfg.bucket_mb) if world > 1 else None
+        self.buckets_d = gdist.GradBuckets(D.parameters(), world, self.cfg.bucket_mb) if world > 1 else None
 
-    def _allreduce(self, module: nn.Module, stats: StepStats):
-        if self.world <= 1:
-            return
-        dev = next(module.parameters()).device
-        if dev.type == "cuda" and not torch.cuda.is_current_stream_capturing():
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            stats.allreduce_bytes += gdist.allreduce_gradients(module.parameters(), self.world)
-            e1.record()
-            stats.extra.setdefault("_events", []).append((e0, e1))
+    def _zero(self, opt, buckets):
+        if buckets is not None:
+            buckets.begin()                # one memset of the flat buffer; the .grad views stay attached
         else:
-            stats.allreduce_bytes += gdist.allreduce_gradients(module.parameters(), self.world)
+            opt.zero_grad(set_to_none=True)
+
+    def _allreduce(self, buckets, stats: StepStats):
+        if buckets is not None:
+            stats.allreduce_bytes += buckets.finish()      # joins the communication stream (the buckets overlapped backward)
 
     def _step_tensors(self, z: torch.Tensor, reals: torch.Tensor, do_r1: bool, stats: Optional[StepStats] = None):
         """One D update + one G update; returns (loss_d, loss_g, r1) as device tensors without synchronising (capturable)."""
@@ -149,7 +150,7 @@ class Trainer:
         stats = stats if stats is not None else StepStats()
         # ---- discriminator: logistic loss (+ lazy R1 on the reals)
         G.requires_grad_(False); D.requires_grad_(True)
-        self.opt_d.zero_grad(set_to_none=True)
+        self._zero(self.opt_d, self.buckets_d)
         with torch.no_grad():
             fakes = G(z, noise_mode=cfg.noise_mode)
         reals_in = reals.detach().requires_grad_(do_r1)
@@ -161,14 +162,14 @@ class Trainer:
             r1 = grad.square().sum(dim=[1, 2, 3]).mean()
             loss_d = loss_d + r1 * (cfg.r1_gamma * 0.5 * cfg.d_reg_interval)
         loss_d.backward()
-        self._allreduce(D, stats)
+        self._allreduce(self.buckets_d, stats)
         self.opt_d.step()
         # ---- generator: non-saturating logistic loss
         G.requires_grad_(True); D.requires_grad_(False)
-        self.opt_g.zero_grad(set_to_none=True)
+        self._zero(self.opt_g, self.buckets_g)
         loss_g = F.softplus(-D(G(z, noise_mode=cfg.noise_mode))).mean()
         loss_g.backward()
-        self._allreduce(G, stats)
+        self._allreduce(self.buckets_g, stats)
         self.opt_g.step()
         # ---- moving average of the generator (and of the mapping outputs: the truncation trick's w_avg)
         with torch.no_grad():
@@ -190,9 +191,6 @@ class Trainer:
         loss_d, loss_g, r1 = self._step_tensors(z, reals, do_r1, stats)
         stats.loss_d, stats.loss_g, stats.r1 = float(loss_d), float(loss_g), float(r1)
         bump_weights_epoch()
-        for e0, e1 in stats.extra.pop("_events", []):
-            e1.synchronize()
-            stats.allreduce_ms += e0.elapsed_time(e1)
         self.it += 1
         return stats
 

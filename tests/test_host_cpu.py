@@ -176,6 +176,55 @@ def test_data_parallel_helpers_world2():
         assert nbytes == (6 + 2) * 4 and mx == 2.0
 
 
+def _bucket_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import gansformer_b200  # noqa: F401
+    from importlib import import_module
+    d = import_module("gansformer-reproducibility-challenge_b200.dist")
+    r, w, _ = d.init_distributed("gloo")
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 32), torch.nn.Tanh(), torch.nn.Linear(32, 16), torch.nn.Tanh(), torch.nn.Linear(16, 1))
+    unused = torch.nn.Parameter(torch.ones(5))                      # a parameter that never receives a gradient
+    params = list(net.parameters()) + [unused]
+    buckets = d.GradBuckets(params, w, bucket_mb=0.0005)            # ~130 floats per bucket: several buckets
+    x = torch.randn(8, 6, generator=torch.Generator().manual_seed(2))
+    outs = []
+    for step in range(2):                                           # second step: the views survive, the buffer is re-zeroed
+        buckets.begin()
+        net(d.shard_batch(x, r, w)).square().mean().backward()
+        nbytes = buckets.finish()
+        outs.append(torch.cat([p.grad.reshape(-1) for p in params]).clone())
+    inside = all(p.grad.data_ptr() >= buckets.flat.data_ptr() and p.grad.data_ptr() < buckets.flat.data_ptr() + buckets.flat.numel() * 4 for p in params)
+    q.put((r, outs[0].numpy(), outs[1].numpy(), nbytes, len(buckets.buckets), inside))
+    d.barrier()
+    dist.destroy_process_group()
+
+
+def test_grad_buckets_world2_equal_full_batch_gradients():
+    """GradBuckets (flat gradient buffer, reverse-order buckets reduced from post-accumulate hooks): the averaged gradients of
+    two ranks on disjoint shards equal the single-process gradients of the full batch; parameters without a gradient stay 0."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 32), torch.nn.Tanh(), torch.nn.Linear(32, 16), torch.nn.Tanh(), torch.nn.Linear(16, 1))
+    x = torch.randn(8, 6, generator=torch.Generator().manual_seed(2))
+    net(x).square().mean().backward()                                # shards of 4 + 4: mean of the shard means == full mean
+    want = torch.cat([p.grad.reshape(-1) for p in net.parameters()] + [torch.zeros(5)])
+    for r, g1, g2, nbytes, nb, inside in res:
+        assert inside and nb >= 2
+        assert nbytes == want.numel() * 4
+        assert torch.allclose(torch.from_numpy(g1), want, atol=1e-6) and torch.allclose(torch.from_numpy(g2), want, atol=1e-6)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # G/D training step (SURVEY row f2): plumbing on CPU without attention layers (the attention op has no CPU form)
 # ---------------------------------------------------------------------------------------------------------
