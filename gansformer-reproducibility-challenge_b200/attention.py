@@ -118,6 +118,15 @@ def _make_postop(postop: Optional[dict], B: int, H: int, W: int, C: int, dev):
         keep.append(t)
         setattr(pst, fld, t.data_ptr())
         setattr(pst, fld + "_ld", t.stride(0))
+    if postop.get("rgb_out") is not None:      # fused tRGB: per-sample weights [B,3,C] in, planar image [B,3,H,W] out
+        rw, ro, rb = postop.get("rgb_w"), postop["rgb_out"], postop.get("rgb_bias")
+        if rw is None or tuple(rw.shape) != (B, 3, C) or tuple(ro.shape) != (B, 3, H, W):
+            raise ValueError("postop.rgb_w must be [B, 3, C] and postop.rgb_out [B, 3, H, W]")
+        for name, t in (("rgb_w", rw), ("rgb_out", ro)) + ((("rgb_bias", rb),) if rb is not None else ()):
+            _check_tensor(t.detach(), "postop." + name, dev)
+            keep.append(t)
+        pst.rgb_w, pst.rgb_out = rw.data_ptr(), ro.data_ptr()
+        pst.rgb_bias = rb.detach().data_ptr() if rb is not None else None
     return pst, keep
 
 
@@ -165,9 +174,9 @@ def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[s
     """x [B,H,W,C] channels-last fp32 (CUDA), y [B,k,D].  Returns (x', att [B,k,H,W] | None, centroids | None).
 
     postop (optional): dict(bias [C] | None, noise [H*W] or [B,H*W] | None, strength 0-d tensor | None, act 'lrelu' |
-    'linear', gain float, in_scale [B,C] | None, post_scale [B,C] | None) -- the demodulation scale of the preceding
-    convolution (load side) and the noise + fused_bias_act step + next-layer style scale (store side), fused into the
-    kernel.
+    'linear', gain float, in_scale [B,C] | None, post_scale [B,C] | None, rgb_w [B,3,C] + rgb_out [B,3,H,W] (+ rgb_bias [3]))
+    -- the demodulation scale of the preceding convolution (load side) and the noise + fused_bias_act step + next-layer style
+    scale (store side), fused into the kernel; with rgb_* also the tRGB 1x1 modulated convolution of the layer output.
 
     stage: "all" | "prologue" | "token".  "prologue" runs stages W + I for a layer whose activations do not exist yet (x may
     be None, give x_shape; postop needs only in_scale) -- they depend on the latents alone (see ``prologue_batch`` for all
@@ -240,6 +249,18 @@ def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[s
         del keep
     att_map = att.view(B, H, W, k).permute(0, 3, 1, 2) if att is not None else None   # [B,k,H,W] view
     return out, att_map, cen
+
+
+def tc_eligible(module: "BipartiteAttention", shape, k: int) -> bool:
+    """Will stage T of this layer call run on the tcgen05 kernel (gf_attn_tc_eligible)?  Decides fusions only that kernel serves."""
+    B, H, W, C = shape
+    desc = _lib.make_desc(B, H, W, C, k, module.latent_dim, heads=module.num_heads, norm=module.norm, integration=module.integration,
+                          pos_dim=module.pos_dim if module.use_pos else 0, duplex=module.duplex,
+                          flags=_lib.FLAG_FP32_EXACT if module.exact_fp32 else 0)
+    rc = _lib.load().gf_attn_tc_eligible(ctypes.byref(desc))
+    if rc < 0:
+        _lib.check(rc, "gf_attn_tc_eligible")
+    return rc == 1
 
 
 @torch.no_grad()

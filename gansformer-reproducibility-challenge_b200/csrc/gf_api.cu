@@ -51,7 +51,12 @@ static int token_pass(const Layout& L, const gf_attn_desc* d, const float* X, fl
     }
   }
   if ((rc = norm_stats(L, d, X, ws, st))) return rc;
-  if (!(d->flags & GF_FLAG_FP32_EXACT) && tc_supported(L, d)) return token_pass_tc(L, d, X, Xout, att, ws, post, st);
+  const bool tc = !(d->flags & GF_FLAG_FP32_EXACT) && tc_supported(L, d);
+  if (post && (post->rgb_out || post->rgb_w)) {
+    if (!post->rgb_out || !post->rgb_w || ((uintptr_t)post->rgb_w & 15)) { set_error("postop: fused tRGB needs rgb_w (16-byte aligned) and rgb_out"); return GF_ERR_INVALID; }
+    if (!tc || L.C > 256) { set_error("postop: the fused tRGB is served by the tcgen05 path with C <= 256 only (see gf_attn_tc_eligible)"); return GF_ERR_UNSUPPORTED; }
+  }
+  if (tc) return token_pass_tc(L, d, X, Xout, att, ws, post, st);
   return token_pass_simt(L, d, X, Xout, att, ws, post, st);
 }
 
@@ -66,6 +71,13 @@ const char* gf_last_error(void) { return g_err; }
 int gf_attn_last_path(void) { return g_path; }
 int gf_attn_last_centroid_path(void) { return g_cen_path; }
 long long gf_attn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int gf_attn_tc_eligible(const gf_attn_desc* desc) {
+  Layout L;
+  int rc = make_layout(desc, &L);
+  if (rc) return rc;
+  return (!(desc->flags & GF_FLAG_FP32_EXACT) && tc_supported(L, desc)) ? 1 : 0;
+}
 
 int gf_attn_debug_layout(const gf_attn_desc* desc, long long* out, int n) {
   Layout L;

@@ -292,6 +292,73 @@ __global__ void __launch_bounds__(256) torgb_kernel(const float4* __restrict__ x
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// G_mapping as ONE kernel: pixel-norm of every latent, then L fully connected layers (+ leaky-ReLU) --
+// one MLP shared by the k local components, one for the global latent -- and the truncation lerp.  All 2 L weight
+// matrices (D x D, equalised-LR and activation gains pre-folded, [in][out]) are staged in shared memory once per CTA;
+// one warp owns one latent row at a time (lane = output feature, the input vector is broadcast from shared memory).
+// Replaces 16 small GEMMs + 16 activation kernels + 6 elementwise kernels per step of the eager form.
+// ------------------------------------------------------------------------------------------------------
+constexpr int MAP_WARPS = 8, MAP_MAXM = 4;          // D <= 128
+__global__ void __launch_bounds__(MAP_WARPS * 32) mapping_kernel(const float* __restrict__ z, const float* __restrict__ Wt,
+                                                                 const float* __restrict__ bias, const float* __restrict__ w_avg, float psi,
+                                                                 float* __restrict__ out, int rows, int k, int D, int L) {
+  extern __shared__ float msm[];
+  float* Ws = msm;                                   // [2][L][D][D]
+  float* bs = Ws + (size_t)2 * L * D * D;            // [2][L][D]
+  float* xs = bs + (size_t)2 * L * D;                // [MAP_WARPS][D]
+  for (int i = threadIdx.x; i < 2 * L * D * D; i += blockDim.x) Ws[i] = Wt[i];
+  for (int i = threadIdx.x; i < 2 * L * D; i += blockDim.x) bs[i] = bias[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* x = xs + warp * D;
+  const int nm = (D + 31) >> 5;
+  for (int row = blockIdx.x * MAP_WARPS + warp; row < rows; row += gridDim.x * MAP_WARPS) {
+    const int comp = row % (k + 1);
+    const int path = comp == k ? 1 : 0;              // the last latent of every sample is the global one
+    // pixel norm: x * rsqrt(mean(x^2) + 1e-8)
+    float v[MAP_MAXM], ss = 0.f;
+#pragma unroll
+    for (int m = 0; m < MAP_MAXM; ++m) {
+      const int o = lane + 32 * m;
+      v[m] = (m < nm && o < D) ? z[(size_t)row * D + o] : 0.f;
+      ss = fmaf(v[m], v[m], ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rn = rsqrtf(ss / (float)D + 1e-8f);
+#pragma unroll
+    for (int m = 0; m < MAP_MAXM; ++m) if (m < nm && lane + 32 * m < D) x[lane + 32 * m] = v[m] * rn;
+    __syncwarp();
+    for (int l = 0; l < L; ++l) {
+      const float* W = Ws + ((size_t)path * L + l) * D * D;
+      const float* bb = bs + ((size_t)path * L + l) * D;
+      float acc[MAP_MAXM];
+#pragma unroll
+      for (int m = 0; m < MAP_MAXM; ++m) acc[m] = (m < nm && lane + 32 * m < D) ? bb[lane + 32 * m] : 0.f;
+      for (int i = 0; i < D; ++i) {
+        const float xi = x[i];                       // broadcast
+#pragma unroll
+        for (int m = 0; m < MAP_MAXM; ++m) if (m < nm && lane + 32 * m < D) acc[m] = fmaf(xi, W[(size_t)i * D + lane + 32 * m], acc[m]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int m = 0; m < MAP_MAXM; ++m) if (m < nm && lane + 32 * m < D) x[lane + 32 * m] = fmaxf(acc[m], 0.2f * acc[m]);   // gain sqrt(2) is in W, b
+      __syncwarp();
+    }
+#pragma unroll
+    for (int m = 0; m < MAP_MAXM; ++m) {
+      const int o = lane + 32 * m;
+      if (m < nm && o < D) {
+        float r = x[o];
+        if (w_avg) { const float a = w_avg[path * D + o]; r = a + psi * (r - a); }      // truncation trick: lerp(w_avg, w, psi)
+        out[(size_t)row * D + o] = r;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 extern "C" {
 
 int gf_chan_scale_nhwc(const float* x, const float* s, int s_ld, float* y, int B, int HW, int C, void* stream) {
@@ -399,6 +466,25 @@ int gf_torgb_scale_nhwc(const float* x, const float* w, const float* styles, int
     case 3: torgb_kernel<3, 3><<<grid, 256, 0, st>>>(x4, w, styles, s_ld, bias, wscale, y, HW, C4, tok_per_cta, s2, s2_ld, reinterpret_cast<float4*>(xs_out)); break;
     default: torgb_kernel<3, 4><<<grid, 256, 0, st>>>(x4, w, styles, s_ld, bias, wscale, y, HW, C4, tok_per_cta, s2, s2_ld, reinterpret_cast<float4*>(xs_out)); break;
   }
+  GF_LAUNCH_OK();
+  return GF_OK;
+}
+
+int gf_mapping_fwd(const float* z, const float* w, const float* b, const float* w_avg, float psi, float* out,
+                   int B, int k, int D, int L, void* stream) {
+  if (!z || !w || !b || !out) { set_error("gf_mapping_fwd: null pointer"); return GF_ERR_INVALID; }
+  if (B <= 0 || k < 0 || D <= 0 || L <= 0) { set_error("gf_mapping_fwd: bad sizes B=%d k=%d D=%d L=%d", B, k, D, L); return GF_ERR_INVALID; }
+  if (D > 32 * MAP_MAXM) { set_error("gf_mapping_fwd: latent width D=%d > %d is not served by the fused kernel", D, 32 * MAP_MAXM); return GF_ERR_UNSUPPORTED; }
+  const size_t smem = ((size_t)2 * L * D * D + (size_t)2 * L * D + (size_t)MAP_WARPS * D) * sizeof(float);
+  int dev = 0, optin = 0;
+  GF_CUDA_OK(cudaGetDevice(&dev));
+  GF_CUDA_OK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (smem > (size_t)optin) { set_error("gf_mapping_fwd: 2*L*D*D weights (%zu bytes) do not fit shared memory", smem); return GF_ERR_UNSUPPORTED; }
+  GF_CUDA_OK(cudaFuncSetAttribute(mapping_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int rows = B * (k + 1);
+  int grid = (rows + MAP_WARPS - 1) / MAP_WARPS;
+  if (grid > num_sms()) grid = num_sms();
+  mapping_kernel<<<grid, MAP_WARPS * 32, smem, (cudaStream_t)stream>>>(z, w, b, w_avg, psi, out, rows, k, D, L);
   GF_LAUNCH_OK();
   return GF_OK;
 }

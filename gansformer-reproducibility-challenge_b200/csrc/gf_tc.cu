@@ -48,6 +48,8 @@ struct Params {
   // fused epilogue (gf_attn_postop)
   const float* pbias; const float* pnoise; const float* pstrength; long long pnoise_bstride; int pact; float pgain; int has_post;
   const float* in_scale; const float* post_scale; int in_ld, post_ld;   // per-(b,c) load-side / store-side scales
+  // fused tRGB (1x1 modulated conv of the layer output to 3 planes): rgb_w [B][3][C] per-sample weights, rgb_out [B][3][n]
+  const float* rgb_w; const float* rgb_bias; float* rgb_out;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -60,6 +62,7 @@ struct Bars {
   uint64_t st_full[2], st_free[2];
   uint64_t acc_full[NACC], acc_empty[NACC];
   uint64_t sc_full[2], sc_free[2];       // per-image load/store-side scale vectors (double-buffered by image parity)
+  uint64_t rgb_full[2], rgb_free[2];     // tRGB partial sums of epilogue group 1 -> group 0 (double-buffered by tile parity)
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -77,9 +80,13 @@ struct Cfg {
   static constexpr int OFF_V = OFF_KP + KP_BYTES;
   static constexpr int OFF_STATS = OFF_V + V_BYTES;
   static constexpr int OFF_PBIAS = OFF_STATS + STATS_BYTES;
-  static constexpr int SCALE_BYTES = 2 * 2 * C * 4;      // [image parity]{in_scale, post_scale}[C]
+  static constexpr int NVEC = NS > 8 ? 2 : 5;             // per-image vectors: in_scale, post_scale (+ tRGB weights r / g / b for C <= 256:
+                                                         // at C = 512 the 12 KB would cost the two-pass ring a stage for a small layer)
+  static constexpr int SCALE_BYTES = 2 * NVEC * C * 4;   // [image parity][NVEC][C]
   static constexpr int OFF_SCALE = OFF_PBIAS + PBIAS_BYTES;
-  static constexpr int OFF_BARS = OFF_SCALE + SCALE_BYTES;
+  static constexpr int RGBP_BYTES = NS > 8 ? 0 : 2 * 3 * TILE * 4;    // [tile parity][plane][row]: group 1's partial sums
+  static constexpr int OFF_RGBP = OFF_SCALE + SCALE_BYTES;
+  static constexpr int OFF_BARS = OFF_RGBP + RGBP_BYTES;
   static constexpr int OFF_RING = (OFF_BARS + (int)sizeof(Bars) + 1023) / 1024 * 1024;
   static constexpr int FIXED_BYTES = OFF_RING;
 };
@@ -101,7 +108,10 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   float* pbias_s = reinterpret_cast<float*>(smem + CF::OFF_PBIAS);
   const float* scale_s = reinterpret_cast<const float*>(smem + CF::OFF_SCALE);
   const uint32_t s_scale = s_base + CF::OFF_SCALE;
-  const bool has_scales = P.in_scale != nullptr || P.post_scale != nullptr;
+  const bool has_rgb = NS <= 8 && P.rgb_out != nullptr;
+  const bool has_scales = P.in_scale != nullptr || P.post_scale != nullptr || has_rgb;      // any per-image vector to stage
+  float* rgbp = reinterpret_cast<float*>(smem + CF::OFF_RGBP);
+  constexpr int NV = CF::NVEC;
   if (P.has_post)
     for (int i = threadIdx.x; i < C; i += NUM_THREADS) pbias_s[i] = P.pbias ? P.pbias[i] : 0.f;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
@@ -126,6 +136,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
     for (int i = 0; i < NACC; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 4); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->sc_full[i]), 1); mbar_init(smem_u32(&bars->sc_free[i]), 12); }   // 4 row + 8 epilogue warps
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->rgb_full[i]), 4); mbar_init(smem_u32(&bars->rgb_free[i]), 4); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -160,9 +171,10 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             const int par = img_changes & 1;
             mbar_wait(smem_u32(&bars->sc_free[par]), (uint32_t)(((img_changes >> 1) & 1) ^ 1));
             const uint32_t sb = smem_u32(&bars->sc_full[par]);
-            mbar_expect_tx(sb, (uint32_t)((P.in_scale ? C * 4 : 0) + (P.post_scale ? C * 4 : 0)));
-            if (P.in_scale) bulk_load_1d(s_scale + par * 2 * C * 4, P.in_scale + (size_t)b * P.in_ld, C * 4, sb);
-            if (P.post_scale) bulk_load_1d(s_scale + (par * 2 + 1) * C * 4, P.post_scale + (size_t)b * P.post_ld, C * 4, sb);
+            mbar_expect_tx(sb, (uint32_t)((P.in_scale ? C * 4 : 0) + (P.post_scale ? C * 4 : 0) + (has_rgb ? 3 * C * 4 : 0)));
+            if (P.in_scale) bulk_load_1d(s_scale + par * NV * C * 4, P.in_scale + (size_t)b * P.in_ld, C * 4, sb);
+            if (P.post_scale) bulk_load_1d(s_scale + (par * NV + 1) * C * 4, P.post_scale + (size_t)b * P.post_ld, C * 4, sb);
+            if (has_rgb) bulk_load_1d(s_scale + (par * NV + 2) * C * 4, P.rgb_w + (size_t)b * 3 * C, 3 * C * 4, sb);   // r | g | b rows are contiguous
           }
           prev_b = b;
           ++img_changes;
@@ -304,7 +316,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           mbar_wait(smem_u32(&bars->slab_full[stage]), ph);
           if (P.norm_layer) {
             const uint8_t* slab = smem + CF::OFF_RING + stage * SLAB_BYTES + row_off;
-            const float4* isc = P.in_scale ? reinterpret_cast<const float4*>(scale_s + spar * 2 * C + s * SLAB_CH) : nullptr;
+            const float4* isc = P.in_scale ? reinterpret_cast<const float4*>(scale_s + spar * NV * C + s * SLAB_CH) : nullptr;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
               float4 x = *reinterpret_cast<const float4*>(slab + ((c ^ sw) << 4));
@@ -413,6 +425,8 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     // post-op noise: one value per token, fetched a tile ahead (its L2 latency sat on the epilogue's critical path)
     const bool has_noise = P.has_post && P.pnoise != nullptr;
     const float pstr = (has_noise && P.pstrength) ? __ldg(P.pstrength) : 1.f;
+    const float rgb_b0 = (has_rgb && P.rgb_bias) ? __ldg(P.rgb_bias) : 0.f, rgb_b1 = (has_rgb && P.rgb_bias) ? __ldg(P.rgb_bias + 1) : 0.f,
+                rgb_b2 = (has_rgb && P.rgb_bias) ? __ldg(P.rgb_bias + 2) : 0.f;
     float pnz_next = 0.f;
     if (has_noise && tile_beg < tile_end) pnz_next = __ldg(P.pnoise + (size_t)b_next * P.pnoise_bstride + min(t_in_img * P.rows + row, P.n - 1));
     for (long long tile = tile_beg; tile < tile_end; ++tile, ++it) {
@@ -420,6 +434,8 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const int buf = (int)(it & 1);
       const uint32_t bphase = (it >> 1) & 1u;
       const float pnz = pnz_next * pstr;             // post-op: per-token noise value
+      const int t_cur = t_in_img;                      // this tile's index inside its image
+      float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;         // fused tRGB: this thread's share (its group's slabs) of the token's 3 sums
       const bool img_first = t_in_img == 0 || tile == tile_beg;
       if (++t_in_img == P.tiles_per_image) { t_in_img = 0; ++b_next; }
       if (has_noise && tile + 1 < tile_end)
@@ -456,8 +472,9 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[a]));
         uint8_t* slab = smem + CF::OFF_RING + stage * SLAB_BYTES + row_off;
-        const float4* isc = P.in_scale ? reinterpret_cast<const float4*>(scale_s + spar * 2 * C + s * SLAB_CH) : nullptr;
-        const float4* psc = P.post_scale ? reinterpret_cast<const float4*>(scale_s + (spar * 2 + 1) * C + s * SLAB_CH) : nullptr;
+        const float4* isc = P.in_scale ? reinterpret_cast<const float4*>(scale_s + spar * NV * C + s * SLAB_CH) : nullptr;
+        const float4* psc = P.post_scale ? reinterpret_cast<const float4*>(scale_s + (spar * NV + 1) * C + s * SLAB_CH) : nullptr;
+        const float4* wrv = reinterpret_cast<const float4*>(scale_s + (spar * NV + (NS <= 8 ? 2 : 0)) * C + s * SLAB_CH);   // tRGB weights (read when has_rgb)
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float4* px = reinterpret_cast<float4*>(slab + ((c ^ sw) << 4));
@@ -477,6 +494,12 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             x.x += pnz + pb.x; x.y += pnz + pb.y; x.z += pnz + pb.z; x.w += pnz + pb.w;
             if (P.pact == 1) { x.x = fmaxf(x.x, 0.2f * x.x); x.y = fmaxf(x.y, 0.2f * x.y); x.z = fmaxf(x.z, 0.2f * x.z); x.w = fmaxf(x.w, 0.2f * x.w); }
             x.x *= P.pgain; x.y *= P.pgain; x.z *= P.pgain; x.w *= P.pgain;
+            if (has_rgb) {                                   // tRGB reads the layer output proper: before the next layer's style scale
+              const float4 w0 = wrv[c], w1 = wrv[(C >> 2) + c], w2 = wrv[2 * (C >> 2) + c];       // shared-memory broadcasts
+              rgb0 = fmaf(x.x, w0.x, fmaf(x.y, w0.y, fmaf(x.z, w0.z, fmaf(x.w, w0.w, rgb0))));
+              rgb1 = fmaf(x.x, w1.x, fmaf(x.y, w1.y, fmaf(x.z, w1.z, fmaf(x.w, w1.w, rgb1))));
+              rgb2 = fmaf(x.x, w2.x, fmaf(x.y, w2.y, fmaf(x.z, w2.z, fmaf(x.w, w2.w, rgb2))));
+            }
             if (psc) { const float4 q4 = psc[c]; x.x *= q4.x; x.y *= q4.y; x.z *= q4.z; x.w *= q4.w; }
           }
           *px = x;
@@ -491,6 +514,26 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             mbar_arrive_n(smem_u32(&bars->slab_empty[pending_stage]), EMPTY_COUNT);
           }
           pending_stage = stage;
+        }
+      }
+      if (has_rgb) {
+        // a token's channels are split over the two epilogue groups: group 1 hands its partial sums to group 0, which adds the
+        // bias and writes the three planes (32 consecutive tokens per warp: 128-byte coalesced stores)
+        float* pb = rgbp + buf * 3 * TILE;
+        if (g == 1) {
+          mbar_wait(smem_u32(&bars->rgb_free[buf]), bphase ^ 1u);
+          pb[row] = rgb0; pb[TILE + row] = rgb1; pb[2 * TILE + row] = rgb2;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->rgb_full[buf]));
+        } else {
+          mbar_wait(smem_u32(&bars->rgb_full[buf]), bphase);
+          rgb0 += pb[row]; rgb1 += pb[TILE + row]; rgb2 += pb[2 * TILE + row];
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->rgb_free[buf]));
+          if (row < P.rows) {
+            float* o = P.rgb_out + (size_t)b * 3 * P.n + (size_t)t_cur * P.rows + row;
+            o[0] = rgb0 + rgb_b0; o[P.n] = rgb1 + rgb_b1; o[2 * (size_t)P.n] = rgb2 + rgb_b2;
+          }
         }
       }
       if (has_scales && img_last) {                  // this warp has read the image's scale vectors for the last time
@@ -560,6 +603,7 @@ static int launch(const Layout& L, const gf_attn_desc* d, const float* X, float*
   P.pnoise_bstride = post ? post->noise_bstride : 0; P.pact = post ? post->act : 0; P.pgain = post ? post->gain : 1.f;
   P.in_scale = post ? post->in_scale : nullptr; P.post_scale = post ? post->post_scale : nullptr;
   P.in_ld = post ? post->in_scale_ld : 0; P.post_ld = post ? post->post_scale_ld : 0;
+  P.rgb_w = post ? post->rgb_w : nullptr; P.rgb_bias = post ? post->rgb_bias : nullptr; P.rgb_out = post ? post->rgb_out : nullptr;
   const int smem_bytes = CF::FIXED_BYTES + nst * SLAB_BYTES + 1024;
   auto kern = token_tc_kernel<KP, NS, MODE, TWO>;
   GF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));

@@ -20,7 +20,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .attention import BipartiteAttention, _Plan, prologue_batch
+from .attention import BipartiteAttention, _Plan, prologue_batch, tc_eligible
 from . import ops
 from ._state import weights_epoch, bump_weights_epoch
 from .ops import fir_filter
@@ -145,6 +145,16 @@ class MappingNetwork(nn.Module):
         k = self.components_num
         if z.dim() != 3 or z.shape[1] != k + 1 or z.shape[2] != self.latent_dim:
             raise ValueError(f"z must be [B, {k + 1}, {self.latent_dim}], got {tuple(z.shape)}")
+        params = [t for fc in list(self.local) + list(self.glob) for t in (fc.weight, fc.bias)]
+        if (z.is_cuda and z.dtype == torch.float32 and _inference(*params) and self.latent_dim <= 128
+                and len(self.local) * self.latent_dim ** 2 * 8 <= 200 * 1024 and not os.environ.get("GF_NO_MAPPING_KERNEL")):
+            # inference: the whole mapping network is ONE kernel (gf_mapping_fwd); effective weights cached until a parameter changes
+            def stack():
+                wl, bl = zip(*[fc.effective() for fc in self.local])
+                wg, bg = zip(*[fc.effective() for fc in self.glob])
+                return (torch.stack([torch.stack(wl), torch.stack(wg)]).contiguous(), torch.stack([torch.stack(bl), torch.stack(bg)]).contiguous())
+            w_eff, b_eff = _cached(self, "stack", params, stack)
+            return ops.mapping_fwd(z, w_eff, b_eff, self.w_avg, float(truncation_psi), k)
         z = z * torch.rsqrt(z.square().mean(dim=2, keepdim=True) + 1e-8)
         loc, glo = z[:, :k], z[:, k:]
         for fc in self.local:
@@ -188,9 +198,11 @@ class SynthesisLayer(nn.Module):
                 and _inference(self.weight, self.bias, self.noise_strength, *a.parameters()))
 
     def forward(self, x, w_glob, y, noise_mode="const", centroids=None, return_att=False, styles=None,
-                prescaled=False, post_scale=None, prepared=None):
+                prescaled=False, post_scale=None, prepared=None, rgb=None):
         """prescaled: x already carries this layer's style scale.  post_scale [B,C]: the NEXT convolution's style scale,
-        folded into this layer's store (only honoured -- and only passed by SynthesisNetwork -- when `fusable`)."""
+        folded into this layer's store (only honoured -- and only passed by SynthesisNetwork -- when `fusable`).
+        rgb: dict(rgb_w [B,3,C], rgb_bias [3], rgb_out [B,3,H,W]) -- the block's tRGB computed by the attention kernel's store side
+        from the layer output (fused path on the tcgen05 kernel only; SynthesisNetwork checks)."""
         if styles is None:
             styles = self.affine(w_glob)
         w_eff = wsq = phases = None
@@ -221,6 +233,8 @@ class SynthesisLayer(nn.Module):
             if fused:   # demod (load side) + noise + bias + leaky-ReLU + next style (store side) ride on the attention kernel
                 post = dict(bias=self.bias, noise=noise, strength=self.noise_strength, act="lrelu", gain=SQRT2,
                             in_scale=in_scale, post_scale=post_scale)
+                if rgb is not None:
+                    post.update(rgb)
                 if prepared is not None and prepared[0] is not None:
                     torch.cuda.current_stream(x.device).wait_event(prepared[0])
                 xo, att, centroids = self.attention(xl, y, centroids=centroids, return_att=return_att, postop=post,
@@ -331,27 +345,43 @@ class SynthesisNetwork(nn.Module):
         for bi, res in enumerate(self.block_resolutions):
             nl = 1 if res == 4 else 2
             prescaled = block_prescaled
+            # the tRGB pass reads x anyway: it can also write the next block's style-modulated input (inference only)
+            nxt = styles_all[li + nl] if (li + nl < len(self.layers) and styles_all[li + nl] is not None and x.is_cuda and not return_features
+                                          and not os.environ.get("GF_NO_TORGB_FUSE")) else None
+            rgb = None
             for j in range(nl):
                 layer = self.layers[li]
                 # conv0 -> conv1 inside a block has a single consumer: conv1's style scale is folded into conv0's store
                 post_scale = None
                 if j == 0 and nl == 2 and styles_all[li + 1] is not None and layer.fusable(x) and not return_features:
                     post_scale = styles_all[li + 1]
+                rgb_args = None
+                if j == nl - 1 and layer.fusable(x) and not return_features and not os.environ.get("GF_NO_TORGB_EPILOGUE"):
+                    # last layer of the block on the tcgen05 path with C <= 256: the attention kernel's store side computes the
+                    # tRGB planes from the layer output and writes x * (next block's style): the tRGB pass disappears
+                    C_ = layer.weight.shape[0]
+                    tg = self.torgbs[bi]
+                    if C_ <= 256 and _inference(tg.weight, tg.bias) and tc_eligible(layer.attention, (B, res, res, C_), k):
+                        st_rgb = styles_all[len(self.layers) + bi]
+                        rgb_w = (tg.weight.reshape(1, 3, C_) * st_rgb[:, None, :] * (1.0 / math.sqrt(C_))).contiguous()
+                        rgb = torch.empty((B, 3, res, res), device=x.device, dtype=torch.float32)
+                        rgb_args = dict(rgb_w=rgb_w, rgb_bias=tg.bias, rgb_out=rgb)
+                        post_scale = nxt
                 x, att, _ = layer(x, w_glob, y, noise_mode=noise_mode, return_att=return_att, styles=styles_all[li],
-                                  prescaled=prescaled, post_scale=post_scale, prepared=prepared[li])
+                                  prescaled=prescaled, post_scale=post_scale, prepared=prepared[li], rgb=rgb_args)
                 prescaled = post_scale is not None
                 li += 1
                 if att is not None:
                     atts.append(att)
                 if return_features and layer.attention is not None:
                     feats.append(x)
-            # the tRGB pass reads x anyway: let it also write the next block's style-modulated input (inference only)
-            nxt = styles_all[li] if (li < len(self.layers) and styles_all[li] is not None and x.is_cuda and not return_features
-                                     and not os.environ.get("GF_NO_TORGB_FUSE")) else None
-            rgb = self.torgbs[bi](x, w_glob, styles=styles_all[len(self.layers) + bi], next_styles=nxt)
-            block_prescaled = nxt is not None
-            if block_prescaled:
-                rgb, x = rgb
+            if rgb is not None:
+                block_prescaled = nxt is not None
+            else:
+                rgb = self.torgbs[bi](x, w_glob, styles=styles_all[len(self.layers) + bi], next_styles=nxt)
+                block_prescaled = nxt is not None
+                if block_prescaled:
+                    rgb, x = rgb
             img = rgb if img is None else ops.upsample2x(img, self.fir, add=rgb)
         out = (img,) + ((atts,) if return_att else ()) + ((feats,) if return_features else ())
         return out[0] if len(out) == 1 else out

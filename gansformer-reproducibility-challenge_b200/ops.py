@@ -274,3 +274,16 @@ def torgb(x: torch.Tensor, weight: torch.Tensor, styles: torch.Tensor, bias: Opt
         rgb = rgb + bias.to(x.dtype)
     rgb = rgb.transpose(1, 2).reshape(B, O, H, W)
     return rgb if next_styles is None else (rgb, x * next_styles[:, :, None, None].to(x.dtype))
+
+
+def mapping_fwd(z: torch.Tensor, w_eff: torch.Tensor, b_eff: torch.Tensor, w_avg: Optional[torch.Tensor], psi: float, k: int) -> torch.Tensor:
+    """G_mapping in one launch (gf_mapping_fwd): z [B, k+1, D]; w_eff [2, L, D, D] ([in, out], gains folded), b_eff [2, L, D];
+    w_avg [2, D] (applied with psi when psi != 1).  CUDA fp32 inference only -- the module keeps the torch form for autograd."""
+    B, kp1, D = z.shape
+    L = w_eff.shape[1]
+    out = torch.empty_like(z)
+    wa = w_avg.contiguous() if (w_avg is not None and psi != 1.0) else None
+    with torch.cuda.device(z.device):
+        _lib.check(_lib.load().gf_mapping_fwd(z.contiguous().data_ptr(), w_eff.data_ptr(), b_eff.data_ptr(), wa.data_ptr() if wa is not None else None,
+                                              float(psi), out.data_ptr(), B, k, D, L, _stream(z.device)), "gf_mapping_fwd")
+    return out

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GF_ATTN_ABI_VERSION 1
+#define GF_ATTN_ABI_VERSION 2
 
 typedef enum gf_status {
   GF_OK = 0,
@@ -80,6 +80,13 @@ typedef struct gf_attn_postop {
   const float* in_scale;     /* [B][in_scale_ld] rows of C floats, 16-byte aligned rows; NULL = 1 */
   const float* post_scale;   /* [B][post_scale_ld]; NULL = 1 */
   int32_t in_scale_ld, post_scale_ld;
+  /* fused tRGB (the 1x1 modulated convolution, no demodulation, that follows the last layer of a resolution block):
+   *   rgb_out[b][o][t] = sum_c x''[b,t,c] * rgb_w[b][o][c] + rgb_bias[o],  o < 3,  x'' = the layer output BEFORE post_scale.
+   * rgb_w [B][3][C] contiguous (weight * style * 1/sqrt(C) per sample), 16-byte aligned; rgb_bias [3] or NULL; rgb_out [B][3][H*W]
+   * planar.  All NULL = off.  Served by the tcgen05 path only (gf_attn_tc_eligible); the CUDA-core path returns UNSUPPORTED. */
+  const float* rgb_w;
+  const float* rgb_bias;
+  float* rgb_out;
 } gf_attn_postop;
 
 /* Raw (un-scaled) parameters of one layer, each [fan_in, fan_out] row-major; equalised-LR scaling
@@ -105,6 +112,10 @@ int gf_attn_last_path(void);
 int gf_attn_last_centroid_path(void);
 /* Number of kernels this library has launched in this process (all threads); bench.py reports the delta. */
 long long gf_attn_launch_count(void);
+
+/* 1 when gf_attn_simplex_fwd / stage T of this layer runs on the tcgen05 (TF32) kernel, 0 when the CUDA-core kernel serves it
+ * (GF_FLAG_FP32_EXACT, instance / batch norm, C not in {64,128,256,512}, ragged n); negative gf_status on a bad descriptor. */
+int gf_attn_tc_eligible(const gf_attn_desc* desc);
 
 /* Debug aid for the bring-up probes (tools/): float offsets {w_PART, w_XBAR, nsplit_cen, KP, w_M, w_Rt2, w_Ct2, w_total} of the workspace. */
 int gf_attn_debug_layout(const gf_attn_desc* desc, long long* out, int n);

@@ -67,6 +67,15 @@ int gf_torgb_nhwc(const float* x, const float* w, const float* styles, int s_ld,
 int gf_torgb_scale_nhwc(const float* x, const float* w, const float* styles, int s_ld, const float* bias, float wscale, float* y,
                         const float* s2, int s2_ld, float* xs_out, int B, int HW, int C, void* stream);
 
+/* G_mapping as one kernel: z [B, k+1, D] -> out [B, k+1, D].  Every latent is pixel-normalised
+ * (x * rsqrt(mean x^2 + 1e-8)), then runs through L fully connected layers with leaky-ReLU(0.2) -- path 0 (shared by the k local
+ * components) or path 1 (the last, global latent) -- and, when w_avg [2, D] is given, the truncation lerp
+ * out = w_avg[path] + psi * (y - w_avg[path]).  w [2, L, D(in), D(out)] and b [2, L, D] are the EFFECTIVE weights (equalised-LR
+ * scale lr_mul/sqrt(D), bias scale lr_mul and the activation gain sqrt(2) folded in: lrelu(g x) = g lrelu(x)).
+ * Replaces the reference's G_mapping dense_layer chain.  D <= 128 and 2*L*D*D floats must fit shared memory. */
+int gf_mapping_fwd(const float* z, const float* w, const float* b, const float* w_avg, float psi, float* out,
+                   int B, int k, int D, int L, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

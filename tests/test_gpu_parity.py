@@ -4,9 +4,9 @@ Oracle = oracle/bipartite.py in float64 (in-repo restatement; reference source u
 
 Tolerances (stated here, per the task contract):
   * fp32-FMA mode (GF_FLAG_FP32_EXACT, CUDA-core kernel):   |y - y64| <= 1e-5 + 1e-4 |y64|      
-  * TF32 tensor-core mode (tcgen05 kind::tf32, default):    |y - y64| <= 8e-3 + 8e-3 |y64|  and  rel-RMS <= 2e-3
-    (calibrated with a CPU emulation of TF32 operand truncation on N(0,1) weights: rel-RMS ~9e-4, max-abs ~1.6e-2
-     at |y| ~ 12; the logits lose ~1e-3 absolute to the 10-bit mantissa.)
+  * TF32 tensor-core mode (tcgen05 kind::tf32, default):    |y - y64| <= 1e-4 + 1.25e-3 max|y64| + 2e-3 |y64|  and  rel-RMS <= 1e-3
+    (frozen in tests/tolerances.json by tools/calibrate_tolerances.py: the SURVEY 8c contract formula plus a scale term --
+     measured worst need 6.4e-4 max|y64|, worst rel-RMS 5.5e-4.)
 """
 import json
 import math
@@ -26,7 +26,7 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden", "attn_cases.npz")
 TOL_PATH = os.path.join(os.path.dirname(__file__), "tolerances.json")
 with open(TOL_PATH) as _f:
     TOLERANCES = json.load(_f)           # frozen by tools/calibrate_tolerances.py (see its docstring and DESIGN.md section 5)
-TOL = {path: (t["atol"], t["rtol"], t["rel_rms"]) for path, t in TOLERANCES["layer"].items()}
+TOL = {path: (t["atol"], t["rtol"], t["rel_rms"], t.get("atol_rel_peak", 0.0)) for path, t in TOLERANCES["layer"].items()}
 CONTRACT = TOLERANCES["contract"]       # SURVEY 8c per-layer TF32 formula: max(4 e_ref, atol + rtol |y64|)
 
 
@@ -44,8 +44,9 @@ def check_close(got, ref64, path, what="", tol_scale=1.0, e_ref=0.0):
     ref64 = ref64.detach().double().cpu()
     assert got.shape == ref64.shape, (got.shape, ref64.shape)
     assert torch.isfinite(got).all(), f"{what}: non-finite output"
-    atol, rtol, rrms = (t * tol_scale for t in TOL[path])
+    atol, rtol, rrms, arel = (t * tol_scale for t in TOL[path])
     err = (got - ref64).abs()
+    atol = atol + arel * ref64.abs().max().item()              # scale term: see tolerances.json "_doc"
     bound = (atol + rtol * ref64.abs()).clamp_min(4.0 * e_ref)
     ratio = (err / bound).max().item()
     contract_ratio = (err / (CONTRACT["atol"] + CONTRACT["rtol"] * ref64.abs()).clamp_min(4.0 * e_ref)).max().item()
@@ -786,3 +787,80 @@ def test_prologue_batch_api(gf, cuda_dev):
         for m, x, sc, w in zip(layers, xs, scales, want):
             got, _, _ = m(x, y, postop=sc[1], stage="token", need_centroids=False)
             assert torch.equal(got, w), (m.dim, m.duplex)
+
+
+@pytest.mark.parametrize("D,k,L,B", [(32, 16, 8, 5), (16, 4, 2, 3), (64, 3, 4, 37), (96, 1, 2, 2)])
+def test_mapping_kernel_matches_definition(gf, cuda_dev, D, k, L, B):
+    """gf_mapping_fwd (G_mapping as one kernel: pixel norm, L FC + leaky-ReLU layers per path, truncation lerp) against the
+    module's float64 torch definition on the CPU, with and without truncation."""
+    import copy
+    from importlib import import_module
+    nets = import_module("gansformer-reproducibility-challenge_b200.networks")
+    torch.manual_seed(D + k)
+    M = nets.MappingNetwork(D, k, num_layers=L)
+    with torch.no_grad():
+        for p in M.parameters():
+            if p.dim() == 1:
+                p.normal_(0, 30.0)               # biases carry lr_mul = 0.01: make them matter
+        M.w_avg.normal_(0, 0.5)
+    ref_mod = copy.deepcopy(M).double()
+    Mg = M.to(cuda_dev).eval()
+    z = torch.randn(B, k + 1, D, generator=torch.Generator().manual_seed(3))
+    for psi in (1.0, 0.6):
+        l0 = gf._lib.launch_count()
+        with torch.no_grad():
+            got = Mg(z.to(cuda_dev), truncation_psi=psi)
+        assert gf._lib.launch_count() - l0 == 1                      # one launch of ours, nothing else
+        want = ref_mod(z.double(), truncation_psi=psi)
+        err = (got.double().cpu() - want).abs().max().item()
+        assert err <= 2e-5 * max(1.0, want.abs().max().item()), (psi, err)
+
+
+@pytest.mark.parametrize("C,H,W,k,duplex,integration", [(128, 16, 16, 16, False, "mul"), (256, 16, 8, 8, False, "both"), (64, 32, 32, 32, True, "mul"),
+                                                          (128, 8, 8, 16, False, "add"), (256, 32, 32, 32, True, "mul")])
+def test_fused_torgb_epilogue(gf, cuda_dev, C, H, W, k, duplex, integration):
+    """Store-side fusion of the tRGB 1x1 modulated convolution (postop.rgb_*): the three planes are computed from the layer output
+    BEFORE the next layer's style scale, which the stored activations carry; both against the float64 oracle."""
+    D = p = 16
+    B = 3
+    g = torch.Generator().manual_seed(C + k + H)
+    x64 = torch.randn(B, C, H, W, generator=g, dtype=torch.float64)
+    y64 = torch.randn(B, k, D, generator=g, dtype=torch.float64)
+    d_in = torch.rand(B, C, generator=g, dtype=torch.float64) + 0.5
+    ps = torch.randn(B, C, generator=g, dtype=torch.float64) + 1.0
+    bias = torch.randn(C, generator=g, dtype=torch.float64) * 0.5
+    noise = torch.randn(H, W, generator=g, dtype=torch.float64)
+    rgb_w = torch.randn(B, 3, C, generator=g, dtype=torch.float64) / math.sqrt(C)
+    rgb_b = torch.randn(3, generator=g, dtype=torch.float64)
+    w = ob.init_params(C, D, k, p, integration, duplex, seed=5, bias_std=0.3)
+    ref, _, _ = ob.transformer_layer(x64 * d_in[:, :, None, None], y64, w, integration=integration, duplex=duplex)
+    ref = torch.nn.functional.leaky_relu(ref + noise * 0.37 + bias[None, :, None, None], 0.2) * math.sqrt(2.0)
+    ref_rgb = torch.einsum("bchw,boc->bohw", ref, rgb_w) + rgb_b[None, :, None, None]
+    ref_out = ref * ps[:, :, None, None]
+    attn = make_layer(gf, cuda_dev, C, D, k, p, integration, "layer", duplex, True, False, w)
+    f = lambda t: t.float().to(cuda_dev)
+    rgb_out = torch.full((B, 3, H, W), float("nan"), device=cuda_dev)
+    post = dict(bias=f(bias), noise=f(noise), strength=torch.tensor(0.37, device=cuda_dev), act="lrelu", gain=math.sqrt(2.0),
+                in_scale=f(d_in), post_scale=f(ps), rgb_w=f(rgb_w).contiguous(), rgb_bias=f(rgb_b), rgb_out=rgb_out)
+    with torch.no_grad():
+        out, _, _ = attn(x64.permute(0, 2, 3, 1).contiguous().float().to(cuda_dev), f(y64), postop=post, need_centroids=False)
+    assert gf._lib.last_path() == "tcgen05_tf32"
+    check_close(out, ref_out.permute(0, 2, 3, 1), "tcgen05_tf32", "torgb-epilogue/out", tol_scale=2.0)
+    check_close(rgb_out, ref_rgb, "tcgen05_tf32", "torgb-epilogue/rgb", tol_scale=2.0)
+    # the CUDA-core path refuses the fusion loudly
+    attn32 = make_layer(gf, cuda_dev, C, D, k, p, integration, "layer", duplex, True, True, w)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="tRGB"):
+        attn32(x64.permute(0, 2, 3, 1).contiguous().float().to(cuda_dev), f(y64), postop=post, need_centroids=False)
+
+
+def test_torgb_epilogue_matches_torgb_kernel(gf, cuda_dev, monkeypatch):
+    """Generator with the tRGB fused into the attention store (default) vs the separate tRGB kernel: same image up to fp32 summation order."""
+    G = _benchmark_generator(gf, cuda_dev, 128, 16, False)
+    z = torch.randn(2, 17, 32, generator=torch.Generator().manual_seed(5)).to(cuda_dev)
+    with torch.no_grad():
+        G(z)
+        l0 = gf._lib.launch_count(); a = G(z).clone(); n_fused = gf._lib.launch_count() - l0
+        monkeypatch.setenv("GF_NO_TORGB_EPILOGUE", "1")
+        l0 = gf._lib.launch_count(); b = G(z).clone(); n_sep = gf._lib.launch_count() - l0
+    assert n_fused < n_sep
+    assert (a - b).abs().max() <= 2e-5 * max(1.0, b.abs().max().item())

@@ -28,13 +28,13 @@ def test_header_symbols_are_exported(gf):
         assert declared == sorted(exports), (header, declared, exports)
         for name in declared:
             assert hasattr(lib, name), f"{name} declared in include/{header} but not exported by libgf_attn.so"
-    assert lib.gf_attn_abi_version() == 1
+    assert lib.gf_attn_abi_version() == 2
 
 
 def test_struct_layouts_match_c(gf):
     assert ctypes.sizeof(gf._lib.GfAttnDesc) == 12 * 4
     assert ctypes.sizeof(gf._lib.GfAttnWeights) == 20 * ctypes.sizeof(ctypes.c_void_p)
-    assert ctypes.sizeof(gf._lib.GfAttnPostop) == 3 * 8 + 8 + 4 + 4 + 2 * 8 + 2 * 4
+    assert ctypes.sizeof(gf._lib.GfAttnPostop) == 3 * 8 + 8 + 4 + 4 + 2 * 8 + 2 * 4 + 3 * 8
 
 
 def test_sizes_and_validation(gf):
