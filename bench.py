@@ -267,23 +267,31 @@ def train_probe(device, rank, world, steps: int = 3, warmup: int = 1, B: int = 3
     torch.cuda.synchronize()
     dist_mod.barrier()
     t = dist_mod.max_over_ranks(e0.elapsed_time(e1) * 1e-3, device=device)
-    # the collective on its own (inside a replayed graph it cannot be bracketed by events): both networks' flat buffers
-    ar_ms, ar_bytes = 0.0, 0.0
+    # the collective on its own (inside a replayed graph it cannot be bracketed by events): every bucket of both networks' flat
+    # gradient buffers, back to back on the communication stream -- in the step these overlap the backward pass
+    ar_ms, ar_bytes, n_buckets = 0.0, 0.0, 0
     if world > 1:
-        for p in list(G.parameters()) + list(D.parameters()):
-            if p.grad is None:
-                p.grad = torch.zeros_like(p)
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        dist_mod.barrier()
-        a0.record()
-        ar_bytes = dist_mod.allreduce_gradients(D.parameters(), world) + dist_mod.allreduce_gradients(G.parameters(), world)
-        a1.record()
-        torch.cuda.synchronize()
-        ar_ms = a0.elapsed_time(a1) * steps
+        bks = [trainer.buckets_d, trainer.buckets_g]
+        n_buckets = sum(len(b.buckets) for b in bks)
+        for rep in range(2):                          # first pass warms NCCL up for these message sizes
+            dist_mod.barrier()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            ar_bytes = 0.0
+            for b in bks:
+                b._active = True
+                b._pending = [1] * len(b.buckets)     # nothing pending from hooks: finish() reduces every bucket
+                ar_bytes += b.finish()
+            a1.record()
+            torch.cuda.synchronize()
+            ar_ms = a0.elapsed_time(a1)
     out = {"workload": "BASELINE configs[3]: 256x256 G+D training step (logistic NS + lazy R1, Adam, EMA), synthetic reals, "
                        f"batch {B}/GPU, data-parallel dp{world}", "images_per_s": world * B * steps / t, "ms_per_step": t / steps * 1e3,
-           "global_batch": world * B, "steps": steps, "warmup": warmup, "allreduce_ms_per_step": ar_ms / steps,
-           "allreduce_bytes_per_step": ar_bytes, "loss_g": last.loss_g, "loss_d": last.loss_d,
+           "global_batch": world * B, "steps": steps, "warmup": warmup, "allreduce_ms_per_step": ar_ms,
+           "allreduce_bytes_per_step": ar_bytes, "allreduce_buckets": n_buckets,
+           "allreduce_note": "bucketed NCCL all-reduce (ReduceOp.AVG) of both networks' flat gradient buffers, timed back to back on its own; "
+                             "inside the step the buckets are launched from backward hooks on a communication stream and overlap backward", "loss_g": last.loss_g, "loss_d": last.loss_d,
            "peak_mem_gb": torch.cuda.max_memory_allocated(device) / 2 ** 30,
            "cuda_graph": bool(graphed),
            "backward": "attention: CUDA forward + hand-written stage-T backward kernel (gf_attn_simplex_bwd) + batched GEMMs for the "

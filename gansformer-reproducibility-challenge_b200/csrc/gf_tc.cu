@@ -425,6 +425,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     // post-op noise: one value per token, fetched a tile ahead (its L2 latency sat on the epilogue's critical path)
     const bool has_noise = P.has_post && P.pnoise != nullptr;
     const float pstr = (has_noise && P.pstrength) ? __ldg(P.pstrength) : 1.f;
+    const float act_a = P.pact == 1 ? 0.6f * P.pgain : P.pgain, act_b = P.pact == 1 ? 0.4f * P.pgain : 0.f;
     const float rgb_b0 = (has_rgb && P.rgb_bias) ? __ldg(P.rgb_bias) : 0.f, rgb_b1 = (has_rgb && P.rgb_bias) ? __ldg(P.rgb_bias + 1) : 0.f,
                 rgb_b2 = (has_rgb && P.rgb_bias) ? __ldg(P.rgb_bias + 2) : 0.f;
     float pnz_next = 0.f;
@@ -433,7 +434,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const int b = b_next;
       const int buf = (int)(it & 1);
       const uint32_t bphase = (it >> 1) & 1u;
-      const float pnz = pnz_next * pstr;             // post-op: per-token noise value
+      const float pnz_t = pnz_next * pstr;           // post-op: per-token noise value (0 without noise / post-op)
       const int t_cur = t_in_img;                      // this tile's index inside its image
       float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;         // fused tRGB: this thread's share (its group's slabs) of the token's 3 sums
       const bool img_first = t_in_img == 0 || tile == tile_beg;
@@ -481,19 +482,21 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           float4 x = *px;
           if (isc) { const float4 d = isc[c]; x.x *= d.x; x.y *= d.y; x.z *= d.z; x.w *= d.w; }
           float xn0 = fmaf(x.x, rstd, mr), xn1 = fmaf(x.y, rstd, mr), xn2 = fmaf(x.z, rstd, mr), xn3 = fmaf(x.w, rstd, mr);
+          // modulation with the post-op's per-token noise riding on the same FMA (pnz_t = 0 without a post-op)
           if constexpr (MODE == GF_INT_MUL) {
-            x.x = xn0 * gv[c * 4 + 0]; x.y = xn1 * gv[c * 4 + 1]; x.z = xn2 * gv[c * 4 + 2]; x.w = xn3 * gv[c * 4 + 3];
+            x.x = fmaf(xn0, gv[c * 4 + 0], pnz_t); x.y = fmaf(xn1, gv[c * 4 + 1], pnz_t); x.z = fmaf(xn2, gv[c * 4 + 2], pnz_t); x.w = fmaf(xn3, gv[c * 4 + 3], pnz_t);
           } else if constexpr (MODE == GF_INT_ADD) {
-            x.x = xn0 + gv[c * 4 + 0]; x.y = xn1 + gv[c * 4 + 1]; x.z = xn2 + gv[c * 4 + 2]; x.w = xn3 + gv[c * 4 + 3];
+            x.x = (xn0 + pnz_t) + gv[c * 4 + 0]; x.y = (xn1 + pnz_t) + gv[c * 4 + 1]; x.z = (xn2 + pnz_t) + gv[c * 4 + 2]; x.w = (xn3 + pnz_t) + gv[c * 4 + 3];
           } else {
-            x.x = fmaf(xn0, gv[c * 4 + 0], bv[c * 4 + 0]); x.y = fmaf(xn1, gv[c * 4 + 1], bv[c * 4 + 1]);
-            x.z = fmaf(xn2, gv[c * 4 + 2], bv[c * 4 + 2]); x.w = fmaf(xn3, gv[c * 4 + 3], bv[c * 4 + 3]);
+            x.x = fmaf(xn0, gv[c * 4 + 0], bv[c * 4 + 0] + pnz_t); x.y = fmaf(xn1, gv[c * 4 + 1], bv[c * 4 + 1] + pnz_t);
+            x.z = fmaf(xn2, gv[c * 4 + 2], bv[c * 4 + 2] + pnz_t); x.w = fmaf(xn3, gv[c * 4 + 3], bv[c * 4 + 3] + pnz_t);
           }
           if (P.has_post) {
             const float4 pb = *reinterpret_cast<const float4*>(pbias_s + s * SLAB_CH + c * 4);   // broadcast read
-            x.x += pnz + pb.x; x.y += pnz + pb.y; x.z += pnz + pb.z; x.w += pnz + pb.w;
-            if (P.pact == 1) { x.x = fmaxf(x.x, 0.2f * x.x); x.y = fmaxf(x.y, 0.2f * x.y); x.z = fmaxf(x.z, 0.2f * x.z); x.w = fmaxf(x.w, 0.2f * x.w); }
-            x.x *= P.pgain; x.y *= P.pgain; x.z *= P.pgain; x.w *= P.pgain;
+            x.x += pb.x; x.y += pb.y; x.z += pb.z; x.w += pb.w;
+            // gain * leaky-ReLU(v) = v * (0.6 gain) + |v| * (0.4 gain)  (linear: act_a = gain, act_b = 0): two instructions
+            x.x = fmaf(fabsf(x.x), act_b, x.x * act_a); x.y = fmaf(fabsf(x.y), act_b, x.y * act_a);
+            x.z = fmaf(fabsf(x.z), act_b, x.z * act_a); x.w = fmaf(fabsf(x.w), act_b, x.w * act_a);
             if (has_rgb) {                                   // tRGB reads the layer output proper: before the next layer's style scale
               const float4 w0 = wrv[c], w1 = wrv[(C >> 2) + c], w2 = wrv[2 * (C >> 2) + c];       // shared-memory broadcasts
               rgb0 = fmaf(x.x, w0.x, fmaf(x.y, w0.y, fmaf(x.z, w0.z, fmaf(x.w, w0.w, rgb0))));
