@@ -115,7 +115,7 @@ centroid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   const uint32_t s_ring2 = s_ring1 + (uint32_t)nst1 * SLAB_BYTES;
   Bars* bars = reinterpret_cast<Bars*>(smem + CF::OFF_BARS);
   const uint32_t s_bars = s_base + CF::OFF_BARS;
-  auto bar = [&](const uint64_t* p) -> uint32_t { return s_bars + (uint32_t)((const uint8_t*)p - (const uint8_t*)bars); };
+  auto bar = [&](const uint64_t* p) -> uint32_t { return smem_u32(p); };
 #ifdef GF_DEBUG_WATCHDOG
 #ifdef GF_DEBUG_WATCHDOG     // bring-up builds only: record where a barrier wait timed out (tools/hang_debug.py)
   if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && g_dbg_buf) g_dbg_buf[1] = s_bars;
