@@ -18,10 +18,11 @@ INTEGRATION = {"mul": 0, "add": 1, "both": 2}
 FLAG_FP32_EXACT = 1
 FLAG_CENTROIDS_IN = 2
 FLAG_TABLES_READY = 4
+FLAG_IMG2LTNT = 8
 PATH_NAMES = {0: "none", 1: "simt_fp32", 2: "tcgen05_tf32"}
 
 WEIGHT_FIELDS = ("wq", "bq", "wpq", "wk", "bk", "wpk", "wv", "bv", "wo", "bo", "pos_latent",
-                 "wq2", "bq2", "wpq2", "wk2", "bk2", "wpk2", "wv2", "bv2", "wkc")
+                 "wq2", "bq2", "wpq2", "wk2", "bk2", "wpk2", "wv2", "bv2", "wkc", "wcq", "wi2l", "bi2l")
 
 # every symbol include/gf_attn.h declares (tests check the .so exports each of them)
 EXPORTS = ("gf_attn_abi_version", "gf_last_error", "gf_attn_last_path", "gf_attn_folded_floats",
@@ -124,7 +125,7 @@ def make_desc(B, H, W, C, k, D, *, heads=1, norm="layer", integration="mul", pos
         raise ValueError(f"unknown norm {norm!r}")
     if integration not in INTEGRATION:
         raise ValueError(f"unknown integration {integration!r}")
-    return GfAttnDesc(B, H, W, C, k, D, heads, NORM[norm], INTEGRATION[integration], pos_dim, int(bool(duplex)), flags)
+    return GfAttnDesc(B, H, W, C, k, D, heads, NORM[norm], INTEGRATION[integration], pos_dim, int(duplex), flags)    # duplex: 0 or the number of k-means iterations
 
 
 def folded_floats(desc: GfAttnDesc) -> int:

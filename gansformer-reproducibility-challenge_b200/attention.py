@@ -26,9 +26,12 @@ from ._state import weights_epoch
 
 SIMPLEX_PARAMS = ("wq", "bq", "wpq", "wk", "bk", "wpk", "wv", "bv", "wo", "bo", "pos_latent")
 DUPLEX_PARAMS = ("wq2", "bq2", "wpq2", "wk2", "bk2", "wpk2", "wv2", "bv2", "wkc")
+KMEANS_PARAMS = ("wcq",)                 # kmeans_iters > 1: centroid -> query projection of the later iterations
+IMG2LTNT_PARAMS = ("wi2l", "bi2l")       # g_img2ltnt: centroid -> latent gain
 
 
-def param_shapes(dim: int, latent_dim: int, components_num: int, pos_dim: int, integration: str, duplex: bool):
+def param_shapes(dim: int, latent_dim: int, components_num: int, pos_dim: int, integration: str, duplex: bool,
+                 kmeans_iters: int = 1, img2ltnt: bool = False):
     """Raw parameter shapes, [fan_in, fan_out]; equalised-LR scaling happens inside the library."""
     C, D, k, p = dim, latent_dim, components_num, pos_dim
     cout = 2 * C if integration == "both" else C
@@ -37,6 +40,10 @@ def param_shapes(dim: int, latent_dim: int, components_num: int, pos_dim: int, i
     if duplex:
         shapes.update({"wq2": (D, C), "bq2": (C,), "wpq2": (p, C), "wk2": (C, C), "bk2": (C,), "wpk2": (p, C),
                        "wv2": (C, C), "bv2": (C,), "wkc": (C, C)})
+        if kmeans_iters > 1:
+            shapes["wcq"] = (C, C)
+        if img2ltnt:
+            shapes.update({"wi2l": (C, D), "bi2l": (D,)})
     return shapes
 
 
@@ -140,10 +147,11 @@ def _plan_call(lib, shape, y: torch.Tensor, params: Dict[str, torch.Tensor], pla
     desc = _lib.make_desc(B, H, W, C, k, D, heads=num_heads, norm=norm, integration=integration, pos_dim=pos_dim,
                           duplex=duplex, flags=flags)
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    names = SIMPLEX_PARAMS + (DUPLEX_PARAMS if duplex else ())
+    names = SIMPLEX_PARAMS + (DUPLEX_PARAMS if duplex else ()) + (KMEANS_PARAMS if int(duplex) > 1 else ()) \
+        + (IMG2LTNT_PARAMS if (duplex and flags & _lib.FLAG_IMG2LTNT) else ())
     if weights_version is None:
         weights_version = tuple((params[n].data_ptr(), params[n]._version) for n in names)
-    fkey = (H, W, k, D, C, pos_dim, integration, duplex, str(dev), weights_version, weights_epoch())
+    fkey = (H, W, k, D, C, pos_dim, integration, int(duplex), flags & _lib.FLAG_IMG2LTNT, str(dev), weights_version, weights_epoch())
     if plan.folded is None or plan.folded_key != fkey or FORCE_REFOLD:
         nfl = _lib.folded_floats(desc)
         if plan.folded is None or plan.folded.numel() != nfl or plan.folded.device != dev:
@@ -156,7 +164,7 @@ def _plan_call(lib, shape, y: torch.Tensor, params: Dict[str, torch.Tensor], pla
         _lib.check(lib.gf_attn_fold_weights(ctypes.byref(desc), ctypes.byref(wstruct), plan.folded.data_ptr(), stream),
                    "gf_attn_fold_weights")
         plan.folded_key = fkey
-    wkey = (B, H, W, C, k, D, pos_dim, integration, norm, duplex, str(dev))
+    wkey = (B, H, W, C, k, D, pos_dim, integration, norm, int(duplex), flags & _lib.FLAG_IMG2LTNT, str(dev))
     ws = plan.ws.get(wkey)
     if ws is None:
         ws = torch.empty(_lib.workspace_bytes(desc), dtype=torch.uint8, device=dev)
@@ -170,8 +178,10 @@ def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[s
                                 centroids: Optional[torch.Tensor] = None, exact_fp32: bool = False,
                                 out: Optional[torch.Tensor] = None, weights_version=None, postop: Optional[dict] = None,
                                 stage: str = "all", x_shape: Optional[Tuple[int, int, int, int]] = None,
-                                need_centroids: bool = True):
+                                need_centroids: bool = True, img2ltnt: bool = False):
     """x [B,H,W,C] channels-last fp32 (CUDA), y [B,k,D].  Returns (x', att [B,k,H,W] | None, centroids | None).
+
+    duplex: False / 0 = simplex; True / n >= 1 = duplex with n k-means iterations (kmeans_iters).  img2ltnt: g_img2ltnt.
 
     postop (optional): dict(bias [C] | None, noise [H*W] or [B,H*W] | None, strength 0-d tensor | None, act 'lrelu' |
     'linear', gain float, in_scale [B,C] | None, post_scale [B,C] | None, rgb_w [B,3,C] + rgb_out [B,3,H,W] (+ rgb_bias [3]))
@@ -201,7 +211,8 @@ def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[s
         raise ValueError(f"y must be [B, k, D] with B={B}, got {tuple(y.shape)}")
     k = y.shape[1]
     flags = ((_lib.FLAG_FP32_EXACT if exact_fp32 else 0) | (_lib.FLAG_CENTROIDS_IN if (duplex and centroids is not None) else 0)
-             | (_lib.FLAG_TABLES_READY if (duplex and stage == "token") else 0))
+             | (_lib.FLAG_TABLES_READY if (duplex and stage == "token") else 0)
+             | (_lib.FLAG_IMG2LTNT if (duplex and img2ltnt) else 0))
 
     with torch.cuda.device(dev):
         desc, ws, stream = _plan_call(lib, (B, H, W, C), y, params, plan, integration=integration, norm=norm, duplex=duplex,
@@ -255,7 +266,7 @@ def tc_eligible(module: "BipartiteAttention", shape, k: int) -> bool:
     """Will stage T of this layer call run on the tcgen05 kernel (gf_attn_tc_eligible)?  Decides fusions only that kernel serves."""
     B, H, W, C = shape
     desc = _lib.make_desc(B, H, W, C, k, module.latent_dim, heads=module.num_heads, norm=module.norm, integration=module.integration,
-                          pos_dim=module.pos_dim if module.use_pos else 0, duplex=module.duplex,
+                          pos_dim=module.pos_dim if module.use_pos else 0, duplex=module.kmeans_iters if module.duplex else 0,
                           flags=_lib.FLAG_FP32_EXACT if module.exact_fp32 else 0)
     rc = _lib.load().gf_attn_tc_eligible(ctypes.byref(desc))
     if rc < 0:
@@ -287,9 +298,9 @@ def prologue_batch(items) -> None:
         stream = None
         for i, (m, y, shape, in_scale) in enumerate(items):
             _check_tensor(y, "y", dev)
-            flags = _lib.FLAG_FP32_EXACT if m.exact_fp32 else 0
+            flags = (_lib.FLAG_FP32_EXACT if m.exact_fp32 else 0) | (_lib.FLAG_IMG2LTNT if (m.duplex and m.img2ltnt) else 0)
             desc, ws, stream = _plan_call(lib, tuple(shape), y, m.param_dict(), m._plan, integration=m.integration, norm=m.norm,
-                                          duplex=m.duplex, num_heads=m.num_heads, use_pos=m.use_pos, flags=flags)
+                                          duplex=m.kmeans_iters if m.duplex else 0, num_heads=m.num_heads, use_pos=m.use_pos, flags=flags)
             pst, kp = _make_postop(dict(in_scale=in_scale) if in_scale is not None else None, shape[0], shape[1], shape[2], shape[3], dev)
             descs.append(desc)
             keep.extend(kp)
@@ -317,17 +328,20 @@ class BipartiteAttention(nn.Module):
 
     def __init__(self, dim: int, latent_dim: int, components_num: int, pos_dim: Optional[int] = None,
                  num_heads: int = 1, integration: str = "mul", norm: Optional[str] = "layer", kmeans: bool = False,
-                 kmeans_iters: int = 1, use_pos: bool = True, att_dp: float = 0.0, exact_fp32: bool = False):
+                 kmeans_iters: int = 1, use_pos: bool = True, att_dp: float = 0.0, exact_fp32: bool = False, img2ltnt: bool = False):
         super().__init__()
-        if kmeans_iters != 1:
-            raise NotImplementedError("kmeans_iters != 1 is not implemented (SURVEY A.4 item 3 freezes 1)")
+        if kmeans_iters < 1 or kmeans_iters > 16:
+            raise ValueError("kmeans_iters must be in 1..16")
+        if (kmeans_iters != 1 or img2ltnt) and not kmeans:
+            raise ValueError("kmeans_iters > 1 / img2ltnt need kmeans=True (duplex attention)")
         if att_dp != 0.0:
             raise NotImplementedError("attention dropout is not implemented in the fused kernel (inference path: 0)")
         self.dim, self.latent_dim, self.components_num = dim, latent_dim, components_num
         self.pos_dim = latent_dim if pos_dim is None else pos_dim
         self.num_heads, self.integration, self.norm = num_heads, integration, norm
         self.duplex, self.use_pos, self.exact_fp32 = bool(kmeans), use_pos, exact_fp32
-        for name, shape in param_shapes(dim, latent_dim, components_num, self.pos_dim, integration, self.duplex).items():
+        self.kmeans_iters, self.img2ltnt = int(kmeans_iters), bool(img2ltnt)
+        for name, shape in param_shapes(dim, latent_dim, components_num, self.pos_dim, integration, self.duplex, self.kmeans_iters, self.img2ltnt).items():
             init = torch.zeros(shape) if name.startswith("b") else torch.randn(shape)
             self.register_parameter(name, nn.Parameter(init))
         self._plan = _Plan()
@@ -346,10 +360,10 @@ class BipartiteAttention(nn.Module):
             from .autograd import bipartite_attention_autograd
             return bipartite_attention_autograd(self, x, y, centroids, return_att)
         return bipartite_attention_forward(x, y, self.param_dict(), self._plan, integration=self.integration,
-                                           norm=self.norm, duplex=self.duplex, num_heads=self.num_heads,
+                                           norm=self.norm, duplex=self.kmeans_iters if self.duplex else 0, num_heads=self.num_heads,
                                            use_pos=self.use_pos, return_att=return_att, centroids=centroids,
                                            exact_fp32=self.exact_fp32, out=out, postop=postop, stage=stage,
-                                           need_centroids=need_centroids)
+                                           need_centroids=need_centroids, img2ltnt=self.img2ltnt)
 
     @torch.no_grad()
     def prepare(self, y: torch.Tensor, x_shape: Tuple[int, int, int, int], in_scale: Optional[torch.Tensor] = None):
@@ -357,7 +371,7 @@ class BipartiteAttention(nn.Module):
         (and the demodulation scale folded into K') only, so the generator runs them for every layer up front on a side stream."""
         post = dict(in_scale=in_scale) if in_scale is not None else None
         bipartite_attention_forward(None, y, self.param_dict(), self._plan, integration=self.integration, norm=self.norm,
-                                    duplex=self.duplex, num_heads=self.num_heads, use_pos=self.use_pos,
+                                    duplex=self.kmeans_iters if self.duplex else 0, num_heads=self.num_heads, use_pos=self.use_pos,
                                     exact_fp32=self.exact_fp32, postop=post, stage="prologue", x_shape=x_shape)
 
 
@@ -374,8 +388,8 @@ def transformer_layer(dim: int, pos_dim: int, from_tensor: torch.Tensor, to_tens
     from_tensor [B, from_len, dim] (grid tokens, row-major over grid_shape=(H, W)); to_tensor [B, to_len, D].
     Returns (from_tensor' [B, from_len, dim], att_probs [B, from_len, to_len], att_vars).
     """
-    if att_dp != 0.0 or kmeans_iters != 1:
-        raise NotImplementedError("att_dp != 0 / kmeans_iters != 1 are not implemented")
+    if att_dp != 0.0:
+        raise NotImplementedError("att_dp != 0 is not implemented")
     H, W = grid_shape
     B = from_tensor.shape[0]
     if from_len != H * W or from_tensor.shape[1] != from_len or from_tensor.shape[2] != dim or to_tensor.shape[1] != to_len:
@@ -387,8 +401,9 @@ def transformer_layer(dim: int, pos_dim: int, from_tensor: torch.Tensor, to_tens
     cen_in = att_vars.get("centroids") if (kmeans and iterative) else None
     x = from_tensor.reshape(B, H, W, dim)
     out, att, cen = bipartite_attention_forward(x, to_tensor, params, plan, integration=integration, norm=norm,
-                                                duplex=kmeans, num_heads=num_heads, use_pos=use_pos, return_att=True,
-                                                centroids=cen_in, exact_fp32=exact_fp32)
+                                                duplex=(kmeans_iters if kmeans else 0), num_heads=num_heads, use_pos=use_pos,
+                                                return_att=True, centroids=cen_in, exact_fp32=exact_fp32,
+                                                img2ltnt=bool(kmeans and "wi2l" in params))
     if cen is not None:
         att_vars["centroids"] = cen
     att_probs = att.permute(0, 2, 3, 1).reshape(B, from_len, to_len)

@@ -24,7 +24,7 @@ def _axis(length, dim, device):
     return torch.cat([torch.sin(ang), torch.cos(ang)], dim=1)            # float64: callers cast to their dtype
 
 
-def composite_forward(x, y, p, *, integration, norm, duplex, use_pos, centroids=None):
+def composite_forward(x, y, p, *, integration, norm, duplex, use_pos, centroids=None, kmeans_iters=1, img2ltnt=False):
     """Same math as the kernels, in torch ops (direct op order), on whatever device x lives on.  x [B,H,W,C]."""
     B, H, W, C = x.shape
     n = H * W
@@ -47,8 +47,13 @@ def composite_forward(x, y, p, *, integration, norm, duplex, use_pos, centroids=
                 Qy = Qy + (Pl @ _e(p["wpq2"]))[None]
                 Kx = Kx + (Pg @ _e(p["wpk2"]))[None]
             Vx = X @ _e(p["wv2"]) + p["bv2"]
-            A = torch.softmax((Qy @ Kx.transpose(1, 2)) * s, dim=2)
-            cen = A @ Vx
+            for it in range(max(1, kmeans_iters)):
+                if it > 0:
+                    Qy = cen @ _e(p["wcq"]) + p["bq2"]
+                    if use_pos:
+                        Qy = Qy + (Pl @ _e(p["wpq2"]))[None]
+                A = torch.softmax((Qy @ Kx.transpose(1, 2)) * s, dim=2)
+                cen = A @ Vx
         K = cen @ _e(p["wkc"]) + p["bk"]
     else:
         K = y @ _e(p["wk"]) + p["bk"]
@@ -56,7 +61,11 @@ def composite_forward(x, y, p, *, integration, norm, duplex, use_pos, centroids=
     if use_pos:
         K = K + (Pl @ _e(p["wpk"]))[None]
         Q = Q + (Pg @ _e(p["wpq"]))[None]
-    V = y @ _e(p["wv"]) + p["bv"]
+    yv = y
+    if duplex and img2ltnt:
+        ym = y.mean(dim=2, keepdim=True)
+        yv = (y - ym) * torch.rsqrt(((y - ym) ** 2).mean(dim=2, keepdim=True) + 1e-8) * (1.0 + cen @ _e(p["wi2l"]) + p["bi2l"])
+    V = yv @ _e(p["wv"]) + p["bv"]
     P = torch.softmax((Q @ K.transpose(1, 2)) * s, dim=2)
     ctl = (P @ V) @ _e(p["wo"]) + p["bo"]
     if norm == "layer":
@@ -126,9 +135,9 @@ class _FusedAttention(torch.autograd.Function):
         pd = dict(zip(names, params))
         out, att, cen = bipartite_attention_forward(
             x.detach(), y.detach(), {k: v.detach() for k, v in pd.items()}, module._plan,
-            integration=module.integration, norm=module.norm, duplex=module.duplex, num_heads=module.num_heads,
+            integration=module.integration, norm=module.norm, duplex=module.kmeans_iters if module.duplex else 0, num_heads=module.num_heads,
             use_pos=module.use_pos, return_att=return_att, centroids=centroids, exact_fp32=module.exact_fp32,
-            weights_version=tuple((v.data_ptr(), v._version) for v in params))
+            weights_version=tuple((v.data_ptr(), v._version) for v in params), img2ltnt=module.img2ltnt)
         ctx.module, ctx.names, ctx.centroids = module, names, centroids
         ctx.save_for_backward(x, y, *params)
         ctx.mark_non_differentiable(*[t for t in (att, cen) if t is not None])
@@ -145,7 +154,8 @@ class _FusedAttention(torch.autograd.Function):
             ys = y.detach().requires_grad_(True)
             ps = [p.detach().requires_grad_(True) for p in params]
             out, _ = composite_forward(xs, ys, dict(zip(ctx.names, ps)), integration=m.integration, norm=m.norm,
-                                       duplex=m.duplex, use_pos=m.use_pos, centroids=ctx.centroids)
+                                       duplex=m.duplex, use_pos=m.use_pos, centroids=ctx.centroids, kmeans_iters=m.kmeans_iters,
+                                       img2ltnt=m.img2ltnt)
             grads = torch.autograd.grad(out, [xs, ys, *ps], g_out, allow_unused=True)
         return (None, None, None, None, *grads)
 

@@ -186,28 +186,42 @@ int gf_attn_duplex_fwd_ex(const gf_attn_desc* desc, const float* X, const float*
   if ((rc = check_device())) return rc;
   float* ws = (float*)ws_;
   cudaStream_t st = (cudaStream_t)stream;
-  if (!(desc->flags & GF_FLAG_CENTROIDS_IN)) {
+  const bool cen_in = (desc->flags & GF_FLAG_CENTROIDS_IN) != 0;
+  // explicit centroids are needed when the caller asks for them, for further k-means iterations and for g_img2ltnt; otherwise the
+  // keys are built straight from the attention-weighted means (one [B*k, C] x [C, C] product less)
+  const bool need_cen = centroids_inout != nullptr || L.iters > 1 || L.img2ltnt;
+  float* cen = centroids_inout ? centroids_inout : ws + L.w_CEN;
+  if (!cen_in) {
     // load-side scale d (x_in = x * d): pass A sees x only through x.M^T and A.x, so d is folded into M and into Xbar
     const float* isc = post ? post->in_scale : nullptr;
     const int isc_ld = post ? post->in_scale_ld : 0;
     if (!(desc->flags & GF_FLAG_TABLES_READY) && (rc = duplex_tables(L, desc, Y, folded, ws, st, isc, isc_ld))) return rc;
     const bool cen_tc = tc_centroid_supported(L, desc);
-    if (cen_tc) {
-      if ((rc = centroid_pass_tc(L, desc, X, ws, st, isc, isc_ld))) return rc;
-      if (L.nsplit_cen > 1 && (rc = centroid_merge(L, ws, st, isc, isc_ld))) return rc;   // one split: the kernel wrote Xbar itself
-      set_centroid_path(GF_PATH_TCGEN05_TF32);
-    } else {
-      if ((rc = centroid_pass_simt(L, desc, X, ws, st, isc, isc_ld))) return rc;
-      set_centroid_path(GF_PATH_SIMT_FP32);
+    for (int it = 0; it < L.iters; ++it) {
+      if (it > 0 && (rc = duplex_tables_from_centroids(L, desc, cen, Y, folded, ws, st, isc, isc_ld))) return rc;   // queries from the centroids
+      if (cen_tc) {
+        if ((rc = centroid_pass_tc(L, desc, X, ws, st, isc, isc_ld))) return rc;
+        if (L.nsplit_cen > 1 && (rc = centroid_merge(L, ws, st, isc, isc_ld))) return rc;   // one split: the kernel wrote Xbar itself
+        set_centroid_path(GF_PATH_TCGEN05_TF32);
+      } else {
+        if ((rc = centroid_pass_simt(L, desc, X, ws, st, isc, isc_ld))) return rc;
+        set_centroid_path(GF_PATH_SIMT_FP32);
+      }
+      // centroids = Xbar @ Wv2_e + bv2
+      if (need_cen && (rc = gemm(st, L.B * L.k, L.C, L.C, ws + L.w_XBAR, L.C, false, folded + L.f_WV2, L.C, false, cen, L.C, 1.f,
+                                 nullptr, 0, 1, folded + L.f_BV2, cen_tc)))
+        return rc;
     }
-    // centroids = Xbar @ Wv2_e + bv2 (skipped when the caller does not want them: the keys then come straight from Xbar)
-    if (centroids_inout && (rc = gemm(st, L.B * L.k, L.C, L.C, ws + L.w_XBAR, L.C, false, folded + L.f_WV2, L.C, false, centroids_inout, L.C, 1.f,
-                   nullptr, 0, 1, folded + L.f_BV2, cen_tc)))
-      return rc;
   }
-  // V^T depends on the latents only: duplex_tables() already built it, unless pass A was skipped (GF_FLAG_CENTROIDS_IN)
-  if ((rc = prologue(L, desc, Y, centroids_inout ? centroids_inout : ws + L.w_XBAR, L.C, folded, ws, st, post ? post->in_scale : nullptr,
-                     post ? post->in_scale_ld : 0, centroids_inout == nullptr, (desc->flags & GF_FLAG_CENTROIDS_IN) != 0)))
+  const float* Yv = Y;
+  if (L.img2ltnt) {
+    if ((rc = img2ltnt(L, Y, cen, folded, ws, st))) return rc;
+    Yv = ws + L.w_Y2;
+  }
+  // V^T depends on the latents only: duplex_tables() already built it, unless pass A was skipped or the latents were modulated
+  const bool keys_from_cen = cen_in || need_cen;
+  if ((rc = prologue(L, desc, Yv, keys_from_cen ? cen : ws + L.w_XBAR, L.C, folded, ws, st, post ? post->in_scale : nullptr,
+                     post ? post->in_scale_ld : 0, !keys_from_cen, cen_in || L.img2ltnt)))
     return rc;
   return token_pass(L, desc, X, Xout, att, ws, post, st);
 }

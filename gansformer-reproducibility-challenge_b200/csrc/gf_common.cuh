@@ -49,6 +49,9 @@ struct Layout {
   size_t w_NSCALE, w_NSHIFT, w_NPART;                 // instance/batch norm statistics
   size_t w_MALL, w_M, w_Rt2, w_Ct2, w_PART, w_XBAR;   // duplex pass A
   size_t f_AK2, f_CK2;                                // duplex: keys straight from Xbar (Wv2 and bv2 folded into AK / CK)
+  size_t f_ACQ, f_WI2L, f_BI2L;                       // kmeans_iters > 1: centroid -> pass-A query table; g_img2ltnt: centroid -> latent gain
+  size_t w_CEN, w_Y2;                                 // scratch centroids [B,k,C] (caller passed none), modulated latents [B,k,D]
+  int iters, img2ltnt;
   size_t w_total;
   int nsplit_norm, nsplit_cen;
 };
@@ -79,6 +82,9 @@ int prologue(const Layout& L, const gf_attn_desc* d, const float* Y, const float
              bool keys_from_xbar = false, bool with_v = true);
 int prologue_batch(int n, const Layout* Ls, const gf_attn_desc* const* ds, const float* const* Ys, const float* const* fs, float* const* wss,
                    const gf_attn_postop* const* posts, cudaStream_t st);
+int duplex_tables_from_centroids(const Layout& L, const gf_attn_desc* d, const float* cen, const float* Y, const float* f, float* ws,
+                                 cudaStream_t st, const float* in_scale, int in_scale_ld);
+int img2ltnt(const Layout& L, const float* Y, const float* cen, const float* f, float* ws, cudaStream_t st);
 int duplex_tables(const Layout& L, const gf_attn_desc* d, const float* Y, const float* folded, float* ws, cudaStream_t st,
                   const float* in_scale = nullptr, int in_scale_ld = 0);
 // C[M,N] = alpha * opA(A) opB(B) + E[(m % emod), n] + v[n]

@@ -20,6 +20,7 @@ int make_layout(const gf_attn_desc* d, Layout* L) {
   if (d->C % 32 != 0 || d->C > 1024) { set_error("C=%d unsupported: need C %% 32 == 0 and C <= 1024", d->C); return GF_ERR_UNSUPPORTED; }
   if (d->k > 32) { set_error("k=%d unsupported: at most 32 latents", d->k); return GF_ERR_UNSUPPORTED; }
   if (d->D > 256) { set_error("D=%d unsupported: latent size at most 256", d->D); return GF_ERR_UNSUPPORTED; }
+  if (d->duplex < 0 || d->duplex > 16) { set_error("duplex=%d: 0 (simplex) or the number of k-means iterations (1..16)", d->duplex); return GF_ERR_INVALID; }
   if (d->heads != 1) { set_error("num_heads=%d unsupported: this build implements 1 head", d->heads); return GF_ERR_UNSUPPORTED; }
   if (d->norm < GF_NORM_NONE || d->norm > GF_NORM_BATCH) { set_error("bad norm %d", d->norm); return GF_ERR_INVALID; }
   if (d->integration < GF_INT_MUL || d->integration > GF_INT_BOTH) { set_error("bad integration %d", d->integration); return GF_ERR_INVALID; }
@@ -55,9 +56,14 @@ int make_layout(const gf_attn_desc* d, Layout* L) {
     l.f_CM = take(k * LDK);
     l.f_MFOLD = take(C * LDK);
     l.f_QCONST = take(k * C);
+    l.f_ACQ = d->duplex > 1 ? take(C * LDK) : 0;
+    l.f_WI2L = (d->flags & GF_FLAG_IMG2LTNT) ? take(C * D) : 0;
+    l.f_BI2L = (d->flags & GF_FLAG_IMG2LTNT) ? take(D) : 0;
   } else {
-    l.f_WV2 = l.f_BV2 = l.f_AM = l.f_CM = l.f_MFOLD = l.f_QCONST = l.f_AK2 = l.f_CK2 = 0;
+    l.f_WV2 = l.f_BV2 = l.f_AM = l.f_CM = l.f_MFOLD = l.f_QCONST = l.f_AK2 = l.f_CK2 = l.f_ACQ = l.f_WI2L = l.f_BI2L = 0;
   }
+  l.iters = d->duplex;
+  l.img2ltnt = (d->duplex && (d->flags & GF_FLAG_IMG2LTNT)) ? 1 : 0;
   l.f_total = o;
 
   // statistics / centroid splits: about two waves of CTAs over the device's SMs
@@ -104,8 +110,10 @@ int make_layout(const gf_attn_desc* d, Layout* L) {
     l.w_Ct2 = take(B * l.W * KP);
     l.w_PART = take(B * (size_t)l.nsplit_cen * KP * (C + 4));
     l.w_XBAR = take(B * k * C);
+    l.w_CEN = take(B * k * C);
+    l.w_Y2 = take(B * k * D);
   } else {
-    l.w_MALL = l.w_M = l.w_Rt2 = l.w_Ct2 = l.w_PART = l.w_XBAR = 0;
+    l.w_MALL = l.w_M = l.w_Rt2 = l.w_Ct2 = l.w_PART = l.w_XBAR = l.w_CEN = l.w_Y2 = 0;
   }
   l.w_total = o;
   return GF_OK;
@@ -324,6 +332,17 @@ int fold_weights(const Layout& L, const gf_attn_desc* d, const gf_attn_weights* 
     if ((rc = gemm(st, k, C, pos ? p : 0, w->pos_latent, p, false, w->wpq2, C, false, f + L.f_QCONST, C, rp, nullptr, 0, 1, w->bq2))) return rc;
     if ((rc = gemm(st, D, LDK, C, w->wq2, C, false, f + L.f_MFOLD, LDK, false, f + L.f_AM, LDK, rD))) return rc;
     if ((rc = gemm(st, k, LDK, C, f + L.f_QCONST, C, false, f + L.f_MFOLD, LDK, false, f + L.f_CM, LDK, 1.f))) return rc;
+    if (L.iters > 1) {          // k-means iterations >= 2: queries from the centroids, M = Cen (wcq_e mfold) + CM
+      if (!w->wcq) { set_error("fold_weights: desc.duplex > 1 needs wcq"); return GF_ERR_INVALID; }
+      if ((rc = gemm(st, C, LDK, C, w->wcq, C, false, f + L.f_MFOLD, LDK, false, f + L.f_ACQ, LDK, rC))) return rc;
+    }
+    if (L.img2ltnt) {
+      if (!w->wi2l || !w->bi2l) { set_error("fold_weights: GF_FLAG_IMG2LTNT needs wi2l and bi2l"); return GF_ERR_INVALID; }
+      scale_copy_kernel<<<blocks_for((size_t)C * D), 256, 0, st>>>(f + L.f_WI2L, w->wi2l, (size_t)C * D, rC, 0.f, 0);
+      GF_LAUNCH_OK();
+      scale_copy_kernel<<<blocks_for(D), 256, 0, st>>>(f + L.f_BI2L, w->bi2l, D, 1.f, 0.f, 0);
+      GF_LAUNCH_OK();
+    }
   } else {
     if ((rc = gemm(st, D, LDK, C, w->wk, C, false, f + L.f_QFOLD, LDK, false, f + L.f_AK, LDK, rD))) return rc;
   }
@@ -688,6 +707,54 @@ int duplex_tables(const Layout& L, const gf_attn_desc* d, const float* Y, const 
   stage_i_fill(batch.job[0], L, Y, f + L.f_AM, f + L.f_CM, f + L.f_AV, f + L.f_CV, f, ws + L.w_M, ws + L.w_Vt, ws + L.w_Rt2, ws + L.w_Ct2,
                in_scale, in_scale_ld, tf32, tf32_v);
   return stage_i_launch(batch, L.B, st);
+}
+
+// k-means iteration >= 2: pass-A query tables from the previous centroids (inner dimension C: tensor cores)
+int duplex_tables_from_centroids(const Layout& L, const gf_attn_desc* d, const float* cen, const float* Y, const float* f, float* ws,
+                                 cudaStream_t st, const float* in_scale, int in_scale_ld) {
+  int rc;
+  const int tf32 = tc_centroid_supported(L, d) ? 1 : 0;
+  if ((rc = gemm(st, L.B * L.k, L.LDK, L.C, cen, L.C, false, f + L.f_ACQ, L.LDK, false, ws + L.w_MALL, L.LDK, 1.f,
+                 f + L.f_CM, L.LDK, L.k, nullptr, tf32 != 0)))
+    return rc;
+  const int npos = ((L.H + L.W) * L.KP + 1023) / 1024;
+  const int nblk = npos + (L.KP * L.C + 256 * 8 - 1) / (256 * 8);
+  finalize_kernel<<<dim3(L.B, nblk), 256, 0, st>>>(ws + L.w_MALL, Y, nullptr, nullptr, f + L.f_ROW, f + L.f_COL,
+                                                   ws + L.w_M, nullptr, ws + L.w_Rt2, ws + L.w_Ct2,
+                                                   L.H, L.W, L.C, L.k, L.D, L.p, L.KP, L.Cout, L.LDK, tf32, npos, in_scale, in_scale_ld);
+  GF_LAUNCH_OK();
+  return GF_OK;
+}
+
+// g_img2ltnt: Y2[r, :] = LN(Y[r, :]) * (1 + Cen[r, :] . WI2L + BI2L), one warp per latent row r = b * k + j
+__global__ void __launch_bounds__(128) img2ltnt_kernel(const float* __restrict__ Y, const float* __restrict__ cen, const float* __restrict__ Wi,
+                                                       const float* __restrict__ bi, float* __restrict__ Y2, int rows, int C, int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + warp;
+  if (r >= rows) return;
+  const float* y = Y + (size_t)r * D;
+  float s = 0.f, ss = 0.f;
+  for (int d0 = lane; d0 < D; d0 += 32) s += y[d0];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mu = s / (float)D;
+  for (int d0 = lane; d0 < D; d0 += 32) { const float t = y[d0] - mu; ss = fmaf(t, t, ss); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss / (float)D + 1e-8f);
+  const float* c = cen + (size_t)r * C;
+  for (int d0 = lane; d0 < D; d0 += 32) {
+    float acc = bi[d0];
+    for (int cc = 0; cc < C; ++cc) acc = fmaf(c[cc], Wi[(size_t)cc * D + d0], acc);      // c[cc]: warp-uniform (one transaction)
+    Y2[(size_t)r * D + d0] = (y[d0] - mu) * rstd * (1.f + acc);
+  }
+}
+
+int img2ltnt(const Layout& L, const float* Y, const float* cen, const float* f, float* ws, cudaStream_t st) {
+  const int rows = L.B * L.k;
+  img2ltnt_kernel<<<(rows + 3) / 4, 128, 0, st>>>(Y, cen, f + L.f_WI2L, f + L.f_BI2L, ws + L.w_Y2, rows, L.C, L.D);
+  GF_LAUNCH_OK();
+  return GF_OK;
 }
 
 // Stage I of several layers (same batch size, same latents or not) in ONE launch: simplex layers get their keys, V^T and

@@ -132,21 +132,32 @@ class FullyConnected(nn.Module):
 
 
 class MappingNetwork(nn.Module):
-    """G_mapping: z [B, k+1, D] -> w [B, k+1, D]; the k local components share one MLP, the global latent has its own."""
+    """G_mapping: z [B, k+1, D] -> w [B, k+1, D]; the k local components share one MLP, the global latent has its own.
 
-    def __init__(self, latent_dim: int, components_num: int, num_layers: int = 8, lr_mul: float = 0.01):
+    ``ltnt2ltnt=True`` (upstream's latent-to-latent option): after every fully connected layer the k local
+    latents attend to each other -- the same bipartite block as in the synthesis network (``BipartiteAttention`` with the
+    latents as both the "grid" [B, k, 1, D] and the attended set, no positional encoding, integration / norm as given), so it runs
+    on the same C-ABI kernels (C = D = 32: the CUDA-core kernel).  Off by default, as in the benchmarked configurations."""
+
+    def __init__(self, latent_dim: int, components_num: int, num_layers: int = 8, lr_mul: float = 0.01, ltnt2ltnt: bool = False,
+                 integration: str = "mul", norm: Optional[str] = "layer", exact_fp32: bool = False):
         super().__init__()
         self.latent_dim, self.components_num = latent_dim, components_num
         self.local = nn.ModuleList([FullyConnected(latent_dim, latent_dim, lr_mul=lr_mul, act="lrelu") for _ in range(num_layers)])
         self.glob = nn.ModuleList([FullyConnected(latent_dim, latent_dim, lr_mul=lr_mul, act="lrelu") for _ in range(num_layers)])
         self.register_buffer("w_avg", torch.zeros(2, latent_dim))
+        self.self_att = None
+        if ltnt2ltnt and components_num > 1:
+            self.self_att = nn.ModuleList([BipartiteAttention(latent_dim, latent_dim, components_num, pos_dim=latent_dim, use_pos=False,
+                                                              integration=integration, norm=norm, exact_fp32=exact_fp32)
+                                           for _ in range(num_layers)])
 
     def forward(self, z: torch.Tensor, truncation_psi: float = 1.0) -> torch.Tensor:
         k = self.components_num
         if z.dim() != 3 or z.shape[1] != k + 1 or z.shape[2] != self.latent_dim:
             raise ValueError(f"z must be [B, {k + 1}, {self.latent_dim}], got {tuple(z.shape)}")
         params = [t for fc in list(self.local) + list(self.glob) for t in (fc.weight, fc.bias)]
-        if (z.is_cuda and z.dtype == torch.float32 and _inference(*params) and self.latent_dim <= 128
+        if (self.self_att is None and z.is_cuda and z.dtype == torch.float32 and _inference(*params) and self.latent_dim <= 128
                 and len(self.local) * self.latent_dim ** 2 * 8 <= 200 * 1024 and not os.environ.get("GF_NO_MAPPING_KERNEL")):
             # inference: the whole mapping network is ONE kernel (gf_mapping_fwd); effective weights cached until a parameter changes
             def stack():
@@ -157,8 +168,12 @@ class MappingNetwork(nn.Module):
             return ops.mapping_fwd(z, w_eff, b_eff, self.w_avg, float(truncation_psi), k)
         z = z * torch.rsqrt(z.square().mean(dim=2, keepdim=True) + 1e-8)
         loc, glo = z[:, :k], z[:, k:]
-        for fc in self.local:
+        for i, fc in enumerate(self.local):
             loc = fc(loc)
+            if self.self_att is not None:           # latents attend to latents: grid = [B, k, 1, D] (H = k, W = 1), attended set = the same latents
+                loc = loc.contiguous()
+                loc, _, _ = self.self_att[i](loc.reshape(loc.shape[0], k, 1, self.latent_dim), loc)
+                loc = loc.reshape(-1, k, self.latent_dim)
         for fc in self.glob:
             glo = fc(glo)
         if truncation_psi != 1.0:
@@ -394,14 +409,15 @@ class Generator(nn.Module):
                  transformer: bool = True, g_start_res: int = 8, g_end_res: Optional[int] = None, kmeans: bool = False,
                  kmeans_iters: int = 1, iterative: bool = False, integration: str = "mul", norm: Optional[str] = "layer",
                  use_pos: bool = True, pos_dim: Optional[int] = None, num_heads: int = 1, mapping_layers: int = 8,
-                 fmap_base: int = 16384, fmap_max: int = 512, exact_fp32: bool = False):
+                 fmap_base: int = 16384, fmap_max: int = 512, exact_fp32: bool = False, ltnt2ltnt: bool = False):
         super().__init__()
         # D = latent_size // components_num unless given
         self.latent_dim = latent_dim if latent_dim is not None else max(latent_size // max(components_num, 1), 1)
         self.components_num, self.resolution = components_num, resolution
         attn_kwargs = dict(pos_dim=pos_dim, num_heads=num_heads, integration=integration, norm=norm, kmeans=kmeans,
                            kmeans_iters=kmeans_iters, use_pos=use_pos, exact_fp32=exact_fp32, iterative=iterative)
-        self.mapping = MappingNetwork(self.latent_dim, components_num, num_layers=mapping_layers)
+        self.mapping = MappingNetwork(self.latent_dim, components_num, num_layers=mapping_layers, ltnt2ltnt=ltnt2ltnt,
+                                      integration=integration, norm=norm, exact_fp32=exact_fp32)
         self.synthesis = SynthesisNetwork(resolution, self.latent_dim, components_num, fmap_base=fmap_base, fmap_max=fmap_max,
                                           g_start_res=g_start_res, g_end_res=g_end_res, transformer=transformer,
                                           attn_kwargs=attn_kwargs)

@@ -45,7 +45,9 @@ enum { GF_INT_MUL = 0, GF_INT_ADD = 1, GF_INT_BOTH = 2 };
 enum {
   GF_FLAG_FP32_EXACT = 1,   /* force the CUDA-core fp32-FMA kernel (tight-tolerance mode); default = tcgen05 TF32 */
   GF_FLAG_CENTROIDS_IN = 2, /* duplex: skip pass A, take centroids_inout as input (iterative=True upstream) */
-  GF_FLAG_TABLES_READY = 4  /* duplex: the pass-A query tables and V^T are already in ws (gf_attn_prologue_batch ran for this layer) */
+  GF_FLAG_TABLES_READY = 4, /* duplex: the pass-A query tables and V^T are already in ws (gf_attn_prologue_batch ran for this layer) */
+  GF_FLAG_IMG2LTNT = 8      /* duplex: g_img2ltnt -- before pass B the latents are modulated by the centroids,
+                               Y <- LN(Y) (1 + dense(Cen, wi2l) + bi2l); values of pass B from the modulated latents */
 };
 /* which kernel family served the last forward on this thread (gf_attn_last_path) */
 enum { GF_PATH_NONE = 0, GF_PATH_SIMT_FP32 = 1, GF_PATH_TCGEN05_TF32 = 2 };
@@ -59,7 +61,8 @@ typedef struct gf_attn_desc {
   int32_t norm;         /* GF_NORM_* */
   int32_t integration;  /* GF_INT_* */
   int32_t pos_dim;      /* width of the positional embeddings; 0 = use_pos False */
-  int32_t duplex;       /* 0 = simplex (latents -> image), 1 = duplex (kmeans, one iteration) */
+  int32_t duplex;       /* 0 = simplex (latents -> image); n >= 1 = duplex (kmeans) with n k-means iterations (kmeans_iters):
+                           iteration i >= 2 takes its queries from the previous centroids through wcq */
   int32_t flags;        /* GF_FLAG_* */
 } gf_attn_desc;
 
@@ -102,6 +105,8 @@ typedef struct gf_attn_weights {
   const float *wk2, *bk2, *wpk2;   /* [C,C] [C] [p,C]   duplex pass A: grid keys      */
   const float *wv2, *bv2;          /* [C,C] [C]         duplex pass A: grid values    */
   const float *wkc;                /* [C,C]             centroid -> key               */
+  const float *wcq;                /* [C,C]             centroid -> query of k-means iterations >= 2 (read when desc.duplex > 1) */
+  const float *wi2l, *bi2l;        /* [C,D] [D]         centroid -> latent gain (read with GF_FLAG_IMG2LTNT) */
 } gf_attn_weights;
 
 /* Library / device introspection. */

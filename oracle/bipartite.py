@@ -66,7 +66,7 @@ SIMPLEX_KEYS = ("wq", "bq", "wpq", "wk", "bk", "wpk", "wv", "bv", "wo", "bo", "p
 DUPLEX_KEYS = ("wq2", "bq2", "wpq2", "wk2", "bk2", "wpk2", "wv2", "bv2", "wkc")
 
 
-def param_shapes(C: int, D: int, k: int, pos_dim: int, integration: str, duplex: bool) -> Dict[str, Tuple[int, ...]]:
+def param_shapes(C: int, D: int, k: int, pos_dim: int, integration: str, duplex: bool, extras: bool = False) -> Dict[str, Tuple[int, ...]]:
     """Raw (un-scaled) parameter shapes of one attention layer.  Weights are [fan_in, fan_out]."""
     cout = 2 * C if integration == "both" else C
     shapes = {
@@ -83,15 +83,17 @@ def param_shapes(C: int, D: int, k: int, pos_dim: int, integration: str, duplex:
             "wv2": (C, C), "bv2": (C,),
             "wkc": (C, C),
         })
+        if extras:      # kmeans_iters > 1: centroid -> query projection; g_img2ltnt: centroid -> latent gain
+            shapes.update({"wcq": (C, C), "wi2l": (C, D), "bi2l": (D,)})
     return shapes
 
 
 def init_params(C: int, D: int, k: int, pos_dim: int, integration: str = "mul", duplex: bool = False,
-                seed: int = 0, dtype=torch.float64, bias_std: float = 0.0) -> Dict[str, Tensor]:
+                seed: int = 0, dtype=torch.float64, bias_std: float = 0.0, extras: bool = False) -> Dict[str, Tensor]:
     """N(0,1) weights, biases N(0, bias_std) (0 in benchmarks, >0 in tests so every term is live)."""
     g = torch.Generator().manual_seed(seed)
     out = {}
-    for name, shp in param_shapes(C, D, k, pos_dim, integration, duplex).items():
+    for name, shp in param_shapes(C, D, k, pos_dim, integration, duplex, extras).items():   # extras come last: earlier draws are unchanged
         t = torch.randn(shp, generator=g, dtype=torch.float64)
         if name.startswith("b"):
             t = t * bias_std
@@ -142,11 +144,17 @@ def _split_heads(t: Tensor, h: int) -> Tensor:
 def transformer_layer(x_nchw: Tensor, y: Tensor, w: Dict[str, Tensor], *, integration: str = "mul",
                       norm: Optional[str] = "layer", duplex: bool = False, num_heads: int = 1,
                       use_pos: bool = True, return_att: bool = False,
-                      centroids_in: Optional[Tensor] = None):
+                      centroids_in: Optional[Tensor] = None, kmeans_iters: int = 1, img2ltnt: bool = False):
     """Bipartite attention, direct form.
 
     x_nchw [B,C,H,W]; y [B,k,D] (the k local latents).  Returns (x' [B,C,H,W], att [B,k,H,W] or None,
     centroids [B,k,C] or None).
+
+    kmeans_iters > 1 (duplex; SURVEY A.3 "repeat with Qy derived from Cen"): iteration i >= 2 takes its queries from the previous
+    centroids, Qy = dense(Cen, wcq) + bq2 (+ latent positional term); keys / values of the grid are unchanged.
+    img2ltnt (duplex; SURVEY A.3 [SPEC] g_img2ltnt): before pass B the latents are modulated by the centroids,
+    Y <- LN(Y) (1 + dense(Cen, wi2l) + bi2l) (layer norm over D, eps as att_norm, no affine); the values of pass B come from
+    the modulated latents, the keys from the centroids.  The update is local to the layer (the caller's latents are not changed).
     """
     B, C, H, W = x_nchw.shape
     n = H * W
@@ -172,8 +180,13 @@ def transformer_layer(x_nchw: Tensor, y: Tensor, w: Dict[str, Tensor], *, integr
                 Qy = Qy + _dense(Pl, w["wpq2"])[None]
                 Kx = Kx + _dense(Pg, w["wpk2"])[None]
             Vx = _dense(X, w["wv2"], w["bv2"])
-            A = torch.softmax((Qy @ Kx.transpose(1, 2)) * (1.0 / math.sqrt(C)), dim=2)  # [B,k,n] over n
-            centroids = A @ Vx  # [B,k,C]
+            for it in range(max(1, kmeans_iters)):
+                if it > 0:                                   # queries from the previous centroids
+                    Qy = _dense(centroids, w["wcq"], w["bq2"])
+                    if use_pos:
+                        Qy = Qy + _dense(Pl, w["wpq2"])[None]
+                A = torch.softmax((Qy @ Kx.transpose(1, 2)) * (1.0 / math.sqrt(C)), dim=2)  # [B,k,n] over n
+                centroids = A @ Vx  # [B,k,C]
         K = _dense(centroids, w["wkc"], w["bk"])
     else:
         K = _dense(y, w["wk"], w["bk"])
@@ -183,7 +196,10 @@ def transformer_layer(x_nchw: Tensor, y: Tensor, w: Dict[str, Tensor], *, integr
     Q = _dense(X, w["wq"], w["bq"])
     if use_pos:
         Q = Q + _dense(Pg, w["wpq"])[None]
-    V = _dense(y, w["wv"], w["bv"])
+    yv = y
+    if duplex and img2ltnt:
+        yv = att_norm(y, "layer") * (1.0 + _dense(centroids, w["wi2l"], w["bi2l"]))
+    V = _dense(yv, w["wv"], w["bv"])
 
     Qh, Kh, Vh = _split_heads(Q, h), _split_heads(K, h), _split_heads(V, h)
     S = (Qh @ Kh.transpose(2, 3)) * scale          # [B,h,n,k]

@@ -83,6 +83,13 @@ def generator_forward(sd: Dict[str, torch.Tensor], z: torch.Tensor, *, resolutio
     for i in range(mapping_layers):
         loc = _fc(loc, sd, f"mapping.local.{i}", D, lr_mul=0.01, act="lrelu")
         glo = _fc(glo, sd, f"mapping.glob.{i}", D, lr_mul=0.01, act="lrelu")
+        pre = f"mapping.self_att.{i}."
+        if (pre + "wq") in sd:      # ltnt2ltnt: the k local latents attend to each other after every layer:
+            # the same block as in the synthesis network with the latents as the "image" [B, D, k, 1] and as the attended set
+            w = {n[len(pre):]: t for n, t in sd.items() if n.startswith(pre)}
+            xl, _, _ = transformer_layer(loc.transpose(1, 2).reshape(B, D, k, 1), loc, w, integration=integration, norm=norm,
+                                         duplex=False, num_heads=num_heads, use_pos=False)
+            loc = xl.reshape(B, D, k).transpose(1, 2)
     if truncation_psi != 1.0:
         loc = sd["mapping.w_avg"][0].lerp(loc, truncation_psi)
         glo = sd["mapping.w_avg"][1].lerp(glo, truncation_psi)

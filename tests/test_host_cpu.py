@@ -33,7 +33,7 @@ def test_header_symbols_are_exported(gf):
 
 def test_struct_layouts_match_c(gf):
     assert ctypes.sizeof(gf._lib.GfAttnDesc) == 12 * 4
-    assert ctypes.sizeof(gf._lib.GfAttnWeights) == 20 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(gf._lib.GfAttnWeights) == 23 * ctypes.sizeof(ctypes.c_void_p)
     assert ctypes.sizeof(gf._lib.GfAttnPostop) == 3 * 8 + 8 + 4 + 4 + 2 * 8 + 2 * 4 + 3 * 8
 
 
