@@ -29,11 +29,16 @@ def cases():
     out.append(dict(integration="both", norm="layer", duplex=True, k=16, use_pos=True))
     out.append(dict(integration="mul", norm="layer", duplex=False, k=8, use_pos=False))
     out.append(dict(integration="mul", norm="layer", duplex=True, k=8, use_pos=False))
+    # round 2 (appended: earlier cases keep their seeds): k-means iterations > 1 and g_img2ltnt
+    out.append(dict(integration="mul", norm="layer", duplex=True, k=16, use_pos=True, kmeans_iters=2))
+    out.append(dict(integration="both", norm="layer", duplex=True, k=8, use_pos=True, img2ltnt=True))
+    out.append(dict(integration="mul", norm="layer", duplex=True, k=4, use_pos=True, kmeans_iters=3, img2ltnt=True))
     return out
 
 
 def case_name(c):
-    return f"{c['integration']}-{c['norm']}-{'duplex' if c['duplex'] else 'simplex'}-k{c['k']}-{'pos' if c['use_pos'] else 'nopos'}"
+    ext = (f"-it{c['kmeans_iters']}" if c.get("kmeans_iters", 1) > 1 else "") + ("-i2l" if c.get("img2ltnt") else "")
+    return f"{c['integration']}-{c['norm']}-{'duplex' if c['duplex'] else 'simplex'}-k{c['k']}-{'pos' if c['use_pos'] else 'nopos'}{ext}"
 
 
 def make_inputs(c, seed):
@@ -41,7 +46,8 @@ def make_inputs(c, seed):
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(B, C, H, W, generator=g, dtype=torch.float64) * 1.5 + 0.3
     y = torch.randn(B, c["k"], D, generator=g, dtype=torch.float64)
-    w = ob.init_params(C, D, c["k"], P, c["integration"], c["duplex"], seed=seed + 1000, bias_std=0.5)
+    w = ob.init_params(C, D, c["k"], P, c["integration"], c["duplex"], seed=seed + 1000, bias_std=0.5,
+                       extras=c.get("kmeans_iters", 1) > 1 or bool(c.get("img2ltnt")))
     return x, y, w
 
 
@@ -51,7 +57,8 @@ def main():
         x, y, w = make_inputs(c, seed=100 + i)
         norm = None if c["norm"] == "none" else c["norm"]
         out, att, cen = ob.transformer_layer(x, y, w, integration=c["integration"], norm=norm, duplex=c["duplex"],
-                                             use_pos=c["use_pos"], return_att=True)
+                                             use_pos=c["use_pos"], return_att=True, kmeans_iters=c.get("kmeans_iters", 1),
+                                             img2ltnt=bool(c.get("img2ltnt")))
         name = case_name(c)
         store[name + "/out"] = out.permute(0, 2, 3, 1).contiguous().numpy().astype(np.float32)   # channels-last
         store[name + "/att"] = att.numpy().astype(np.float32)

@@ -59,20 +59,21 @@ def check_close(got, ref64, path, what="", tol_scale=1.0, e_ref=0.0):
     assert rel_rms <= rrms, f"{what}: path={path} rel_rms {rel_rms:.3e} > {rrms}"
 
 
-def make_layer(gf, dev, C, D, k, p, integration, norm, duplex, use_pos, exact, w):
+def make_layer(gf, dev, C, D, k, p, integration, norm, duplex, use_pos, exact, w, kmeans_iters=1, img2ltnt=False):
     attn = gf.BipartiteAttention(C, D, k, pos_dim=p, integration=integration, norm=norm, kmeans=duplex, use_pos=use_pos,
-                                 exact_fp32=exact).to(dev)
+                                 exact_fp32=exact, kmeans_iters=kmeans_iters, img2ltnt=img2ltnt).to(dev)
     with torch.no_grad():
         for n, prm in attn.named_parameters():
             prm.copy_(w[n].float())
     return attn
 
 
-def run_layer(gf, dev, x64_nchw, y64, w, *, integration, norm, duplex, use_pos, exact, return_att=True, centroids=None):
+def run_layer(gf, dev, x64_nchw, y64, w, *, integration, norm, duplex, use_pos, exact, return_att=True, centroids=None,
+              kmeans_iters=1, img2ltnt=False):
     B, C, H, W = x64_nchw.shape
     k, D = y64.shape[1], y64.shape[2]
     p = w["pos_latent"].shape[1]
-    attn = make_layer(gf, dev, C, D, k, p, integration, norm, duplex, use_pos, exact, w)
+    attn = make_layer(gf, dev, C, D, k, p, integration, norm, duplex, use_pos, exact, w, kmeans_iters, img2ltnt)
     x = x64_nchw.permute(0, 2, 3, 1).contiguous().float().to(dev)
     y = y64.float().to(dev)
     with torch.no_grad():
@@ -93,10 +94,10 @@ def test_layer_matches_golden(gf, cuda_dev, idx, exact):
     x, y, w = mg.make_inputs(c, 100 + idx)
     norm = None if c["norm"] == "none" else c["norm"]
     out, att, cen, path = run_layer(gf, cuda_dev, x, y, w, integration=c["integration"], norm=norm, duplex=c["duplex"],
-                                    use_pos=c["use_pos"], exact=exact)
+                                    use_pos=c["use_pos"], exact=exact, kmeans_iters=c.get("kmeans_iters", 1), img2ltnt=bool(c.get("img2ltnt")))
     if exact:
         assert path == "simt_fp32"
-    check_close(out, torch.from_numpy(gold[name + "/out"]), path, name + "/out")
+    check_close(out, torch.from_numpy(gold[name + "/out"]), path, name + "/out", tol_scale=1.5 if c.get("kmeans_iters", 1) > 1 else 1.0)
     a_atol = 1e-6 if path == "simt_fp32" else 2e-3
     assert (att.cpu().double() - torch.from_numpy(gold[name + "/att"]).double()).abs().max() <= a_atol + (1e-4 if exact else 5e-3)
     if c["duplex"]:
@@ -894,7 +895,8 @@ def test_mapping_latent_self_attention(gf, cuda_dev, exact):
     G2.load_state_dict({n: v for n, v in G.state_dict().items() if not n.startswith("mapping.self_att")})
     with torch.no_grad():
         ws2 = G2.mapping(z.to(cuda_dev))
-    assert (ws[:, :8] - ws2[:, :8]).abs().max() > 1e-3 and torch.equal(ws[:, 8], ws2[:, 8])
+    assert (ws[:, :8] - ws2[:, :8]).abs().max() > 1e-3                       # the local latents changed ...
+    assert (ws[:, 8] - ws2[:, 8]).abs().max() <= 1e-5 * max(1.0, ws2[:, 8].abs().max().item())    # ... the global one did not (torch path vs the fused kernel: fp32 rounding)
 
 
 @pytest.mark.parametrize("exact", [True, False], ids=["fp32", "default"])
