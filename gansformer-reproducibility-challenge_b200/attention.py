@@ -151,7 +151,7 @@ def _plan_call(lib, shape, y: torch.Tensor, params: Dict[str, torch.Tensor], pla
         + (IMG2LTNT_PARAMS if (duplex and flags & _lib.FLAG_IMG2LTNT) else ())
     if weights_version is None:
         weights_version = tuple((params[n].data_ptr(), params[n]._version) for n in names)
-    fkey = (H, W, k, D, C, pos_dim, integration, int(duplex), flags & _lib.FLAG_IMG2LTNT, str(dev), weights_version, weights_epoch())
+    fkey = (H, W, k, D, C, pos_dim, integration, int(duplex), num_heads, flags & _lib.FLAG_IMG2LTNT, str(dev), weights_version, weights_epoch())
     if plan.folded is None or plan.folded_key != fkey or FORCE_REFOLD:
         nfl = _lib.folded_floats(desc)
         if plan.folded is None or plan.folded.numel() != nfl or plan.folded.device != dev:
@@ -164,7 +164,7 @@ def _plan_call(lib, shape, y: torch.Tensor, params: Dict[str, torch.Tensor], pla
         _lib.check(lib.gf_attn_fold_weights(ctypes.byref(desc), ctypes.byref(wstruct), plan.folded.data_ptr(), stream),
                    "gf_attn_fold_weights")
         plan.folded_key = fkey
-    wkey = (B, H, W, C, k, D, pos_dim, integration, norm, int(duplex), flags & _lib.FLAG_IMG2LTNT, str(dev))
+    wkey = (B, H, W, C, k, D, pos_dim, integration, norm, int(duplex), num_heads, flags & _lib.FLAG_IMG2LTNT, str(dev))
     ws = plan.ws.get(wkey)
     if ws is None:
         ws = torch.empty(_lib.workspace_bytes(desc), dtype=torch.uint8, device=dev)

@@ -24,7 +24,7 @@ def _axis(length, dim, device):
     return torch.cat([torch.sin(ang), torch.cos(ang)], dim=1)            # float64: callers cast to their dtype
 
 
-def composite_forward(x, y, p, *, integration, norm, duplex, use_pos, centroids=None, kmeans_iters=1, img2ltnt=False):
+def composite_forward(x, y, p, *, integration, norm, duplex, use_pos, centroids=None, kmeans_iters=1, img2ltnt=False, num_heads=1):
     """Same math as the kernels, in torch ops (direct op order), on whatever device x lives on.  x [B,H,W,C]."""
     B, H, W, C = x.shape
     n = H * W
@@ -66,8 +66,14 @@ def composite_forward(x, y, p, *, integration, norm, duplex, use_pos, centroids=
         ym = y.mean(dim=2, keepdim=True)
         yv = (y - ym) * torch.rsqrt(((y - ym) ** 2).mean(dim=2, keepdim=True) + 1e-8) * (1.0 + cen @ _e(p["wi2l"]) + p["bi2l"])
     V = yv @ _e(p["wv"]) + p["bv"]
-    P = torch.softmax((Q @ K.transpose(1, 2)) * s, dim=2)
-    ctl = (P @ V) @ _e(p["wo"]) + p["bo"]
+    if num_heads == 1:
+        P = torch.softmax((Q @ K.transpose(1, 2)) * s, dim=2)
+        ctl = (P @ V) @ _e(p["wo"]) + p["bo"]
+    else:                                   # heads split the channels; softmax over the latents per head; scale 1/sqrt(C/heads)
+        h, kk = num_heads, K.shape[1]
+        sp = lambda t, L: t.reshape(B, L, h, C // h).permute(0, 2, 1, 3)
+        Ph = torch.softmax((sp(Q, n) @ sp(K, kk).transpose(2, 3)) * (1.0 / math.sqrt(C / h)), dim=3)
+        ctl = (Ph @ sp(V, kk)).permute(0, 2, 1, 3).reshape(B, n, C) @ _e(p["wo"]) + p["bo"]
     if norm == "layer":
         mu = X.mean(dim=2, keepdim=True)
         Xn = (X - mu) * torch.rsqrt(((X - mu) ** 2).mean(dim=2, keepdim=True) + 1e-8)
@@ -155,7 +161,7 @@ class _FusedAttention(torch.autograd.Function):
             ps = [p.detach().requires_grad_(True) for p in params]
             out, _ = composite_forward(xs, ys, dict(zip(ctx.names, ps)), integration=m.integration, norm=m.norm,
                                        duplex=m.duplex, use_pos=m.use_pos, centroids=ctx.centroids, kmeans_iters=m.kmeans_iters,
-                                       img2ltnt=m.img2ltnt)
+                                       img2ltnt=m.img2ltnt, num_heads=m.num_heads)
             grads = torch.autograd.grad(out, [xs, ys, *ps], g_out, allow_unused=True)
         return (None, None, None, None, *grads)
 

@@ -21,7 +21,16 @@ int make_layout(const gf_attn_desc* d, Layout* L) {
   if (d->k > 32) { set_error("k=%d unsupported: at most 32 latents", d->k); return GF_ERR_UNSUPPORTED; }
   if (d->D > 256) { set_error("D=%d unsupported: latent size at most 256", d->D); return GF_ERR_UNSUPPORTED; }
   if (d->duplex < 0 || d->duplex > 16) { set_error("duplex=%d: 0 (simplex) or the number of k-means iterations (1..16)", d->duplex); return GF_ERR_INVALID; }
-  if (d->heads != 1) { set_error("num_heads=%d unsupported: this build implements 1 head", d->heads); return GF_ERR_UNSUPPORTED; }
+  if (d->heads < 1) { set_error("num_heads=%d: must be >= 1", d->heads); return GF_ERR_INVALID; }
+  if (d->heads > 1) {
+    // multi-head stage T: the heads become column segments of the per-image tables (K' / V^T / Rt / Ct hold heads * seg "latents",
+    // the softmax runs per segment).  Segments of 8, 16 or 32 columns; heads * seg <= 32.
+    int seg = d->k <= 8 ? 8 : (d->k <= 16 ? 16 : 32);
+    if (d->C % d->heads != 0 || ((d->C / d->heads) & 3)) { set_error("num_heads=%d must divide C=%d into multiples of 4 channels", d->heads, d->C); return GF_ERR_UNSUPPORTED; }
+    if (d->heads != 2 && d->heads != 4) { set_error("num_heads=%d unsupported: 1, 2 or 4 heads", d->heads); return GF_ERR_UNSUPPORTED; }
+    if (d->heads * seg > 32) { set_error("num_heads=%d with k=%d needs %d table columns: at most 32 (heads * k rounded up to 8 / 16)", d->heads, d->k, d->heads * seg); return GF_ERR_UNSUPPORTED; }
+    if (d->duplex) { set_error("num_heads > 1 is implemented for simplex layers (duplex: 1 head)"); return GF_ERR_UNSUPPORTED; }
+  }
   if (d->norm < GF_NORM_NONE || d->norm > GF_NORM_BATCH) { set_error("bad norm %d", d->norm); return GF_ERR_INVALID; }
   if (d->integration < GF_INT_MUL || d->integration > GF_INT_BOTH) { set_error("bad integration %d", d->integration); return GF_ERR_INVALID; }
   if (d->pos_dim < 0 || d->pos_dim % 4 != 0 || d->pos_dim > 256) { set_error("pos_dim=%d unsupported: need multiple of 4, <= 256", d->pos_dim); return GF_ERR_UNSUPPORTED; }
@@ -29,7 +38,10 @@ int make_layout(const gf_attn_desc* d, Layout* L) {
 
   Layout& l = *L;
   l.B = d->B; l.H = d->H; l.W = d->W; l.C = d->C; l.k = d->k; l.D = d->D; l.p = d->pos_dim;
-  l.KP = pad_k(d->k);
+  l.heads = d->heads;
+  l.seg = d->heads > 1 ? (d->k <= 8 ? 8 : (d->k <= 16 ? 16 : 32)) : pad_k(d->k);
+  l.KP = d->heads > 1 ? pad_k(l.heads * l.seg) : pad_k(d->k);
+  // heads in {2, 4} and seg in {8, 16}: heads * seg is 16 or 32, i.e. KP == heads * seg
   l.Cout = d->integration == GF_INT_BOTH ? 2 * d->C : d->C;
   l.LDK = (d->C + d->pos_dim + 4 + 3) & ~3;          // rows of the [.., LDK] matrices are read as float4
   l.n = d->H * d->W;
@@ -39,10 +51,11 @@ int make_layout(const gf_attn_desc* d, Layout* L) {
 
   size_t o = 0;
   auto take = [&](size_t nfloats) { size_t r = o; o += align64(nfloats); return r; };
-  l.f_AK = take(Din * LDK);
-  l.f_CK = take(k * LDK);
-  l.f_AV = take(D * l.Cout);
-  l.f_CV = take(l.Cout);
+  const size_t nh = l.heads;                         // per-head copies of the key / value folds (simplex)
+  l.f_AK = take(nh * Din * LDK);
+  l.f_CK = take(nh * k * LDK);
+  l.f_AV = take(nh * D * l.Cout);
+  l.f_CV = take(nh * l.Cout);
   l.f_ROW = take((size_t)l.H * (p / 2) + 1);
   l.f_COL = take((size_t)l.W * (p / 2) + 1);
   l.f_QFOLD = take(C * LDK);
@@ -304,7 +317,8 @@ int fold_weights(const Layout& L, const gf_attn_desc* d, const gf_attn_weights* 
   if (L.duplex && (!w->wq2 || !w->bq2 || !w->wk2 || !w->wv2 || !w->bv2 || !w->wkc || (pos && (!w->wpq2 || !w->wpk2)))) {
     set_error("fold_weights: duplex weights are null"); return GF_ERR_INVALID;
   }
-  const float s = 1.f / sqrtf((float)C);           // 1/sqrt(C/heads), heads = 1
+  const int nh = L.heads, ch = C / nh;            // channels per head
+  const float s = 1.f / sqrtf((float)ch);         // 1/sqrt(C/heads)
   const float rC = 1.f / sqrtf((float)C), rD = 1.f / sqrtf((float)D), rp = pos ? 1.f / sqrtf((float)p) : 0.f;
   int rc;
   // qfold [C, LDK]
@@ -344,11 +358,25 @@ int fold_weights(const Layout& L, const gf_attn_desc* d, const gf_attn_weights* 
       GF_LAUNCH_OK();
     }
   } else {
-    if ((rc = gemm(st, D, LDK, C, w->wk, C, false, f + L.f_QFOLD, LDK, false, f + L.f_AK, LDK, rD))) return rc;
+    // per head h: the key's channels of that head only -- AK_h = wk_e[:, h] qfold[h, :],  CK_h = kconst[:, h] qfold[h, :]
+    for (int h = 0; h < nh; ++h) {
+      if ((rc = gemm(st, D, LDK, ch, w->wk + h * ch, C, false, f + L.f_QFOLD + (size_t)h * ch * LDK, LDK, false,
+                     f + L.f_AK + (size_t)h * D * LDK, LDK, rD)))
+        return rc;
+      if (h > 0 && (rc = gemm(st, k, LDK, ch, f + L.f_KCONST + h * ch, C, false, f + L.f_QFOLD + (size_t)h * ch * LDK, LDK, false,
+                              f + L.f_CK + (size_t)h * k * LDK, LDK, 1.f)))
+        return rc;
+    }
+    if (nh > 1 && (rc = gemm(st, k, LDK, ch, f + L.f_KCONST, C, false, f + L.f_QFOLD, LDK, false, f + L.f_CK, LDK, 1.f))) return rc;   // head 0 (overwrites the full-C product)
   }
-  // AV [D, Cout] = wv_e @ wo_e ; CV = bv @ wo_e + bo (+1 on the gain half)
-  if ((rc = gemm(st, D, Cout, C, w->wv, C, false, w->wo, Cout, false, f + L.f_AV, Cout, rD * rC))) return rc;
-  if ((rc = gemm(st, 1, Cout, C, w->bv, C, false, w->wo, Cout, false, f + L.f_CV, Cout, rC, nullptr, 0, 1, w->bo))) return rc;
+  // per head: AV_h [D, Cout] = wv_e[:, h] @ wo_e[h, :] ; CV_h = bv[h] @ wo_e[h, :]; head 0 also carries bo (+1 on the gain half):
+  // every head's probabilities sum to one, so a constant may ride on any single head
+  for (int h = 0; h < nh; ++h) {
+    if ((rc = gemm(st, D, Cout, ch, w->wv + h * ch, C, false, w->wo + (size_t)h * ch * Cout, Cout, false, f + L.f_AV + (size_t)h * D * Cout, Cout, rD * rC))) return rc;
+    if ((rc = gemm(st, 1, Cout, ch, w->bv + h * ch, C, false, w->wo + (size_t)h * ch * Cout, Cout, false, f + L.f_CV + (size_t)h * Cout, Cout, rC,
+                   nullptr, 0, 1, h == 0 ? w->bo : nullptr)))
+      return rc;
+  }
   if (d->integration != GF_INT_ADD) {
     scale_copy_kernel<<<blocks_for(Cout), 256, 0, st>>>(f + L.f_CV, f + L.f_CV, Cout, 1.f, 1.f, (size_t)C);
     GF_LAUNCH_OK();
@@ -501,6 +529,7 @@ struct StageIJob {
   const float *Y, *A, *Cst, *AV, *CV, *ROW, *COL, *in_scale;
   float *Kp, *Vt, *Rt, *Ct;
   int H, W, C, k, D, p, KP, Cout, LDK, in_ld;
+  int heads, seg;                // multi-head: table column J = head * seg + j; A / Cst / AV / CV hold one copy per head
   int tf32_k, tf32_v;            // round K' (and take the logits in log2 units) / round V^T for the tcgen05 kernels
   int nvblk, npos, nkblk;        // CTAs per image and role
   int blk_begin;                 // first blockIdx.y of this job
@@ -522,30 +551,32 @@ __global__ void __launch_bounds__(256, 4) stage_i_kernel(const __grid_constant__
     const int Cout = J.Cout;
     const int c = blk * 256 + threadIdx.x;
     if (c >= Cout) return;
-    const float cv = J.CV[c];
     float* out = J.Vt + ((size_t)b * Cout + c) * KP;
-    for (int j0 = 0; j0 < KP; j0 += 16) {
-      float acc[16];
+    for (int j0 = 0; j0 < KP; j0 += 8) {                          // 8 table columns at a time: one head (seg >= 8)
+      const int head = j0 / J.seg, jb = j0 - head * J.seg;        // latent index of column j0 inside its head
+      const float* AVh = J.AV + (size_t)head * D * Cout;
+      const float cv = J.CV[(size_t)head * Cout + c];
+      float acc[8];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
       for (int d0 = 0; d0 < D; d0 += 16) {
         float a[16];
 #pragma unroll
-        for (int dd = 0; dd < 16; ++dd) a[dd] = d0 + dd < D ? J.AV[(size_t)(d0 + dd) * Cout + c] : 0.f;
+        for (int dd = 0; dd < 16; ++dd) a[dd] = d0 + dd < D ? AVh[(size_t)(d0 + dd) * Cout + c] : 0.f;
 #pragma unroll
         for (int dd = 0; dd < 16; ++dd) {
           if (d0 + dd < D) {
-            const float* yr = ysm + (size_t)j0 * D + d0 + dd;
+            const float* yr = ysm + (size_t)jb * D + d0 + dd;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) if (j0 + j < k) acc[j] = fmaf(yr[j * D], a[dd], acc[j]);
+            for (int j = 0; j < 8; ++j) if (jb + j < k) acc[j] = fmaf(yr[j * D], a[dd], acc[j]);
           }
         }
       }
 #pragma unroll
-      for (int j4 = 0; j4 < 4; ++j4) {
+      for (int j4 = 0; j4 < 2; ++j4) {
         float4 r;
-        r.x = j0 + j4 * 4 + 0 < k ? acc[j4 * 4 + 0] + cv : 0.f; r.y = j0 + j4 * 4 + 1 < k ? acc[j4 * 4 + 1] + cv : 0.f;
-        r.z = j0 + j4 * 4 + 2 < k ? acc[j4 * 4 + 2] + cv : 0.f; r.w = j0 + j4 * 4 + 3 < k ? acc[j4 * 4 + 3] + cv : 0.f;
+        r.x = jb + j4 * 4 + 0 < k ? acc[j4 * 4 + 0] + cv : 0.f; r.y = jb + j4 * 4 + 1 < k ? acc[j4 * 4 + 1] + cv : 0.f;
+        r.z = jb + j4 * 4 + 2 < k ? acc[j4 * 4 + 2] + cv : 0.f; r.w = jb + j4 * 4 + 3 < k ? acc[j4 * 4 + 3] + cv : 0.f;
         if (J.tf32_v) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
         reinterpret_cast<float4*>(out)[j0 / 4 + j4] = r;
       }
@@ -556,17 +587,20 @@ __global__ void __launch_bounds__(256, 4) stage_i_kernel(const __grid_constant__
     // ---- positional logit tables: kap[j, q] = (Y[b] . A + Cst)[j, C + q], q <= p (the last one is the bias column)
     float* kap = ysm + k * D;
     const int pw = p + 1;
-    for (int i = threadIdx.x; i < k * pw; i += blockDim.x) {
-      const int j = i / pw, q = i - j * pw;
+    for (int i = threadIdx.x; i < KP * pw; i += blockDim.x) {
+      const int Jc = i / pw, q = i - Jc * pw;
+      const int head = Jc / J.seg, j = Jc - head * J.seg;
+      if (j >= k) { kap[i] = 0.f; continue; }
+      const float* Ah = J.A + (size_t)head * D * LDK;
       float acc = 0.f;
       for (int d0 = 0; d0 < D; d0 += 8) {                 // 8 independent loads in flight (one L2 round trip per batch)
         float a[8];
 #pragma unroll
-        for (int dd = 0; dd < 8; ++dd) a[dd] = d0 + dd < D ? J.A[(size_t)(d0 + dd) * LDK + C + q] : 0.f;
+        for (int dd = 0; dd < 8; ++dd) a[dd] = d0 + dd < D ? Ah[(size_t)(d0 + dd) * LDK + C + q] : 0.f;
 #pragma unroll
         for (int dd = 0; dd < 8; ++dd) if (d0 + dd < D) acc = fmaf(ysm[j * D + d0 + dd], a[dd], acc);
       }
-      kap[i] = acc + J.Cst[(size_t)j * LDK + C + q];
+      kap[i] = acc + J.Cst[((size_t)head * k + j) * LDK + C + q];
     }
     __syncthreads();
     const int half = p / 2, H = J.H, W = J.W;
@@ -574,7 +608,7 @@ __global__ void __launch_bounds__(256, 4) stage_i_kernel(const __grid_constant__
       const int r = i / KP, j = i % KP;
       const bool is_row = r < H;
       float val;
-      if (j >= k) {
+      if (j % J.seg >= k) {                          // padded column of its head: probability exactly 0
         val = is_row ? -INFINITY : 0.f;
       } else {
         const float* kj = kap + j * pw;
@@ -599,7 +633,9 @@ __global__ void __launch_bounds__(256, 4) stage_i_kernel(const __grid_constant__
   const float4* isc4 = J.in_scale ? reinterpret_cast<const float4*>(J.in_scale + (size_t)b * J.in_ld) : nullptr;
   float4* Kp4 = reinterpret_cast<float4*>(J.Kp + (size_t)b * KP * C);
   for (int item = (blk - J.nvblk - J.npos) * blockDim.x + threadIdx.x; item < C4 * groups; item += J.nkblk * blockDim.x) {
-    const int g = item / C4, c4 = item - g * C4, j0 = g * 8;
+    const int g = item / C4, c4 = item - g * C4;
+    const int head = (g * 8) / J.seg, j0 = g * 8 - head * J.seg;      // 8 table columns of one head (seg >= 8): latents j0 .. j0 + 7
+    const float* Ah = J.A + (size_t)head * D * LDK;
     float4 acc[8];
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) acc[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -607,7 +643,7 @@ __global__ void __launch_bounds__(256, 4) stage_i_kernel(const __grid_constant__
       for (int d0 = 0; d0 < D; d0 += 4) {
         float4 a[4];
 #pragma unroll
-        for (int dd = 0; dd < 4; ++dd) a[dd] = d0 + dd < D ? *reinterpret_cast<const float4*>(J.A + (size_t)(d0 + dd) * LDK + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int dd = 0; dd < 4; ++dd) a[dd] = d0 + dd < D ? *reinterpret_cast<const float4*>(Ah + (size_t)(d0 + dd) * LDK + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int dd = 0; dd < 4; ++dd) {
           if (d0 + dd < D) {
@@ -628,14 +664,14 @@ __global__ void __launch_bounds__(256, 4) stage_i_kernel(const __grid_constant__
     for (int jj = 0; jj < 8; ++jj) {
       float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
       if (j0 + jj < k) {
-        const float4 cst = *reinterpret_cast<const float4*>(J.Cst + (size_t)(j0 + jj) * LDK + c4 * 4);
+        const float4 cst = *reinterpret_cast<const float4*>(J.Cst + ((size_t)head * k + j0 + jj) * LDK + c4 * 4);
         r = make_float4((acc[jj].x + cst.x) * d.x, (acc[jj].y + cst.y) * d.y, (acc[jj].z + cst.z) * d.z, (acc[jj].w + cst.w) * d.w);
         if (J.tf32_k) {
           constexpr float kf = GF_TF32_TRUNC_COMP * GF_LOG2E;
           r.x = round_tf32(r.x * kf); r.y = round_tf32(r.y * kf); r.z = round_tf32(r.z * kf); r.w = round_tf32(r.w * kf);
         }
       }
-      Kp4[(size_t)(j0 + jj) * C4 + c4] = r;
+      Kp4[(size_t)(g * 8 + jj) * C4 + c4] = r;
     }
   }
 }
@@ -646,6 +682,7 @@ static void stage_i_fill(StageIJob& J, const Layout& L, const float* Y, const fl
   J.Kp = Kp; J.Vt = Vt; J.Rt = Rt; J.Ct = Ct;
   J.H = L.H; J.W = L.W; J.C = L.C; J.k = L.k; J.D = L.D; J.p = L.p; J.KP = L.KP; J.Cout = L.Cout; J.LDK = L.LDK; J.in_ld = in_ld;
   J.tf32_k = tf32_k; J.tf32_v = tf32_v;
+  J.heads = L.heads; J.seg = L.heads > 1 ? L.seg : L.KP;       // one head: a single segment of KP columns
   J.nvblk = Vt ? (L.Cout + 255) / 256 : 0;
   J.npos = ((L.H + L.W) * L.KP + 1023) / 1024;
   J.nkblk = ((L.C / 4) * (L.KP / 8) + 255) / 256;
@@ -659,7 +696,7 @@ static int stage_i_launch(StageIBatch& batch, int B, cudaStream_t st) {
     StageIJob& J = batch.job[i];
     J.blk_begin = total;
     total += J.nvblk + J.npos + J.nkblk;
-    const size_t need = ((size_t)J.k * J.D + (size_t)J.k * (J.p + 1)) * sizeof(float);
+    const size_t need = ((size_t)J.k * J.D + (size_t)J.KP * (J.p + 1)) * sizeof(float);
     if (need > smem) smem = need;
   }
   if (smem > 48 * 1024) { set_error("stage I: k * (D + p + 1) floats exceed 48 KB of shared memory"); return GF_ERR_UNSUPPORTED; }

@@ -21,6 +21,7 @@ struct TokenParams {
   // fused epilogue (gf_attn_postop)
   const float* pbias; const float* pnoise; const float* pstrength; long long pnoise_bstride; int pact; float pgain; int has_post;
   const float* in_scale; const float* post_scale; int in_ld, post_ld;
+  int heads, seg;            // multi-head: softmax per segment of `seg` table columns (heads * seg == KP)
 };
 
 __device__ __forceinline__ void load_x_chunk(float (*xs)[XS], const float* __restrict__ Xb, int t0, int n, int C, int c0) {
@@ -87,19 +88,40 @@ __global__ void __launch_bounds__(TM) token_simt_kernel(const TokenParams P) {
   }
 
   // ---- softmax over the k latents (padded latents carry -inf from Rt) ------------------------------
-  float mx = s[0];
+  if (P.heads == 1) {
+    float mx = s[0];
 #pragma unroll
-  for (int j = 1; j < KP; ++j) mx = fmaxf(mx, s[j]);
-  float den = 0.f;
+    for (int j = 1; j < KP; ++j) mx = fmaxf(mx, s[j]);
+    float den = 0.f;
 #pragma unroll
-  for (int j = 0; j < KP; ++j) { s[j] = expf(s[j] - mx); den += s[j]; }
-  const float inv = 1.f / den;
+    for (int j = 0; j < KP; ++j) { s[j] = expf(s[j] - mx); den += s[j]; }
+    const float inv = 1.f / den;
 #pragma unroll
-  for (int j = 0; j < KP; ++j) s[j] *= inv;
-  if (P.att && valid) {
-    float* a = P.att + ((size_t)b * n + t) * P.k;
+    for (int j = 0; j < KP; ++j) s[j] *= inv;
+    if (P.att && valid) {
+      float* a = P.att + ((size_t)b * n + t) * P.k;
 #pragma unroll
-    for (int j = 0; j < KP; ++j) if (j < P.k) a[j] = s[j];
+      for (int j = 0; j < KP; ++j) if (j < P.k) a[j] = s[j];
+    }
+  } else {
+    // multi-head: one softmax per head (column segment); attention map = mean over the heads
+    const int seg = P.seg;
+    float mxs[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, dens[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < KP; ++j) { const int g_ = j / seg; mxs[g_] = fmaxf(mxs[g_], s[j]); }
+#pragma unroll
+    for (int j = 0; j < KP; ++j) { const int g_ = j / seg; s[j] = expf(s[j] - mxs[g_]); dens[g_] += s[j]; }
+#pragma unroll
+    for (int j = 0; j < KP; ++j) s[j] /= dens[j / seg];
+    if (P.att && valid) {
+      float* a = P.att + ((size_t)b * n + t) * P.k;
+      for (int j = 0; j < P.k; ++j) {
+        float m = 0.f;
+#pragma unroll
+        for (int c = 0; c < KP; ++c) if (c % seg == j) m += s[c];
+        a[j] = m / (float)P.heads;
+      }
+    }
   }
 
   float mean = 0.f, rstd = 1.f;
@@ -189,6 +211,7 @@ int token_pass_simt(const Layout& L, const gf_attn_desc* d, const float* X, floa
   P.pnoise_bstride = post ? post->noise_bstride : 0; P.pact = post ? post->act : 0; P.pgain = post ? post->gain : 1.f;
   P.in_scale = post ? post->in_scale : nullptr; P.post_scale = post ? post->post_scale : nullptr;
   P.in_ld = post ? post->in_scale_ld : 0; P.post_ld = post ? post->post_scale_ld : 0;
+  P.heads = L.heads; P.seg = L.seg;
   dim3 grid((L.n + TM - 1) / TM, L.B);
   if (L.KP == 16) token_simt_kernel<16><<<grid, TM, 0, st>>>(P);
   else token_simt_kernel<32><<<grid, TM, 0, st>>>(P);

@@ -50,6 +50,7 @@ struct Params {
   const float* in_scale; const float* post_scale; int in_ld, post_ld;   // per-(b,c) load-side / store-side scales
   // fused tRGB (1x1 modulated conv of the layer output to 3 planes): rgb_w [B][3][C] per-sample weights, rgb_out [B][3][n]
   const float* rgb_w; const float* rgb_bias; float* rgb_out;
+  int heads, seg_shift;      // multi-head: the softmax runs per segment of (1 << seg_shift) table columns (heads * seg == KP)
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -369,25 +370,58 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       // ---- softmax over the latents: S (TMEM) -> P (TMEM)
       mbar_wait(smem_u32(&bars->s_full[buf]), bphase);
       tc_fence_after();
-      float mx = -INFINITY;
+      if (P.heads == 1) {
+        float mx = -INFINITY;
 #pragma unroll
-      for (int hh = 0; hh < KP / 16; ++hh) {                        // 16 columns at a time: keeps the register peak down
-        float acc[16];
-        tmem_ld16(tmem + lane_addr + COL_S + buf * 32 + hh * 16, acc);
-        tmem_wait_ld();
+        for (int hh = 0; hh < KP / 16; ++hh) {                        // 16 columns at a time: keeps the register peak down
+          float acc[16];
+          tmem_ld16(tmem + lane_addr + COL_S + buf * 32 + hh * 16, acc);
+          tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { sv[hh * 16 + j] += acc[j]; mx = fmaxf(mx, sv[hh * 16 + j]); }
-      }
-      float den = 0.f;
+          for (int j = 0; j < 16; ++j) { sv[hh * 16 + j] += acc[j]; mx = fmaxf(mx, sv[hh * 16 + j]); }
+        }
+        float den = 0.f;
 #pragma unroll
-      for (int j = 0; j < KP; ++j) { sv[j] = exp2f(sv[j] - mx); den += sv[j]; }   // logits arrive in log2 units (gf_fold.cu folds log2 e into K' / Rt / Ct)
-      const float inv = 1.f / den;
+        for (int j = 0; j < KP; ++j) { sv[j] = exp2f(sv[j] - mx); den += sv[j]; }   // logits arrive in log2 units (gf_fold.cu folds log2 e into K' / Rt / Ct)
+        const float inv = 1.f / den;
 #pragma unroll
-      for (int j = 0; j < KP; ++j) sv[j] *= inv;
-      if (P.att && row < P.rows) {
-        float* a = P.att + ((size_t)(img_last ? b - 1 : b) * P.n + tok) * P.k;
+        for (int j = 0; j < KP; ++j) sv[j] *= inv;
+        if (P.att && row < P.rows) {
+          float* a = P.att + ((size_t)(img_last ? b - 1 : b) * P.n + tok) * P.k;
 #pragma unroll
-        for (int j = 0; j < KP; ++j) if (j < P.k) a[j] = sv[j];
+          for (int j = 0; j < KP; ++j) if (j < P.k) a[j] = sv[j];
+        }
+      } else {
+        // multi-head: one softmax per segment of table columns (head h owns columns [h * seg, (h + 1) * seg)); the attention map is
+        // the mean over the heads
+#pragma unroll
+        for (int hh = 0; hh < KP / 16; ++hh) {
+          float acc[16];
+          tmem_ld16(tmem + lane_addr + COL_S + buf * 32 + hh * 16, acc);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sv[hh * 16 + j] += acc[j];
+        }
+        float mxs[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, dens[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < KP; ++j) { const int g_ = j >> P.seg_shift; mxs[g_] = fmaxf(mxs[g_], sv[j]); }
+#pragma unroll
+        for (int j = 0; j < KP; ++j) { const int g_ = j >> P.seg_shift; sv[j] = exp2f(sv[j] - mxs[g_]); dens[g_] += sv[j]; }
+#pragma unroll
+        for (int g_ = 0; g_ < 4; ++g_) dens[g_] = 1.f / dens[g_];
+#pragma unroll
+        for (int j = 0; j < KP; ++j) sv[j] *= dens[j >> P.seg_shift];
+        if (P.att && row < P.rows) {
+          float* a = P.att + ((size_t)(img_last ? b - 1 : b) * P.n + tok) * P.k;
+          const int seg = 1 << P.seg_shift;
+          const float ih = 1.f / (float)P.heads;
+          for (int j = 0; j < P.k; ++j) {
+            float m = 0.f;
+#pragma unroll
+            for (int c = 0; c < KP; ++c) if ((c & (seg - 1)) == j) m += sv[c];
+            a[j] = m * ih;
+          }
+        }
       }
       // round P to the nearest TF32 so the tensor core's operand truncation is exact (see gf_fold.cu: round_tf32)
 #pragma unroll
@@ -607,6 +641,7 @@ static int launch(const Layout& L, const gf_attn_desc* d, const float* X, float*
   P.in_scale = post ? post->in_scale : nullptr; P.post_scale = post ? post->post_scale : nullptr;
   P.in_ld = post ? post->in_scale_ld : 0; P.post_ld = post ? post->post_scale_ld : 0;
   P.rgb_w = post ? post->rgb_w : nullptr; P.rgb_bias = post ? post->rgb_bias : nullptr; P.rgb_out = post ? post->rgb_out : nullptr;
+  P.heads = L.heads; P.seg_shift = L.seg == 8 ? 3 : (L.seg == 16 ? 4 : 5);
   const int smem_bytes = CF::FIXED_BYTES + nst * SLAB_BYTES + 1024;
   auto kern = token_tc_kernel<KP, NS, MODE, TWO>;
   GF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));

@@ -33,11 +33,14 @@ def cases():
     out.append(dict(integration="mul", norm="layer", duplex=True, k=16, use_pos=True, kmeans_iters=2))
     out.append(dict(integration="both", norm="layer", duplex=True, k=8, use_pos=True, img2ltnt=True))
     out.append(dict(integration="mul", norm="layer", duplex=True, k=4, use_pos=True, kmeans_iters=3, img2ltnt=True))
+    out.append(dict(integration="mul", norm="layer", duplex=False, k=8, use_pos=True, num_heads=2))
+    out.append(dict(integration="both", norm="layer", duplex=False, k=5, use_pos=True, num_heads=4))
     return out
 
 
 def case_name(c):
-    ext = (f"-it{c['kmeans_iters']}" if c.get("kmeans_iters", 1) > 1 else "") + ("-i2l" if c.get("img2ltnt") else "")
+    ext = (f"-it{c['kmeans_iters']}" if c.get("kmeans_iters", 1) > 1 else "") + ("-i2l" if c.get("img2ltnt") else "") \
+        + (f"-h{c['num_heads']}" if c.get("num_heads", 1) > 1 else "")
     return f"{c['integration']}-{c['norm']}-{'duplex' if c['duplex'] else 'simplex'}-k{c['k']}-{'pos' if c['use_pos'] else 'nopos'}{ext}"
 
 
@@ -58,7 +61,7 @@ def main():
         norm = None if c["norm"] == "none" else c["norm"]
         out, att, cen = ob.transformer_layer(x, y, w, integration=c["integration"], norm=norm, duplex=c["duplex"],
                                              use_pos=c["use_pos"], return_att=True, kmeans_iters=c.get("kmeans_iters", 1),
-                                             img2ltnt=bool(c.get("img2ltnt")))
+                                             img2ltnt=bool(c.get("img2ltnt")), num_heads=c.get("num_heads", 1))
         name = case_name(c)
         store[name + "/out"] = out.permute(0, 2, 3, 1).contiguous().numpy().astype(np.float32)   # channels-last
         store[name + "/att"] = att.numpy().astype(np.float32)

@@ -59,9 +59,9 @@ def check_close(got, ref64, path, what="", tol_scale=1.0, e_ref=0.0):
     assert rel_rms <= rrms, f"{what}: path={path} rel_rms {rel_rms:.3e} > {rrms}"
 
 
-def make_layer(gf, dev, C, D, k, p, integration, norm, duplex, use_pos, exact, w, kmeans_iters=1, img2ltnt=False):
+def make_layer(gf, dev, C, D, k, p, integration, norm, duplex, use_pos, exact, w, kmeans_iters=1, img2ltnt=False, num_heads=1):
     attn = gf.BipartiteAttention(C, D, k, pos_dim=p, integration=integration, norm=norm, kmeans=duplex, use_pos=use_pos,
-                                 exact_fp32=exact, kmeans_iters=kmeans_iters, img2ltnt=img2ltnt).to(dev)
+                                 exact_fp32=exact, kmeans_iters=kmeans_iters, img2ltnt=img2ltnt, num_heads=num_heads).to(dev)
     with torch.no_grad():
         for n, prm in attn.named_parameters():
             prm.copy_(w[n].float())
@@ -69,11 +69,11 @@ def make_layer(gf, dev, C, D, k, p, integration, norm, duplex, use_pos, exact, w
 
 
 def run_layer(gf, dev, x64_nchw, y64, w, *, integration, norm, duplex, use_pos, exact, return_att=True, centroids=None,
-              kmeans_iters=1, img2ltnt=False):
+              kmeans_iters=1, img2ltnt=False, num_heads=1):
     B, C, H, W = x64_nchw.shape
     k, D = y64.shape[1], y64.shape[2]
     p = w["pos_latent"].shape[1]
-    attn = make_layer(gf, dev, C, D, k, p, integration, norm, duplex, use_pos, exact, w, kmeans_iters, img2ltnt)
+    attn = make_layer(gf, dev, C, D, k, p, integration, norm, duplex, use_pos, exact, w, kmeans_iters, img2ltnt, num_heads)
     x = x64_nchw.permute(0, 2, 3, 1).contiguous().float().to(dev)
     y = y64.float().to(dev)
     with torch.no_grad():
@@ -94,7 +94,8 @@ def test_layer_matches_golden(gf, cuda_dev, idx, exact):
     x, y, w = mg.make_inputs(c, 100 + idx)
     norm = None if c["norm"] == "none" else c["norm"]
     out, att, cen, path = run_layer(gf, cuda_dev, x, y, w, integration=c["integration"], norm=norm, duplex=c["duplex"],
-                                    use_pos=c["use_pos"], exact=exact, kmeans_iters=c.get("kmeans_iters", 1), img2ltnt=bool(c.get("img2ltnt")))
+                                    use_pos=c["use_pos"], exact=exact, kmeans_iters=c.get("kmeans_iters", 1), img2ltnt=bool(c.get("img2ltnt")),
+                                    num_heads=c.get("num_heads", 1))
     if exact:
         assert path == "simt_fp32"
     check_close(out, torch.from_numpy(gold[name + "/out"]), path, name + "/out", tol_scale=1.5 if c.get("kmeans_iters", 1) > 1 else 1.0)
@@ -284,9 +285,12 @@ def test_errors_are_loud(gf, cuda_dev):
             attn(x.transpose(1, 2), y)
         with pytest.raises(ValueError):
             attn(x, y[:, :, :8].contiguous().reshape(2, 4, 4))
-    a2 = gf.BipartiteAttention(64, 16, 4, num_heads=2).to(cuda_dev)
+    a2 = gf.BipartiteAttention(64, 16, 4, num_heads=8).to(cuda_dev)            # 8 heads x 8 columns > 32 table columns
     with torch.no_grad(), pytest.raises(RuntimeError, match="num_heads"):
         a2(x, y)
+    a3 = gf.BipartiteAttention(64, 16, 4, num_heads=2, kmeans=True).to(cuda_dev)   # multi-head duplex: not built
+    with torch.no_grad(), pytest.raises(RuntimeError, match="num_heads"):
+        a3(x, y)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -931,3 +935,35 @@ def test_kmeans_iters_and_img2ltnt(gf, cuda_dev, C, H, W, k, integration, iters,
     else:
         check_close(out2, ref.permute(0, 2, 3, 1), path, "kmeans/out-no-centroids", tol_scale=scale)
     assert (att.cpu().double() - ratt).abs().max() <= (1e-4 if path == "simt_fp32" else 5e-3)
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["fp32", "default"])
+@pytest.mark.parametrize("C,H,W,k,heads,integration,norm", [(128, 16, 16, 16, 2, "mul", "layer"), (256, 16, 16, 8, 4, "both", "layer"),
+                                                             (512, 8, 8, 8, 2, "mul", "layer"), (64, 32, 32, 5, 2, "add", "none"),
+                                                             (96, 10, 13, 7, 2, "mul", "instance"), (128, 32, 32, 16, 2, "mul", "layer")])
+def test_multi_head_simplex(gf, cuda_dev, C, H, W, k, heads, integration, norm, exact):
+    """num_heads > 1 (simplex): the heads are column segments of the per-image tables, one softmax per segment; output and the
+    head-averaged attention map against the fp64 oracle (direct form with split heads)."""
+    D = p = 16
+    B = 3
+    g = torch.Generator().manual_seed(C + k + heads)
+    x = torch.randn(B, C, H, W, generator=g, dtype=torch.float64) * 1.2 + 0.1
+    y = torch.randn(B, k, D, generator=g, dtype=torch.float64)
+    w = ob.init_params(C, D, k, p, integration, False, seed=13, bias_std=0.3)
+    nrm = None if norm == "none" else norm
+    ref, ratt, _ = ob.transformer_layer(x, y, w, integration=integration, norm=nrm, num_heads=heads, return_att=True)
+    attn = gf.BipartiteAttention(C, D, k, pos_dim=p, integration=integration, norm=nrm, num_heads=heads, exact_fp32=exact).to(cuda_dev)
+    with torch.no_grad():
+        for n, prm in attn.named_parameters():
+            prm.copy_(w[n].float())
+        out, att, _ = attn(x.permute(0, 2, 3, 1).contiguous().float().to(cuda_dev), y.float().to(cuda_dev), return_att=True)
+    path = gf._lib.last_path()
+    check_close(out, ref.permute(0, 2, 3, 1), path, f"heads{heads}/out")
+    assert att.shape == (B, k, H, W)
+    assert (att.cpu().double() - ratt).abs().max() <= (1e-5 if path == "simt_fp32" else 5e-3)
+    assert (att.sum(dim=1) - 1).abs().max() < 1e-5
+    # training path: composite backward with split heads
+    xg = x.permute(0, 2, 3, 1).contiguous().float().to(cuda_dev).requires_grad_(True)
+    o2, _, _ = attn(xg, y.float().to(cuda_dev))
+    o2.square().mean().backward()
+    assert torch.isfinite(xg.grad).all() and xg.grad.abs().max() > 0

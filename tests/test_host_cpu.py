@@ -46,7 +46,7 @@ def test_sizes_and_validation(gf):
     assert L.workspace_bytes(d2) > w1 and L.folded_floats(d2) == f1          # folded weights do not depend on B
     dd = L.make_desc(4, 16, 16, 128, 16, 32, pos_dim=32, duplex=True)
     assert L.folded_floats(dd) > f1 and L.workspace_bytes(dd) > w1
-    for bad, msg in [(dict(C=100), "C=100"), (dict(k=33), "k=33"), (dict(heads=2), "num_heads"), (dict(pos_dim=6), "pos_dim")]:
+    for bad, msg in [(dict(C=100), "C=100"), (dict(k=33), "k=33"), (dict(heads=8), "num_heads"), (dict(pos_dim=6), "pos_dim")]:
         kw = dict(B=1, H=8, W=8, C=64, k=4, D=16, heads=1, pos_dim=16)
         kw.update(bad)
         desc = L.make_desc(kw["B"], kw["H"], kw["W"], kw["C"], kw["k"], kw["D"], heads=kw["heads"], pos_dim=kw["pos_dim"])

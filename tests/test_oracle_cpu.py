@@ -27,7 +27,8 @@ def _run_case(c, seed, dtype=torch.float64):
     x, y = x.to(dtype), y.to(dtype)
     w = {k: v.to(dtype) for k, v in w.items()}
     return ob.transformer_layer(x, y, w, integration=c["integration"], norm=norm, duplex=c["duplex"],
-                                use_pos=c["use_pos"], return_att=True, kmeans_iters=c.get("kmeans_iters", 1), img2ltnt=bool(c.get("img2ltnt")))
+                                use_pos=c["use_pos"], return_att=True, kmeans_iters=c.get("kmeans_iters", 1), img2ltnt=bool(c.get("img2ltnt")),
+                                num_heads=c.get("num_heads", 1))
 
 
 @pytest.mark.parametrize("idx", range(len(mg.cases())))
