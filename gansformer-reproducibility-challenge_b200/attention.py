@@ -31,7 +31,7 @@ IMG2LTNT_PARAMS = ("wi2l", "bi2l")       # g_img2ltnt: centroid -> latent gain
 
 
 def param_shapes(dim: int, latent_dim: int, components_num: int, pos_dim: int, integration: str, duplex: bool,
-                 kmeans_iters: int = 1, img2ltnt: bool = False):
+                 kmeans_iters: int = 1, img2ltnt: bool = False, iterative: bool = False):
     """Raw parameter shapes, [fan_in, fan_out]; equalised-LR scaling happens inside the library."""
     C, D, k, p = dim, latent_dim, components_num, pos_dim
     cout = 2 * C if integration == "both" else C
@@ -40,7 +40,7 @@ def param_shapes(dim: int, latent_dim: int, components_num: int, pos_dim: int, i
     if duplex:
         shapes.update({"wq2": (D, C), "bq2": (C,), "wpq2": (p, C), "wk2": (C, C), "bk2": (C,), "wpk2": (p, C),
                        "wv2": (C, C), "bv2": (C,), "wkc": (C, C)})
-        if kmeans_iters > 1:
+        if kmeans_iters > 1 or iterative:
             shapes["wcq"] = (C, C)
         if img2ltnt:
             shapes.update({"wi2l": (C, D), "bi2l": (D,)})
@@ -147,11 +147,12 @@ def _plan_call(lib, shape, y: torch.Tensor, params: Dict[str, torch.Tensor], pla
     desc = _lib.make_desc(B, H, W, C, k, D, heads=num_heads, norm=norm, integration=integration, pos_dim=pos_dim,
                           duplex=duplex, flags=flags)
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    names = SIMPLEX_PARAMS + (DUPLEX_PARAMS if duplex else ()) + (KMEANS_PARAMS if int(duplex) > 1 else ()) \
+    names = SIMPLEX_PARAMS + (DUPLEX_PARAMS if duplex else ()) + (KMEANS_PARAMS if (int(duplex) > 1 or flags & _lib.FLAG_CENTROIDS_INIT) else ()) \
         + (IMG2LTNT_PARAMS if (duplex and flags & _lib.FLAG_IMG2LTNT) else ())
     if weights_version is None:
         weights_version = tuple((params[n].data_ptr(), params[n]._version) for n in names)
-    fkey = (H, W, k, D, C, pos_dim, integration, int(duplex), num_heads, flags & _lib.FLAG_IMG2LTNT, str(dev), weights_version, weights_epoch())
+    fkey = (H, W, k, D, C, pos_dim, integration, int(duplex), num_heads, flags & (_lib.FLAG_IMG2LTNT | _lib.FLAG_CENTROIDS_INIT), str(dev),
+            weights_version, weights_epoch())
     if plan.folded is None or plan.folded_key != fkey or FORCE_REFOLD:
         nfl = _lib.folded_floats(desc)
         if plan.folded is None or plan.folded.numel() != nfl or plan.folded.device != dev:
@@ -164,7 +165,7 @@ def _plan_call(lib, shape, y: torch.Tensor, params: Dict[str, torch.Tensor], pla
         _lib.check(lib.gf_attn_fold_weights(ctypes.byref(desc), ctypes.byref(wstruct), plan.folded.data_ptr(), stream),
                    "gf_attn_fold_weights")
         plan.folded_key = fkey
-    wkey = (B, H, W, C, k, D, pos_dim, integration, norm, int(duplex), num_heads, flags & _lib.FLAG_IMG2LTNT, str(dev))
+    wkey = (B, H, W, C, k, D, pos_dim, integration, norm, int(duplex), num_heads, flags & (_lib.FLAG_IMG2LTNT | _lib.FLAG_CENTROIDS_INIT), str(dev))
     ws = plan.ws.get(wkey)
     if ws is None:
         ws = torch.empty(_lib.workspace_bytes(desc), dtype=torch.uint8, device=dev)
@@ -178,10 +179,12 @@ def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[s
                                 centroids: Optional[torch.Tensor] = None, exact_fp32: bool = False,
                                 out: Optional[torch.Tensor] = None, weights_version=None, postop: Optional[dict] = None,
                                 stage: str = "all", x_shape: Optional[Tuple[int, int, int, int]] = None,
-                                need_centroids: bool = True, img2ltnt: bool = False):
+                                need_centroids: bool = True, img2ltnt: bool = False, centroids_init: Optional[torch.Tensor] = None):
     """x [B,H,W,C] channels-last fp32 (CUDA), y [B,k,D].  Returns (x', att [B,k,H,W] | None, centroids | None).
 
     duplex: False / 0 = simplex; True / n >= 1 = duplex with n k-means iterations (kmeans_iters).  img2ltnt: g_img2ltnt.
+    centroids: skip pass A and take these as the centroids (GF_FLAG_CENTROIDS_IN).  centroids_init (`iterative`): the previous
+    attention layer's centroids [B,k,C]; the first k-means iteration takes its queries from them (GF_FLAG_CENTROIDS_INIT).
 
     postop (optional): dict(bias [C] | None, noise [H*W] or [B,H*W] | None, strength 0-d tensor | None, act 'lrelu' |
     'linear', gain float, in_scale [B,C] | None, post_scale [B,C] | None, rgb_w [B,3,C] + rgb_out [B,3,H,W] (+ rgb_bias [3]))
@@ -212,7 +215,8 @@ def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[s
     k = y.shape[1]
     flags = ((_lib.FLAG_FP32_EXACT if exact_fp32 else 0) | (_lib.FLAG_CENTROIDS_IN if (duplex and centroids is not None) else 0)
              | (_lib.FLAG_TABLES_READY if (duplex and stage == "token") else 0)
-             | (_lib.FLAG_IMG2LTNT if (duplex and img2ltnt) else 0))
+             | (_lib.FLAG_IMG2LTNT if (duplex and img2ltnt) else 0)
+             | (_lib.FLAG_CENTROIDS_INIT if (duplex and centroids_init is not None and centroids is None) else 0))
 
     with torch.cuda.device(dev):
         desc, ws, stream = _plan_call(lib, (B, H, W, C), y, params, plan, integration=integration, norm=norm, duplex=duplex,
@@ -232,7 +236,12 @@ def bipartite_attention_forward(x: torch.Tensor, y: torch.Tensor, params: Dict[s
         if duplex:
             if timer is not None:
                 ev0.record()
-            if centroids is None:
+            if centroids is None and centroids_init is not None:
+                if tuple(centroids_init.shape) != (B, k, C):
+                    raise ValueError(f"centroids_init must be [B, k, C] = {(B, k, C)}, got {tuple(centroids_init.shape)}")
+                cen = centroids_init.detach().to(torch.float32).clone()        # in/out buffer: carried-in centroids -> this layer's
+                _check_tensor(cen, "centroids_init", dev)
+            elif centroids is None:
                 # need_centroids=False: the keys are built straight from the attention-weighted means (Wv2 / bv2 folded into
                 # the key projection), one [B*k, C] x [C, C] product less on the critical path
                 cen = torch.empty((B, k, C), dtype=torch.float32, device=dev) if need_centroids else None
@@ -328,7 +337,8 @@ class BipartiteAttention(nn.Module):
 
     def __init__(self, dim: int, latent_dim: int, components_num: int, pos_dim: Optional[int] = None,
                  num_heads: int = 1, integration: str = "mul", norm: Optional[str] = "layer", kmeans: bool = False,
-                 kmeans_iters: int = 1, use_pos: bool = True, att_dp: float = 0.0, exact_fp32: bool = False, img2ltnt: bool = False):
+                 kmeans_iters: int = 1, use_pos: bool = True, att_dp: float = 0.0, exact_fp32: bool = False, img2ltnt: bool = False,
+                 iterative: bool = False):
         super().__init__()
         if kmeans_iters < 1 or kmeans_iters > 16:
             raise ValueError("kmeans_iters must be in 1..16")
@@ -340,8 +350,9 @@ class BipartiteAttention(nn.Module):
         self.pos_dim = latent_dim if pos_dim is None else pos_dim
         self.num_heads, self.integration, self.norm = num_heads, integration, norm
         self.duplex, self.use_pos, self.exact_fp32 = bool(kmeans), use_pos, exact_fp32
-        self.kmeans_iters, self.img2ltnt = int(kmeans_iters), bool(img2ltnt)
-        for name, shape in param_shapes(dim, latent_dim, components_num, self.pos_dim, integration, self.duplex, self.kmeans_iters, self.img2ltnt).items():
+        self.kmeans_iters, self.img2ltnt, self.iterative = int(kmeans_iters), bool(img2ltnt), bool(iterative and kmeans)
+        for name, shape in param_shapes(dim, latent_dim, components_num, self.pos_dim, integration, self.duplex, self.kmeans_iters, self.img2ltnt,
+                                        self.iterative).items():
             init = torch.zeros(shape) if name.startswith("b") else torch.randn(shape)
             self.register_parameter(name, nn.Parameter(init))
         self._plan = _Plan()
@@ -351,19 +362,22 @@ class BipartiteAttention(nn.Module):
 
     def forward(self, x: torch.Tensor, y: torch.Tensor, centroids: Optional[torch.Tensor] = None,
                 return_att: bool = False, out: Optional[torch.Tensor] = None, postop: Optional[dict] = None,
-                stage: str = "all", need_centroids: bool = True):
+                stage: str = "all", need_centroids: bool = True, centroids_init: Optional[torch.Tensor] = None):
         """x [B,H,W,C] channels-last, y [B,k,D] -> (x', att [B,k,H,W] | None, centroids [B,k,C] | None).
         stage="token": the latent-only tables were already built by ``prepare`` / ``prologue_batch`` (same y, same in_scale)."""
         if torch.is_grad_enabled() and (x.requires_grad or y.requires_grad or any(p.requires_grad for p in self.parameters())):
             if postop is not None:
                 raise RuntimeError("the fused post-op is inference-only; apply noise/bias/activation outside when training")
+            if centroids_init is not None:
+                raise RuntimeError("iterative centroid carry (centroids_init) is an inference feature in this build")
             from .autograd import bipartite_attention_autograd
             return bipartite_attention_autograd(self, x, y, centroids, return_att)
         return bipartite_attention_forward(x, y, self.param_dict(), self._plan, integration=self.integration,
                                            norm=self.norm, duplex=self.kmeans_iters if self.duplex else 0, num_heads=self.num_heads,
                                            use_pos=self.use_pos, return_att=return_att, centroids=centroids,
                                            exact_fp32=self.exact_fp32, out=out, postop=postop, stage=stage,
-                                           need_centroids=need_centroids, img2ltnt=self.img2ltnt)
+                                           need_centroids=need_centroids, img2ltnt=self.img2ltnt,
+                                           centroids_init=centroids_init if self.iterative else None)
 
     @torch.no_grad()
     def prepare(self, y: torch.Tensor, x_shape: Tuple[int, int, int, int], in_scale: Optional[torch.Tensor] = None):

@@ -182,7 +182,8 @@ int gf_attn_duplex_fwd_ex(const gf_attn_desc* desc, const float* X, const float*
   if (rc) return rc;
   if (!L.duplex) { set_error("gf_attn_duplex_fwd: desc.duplex is 0"); return GF_ERR_INVALID; }
   if (!X || !Y || !folded || !Xout || !ws_) { set_error("gf_attn_duplex_fwd: null pointer"); return GF_ERR_INVALID; }
-  if (!centroids_inout && (desc->flags & GF_FLAG_CENTROIDS_IN)) { set_error("gf_attn_duplex_fwd: GF_FLAG_CENTROIDS_IN without centroids"); return GF_ERR_INVALID; }
+  if (!centroids_inout && (desc->flags & (GF_FLAG_CENTROIDS_IN | GF_FLAG_CENTROIDS_INIT))) { set_error("gf_attn_duplex_fwd: GF_FLAG_CENTROIDS_IN / _INIT without centroids"); return GF_ERR_INVALID; }
+  if ((desc->flags & GF_FLAG_CENTROIDS_IN) && (desc->flags & GF_FLAG_CENTROIDS_INIT)) { set_error("gf_attn_duplex_fwd: GF_FLAG_CENTROIDS_IN and _INIT are exclusive"); return GF_ERR_INVALID; }
   if ((rc = check_device())) return rc;
   float* ws = (float*)ws_;
   cudaStream_t st = (cudaStream_t)stream;
@@ -195,10 +196,11 @@ int gf_attn_duplex_fwd_ex(const gf_attn_desc* desc, const float* X, const float*
     // load-side scale d (x_in = x * d): pass A sees x only through x.M^T and A.x, so d is folded into M and into Xbar
     const float* isc = post ? post->in_scale : nullptr;
     const int isc_ld = post ? post->in_scale_ld : 0;
-    if (!(desc->flags & GF_FLAG_TABLES_READY) && (rc = duplex_tables(L, desc, Y, folded, ws, st, isc, isc_ld))) return rc;
+    const bool cen_init = (desc->flags & GF_FLAG_CENTROIDS_INIT) != 0;      // `iterative`: the first queries come from the carried-in centroids
+    if (!cen_init && !(desc->flags & GF_FLAG_TABLES_READY) && (rc = duplex_tables(L, desc, Y, folded, ws, st, isc, isc_ld))) return rc;
     const bool cen_tc = tc_centroid_supported(L, desc);
     for (int it = 0; it < L.iters; ++it) {
-      if (it > 0 && (rc = duplex_tables_from_centroids(L, desc, cen, Y, folded, ws, st, isc, isc_ld))) return rc;   // queries from the centroids
+      if ((it > 0 || cen_init) && (rc = duplex_tables_from_centroids(L, desc, cen, Y, folded, ws, st, isc, isc_ld))) return rc;   // queries from the centroids
       if (cen_tc) {
         if ((rc = centroid_pass_tc(L, desc, X, ws, st, isc, isc_ld))) return rc;
         if (L.nsplit_cen > 1 && (rc = centroid_merge(L, ws, st, isc, isc_ld))) return rc;   // one split: the kernel wrote Xbar itself
@@ -208,8 +210,9 @@ int gf_attn_duplex_fwd_ex(const gf_attn_desc* desc, const float* X, const float*
         set_centroid_path(GF_PATH_SIMT_FP32);
       }
       // centroids = Xbar @ Wv2_e + bv2
+      // (fp32 when the centroids feed further k-means iterations or are carried on: see duplex_tables_from_centroids)
       if (need_cen && (rc = gemm(st, L.B * L.k, L.C, L.C, ws + L.w_XBAR, L.C, false, folded + L.f_WV2, L.C, false, cen, L.C, 1.f,
-                                 nullptr, 0, 1, folded + L.f_BV2, cen_tc)))
+                                 nullptr, 0, 1, folded + L.f_BV2, cen_tc && L.iters == 1 && !cen_init)))
         return rc;
     }
   }
@@ -221,7 +224,8 @@ int gf_attn_duplex_fwd_ex(const gf_attn_desc* desc, const float* X, const float*
   // V^T depends on the latents only: duplex_tables() already built it, unless pass A was skipped or the latents were modulated
   const bool keys_from_cen = cen_in || need_cen;
   if ((rc = prologue(L, desc, Yv, keys_from_cen ? cen : ws + L.w_XBAR, L.C, folded, ws, st, post ? post->in_scale : nullptr,
-                     post ? post->in_scale_ld : 0, !keys_from_cen, cen_in || L.img2ltnt)))
+                     post ? post->in_scale_ld : 0, !keys_from_cen,
+                     cen_in || L.img2ltnt || ((desc->flags & GF_FLAG_CENTROIDS_INIT) && !(desc->flags & GF_FLAG_TABLES_READY)))))
     return rc;
   return token_pass(L, desc, X, Xout, att, ws, post, st);
 }

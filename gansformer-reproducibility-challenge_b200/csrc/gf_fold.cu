@@ -69,7 +69,7 @@ int make_layout(const gf_attn_desc* d, Layout* L) {
     l.f_CM = take(k * LDK);
     l.f_MFOLD = take(C * LDK);
     l.f_QCONST = take(k * C);
-    l.f_ACQ = d->duplex > 1 ? take(C * LDK) : 0;
+    l.f_ACQ = (d->duplex > 1 || (d->flags & GF_FLAG_CENTROIDS_INIT)) ? take(C * LDK) : 0;
     l.f_WI2L = (d->flags & GF_FLAG_IMG2LTNT) ? take(C * D) : 0;
     l.f_BI2L = (d->flags & GF_FLAG_IMG2LTNT) ? take(D) : 0;
   } else {
@@ -346,8 +346,8 @@ int fold_weights(const Layout& L, const gf_attn_desc* d, const gf_attn_weights* 
     if ((rc = gemm(st, k, C, pos ? p : 0, w->pos_latent, p, false, w->wpq2, C, false, f + L.f_QCONST, C, rp, nullptr, 0, 1, w->bq2))) return rc;
     if ((rc = gemm(st, D, LDK, C, w->wq2, C, false, f + L.f_MFOLD, LDK, false, f + L.f_AM, LDK, rD))) return rc;
     if ((rc = gemm(st, k, LDK, C, f + L.f_QCONST, C, false, f + L.f_MFOLD, LDK, false, f + L.f_CM, LDK, 1.f))) return rc;
-    if (L.iters > 1) {          // k-means iterations >= 2: queries from the centroids, M = Cen (wcq_e mfold) + CM
-      if (!w->wcq) { set_error("fold_weights: desc.duplex > 1 needs wcq"); return GF_ERR_INVALID; }
+    if (L.f_ACQ) {              // k-means iterations >= 2 / carried-in centroids: queries from the centroids, M = Cen (wcq_e mfold) + CM
+      if (!w->wcq) { set_error("fold_weights: desc.duplex > 1 / GF_FLAG_CENTROIDS_INIT need wcq"); return GF_ERR_INVALID; }
       if ((rc = gemm(st, C, LDK, C, w->wcq, C, false, f + L.f_MFOLD, LDK, false, f + L.f_ACQ, LDK, rC))) return rc;
     }
     if (L.img2ltnt) {
@@ -751,8 +751,10 @@ int duplex_tables_from_centroids(const Layout& L, const gf_attn_desc* d, const f
                                  cudaStream_t st, const float* in_scale, int in_scale_ld) {
   int rc;
   const int tf32 = tc_centroid_supported(L, d) ? 1 : 0;
+  // fp32 product: the queries feed a softmax over the n grid cells, and the k-means loop feeds its own output back -- a TF32 error
+  // here is amplified by every further iteration (measured: image rel-RMS 3.2e-3 with TF32 against 4.7e-4 for a plain duplex layer)
   if ((rc = gemm(st, L.B * L.k, L.LDK, L.C, cen, L.C, false, f + L.f_ACQ, L.LDK, false, ws + L.w_MALL, L.LDK, 1.f,
-                 f + L.f_CM, L.LDK, L.k, nullptr, tf32 != 0)))
+                 f + L.f_CM, L.LDK, L.k, nullptr, false)))
     return rc;
   const int npos = ((L.H + L.W) * L.KP + 1023) / 1024;
   const int nblk = npos + (L.KP * L.C + 256 * 8 - 1) / (256 * 8);

@@ -213,7 +213,7 @@ class SynthesisLayer(nn.Module):
                 and _inference(self.weight, self.bias, self.noise_strength, *a.parameters()))
 
     def forward(self, x, w_glob, y, noise_mode="const", centroids=None, return_att=False, styles=None,
-                prescaled=False, post_scale=None, prepared=None, rgb=None):
+                prescaled=False, post_scale=None, prepared=None, rgb=None, centroids_init=None):
         """prescaled: x already carries this layer's style scale.  post_scale [B,C]: the NEXT convolution's style scale,
         folded into this layer's store (only honoured -- and only passed by SynthesisNetwork -- when `fusable`).
         rgb: dict(rgb_w [B,3,C], rgb_bias [3], rgb_out [B,3,H,W]) -- the block's tRGB computed by the attention kernel's store side
@@ -254,9 +254,10 @@ class SynthesisLayer(nn.Module):
                     torch.cuda.current_stream(x.device).wait_event(prepared[0])
                 xo, att, centroids = self.attention(xl, y, centroids=centroids, return_att=return_att, postop=post,
                                                     stage="token" if prepared is not None else "all",
-                                                    need_centroids=False)     # the synthesis network never reads them back
+                                                    need_centroids=self.attention.iterative,     # read back only to carry them on
+                                                    centroids_init=centroids_init)
                 return xo.permute(0, 3, 1, 2), att, centroids
-            xo, att, centroids = self.attention(xl, y, centroids=centroids, return_att=return_att)
+            xo, att, centroids = self.attention(xl, y, centroids=centroids, return_att=return_att, centroids_init=centroids_init)
             x = xo.permute(0, 3, 1, 2)                                  # back to an NCHW view of channels-last data
         x = ops.bias_act(x, self.bias, "lrelu", noise=noise, strength=self.noise_strength)
         if post_scale is not None:
@@ -295,12 +296,10 @@ class SynthesisNetwork(nn.Module):
         self.layers = nn.ModuleList()
         self.torgbs = nn.ModuleList()
         self.layer_res: List[int] = []
-        if attn_kwargs.pop("iterative", False):
-            # `iterative` carries the centroids of one layer into the next layer's k-means initialisation.  The
-            # channel width changes between resolutions and the reference source that would define the carry is not
-            # available, so the option is refused instead of being silently ignored.
-            raise NotImplementedError("iterative=True (cross-layer centroid carry) is not implemented; use iterative=False "
-                                      "(BipartiteAttention.forward(centroids=...) skips pass A for a caller-managed carry)")
+        # `iterative` ([SPEC]): a duplex layer's centroids initialise the k-means of the NEXT attention layer when the
+        # channel width is the same (both layers of a block; consecutive blocks of equal width): that layer's first queries come
+        # from the carried centroids (through wcq) instead of from the latents.  Across a change of width nothing is carried.
+        self.iterative = bool(attn_kwargs.get("iterative", False)) and bool(attn_kwargs.get("kmeans", False))
         for res in self.block_resolutions:
             out_ch = nf(res, fmap_base, fmap_max)
             use_att = transformer and components_num > 0 and g_start_res <= res <= g_end_res
@@ -357,6 +356,7 @@ class SynthesisNetwork(nn.Module):
         feats = []
         li = 0
         block_prescaled = False
+        cen_prev = None
         for bi, res in enumerate(self.block_resolutions):
             nl = 1 if res == 4 else 2
             prescaled = block_prescaled
@@ -366,6 +366,10 @@ class SynthesisNetwork(nn.Module):
             rgb = None
             for j in range(nl):
                 layer = self.layers[li]
+                cen_init = None                     # iterative: carry the previous attention layer's centroids when the widths match
+                if self.iterative and layer.attention is not None and cen_prev is not None and cen_prev.shape[2] == layer.weight.shape[0] \
+                        and _inference(*layer.attention.parameters()):
+                    cen_init = cen_prev
                 # conv0 -> conv1 inside a block has a single consumer: conv1's style scale is folded into conv0's store
                 post_scale = None
                 if j == 0 and nl == 2 and styles_all[li + 1] is not None and layer.fusable(x) and not return_features:
@@ -382,8 +386,11 @@ class SynthesisNetwork(nn.Module):
                         rgb = torch.empty((B, 3, res, res), device=x.device, dtype=torch.float32)
                         rgb_args = dict(rgb_w=rgb_w, rgb_bias=tg.bias, rgb_out=rgb)
                         post_scale = nxt
-                x, att, _ = layer(x, w_glob, y, noise_mode=noise_mode, return_att=return_att, styles=styles_all[li],
-                                  prescaled=prescaled, post_scale=post_scale, prepared=prepared[li], rgb=rgb_args)
+                x, att, cen_out = layer(x, w_glob, y, noise_mode=noise_mode, return_att=return_att, styles=styles_all[li],
+                                        prescaled=prescaled, post_scale=post_scale, prepared=prepared[li], rgb=rgb_args,
+                                        centroids_init=cen_init)
+                if layer.attention is not None:
+                    cen_prev = cen_out if self.iterative else None
                 prescaled = post_scale is not None
                 li += 1
                 if att is not None:
@@ -409,13 +416,14 @@ class Generator(nn.Module):
                  transformer: bool = True, g_start_res: int = 8, g_end_res: Optional[int] = None, kmeans: bool = False,
                  kmeans_iters: int = 1, iterative: bool = False, integration: str = "mul", norm: Optional[str] = "layer",
                  use_pos: bool = True, pos_dim: Optional[int] = None, num_heads: int = 1, mapping_layers: int = 8,
-                 fmap_base: int = 16384, fmap_max: int = 512, exact_fp32: bool = False, ltnt2ltnt: bool = False):
+                 fmap_base: int = 16384, fmap_max: int = 512, exact_fp32: bool = False, ltnt2ltnt: bool = False, g_img2ltnt: bool = False):
         super().__init__()
         # D = latent_size // components_num unless given
         self.latent_dim = latent_dim if latent_dim is not None else max(latent_size // max(components_num, 1), 1)
         self.components_num, self.resolution = components_num, resolution
         attn_kwargs = dict(pos_dim=pos_dim, num_heads=num_heads, integration=integration, norm=norm, kmeans=kmeans,
-                           kmeans_iters=kmeans_iters, use_pos=use_pos, exact_fp32=exact_fp32, iterative=iterative)
+                           kmeans_iters=kmeans_iters, use_pos=use_pos, exact_fp32=exact_fp32, iterative=iterative,
+                           img2ltnt=bool(g_img2ltnt and kmeans))
         self.mapping = MappingNetwork(self.latent_dim, components_num, num_layers=mapping_layers, ltnt2ltnt=ltnt2ltnt,
                                       integration=integration, norm=norm, exact_fp32=exact_fp32)
         self.synthesis = SynthesisNetwork(resolution, self.latent_dim, components_num, fmap_base=fmap_base, fmap_max=fmap_max,

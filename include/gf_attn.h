@@ -46,6 +46,9 @@ enum {
   GF_FLAG_FP32_EXACT = 1,   /* force the CUDA-core fp32-FMA kernel (tight-tolerance mode); default = tcgen05 TF32 */
   GF_FLAG_CENTROIDS_IN = 2, /* duplex: skip pass A, take centroids_inout as input (iterative=True upstream) */
   GF_FLAG_TABLES_READY = 4, /* duplex: the pass-A query tables and V^T are already in ws (gf_attn_prologue_batch ran for this layer) */
+  GF_FLAG_CENTROIDS_INIT = 16, /* duplex: `iterative` -- centroids_inout holds the previous attention layer's centroids on entry; the
+                               first k-means iteration takes its queries from them (through wcq) instead of from the latents; on
+                               return it holds this layer's centroids */
   GF_FLAG_IMG2LTNT = 8      /* duplex: g_img2ltnt -- before pass B the latents are modulated by the centroids,
                                Y <- LN(Y) (1 + dense(Cen, wi2l) + bi2l); values of pass B from the modulated latents */
 };

@@ -144,7 +144,8 @@ def _split_heads(t: Tensor, h: int) -> Tensor:
 def transformer_layer(x_nchw: Tensor, y: Tensor, w: Dict[str, Tensor], *, integration: str = "mul",
                       norm: Optional[str] = "layer", duplex: bool = False, num_heads: int = 1,
                       use_pos: bool = True, return_att: bool = False,
-                      centroids_in: Optional[Tensor] = None, kmeans_iters: int = 1, img2ltnt: bool = False):
+                      centroids_in: Optional[Tensor] = None, kmeans_iters: int = 1, img2ltnt: bool = False,
+                      centroids_init: Optional[Tensor] = None):
     """Bipartite attention, direct form.
 
     x_nchw [B,C,H,W]; y [B,k,D] (the k local latents).  Returns (x' [B,C,H,W], att [B,k,H,W] or None,
@@ -155,6 +156,9 @@ def transformer_layer(x_nchw: Tensor, y: Tensor, w: Dict[str, Tensor], *, integr
     img2ltnt (duplex; SURVEY A.3 [SPEC] g_img2ltnt): before pass B the latents are modulated by the centroids,
     Y <- LN(Y) (1 + dense(Cen, wi2l) + bi2l) (layer norm over D, eps as att_norm, no affine); the values of pass B come from
     the modulated latents, the keys from the centroids.  The update is local to the layer (the caller's latents are not changed).
+    centroids_init (duplex; `iterative=True` upstream, [SPEC]): centroids carried over from the previous attention layer of the same
+    channel width initialise the k-means: the FIRST iteration already takes its queries from them (through wcq) instead of from the
+    latents.
     """
     B, C, H, W = x_nchw.shape
     n = H * W
@@ -180,8 +184,9 @@ def transformer_layer(x_nchw: Tensor, y: Tensor, w: Dict[str, Tensor], *, integr
                 Qy = Qy + _dense(Pl, w["wpq2"])[None]
                 Kx = Kx + _dense(Pg, w["wpk2"])[None]
             Vx = _dense(X, w["wv2"], w["bv2"])
+            centroids = centroids_init
             for it in range(max(1, kmeans_iters)):
-                if it > 0:                                   # queries from the previous centroids
+                if it > 0 or centroids_init is not None:     # queries from the previous centroids (carried in, or of the last iteration)
                     Qy = _dense(centroids, w["wcq"], w["bq2"])
                     if use_pos:
                         Qy = Qy + _dense(Pl, w["wpq2"])[None]

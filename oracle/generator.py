@@ -70,7 +70,8 @@ def generator_forward(sd: Dict[str, torch.Tensor], z: torch.Tensor, *, resolutio
                       latent_dim: int, integration="mul", norm="layer", duplex=False, use_pos=True, num_heads=1,
                       truncation_psi: float = 1.0, noise_mode: str = "const", mapping_layers: int = 8,
                       g_start_res: int = 8, g_end_res: Optional[int] = None, dtype=torch.float64,
-                      return_att: bool = False, return_features: bool = False):
+                      return_att: bool = False, return_features: bool = False, kmeans_iters: int = 1, img2ltnt: bool = False,
+                      iterative: bool = False):
     """z [B, k+1, D] -> img [B, 3, R, R] (NCHW).  `sd` = product Generator.state_dict() (any device/dtype)."""
     sd = {k_: v.detach().to("cpu", dtype) if v.is_floating_point() else v.detach().cpu() for k_, v in sd.items()}
     z = z.detach().to("cpu", dtype)
@@ -101,6 +102,7 @@ def generator_forward(sd: Dict[str, torch.Tensor], z: torch.Tensor, *, resolutio
     atts: List[torch.Tensor] = []
     feats: List[torch.Tensor] = []
     li = 0
+    cen_prev = None
     res_list = [2 ** i for i in range(2, int(math.log2(resolution)) + 1)]
     for bi, res in enumerate(res_list):
         for j in range(1 if res == 4 else 2):
@@ -112,8 +114,10 @@ def generator_forward(sd: Dict[str, torch.Tensor], z: torch.Tensor, *, resolutio
             x = _modconv(x, sd[pre + ".weight"], styles, up=up, f=f)
             if (pre + ".attention.wq") in sd and g_start_res <= res <= g_end_res:
                 w = {n[len(pre) + 11:]: t for n, t in sd.items() if n.startswith(pre + ".attention.")}
-                x, att, _ = transformer_layer(x, y, w, integration=integration, norm=norm, duplex=duplex,
-                                              num_heads=num_heads, use_pos=use_pos, return_att=return_att)
+                cen_init = cen_prev if (iterative and duplex and cen_prev is not None and cen_prev.shape[2] == x.shape[1]) else None
+                x, att, cen_prev = transformer_layer(x, y, w, integration=integration, norm=norm, duplex=duplex,
+                                                     num_heads=num_heads, use_pos=use_pos, return_att=return_att,
+                                                     kmeans_iters=kmeans_iters, img2ltnt=img2ltnt, centroids_init=cen_init)
                 if att is not None:
                     atts.append(att)
                 has_att = True

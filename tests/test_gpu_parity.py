@@ -365,7 +365,7 @@ def test_generator_end_to_end(gf, cuda_dev, duplex, exact):
         assert (a.double().cpu() - r).abs().max() <= e2e["att_abs"]
 
 
-def check_image(img, ref64, mode, what):
+def check_image(img, ref64, mode, what, scale=1.0):
     """End-to-end image bound of SURVEY 8c, for an image whose range is set by random weights instead of [-1, 1]: the
     bounds are relative to the reference's peak |value|.  max-abs <= max_abs_rel_peak * peak, PSNR >= psnr_db, rel-RMS."""
     e2e = TOLERANCES["e2e"]["simt_fp32" if mode == "fp32" else "tcgen05_tf32"]
@@ -379,9 +379,9 @@ def check_image(img, ref64, mode, what):
     print(f"[e2e] {what} mode={mode} max_abs={err.max().item():.3e} peak={peak:.3f} max_abs/peak={err.max().item() / peak:.3e} "
           f"rel_rms={rel_rms:.3e} psnr={psnr:.1f} dB")
     _log_parity(dict(what=what, path="e2e-" + mode, max_abs=err.max().item(), peak=peak, rel_rms=rel_rms, psnr=psnr))
-    assert err.max().item() <= e2e["max_abs_rel_peak"] * peak, what
-    assert rel_rms <= e2e["rel_rms"], what
-    assert psnr >= e2e["psnr_db"], what
+    assert err.max().item() <= scale * e2e["max_abs_rel_peak"] * peak, what
+    assert rel_rms <= scale * e2e["rel_rms"], what
+    assert psnr >= e2e["psnr_db"] - 20.0 * math.log10(scale), what
 
 
 def _benchmark_generator(gf, dev, resolution, k, duplex, exact=False):
@@ -967,3 +967,30 @@ def test_multi_head_simplex(gf, cuda_dev, C, H, W, k, heads, integration, norm, 
     o2, _, _ = attn(xg, y.float().to(cuda_dev))
     o2.square().mean().backward()
     assert torch.isfinite(xg.grad).all() and xg.grad.abs().max() > 0
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["fp32", "default"])
+def test_generator_duplex_extensions_end_to_end(gf, cuda_dev, exact):
+    """Duplex generator with every duplex extension on -- iterative centroid carry between layers of equal width, two k-means
+    iterations, g_img2ltnt -- against the oracle generator (image + attention maps); and the carry really changes the result."""
+    kw = dict(kmeans=True, iterative=True, kmeans_iters=2, g_img2ltnt=True)
+    G = _small_generator(gf, cuda_dev, exact, **kw)
+    z = torch.randn(3, 9, 32, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        img, atts = G(z.to(cuda_dev), return_att=True)
+        img_fused = G(z.to(cuda_dev))
+    ref, ratts = og.generator_forward(G.state_dict(), z, resolution=64, components_num=8, latent_dim=32, duplex=True, mapping_layers=4,
+                                      return_att=True, kmeans_iters=2, img2ltnt=True, iterative=True)
+    # The k-means loop feeds its centroids back into the next iteration's (and, carried, the next layer's) queries, and those queries
+    # go through a softmax over all n grid cells: errors are amplified by every iteration.  fp32 mode: 3x the e2e bound (measured
+    # 2.0e-5 peak-relative); TF32 mode (pass-A logits in TF32 inside the loop; the centroid -> query products are kept in fp32):
+    # 6x (measured max-abs 5.2e-3 of the peak, rel-RMS 2.6e-3, 67.6 dB against 4.7e-4 / 78 dB for the plain duplex generator).
+    sc = 3.0 if exact else 6.0
+    check_image(img, ref, "fp32" if exact else "tf32", "duplex-ext/image", scale=sc)
+    check_image(img_fused, ref, "fp32" if exact else "tf32", "duplex-ext/image-fused", scale=sc)
+    e2e = TOLERANCES["e2e"]["simt_fp32" if exact else "tcgen05_tf32"]
+    for a, r in zip(atts, ratts):
+        assert (a.double().cpu() - r).abs().max() <= sc * e2e["att_abs"]
+    ref_nocarry = og.generator_forward(G.state_dict(), z, resolution=64, components_num=8, latent_dim=32, duplex=True, mapping_layers=4,
+                                       kmeans_iters=2, img2ltnt=True, iterative=False)
+    assert (ref - ref_nocarry).abs().max() > 1e-3 * ref.abs().max()

@@ -86,15 +86,21 @@ def test_generator_plumbing_matches_oracle_without_attention(gf):
     assert (img - ref).abs().max() < 1e-9 * max(1.0, ref.abs().max().item())
 
 
-@pytest.mark.parametrize("duplex", [False, True])
+@pytest.mark.parametrize("duplex", [False, True, "extensions"])
 def test_generator_plumbing_matches_oracle_with_patched_attention(gf, monkeypatch, duplex):
-    """Host plumbing (layout, layer order, skip connections) checked on CPU by swapping the CUDA op for the oracle."""
-    G = _small_generator(gf, kmeans=duplex, integration="both")
+    """Host plumbing (layout, layer order, skip connections, the `iterative` centroid carry) checked on CPU by swapping the CUDA
+    op for the oracle.  "extensions" = duplex with iterative carry, two k-means iterations and g_img2ltnt."""
+    ext = duplex == "extensions"
+    duplex = bool(duplex)
+    G = _small_generator(gf, kmeans=duplex, integration="both", **(dict(iterative=True, kmeans_iters=2, g_img2ltnt=True) if ext else {}))
+    carried = []
 
-    def fake_forward(self, x, y, centroids=None, return_att=False, out=None):
+    def fake_forward(self, x, y, centroids=None, return_att=False, out=None, centroids_init=None):
         w = {n: p.detach() for n, p in self.named_parameters(recurse=False)}
+        carried.append(centroids_init is not None)
         o, att, cen = ob.transformer_layer(x.permute(0, 3, 1, 2), y, w, integration=self.integration, norm=self.norm,
-                                           duplex=self.duplex, use_pos=self.use_pos, return_att=return_att)
+                                           duplex=self.duplex, use_pos=self.use_pos, return_att=return_att,
+                                           kmeans_iters=self.kmeans_iters, img2ltnt=self.img2ltnt, centroids_init=centroids_init)
         return o.permute(0, 2, 3, 1).contiguous(), att, cen
 
     monkeypatch.setattr(gf.BipartiteAttention, "forward", fake_forward)
@@ -102,8 +108,10 @@ def test_generator_plumbing_matches_oracle_with_patched_attention(gf, monkeypatc
     with torch.no_grad():
         img, atts = G(z, return_att=True)
     ref, ratts = og.generator_forward(G.state_dict(), z, resolution=32, components_num=4, latent_dim=16, integration="both",
-                                      duplex=duplex, mapping_layers=2, return_att=True)
+                                      duplex=duplex, mapping_layers=2, return_att=True,
+                                      **(dict(iterative=True, kmeans_iters=2, img2ltnt=True) if ext else {}))
     assert len(atts) == len(ratts) == G.synthesis.num_attention_layers == 6
+    assert any(carried) == ext                         # widths: 64 (res 8), 64 (res 16), 32 (res 32): carries inside and across blocks
     assert (img - ref).abs().max() < 1e-9 * max(1.0, ref.abs().max().item())
     for a, r in zip(atts, ratts):
         assert (a - r).abs().max() < 1e-10
@@ -410,5 +418,7 @@ def test_weight_caches_follow_the_weights_epoch(gf):
     e0 = state.weights_epoch()
     G2.load_state_dict(G.state_dict())
     assert state.weights_epoch() == e0 + 1
-    with pytest.raises(NotImplementedError, match="iterative"):
-        gf.Generator(resolution=16, components_num=2, latent_dim=8, fmap_base=64, fmap_max=16, kmeans=True, iterative=True)
+    Gi = gf.Generator(resolution=16, components_num=2, latent_dim=8, fmap_base=64, fmap_max=16, kmeans=True, iterative=True, kmeans_iters=2,
+                      g_img2ltnt=True)
+    a = Gi.synthesis.layers[1].attention
+    assert Gi.synthesis.iterative and a.iterative and a.kmeans_iters == 2 and a.img2ltnt and {"wcq", "wi2l", "bi2l"} <= set(a.param_dict())
