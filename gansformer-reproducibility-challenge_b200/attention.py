@@ -65,6 +65,30 @@ class StageTimer:
 STAGE_TIMER: Optional[StageTimer] = None
 
 
+# ---- attention dropout (att_dp): one device-resident {seed, step} pair per device; the kernels read it when they run, so a
+#      replayed CUDA graph draws fresh masks once `advance_dropout` has bumped the step on the device ------------------------------
+_DP_STATE: Dict[str, torch.Tensor] = {}
+_DP_SALT = [0]
+
+
+def dropout_state(device) -> torch.Tensor:
+    """int64 [2] = {seed, step} on `device` (created with seed 0x5eed1234 on first use; see set_dropout_seed)."""
+    key = str(device)
+    t = _DP_STATE.get(key)
+    if t is None:
+        t = _DP_STATE[key] = torch.tensor([0x5EED1234, 0], dtype=torch.int64, device=device)
+    return t
+
+
+def set_dropout_seed(seed: int, device, step: int = 0) -> None:
+    dropout_state(device).copy_(torch.tensor([int(seed), int(step)], dtype=torch.int64))
+
+
+def advance_dropout(device) -> None:
+    """step += 1 on the device (stream-ordered, capturable): call between training steps / between the D and G phases."""
+    dropout_state(device)[1:].add_(1)
+
+
 FORCE_REFOLD = False      # set by training.Trainer while it captures a CUDA graph (see networks.CACHE_BYPASS)
 
 
@@ -134,6 +158,12 @@ def _make_postop(postop: Optional[dict], B: int, H: int, W: int, C: int, dev):
             keep.append(t)
         pst.rgb_w, pst.rgb_out = rw.data_ptr(), ro.data_ptr()
         pst.rgb_bias = rb.detach().data_ptr() if rb is not None else None
+    if postop.get("att_dp", 0.0):                 # attention dropout (training): state = int64 [2] {seed, step} on the device
+        st = postop["dp_state"]
+        if st.dtype != torch.int64 or st.numel() != 2 or st.device != dev:
+            raise ValueError("postop.dp_state must be an int64 [2] tensor on the activation's device")
+        keep.append(st)
+        pst.att_dp, pst.dp_salt, pst.dp_state = float(postop["att_dp"]), int(postop.get("dp_salt", 0)) & 0xFFFFFFFF, st.data_ptr()
     return pst, keep
 
 
@@ -344,13 +374,16 @@ class BipartiteAttention(nn.Module):
             raise ValueError("kmeans_iters must be in 1..16")
         if (kmeans_iters != 1 or img2ltnt) and not kmeans:
             raise ValueError("kmeans_iters > 1 / img2ltnt need kmeans=True (duplex attention)")
-        if att_dp != 0.0:
-            raise NotImplementedError("attention dropout is not implemented in the fused kernel (inference path: 0)")
+        if not 0.0 <= att_dp < 1.0:
+            raise ValueError("att_dp must be in [0, 1)")
         self.dim, self.latent_dim, self.components_num = dim, latent_dim, components_num
         self.pos_dim = latent_dim if pos_dim is None else pos_dim
         self.num_heads, self.integration, self.norm = num_heads, integration, norm
         self.duplex, self.use_pos, self.exact_fp32 = bool(kmeans), use_pos, exact_fp32
         self.kmeans_iters, self.img2ltnt, self.iterative = int(kmeans_iters), bool(img2ltnt), bool(iterative and kmeans)
+        self.att_dp = float(att_dp)                       # attention dropout, active in training mode only (reference: p ~ 0.12)
+        _DP_SALT[0] += 1
+        self.dp_salt = _DP_SALT[0] * 0x9E3779B1 & 0xFFFFFFFF   # distinct masks per layer
         for name, shape in param_shapes(dim, latent_dim, components_num, self.pos_dim, integration, self.duplex, self.kmeans_iters, self.img2ltnt,
                                         self.iterative).items():
             init = torch.zeros(shape) if name.startswith("b") else torch.randn(shape)
@@ -360,6 +393,12 @@ class BipartiteAttention(nn.Module):
     def param_dict(self) -> Dict[str, torch.Tensor]:
         return {n: p for n, p in self.named_parameters(recurse=False)}
 
+    def dropout_postop(self, device) -> dict:
+        """Post-op members that switch attention dropout on for this call ({} in eval mode / att_dp = 0)."""
+        if not (self.training and self.att_dp > 0.0):
+            return {}
+        return dict(att_dp=self.att_dp, dp_salt=self.dp_salt, dp_state=dropout_state(device))
+
     def forward(self, x: torch.Tensor, y: torch.Tensor, centroids: Optional[torch.Tensor] = None,
                 return_att: bool = False, out: Optional[torch.Tensor] = None, postop: Optional[dict] = None,
                 stage: str = "all", need_centroids: bool = True, centroids_init: Optional[torch.Tensor] = None):
@@ -368,10 +407,17 @@ class BipartiteAttention(nn.Module):
         if torch.is_grad_enabled() and (x.requires_grad or y.requires_grad or any(p.requires_grad for p in self.parameters())):
             if postop is not None:
                 raise RuntimeError("the fused post-op is inference-only; apply noise/bias/activation outside when training")
+            if self.att_dp > 0.0 and self.training and (self.duplex or self.num_heads != 1):
+                raise NotImplementedError("attention dropout is implemented for single-head simplex layers")
             if centroids_init is not None:
                 raise RuntimeError("iterative centroid carry (centroids_init) is an inference feature in this build")
             from .autograd import bipartite_attention_autograd
             return bipartite_attention_autograd(self, x, y, centroids, return_att)
+        dp = self.dropout_postop(x.device)
+        if dp:
+            if self.duplex or self.num_heads != 1:
+                raise NotImplementedError("attention dropout is implemented for single-head simplex layers")
+            postop = {**(postop or {"act": "linear", "gain": 1.0}), **dp}
         return bipartite_attention_forward(x, y, self.param_dict(), self._plan, integration=self.integration,
                                            norm=self.norm, duplex=self.kmeans_iters if self.duplex else 0, num_heads=self.num_heads,
                                            use_pos=self.use_pos, return_att=return_att, centroids=centroids,
@@ -402,8 +448,6 @@ def transformer_layer(dim: int, pos_dim: int, from_tensor: torch.Tensor, to_tens
     from_tensor [B, from_len, dim] (grid tokens, row-major over grid_shape=(H, W)); to_tensor [B, to_len, D].
     Returns (from_tensor' [B, from_len, dim], att_probs [B, from_len, to_len], att_vars).
     """
-    if att_dp != 0.0:
-        raise NotImplementedError("att_dp != 0 is not implemented")
     H, W = grid_shape
     B = from_tensor.shape[0]
     if from_len != H * W or from_tensor.shape[1] != from_len or from_tensor.shape[2] != dim or to_tensor.shape[1] != to_len:
@@ -414,10 +458,13 @@ def transformer_layer(dim: int, pos_dim: int, from_tensor: torch.Tensor, to_tens
     att_vars = dict(att_vars or {})
     cen_in = att_vars.get("centroids") if (kmeans and iterative) else None
     x = from_tensor.reshape(B, H, W, dim)
+    post = None
+    if att_dp:          # training-time dropout of the probabilities: att_vars may carry "dp_salt"; the {seed, step} state is the device's
+        post = dict(act="linear", gain=1.0, att_dp=float(att_dp), dp_salt=int(att_vars.get("dp_salt", 0)), dp_state=dropout_state(x.device))
     out, att, cen = bipartite_attention_forward(x, to_tensor, params, plan, integration=integration, norm=norm,
                                                 duplex=(kmeans_iters if kmeans else 0), num_heads=num_heads, use_pos=use_pos,
                                                 return_att=True, centroids=cen_in, exact_fp32=exact_fp32,
-                                                img2ltnt=bool(kmeans and "wi2l" in params))
+                                                img2ltnt=bool(kmeans and "wi2l" in params), postop=post)
     if cen is not None:
         att_vars["centroids"] = cen
     att_probs = att.permute(0, 2, 3, 1).reshape(B, from_len, to_len)

@@ -127,7 +127,8 @@ def folded_tables(y, p, *, H, W, C, integration, use_pos):
         cv = cv + torch.cat([torch.ones(C, device=y.device, dtype=y.dtype), torch.zeros(cv.numel() - C, device=y.device, dtype=y.dtype)])
     v = y @ (_e(p["wv"]) @ wo) + cv                                      # [B, k, Cout]
     Vt = torch.nn.functional.pad(v.transpose(1, 2), (0, KP - k))
-    return Kp.contiguous(), Vt.contiguous(), Rt.contiguous(), Ct.contiguous()
+    cb = cv - p["bv"] @ wo                       # bo (+1 on the gain half): the constants attention dropout leaves unscaled
+    return Kp.contiguous(), Vt.contiguous(), Rt.contiguous(), Ct.contiguous(), cb.contiguous()
 
 
 def _kernel_backward_ok(m, x) -> bool:
@@ -143,8 +144,10 @@ class _FusedAttention(torch.autograd.Function):
             x.detach(), y.detach(), {k: v.detach() for k, v in pd.items()}, module._plan,
             integration=module.integration, norm=module.norm, duplex=module.kmeans_iters if module.duplex else 0, num_heads=module.num_heads,
             use_pos=module.use_pos, return_att=return_att, centroids=centroids, exact_fp32=module.exact_fp32,
-            weights_version=tuple((v.data_ptr(), v._version) for v in params), img2ltnt=module.img2ltnt)
+            weights_version=tuple((v.data_ptr(), v._version) for v in params), img2ltnt=module.img2ltnt,
+            postop=({"act": "linear", "gain": 1.0, **module.dropout_postop(x.device)} if module.dropout_postop(x.device) else None))
         ctx.module, ctx.names, ctx.centroids = module, names, centroids
+        ctx.dropout = module.dropout_postop(x.device)                  # the backward regenerates the same mask (same device state)
         ctx.save_for_backward(x, y, *params)
         ctx.mark_non_differentiable(*[t for t in (att, cen) if t is not None])
         return out, att, cen
@@ -154,7 +157,9 @@ class _FusedAttention(torch.autograd.Function):
         m = ctx.module
         x, y, *params = ctx.saved_tensors
         if _kernel_backward_ok(m, x):
-            return (None, None, None, None, *_kernel_backward(m, ctx.names, x, y, params, g_out))
+            return (None, None, None, None, *_kernel_backward(m, ctx.names, x, y, params, g_out, ctx.dropout))
+        if ctx.dropout:
+            raise NotImplementedError("attention dropout needs the stage-T backward kernel (single-head simplex, layer norm / none)")
         with torch.enable_grad():
             xs = x.detach().requires_grad_(True)
             ys = y.detach().requires_grad_(True)
@@ -166,7 +171,7 @@ class _FusedAttention(torch.autograd.Function):
         return (None, None, None, None, *grads)
 
 
-def _kernel_backward(m, names, x, y, params, g_out):
+def _kernel_backward(m, names, x, y, params, g_out, dropout=None):
     """d(loss)/d(x, y, params) of a simplex layer through gf_attn_simplex_bwd (see the module docstring)."""
     import ctypes
     from . import _lib
@@ -175,7 +180,7 @@ def _kernel_backward(m, names, x, y, params, g_out):
     with torch.enable_grad():
         ys = y.detach().requires_grad_(True)
         ps = [p.detach().requires_grad_(True) for p in params]
-        Kp, Vt, Rt, Ct = folded_tables(ys, dict(zip(names, ps)), H=H, W=W, C=C, integration=m.integration, use_pos=m.use_pos)
+        Kp, Vt, Rt, Ct, cb = folded_tables(ys, dict(zip(names, ps)), H=H, W=W, C=C, integration=m.integration, use_pos=m.use_pos)
     KP, Cout = Kp.shape[1], Vt.shape[1]
     xc, gc = x.detach().contiguous(), g_out.detach().contiguous()
     dX = torch.empty_like(xc)
@@ -185,16 +190,23 @@ def _kernel_backward(m, names, x, y, params, g_out):
     desc = _lib.make_desc(B, H, W, C, k, y.shape[2], heads=1, norm=m.norm, integration=m.integration,
                           pos_dim=m.pos_dim if m.use_pos else 0, duplex=False, flags=0)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.load().gf_attn_simplex_bwd(ctypes.byref(desc), xc.data_ptr(), gc.data_ptr(), Kp.data_ptr(), Vt.data_ptr(),
-                                                   Rt.data_ptr(), Ct.data_ptr(), dX.data_ptr(), dS.data_ptr(), P.data_ptr(),
-                                                   dCtl.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)),
-                   "gf_attn_simplex_bwd")
+        dpo = dropout or {}
+        _lib.check(_lib.load().gf_attn_simplex_bwd_ex(ctypes.byref(desc), xc.data_ptr(), gc.data_ptr(), Kp.data_ptr(), Vt.data_ptr(),
+                                                      Rt.data_ptr(), Ct.data_ptr(), dX.data_ptr(), dS.data_ptr(), P.data_ptr(),
+                                                      dCtl.data_ptr(), ctypes.c_float(dpo.get("att_dp", 0.0)), int(dpo.get("dp_salt", 0)),
+                                                      dpo["dp_state"].data_ptr() if dpo else None, cb.detach().data_ptr() if dpo else None,
+                                                      ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)),
+                   "gf_attn_simplex_bwd_ex")
     # reductions over the tokens: plain batched GEMMs / sums
     dKp = torch.bmm(dS.transpose(1, 2), xc.reshape(B, n, C))             # [B, KP, C]
     dVt = torch.bmm(dCtl.transpose(1, 2), P)                             # [B, Cout, KP]
     dS4 = dS.reshape(B, H, W, KP)
     dRt, dCt = dS4.sum(dim=2), dS4.sum(dim=1)
-    gy, *gp = torch.autograd.grad([Kp, Vt, Rt, Ct], [ys, *ps], [dKp, dVt, dRt, dCt], allow_unused=True)
+    outs, grads = [Kp, Vt, Rt, Ct], [dKp, dVt, dRt, dCt]
+    if dpo:                                      # ctl = sum_j q_j (Vt_j - cb) + cb: the constants' own gradient
+        outs.append(cb)
+        grads.append((dCtl * (1.0 - P.sum(dim=2, keepdim=True))).sum(dim=(0, 1)))
+    gy, *gp = torch.autograd.grad(outs, [ys, *ps], grads, allow_unused=True)
     return (dX, gy, *gp)
 
 

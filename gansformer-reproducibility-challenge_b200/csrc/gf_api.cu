@@ -38,6 +38,29 @@ int check_device() {
   return GF_OK;
 }
 
+int dropout_args(const gf_attn_postop* post, DropoutArgs* out) {
+  out->state = nullptr; out->thr = 0; out->salt = 0; out->scale = 1.f;
+  if (!post || post->att_dp == 0.f || !post->dp_state) return GF_OK;
+  if (!(post->att_dp > 0.f && post->att_dp < 1.f)) { set_error("postop: att_dp = %g must be in [0, 1)", (double)post->att_dp); return GF_ERR_INVALID; }
+  double t = (double)post->att_dp * 4294967296.0 + 0.5;
+  out->thr = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+  if (out->thr == 0) out->thr = 1;
+  out->salt = post->dp_salt; out->state = post->dp_state; out->scale = 1.f / (1.f - post->att_dp);
+  return GF_OK;
+}
+
+__global__ void dropout_mask_kernel(float* __restrict__ mask, DropoutArgs D, long long tokens, int KP) {
+  const unsigned long long seed = D.state[0], step = D.state[1];
+  const long long total = tokens * (KP / 4);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long tok = i / (KP / 4);
+    const int q = (int)(i % (KP / 4));
+    float mk[4];
+    dropout_mult4(D, seed, step, (uint32_t)tok, q, mk);
+    reinterpret_cast<float4*>(mask)[i] = make_float4(mk[0], mk[1], mk[2], mk[3]);
+  }
+}
+
 static int token_pass(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws,
                       const gf_attn_postop* post, cudaStream_t st) {
   int rc;
@@ -51,7 +74,8 @@ static int token_pass(const Layout& L, const gf_attn_desc* d, const float* X, fl
     }
   }
   if ((rc = norm_stats(L, d, X, ws, st))) return rc;
-  const bool tc = !(d->flags & GF_FLAG_FP32_EXACT) && tc_supported(L, d);
+  const bool dropout = post && post->att_dp != 0.f && post->dp_state;
+  const bool tc = !(d->flags & GF_FLAG_FP32_EXACT) && tc_supported(L, d) && !dropout;     // attention dropout: CUDA-core kernels
   if (post && (post->rgb_out || post->rgb_w)) {
     if (!post->rgb_out || !post->rgb_w || ((uintptr_t)post->rgb_w & 15)) { set_error("postop: fused tRGB needs rgb_w (16-byte aligned) and rgb_out"); return GF_ERR_INVALID; }
     if (!tc || L.C > 256) { set_error("postop: the fused tRGB is served by the tcgen05 path with C <= 256 only (see gf_attn_tc_eligible)"); return GF_ERR_UNSUPPORTED; }
@@ -145,6 +169,26 @@ int gf_attn_prologue_batch(int n, const gf_attn_desc* const* descs, const float*
   }
   if ((rc = check_device())) return rc;
   return prologue_batch(n, Ls, descs, Y, folded, wsf, posts, (cudaStream_t)stream);
+}
+
+int gf_attn_dropout_mask(const gf_attn_desc* desc, float att_dp, uint32_t dp_salt, const unsigned long long* dp_state, float* mask, void* stream) {
+  Layout L;
+  int rc = make_layout(desc, &L);
+  if (rc) return rc;
+  if (!mask || !dp_state) { set_error("gf_attn_dropout_mask: null pointer"); return GF_ERR_INVALID; }
+  gf_attn_postop post;
+  memset(&post, 0, sizeof(post));
+  post.att_dp = att_dp; post.dp_salt = dp_salt; post.dp_state = dp_state;
+  DropoutArgs D;
+  if ((rc = dropout_args(&post, &D))) return rc;
+  if (!D.thr) { set_error("gf_attn_dropout_mask: att_dp must be > 0"); return GF_ERR_INVALID; }
+  if ((rc = check_device())) return rc;
+  const long long tokens = (long long)L.B * L.n;
+  long long blocks = (tokens * (L.KP / 4) + 255) / 256;
+  if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+  dropout_mask_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mask, D, tokens, L.KP);
+  GF_LAUNCH_OK();
+  return GF_OK;
 }
 
 int gf_attn_norm_stats(const gf_attn_desc* desc, const float* X, void* ws, void* stream) {

@@ -12,6 +12,7 @@
 //     dK'[b] = dS[b]^T X[b],   dV^T[b] = dCtl[b]^T P[b],   dRt = sum_w dS,   dCt = sum_h dS,
 // and the chain rule through stages I and W is torch autograd over tiny [B,k,*] tensors.
 // Replaces ~45 full passes over [B,n,C]-sized tensors of the direct-form autograd composite by 8.
+#include <string.h>
 #include "gf_common.cuh"
 
 namespace gf {
@@ -24,6 +25,8 @@ struct BwdParams {
   const float* X; const float* dOut; const float* Kp; const float* Vt; const float* Rt; const float* Ct;
   float* dX; float* dS; float* P; float* dCtl;
   int n, H, W, C, k, Cout, norm, integration;
+  DropoutArgs dp;            // attention dropout of the forward call (thr = 0: off)
+  const float* cb;           // [Cout] bo (+1): ctl = sum_j q_j (Vt_j - cb) + cb when dropout is on
 };
 
 __device__ __forceinline__ void bwd_load_chunk(float (*dst)[BXS], const float* __restrict__ src, int t0, int n, int ld, int c0) {
@@ -103,6 +106,27 @@ __global__ void __launch_bounds__(BTM) token_bwd_kernel(const BwdParams P) {
   const float inv = 1.f / den;
 #pragma unroll
   for (int j = 0; j < KP; ++j) s[j] *= inv;                       // s = p from here on
+  // attention dropout: q = p * mk feeds the control signal (and the dV^T reduction); the softmax backward uses p itself
+  float pk[KP];                                                  // p before dropout (only read when dropout is on)
+  float mk[KP];
+#pragma unroll
+  for (int j = 0; j < KP; ++j) { pk[j] = s[j]; mk[j] = 1.f; }
+  if (P.dp.thr) {
+    const unsigned long long seed = P.dp.state[0], step = P.dp.state[1];
+#pragma unroll
+    for (int q = 0; q < KP / 4; ++q) {
+      dropout_mult4(P.dp, seed, step, (uint32_t)((size_t)b * n + (valid ? t : 0)), q, mk + q * 4);
+      s[q * 4] *= mk[q * 4]; s[q * 4 + 1] *= mk[q * 4 + 1]; s[q * 4 + 2] *= mk[q * 4 + 2]; s[q * 4 + 3] *= mk[q * 4 + 3];
+    }
+  }                                                              // s = q (= p without dropout) from here on
+  float qdef = 0.f;                                              // 1 - sum q (0 without dropout)
+  if (P.dp.thr) {
+    float qs = 0.f;
+#pragma unroll
+    for (int j = 0; j < KP; ++j) qs += s[j];
+    qdef = 1.f - qs;
+  }
+  float dcb = 0.f;                                               // sum_c dctl[c] * cb[c]: d/dq_j of the (1 - sum q) cb term is -cb
   float mean = 0.f, rstd = 1.f;
   const bool ln = P.norm == GF_NORM_LAYER;
   if (ln) {
@@ -143,7 +167,12 @@ __global__ void __launch_bounds__(BTM) token_bwd_kernel(const BwdParams P) {
           const float4 v = *reinterpret_cast<const float4*>(&vs[cc][j4]);
           g = fmaf(s[j4], v.x, fmaf(s[j4 + 1], v.y, fmaf(s[j4 + 2], v.z, fmaf(s[j4 + 3], v.w, g))));
         }
+        if (P.dp.thr) g = fmaf(qdef, __ldg(P.cb + c0 + cc), g);
         dxn = go * g; dc = go * xn;
+      }
+      if (P.dp.thr) {
+        dcb = fmaf(dc, __ldg(P.cb + c0 + cc), dcb);
+        if (integ == GF_INT_BOTH) dcb = fmaf(go, __ldg(P.cb + C + c0 + cc), dcb);
       }
       a1 += dxn; a2 = fmaf(dxn, xn, a2);
 #pragma unroll
@@ -168,9 +197,9 @@ __global__ void __launch_bounds__(BTM) token_bwd_kernel(const BwdParams P) {
   // ---- softmax backward; dS and P rows
   float pd = 0.f;
 #pragma unroll
-  for (int j = 0; j < KP; ++j) pd = fmaf(s[j], dp[j], pd);
+  for (int j = 0; j < KP; ++j) { dp[j] = (dp[j] - dcb) * mk[j]; pd = fmaf(pk[j], dp[j], pd); }   // d/dq (minus the cb term) -> d/dp through the mask
 #pragma unroll
-  for (int j = 0; j < KP; ++j) dp[j] = s[j] * (dp[j] - pd);      // dp = ds from here on
+  for (int j = 0; j < KP; ++j) dp[j] = pk[j] * (dp[j] - pd);     // dp = ds from here on
   if (valid) {
     float4* ds4 = reinterpret_cast<float4*>(P.dS + ((size_t)b * n + t) * KP);
     float4* p4 = reinterpret_cast<float4*>(P.P + ((size_t)b * n + t) * KP);
@@ -206,6 +235,7 @@ __global__ void __launch_bounds__(BTM) token_bwd_kernel(const BwdParams P) {
           const float4 v = *reinterpret_cast<const float4*>(&vs[cc][j4]);
           g = fmaf(s[j4], v.x, fmaf(s[j4 + 1], v.y, fmaf(s[j4 + 2], v.z, fmaf(s[j4 + 3], v.w, g))));
         }
+        if (P.dp.thr) g = fmaf(qdef, __ldg(P.cb + c0 + cc), g);
         dxn = go * g;
       }
       float dx = dxn;
@@ -228,6 +258,12 @@ using namespace gf;
 
 extern "C" int gf_attn_simplex_bwd(const gf_attn_desc* desc, const float* X, const float* dOut, const float* Kp, const float* Vt,
                                    const float* Rt, const float* Ct, float* dX, float* dS, float* Pout, float* dCtl, void* stream) {
+  return gf_attn_simplex_bwd_ex(desc, X, dOut, Kp, Vt, Rt, Ct, dX, dS, Pout, dCtl, 0.f, 0, nullptr, nullptr, stream);
+}
+
+extern "C" int gf_attn_simplex_bwd_ex(const gf_attn_desc* desc, const float* X, const float* dOut, const float* Kp, const float* Vt,
+                                      const float* Rt, const float* Ct, float* dX, float* dS, float* Pout, float* dCtl,
+                                      float att_dp, uint32_t dp_salt, const unsigned long long* dp_state, const float* cb, void* stream) {
   Layout L;
   int rc = make_layout(desc, &L);
   if (rc) return rc;
@@ -239,6 +275,15 @@ extern "C" int gf_attn_simplex_bwd(const gf_attn_desc* desc, const float* X, con
   BwdParams P;
   P.X = X; P.dOut = dOut; P.Kp = Kp; P.Vt = Vt; P.Rt = Rt; P.Ct = Ct; P.dX = dX; P.dS = dS; P.P = Pout; P.dCtl = dCtl;
   P.n = L.n; P.H = L.H; P.W = L.W; P.C = L.C; P.k = L.k; P.Cout = L.Cout; P.norm = desc->norm; P.integration = desc->integration;
+  {
+    gf_attn_postop post;
+    memset(&post, 0, sizeof(post));
+    post.att_dp = att_dp; post.dp_salt = dp_salt; post.dp_state = dp_state;
+    if ((rc = dropout_args(&post, &P.dp))) return rc;
+    if (P.dp.thr && !cb) { set_error("gf_attn_simplex_bwd_ex: attention dropout needs cb (bo, +1 on the gain half)"); return GF_ERR_INVALID; }
+    P.cb = cb;
+  }
+  if (L.heads != 1) { set_error("gf_attn_simplex_bwd: one head (multi-head layers use the composite backward)"); return GF_ERR_UNSUPPORTED; }
   dim3 grid((L.n + BTM - 1) / BTM, L.B);
   const int smem = (int)(2 * sizeof(float) * BTM * BXS + 3 * sizeof(float) * L.KP * BCH);
   cudaStream_t st = (cudaStream_t)stream;

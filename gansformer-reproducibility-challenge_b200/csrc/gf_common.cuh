@@ -49,6 +49,7 @@ struct Layout {
   size_t w_NSCALE, w_NSHIFT, w_NPART;                 // instance/batch norm statistics
   size_t w_MALL, w_M, w_Rt2, w_Ct2, w_PART, w_XBAR;   // duplex pass A
   size_t f_AK2, f_CK2;                                // duplex: keys straight from Xbar (Wv2 and bv2 folded into AK / CK)
+  size_t f_CB, w_CB;                                  // bo (+1 on the gain half): the part of the control signal attention dropout must NOT scale
   size_t f_ACQ, f_WI2L, f_BI2L;                       // kmeans_iters > 1: centroid -> pass-A query table; g_img2ltnt: centroid -> latent gain
   size_t w_CEN, w_Y2;                                 // scratch centroids [B,k,C] (caller passed none), modulated latents [B,k,D]
   int iters, img2ltnt;
@@ -67,6 +68,36 @@ inline int num_sms() {
   }
   return v;
 }
+
+// ---- attention dropout (att_dp, training): counter-based Philox4x32-10, reproducible on the CPU (oracle/philox.py) ----------
+// One call yields the keep decisions of 4 consecutive table columns of one token:
+//   counter = (global token index b * n + t, column block j / 4, salt (per layer), 0x5eed),  key = seed (lo, hi)
+//   keep_j  = word_j >= thr,  thr = round(p * 2^32);  kept probabilities are scaled by 1 / (1 - p).
+struct DropoutArgs {
+  const unsigned long long* state;   // device: {seed, step counter} -- read at run time, so a replayed CUDA graph draws fresh masks
+  uint32_t thr;                      // 0 = dropout off
+  uint32_t salt;                     // distinguishes the layers of a network
+  float scale;                       // 1 / (1 - p)
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// multipliers (0 or 1/(1-p)) of columns 4q .. 4q+3 of global token `tok`
+__device__ __forceinline__ void dropout_mult4(const DropoutArgs& D, unsigned long long seed, unsigned long long step, uint32_t tok, int q, float mk[4]) {
+  uint32_t w[4];
+  philox4x32_10(tok, (uint32_t)q | ((uint32_t)step << 8), D.salt ^ (uint32_t)(step >> 24), 0x5eedu, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) mk[i] = w[i] >= D.thr ? D.scale : 0.f;
+}
+#endif
 
 inline size_t align64(size_t x) { return (x + 63) & ~size_t(63); }
 inline int pad_k(int k) { return k <= 16 ? 16 : 32; }
@@ -99,6 +130,8 @@ int gemm_tc(cudaStream_t st, int M, int N, int K, const float* A, const float* B
 
 // ---- stage T kernels ----------------------------------------------------------------------------------
 int token_pass_simt(const Layout& L, const gf_attn_desc* d, const float* X, float* Xout, float* att, float* ws, const gf_attn_postop* post, cudaStream_t st);
+// postop -> DropoutArgs (thr = 0 when off); GF_ERR_INVALID on a bad probability / missing state
+int dropout_args(const gf_attn_postop* post, DropoutArgs* out);
 int norm_stats(const Layout& L, const gf_attn_desc* d, const float* X, float* ws, cudaStream_t st);
 int centroid_pass_simt(const Layout& L, const gf_attn_desc* d, const float* X, float* ws, cudaStream_t st,
                        const float* in_scale = nullptr, int in_scale_ld = 0);

@@ -56,6 +56,7 @@ int make_layout(const gf_attn_desc* d, Layout* L) {
   l.f_CK = take(nh * k * LDK);
   l.f_AV = take(nh * D * l.Cout);
   l.f_CV = take(nh * l.Cout);
+  l.f_CB = take(l.Cout);
   l.f_ROW = take((size_t)l.H * (p / 2) + 1);
   l.f_COL = take((size_t)l.W * (p / 2) + 1);
   l.f_QFOLD = take(C * LDK);
@@ -109,6 +110,7 @@ int make_layout(const gf_attn_desc* d, Layout* L) {
   l.w_Vt = take(B * l.Cout * KP);
   l.w_Rt = take(B * l.H * KP);
   l.w_Ct = take(B * l.W * KP);
+  l.w_CB = take(l.Cout);
   if (d->norm == GF_NORM_INSTANCE || d->norm == GF_NORM_BATCH) {
     l.w_NSCALE = take(B * C);
     l.w_NSHIFT = take(B * C);
@@ -381,6 +383,10 @@ int fold_weights(const Layout& L, const gf_attn_desc* d, const gf_attn_weights* 
     scale_copy_kernel<<<blocks_for(Cout), 256, 0, st>>>(f + L.f_CV, f + L.f_CV, Cout, 1.f, 1.f, (size_t)C);
     GF_LAUNCH_OK();
   }
+  // CB = bo (+1 on the gain half): with attention dropout the probabilities no longer sum to one, so the constants folded into V^T
+  // are re-added as (1 - sum q) * CB by the kernels that apply the mask
+  scale_copy_kernel<<<blocks_for(Cout), 256, 0, st>>>(f + L.f_CB, w->bo, Cout, 1.f, d->integration != GF_INT_ADD ? 1.f : 0.f, (size_t)C);
+  GF_LAUNCH_OK();
   if (pos) {
     pos_axis_kernel<<<blocks_for((size_t)L.H * (p / 2)), 256, 0, st>>>(f + L.f_ROW, L.H, p / 2);
     GF_LAUNCH_OK();
@@ -526,8 +532,8 @@ __global__ void __launch_bounds__(256, 4) finalize_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------------------
 constexpr int STAGE_I_MAX_JOBS = 16;
 struct StageIJob {
-  const float *Y, *A, *Cst, *AV, *CV, *ROW, *COL, *in_scale;
-  float *Kp, *Vt, *Rt, *Ct;
+  const float *Y, *A, *Cst, *AV, *CV, *ROW, *COL, *in_scale, *CB;
+  float *Kp, *Vt, *Rt, *Ct, *CBout;
   int H, W, C, k, D, p, KP, Cout, LDK, in_ld;
   int heads, seg;                // multi-head: table column J = head * seg + j; A / Cst / AV / CV hold one copy per head
   int tf32_k, tf32_v;            // round K' (and take the logits in log2 units) / round V^T for the tcgen05 kernels
@@ -551,6 +557,7 @@ __global__ void __launch_bounds__(256, 4) stage_i_kernel(const __grid_constant__
     const int Cout = J.Cout;
     const int c = blk * 256 + threadIdx.x;
     if (c >= Cout) return;
+    if (b == 0 && J.CBout) J.CBout[c] = J.CB[c];                     // batch-independent constant of the control signal (dropout path)
     float* out = J.Vt + ((size_t)b * Cout + c) * KP;
     for (int j0 = 0; j0 < KP; j0 += 8) {                          // 8 table columns at a time: one head (seg >= 8)
       const int head = j0 / J.seg, jb = j0 - head * J.seg;        // latent index of column j0 inside its head
@@ -680,6 +687,7 @@ static void stage_i_fill(StageIJob& J, const Layout& L, const float* Y, const fl
                          const float* f, float* Kp, float* Vt, float* Rt, float* Ct, const float* in_scale, int in_ld, int tf32_k, int tf32_v) {
   J.Y = Y; J.A = A; J.Cst = Cst; J.AV = AV; J.CV = CV; J.ROW = f + L.f_ROW; J.COL = f + L.f_COL; J.in_scale = in_scale;
   J.Kp = Kp; J.Vt = Vt; J.Rt = Rt; J.Ct = Ct;
+  J.CB = f + L.f_CB; J.CBout = nullptr;
   J.H = L.H; J.W = L.W; J.C = L.C; J.k = L.k; J.D = L.D; J.p = L.p; J.KP = L.KP; J.Cout = L.Cout; J.LDK = L.LDK; J.in_ld = in_ld;
   J.tf32_k = tf32_k; J.tf32_v = tf32_v;
   J.heads = L.heads; J.seg = L.heads > 1 ? L.seg : L.KP;       // one head: a single segment of KP columns
@@ -718,6 +726,7 @@ int prologue(const Layout& L, const gf_attn_desc* d, const float* Y, const float
     batch.njobs = 1;
     stage_i_fill(batch.job[0], L, Y, AK, CK, f + L.f_AV, f + L.f_CV, f, ws + L.w_Kp, ws + L.w_Vt, ws + L.w_Rt, ws + L.w_Ct,
                  in_scale, in_scale_ld, tf32, tf32);
+    batch.job[0].CBout = ws + L.w_CB;
     return stage_i_launch(batch, L.B, st);
   }
   // duplex: KPALL [B*k, LDK] = key_source @ AK + CK with key_source = Xbar or the centroids (inner dimension C): tensor cores
@@ -818,9 +827,11 @@ int prologue_batch(int n, const Layout* Ls, const gf_attn_desc* const* ds, const
       if (L.duplex)
         stage_i_fill(J, L, Ys[done], f + L.f_AM, f + L.f_CM, f + L.f_AV, f + L.f_CV, f, ws + L.w_M, ws + L.w_Vt, ws + L.w_Rt2, ws + L.w_Ct2,
                      isc, isc_ld, tc_centroid_supported(L, d) ? 1 : 0, tf32_t);
-      else
+      else {
         stage_i_fill(J, L, Ys[done], f + L.f_AK, f + L.f_CK, f + L.f_AV, f + L.f_CV, f, ws + L.w_Kp, ws + L.w_Vt, ws + L.w_Rt, ws + L.w_Ct,
                      isc, isc_ld, tf32_t, tf32_t);
+        J.CBout = ws + L.w_CB;
+      }
       ++done;
     }
     int rc = stage_i_launch(batch, B, st);

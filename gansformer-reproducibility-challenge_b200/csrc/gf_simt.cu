@@ -22,6 +22,8 @@ struct TokenParams {
   const float* pbias; const float* pnoise; const float* pstrength; long long pnoise_bstride; int pact; float pgain; int has_post;
   const float* in_scale; const float* post_scale; int in_ld, post_ld;
   int heads, seg;            // multi-head: softmax per segment of `seg` table columns (heads * seg == KP)
+  DropoutArgs dp;            // attention dropout (training): thr = 0 when off
+  const float* cb;           // [Cout] bo (+1): re-added as (1 - sum q) * cb when the mask broke sum q = 1
 };
 
 __device__ __forceinline__ void load_x_chunk(float (*xs)[XS], const float* __restrict__ Xb, int t0, int n, int C, int c0) {
@@ -124,6 +126,20 @@ __global__ void __launch_bounds__(TM) token_simt_kernel(const TokenParams P) {
     }
   }
 
+  float qdef = 0.f;          // 1 - sum of the (dropped, rescaled) probabilities: weight of the un-droppable constants
+  if (P.dp.thr) {            // attention dropout: drop / rescale the probabilities (the attention map above is pre-dropout)
+    const unsigned long long seed = P.dp.state[0], step = P.dp.state[1];
+    float qs = 0.f;
+#pragma unroll
+    for (int q = 0; q < KP / 4; ++q) {
+      float mk[4];
+      dropout_mult4(P.dp, seed, step, (uint32_t)((size_t)b * n + (valid ? t : 0)), q, mk);
+      s[q * 4] *= mk[0]; s[q * 4 + 1] *= mk[1]; s[q * 4 + 2] *= mk[2]; s[q * 4 + 3] *= mk[3];
+      qs += (s[q * 4] + s[q * 4 + 1]) + (s[q * 4 + 2] + s[q * 4 + 3]);
+    }
+    qdef = 1.f - qs;
+  }
+
   float mean = 0.f, rstd = 1.f;
   if (P.norm == GF_NORM_LAYER) {
     const float invC = 1.f / (float)C;
@@ -166,6 +182,7 @@ __global__ void __launch_bounds__(TM) token_simt_kernel(const TokenParams P) {
         const float4 v = *reinterpret_cast<const float4*>(&vs[cc][j4]);
         g = fmaf(s[j4], v.x, fmaf(s[j4 + 1], v.y, fmaf(s[j4 + 2], v.z, fmaf(s[j4 + 3], v.w, g))));
       }
+      if (P.dp.thr) g = fmaf(qdef, __ldg(P.cb + c0 + cc), g);      // the constants (bo, the 1 of 1 + gain) are not dropped
       const float x = xs[tid][cc] * isc[cc];
       float xn;
       if (affine) xn = fmaf(x, nsc[cc], nsh[cc]);
@@ -180,6 +197,7 @@ __global__ void __launch_bounds__(TM) token_simt_kernel(const TokenParams P) {
           const float4 v = *reinterpret_cast<const float4*>(&vs2[cc][j4]);
           bb = fmaf(s[j4], v.x, fmaf(s[j4 + 1], v.y, fmaf(s[j4 + 2], v.z, fmaf(s[j4 + 3], v.w, bb))));
         }
+        if (P.dp.thr) bb = fmaf(qdef, __ldg(P.cb + C + c0 + cc), bb);
         y = fmaf(xn, g, bb);
       }
       if (P.has_post) {
@@ -212,6 +230,8 @@ int token_pass_simt(const Layout& L, const gf_attn_desc* d, const float* X, floa
   P.in_scale = post ? post->in_scale : nullptr; P.post_scale = post ? post->post_scale : nullptr;
   P.in_ld = post ? post->in_scale_ld : 0; P.post_ld = post ? post->post_scale_ld : 0;
   P.heads = L.heads; P.seg = L.seg;
+  { int rcd = dropout_args(post, &P.dp); if (rcd) return rcd; }
+  P.cb = ws + L.w_CB;
   dim3 grid((L.n + TM - 1) / TM, L.B);
   if (L.KP == 16) token_simt_kernel<16><<<grid, TM, 0, st>>>(P);
   else token_simt_kernel<32><<<grid, TM, 0, st>>>(P);

@@ -250,6 +250,7 @@ class SynthesisLayer(nn.Module):
                             in_scale=in_scale, post_scale=post_scale)
                 if rgb is not None:
                     post.update(rgb)
+                post.update(self.attention.dropout_postop(x.device))     # training-mode forward under no_grad (the D step's fakes)
                 if prepared is not None and prepared[0] is not None:
                     torch.cuda.current_stream(x.device).wait_event(prepared[0])
                 xo, att, centroids = self.attention(xl, y, centroids=centroids, return_att=return_att, postop=post,
@@ -380,7 +381,8 @@ class SynthesisNetwork(nn.Module):
                     # tRGB planes from the layer output and writes x * (next block's style): the tRGB pass disappears
                     C_ = layer.weight.shape[0]
                     tg = self.torgbs[bi]
-                    if C_ <= 256 and _inference(tg.weight, tg.bias) and tc_eligible(layer.attention, (B, res, res, C_), k):
+                    if C_ <= 256 and _inference(tg.weight, tg.bias) and tc_eligible(layer.attention, (B, res, res, C_), k) \
+                            and not layer.attention.dropout_postop(x.device):        # (dropout runs on the CUDA-core kernel)
                         st_rgb = styles_all[len(self.layers) + bi]
                         rgb_w = (tg.weight.reshape(1, 3, C_) * st_rgb[:, None, :] * (1.0 / math.sqrt(C_))).contiguous()
                         rgb = torch.empty((B, 3, res, res), device=x.device, dtype=torch.float32)
@@ -416,14 +418,15 @@ class Generator(nn.Module):
                  transformer: bool = True, g_start_res: int = 8, g_end_res: Optional[int] = None, kmeans: bool = False,
                  kmeans_iters: int = 1, iterative: bool = False, integration: str = "mul", norm: Optional[str] = "layer",
                  use_pos: bool = True, pos_dim: Optional[int] = None, num_heads: int = 1, mapping_layers: int = 8,
-                 fmap_base: int = 16384, fmap_max: int = 512, exact_fp32: bool = False, ltnt2ltnt: bool = False, g_img2ltnt: bool = False):
+                 fmap_base: int = 16384, fmap_max: int = 512, exact_fp32: bool = False, ltnt2ltnt: bool = False, g_img2ltnt: bool = False,
+                 att_dp: float = 0.0):
         super().__init__()
         # D = latent_size // components_num unless given
         self.latent_dim = latent_dim if latent_dim is not None else max(latent_size // max(components_num, 1), 1)
         self.components_num, self.resolution = components_num, resolution
         attn_kwargs = dict(pos_dim=pos_dim, num_heads=num_heads, integration=integration, norm=norm, kmeans=kmeans,
                            kmeans_iters=kmeans_iters, use_pos=use_pos, exact_fp32=exact_fp32, iterative=iterative,
-                           img2ltnt=bool(g_img2ltnt and kmeans))
+                           img2ltnt=bool(g_img2ltnt and kmeans), att_dp=att_dp)
         self.mapping = MappingNetwork(self.latent_dim, components_num, num_layers=mapping_layers, ltnt2ltnt=ltnt2ltnt,
                                       integration=integration, norm=norm, exact_fp32=exact_fp32)
         self.synthesis = SynthesisNetwork(resolution, self.latent_dim, components_num, fmap_base=fmap_base, fmap_max=fmap_max,

@@ -165,12 +165,17 @@ class Trainer:
         self._allreduce(self.buckets_d, stats)
         self.opt_d.step()
         # ---- generator: non-saturating logistic loss
+        if z.is_cuda:
+            from .attention import advance_dropout
+            advance_dropout(z.device)                 # attention dropout: fresh masks for the G phase (device-side, capturable)
         G.requires_grad_(True); D.requires_grad_(False)
         self._zero(self.opt_g, self.buckets_g)
         loss_g = F.softplus(-D(G(z, noise_mode=cfg.noise_mode))).mean()
         loss_g.backward()
         self._allreduce(self.buckets_g, stats)
         self.opt_g.step()
+        if z.is_cuda:
+            advance_dropout(z.device)                 # ... and for the next step
         # ---- moving average of the generator (and of the mapping outputs: the truncation trick's w_avg)
         with torch.no_grad():
             if hasattr(G, "mapping") and hasattr(G.mapping, "w_avg"):

@@ -93,6 +93,14 @@ typedef struct gf_attn_postop {
   const float* rgb_w;
   const float* rgb_bias;
   float* rgb_out;
+  /* attention dropout (att_dp of transformer_layer; training only): every probability of the k-softmax is dropped with probability
+   * att_dp and the survivors are scaled by 1 / (1 - att_dp).  The mask is Philox4x32-10 of (token, column block, dp_salt, step) keyed
+   * by the seed; dp_state points to DEVICE memory {uint64 seed, uint64 step} read when the kernel runs (bump `step` on the device
+   * between training steps: a replayed CUDA graph then draws fresh masks).  Served by the CUDA-core kernels (the call takes the
+   * fp32 path); the attention map output is the probabilities BEFORE dropout.  att_dp = 0 or dp_state = NULL: off. */
+  float att_dp;
+  uint32_t dp_salt;
+  const unsigned long long* dp_state;
 } gf_attn_postop;
 
 /* Raw (un-scaled) parameters of one layer, each [fan_in, fan_out] row-major; equalised-LR scaling
@@ -185,6 +193,18 @@ int gf_attn_norm_stats(const gf_attn_desc* desc, const float* X, void* ws, void*
  *   dKp[b] = dS[b]^T X[b],  dVt[b] = dCtl[b]^T P[b],  dRt[b,h,:] = sum_w dS[b,h,w,:],  dCt[b,w,:] = sum_h dS[b,h,w,:]. */
 int gf_attn_simplex_bwd(const gf_attn_desc* desc, const float* X, const float* dOut, const float* Kp, const float* Vt,
                         const float* Rt, const float* Ct, float* dX, float* dS, float* P, float* dCtl, void* stream);
+
+/* gf_attn_simplex_bwd with attention dropout: the same (att_dp, dp_salt, dp_state) as the forward call regenerate the mask;
+ * P then receives the probabilities AFTER dropout q (what dVt = dCtl^T P needs), dS the gradient w.r.t. the logits.
+ * cb [Cout] = bo (+1 on the gain half): the constants dropout does not scale -- ctl = sum_j q_j (Vt_j - cb) + cb; the caller adds
+ * dcb = sum_tokens dCtl * (1 - sum_j q_j) to the gradient of bo.  cb may be NULL when att_dp == 0. */
+int gf_attn_simplex_bwd_ex(const gf_attn_desc* desc, const float* X, const float* dOut, const float* Kp, const float* Vt,
+                           const float* Rt, const float* Ct, float* dX, float* dS, float* P, float* dCtl,
+                           float att_dp, uint32_t dp_salt, const unsigned long long* dp_state, const float* cb, void* stream);
+
+/* The dropout multipliers themselves, mask [B, H*W, KP] (0 or 1 / (1 - att_dp); KP = 16 for k <= 16, else 32; columns of a
+ * multi-head layer: head * seg + j): what the fused kernels apply.  For the composite training path and for tests. */
+int gf_attn_dropout_mask(const gf_attn_desc* desc, float att_dp, uint32_t dp_salt, const unsigned long long* dp_state, float* mask, void* stream);
 
 #ifdef __cplusplus
 }

@@ -145,7 +145,7 @@ def transformer_layer(x_nchw: Tensor, y: Tensor, w: Dict[str, Tensor], *, integr
                       norm: Optional[str] = "layer", duplex: bool = False, num_heads: int = 1,
                       use_pos: bool = True, return_att: bool = False,
                       centroids_in: Optional[Tensor] = None, kmeans_iters: int = 1, img2ltnt: bool = False,
-                      centroids_init: Optional[Tensor] = None):
+                      centroids_init: Optional[Tensor] = None, att_mult: Optional[Tensor] = None):
     """Bipartite attention, direct form.
 
     x_nchw [B,C,H,W]; y [B,k,D] (the k local latents).  Returns (x' [B,C,H,W], att [B,k,H,W] or None,
@@ -159,6 +159,8 @@ def transformer_layer(x_nchw: Tensor, y: Tensor, w: Dict[str, Tensor], *, integr
     centroids_init (duplex; `iterative=True` upstream, [SPEC]): centroids carried over from the previous attention layer of the same
     channel width initialise the k-means: the FIRST iteration already takes its queries from them (through wcq) instead of from the
     latents.
+    att_mult [B,n,k] (training; att_dp): dropout multipliers (0 or 1/(1-p), oracle/philox.py) applied to the probabilities before they
+    weight the values; the returned attention map is the probabilities before dropout.
     """
     B, C, H, W = x_nchw.shape
     n = H * W
@@ -209,7 +211,8 @@ def transformer_layer(x_nchw: Tensor, y: Tensor, w: Dict[str, Tensor], *, integr
     Qh, Kh, Vh = _split_heads(Q, h), _split_heads(K, h), _split_heads(V, h)
     S = (Qh @ Kh.transpose(2, 3)) * scale          # [B,h,n,k]
     P = torch.softmax(S, dim=3)                    # over the k latents
-    ctrl = (P @ Vh).permute(0, 2, 1, 3).reshape(B, n, C)
+    Pd = P if att_mult is None else P * att_mult.to(dt)[:, None]      # attention dropout (same mask for every head: single-head layers only)
+    ctrl = (Pd @ Vh).permute(0, 2, 1, 3).reshape(B, n, C)
     control = _dense(ctrl, w["wo"], w["bo"])       # gain (| bias)
     Xo = integrate(X, control, integration, norm)
 

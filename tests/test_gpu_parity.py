@@ -734,9 +734,9 @@ def test_training_step_graph_replay(gf, cuda_dev):
     from importlib import import_module
     tr = import_module("gansformer-reproducibility-challenge_b200.training")
     torch.manual_seed(0)
-    G = gf.Generator(resolution=64, components_num=8, latent_dim=32, fmap_base=2048, fmap_max=128, mapping_layers=4).to(cuda_dev)
+    G = gf.Generator(resolution=64, components_num=8, latent_dim=32, fmap_base=2048, fmap_max=128, mapping_layers=4, att_dp=0.12).to(cuda_dev)
     D = tr.Discriminator(64, fmap_base=2048, fmap_max=128).to(cuda_dev)
-    trainer = tr.Trainer(G, D, tr.TrainConfig(d_reg_interval=2))
+    trainer = tr.Trainer(G, D, tr.TrainConfig(d_reg_interval=2))        # attention dropout on: the masks come from device state
     g = torch.Generator().manual_seed(5)
     z = torch.randn(4, 9, 32, generator=g).to(cuda_dev)
     reals = (torch.rand(4, 3, 64, 64, generator=g) * 2 - 1).to(cuda_dev)
@@ -994,3 +994,86 @@ def test_generator_duplex_extensions_end_to_end(gf, cuda_dev, exact):
     ref_nocarry = og.generator_forward(G.state_dict(), z, resolution=64, components_num=8, latent_dim=32, duplex=True, mapping_layers=4,
                                        kmeans_iters=2, img2ltnt=True, iterative=False)
     assert (ref - ref_nocarry).abs().max() > 1e-3 * ref.abs().max()
+
+
+def _dropout_mask(gf, dev, B, H, W, C, k, D, p, salt, seed, step):
+    """gf_attn_dropout_mask -> [B, n, KP] float32 on the CPU."""
+    import ctypes
+    from importlib import import_module
+    am = import_module("gansformer-reproducibility-challenge_b200.attention")
+    am.set_dropout_seed(seed, dev, step)
+    desc = gf._lib.make_desc(B, H, W, C, k, D, pos_dim=0)
+    KP = 16 if k <= 16 else 32
+    mask = torch.empty(B, H * W, KP, device=dev)
+    gf._lib.check(gf._lib.load().gf_attn_dropout_mask(ctypes.byref(desc), ctypes.c_float(p), salt, am.dropout_state(dev).data_ptr(), mask.data_ptr(),
+                                                      ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "gf_attn_dropout_mask")
+    torch.cuda.synchronize()
+    return mask.cpu()
+
+
+def test_dropout_mask_matches_philox_oracle(gf, cuda_dev):
+    """The kernels' attention-dropout mask (Philox4x32-10, csrc/gf_common.cuh) is reproduced bit for bit by oracle/philox.py, whose
+    Philox matches the published Random123 known-answer vectors; the keep rate is 1 - p."""
+    from oracle import philox as ph
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        assert tuple(int(x) for x in ph.philox4x32_10(*ctr, *key)) == want
+    for (B, H, W, k, p, salt, seed, step) in [(2, 10, 13, 7, 0.12, 5, 1234567890123, 0), (3, 16, 16, 20, 0.5, 0xdeadbeef, 42, 300), (1, 64, 64, 16, 0.12, 1, 7, 70000000)]:
+        got = _dropout_mask(gf, cuda_dev, B, H, W, 64, k, 16, p, salt, seed, step)
+        want = ph.dropout_mult(p, seed, step, salt, B * H * W, got.shape[2]).reshape(got.shape)
+        assert np.array_equal(got.numpy(), want)
+        keep = (got > 0).float().mean().item()
+        assert abs(keep - (1 - p)) < 4 * math.sqrt(p * (1 - p) / got.numel()) + 1e-3
+        assert torch.all((got == 0) | ((got - 1 / (1 - p)).abs() < 1e-6))
+
+
+@pytest.mark.parametrize("C,H,W,k,integration,norm", [(64, 8, 16, 4, "both", "layer"), (96, 10, 13, 20, "mul", "layer"), (128, 16, 16, 16, "add", "none")])
+def test_attention_dropout_forward_and_backward(gf, cuda_dev, C, H, W, k, integration, norm):
+    """att_dp (training mode): forward and gradients of a simplex layer with dropped probabilities against the oracle given the SAME
+    mask (oracle/philox.py); eval mode and a bumped step behave as expected."""
+    from importlib import import_module
+    from oracle import philox as ph
+    am = import_module("gansformer-reproducibility-challenge_b200.attention")
+    D = p = 16
+    B, pd = 2, 0.25
+    g = torch.Generator().manual_seed(C + k)
+    x64 = torch.randn(B, C, H, W, generator=g, dtype=torch.float64).requires_grad_(True)
+    y64 = torch.randn(B, k, D, generator=g, dtype=torch.float64).requires_grad_(True)
+    w = {n: t.requires_grad_(True) for n, t in ob.init_params(C, D, k, p, integration, False, seed=4, bias_std=0.3).items()}
+    nrm = None if norm == "none" else norm
+    attn = gf.BipartiteAttention(C, D, k, pos_dim=p, integration=integration, norm=nrm, att_dp=pd, exact_fp32=True).to(cuda_dev)
+    with torch.no_grad():
+        for n, prm in attn.named_parameters():
+            prm.copy_(w[n].detach().float())
+    seed, step = 987654321, 3
+    am.set_dropout_seed(seed, cuda_dev, step)
+    KP = 16 if k <= 16 else 32
+    mult = torch.from_numpy(ph.dropout_mult(pd, seed, step, attn.dp_salt, B * H * W, KP).reshape(B, H * W, KP)[:, :, :k].copy())
+    ref, ratt, _ = ob.transformer_layer(x64, y64, w, integration=integration, norm=nrm, return_att=True, att_mult=mult)
+    gout = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+    ref.backward(gout)
+    xg = x64.detach().permute(0, 2, 3, 1).contiguous().float().to(cuda_dev)
+    yg = y64.detach().float().to(cuda_dev)
+    attn.train()
+    with torch.no_grad():                                            # training-mode forward without autograd (the D step's fakes)
+        out, att, _ = attn(xg, yg, return_att=True)
+    check_close(out, ref.detach().permute(0, 2, 3, 1), "simt_fp32", "dropout/forward", tol_scale=2.0)
+    assert (att.cpu().double() - ratt.detach()).abs().max() <= 1e-5   # the map is the probabilities BEFORE dropout
+    xr, yr = xg.clone().requires_grad_(True), yg.clone().requires_grad_(True)
+    out2, _, _ = attn(xr, yr)
+    assert torch.equal(out2.detach(), out)
+    out2.backward(gout.permute(0, 2, 3, 1).contiguous().float().to(cuda_dev))
+    rel = lambda a, b: ((a.double().cpu() - b).norm() / b.norm().clamp_min(1e-30)).item()
+    assert rel(xr.grad, x64.grad.permute(0, 2, 3, 1)) < 1e-4 and rel(yr.grad, y64.grad) < 1e-4
+    for n in ("wq", "wv", "wo", "wk", "pos_latent", "bo", "bv", "bq"):
+        assert rel(getattr(attn, n).grad, w[n].grad) < 2e-4, n
+    with torch.no_grad():
+        am.advance_dropout(cuda_dev)                                 # next step: another mask
+        out3, _, _ = attn(xg, yg)
+        attn.eval()                                                  # eval: no dropout
+        out4, _, _ = attn(xg, yg)
+    assert (out3 - out).abs().max() > 1e-3
+    ref0, _, _ = ob.transformer_layer(x64.detach(), y64.detach(), {n: t.detach() for n, t in w.items()}, integration=integration, norm=nrm)
+    check_close(out4, ref0.permute(0, 2, 3, 1), "simt_fp32", "dropout/eval")

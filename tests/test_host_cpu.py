@@ -34,7 +34,7 @@ def test_header_symbols_are_exported(gf):
 def test_struct_layouts_match_c(gf):
     assert ctypes.sizeof(gf._lib.GfAttnDesc) == 12 * 4
     assert ctypes.sizeof(gf._lib.GfAttnWeights) == 23 * ctypes.sizeof(ctypes.c_void_p)
-    assert ctypes.sizeof(gf._lib.GfAttnPostop) == 3 * 8 + 8 + 4 + 4 + 2 * 8 + 2 * 4 + 3 * 8
+    assert ctypes.sizeof(gf._lib.GfAttnPostop) == 3 * 8 + 8 + 4 + 4 + 2 * 8 + 2 * 4 + 3 * 8 + 4 + 4 + 8
 
 
 def test_sizes_and_validation(gf):
@@ -317,7 +317,7 @@ def test_folded_tables_match_oracle_prologue(gf, C, H, W, k, D, p, integration, 
     y = torch.randn(2, k, D, generator=torch.Generator().manual_seed(9), dtype=torch.float64)
     f = of.fold_weights(w, C=C, k=k, integration=integration, duplex=False, use_pos=use_pos)
     Kp, Vt, Rt, Ct = of.prologue(y, f, C=C, H=H, W=W, p=p, use_pos=use_pos)
-    gKp, gVt, gRt, gCt = ag.folded_tables(y, w, H=H, W=W, C=C, integration=integration, use_pos=use_pos)
+    gKp, gVt, gRt, gCt, gcb = ag.folded_tables(y, w, H=H, W=W, C=C, integration=integration, use_pos=use_pos)
     for got, want in ((gKp, Kp), (gVt, Vt), (gCt, Ct)):
         assert got.shape == want.shape and (got - want).abs().max() < 1e-11 * max(1.0, want.abs().max().item())
     fin = torch.isfinite(Rt)
