@@ -496,6 +496,31 @@ def run_ours(args):
         torch.backends.cuda.matmul.allow_tf32 = True
         del replay32
 
+    # ---- the same resident steps with cuDNN's TF32 stride-1 convolutions instead of the library's own implicit-GEMM kernel (row f1) ----
+    t_cudnn = None
+    if not args.no_fp32_convs:
+        os.environ["GF_CUDNN_CONV"] = "1"
+        try:
+            with torch.no_grad():
+                G(z_dev)
+            replay_c = G.graphed(B) if use_graph else None      # graph key includes the switch: a new capture
+            nc = max(3, min(args.steps, 10))
+            for _ in range(2):
+                replay_c(z_dev) if replay_c is not None else step_eager()
+            dist_mod.barrier()
+            torch.cuda.synchronize()
+            c0_, c1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0_.record()
+            for _ in range(nc):
+                replay_c(z_dev) if replay_c is not None else step_eager()
+            c1_.record()
+            torch.cuda.synchronize()
+            dist_mod.barrier()
+            t_cudnn = dist_mod.max_over_ranks(c0_.elapsed_time(c1_) * 1e-3, device) / nc
+            del replay_c
+        finally:
+            del os.environ["GF_CUDNN_CONV"]
+
     # ---- BASELINE configs[3]: the training step (the only collective of the system: the gradient all-reduce).  Runs at every N
     #      (SCALE carries it); a watchdog prints the headline line without it if a rank hangs inside the probe.
     tp = None
@@ -518,7 +543,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": world * B * args.steps / t_total, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32 (fp32 storage; tcgen05 kind::tf32 attention, TF32 cuDNN convs; value_fp32_convs = the same with fp32 convs)" if path == "tcgen05_tf32" else "f32 (CUDA-core attention; TF32 cuDNN convs)",
+            "vs_baseline": None, "dtype": "tf32 (fp32 storage; tcgen05 kind::tf32 attention and stride-1 3x3 convolutions (own kernels), TF32 cuDNN up-convolutions; value_fp32_convs = the same with fp32 cuDNN convolutions)" if path == "tcgen05_tf32" else "f32 (CUDA-core attention; TF32 cuDNN convs)",
             "data": "synthetic",
             "config": {"workload": cfg["label"] + ", integration=mul, norm=layer, random-init weights (seed 0), latents seed 1",
                        "global_batch": world * B, "parallelism": f"dp{world} (images sharded, no data-path collective)",
@@ -546,6 +571,10 @@ def run_ours(args):
         if t_fp32 is not None:
             line["value_fp32_convs"] = {"value": world * B / t_fp32, "unit": UNIT, "ms_per_step": t_fp32 * 1e3,
                                         "note": "same step, torch.backends.cudnn.allow_tf32 = False (fp32 cuDNN convolutions); attention unchanged"}
+        if t_cudnn is not None:
+            line["value_cudnn_convs"] = {"value": world * B / t_cudnn, "unit": UNIT, "ms_per_step": t_cudnn * 1e3,
+                                         "note": "same step with GF_CUDNN_CONV=1: cuDNN TF32 for the five stride-1 3x3 convolutions that otherwise run on "
+                                                 "the library's own tcgen05 implicit-GEMM kernel (gf_conv3x3_nhwc_tf32, SURVEY row f1)"}
         state["line"] = line
     if world == 1 and not args.no_duplex_probe and args.config == 2:
         peak, _ = measured_peak_gbs()

@@ -74,12 +74,14 @@ def nf(res: int, fmap_base: int = 16384, fmap_max: int = 512) -> int:
 def modulated_conv2d(x: torch.Tensor, weight: torch.Tensor, styles: torch.Tensor, *, demodulate: bool = True,
                      up: int = 1, f: Optional[torch.Tensor] = None, w_eff: Optional[torch.Tensor] = None,
                      wsq: Optional[torch.Tensor] = None, prescaled: bool = False, defer_demod: bool = False,
-                     d: Optional[torch.Tensor] = None, phases=None):
+                     d: Optional[torch.Tensor] = None, phases=None, wt_packed: Optional[torch.Tensor] = None):
     """StyleGAN2 modulated convolution in its activation-scaling form: (x * s) conv w, then * demod.
 
     Identical in exact arithmetic to modulating the weights per sample (the reference's grouped-conv form);
     avoids B separate weight tensors.  weight [O, I, kh, kw]; styles [B, I].  The two scalings and the FIR blur of the
-    upsampling path are the native ops of ops.py (gf_ops.h); the convolution itself is cuDNN (SURVEY row f1 is next).
+    upsampling path are the native ops of ops.py (gf_ops.h).  The stride-1 3x3 convolution runs on the library's own tcgen05
+    implicit-GEMM kernel (wt_packed, row f1) when TF32 convolutions are allowed and the shape is eligible, else on cuDNN; the
+    polyphase up-convolutions are cuDNN.
     w_eff / wsq: optional cached equalised-LR weight (already transposed for up=2) and its squared sum over the taps.
     prescaled: x already carries the style scale (fused into the producer's store).  defer_demod (up == 1 only): return
     (conv output, d) and let the consumer (the attention kernel's load side) apply the demodulation."""
@@ -95,7 +97,10 @@ def modulated_conv2d(x: torch.Tensor, weight: torch.Tensor, styles: torch.Tensor
     if not prescaled:
         x = ops.chan_scale(x, styles)
     if up == 1:
-        x = F.conv2d(x, w_eff, padding=kh // 2)
+        if wt_packed is not None:
+            x = ops.conv3x3_native(x, wt_packed)                      # row f1: own tcgen05 implicit-GEMM kernel (TF32)
+        else:
+            x = F.conv2d(x, w_eff, padding=kh // 2)
         if defer_demod:
             return x, d
         if d is not None:
@@ -202,9 +207,12 @@ class SynthesisLayer(nn.Module):
         w = self.weight * (1.0 / math.sqrt(I * kh * kw))
         wsq = w.square().sum(dim=[2, 3])
         phases = ops.upconv_phase_weights(w) if self.up else None
+        packed = None
+        if not self.up and w.is_cuda and kh == 3 and I % 32 == 0 and O % 64 == 0:
+            packed = ops.conv3x3_pack(w)                               # [9, O, I], TF32-rounded: operand of gf_conv3x3_nhwc_tf32
         if self.up:
             w = w.transpose(0, 1)
-        return w.contiguous(memory_format=torch.channels_last), wsq.contiguous(), phases
+        return w.contiguous(memory_format=torch.channels_last), wsq.contiguous(), phases, packed
 
     def fusable(self, x) -> bool:
         """Inference on CUDA with an attention block whose norm the kernels can fuse around."""
@@ -220,9 +228,13 @@ class SynthesisLayer(nn.Module):
         from the layer output (fused path on the tcgen05 kernel only; SynthesisNetwork checks)."""
         if styles is None:
             styles = self.affine(w_glob)
-        w_eff = wsq = phases = None
+        w_eff = wsq = phases = packed = None
         if _inference(self.weight) and x.is_cuda:
-            w_eff, wsq, phases = _cached(self, "conv", (self.weight,), self._conv_weights)
+            w_eff, wsq, phases, packed = _cached(self, "conv", (self.weight,), self._conv_weights)
+            # own convolution kernel: TF32 only (the parity tests run true-fp32 convolutions), patches of 8 x 16 pixels
+            if packed is not None and not (torch.backends.cudnn.allow_tf32 and x.dtype == torch.float32 and x.shape[2] % 8 == 0
+                                           and x.shape[3] % 16 == 0 and not os.environ.get("GF_CUDNN_CONV")):
+                packed = None
         fused = self.fusable(x)
         in_scale = None
         # prepared = (event | None, demod): SynthesisNetwork already ran this layer's stage I (batched launch)
@@ -230,10 +242,11 @@ class SynthesisLayer(nn.Module):
             raise RuntimeError("internal: prepared prologue for a layer that does not take the fused path")
         if fused and not self.up:      # demodulation rides on the attention kernel's load side (folded into K')
             x, in_scale = modulated_conv2d(x, self.weight, styles, up=1, f=self.fir, w_eff=w_eff, wsq=wsq,
-                                           prescaled=prescaled, defer_demod=True, d=prepared[1] if prepared is not None else None)
+                                           prescaled=prescaled, defer_demod=True, d=prepared[1] if prepared is not None else None,
+                                           wt_packed=packed)
         else:
             x = modulated_conv2d(x, self.weight, styles, up=2 if self.up else 1, f=self.fir, w_eff=w_eff, wsq=wsq,
-                                 prescaled=prescaled, phases=phases)
+                                 prescaled=prescaled, phases=phases, wt_packed=None if self.up else packed)
         if noise_mode == "const":
             noise = self.noise_const
         elif noise_mode == "random":
@@ -346,7 +359,7 @@ class SynthesisNetwork(nn.Module):
                     continue
                 d_ = None
                 if not layer.up:        # the demodulation of a stride-1 convolution rides on the attention kernel's load side
-                    _, wsq_, _ = _cached(layer, "conv", (layer.weight,), layer._conv_weights)
+                    _, wsq_, _, _ = _cached(layer, "conv", (layer.weight,), layer._conv_weights)
                     d_ = ops.demod_coef(styles_all[li_], wsq_)
                 C_ = layer.weight.shape[0]
                 items.append((layer.attention, y, (B, layer.resolution, layer.resolution, C_), d_))
@@ -466,7 +479,7 @@ class Generator(nn.Module):
         The returned image tensor is a static buffer overwritten by the next replay.  Weight-derived tensors (folded
         attention weights, scaled conv weights) are baked at capture, so the graph is keyed on the parameters' storage,
         version counters and the process-wide weights epoch: any weight update re-captures."""
-        key = (batch_size, float(truncation_psi), noise_mode, weights_epoch(), bool(torch.backends.cudnn.allow_tf32),
+        key = (batch_size, float(truncation_psi), noise_mode, weights_epoch(), bool(torch.backends.cudnn.allow_tf32), bool(os.environ.get("GF_CUDNN_CONV")),
                tuple((p.data_ptr(), p._version) for p in self.parameters()))
         cache = self.__dict__.setdefault("_graphs", {})
         if key in cache:

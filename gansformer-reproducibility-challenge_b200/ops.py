@@ -287,3 +287,26 @@ def mapping_fwd(z: torch.Tensor, w_eff: torch.Tensor, b_eff: torch.Tensor, w_avg
         _lib.check(_lib.load().gf_mapping_fwd(z.contiguous().data_ptr(), w_eff.data_ptr(), b_eff.data_ptr(), wa.data_ptr() if wa is not None else None,
                                               float(psi), out.data_ptr(), B, k, D, L, _stream(z.device)), "gf_mapping_fwd")
     return out
+
+
+def conv3x3_pack(weight: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """weight [O, I, 3, 3] -> the tap-major, TF32-rounded [9, O, I] layout gf_conv3x3_nhwc_tf32 consumes (gf_conv3x3_pack_weights)."""
+    O, I = weight.shape[:2]
+    wt = torch.empty((9, O, I), dtype=torch.float32, device=weight.device)
+    with torch.cuda.device(weight.device):
+        _lib.check(_lib.load().gf_conv3x3_pack_weights(weight.detach().contiguous().data_ptr(), wt.data_ptr(), O, I, ctypes.c_float(scale),
+                                                       _stream(weight.device)), "gf_conv3x3_pack_weights")
+    return wt
+
+
+def conv3x3_native(x: torch.Tensor, wt: torch.Tensor) -> torch.Tensor:
+    """3x3 stride-1 zero-padded convolution on the tcgen05 implicit-GEMM kernel (row f1, TF32): x [B, I, H, W] (channels-last
+    storage), wt from conv3x3_pack -> [B, O, H, W] (channels-last storage).  CUDA fp32 inference only."""
+    xv = _nhwc_view(x)
+    B, H, W, I = xv.shape
+    O = wt.shape[1]
+    y = torch.empty((B, H, W, O), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().gf_conv3x3_nhwc_tf32(xv.data_ptr(), wt.data_ptr(), y.data_ptr(), B, H, W, I, O, _stream(x.device)),
+                   "gf_conv3x3_nhwc_tf32")
+    return y.permute(0, 3, 1, 2)

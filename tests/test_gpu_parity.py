@@ -1077,3 +1077,53 @@ def test_attention_dropout_forward_and_backward(gf, cuda_dev, C, H, W, k, integr
     assert (out3 - out).abs().max() > 1e-3
     ref0, _, _ = ob.transformer_layer(x64.detach(), y64.detach(), {n: t.detach() for n, t in w.items()}, integration=integration, norm=nrm)
     check_close(out4, ref0.permute(0, 2, 3, 1), "simt_fp32", "dropout/eval")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 64, 64), (3, 32, 16, 128, 128), (1, 8, 32, 256, 256), (2, 24, 48, 96, 192), (1, 64, 64, 32, 512)])
+def test_conv3x3_implicit_gemm(gf, cuda_dev, B, H, W, Cin, Cout):
+    """Row f1: the tcgen05 implicit-GEMM 3x3 convolution (TF32, zero padding by TMA out-of-bounds fill) against the oracle's
+    convolution (oracle/generator.py::_modconv without modulation) in float64."""
+    from importlib import import_module
+    ops = import_module("gansformer-reproducibility-challenge_b200.ops")
+    g = torch.Generator().manual_seed(B + H + Cin)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g)
+    ones = torch.ones(B, Cin, dtype=torch.float64)
+    want = og._modconv(x.double(), w.double(), ones, demodulate=False)                      # includes the 1/sqrt(fan_in) scale
+    xc = x.to(cuda_dev).contiguous(memory_format=torch.channels_last)
+    wt = ops.conv3x3_pack(w.to(cuda_dev), scale=1.0 / math.sqrt(Cin * 9))
+    with torch.no_grad():
+        got = ops.conv3x3_native(xc, wt)
+    torch.cuda.synchronize()
+    assert got.shape == want.shape
+    err = (got.double().cpu() - want).abs()
+    rel_rms = (err.pow(2).mean().sqrt() / want.pow(2).mean().sqrt()).item()
+    print(f"[conv] B={B} {H}x{W} {Cin}->{Cout} max_abs={err.max().item():.3e} peak={want.abs().max().item():.2f} rel_rms={rel_rms:.3e}")
+    assert rel_rms <= 5e-4 and err.max().item() <= 3e-3 * want.abs().max().item()       # TF32 operands, fp32 accumulation over 9 * Cin terms
+
+
+def test_generator_with_own_tf32_convolutions(gf, cuda_dev, monkeypatch):
+    """The benchmarked path end to end: TF32 convolutions allowed, so the five stride-1 3x3 convolutions of the 256^2 generator run on
+    the library's own tcgen05 implicit-GEMM kernel (row f1) and the rest on cuDNN TF32 -- image vs the fp64 oracle within the
+    SURVEY 8c end-to-end bound (5e-3 of the peak, 60 dB), and against the same network with cuDNN TF32 convolutions everywhere."""
+    G = _benchmark_generator(gf, cuda_dev, 256, 16, False)
+    z = torch.randn(2, 17, 32, generator=torch.Generator().manual_seed(1))
+    try:
+        torch.backends.cudnn.allow_tf32 = True
+        with torch.no_grad():
+            l0 = gf._lib.launch_count(); G(z.to(cuda_dev)); 
+            l0 = gf._lib.launch_count(); img = G(z.to(cuda_dev)).clone(); n_own = gf._lib.launch_count() - l0
+            monkeypatch.setenv("GF_CUDNN_CONV", "1")
+            l0 = gf._lib.launch_count(); img_c = G(z.to(cuda_dev)).clone(); n_cudnn = gf._lib.launch_count() - l0
+    finally:
+        torch.backends.cudnn.allow_tf32 = False
+    assert n_own == n_cudnn + 5                                    # res 16 .. 256: five convolutions on the own kernel
+    ref = og.generator_forward(G.state_dict(), z, resolution=256, components_num=16, latent_dim=32)
+    for name, im in (("own-conv", img), ("cudnn-tf32", img_c)):
+        err = (im.double().cpu() - ref).abs()
+        peak = ref.abs().max().item()
+        rmse = err.pow(2).mean().sqrt().item()
+        psnr = 20 * math.log10(peak / rmse)
+        print(f"[e2e-tf32conv] {name}: max_abs/peak={err.max().item() / peak:.3e} rel_rms={rmse / ref.pow(2).mean().sqrt().item():.3e} psnr={psnr:.1f} dB")
+        _log_parity(dict(what="tf32conv/" + name, path="e2e-tf32conv", max_abs=err.max().item(), peak=peak, psnr=psnr))
+        assert err.max().item() <= 5e-3 * peak and psnr >= 60.0
