@@ -210,6 +210,193 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Version 2: the three taps of a filter COLUMN share one activation box.  For a fixed dx the boxes of dy = 0, 1, 2 are the same
+// pixels shifted by whole image rows, and one image row of the 16-wide patch is 16 shared-memory rows = 2 KB -- a multiple of the
+// 1 KB swizzle repeat.  So one {32 ch, 16 w, 8 MT + 2 h} box per (dx, channel slab) serves all three dy taps (and both stacked
+// patches) through UMMA descriptors that differ only by (dy + 8 mt) * 2048 bytes: the activation traffic from L2 drops from 9 to
+// 3 * (8 MT + 2) / (8 MT) reads per input byte (3.4 for MT = 2), which is what bounded version 1.  Weights have their own ring
+// (one [BN x 32] slab per tap and channel slab).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int MAX_STA = 4, MAX_STB = 6;
+struct Bars2 {
+  uint64_t fullA[MAX_STA], emptyA[MAX_STA];
+  uint64_t fullB[MAX_STB], emptyB[MAX_STB];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base, pad;
+};
+struct Params2 {
+  int B, H, W, Cin, Cout;
+  int tiles_h, tiles_w, tiles_n;
+  long long total_tiles;
+  int nsta, nstb;
+  float alpha;
+};
+
+template <int BN, int MT, int NBUF>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3x3_tc_kernel_v2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY,
+                     const Params2 P) {
+  constexpr int A2_BYTES = (PH * MT + 2) * PW * 128;                         // halo box: (8 MT + 2) image rows x 16 pixels x 128 B
+  constexpr int B_BYTES = BN * BK * 4;
+  constexpr int ACC_COLS = MT * BN;
+  constexpr int TMEM_COLS = NBUF * ACC_COLS <= 128 ? 128 : (NBUF * ACC_COLS <= 256 ? 256 : 512);
+  static_assert(NBUF * ACC_COLS <= 512, "accumulators exceed TMEM");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t s_base = smem_u32(smem);
+  const int nsta = P.nsta, nstb = P.nstb;
+  const uint32_t s_a = s_base, s_b = s_base + (uint32_t)nsta * A2_BYTES;
+  const uint32_t s_out = s_b + (uint32_t)nstb * B_BYTES;                     // two staging slabs of 16 KB
+  uint8_t* out_ptr = smem + (size_t)nsta * A2_BYTES + (size_t)nstb * B_BYTES;
+  Bars2* bars = reinterpret_cast<Bars2*>(out_ptr + 2 * A_BYTES);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int nslab = P.Cin / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmX); prefetch_tmap(&tmW); prefetch_tmap(&tmY);
+    for (int i = 0; i < nsta; ++i) { mbar_init(smem_u32(&bars->fullA[i]), 1); mbar_init(smem_u32(&bars->emptyA[i]), 1); }
+    for (int i = 0; i < nstb; ++i) { mbar_init(smem_u32(&bars->fullB[i]), 1); mbar_init(smem_u32(&bars->emptyB[i]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
+
+  auto decode = [&](long long t, int& nt, int& pw, int& ph, int& b) {
+    nt = (int)(t % P.tiles_n); t /= P.tiles_n;
+    pw = (int)(t % P.tiles_w); t /= P.tiles_w;
+    ph = (int)(t % P.tiles_h); b = (int)(t / P.tiles_h);
+  };
+
+  if (warp == 0) {
+    // =============================== TMA producer: loads in the order the MMA warp consumes them ===============================
+    if (lane == 0) {
+      int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+      for (long long t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+        int nt, pw, ph, b;
+        decode(t, nt, pw, ph, b);
+        const int h0 = ph * PH * MT, w0 = pw * PW, n0 = nt * BN;
+        for (int sl = 0; sl < nslab; ++sl) {
+          for (int dx = 0; dx < 3; ++dx) {
+            mbar_wait(smem_u32(&bars->emptyA[sa]), pa ^ 1u);
+            const uint32_t fa = smem_u32(&bars->fullA[sa]);
+            mbar_expect_tx(fa, (uint32_t)A2_BYTES);
+            tma_load_4d(s_a + (uint32_t)sa * A2_BYTES, &tmX, fa, sl * BK, w0 + dx - 1, h0 - 1, b);      // rows h0-1 .. h0+8MT: zero-filled outside
+            if (++sa == nsta) { sa = 0; pa ^= 1u; }
+            for (int dy = 0; dy < 3; ++dy) {
+              mbar_wait(smem_u32(&bars->emptyB[sb]), pb ^ 1u);
+              const uint32_t fb = smem_u32(&bars->fullB[sb]);
+              mbar_expect_tx(fb, (uint32_t)B_BYTES);
+              tma_load_2d(s_b + (uint32_t)sb * B_BYTES, &tmW, fb, sl * BK, (dy * 3 + dx) * P.Cout + n0);
+              if (++sb == nstb) { sb = 0; pb ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer (warp-converged) ===============================
+    constexpr uint32_t IDESC = umma_idesc_tf32(TILE_M, BN);
+    const uint64_t dA0 = umma_desc(s_a, 1024, LAYOUT_SW128);
+    const uint64_t dB0 = umma_desc(s_b, 1024, LAYOUT_SW128);
+    int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+    uint32_t it = 0;
+    for (long long t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
+      const int buf = (int)(it % NBUF);
+      mbar_wait(smem_u32(&bars->acc_empty[buf]), ((it / NBUF) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_acc = tmem + (uint32_t)buf * ACC_COLS;
+      uint32_t first = 0;                                      // 0 until the tile's first MMA has been issued
+#pragma unroll 1
+      for (int sl = 0; sl < nslab; ++sl) {
+#pragma unroll 1
+        for (int dx = 0; dx < 3; ++dx) {
+          mbar_wait(smem_u32(&bars->fullA[sa]), pa);
+          tc_fence_after();
+          const uint64_t da = dA0 + (uint64_t)(sa * (A2_BYTES >> 4));
+#pragma unroll 1
+          for (int dy = 0; dy < 3; ++dy) {
+            mbar_wait(smem_u32(&bars->fullB[sb]), pb);
+            tc_fence_after();
+            const uint64_t db = dB0 + (uint64_t)(sb * (B_BYTES >> 4));
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                // patch mt, tap row dy: the box shifted down by (dy + 8 mt) image rows of 16 pixels x 128 B = 2 KB each
+                umma_ss_elect(d_acc + mt * BN, da + (uint64_t)(((dy + PH * mt) * PW * 128) >> 4) + kk * 2, db + kk * 2, IDESC, first | (uint32_t)kk);
+              }
+            first = 1;
+            umma_commit_elect(smem_u32(&bars->emptyB[sb]));
+            if (++sb == nstb) { sb = 0; pb ^= 1u; }
+          }
+          umma_commit_elect(smem_u32(&bars->emptyA[sa]));
+          if (++sa == nsta) { sa = 0; pa ^= 1u; }
+        }
+      }
+      umma_commit_elect(smem_u32(&bars->acc_full[buf]));
+    }
+  } else {
+    // =============================== epilogue warps (as version 1) ===============================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int sw = row & 7;
+    const bool leader = warp == 2 && lane == 0;
+    uint32_t it = 0, slab_ctr = 0;
+    for (long long t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
+      int nt, pw, ph, b;
+      decode(t, nt, pw, ph, b);
+      const int buf = (int)(it % NBUF);
+      mbar_wait(smem_u32(&bars->acc_full[buf]), (it / NBUF) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < MT * BN; cc += 32, ++slab_ctr) {
+        const int mt = cc / BN, c0 = cc - mt * BN;
+        float v[32];
+        tmem_ld16(tmem + lane_addr + (uint32_t)buf * ACC_COLS + cc, v);
+        tmem_ld16(tmem + lane_addr + (uint32_t)buf * ACC_COLS + cc + 16, v + 16);
+        tmem_wait_ld();
+        const int sl = (int)(slab_ctr & 1u);
+        if (slab_ctr >= 2) {
+          if (leader) tma_wait_read1();
+          named_bar_sync(1, 128);
+        }
+        uint8_t* dst = out_ptr + (size_t)sl * A_BYTES + (size_t)row * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<float4*>(dst + ((c ^ sw) << 4)) =
+              make_float4(v[c * 4] * P.alpha, v[c * 4 + 1] * P.alpha, v[c * 4 + 2] * P.alpha, v[c * 4 + 3] * P.alpha);
+        fence_proxy_async();
+        named_bar_sync(2, 128);
+        if (leader) {
+          tma_store_4d(&tmY, s_out + (uint32_t)sl * A_BYTES, nt * BN + c0, pw * PW, (ph * MT + mt) * PH, b);
+          tma_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[buf]));
+    }
+    if (leader) tma_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+  }
+}
+
 // 4-D fp32 NHWC tensor map: dims {C, W, H, B}, box {box_c, box_w, box_h, 1}
 static int make_map_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, int C, int box_c, int box_w, int box_h) {
   EncodeTiledFn enc = get_encode();
@@ -243,6 +430,39 @@ static int launch(const float* x, const float* wt, float* y, int B, int H, int W
   P.alpha = 1.000352220f;              // the tensor core truncates x to TF32 (mean relative bias 0.7213 * 2^-11); the weights are pre-rounded
   const int smem_bytes = nst * STAGE_BYTES + 2 * A_BYTES + (int)sizeof(Bars) + 1024;
   auto kern = conv3x3_tc_kernel<BN, MT, NBUF>;
+  GF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  long long grid = device_sms();
+  if (grid > P.total_tiles) grid = P.total_tiles;
+  kern<<<(unsigned)grid, NUM_THREADS, smem_bytes, st>>>(tmX, tmW, tmY, P);
+  GF_LAUNCH_OK();
+  return GF_OK;
+}
+
+template <int BN, int MT, int NBUF>
+static int launch_v2(const float* x, const float* wt, float* y, int B, int H, int W, int Cin, int Cout, cudaStream_t st) {
+  constexpr int A2_BYTES = (PH * MT + 2) * PW * 128, B_BYTES = BN * BK * 4;
+  CUtensorMap tmX, tmW, tmY;
+  int rc;
+  if ((rc = make_map_nhwc(&tmX, x, B, H, W, Cin, BK, PW, PH * MT + 2))) return rc;
+  if ((rc = make_map(&tmW, wt, (uint64_t)9 * Cout, (uint64_t)Cin, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map_nhwc(&tmY, y, B, H, W, Cout, 32, PW, PH))) return rc;
+  Params2 P;
+  P.B = B; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout;
+  P.tiles_h = H / (PH * MT); P.tiles_w = W / PW; P.tiles_n = Cout / BN;
+  P.total_tiles = (long long)B * P.tiles_h * P.tiles_w * P.tiles_n;
+  // shared memory: activation ring (one box per filter column) + weight ring (three slabs per box) + two staging slabs
+  const int avail = device_smem_optin() - 2 * A_BYTES - (int)sizeof(Bars2) - 1024;
+  int nsta = 2, nstb = (avail - nsta * A2_BYTES) / B_BYTES;
+  if (nstb > MAX_STB) {                                   // room to spare: a third activation stage
+    nsta = 3;
+    nstb = (avail - nsta * A2_BYTES) / B_BYTES;
+    if (nstb > MAX_STB) nstb = MAX_STB;
+  }
+  if (nstb < 2) { set_error("conv3x3 v2: shared memory too small (BN=%d MT=%d)", BN, MT); return GF_ERR_UNSUPPORTED; }
+  P.nsta = nsta; P.nstb = nstb;
+  P.alpha = 1.000352220f;
+  const int smem_bytes = nsta * A2_BYTES + nstb * B_BYTES + 2 * A_BYTES + (int)sizeof(Bars2) + 1024;
+  auto kern = conv3x3_tc_kernel_v2<BN, MT, NBUF>;
   GF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   long long grid = device_sms();
   if (grid > P.total_tiles) grid = P.total_tiles;
@@ -287,12 +507,27 @@ extern "C" int gf_conv3x3_nhwc_tf32(const float* x, const float* wt, float* y, i
   int rc;
   if ((rc = check_device())) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  // Dispatch (measured on the generator's shapes, batch 32, tools/conv_bench.py; GF_CONV_V2=0 / 1 and GF_CONV_BIG / GF_CONV_MT force):
+  //   * 16 x 16 patches need enough tiles to fill the GPU: fewer than one per SM -> version 1 with 8 x 16 patches (res 16: 0.056 ms,
+  //     cuDNN 0.056)
+  //   * Cin >= 512 with plenty of tiles -> version 1 with 256 x 256 tiles (res 64: 0.702 ms = 881 TFLOP/s, cuDNN 0.698)
+  //   * everything else -> version 2, shared filter-column boxes (res 32: 0.193 ms vs cuDNN 0.199; res 128: 0.721 vs 0.739;
+  //     res 256: 0.831 vs 0.781)
+  static const int v2env = []() { const char* e = getenv("GF_CONV_V2"); return e ? atoi(e) : -1; }();
+  const int nsm = num_sms();
+  const long long t2 = H % 16 == 0 ? (long long)B * (H / 16) * (W / 16) * (Cout / (Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64))) : 0;
+  const bool big_v1 = Cout % 256 == 0 && Cin >= 512 && t2 >= 4ll * nsm;
+  const bool use_v2 = v2env >= 0 ? v2env != 0 : (t2 >= nsm && !big_v1);
+  if (use_v2) {
+    const bool m2 = H % 16 == 0;
+    if (Cout % 256 == 0) return (m2 && v2env != 2) ? cv::launch_v2<256, 2, 1>(x, wt, y, B, H, W, Cin, Cout, st) : cv::launch_v2<256, 1, 2>(x, wt, y, B, H, W, Cin, Cout, st);
+    if (Cout % 128 == 0) return m2 ? cv::launch_v2<128, 2, 2>(x, wt, y, B, H, W, Cin, Cout, st) : cv::launch_v2<128, 1, 2>(x, wt, y, B, H, W, Cin, Cout, st);
+    return m2 ? cv::launch_v2<64, 2, 2>(x, wt, y, B, H, W, Cin, Cout, st) : cv::launch_v2<64, 1, 2>(x, wt, y, B, H, W, Cin, Cout, st);
+  }
   static const int force_mt = []() { const char* e = getenv("GF_CONV_MT"); return e ? atoi(e) : 0; }();     // tuning aid, read once
-  const bool mt2 = (H % 16 == 0) && force_mt != 1;
-  // 256 x 256 tiles (all 512 TMEM columns, epilogue not overlapped) pay off when the K loop is long: Cin >= 256
-  // (res 64, Cin = 512: 0.776 -> 0.702 ms = cuDNN's 0.698; res 128, Cin = 256: 0.857 -> 0.836 ms).  GF_CONV_BIG=0 / 1 forces.
+  const bool mt2 = (H % 16 == 0) && force_mt != 1 && t2 >= nsm;
   static const int big_env = []() { const char* e = getenv("GF_CONV_BIG"); return e ? atoi(e) : -1; }();
-  const bool big = big_env >= 0 ? big_env != 0 : Cin >= 256;
+  const bool big = big_env >= 0 ? big_env != 0 : big_v1;
   if (Cout % 256 == 0 && big && H % 16 == 0) return cv::launch<256, 2, 1>(x, wt, y, B, H, W, Cin, Cout, st);
   if (Cout % 256 == 0 && force_mt != 2) return cv::launch<256, 1, 2>(x, wt, y, B, H, W, Cin, Cout, st);
   if (Cout % 128 == 0) return mt2 ? cv::launch<128, 2, 2>(x, wt, y, B, H, W, Cin, Cout, st) : cv::launch<128, 1, 2>(x, wt, y, B, H, W, Cin, Cout, st);
