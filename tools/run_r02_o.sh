@@ -1,0 +1,6 @@
+mkdir -p gpurun_out
+rm -f gpurun_out/parity_log.jsonl
+GF_PARITY_LOG=gpurun_out/parity_log.jsonl timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_o.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_o.log; tail -4 gpurun_out/pytest_gpu_o.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+python bench.py > gpurun_out/bench_o.json 2> gpurun_out/bench_o.err; tail -c 300 gpurun_out/bench_o.err
+ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/step_launches_o.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train-probe --no-duplex-probe --no-fp32-convs > /dev/null 2>&1
