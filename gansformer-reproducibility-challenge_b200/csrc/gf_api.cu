@@ -78,7 +78,10 @@ static int token_pass(const Layout& L, const gf_attn_desc* d, const float* X, fl
   const bool tc = !(d->flags & GF_FLAG_FP32_EXACT) && tc_supported(L, d) && !dropout;     // attention dropout: CUDA-core kernels
   if (post && (post->rgb_out || post->rgb_w)) {
     if (!post->rgb_out || !post->rgb_w || ((uintptr_t)post->rgb_w & 15)) { set_error("postop: fused tRGB needs rgb_w (16-byte aligned) and rgb_out"); return GF_ERR_INVALID; }
-    if (!tc || L.C > 256) { set_error("postop: the fused tRGB is served by the tcgen05 path with C <= 256 only (see gf_attn_tc_eligible)"); return GF_ERR_UNSUPPORTED; }
+    if (!tc || (L.C > 256 && L.KP > 16)) {
+      set_error("postop: the fused tRGB is served by the tcgen05 path with C <= 256, or C = 512 and k <= 16 (see gf_attn_tc_eligible)");
+      return GF_ERR_UNSUPPORTED;
+    }
   }
   if (tc) return token_pass_tc(L, d, X, Xout, att, ws, post, st);
   return token_pass_simt(L, d, X, Xout, att, ws, post, st);

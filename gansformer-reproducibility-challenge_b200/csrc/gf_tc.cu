@@ -81,11 +81,13 @@ struct Cfg {
   static constexpr int OFF_V = OFF_KP + KP_BYTES;
   static constexpr int OFF_STATS = OFF_V + V_BYTES;
   static constexpr int OFF_PBIAS = OFF_STATS + STATS_BYTES;
-  static constexpr int NVEC = NS > 8 ? 2 : 5;             // per-image vectors: in_scale, post_scale (+ tRGB weights r / g / b for C <= 256:
-                                                         // at C = 512 the 12 KB would cost the two-pass ring a stage for a small layer)
+  // fused tRGB: C <= 256, and C = 512 with k <= 16 (its weights + partial sums cost the two-pass ring one of 9 stages there;
+  // with k = 32 the tables already leave the ring 5 stages, so that shape keeps the separate tRGB kernel)
+  static constexpr bool RGB_OK = NS <= 8 || KP <= 16;
+  static constexpr int NVEC = RGB_OK ? 5 : 2;             // per-image vectors: in_scale, post_scale (+ tRGB weights r / g / b)
   static constexpr int SCALE_BYTES = 2 * NVEC * C * 4;   // [image parity][NVEC][C]
   static constexpr int OFF_SCALE = OFF_PBIAS + PBIAS_BYTES;
-  static constexpr int RGBP_BYTES = NS > 8 ? 0 : 2 * 3 * TILE * 4;    // [tile parity][plane][row]: group 1's partial sums
+  static constexpr int RGBP_BYTES = RGB_OK ? 2 * 3 * TILE * 4 : 0;    // [tile parity][plane][row]: group 1's partial sums
   static constexpr int OFF_RGBP = OFF_SCALE + SCALE_BYTES;
   static constexpr int OFF_BARS = OFF_RGBP + RGBP_BYTES;
   static constexpr int OFF_RING = (OFF_BARS + (int)sizeof(Bars) + 1023) / 1024 * 1024;
@@ -109,7 +111,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   float* pbias_s = reinterpret_cast<float*>(smem + CF::OFF_PBIAS);
   const float* scale_s = reinterpret_cast<const float*>(smem + CF::OFF_SCALE);
   const uint32_t s_scale = s_base + CF::OFF_SCALE;
-  const bool has_rgb = NS <= 8 && P.rgb_out != nullptr;
+  const bool has_rgb = CF::RGB_OK && P.rgb_out != nullptr;
   const bool has_scales = P.in_scale != nullptr || P.post_scale != nullptr || has_rgb;      // any per-image vector to stage
   float* rgbp = reinterpret_cast<float*>(smem + CF::OFF_RGBP);
   constexpr int NV = CF::NVEC;
@@ -509,7 +511,7 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         uint8_t* slab = smem + CF::OFF_RING + stage * SLAB_BYTES + row_off;
         const float4* isc = P.in_scale ? reinterpret_cast<const float4*>(scale_s + spar * NV * C + s * SLAB_CH) : nullptr;
         const float4* psc = P.post_scale ? reinterpret_cast<const float4*>(scale_s + (spar * NV + 1) * C + s * SLAB_CH) : nullptr;
-        const float4* wrv = reinterpret_cast<const float4*>(scale_s + (spar * NV + (NS <= 8 ? 2 : 0)) * C + s * SLAB_CH);   // tRGB weights (read when has_rgb)
+        const float4* wrv = reinterpret_cast<const float4*>(scale_s + (spar * NV + (CF::RGB_OK ? 2 : 0)) * C + s * SLAB_CH);   // tRGB weights (read when has_rgb)
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float4* px = reinterpret_cast<float4*>(slab + ((c ^ sw) << 4));

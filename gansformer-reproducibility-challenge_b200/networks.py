@@ -390,11 +390,11 @@ class SynthesisNetwork(nn.Module):
                     post_scale = styles_all[li + 1]
                 rgb_args = None
                 if j == nl - 1 and layer.fusable(x) and not return_features and not os.environ.get("GF_NO_TORGB_EPILOGUE"):
-                    # last layer of the block on the tcgen05 path with C <= 256: the attention kernel's store side computes the
+                    # last layer of the block on the tcgen05 path (C <= 256, or 512 with k <= 16): the attention kernel's store side computes the
                     # tRGB planes from the layer output and writes x * (next block's style): the tRGB pass disappears
                     C_ = layer.weight.shape[0]
                     tg = self.torgbs[bi]
-                    if C_ <= 256 and _inference(tg.weight, tg.bias) and tc_eligible(layer.attention, (B, res, res, C_), k) \
+                    if (C_ <= 256 or (k <= 16 and not os.environ.get("GF_TORGB_EPILOGUE_C256"))) and _inference(tg.weight, tg.bias) and tc_eligible(layer.attention, (B, res, res, C_), k) \
                             and not layer.attention.dropout_postop(x.device):        # (dropout runs on the CUDA-core kernel)
                         st_rgb = styles_all[len(self.layers) + bi]
                         rgb_w = (tg.weight.reshape(1, 3, C_) * st_rgb[:, None, :] * (1.0 / math.sqrt(C_))).contiguous()

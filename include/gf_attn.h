@@ -89,7 +89,8 @@ typedef struct gf_attn_postop {
   /* fused tRGB (the 1x1 modulated convolution, no demodulation, that follows the last layer of a resolution block):
    *   rgb_out[b][o][t] = sum_c x''[b,t,c] * rgb_w[b][o][c] + rgb_bias[o],  o < 3,  x'' = the layer output BEFORE post_scale.
    * rgb_w [B][3][C] contiguous (weight * style * 1/sqrt(C) per sample), 16-byte aligned; rgb_bias [3] or NULL; rgb_out [B][3][H*W]
-   * planar.  All NULL = off.  Served by the tcgen05 path only (gf_attn_tc_eligible); the CUDA-core path returns UNSUPPORTED. */
+   * planar.  All NULL = off.  Served by the tcgen05 path only (gf_attn_tc_eligible) for C <= 256, or C = 512 with k <= 16; other
+   * shapes and the CUDA-core path return UNSUPPORTED. */
   const float* rgb_w;
   const float* rgb_bias;
   float* rgb_out;

@@ -822,7 +822,8 @@ def test_mapping_kernel_matches_definition(gf, cuda_dev, D, k, L, B):
 
 
 @pytest.mark.parametrize("C,H,W,k,duplex,integration", [(128, 16, 16, 16, False, "mul"), (256, 16, 8, 8, False, "both"), (64, 32, 32, 32, True, "mul"),
-                                                          (128, 8, 8, 16, False, "add"), (256, 32, 32, 32, True, "mul")])
+                                                          (128, 8, 8, 16, False, "add"), (256, 32, 32, 32, True, "mul"),
+                                                          (512, 16, 16, 16, False, "mul"), (512, 8, 16, 8, True, "both")])
 def test_fused_torgb_epilogue(gf, cuda_dev, C, H, W, k, duplex, integration):
     """Store-side fusion of the tRGB 1x1 modulated convolution (postop.rgb_*): the three planes are computed from the layer output
     BEFORE the next layer's style scale, which the stored activations carry; both against the float64 oracle."""
@@ -856,6 +857,16 @@ def test_fused_torgb_epilogue(gf, cuda_dev, C, H, W, k, duplex, integration):
     attn32 = make_layer(gf, cuda_dev, C, D, k, p, integration, "layer", duplex, True, True, w)
     with torch.no_grad(), pytest.raises(RuntimeError, match="tRGB"):
         attn32(x64.permute(0, 2, 3, 1).contiguous().float().to(cuda_dev), f(y64), postop=post, need_centroids=False)
+
+
+def test_fused_torgb_refused_for_512_channels_and_32_latents(gf, cuda_dev):
+    """C = 512 with k = 32: the two-pass ring has no room for the tRGB weights -- the call says so (SynthesisNetwork keeps the separate kernel)."""
+    C, k, D = 512, 32, 16
+    attn = make_layer(gf, cuda_dev, C, D, k, 16, "mul", "layer", False, True, False, ob.init_params(C, D, k, 16, "mul", False, seed=1))
+    x = torch.randn(2, 8, 16, C, device=cuda_dev)
+    post = dict(rgb_w=torch.randn(2, 3, C, device=cuda_dev), rgb_bias=torch.zeros(3, device=cuda_dev), rgb_out=torch.empty(2, 3, 8, 16, device=cuda_dev))
+    with torch.no_grad(), pytest.raises(RuntimeError, match="tRGB"):
+        attn(x, torch.randn(2, k, D, device=cuda_dev), postop=post, need_centroids=False)
 
 
 def test_torgb_epilogue_matches_torgb_kernel(gf, cuda_dev, monkeypatch):
