@@ -140,29 +140,39 @@ __global__ void __launch_bounds__(256) blur_up_phases_kernel(const PhasePtrs P, 
   }
 }
 
+// Polyphase form of upfirdn2d(x, [1,3,3,1]/8, up=2, pad=(2,1), gain=4): per dimension out[2i] = 0.25 x[i-1] + 0.75 x[i],
+// out[2i+1] = 0.75 x[i] + 0.25 x[i+1] (zero outside).  One thread per INPUT pixel: its 3x3 neighbourhood gives the 2x2 output quad,
+// stored as two float2 (a warp writes 256 contiguous bytes per output row).
 __global__ void __launch_bounds__(256) upsample2x_nchw_kernel(const float* __restrict__ x, const float* __restrict__ add,
                                                               float* __restrict__ y, int planes, int H, int W) {
-  const int OW = 2 * W, OH = 2 * H;
-  const size_t total = (size_t)planes * OH * OW;
-  const float f[4] = {0.125f, 0.375f, 0.375f, 0.125f};
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int ox = (int)(i % OW), oy = (int)((i / OW) % OH);
-    const size_t pl = i / ((size_t)OW * OH);
+  const long long total = (long long)planes * H * W;
+  const int OW = 2 * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % W);
+    const long long r = i / W;
+    const int h = (int)(r % H);
+    const long long pl = r / H;
     const float* xp = x + pl * H * W;
-    float acc = 0.f;
+    float v[3][3];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int u = oy + a - 2;                   // row in the zero-inserted image
-      if (u < 0 || (u & 1) || (u >> 1) >= H) continue;
+    for (int a = 0; a < 3; ++a)
 #pragma unroll
-      for (int bq = 0; bq < 4; ++bq) {
-        const int v = ox + bq - 2;
-        if (v < 0 || (v & 1) || (v >> 1) >= W) continue;
-        acc = fmaf(f[a] * f[bq], xp[(size_t)(u >> 1) * W + (v >> 1)], acc);
+      for (int b = 0; b < 3; ++b) {
+        const int hh = h + a - 1, jj = j + b - 1;
+        v[a][b] = (hh >= 0 && hh < H && jj >= 0 && jj < W) ? __ldg(xp + (size_t)hh * W + jj) : 0.f;
       }
+    float lo[3], hi[3];                               // vertical pass: output rows 2h and 2h+1, per input column
+#pragma unroll
+    for (int b = 0; b < 3; ++b) { lo[b] = 0.25f * v[0][b] + 0.75f * v[1][b]; hi[b] = 0.75f * v[1][b] + 0.25f * v[2][b]; }
+    float2 o0 = make_float2(0.25f * lo[0] + 0.75f * lo[1], 0.75f * lo[1] + 0.25f * lo[2]);
+    float2 o1 = make_float2(0.25f * hi[0] + 0.75f * hi[1], 0.75f * hi[1] + 0.25f * hi[2]);
+    const size_t o = ((size_t)pl * 2 * H + 2 * h) * OW + 2 * j;
+    if (add) {
+      const float2 a0 = __ldg(reinterpret_cast<const float2*>(add + o)), a1 = __ldg(reinterpret_cast<const float2*>(add + o + OW));
+      o0.x += a0.x; o0.y += a0.y; o1.x += a1.x; o1.y += a1.y;
     }
-    acc *= 4.f;
-    y[i] = add ? acc + add[i] : acc;
+    *reinterpret_cast<float2*>(y + o) = o0;
+    *reinterpret_cast<float2*>(y + o + OW) = o1;
   }
 }
 
@@ -202,6 +212,38 @@ __global__ void __launch_bounds__(256) demod_coef_kernel(const float* __restrict
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
   if (lane == 0) d[warp] = rsqrtf(acc + eps);
+}
+
+// every convolution layer of a network in one launch: blockIdx.y = layer.  One warp per output channel o: its wsq row stays in
+// registers (first 512 input channels; the rest is re-read) while the warp walks the batch, two samples in flight
+// (one warp per (b, o) was latency-bound: 213 k short-lived warps for config 2, 65 us)
+struct DemodBatch { gf_demod_job job[GF_DEMOD_MAX_JOBS]; };
+__global__ void __launch_bounds__(256) demod_coef_batch_kernel(const __grid_constant__ DemodBatch Jb, int B, float eps) {
+  const gf_demod_job& J = Jb.job[blockIdx.y];
+  const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (o >= J.O) return;
+  const float* wo = J.wsq + (size_t)o * J.I;
+  float wr[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) { const int i = lane + 32 * q; wr[q] = i < J.I ? __ldg(wo + i) : 0.f; }
+  for (int b = 0; b < B; b += 2) {
+    const float* s0 = J.styles + (size_t)b * J.s_ld;
+    const bool two = b + 1 < B;
+    const float* s1 = two ? s0 + J.s_ld : s0;
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int i = lane + 32 * q;
+      if (i < J.I) { const float v0 = __ldg(s0 + i), v1 = __ldg(s1 + i); a0 = fmaf(v0 * v0, wr[q], a0); a1 = fmaf(v1 * v1, wr[q], a1); }
+    }
+    for (int i = 512 + lane; i < J.I; i += 32) { const float w = __ldg(wo + i), v0 = s0[i], v1 = s1[i]; a0 = fmaf(v0 * v0, w, a0); a1 = fmaf(v1 * v1, w, a1); }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, off); a1 += __shfl_xor_sync(0xffffffffu, a1, off); }
+    if (lane == 0) {
+      J.d[(size_t)b * J.O + o] = rsqrtf(a0 + eps);
+      if (two) J.d[(size_t)(b + 1) * J.O + o] = rsqrtf(a1 + eps);
+    }
+  }
 }
 
 }  // namespace gf
@@ -415,7 +457,8 @@ int gf_fir4_nhwc(const float* x, float* y, int B, int Hin, int Win, int C, int p
 int gf_upsample2x_nchw(const float* x, const float* add, float* y, int B, int C, int H, int W, void* stream) {
   if (!x || !y) { set_error("gf_upsample2x_nchw: null pointer"); return GF_ERR_INVALID; }
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0) { set_error("gf_upsample2x_nchw: bad shape"); return GF_ERR_INVALID; }
-  const size_t total = (size_t)B * C * 4 * H * W;
+  if (((uintptr_t)y & 7) || (add && ((uintptr_t)add & 7))) { set_error("gf_upsample2x_nchw: y / add must be 8-byte aligned"); return GF_ERR_INVALID; }
+  const size_t total = (size_t)B * C * H * W;                    // one thread per input pixel
   upsample2x_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, add, y, B * C, H, W);
   GF_LAUNCH_OK();
   return GF_OK;
@@ -437,6 +480,22 @@ int gf_demod_coef(const float* styles, int s_ld, const float* wsq, float* d, int
   if (B <= 0 || O <= 0 || I <= 0 || s_ld < I) { set_error("gf_demod_coef: bad shape"); return GF_ERR_INVALID; }
   const long long warps = (long long)B * O;
   demod_coef_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(styles, wsq, d, B, O, I, eps, s_ld);
+  GF_LAUNCH_OK();
+  return GF_OK;
+}
+
+int gf_demod_coef_batch(const gf_demod_job* jobs, int n, int B, float eps, void* stream) {
+  if (!jobs || n <= 0 || n > GF_DEMOD_MAX_JOBS || B <= 0) { set_error("gf_demod_coef_batch: needs 1 <= n <= %d jobs and B > 0 (got n=%d B=%d)", GF_DEMOD_MAX_JOBS, n, B); return GF_ERR_INVALID; }
+  DemodBatch Jb;
+  int max_o = 0;
+  for (int i = 0; i < n; ++i) {
+    const gf_demod_job& J = jobs[i];
+    if (!J.styles || !J.wsq || !J.d || J.O <= 0 || J.I <= 0 || J.s_ld < J.I) { set_error("gf_demod_coef_batch: job %d: null pointer or bad shape", i); return GF_ERR_INVALID; }
+    Jb.job[i] = J;
+    if (J.O > max_o) max_o = J.O;
+  }
+  dim3 grid((unsigned)(((long long)max_o * 32 + 255) / 256), (unsigned)n);
+  demod_coef_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(Jb, B, eps);
   GF_LAUNCH_OK();
   return GF_OK;
 }

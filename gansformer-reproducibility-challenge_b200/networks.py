@@ -221,7 +221,7 @@ class SynthesisLayer(nn.Module):
                 and _inference(self.weight, self.bias, self.noise_strength, *a.parameters()))
 
     def forward(self, x, w_glob, y, noise_mode="const", centroids=None, return_att=False, styles=None,
-                prescaled=False, post_scale=None, prepared=None, rgb=None, centroids_init=None):
+                prescaled=False, post_scale=None, prepared=None, rgb=None, centroids_init=None, demod=None):
         """prescaled: x already carries this layer's style scale.  post_scale [B,C]: the NEXT convolution's style scale,
         folded into this layer's store (only honoured -- and only passed by SynthesisNetwork -- when `fusable`).
         rgb: dict(rgb_w [B,3,C], rgb_bias [3], rgb_out [B,3,H,W]) -- the block's tRGB computed by the attention kernel's store side
@@ -242,11 +242,11 @@ class SynthesisLayer(nn.Module):
             raise RuntimeError("internal: prepared prologue for a layer that does not take the fused path")
         if fused and not self.up:      # demodulation rides on the attention kernel's load side (folded into K')
             x, in_scale = modulated_conv2d(x, self.weight, styles, up=1, f=self.fir, w_eff=w_eff, wsq=wsq,
-                                           prescaled=prescaled, defer_demod=True, d=prepared[1] if prepared is not None else None,
+                                           prescaled=prescaled, defer_demod=True, d=prepared[1] if prepared is not None else demod,
                                            wt_packed=packed)
         else:
             x = modulated_conv2d(x, self.weight, styles, up=2 if self.up else 1, f=self.fir, w_eff=w_eff, wsq=wsq,
-                                 prescaled=prescaled, phases=phases, wt_packed=None if self.up else packed)
+                                 prescaled=prescaled, phases=phases, wt_packed=None if self.up else packed, d=demod)
         if noise_mode == "const":
             noise = self.noise_const
         elif noise_mode == "random":
@@ -352,6 +352,11 @@ class SynthesisNetwork(nn.Module):
         # duplex layer) depends only on the latents and the styles: ONE batched launch for the whole network
         # (gf_attn_prologue_batch) instead of two small launches in front of every layer's token pass.
         prepared = [None] * len(self.layers)
+        demods = [None] * len(self.layers)
+        if x.is_cuda and styles_all[0] is not None and _inference(*[l.weight for l in self.layers]):
+            # every layer's demodulation coefficients depend on the styles only: one launch for the network (gf_demod_coef_batch)
+            demods = ops.demod_coef_batch([(styles_all[li_], _cached(l, "conv", (l.weight,), l._conv_weights)[1])
+                                           for li_, l in enumerate(self.layers)])
         if x.is_cuda and styles_all[0] is not None and not os.environ.get("GF_NO_BATCH_PROLOGUE"):
             items = []
             for li_, layer in enumerate(self.layers):
@@ -359,8 +364,10 @@ class SynthesisNetwork(nn.Module):
                     continue
                 d_ = None
                 if not layer.up:        # the demodulation of a stride-1 convolution rides on the attention kernel's load side
-                    _, wsq_, _, _ = _cached(layer, "conv", (layer.weight,), layer._conv_weights)
-                    d_ = ops.demod_coef(styles_all[li_], wsq_)
+                    d_ = demods[li_]
+                    if d_ is None:
+                        _, wsq_, _, _ = _cached(layer, "conv", (layer.weight,), layer._conv_weights)
+                        d_ = ops.demod_coef(styles_all[li_], wsq_)
                 C_ = layer.weight.shape[0]
                 items.append((layer.attention, y, (B, layer.resolution, layer.resolution, C_), d_))
                 prepared[li_] = (None, d_)
@@ -403,7 +410,7 @@ class SynthesisNetwork(nn.Module):
                         post_scale = nxt
                 x, att, cen_out = layer(x, w_glob, y, noise_mode=noise_mode, return_att=return_att, styles=styles_all[li],
                                         prescaled=prescaled, post_scale=post_scale, prepared=prepared[li], rgb=rgb_args,
-                                        centroids_init=cen_init)
+                                        centroids_init=cen_init, demod=demods[li])
                 if layer.attention is not None:
                     cen_prev = cen_out if self.iterative else None
                 prescaled = post_scale is not None

@@ -241,6 +241,37 @@ def demod_coef(styles: torch.Tensor, wsq: torch.Tensor, eps: float = 1e-8) -> to
     return torch.rsqrt(styles.square() @ wsq.t() + eps)
 
 
+def demod_coef_batch(pairs, eps: float = 1e-8):
+    """[(styles [B,I_l], wsq [O_l,I_l]), ...] -> [d_l [B,O_l], ...]: every layer's demodulation coefficients in one launch
+    (gf_demod_coef_batch).  CUDA fp32 only; the per-layer call serves everything else."""
+    if not pairs:
+        return []
+    if len(pairs) > _lib.DEMOD_MAX_JOBS or not all(_use_cuda(s_, w_) for s_, w_ in pairs):
+        return [demod_coef(s_, w_, eps) for s_, w_ in pairs]
+    dev = pairs[0][0].device
+    B = pairs[0][0].shape[0]
+    total = sum(w_.shape[0] for _, w_ in pairs)
+    d_all = torch.empty((B * total,), dtype=torch.float32, device=dev)       # one allocation, one [B, O_l] block per layer
+    jobs = (_lib.GfDemodJob * len(pairs))()
+    outs, keep, off = [], [], 0
+    for i, (s_, w_) in enumerate(pairs):
+        if s_.shape[0] != B or s_.shape[1] != w_.shape[1]:
+            raise ValueError("demod_coef_batch: styles [B, I] / wsq [O, I] mismatch")
+        sr, ld = _rows(s_)
+        wc = w_.contiguous()
+        O, I = wc.shape
+        d = d_all[off:off + B * O].view(B, O)
+        off += B * O
+        jobs[i].styles, jobs[i].wsq, jobs[i].d = sr.data_ptr(), wc.data_ptr(), d.data_ptr()
+        jobs[i].s_ld, jobs[i].O, jobs[i].I = ld, O, I
+        outs.append(d)
+        keep += [sr, wc]
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().gf_demod_coef_batch(ctypes.cast(jobs, ctypes.c_void_p), len(pairs), B, float(eps), _stream(dev)),
+                   "gf_demod_coef_batch")
+    return outs
+
+
 def torgb(x: torch.Tensor, weight: torch.Tensor, styles: torch.Tensor, bias: Optional[torch.Tensor],
           next_styles: Optional[torch.Tensor] = None):
     """tRGB: 1x1 modulated convolution without demodulation.  x [B,C,H,W], weight [3,C,1,1] (raw; equalised-LR scale

@@ -54,6 +54,17 @@ int gf_bias_act_nhwc(const float* x, float* y, const float* bias, const float* n
  *   d[b,o] = rsqrt( sum_i styles[b*s_ld + i]^2 * wsq[o,i] + eps ),  wsq[o,i] = sum_{kh,kw} w_eff[o,i,kh,kw]^2 */
 int gf_demod_coef(const float* styles, int s_ld, const float* wsq, float* d, int B, int O, int I, float eps, void* stream);
 
+/* The same for every convolution layer of a network in ONE launch (the layers' style vectors all come from one latent, so their
+ * demodulation coefficients can be computed up front): n <= GF_DEMOD_MAX_JOBS jobs, common batch B. */
+#define GF_DEMOD_MAX_JOBS 32
+typedef struct gf_demod_job {
+  const float* styles;   /* [B][s_ld], I used */
+  const float* wsq;      /* [O][I] */
+  float* d;              /* [B][O] out */
+  int32_t s_ld, O, I, pad_;
+} gf_demod_job;
+int gf_demod_coef_batch(const gf_demod_job* jobs, int n, int B, float eps, void* stream);
+
 /* tRGB: 1x1 modulated convolution WITHOUT demodulation from channels-last activations to a planar image,
  *   y[b,o,t] = sum_c x[b,t,c] * w[o*C + c] * styles[b*s_ld + c] * wscale + bias[o],   o < 3
  * (modulated_conv2d_layer(..., demodulate=False, kernel=1) + bias of the reference's torgb); x is read once.

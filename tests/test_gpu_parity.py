@@ -625,6 +625,12 @@ def test_native_ops_match_definitions(gf, cuda_dev):
             dd = ops.demod_coef(wide[:, 4:4 + C], wsq)
             want_d = torch.rsqrt(wide[:, 4:4 + C].double().square() @ wsq.double().t() + 1e-8)
             assert (dd.double() - want_d).abs().max() <= 1e-5 * want_d.abs().max()
+            # every layer of a network in one launch: bit-identical to the per-layer call (same summation order)
+            wsq2 = torch.rand(20, C, generator=g).to(cuda_dev)
+            wsq3 = torch.rand(7, C + 8, generator=g).to(cuda_dev)
+            batch = ops.demod_coef_batch([(wide[:, 4:4 + C], wsq), (s, wsq2), (wide, wsq3)])
+            for got_d, (s_, w_) in zip(batch, [(wide[:, 4:4 + C], wsq), (s, wsq2), (wide, wsq3)]):
+                assert torch.equal(got_d, ops.demod_coef(s_, w_))
             bias = torch.randn(C, generator=g).to(cuda_dev)
             nz = torch.randn(H, W, generator=g).to(cuda_dev)
             st = torch.tensor(0.3, device=cuda_dev)
