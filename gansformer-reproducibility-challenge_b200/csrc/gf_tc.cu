@@ -606,7 +606,10 @@ static int stages_for(int smem_limit) {
   return st > MAX_STAGES ? MAX_STAGES : st;
 }
 // single-pass needs the whole tile resident; two-pass only streams (a few slabs of slack keep the pipes busy)
-template <int NS> constexpr bool two_pass_shape() { return NS > 8; }
+#ifndef GF_TWO_PASS_MIN_NS
+#define GF_TWO_PASS_MIN_NS 16
+#endif
+template <int NS> constexpr bool two_pass_shape() { return NS >= GF_TWO_PASS_MIN_NS; }
 template <int NS> constexpr int min_stages() { return two_pass_shape<NS>() ? 4 : NS; }
 
 template <int KP, int NS, int MODE>
