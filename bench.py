@@ -302,7 +302,7 @@ def train_probe(device, rank, world, steps: int = 3, warmup: int = 1, B: int = 3
            "peak_mem_gb": torch.cuda.max_memory_allocated(device) / 2 ** 30,
            "cuda_graph": bool(graphed),
            "attention_dropout": 0.12,
-           "backward": "attention: CUDA forward (CUDA-core kernel: Philox attention dropout p = 0.12) + hand-written stage-T backward kernel "
+           "backward": "attention: CUDA forward (tcgen05 kernel with Philox attention dropout p = 0.12 on the probabilities) + hand-written stage-T backward kernel "
                        "(gf_attn_simplex_bwd_ex, same mask) + batched GEMMs for the token reductions; FIR filters: native (self-adjoint) "
                        "kernel; convolutions / discriminator: cuDNN; gradients: bucketed NCCL all-reduce overlapped with backward"}
     del trainer, G, D

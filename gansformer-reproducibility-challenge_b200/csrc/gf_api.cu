@@ -74,8 +74,7 @@ static int token_pass(const Layout& L, const gf_attn_desc* d, const float* X, fl
     }
   }
   if ((rc = norm_stats(L, d, X, ws, st))) return rc;
-  const bool dropout = post && post->att_dp != 0.f && post->dp_state;
-  const bool tc = !(d->flags & GF_FLAG_FP32_EXACT) && tc_supported(L, d) && !dropout;     // attention dropout: CUDA-core kernels
+  const bool tc = !(d->flags & GF_FLAG_FP32_EXACT) && tc_supported(L, d);
   if (post && (post->rgb_out || post->rgb_w)) {
     if (!post->rgb_out || !post->rgb_w || ((uintptr_t)post->rgb_w & 15)) { set_error("postop: fused tRGB needs rgb_w (16-byte aligned) and rgb_out"); return GF_ERR_INVALID; }
     if (!tc || (L.C > 256 && L.KP > 16)) {

@@ -51,6 +51,9 @@ struct Params {
   // fused tRGB (1x1 modulated conv of the layer output to 3 planes): rgb_w [B][3][C] per-sample weights, rgb_out [B][3][n]
   const float* rgb_w; const float* rgb_bias; float* rgb_out;
   int heads, seg_shift;      // multi-head: the softmax runs per segment of (1 << seg_shift) table columns (heads * seg == KP)
+  // attention dropout (training): the row warps drop / rescale the probabilities with the Philox mask the CUDA-core kernels and the
+  // backward draw, and pass 1 - sum(q) to the store side, which re-adds the un-droppable constants cb [Cout] (bo, the 1 of 1 + gain)
+  DropoutArgs dp; const float* cb;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -75,7 +78,7 @@ struct Cfg {
   static constexpr int KP_BYTES = KP * C * 4;            // K' : NS chunks of [KP rows x 128 B]
   static constexpr int V_ROW_BYTES = KP * 4;             // V^T row (one channel): KP latents
   static constexpr int V_BYTES = COUT * V_ROW_BYTES;
-  static constexpr int STATS_BYTES = 2 * TILE * 2 * 4;   // [tile parity][row]{mean, rstd}
+  static constexpr int STATS_BYTES = 2 * TILE * 4 * 4;   // [tile parity][row]{mean, rstd, 1 - sum q (dropout), -}
   static constexpr int PBIAS_BYTES = C * 4;              // post-op bias vector
   static constexpr int OFF_KP = 0;
   static constexpr int OFF_V = OFF_KP + KP_BYTES;
@@ -364,11 +367,13 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
         for (int j4 = 0; j4 < KP / 4; ++j4) pc[j4] = __ldg(ct_nxt + j4);
       }
-      mbar_wait(smem_u32(&bars->st_free[buf]), bphase ^ 1u);       // epilogue of the tile two iterations back has read its stats
-      stats[(buf * TILE + row) * 2 + 0] = mean;
-      stats[(buf * TILE + row) * 2 + 1] = rstd;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars->st_full[buf]));
+      const bool dp_on = P.dp.thr != 0;                            // (kernel parameter: uniform)
+      if (!dp_on) {                                                // with dropout the hand-off waits for 1 - sum q, below
+        mbar_wait(smem_u32(&bars->st_free[buf]), bphase ^ 1u);     // epilogue of the tile two iterations back has read its stats
+        *reinterpret_cast<float2*>(stats + (buf * TILE + row) * 4) = make_float2(mean, rstd);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->st_full[buf]));
+      }
       // ---- softmax over the latents: S (TMEM) -> P (TMEM)
       mbar_wait(smem_u32(&bars->s_full[buf]), bphase);
       tc_fence_after();
@@ -424,6 +429,23 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             a[j] = m * ih;
           }
         }
+      }
+      if (dp_on) {
+        // attention dropout on the probabilities (the map above is pre-dropout): same Philox stream as token_simt_kernel / the backward
+        const unsigned long long seed = P.dp.state[0], step = P.dp.state[1];
+        const uint32_t gtok = (uint32_t)((size_t)(img_last ? b - 1 : b) * P.n + tok);
+        float qs = 0.f;
+#pragma unroll
+        for (int q4 = 0; q4 < KP / 4; ++q4) {
+          float mk[4];
+          dropout_mult4(P.dp, seed, step, gtok, q4, mk);
+          sv[q4 * 4] *= mk[0]; sv[q4 * 4 + 1] *= mk[1]; sv[q4 * 4 + 2] *= mk[2]; sv[q4 * 4 + 3] *= mk[3];
+          qs += (sv[q4 * 4] + sv[q4 * 4 + 1]) + (sv[q4 * 4 + 2] + sv[q4 * 4 + 3]);
+        }
+        mbar_wait(smem_u32(&bars->st_free[buf]), bphase ^ 1u);
+        *reinterpret_cast<float4*>(stats + (buf * TILE + row) * 4) = make_float4(mean, rstd, 1.f - qs, 0.f);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->st_full[buf]));
       }
       // round P to the nearest TF32 so the tensor core's operand truncation is exact (see gf_fold.cu: round_tf32)
 #pragma unroll
@@ -482,7 +504,8 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       if (has_scales && img_first) mbar_wait(smem_u32(&bars->sc_full[spar]), (uint32_t)((imgc >> 1) & 1));
       // ---- row statistics from the row warps
       mbar_wait(smem_u32(&bars->st_full[buf]), bphase);
-      const float mean = stats[(buf * TILE + row) * 2 + 0], rstd = stats[(buf * TILE + row) * 2 + 1];
+      const float4 st4 = *reinterpret_cast<const float4*>(stats + (buf * TILE + row) * 4);
+      const float mean = st4.x, rstd = st4.y, qdef = st4.z;        // qdef: only written (and read) with dropout on
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bars->st_free[buf]));
       const float mr = -mean * rstd;
@@ -508,6 +531,24 @@ token_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[a]));
+        if (P.dp.thr) {                                // dropout broke sum q = 1: re-add the constants the fold put into V^T
+          const float4* cbg = reinterpret_cast<const float4*>(P.cb + s * SLAB_CH);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = __ldg(cbg + c);
+            gv[c * 4] = fmaf(qdef, v.x, gv[c * 4]); gv[c * 4 + 1] = fmaf(qdef, v.y, gv[c * 4 + 1]);
+            gv[c * 4 + 2] = fmaf(qdef, v.z, gv[c * 4 + 2]); gv[c * 4 + 3] = fmaf(qdef, v.w, gv[c * 4 + 3]);
+          }
+          if constexpr (MODE == GF_INT_BOTH) {
+            const float4* cbb = reinterpret_cast<const float4*>(P.cb + C + s * SLAB_CH);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 v = __ldg(cbb + c);
+              bv[c * 4] = fmaf(qdef, v.x, bv[c * 4]); bv[c * 4 + 1] = fmaf(qdef, v.y, bv[c * 4 + 1]);
+              bv[c * 4 + 2] = fmaf(qdef, v.z, bv[c * 4 + 2]); bv[c * 4 + 3] = fmaf(qdef, v.w, bv[c * 4 + 3]);
+            }
+          }
+        }
         uint8_t* slab = smem + CF::OFF_RING + stage * SLAB_BYTES + row_off;
         const float4* isc = P.in_scale ? reinterpret_cast<const float4*>(scale_s + spar * NV * C + s * SLAB_CH) : nullptr;
         const float4* psc = P.post_scale ? reinterpret_cast<const float4*>(scale_s + (spar * NV + 1) * C + s * SLAB_CH) : nullptr;
@@ -647,6 +688,8 @@ static int launch(const Layout& L, const gf_attn_desc* d, const float* X, float*
   P.in_ld = post ? post->in_scale_ld : 0; P.post_ld = post ? post->post_scale_ld : 0;
   P.rgb_w = post ? post->rgb_w : nullptr; P.rgb_bias = post ? post->rgb_bias : nullptr; P.rgb_out = post ? post->rgb_out : nullptr;
   P.heads = L.heads; P.seg_shift = L.seg == 8 ? 3 : (L.seg == 16 ? 4 : 5);
+  if ((rc = dropout_args(post, &P.dp))) return rc;
+  P.cb = ws + L.w_CB;
   const int smem_bytes = CF::FIXED_BYTES + nst * SLAB_BYTES + 1024;
   auto kern = token_tc_kernel<KP, NS, MODE, TWO>;
   GF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));

@@ -401,8 +401,8 @@ class SynthesisNetwork(nn.Module):
                     # tRGB planes from the layer output and writes x * (next block's style): the tRGB pass disappears
                     C_ = layer.weight.shape[0]
                     tg = self.torgbs[bi]
-                    if (C_ <= 256 or (k <= 16 and not os.environ.get("GF_TORGB_EPILOGUE_C256"))) and _inference(tg.weight, tg.bias) and tc_eligible(layer.attention, (B, res, res, C_), k) \
-                            and not layer.attention.dropout_postop(x.device):        # (dropout runs on the CUDA-core kernel)
+                    if (C_ <= 256 or (k <= 16 and not os.environ.get("GF_TORGB_EPILOGUE_C256"))) and _inference(tg.weight, tg.bias) \
+                            and tc_eligible(layer.attention, (B, res, res, C_), k):
                         st_rgb = styles_all[len(self.layers) + bi]
                         rgb_w = (tg.weight.reshape(1, 3, C_) * st_rgb[:, None, :] * (1.0 / math.sqrt(C_))).contiguous()
                         rgb = torch.empty((B, 3, res, res), device=x.device, dtype=torch.float32)

@@ -97,8 +97,9 @@ typedef struct gf_attn_postop {
   /* attention dropout (att_dp of transformer_layer; training only): every probability of the k-softmax is dropped with probability
    * att_dp and the survivors are scaled by 1 / (1 - att_dp).  The mask is Philox4x32-10 of (token, column block, dp_salt, step) keyed
    * by the seed; dp_state points to DEVICE memory {uint64 seed, uint64 step} read when the kernel runs (bump `step` on the device
-   * between training steps: a replayed CUDA graph then draws fresh masks).  Served by the CUDA-core kernels (the call takes the
-   * fp32 path); the attention map output is the probabilities BEFORE dropout.  att_dp = 0 or dp_state = NULL: off. */
+   * between training steps: a replayed CUDA graph then draws fresh masks).  Both kernel families serve it with the same mask (the
+   * tcgen05 kernel drops the probabilities before they become GEMM2's operand); the attention map output is the probabilities
+   * BEFORE dropout.  att_dp = 0 or dp_state = NULL: off. */
   float att_dp;
   uint32_t dp_salt;
   const unsigned long long* dp_state;

@@ -1096,6 +1096,62 @@ def test_attention_dropout_forward_and_backward(gf, cuda_dev, C, H, W, k, integr
     check_close(out4, ref0.permute(0, 2, 3, 1), "simt_fp32", "dropout/eval")
 
 
+@pytest.mark.parametrize("C,H,W,k,integration,norm", [(128, 16, 16, 16, "mul", "layer"), (256, 16, 24, 20, "both", "layer"),
+                                                      (512, 8, 16, 8, "add", "none"), (64, 8, 8, 4, "mul", "layer")])
+def test_attention_dropout_on_the_tensor_path(gf, cuda_dev, C, H, W, k, integration, norm):
+    """att_dp on the tcgen05 kernel (training forward of the default path): against the oracle given the SAME Philox mask, with the
+    fused post-op around it; and the gradients through that forward (stage-T backward kernel, same mask) against the oracle's."""
+    from importlib import import_module
+    from oracle import philox as ph
+    am = import_module("gansformer-reproducibility-challenge_b200.attention")
+    D = p = 16
+    B, pd = 3, 0.2
+    g = torch.Generator().manual_seed(C + k)
+    x64 = torch.randn(B, C, H, W, generator=g, dtype=torch.float64).requires_grad_(True)
+    y64 = torch.randn(B, k, D, generator=g, dtype=torch.float64).requires_grad_(True)
+    w = {n: t.requires_grad_(True) for n, t in ob.init_params(C, D, k, p, integration, False, seed=4, bias_std=0.3).items()}
+    nrm = None if norm == "none" else norm
+    attn = gf.BipartiteAttention(C, D, k, pos_dim=p, integration=integration, norm=nrm, att_dp=pd).to(cuda_dev)
+    with torch.no_grad():
+        for n, prm in attn.named_parameters():
+            prm.copy_(w[n].detach().float())
+    seed, step = 123456789, 11
+    am.set_dropout_seed(seed, cuda_dev, step)
+    KP = 16 if k <= 16 else 32
+    mult = torch.from_numpy(ph.dropout_mult(pd, seed, step, attn.dp_salt, B * H * W, KP).reshape(B, H * W, KP)[:, :, :k].copy())
+    ref, ratt, _ = ob.transformer_layer(x64, y64, w, integration=integration, norm=nrm, return_att=True, att_mult=mult)
+    xg = x64.detach().permute(0, 2, 3, 1).contiguous().float().to(cuda_dev)
+    yg = y64.detach().float().to(cuda_dev)
+    attn.train()
+    with torch.no_grad():
+        out, att, _ = attn(xg, yg, return_att=True)
+    assert gf._lib.last_path() == "tcgen05_tf32"
+    check_close(out, ref.detach().permute(0, 2, 3, 1), "tcgen05_tf32", "dropout-tc/forward", tol_scale=2.0)
+    assert (att.cpu().double() - ratt.detach()).abs().max() <= 2e-3           # pre-dropout probabilities, TF32 logits
+    gout = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+    ref.backward(gout)
+    xr, yr = xg.clone().requires_grad_(True), yg.clone().requires_grad_(True)
+    out2, _, _ = attn(xr, yr)
+    assert torch.equal(out2.detach(), out)
+    out2.backward(gout.permute(0, 2, 3, 1).contiguous().float().to(cuda_dev))
+    rel = lambda a, b: ((a.double().cpu() - b).norm() / b.norm().clamp_min(1e-30)).item()
+    assert rel(xr.grad, x64.grad.permute(0, 2, 3, 1)) < 2e-3 and rel(yr.grad, y64.grad) < 2e-3     # fp32 backward of a TF32 forward
+    for n in ("wq", "wv", "wo", "wk"):
+        assert rel(getattr(attn, n).grad, w[n].grad) < 2e-3, n
+    # fused post-op + dropout, as the D step's fake images run (training-mode forward under no_grad)
+    bias = torch.randn(C, generator=g, dtype=torch.float64) * 0.5
+    d_in = torch.rand(B, C, generator=g, dtype=torch.float64) + 0.5
+    refp, _, _ = ob.transformer_layer(x64.detach() * d_in[:, :, None, None], y64.detach(), {n: t.detach() for n, t in w.items()},
+                                      integration=integration, norm=nrm, att_mult=mult)
+    refp = torch.nn.functional.leaky_relu(refp + bias[None, :, None, None], 0.2) * math.sqrt(2.0)
+    post = dict(bias=bias.float().to(cuda_dev), act="lrelu", gain=math.sqrt(2.0), in_scale=d_in.float().to(cuda_dev))
+    post.update(attn.dropout_postop(cuda_dev))
+    with torch.no_grad():
+        outp, _, _ = attn(xg, yg, postop=post, need_centroids=False)
+    assert gf._lib.last_path() == "tcgen05_tf32"
+    check_close(outp, refp.permute(0, 2, 3, 1), "tcgen05_tf32", "dropout-tc/postop", tol_scale=2.0)
+
+
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 64, 64), (3, 32, 16, 128, 128), (1, 8, 32, 256, 256), (2, 24, 48, 96, 192), (1, 64, 64, 32, 512)])
 def test_conv3x3_implicit_gemm(gf, cuda_dev, B, H, W, Cin, Cout):
     """Row f1: the tcgen05 implicit-GEMM 3x3 convolution (TF32, zero padding by TMA out-of-bounds fill) against the oracle's
