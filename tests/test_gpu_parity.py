@@ -1096,7 +1096,7 @@ def test_attention_dropout_forward_and_backward(gf, cuda_dev, C, H, W, k, integr
     check_close(out4, ref0.permute(0, 2, 3, 1), "simt_fp32", "dropout/eval")
 
 
-@pytest.mark.parametrize("C,H,W,k,integration,norm", [(128, 16, 16, 16, "mul", "layer"), (256, 16, 24, 20, "both", "layer"),
+@pytest.mark.parametrize("C,H,W,k,integration,norm", [(128, 16, 16, 16, "mul", "layer"), (256, 16, 24, 20, "mul", "layer"), (128, 8, 16, 8, "both", "layer"),
                                                       (512, 8, 16, 8, "add", "none"), (64, 8, 8, 4, "mul", "layer")])
 def test_attention_dropout_on_the_tensor_path(gf, cuda_dev, C, H, W, k, integration, norm):
     """att_dp on the tcgen05 kernel (training forward of the default path): against the oracle given the SAME Philox mask, with the
