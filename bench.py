@@ -16,6 +16,7 @@ globally seeded batch, no data-path collective -- SURVEY 8e).  Rank 0 prints ONE
                    write X' once per layer) / CUDA-event time, vs MEASURED_PEAKS.json hbm_gbs; stage_T = the
                    dominant kernel alone; traffic = DRAM bytes of the largest stage-T launch parsed from the tracked
                    profiles/r02/traffic_config<N>.csv (tools/traffic_capture.sh, ncu on the current build)
+  roofline_conv    row f1: the library's own 3x3 convolution kernel against the tensor roofline (TFLOP/s, measured bf16 peak / 2)
   roofline_duplex  BASELINE's second named metric: the 12 duplex layer calls of configs[2] (K=32, batch 64), same formula
   train_step       BASELINE configs[3]: G+D training step, data-parallel with the NCCL gradient all-reduce, at every N
   cpu_baseline     the CPU oracle (oracle/generator.py, fp32, pinned thread count, median of 3) on a bounded sample, N = 1 only
@@ -68,6 +69,46 @@ def measured_peak_gbs():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def conv_roofline_probe(device, iters: int = 5):
+    """Row f1 kernel against the tensor roofline: the five stride-1 3x3 convolutions of the 256x256 generator (batch 32) on the library's
+    own tcgen05 implicit-GEMM kernel, each layer timed on its own with CUDA events after warm-up (inputs 67 MB ... 1.07 GB, alternating
+    between two buffers).  FLOPs = 2 * 9 * B * H * W * Cin * Cout.  Peak = measured cuBLAS bf16 throughput / 2 (kind::tf32 runs at half
+    the bf16 rate)."""
+    from importlib import import_module
+    ops = import_module("gansformer-reproducibility-challenge_b200.ops")
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            pk = json.load(f)
+        peak, src = float(pk["bf16_tflops"]) / 2, "measured cuBLAS bf16 burst (MEASURED_PEAKS.json) / 2"
+    except Exception:
+        peak, src = 1125.0, "nominal dense TF32 (2250 bf16 / 2)"
+    B = 32
+    layers, tot_flop, tot_ms = [], 0.0, 0.0
+    for res, C in [(16, 512), (32, 512), (64, 512), (128, 256), (256, 128)]:
+        xs = [torch.randn(B, C, res, res, device=device).contiguous(memory_format=torch.channels_last) for _ in range(2)]
+        wt = ops.conv3x3_pack(torch.randn(C, C, 3, 3, device=device) / (3.0 * C ** 0.5))
+        for i in range(3):
+            ops.conv3x3_native(xs[i & 1], wt)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            ops.conv3x3_native(xs[i & 1], wt)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        fl = 2.0 * 9 * B * res * res * C * C
+        layers.append({"res": res, "channels": C, "ms": ms, "tflops": fl / ms / 1e9})
+        tot_flop += fl
+        tot_ms += ms
+        del xs, wt
+    torch.cuda.empty_cache()
+    ach = tot_flop / tot_ms / 1e9
+    return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": src,
+            "kernel": "conv3x3_tc_kernel / conv3x3_tc_kernel_v2 (gf_conv3x3_nhwc_tf32): the five stride-1 3x3 convolutions of the step, "
+                      "timed layer by layer outside the step", "ms_total": tot_ms, "layers": layers}
 
 
 class ClockSampler:
@@ -588,6 +629,11 @@ def run_ours(args):
         if "frac" in da:      # BASELINE's second named metric ("duplex-attn %HBM-peak") in roofline form
             state["line"]["roofline_duplex"] = {"bound": "hbm", "achieved": da["achieved"], "peak": peak, "unit": "GB/s", "frac": da["frac"],
                                                 "traffic": None, "kernel": "12 duplex layer calls of configs[2] (stage I + pass A + key products + stage T)"}
+    if world == 1 and not args.no_duplex_probe and args.config == 2:
+        try:
+            state["line"]["roofline_conv"] = conv_roofline_probe(device)
+        except Exception as exc:
+            state["line"]["roofline_conv"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     if world == 1 and not args.no_cpu_baseline:
         ips, t, cores = cpu_oracle_run(G.state_dict(), steps=3, warmup=1, sample_b=B_PER_GPU if args.config == 1 else (1 if RES >= 512 else 2))
         state["line"]["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",

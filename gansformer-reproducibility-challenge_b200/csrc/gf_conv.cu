@@ -15,9 +15,11 @@
 //            one of two TMEM accumulators (the epilogue of tile i overlaps the MMAs of tile i+1)
 //   warps 2-5 epilogue: TMEM -> registers -> swizzled staging slab (128 pixels x 32 ch) -> TMA 4-D store, two slabs in flight
 // Persistent grid (one CTA per SM), tiles handed out round-robin with the N tile innermost.
-// Every tap's A box is fetched separately (9x from L2 per input byte), so the kernel is bound by the L2 -> shared-memory path, not by
-// the tensor pipe: tile shapes are chosen for flops per loaded byte (see the dispatch at the bottom).  Measured against cuDNN's TF32
-// kernels on the generator's shapes (batch 32): 100 % at res 16 / 32 / 64, 88 % at res 128, 86 % at res 256.
+// Two kernels: version 1 below fetches every tap's A box separately (9 reads of each input byte from L2) and is bound by the
+// L2 -> shared-memory path; version 2 further down shares one activation box per filter column among its three taps (3.4 reads) and
+// is bound by the tensor pipe (ncu: 84-89 % active).  The dispatch at the bottom picks per shape from measurements: version 2 wherever
+// the grid fills the GPU, version 1 for small grids (res 16) and, with 256 x 256 tiles, for Cin >= 512 (res 64).  Against cuDNN's
+// TF32 kernels on the generator's five stride-1 layers (batch 32): 2.50-2.63 ms vs 2.48-2.50 ms in total.
 #include <stdlib.h>
 #include <string.h>
 #include "gf_common.cuh"
