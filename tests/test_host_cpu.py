@@ -35,6 +35,22 @@ def test_struct_layouts_match_c(gf):
     assert ctypes.sizeof(gf._lib.GfAttnDesc) == 12 * 4
     assert ctypes.sizeof(gf._lib.GfAttnWeights) == 23 * ctypes.sizeof(ctypes.c_void_p)
     assert ctypes.sizeof(gf._lib.GfAttnPostop) == 3 * 8 + 8 + 4 + 4 + 2 * 8 + 2 * 4 + 3 * 8 + 4 + 4 + 8
+    assert ctypes.sizeof(gf._lib.GfDemodJob) == 3 * 8 + 4 * 4                      # gf_demod_job of include/gf_ops.h
+    assert gf._lib.GfDemodJob.O.offset == 28 and gf._lib.GfDemodJob.I.offset == 32
+    header = open(os.path.join(ROOT, "include", "gf_ops.h")).read()
+    assert f"#define GF_DEMOD_MAX_JOBS {gf._lib.DEMOD_MAX_JOBS}" in header
+
+
+def test_batched_demodulation_falls_back_per_layer_on_cpu():
+    """ops.demod_coef_batch without CUDA tensors = the per-layer definition (the batched launch is a CUDA-only fast path)."""
+    from importlib import import_module
+    ops = import_module("gansformer-reproducibility-challenge_b200.ops")
+    g = torch.Generator().manual_seed(3)
+    pairs = [(torch.rand(3, 20, generator=g) + 0.5, torch.rand(7, 20, generator=g)), (torch.rand(3, 12, generator=g), torch.rand(5, 12, generator=g))]
+    got = ops.demod_coef_batch(pairs)
+    for d, (s_, w_) in zip(got, pairs):
+        assert torch.allclose(d, torch.rsqrt(s_.square() @ w_.t() + 1e-8))
+    assert ops.demod_coef_batch([]) == []
 
 
 def test_sizes_and_validation(gf):
