@@ -41,6 +41,16 @@ def test_struct_layouts_match_c(gf):
     assert f"#define GF_DEMOD_MAX_JOBS {gf._lib.DEMOD_MAX_JOBS}" in header
 
 
+def test_integration_stub_matches_the_abi(gf):
+    """The ctypes stub shown in INTEGRATION.md declares the same descriptor / weight members as the binding the tests run through."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"class gf_attn_weights\(C\.Structure\):.*?\((\"wq\".*?)\)\]", doc, re.S)
+    assert m, "weights stub not found"
+    assert tuple(re.findall(r'"(\w+)"', m.group(1))) == tuple(gf._lib.WEIGHT_FIELDS)
+    m = re.search(r"class gf_attn_desc\(C\.Structure\):.*?\((\"B\".*?)\)\]", doc, re.S)
+    assert m and tuple(re.findall(r'"(\w+)"', m.group(1))) == tuple(n for n, _ in gf._lib.GfAttnDesc._fields_)
+
+
 def test_batched_demodulation_falls_back_per_layer_on_cpu():
     """ops.demod_coef_batch without CUDA tensors = the per-layer definition (the batched launch is a CUDA-only fast path)."""
     from importlib import import_module
