@@ -41,6 +41,21 @@ def test_struct_layouts_match_c(gf):
     assert f"#define GF_DEMOD_MAX_JOBS {gf._lib.DEMOD_MAX_JOBS}" in header
 
 
+def test_native_op_entry_points_validate_before_touching_the_device(gf):
+    """gf_ops.h entry points added in round 2: argument errors come back as gf_status + message (no GPU needed to see them)."""
+    lib = gf._lib.load()
+    err = lambda: lib.gf_last_error().decode()
+    assert lib.gf_conv3x3_nhwc_tf32(1, 1, 1, 2, 7, 16, 32, 64, None) == -2 and "H % 8 == 0" in err()       # GF_ERR_UNSUPPORTED
+    assert lib.gf_conv3x3_nhwc_tf32(1, 1, 1, 2, 8, 16, 48, 64, None) == -2 and "Cin % 32" in err()
+    assert lib.gf_conv3x3_nhwc_tf32(None, 1, 1, 2, 8, 16, 32, 64, None) == -1 and "null pointer" in err()    # GF_ERR_INVALID
+    assert lib.gf_conv3x3_pack_weights(None, None, 4, 4, 1.0, None) == -1
+    jobs = (gf._lib.GfDemodJob * 1)()
+    as_ptr = ctypes.cast(jobs, ctypes.c_void_p)
+    assert lib.gf_demod_coef_batch(None, 0, 4, 1e-8, None) == -1 and "1 <= n <= 32" in err()
+    assert lib.gf_demod_coef_batch(as_ptr, gf._lib.DEMOD_MAX_JOBS + 1, 4, 1e-8, None) == -1
+    assert lib.gf_demod_coef_batch(as_ptr, 1, 4, 1e-8, None) == -1 and "job 0" in err()
+
+
 def test_integration_stub_matches_the_abi(gf):
     """The ctypes stub shown in INTEGRATION.md declares the same descriptor / weight members as the binding the tests run through."""
     doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
