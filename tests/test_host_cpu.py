@@ -391,6 +391,25 @@ def test_upconv_polyphase_decomposition_cpu(gf):
     assert torch.equal(xs, x * s2[:, :, None, None]) and torch.equal(rgb, ops.torgb(x, wr, st, None))
 
 
+def test_bench_configs_follow_baseline_json():
+    """bench.py's --config table carries the resolution / K / batch figures BASELINE.json names (configs[3] is the train probe)."""
+    import importlib.util, json
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))["configs"]
+    for n, c in bench.CONFIGS.items():
+        txt = base[n - 1].replace("\u00d7", "x")
+        assert f"{c['res']}x{c['res']}" in txt and f"K={c['k']}" in txt, (n, txt)
+        per_gpu = c["batch"] * (8 if n == 5 else 1)                     # configs[4] names the 8-GPU global batch
+        assert f"batch={per_gpu}" in txt, (n, txt)
+        assert ("duplex" in txt) == c["duplex"]
+    c = bench.select_config(3)
+    assert bench.RES == 256 and bench.K_LATENTS == 32 and bench.DUPLEX and "duplex" in bench.METRIC
+    bench.select_config(2)
+    assert "256^2" in bench.METRIC and "K=16" in bench.METRIC and bench.UNIT == "images/s"
+
+
 def test_bench_reference_arm_json_contract():
     """`bench.py --impl reference` (the CPU oracle port timed on the host cores) runs without a GPU and prints ONE JSON line
     carrying the keys of the bench contract."""
