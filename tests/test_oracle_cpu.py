@@ -124,3 +124,38 @@ def test_positional_table_is_separable():
     assert t.shape == (32, 8)
     row, col = ob.sinusoidal_axis(4, 4), ob.sinusoidal_axis(8, 4)
     assert torch.equal(t.reshape(4, 8, 8)[2, 5], torch.cat([row[2], col[5]]))
+
+
+def test_philox_oracle_matches_random123_known_answers():
+    """oracle/philox.py against the published Philox4x32-10 known-answer vectors (Random123 kat_vectors) -- the one part of the
+    oracle a third party pins; the GPU suite then checks the kernels' mask against this oracle bit for bit."""
+    from oracle import philox as ph
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        assert tuple(int(x) for x in ph.philox4x32_10(*ctr, *key)) == want
+    m = ph.dropout_mult(0.25, seed=1234567890123, step=7, salt=5, tokens=4096, KP=16)
+    assert m.shape == (4096, 16) and set(np.unique(m).tolist()) == {0.0, float(np.float32(1.0) / np.float32(0.75))}
+    keep = (m > 0).mean()
+    assert abs(keep - 0.75) < 4 * (0.25 * 0.75 / m.size) ** 0.5 + 1e-3
+    assert not np.array_equal(m, ph.dropout_mult(0.25, seed=1234567890123, step=8, salt=5, tokens=4096, KP=16))     # next step: new mask
+    assert not np.array_equal(m, ph.dropout_mult(0.25, seed=1234567890123, step=7, salt=6, tokens=4096, KP=16))     # another layer
+
+
+def test_attention_dropout_algebra_of_the_oracle():
+    """att_mult: an all-ones mask is the plain layer; an all-zero mask leaves only the un-droppable constants -- the output then does
+    not depend on the latents' values (what the kernels re-add as (1 - sum q) * cb)."""
+    C, D, k, p = 32, 16, 4, 16
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, C, 8, 8, generator=g, dtype=torch.float64)
+    y = torch.randn(2, k, D, generator=g, dtype=torch.float64)
+    w = ob.init_params(C, D, k, p, "mul", False, seed=2, bias_std=0.3)
+    ref, _, _ = ob.transformer_layer(x, y, w, integration="mul")
+    ones = torch.ones(2, 64, k, dtype=torch.float64)
+    out1, _, _ = ob.transformer_layer(x, y, w, integration="mul", att_mult=ones)
+    assert torch.allclose(out1, ref, atol=1e-12)
+    zeros = torch.zeros(2, 64, k, dtype=torch.float64)
+    out0a, _, _ = ob.transformer_layer(x, y, w, integration="mul", att_mult=zeros)
+    out0b, _, _ = ob.transformer_layer(x, y + 3.0, w, integration="mul", att_mult=zeros)
+    assert torch.allclose(out0a, out0b, atol=1e-12) and not torch.allclose(out0a, ref, atol=1e-3)
